@@ -1,0 +1,31 @@
+"""CPU oracle for the ILRMA / AuxIVA iterative demixing hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``ssspy_b200/`` may import this
+package: only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
+``--impl reference`` legs of ``bench.py`` use it, and there only as the checker
+(or as the CPU arm that is timed *beside* the product), never as the product.
+
+What it is: an fp64 NumPy restatement, written from the update equations, of
+the reference path named in SURVEY.md section 8(a):
+
+* ``oracle.linalg``           <- ssspy/linalg/{_solve,inv,eigh}.py
+* ``oracle.spatial``          <- ssspy/bss/_update_spatial_model.py (IP1, IP2, ISS1)
+* ``oracle.projection_back``  <- ssspy/algorithm/projection_back.py
+* ``oracle.ilrma``            <- ssspy/bss/ilrma.py (GaussILRMA, MM/ME, IP1/IP2/ISS1)
+* ``oracle.iva``              <- ssspy/bss/iva.py  (AuxLaplaceIVA / AuxGaussIVA)
+
+Unlike the reference it never materialises the (I,N,N,N,J) broadcast
+temporaries (ssspy/bss/ilrma.py:1500-1505); contractions are einsum/matmul.
+
+Parity pinning: the reference ships no offline golden vectors for this path
+(its ``target.npz`` regression files are network downloads).
+The oracle is therefore pinned against outputs of the reference itself, run in
+the build container by ``tests/golden/make_golden.py`` (script committed, vectors
+committed as ``tests/golden/*.npz``) and by the docstring known-answer values of
+``inv2`` / ``eigh2`` (ssspy/linalg/inv.py:20-37, ssspy/linalg/eigh.py:53-74,131-152).
+``tests/test_oracle_golden.py`` checks every fixture.
+"""
+
+from . import ilrma, iva, linalg, projection_back, spatial  # noqa: F401
+
+EPS = 1e-10

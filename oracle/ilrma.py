@@ -1,0 +1,159 @@
+"""GaussILRMA iteration (oracle; see oracle/__init__.py).
+
+Restated from SURVEY.md Appendix A.1 = ssspy/bss/ilrma.py:900-922 (update_once),
+:1051-1204 (MM basis/activation), :1249-1401 (ME), :1440-1696 (IP1/IP2/ISS1),
+:365-514 (normalisation), :1910-1967 (loss), :538-565 / :1969-1979 (scale).
+``partitioning=False`` only.  State is a plain dict:
+``X[N,I,J]`` c128, ``W[I,N,N]`` c128 or None (ISS), ``Y[N,I,J]``, ``T[N,I,K]``,
+``V[N,K,J]``.
+"""
+import numpy as np
+
+from . import spatial
+from .projection_back import projection_back
+
+
+def separate(X, W):
+    """Y[n,i,j] = sum_m W[i,n,m] X[m,i,j] (ssspy/bss/ilrma.py:292-295)."""
+    return (W @ X.transpose(1, 0, 2)).transpose(1, 0, 2)
+
+
+def init_state(X, T, V, W=None, spatial_algorithm="IP"):
+    """ssspy/bss/ilrma.py:186-199, :897-898."""
+    N, I, J = X.shape
+    if W is None:
+        W = np.tile(np.eye(N, dtype=np.complex128), (I, 1, 1))
+    st = dict(X=X.astype(np.complex128), W=W.astype(np.complex128).copy(),
+              T=T.astype(np.float64).copy(), V=V.astype(np.float64).copy())
+    st["Y"] = separate(st["X"], st["W"])
+    if spatial_algorithm in ("ISS", "ISS1"):
+        st["W"] = None
+    return st
+
+
+def _Y(st):
+    return st["Y"] if st["W"] is None else separate(st["X"], st["W"])
+
+
+def update_basis(st, p=2, floor=spatial.max_flooring, source_algorithm="MM"):
+    """T <- floor(T (sum_j V P/R^a / sum_j V/R)^b), a=(p+2)/p, b=p/(p+2) for MM
+    (ssspy/bss/ilrma.py:1116-1126); ME: a=2, b=1, p==2 (:1311-1323)."""
+    P = np.abs(_Y(st)) ** 2
+    T, V = st["T"], st["V"]
+    R = T @ V
+    a, b = ((p + 2) / p, p / (p + 2)) if source_algorithm == "MM" else (2.0, 1.0)
+    num = np.einsum("nkj,nij->nik", V, P / R ** a)
+    den = np.einsum("nkj,nij->nik", V, 1 / R)
+    st["T"] = floor(((num / den) ** b) * T)
+
+
+def update_activation(st, p=2, floor=spatial.max_flooring, source_algorithm="MM"):
+    """Same with the new T, reduced over bins (ssspy/bss/ilrma.py:1192-1202; ME :1387-1399)."""
+    P = np.abs(_Y(st)) ** 2
+    T, V = st["T"], st["V"]
+    R = T @ V
+    a, b = ((p + 2) / p, p / (p + 2)) if source_algorithm == "MM" else (2.0, 1.0)
+    num = np.einsum("nik,nij->nkj", T, P / R ** a)
+    den = np.einsum("nik,nij->nkj", T, 1 / R)
+    st["V"] = floor(((num / den) ** b) * V)
+
+
+def update_spatial(st, p=2, floor=spatial.max_flooring, spatial_algorithm="IP", pairs=None):
+    """phi = 1/(T V)^(2/p) (no floor), then IP1 / IP2 on W or ISS1 on Y
+    (ssspy/bss/ilrma.py:1494-1507, :1618-1633, :1690-1696)."""
+    phi = 1 / (st["T"] @ st["V"]) ** (2 / p)
+    if spatial_algorithm in ("IP", "IP1"):
+        st["W"] = spatial.update_by_ip1(st["W"], spatial.weighted_covariance(st["X"], phi), floor)
+    elif spatial_algorithm == "IP2":
+        st["W"] = spatial.update_by_ip2(st["W"], spatial.weighted_covariance(st["X"], phi), floor, pairs)
+    elif spatial_algorithm in ("ISS", "ISS1"):
+        st["Y"] = spatial.update_by_iss1(st["Y"], phi, floor)
+    else:
+        raise NotImplementedError(spatial_algorithm)
+
+
+def normalize(st, p=2, floor=spatial.max_flooring, normalization=True, reference_id=0):
+    """Power: psi_n = floor(sqrt(mean_ij |y|^2)); T /= psi^p; W[:,n,:] /= psi (or Y)
+    (ssspy/bss/ilrma.py:412-444).  Projection back: s = (W^-1)[ref,:]; W[i,n,:] *= s;
+    T[n,i,:] *= |s|^p (:486-514)."""
+    if normalization is True or normalization == "power":
+        Y = _Y(st)
+        psi = floor(np.sqrt(np.mean(np.abs(Y) ** 2, axis=(-2, -1))))
+        st["T"] = st["T"] / psi[:, None, None] ** p
+        if st["W"] is None:
+            st["Y"] = Y / psi[:, None, None]
+        else:
+            st["W"] = st["W"] / psi[None, :, None]
+    elif normalization == "projection_back":
+        ref = 0 if reference_id is None else reference_id
+        if st["W"] is None:
+            Y = st["Y"].transpose(1, 0, 2)
+            X = st["X"].transpose(1, 0, 2)
+            YH = np.conj(Y.transpose(0, 2, 1))
+            scale = ((X @ YH) @ np.linalg.inv(Y @ YH))[..., ref, :]
+            st["Y"] = (Y * scale[..., None]).swapaxes(-3, -2)
+        else:
+            scale = np.linalg.inv(st["W"])[:, ref, :]
+            st["W"] = st["W"] * scale[:, :, None]
+        st["T"] = st["T"] * (np.abs(scale.T) ** p)[:, :, None]
+    else:
+        raise NotImplementedError("Normalization {} is not implemented.".format(normalization))
+
+
+def update_once(st, p=2, floor=spatial.max_flooring, spatial_algorithm="IP", source_algorithm="MM",
+                normalization=True, pairs=None, reference_id=0):
+    """ssspy/bss/ilrma.py:900-922."""
+    update_basis(st, p, floor, source_algorithm)
+    update_activation(st, p, floor, source_algorithm)
+    update_spatial(st, p, floor, spatial_algorithm, pairs)
+    if normalization:
+        normalize(st, p, floor, normalization, reference_id)
+
+
+def compute_loss(st, p=2):
+    """sum_i( sum_n mean_j(P/R^(2/p) + (2/p) log TV) - 2 log|det W_i| )
+    (ssspy/bss/ilrma.py:1936-1967); W-free form recovers W = Y X^H (X X^H)^-1 (:1939-1944)."""
+    if st["W"] is None:
+        Y = st["Y"]
+        Xi, Yi = st["X"].transpose(1, 0, 2), Y.transpose(1, 0, 2)
+        XH = np.conj(Xi.transpose(0, 2, 1))
+        W = Yi @ XH @ np.linalg.inv(Xi @ XH)
+    else:
+        W = st["W"]
+        Y = separate(st["X"], W)
+    TV = st["T"] @ st["V"]
+    loss = np.abs(Y) ** 2 / TV ** (2 / p) + (2 / p) * np.log(TV)
+    _, logdet = np.linalg.slogdet(W)
+    return float((np.sum(loss.mean(axis=-1), axis=0) - 2 * logdet).sum())
+
+
+def restore_scale(st, reference_id=0):
+    """ssspy/bss/ilrma.py:557-565 (W-form) / :1971-1977 (Y-form)."""
+    if st["W"] is None:
+        st["Y"] = projection_back(st["Y"], reference=st["X"], reference_id=reference_id)
+    else:
+        st["W"] = projection_back(st["W"], reference_id=reference_id)
+        st["Y"] = separate(st["X"], st["W"])
+
+
+def run(X, T, V, n_iter, W=None, p=2, floor=spatial.max_flooring, spatial_algorithm="IP",
+        source_algorithm="MM", normalization=True, pairs=None, reference_id=0,
+        scale_restoration=True, record_loss=True, snapshots=False):
+    """GaussILRMA.__call__ (ssspy/bss/ilrma.py:820-855 + ssspy/bss/base.py:48-77)."""
+    st = init_state(X, T, V, W, spatial_algorithm)
+    loss, snaps = [], []
+    if record_loss:
+        loss.append(compute_loss(st, p))
+    for _ in range(n_iter):
+        update_once(st, p, floor, spatial_algorithm, source_algorithm, normalization, pairs, reference_id)
+        if record_loss:
+            loss.append(compute_loss(st, p))
+        if snapshots:
+            snaps.append({k: (None if v is None else v.copy()) for k, v in st.items() if k != "X"})
+    if scale_restoration:
+        restore_scale(st, reference_id)
+    elif st["W"] is not None:
+        st["Y"] = separate(st["X"], st["W"])
+    st["loss"] = loss
+    st["snapshots"] = snaps
+    return st

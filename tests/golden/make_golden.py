@@ -1,0 +1,214 @@
+"""Generate golden vectors for the hot path by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):
+    python tests/golden/make_golden.py
+Writes tests/golden/*.npz.  The GPU box has no /root/reference; tests read only
+the committed .npz files.  Inputs are stored in the fixtures (complex128) so the
+consumer never needs the reference.
+"""
+import functools
+import os
+import sys
+
+import numpy as np
+
+REF = os.environ.get("SSSPY_REF", "/root/reference")
+sys.path.insert(0, REF)
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+
+from ssspy.algorithm import projection_back  # noqa: E402
+from ssspy.bss._update_spatial_model import (  # noqa: E402
+    update_by_ip1, update_by_ip2, update_by_ip2_one_pair, update_by_iss1)
+from ssspy.bss.ilrma import GaussILRMA  # noqa: E402
+from ssspy.bss.iva import AuxGaussIVA, AuxLaplaceIVA  # noqa: E402
+from ssspy.linalg import eigh, eigh2, inv2  # noqa: E402
+from ssspy.linalg._solve import solve  # noqa: E402
+from ssspy.special.flooring import add_flooring, max_flooring  # noqa: E402
+from ssspy.utils.select_pair import combination_pair_selector, sequential_pair_selector  # noqa: E402
+
+from ssspy_b200.utils.synth import make_mixture, make_nmf_init  # noqa: E402
+
+FLOOR = {"max": functools.partial(max_flooring, eps=1e-10),
+         "add": functools.partial(add_flooring, eps=1e-10), "none": None}
+
+
+def rand_w(rng, I, N):
+    """Non-identity, well-conditioned initial demixing filters."""
+    return np.eye(N)[None] + 0.3 * (rng.standard_normal((I, N, N)) + 1j * rng.standard_normal((I, N, N)))
+
+
+def ilrma_case(name, N, I, J, K, n_iter, spatial="IP", source="MM", domain=2, normalization=True,
+               flooring="max", reference_id=0, scale_restoration=True, pairs=None, w_init=False, seed=0):
+    X = make_mixture(N, I, J, seed=seed, mode="mix")
+    T, V = make_nmf_init(N, I, J, K, seed=42 + seed)
+    kwargs = dict(basis=T, activation=V)
+    rng = np.random.default_rng(7 + seed)
+    W0 = rand_w(rng, I, N) if w_init else None
+    if W0 is not None:
+        kwargs["demix_filter"] = W0
+    snaps = []
+
+    def cb(m):
+        snaps.append((None if m.demix_filter is None else m.demix_filter.copy(), m.output.copy(),
+                      m.basis.copy(), m.activation.copy()))
+    sel = None
+    if pairs == "combination":
+        sel = combination_pair_selector
+    elif pairs == "sequential_sorted":
+        sel = functools.partial(sequential_pair_selector, sort=True)
+    m = GaussILRMA(n_basis=K, spatial_algorithm=spatial, source_algorithm=source, domain=domain,
+                   flooring_fn=FLOOR[flooring], pair_selector=sel, callbacks=cb,
+                   normalization=normalization, scale_restoration=scale_restoration,
+                   record_loss=True, reference_id=reference_id, rng=np.random.default_rng(0))
+    Y = m(X, n_iter=n_iter, **kwargs)
+    pair_list = np.array(list((sel or sequential_pair_selector)(N)), dtype=np.int32)
+    out = dict(kind="ilrma", X=X, T0=T, V0=V, Y=Y, T=m.basis, V=m.activation, loss=np.array(m.loss),
+               Y_last_iter=snaps[-1][1], T_first_iter=snaps[1][2], V_first_iter=snaps[1][3],
+               n_iter=n_iter, spatial=spatial, source=source, domain=float(domain),
+               normalization=str(normalization), flooring=flooring,
+               reference_id=-1 if reference_id is None else reference_id,
+               scale_restoration=scale_restoration, pairs=pair_list)
+    if W0 is not None:
+        out["W0"] = W0
+    if m.demix_filter is not None:
+        out["W"] = m.demix_filter
+        out["W_first_iter"] = snaps[1][0]
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "loss", m.loss[0], "->", m.loss[-1])
+
+
+def iva_case(name, N, I, J, n_iter, model="laplace", spatial="IP", flooring="max", reference_id=0,
+             scale_restoration=True, pairs=None, w_init=False, seed=0):
+    X = make_mixture(N, I, J, seed=100 + seed, mode="mix")
+    rng = np.random.default_rng(9 + seed)
+    kwargs = {}
+    W0 = rand_w(rng, I, N) if w_init else None
+    if W0 is not None:
+        kwargs["demix_filter"] = W0
+    sel = combination_pair_selector if pairs == "combination" else None
+    cls = AuxLaplaceIVA if model == "laplace" else AuxGaussIVA
+    m = cls(spatial_algorithm=spatial, flooring_fn=FLOOR[flooring], pair_selector=sel,
+            scale_restoration=scale_restoration, record_loss=True, reference_id=reference_id)
+    Y = m(X, n_iter=n_iter, **kwargs)
+    pair_list = np.array(list((sel or sequential_pair_selector)(N)), dtype=np.int32)
+    out = dict(kind="iva", X=X, Y=Y, loss=np.array(m.loss), n_iter=n_iter, model=model, spatial=spatial,
+               flooring=flooring, reference_id=reference_id, scale_restoration=scale_restoration,
+               pairs=pair_list)
+    if W0 is not None:
+        out["W0"] = W0
+    if m.demix_filter is not None:
+        out["W"] = m.demix_filter
+    if model == "gauss":
+        out["variance"] = m.variance
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "loss", m.loss[0], "->", m.loss[-1])
+
+
+def kernel_cases():
+    """update_by_* on the reference's own smoke-test shapes (tests/package/bss/
+    test_update_spatial_model.py:45-171: rng=default_rng(42), (I,J)=(31,20), N in {2,3})."""
+    out = {}
+    for N in (2, 3, 4):
+        rng = np.random.default_rng(42)
+        I, J = 31, 20
+        X = rng.standard_normal((N, I, J)) + 1j * rng.standard_normal((N, I, J))
+        phi = 1 / (rng.random((N, I, J)) + 0.1)
+        W = rand_w(rng, I, N)
+        XX = X[:, None] * X[None].conj()
+        U = np.mean(phi.transpose(1, 0, 2)[:, :, None, None, :] * XX.transpose(2, 0, 1, 3)[:, None], axis=-1)
+        out[f"N{N}_X"], out[f"N{N}_phi"], out[f"N{N}_W"], out[f"N{N}_U"] = X, phi, W, U
+        for fl in ("max", "add", "none"):
+            out[f"N{N}_ip1_{fl}"] = update_by_ip1(W, U, flooring_fn=FLOOR[fl], overwrite=False)
+            out[f"N{N}_ip2_{fl}"] = update_by_ip2(W, U, flooring_fn=FLOOR[fl], overwrite=False)
+            Y = (W @ X.transpose(1, 0, 2)).transpose(1, 0, 2)
+            out[f"N{N}_iss1_{fl}"] = update_by_iss1(Y, phi, flooring_fn=FLOOR[fl])
+        # pair selector with negative indices (test_update_spatial_model.py:19-24)
+        def neg_sel(n):
+            for m in range(n):
+                yield m - n, (m + 1) % n - n
+        out[f"N{N}_ip2_negpairs"] = update_by_ip2(W, U, pair_selector=neg_sel, overwrite=False)
+        out[f"N{N}_ip2_comb"] = update_by_ip2(W, U, pair_selector=combination_pair_selector, overwrite=False)
+        out[f"N{N}_ip2pair01"] = update_by_ip2_one_pair(W, U[:, (0, 1)], pair=(0, 1))
+    np.savez_compressed(os.path.join(HERE, "spatial_kernels.npz"), **out)
+    print("spatial_kernels done")
+
+
+def linalg_cases():
+    rng = np.random.default_rng(111)
+    out = {}
+    out["inv2_in"] = np.array([[[0, 1], [2, 3]], [[4, 5], [6, 7]]], dtype=np.float64)
+    out["inv2_out"] = inv2(out["inv2_in"])
+    A = np.array([[1, -2j], [2j, 3]])
+    B = np.array([[2, -3j], [3j, 5]])
+    out["eigh2_A"], out["eigh2_B"] = A, B
+    out["eigh2_lamb_std"], _ = eigh2(A)
+    for t in (1, 2, 3):
+        lam, z = eigh2(A, B, type=t)
+        out[f"eigh2_lamb_t{t}"], out[f"eigh2_z_t{t}"] = lam, z
+    for n in (2, 3, 4, 8):
+        a = rng.standard_normal((16, n, n)) + 1j * rng.standard_normal((16, n, n))
+        b = rng.standard_normal((16, n, n)) + 1j * rng.standard_normal((16, n, n))
+        Ah = a @ a.conj().transpose(0, 2, 1)
+        Bh = b @ b.conj().transpose(0, 2, 1) + n * np.eye(n)
+        rhs = rng.standard_normal((16, n)) + 1j * rng.standard_normal((16, n))
+        out[f"n{n}_A"], out[f"n{n}_B"], out[f"n{n}_a"], out[f"n{n}_rhs"] = Ah, Bh, a, rhs
+        out[f"n{n}_solve"] = solve(a, rhs)
+        out[f"n{n}_inv"] = np.linalg.inv(a)
+        for t in (1, 2, 3):
+            lam, z = eigh(Ah, Bh, type=t)
+            out[f"n{n}_lamb_t{t}"] = lam
+        out[f"n{n}_lamb_std"], _ = eigh(Ah)
+        W = a
+        out[f"n{n}_pb_w_ref0"] = projection_back(W, reference_id=0)
+        out[f"n{n}_pb_w_ref1"] = projection_back(W, reference_id=1)
+        out[f"n{n}_pb_w_refnone"] = projection_back(W, reference_id=None)
+    X = make_mixture(3, 9, 14, seed=5)
+    Y = make_mixture(3, 9, 14, seed=6)
+    out["pb_X"], out["pb_Y"] = X, Y
+    out["pb_y_ref0"] = projection_back(Y, reference=X, reference_id=0)
+    out["pb_y_ref2"] = projection_back(Y, reference=X, reference_id=2)
+    out["pb_y_refnone"] = projection_back(Y, reference=X, reference_id=None)
+    np.savez_compressed(os.path.join(HERE, "linalg.npz"), **out)
+    print("linalg done")
+
+
+def main():
+    linalg_cases()
+    kernel_cases()
+    # GaussILRMA: spatial x source x domain x normalisation x flooring grid (regression-test pattern,
+    # tests/regression/bss/test_ilrma.py:48-62: inject basis/activation, fixed n_iter, compare).
+    ilrma_case("ilrma_ip1_mm_n2", 2, 33, 40, 4, 10)
+    ilrma_case("ilrma_ip1_mm_n3_winit", 3, 17, 23, 4, 5, w_init=True, seed=1)
+    ilrma_case("ilrma_ip1_mm_n4", 4, 20, 36, 5, 8, seed=2)
+    ilrma_case("ilrma_ip1_mm_n8", 8, 9, 64, 3, 4, seed=3)
+    ilrma_case("ilrma_ip1_mm_p1", 3, 17, 23, 4, 5, domain=1, seed=4)
+    ilrma_case("ilrma_ip1_me", 3, 17, 23, 4, 5, source="ME", seed=5)
+    ilrma_case("ilrma_ip1_nonorm", 2, 17, 23, 4, 5, normalization=False, seed=6)
+    ilrma_case("ilrma_ip1_pbnorm", 3, 17, 23, 4, 5, normalization="projection_back", reference_id=1, seed=7)
+    ilrma_case("ilrma_ip1_addfloor", 2, 17, 23, 4, 5, flooring="add", seed=8)
+    ilrma_case("ilrma_ip1_nofloor_noscale", 2, 17, 23, 4, 5, flooring="none", scale_restoration=False, seed=9)
+    ilrma_case("ilrma_ip2_mm_n2", 2, 33, 40, 4, 10, spatial="IP2", seed=10)
+    ilrma_case("ilrma_ip2_mm_n3", 3, 17, 23, 4, 5, spatial="IP2", w_init=True, seed=11)
+    ilrma_case("ilrma_ip2_mm_n4_comb", 4, 20, 36, 5, 6, spatial="IP2", pairs="combination", seed=12)
+    ilrma_case("ilrma_ip2_p1", 3, 17, 23, 4, 5, spatial="IP2", domain=1, seed=13)
+    ilrma_case("ilrma_ip2_n8", 8, 9, 64, 3, 3, spatial="IP2", seed=14)
+    ilrma_case("ilrma_iss1_mm_n2", 2, 33, 40, 4, 10, spatial="ISS", seed=15)
+    ilrma_case("ilrma_iss1_mm_n3", 3, 17, 23, 4, 5, spatial="ISS", reference_id=2, seed=16)
+    ilrma_case("ilrma_iss1_mm_n4_p1", 4, 20, 36, 5, 6, spatial="ISS", domain=1, seed=17)
+    ilrma_case("ilrma_iss1_pbnorm", 3, 17, 23, 4, 5, spatial="ISS", normalization="projection_back", seed=18)
+    ilrma_case("ilrma_iss1_me_nonorm", 3, 17, 23, 4, 5, spatial="ISS", source="ME", normalization=False, seed=19)
+    # AuxIVA
+    for model in ("laplace", "gauss"):
+        iva_case(f"iva_{model}_ip1_n2", 2, 33, 40, 10, model=model)
+        iva_case(f"iva_{model}_ip1_n3_winit", 3, 17, 23, 5, model=model, w_init=True, seed=1)
+        iva_case(f"iva_{model}_ip2_n2", 2, 33, 40, 8, model=model, spatial="IP2", seed=2)
+        iva_case(f"iva_{model}_ip2_n4_comb", 4, 20, 36, 5, model=model, spatial="IP2", pairs="combination", seed=3)
+        iva_case(f"iva_{model}_iss1_n2", 2, 33, 40, 10, model=model, spatial="ISS", seed=4)
+        iva_case(f"iva_{model}_iss1_n4", 4, 20, 36, 6, model=model, spatial="ISS", reference_id=1, seed=5)
+    iva_case("iva_laplace_ip1_addfloor_noscale", 3, 17, 23, 5, flooring="add", scale_restoration=False, seed=6)
+    iva_case("iva_laplace_ip1_n8", 8, 9, 64, 4, seed=7)
+
+
+if __name__ == "__main__":
+    main()

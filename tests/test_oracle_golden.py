@@ -1,0 +1,116 @@
+"""Pin the oracle (oracle/) against golden vectors produced by the unmodified reference
+(tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+
+from oracle import ilrma as oilrma
+from oracle import iva as oiva
+from oracle import linalg as olinalg
+from oracle import spatial as ospatial
+from oracle.projection_back import projection_back
+
+from helpers import FLOORS, golden_cases, load, norm_arg, phase_align_rows, relerr
+
+TOL = 1e-9
+
+
+@pytest.mark.parametrize("name", golden_cases("ilrma_"))
+def test_ilrma_oracle_matches_reference(name):
+    g = load(name)
+    ref_id = None if int(g["reference_id"]) < 0 else int(g["reference_id"])
+    st = oilrma.run(g["X"], g["T0"], g["V0"], int(g["n_iter"]), W=g.get("W0"), p=float(g["domain"]),
+                    floor=FLOORS[str(g["flooring"])], spatial_algorithm=str(g["spatial"]),
+                    source_algorithm=str(g["source"]), normalization=norm_arg(g["normalization"]),
+                    pairs=[tuple(p) for p in g["pairs"]], reference_id=ref_id,
+                    scale_restoration=bool(g["scale_restoration"]), snapshots=True)
+    assert relerr(st["Y"], g["Y"]) < TOL
+    assert relerr(st["T"], g["T"]) < TOL
+    assert relerr(st["V"], g["V"]) < TOL
+    assert relerr(st["snapshots"][0]["T"], g["T_first_iter"]) < TOL
+    assert relerr(st["snapshots"][0]["V"], g["V_first_iter"]) < TOL
+    np.testing.assert_allclose(st["loss"], g["loss"], rtol=1e-10, atol=1e-9)
+    if "W" in g:
+        assert relerr(st["W"], g["W"]) < TOL
+        W1 = st["snapshots"][0]["W"]
+        if str(g["spatial"]) == "IP2":  # eigenvector phase is LAPACK's choice
+            W1 = phase_align_rows(W1, g["W_first_iter"])
+        assert relerr(W1, g["W_first_iter"]) < TOL
+
+
+@pytest.mark.parametrize("name", golden_cases("iva_"))
+def test_iva_oracle_matches_reference(name):
+    g = load(name)
+    st = oiva.run(g["X"], int(g["n_iter"]), W=g.get("W0"), floor=FLOORS[str(g["flooring"])],
+                  spatial_algorithm=str(g["spatial"]), model=str(g["model"]),
+                  pairs=[tuple(p) for p in g["pairs"]], reference_id=int(g["reference_id"]),
+                  scale_restoration=bool(g["scale_restoration"]))
+    assert relerr(st["Y"], g["Y"]) < TOL
+    np.testing.assert_allclose(st["loss"], g["loss"], rtol=1e-10, atol=1e-9)
+    if "W" in g:
+        assert relerr(st["W"], g["W"]) < TOL
+    if "variance" in g:
+        assert relerr(st["variance"], g["variance"]) < TOL
+
+
+def _ip2_err(W, Wref):
+    """IP2 rows are defined up to LAPACK's eigenvector phase."""
+    return relerr(phase_align_rows(W, Wref), Wref)
+
+
+@pytest.mark.parametrize("N", [2, 3, 4])
+def test_spatial_kernels_oracle(N):
+    g = load("spatial_kernels")
+    X, phi, W, U = (g[f"N{N}_{k}"] for k in ("X", "phi", "W", "U"))
+    assert relerr(ospatial.weighted_covariance(X, phi), U) < 1e-12
+    for fl in ("max", "add", "none"):
+        assert relerr(ospatial.update_by_ip1(W, U, FLOORS[fl]), g[f"N{N}_ip1_{fl}"]) < TOL
+        assert _ip2_err(ospatial.update_by_ip2(W, U, FLOORS[fl]), g[f"N{N}_ip2_{fl}"]) < TOL
+        Y = oilrma.separate(X, W)
+        assert relerr(ospatial.update_by_iss1(Y, phi, FLOORS[fl]), g[f"N{N}_iss1_{fl}"]) < TOL
+    neg = [(m - N, (m + 1) % N - N) for m in range(N)]
+    assert _ip2_err(ospatial.update_by_ip2(W, U, pairs=neg), g[f"N{N}_ip2_negpairs"]) < TOL
+    import itertools
+    comb = list(itertools.combinations(range(N), 2))
+    assert _ip2_err(ospatial.update_by_ip2(W, U, pairs=comb), g[f"N{N}_ip2_comb"]) < TOL
+    assert _ip2_err(ospatial.update_by_ip2_one_pair(W, U[:, (0, 1)], (0, 1)), g[f"N{N}_ip2pair01"]) < TOL
+
+
+def test_linalg_known_answers():
+    """Docstring known answers: ssspy/linalg/inv.py:20-37, ssspy/linalg/eigh.py:53-74,131-152."""
+    g = load("linalg")
+    np.testing.assert_allclose(olinalg.inv2(g["inv2_in"]),
+                               [[[-1.5, 0.5], [1.0, 0.0]], [[-3.5, 2.5], [3.0, -2.0]]], atol=1e-12)
+    np.testing.assert_allclose(olinalg.inv2(g["inv2_in"]), g["inv2_out"], atol=1e-12)
+    A, B = g["eigh2_A"], g["eigh2_B"]
+    lam, z = olinalg.eigh2(A)
+    np.testing.assert_allclose(lam, [-0.23606798, 4.23606798], atol=1e-8)
+    lam, z = olinalg.eigh2(A, B)
+    np.testing.assert_allclose(lam, [-1.61803399, 0.61803399], atol=1e-8)
+    np.testing.assert_allclose(A @ z, lam * (B @ z), atol=1e-10)
+    for t in (1, 2, 3):
+        lam, z = olinalg.eigh2(A, B, type=t)
+        np.testing.assert_allclose(lam, g[f"eigh2_lamb_t{t}"], atol=1e-10)
+        np.testing.assert_allclose(z, g[f"eigh2_z_t{t}"], atol=1e-10)
+
+
+@pytest.mark.parametrize("n", [2, 3, 4, 8])
+def test_linalg_nxn(n):
+    g = load("linalg")
+    a, rhs, Ah, Bh = g[f"n{n}_a"], g[f"n{n}_rhs"], g[f"n{n}_A"], g[f"n{n}_B"]
+    assert relerr(olinalg.solve(a, rhs), g[f"n{n}_solve"]) < 1e-12
+    for t in (1, 2, 3):
+        lam, z = olinalg.eigh(Ah, Bh, type=t)
+        np.testing.assert_allclose(lam, g[f"n{n}_lamb_t{t}"], rtol=1e-10)
+        lhs = {1: Ah @ z, 2: Ah @ Bh @ z, 3: Bh @ Ah @ z}[t]
+        rhs_ = {1: (Bh @ z) * lam[:, None, :], 2: z * lam[:, None, :], 3: z * lam[:, None, :]}[t]
+        assert relerr(lhs, rhs_) < 1e-9
+    for ref, key in ((0, "ref0"), (1, "ref1"), (None, "refnone")):
+        assert relerr(projection_back(a, reference_id=ref), g[f"n{n}_pb_w_{key}"]) < 1e-12
+
+
+def test_projection_back_y_form():
+    g = load("linalg")
+    for ref, key in ((0, "ref0"), (2, "ref2"), (None, "refnone")):
+        out = projection_back(g["pb_Y"], reference=g["pb_X"], reference_id=ref)
+        assert out.shape == g[f"pb_y_{key}"].shape
+        assert relerr(out, g[f"pb_y_{key}"]) < 1e-12
