@@ -1,0 +1,176 @@
+/*
+ * ssb.h -- C-ABI of the B200-native iterative demixing path (ILRMA / AuxIVA).
+ *
+ * The reference (tky823/ssspy) is pure Python/NumPy and has no FFI layer; the boundary this
+ * library sits behind is its separator-class API.  Every entry point below
+ * names the reference function it replaces (path:line under the reference tree).  The Python
+ * host mirror (ssspy_b200/) binds these with ctypes; INTEGRATION.md shows the stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C, no exceptions; every function returns 0 on success, non-zero on error;
+ *     ssb_last_error() returns the message of the last failure on the calling thread.
+ *   - all array arguments are DEVICE pointers owned by the caller unless marked "host";
+ *     complex64 = interleaved (re, im) float pairs, complex128 = interleaved doubles.
+ *   - layouts are the reference's with a leading batch axis of independent mixtures:
+ *       X[B,N,I,J] c64   mixture STFT            (ssspy/bss/ilrma.py:840, input)
+ *       W[B,I,N,N] c64   demixing filters, rows are w_n^H   (ilrma.py:186-188)
+ *       Y[B,N,I,J] c64   separated STFT          (ilrma.py:292-295)
+ *       T[B,N,I,K] f32   NMF basis, V[B,N,K,J] f32 NMF activation  (ilrma.py:256-268)
+ *   - every launch is asynchronous on the caller's stream (a cudaStream_t passed as void*);
+ *     no hidden host synchronisation.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef SSB_H_
+#define SSB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSB_VERSION 100
+
+/* model: which separator class the plan mirrors */
+enum {
+  SSB_MODEL_ILRMA_GAUSS = 0, /* ssspy/bss/ilrma.py:582 GaussILRMA      */
+  SSB_MODEL_IVA_LAPLACE = 1, /* ssspy/bss/iva.py:2976 AuxLaplaceIVA    */
+  SSB_MODEL_IVA_GAUSS = 2    /* ssspy/bss/iva.py:3131 AuxGaussIVA      */
+};
+/* spatial_algorithm (ssspy/bss/ilrma.py:27, ssspy/bss/iva.py:44) */
+enum { SSB_SPATIAL_IP1 = 0, SSB_SPATIAL_IP2 = 1, SSB_SPATIAL_ISS1 = 2 };
+/* source_algorithm (ssspy/bss/ilrma.py:28) */
+enum { SSB_SOURCE_MM = 0, SSB_SOURCE_ME = 1 };
+/* flooring_fn (ssspy/special/flooring.py:6-18): max(x,eps) | x+eps | identity */
+enum { SSB_FLOOR_MAX = 0, SSB_FLOOR_ADD = 1, SSB_FLOOR_NONE = 2 };
+/* normalization (ssspy/bss/ilrma.py:333-363) */
+enum { SSB_NORM_NONE = 0, SSB_NORM_POWER = 1, SSB_NORM_PROJECTION_BACK = 2 };
+
+#define SSB_MAX_SOURCES 8
+#define SSB_MAX_BASIS 64
+#define SSB_MAX_PAIRS 64
+
+typedef struct ssb_config {
+  int32_t model;
+  int32_t spatial;
+  int32_t source;
+  int32_t n_batch;   /* B: independent mixtures (extension; the reference has B = 1) */
+  int32_t n_sources; /* N = n_channels, 2..SSB_MAX_SOURCES (determined case, ilrma.py:180-181) */
+  int32_t n_bins;    /* I */
+  int32_t n_frames;  /* J */
+  int32_t n_basis;   /* K (ILRMA only), 1..SSB_MAX_BASIS */
+  float domain;      /* p in (0, 2] (ilrma.py:786) */
+  int32_t flooring;
+  float eps;         /* 1e-10 in the reference (ssspy/special/flooring.py:3) */
+  int32_t normalization;
+  int32_t reference_id; /* projection-back reference channel */
+  int32_t n_pairs;      /* IP2: number of (m, n) pairs per iteration */
+  int32_t pairs[2 * SSB_MAX_PAIRS]; /* host copy of pair_selector(N), already wrapped into [0, N)
+                                       (ssspy/utils/select_pair.py:35-44; negative indices wrap as
+                                       NumPy indexing does, tests/package/bss/test_update_spatial_model.py:19-24) */
+  int32_t fast_path; /* 1: use the fused sm_100a kernels where the configuration allows (default),
+                        0: always the modular kernels */
+} ssb_config;
+
+typedef struct ssb_plan ssb_plan;
+
+const char* ssb_last_error(void);
+int ssb_version(void);
+/* number of visible CUDA devices (0 => every compute call fails loudly) */
+int ssb_device_count(int* count);
+
+/* launch accounting: total kernel launches issued by this library in the process */
+int ssb_launch_count(unsigned long long* count);
+/* per-kernel device timing: events are recorded after every launch between begin and end;
+ * ssb_profile_end synchronises and writes "kernel_name launches total_ms" lines into buf */
+int ssb_profile_begin(void* stream);
+int ssb_profile_end(char* buf, size_t buf_bytes);
+
+/* ---- plan: one bound problem instance = the state of one separator object ------------------ */
+int ssb_plan_create(const ssb_config* cfg, ssb_plan** plan);
+int ssb_plan_destroy(ssb_plan* plan);
+/* bytes of scratch the plan needs (caller allocates, e.g. a torch uint8 tensor) */
+int ssb_plan_workspace_bytes(const ssb_plan* plan, size_t* bytes);
+/* Bind caller-owned device buffers.  W may be NULL in ISS modes (state lives in Y,
+ * ssspy/bss/ilrma.py:897-898); T, V NULL for IVA; variance[B,N,J] f32 only for IVA_GAUSS
+ * (ssspy/bss/iva.py:3317).  workspace must hold ssb_plan_workspace_bytes() bytes. */
+int ssb_plan_bind(ssb_plan* plan, const void* X, void* W, void* Y, void* T, void* V, void* variance,
+                  void* workspace, size_t workspace_bytes);
+/* change the flooring policy of later calls (update_once(flooring_fn=...), ilrma.py:900-922) */
+int ssb_plan_set_flooring(ssb_plan* plan, int flooring, float eps);
+/* one-time work after bind or after X changed (per-bin unweighted covariance used by the power
+ * normalisation) */
+int ssb_plan_prepare(ssb_plan* plan, void* stream);
+
+/* GaussILRMA.update_once (ilrma.py:900-922) / AuxIVA.update_once (iva.py:1699-1734,3319-3337) */
+int ssb_update_once(ssb_plan* plan, void* stream);
+/* n_iter x update_once; if loss != NULL (double[(n_iter)*B], device) the loss after every
+ * iteration is written there (ssspy/bss/base.py:68-73) */
+int ssb_run(ssb_plan* plan, int n_iter, double* loss, void* stream);
+/* update_source_model: ilrma.py:924-978 (MM/ME basis+activation); iva.py:3465-3473 (variance) */
+int ssb_update_source_model(ssb_plan* plan, void* stream);
+/* update_spatial_model: ilrma.py:1403-1438 (IP1/IP2/ISS1); AuxIVA update_once_{ip1,ip2,iss1}
+ * iva.py:1736-1966 */
+int ssb_update_spatial_model(ssb_plan* plan, void* stream);
+/* normalize: ilrma.py:333-514 */
+int ssb_normalize(ssb_plan* plan, void* stream);
+/* compute_loss: ilrma.py:1910-1967, iva.py:200-222,2177-2192; loss is double[B] (device) */
+int ssb_compute_loss(ssb_plan* plan, double* loss, void* stream);
+/* restore_scale / apply_projection_back: ilrma.py:538-565,1969-1979; iva.py:238-267,2194-2204.
+ * W-modes: W <- projection_back(W), Y <- W X.  ISS modes: Y <- projection_back(Y, X). */
+int ssb_restore_scale(ssb_plan* plan, void* stream);
+/* Y <- W X with the plan's current W (ilrma.py:272-295); no-op in ISS modes */
+int ssb_plan_separate(ssb_plan* plan, void* stream);
+
+/* ---- standalone batched operators (no plan) -------------------------------------------------- */
+/* separate: Y[b,n,i,j] = sum_m W[b,i,n,m] X[b,m,i,j]   (ilrma.py:272-295, iva.py:171-194) */
+int ssb_separate(const void* X, const void* W, void* Y, int B, int N, int I, int J, void* stream);
+/* weighted covariance U[b,i,s,:,:] = (1/J) sum_j phi[...] x x^H for the n_src sources listed in
+ * src (host int32[n_src], NULL = 0..n_src-1).  phi element (b, src[s], i, j) is read at
+ * phi[b*phi_sb + src[s]*phi_sn + i*phi_si + j] (phi_si = 0 for IVA weights [N,J])
+ * (ilrma.py:1500-1505, iva.py:1785-1791).  U is c64 [B,I,n_src,N,N]. */
+int ssb_weighted_covariance(const void* X, const float* phi, long long phi_sb, long long phi_sn,
+                            long long phi_si, const int32_t* src, int n_src, void* U, int B, int N,
+                            int I, int J, void* stream);
+/* update_by_ip1 (ssspy/bss/_update_spatial_model.py:17-78): W[n_mat,N,N] c64 in place,
+ * U[n_mat,N,N,N] c64 */
+int ssb_update_by_ip1(void* W, const void* U, int n_mat, int N, int flooring, float eps, void* stream);
+/* update_by_ip2 (_update_spatial_model.py:81-143,317-395): pairs = host int32[2*n_pairs] in [0,N);
+ * U[n_mat,N,N,N] c64 holds all sources */
+int ssb_update_by_ip2(void* W, const void* U, int n_mat, int N, const int32_t* pairs, int n_pairs,
+                      int flooring, float eps, void* stream);
+/* update_by_ip2_one_pair (_update_spatial_model.py:317-395): U_pair[n_mat,2,N,N] */
+int ssb_update_by_ip2_one_pair(void* W, const void* U_pair, int n_mat, int N, int m, int n, int flooring,
+                               float eps, void* stream);
+/* update_by_iss1 (_update_spatial_model.py:146-194): Y[B,N,I,J] c64 in place; phi addressed as in
+ * ssb_weighted_covariance */
+int ssb_update_by_iss1(void* Y, const float* phi, long long phi_sb, long long phi_sn, long long phi_si,
+                       int B, int N, int I, int J, int flooring, float eps, void* stream);
+/* projection_back, filter form (ssspy/algorithm/projection_back.py:87-99):
+ * Wout[m,n,:] = W[m,n,:] * (W[m]^-1)[ref, n]; Wout may alias W. */
+int ssb_projection_back_w(const void* W, void* Wout, int n_mat, int N, int reference_id, void* stream);
+/* projection_back, spectrogram form (projection_back.py:100-121): scale[b,i,c,n] =
+ * (X Y^H (Y Y^H)^-1)[c,n]; Yout[b,n,i,:] = Y[b,n,i,:] * scale[b,i,ref,n]; Yout may alias Y.
+ * scale_out (c64 [B,I,N,N], REQUIRED: it is also the kernel's scratch) receives the full scale matrix
+ * (the reference_id=None case reads it); Yout may be NULL to compute only the scale. */
+int ssb_projection_back_y(const void* Y, const void* X, void* Yout, void* scale_out, int B, int N, int I,
+                          int J, int reference_id, void* stream);
+
+/* ---- ssspy.linalg helpers, batched over n_mat small matrices, complex128 in/out -------------- */
+/* inv2 (ssspy/linalg/inv.py:4-54) generalised to N x N (np.linalg.inv call sites:
+ * projection_back.py:89,110; ilrma.py:495,504,1944) */
+int ssb_inv(const void* A, void* Ainv, int n_mat, int N, void* stream);
+/* solve (ssspy/linalg/_solve.py:9-21): A[n_mat,N,N], B[n_mat,N,R] -> X[n_mat,N,R] */
+int ssb_solve(const void* A, const void* B, void* X, int n_mat, int N, int R, void* stream);
+/* eigh / eigh2 (ssspy/linalg/eigh.py:8-207): Hermitian A (and positive definite B unless NULL),
+ * type 1: A z = l B z, 2: A B z = l z, 3: B A z = l z; ascending eigenvalues lamb[n_mat,N] f64,
+ * eigenvectors in the columns of Z[n_mat,N,N] c128 */
+int ssb_eigh(const void* A, const void* B, int type, double* lamb, void* Z, int n_mat, int N,
+             void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSB_H_ */

@@ -1,0 +1,327 @@
+"""GaussILRMA on the device (host mirror of ssspy/bss/ilrma.py: ILRMABase :32-579, GaussILRMA
+:582-1989).  Same constructor, ``__call__``, ``update_once`` / ``update_source_model`` /
+``update_spatial_model`` / ``normalize`` / ``compute_loss`` / ``restore_scale`` /
+``apply_projection_back`` and attribute names; all arithmetic runs in libssb.so's CUDA kernels.
+
+Covered: spatial_algorithm IP / IP1 / IP2 / ISS / ISS1, source_algorithm MM /
+ME, any ``domain`` in (0, 2], ``partitioning=False``, normalization True / "power" /
+"projection_back" / False, projection-back scale restoration.  ISS2, IPA, partitioning and the
+minimal-distortion principle are "next" rows and raise NotImplementedError (no CPU fallback).
+"""
+import ctypes
+import functools
+
+import numpy as np
+import torch
+
+from .. import _device, _lib
+from ..special.flooring import EPS, identity, max_flooring
+from ..utils.flooring import choose_flooring_fn, flooring_to_enum
+from ..utils.select_pair import sequential_pair_selector, wrap_pairs
+from ._engine import DeviceSeparatorMixin
+from .base import IterativeMethodBase
+
+__all__ = ["GaussILRMA"]
+
+spatial_algorithms = ["IP", "IP1", "IP2", "ISS", "ISS1", "ISS2", "IPA"]
+source_algorithms = ["MM", "ME"]
+PROJECTION_BACK_KEYWORDS = ["projection_back", "projection-back", "PB"]
+MINIMAL_DISTORTION_PRINCIPLE_KEYWORDS = ["minimal_distortion_principle", "minimal-distortion-principle", "MDP"]
+
+_SPATIAL_ENUM = {"IP": _lib.SPATIAL_IP1, "IP1": _lib.SPATIAL_IP1, "IP2": _lib.SPATIAL_IP2,
+                 "ISS": _lib.SPATIAL_ISS1, "ISS1": _lib.SPATIAL_ISS1}
+
+
+def _not_on_device(what):
+    raise NotImplementedError("{} is not implemented on the device yet and there is no CPU fallback.".format(what))
+
+
+class ILRMABase(DeviceSeparatorMixin, IterativeMethodBase):
+    """ssspy/bss/ilrma.py:32-579."""
+
+    def __init__(self, n_basis, partitioning=False, flooring_fn=functools.partial(max_flooring, eps=EPS),
+                 callbacks=None, scale_restoration=True, record_loss=True, reference_id=0, rng=None):
+        IterativeMethodBase.__init__(self, callbacks=callbacks, record_loss=record_loss)
+        self._init_device_state()
+        self.n_basis = n_basis
+        self.partitioning = partitioning
+        self.flooring_fn = identity if flooring_fn is None else flooring_fn
+        self.scale_restoration = scale_restoration
+        if reference_id is None and scale_restoration:
+            raise ValueError("Specify 'reference_id' if scale_restoration=True.")
+        self.reference_id = reference_id
+        self.rng = np.random.default_rng() if rng is None else rng
+
+    def __repr__(self):
+        s = "ILRMA(n_basis={n_basis}, partitioning={partitioning}, scale_restoration={scale_restoration}"
+        s += ", record_loss={record_loss}"
+        if self.scale_restoration:
+            s += ", reference_id={reference_id}"
+        return (s + ")").format(**self.__dict__)
+
+    # ---- state initialisation (ilrma.py:151-270) ---------------------------------------------------
+    def _batchify(self, name, tail_shape):
+        """Bring a user-supplied state entry to its batched device layout ``(B,) + tail_shape``."""
+        t = self._dev(name)
+        B = self._dims()[0]
+        if tuple(t.shape[1:]) != tuple(tail_shape) or t.shape[0] not in (1, B):
+            raise ValueError("{} has shape {} but {} is expected.".format(
+                name, tuple(t.shape[1:] if not self._batched else t.shape), tuple(tail_shape)))
+        if t.shape[0] != B:
+            self._state[name] = t.expand(B, *tail_shape).contiguous()
+            self._plan_key = None
+
+    def _reset(self, flooring_fn="self", **kwargs):
+        assert self.input is not None, "Specify data!"
+        flooring_fn = choose_flooring_fn(flooring_fn, method=self)
+        for key, value in kwargs.items():
+            setattr(self, key, value)
+        B, N, I, J = self._dims()
+        self.n_sources, self.n_channels = N, N  # determined case (ilrma.py:180-181)
+        self.n_bins, self.n_frames = I, J
+        if not (2 <= N <= _lib.SSB_MAX_SOURCES):
+            raise NotImplementedError("n_sources={} is outside the supported range 2..{}.".format(N, _lib.SSB_MAX_SOURCES))
+        if not self._has("demix_filter"):
+            eye = torch.eye(N, dtype=torch.complex64, device=self._dX.device)
+            self._state["demix_filter"] = eye.expand(B, I, N, N).contiguous()
+        elif self._state["demix_filter"] is not None:
+            self._batchify("demix_filter", (I, N, N))
+        W = self._dev("demix_filter")
+        if W is None:
+            self.separate(self.input, demix_filter=None)  # raises like the reference (None @ ndarray)
+        Y = torch.empty_like(self._dX)
+        _lib.call("ssb_separate", self._dX.data_ptr(), W.data_ptr(), Y.data_ptr(), B, N, I, J, _device.stream_ptr())
+        self._state["output"] = Y
+        self._init_nmf(flooring_fn=flooring_fn, rng=self.rng)
+        self._plan_key = None
+
+    def _init_nmf(self, flooring_fn="self", rng=None):
+        """T then V drawn on the host from the caller's Generator in the reference's order
+        (ilrma.py:256-268), one mixture after the other for batched input."""
+        flooring_fn = choose_flooring_fn(flooring_fn, method=self)
+        if rng is None:
+            rng = np.random.default_rng()
+        if self.partitioning:
+            _not_on_device("partitioning=True")
+        B, N, I, J = self._dims()
+        K = self.n_basis
+        if not (1 <= K <= _lib.SSB_MAX_BASIS):
+            raise NotImplementedError("n_basis={} is outside the supported range 1..{}.".format(K, _lib.SSB_MAX_BASIS))
+        need_T, need_V = not self._has("basis"), not self._has("activation")
+        T = np.empty((B, N, I, K)) if need_T else None
+        V = np.empty((B, N, K, J)) if need_V else None
+        for b in range(B):
+            if need_T:
+                T[b] = flooring_fn(rng.random((N, I, K)))
+            if need_V:
+                V[b] = flooring_fn(rng.random((N, K, J)))
+        if need_T:
+            self._state["basis"] = _device.to_device(T, torch.float32)
+        else:
+            self._batchify("basis", (N, I, K))
+        if need_V:
+            self._state["activation"] = _device.to_device(V, torch.float32)
+        else:
+            self._batchify("activation", (N, K, J))
+
+    # ---- C-ABI plan ------------------------------------------------------------------------------
+    def _plan_config(self):
+        B, N, I, J = self._dims()
+        cfg = _lib.SsbConfig()
+        cfg.model = _lib.MODEL_ILRMA_GAUSS
+        cfg.spatial = _SPATIAL_ENUM[self.spatial_algorithm]
+        cfg.source = _lib.SOURCE_MM if self.source_algorithm == "MM" else _lib.SOURCE_ME
+        cfg.n_batch, cfg.n_sources, cfg.n_bins, cfg.n_frames, cfg.n_basis = B, N, I, J, self.n_basis
+        cfg.domain = float(self.domain)
+        cfg.flooring, cfg.eps = flooring_to_enum(self.flooring_fn)
+        norm = self.normalization
+        if not norm:
+            cfg.normalization = _lib.NORM_NONE
+        elif norm is True or norm == "power":
+            cfg.normalization = _lib.NORM_POWER
+        elif norm == "projection_back":
+            cfg.normalization = _lib.NORM_PROJECTION_BACK
+        else:
+            raise NotImplementedError("Normalization {} is not implemented.".format(norm))
+        cfg.reference_id = 0 if self.reference_id is None else int(self.reference_id)
+        pairs = []
+        if cfg.spatial == _lib.SPATIAL_IP2:
+            pairs = wrap_pairs(self.pair_selector(N), N)
+            if len(pairs) > _lib.SSB_MAX_PAIRS:
+                raise NotImplementedError("more than {} pairs per iteration".format(_lib.SSB_MAX_PAIRS))
+        cfg.n_pairs = len(pairs)
+        for q, (m, n) in enumerate(pairs):
+            cfg.pairs[2 * q], cfg.pairs[2 * q + 1] = m, n
+        cfg.fast_path = 1 if getattr(self, "fast_path", True) else 0
+        return cfg
+
+    # ---- normalisation (ilrma.py:333-514) ----------------------------------------------------------
+    def normalize(self, flooring_fn="self"):
+        normalization = self.normalization
+        flooring_fn = choose_flooring_fn(flooring_fn, method=self)
+        assert normalization, "Set normalization."
+        if type(normalization) is bool:
+            normalization = "power"
+        if normalization == "power":
+            self.normalize_by_power(flooring_fn=flooring_fn)
+        elif normalization == "projection_back":
+            self.normalize_by_projection_back()
+        else:
+            raise NotImplementedError("Normalization {} is not implemented.".format(normalization))
+
+    def normalize_by_power(self, flooring_fn="self"):
+        flooring_fn = choose_flooring_fn(flooring_fn, method=self)
+        self._with_normalization("power", flooring_fn)
+
+    def normalize_by_projection_back(self):
+        self._with_normalization("projection_back", self.flooring_fn)
+
+    def _with_normalization(self, kind, flooring_fn):
+        saved = self.normalization
+        self.normalization = kind
+        try:
+            self._set_flooring(flooring_fn)
+            self._plan_call("ssb_normalize")
+        finally:
+            self.normalization = saved
+
+    # ---- loss / scale ----------------------------------------------------------------------------
+    def compute_loss(self):
+        raise NotImplementedError("Implement 'compute_loss' method.")
+
+    def restore_scale(self):
+        scale_restoration = self.scale_restoration
+        assert scale_restoration, "Set self.scale_restoration=True."
+        if type(scale_restoration) is bool:
+            scale_restoration = PROJECTION_BACK_KEYWORDS[0]
+        if scale_restoration in PROJECTION_BACK_KEYWORDS:
+            self.apply_projection_back()
+        elif scale_restoration in MINIMAL_DISTORTION_PRINCIPLE_KEYWORDS:
+            self.apply_minimal_distortion_principle()
+        else:
+            raise ValueError("{} is not supported for scale restoration.".format(scale_restoration))
+
+    def apply_projection_back(self):
+        """W-modes: W <- projection_back(W), Y <- W X (ilrma.py:557-565); ISS modes:
+        Y <- projection_back(Y, X) (ilrma.py:1971-1977)."""
+        assert self.scale_restoration, "Set self.scale_restoration=True."
+        self._plan_call("ssb_restore_scale")
+
+    def apply_minimal_distortion_principle(self):
+        _not_on_device("scale_restoration='minimal_distortion_principle'")
+
+
+class GaussILRMA(ILRMABase):
+    """ssspy/bss/ilrma.py:582-1989 (signature :752-772)."""
+
+    def __init__(self, n_basis, spatial_algorithm="IP", source_algorithm="MM", domain=2, partitioning=False,
+                 flooring_fn=functools.partial(max_flooring, eps=EPS), pair_selector=None, callbacks=None,
+                 normalization=True, scale_restoration=True, record_loss=True, reference_id=0, rng=None, **kwargs):
+        super().__init__(n_basis=n_basis, partitioning=partitioning, flooring_fn=flooring_fn, callbacks=callbacks,
+                         scale_restoration=scale_restoration, record_loss=record_loss, reference_id=reference_id,
+                         rng=rng)
+        assert spatial_algorithm in spatial_algorithms, "Not support {}.".format(spatial_algorithm)
+        assert source_algorithm in source_algorithms, "Not support {}.".format(source_algorithm)
+        assert 0 < domain <= 2, "domain parameter should be chosen from [0, 2]."
+        if source_algorithm == "ME":
+            assert domain == 2, "domain parameter should be 2 when you specify ME algorithm."
+        if spatial_algorithm not in _SPATIAL_ENUM:
+            _not_on_device("spatial_algorithm={!r}".format(spatial_algorithm))
+        if partitioning:
+            _not_on_device("partitioning=True")
+        self.spatial_algorithm = spatial_algorithm
+        self.source_algorithm = source_algorithm
+        self.domain = domain
+        self.normalization = normalization
+        if pair_selector is None:
+            if spatial_algorithm in ["IP2", "ISS2"]:
+                self.pair_selector = sequential_pair_selector
+        else:
+            self.pair_selector = pair_selector
+        invalid_keys = set(kwargs)  # IPA-only keywords are the only valid extras (ilrma.py:802-812)
+        assert invalid_keys == set(), "Invalid keywords {} are given.".format(invalid_keys)
+
+    def __call__(self, input, n_iter=100, initial_call=True, **kwargs):
+        """Separate ``input`` of shape (n_channels, n_bins, n_frames) [or (batch, ...)] (ilrma.py:820-855)."""
+        self.input = input
+        self._reset(flooring_fn=self.flooring_fn, **kwargs)
+        self._iterate(n_iter=n_iter, initial_call=initial_call)
+        if self.scale_restoration:
+            self.restore_scale()
+        elif self._state.get("demix_filter") is not None:
+            self._plan_call("ssb_plan_separate")
+        return self.output
+
+    def _iterate(self, n_iter, initial_call):
+        """base.py:48-77.  Without callbacks or user overrides the whole loop is one C call."""
+        cls = type(self)
+        stock = (self.callbacks is None and cls.update_once is GaussILRMA.update_once
+                 and cls.compute_loss is GaussILRMA.compute_loss and self._stock_update_methods())
+        if not stock:
+            IterativeMethodBase.__call__(self, n_iter=n_iter, initial_call=initial_call)
+            return
+        if initial_call and self.record_loss:
+            self.loss.append(self.compute_loss())
+        if n_iter <= 0:
+            return
+        self._set_flooring(self.flooring_fn)
+        B = self._dims()[0]
+        buf = _device.empty((n_iter, B), torch.float64) if self.record_loss else None
+        self._ensure_plan()
+        _lib.call("ssb_run", self._plan, int(n_iter), _device.ptr(buf), _device.stream_ptr())
+        if self.record_loss:
+            vals = buf.cpu().numpy()
+            self.loss.extend(vals[i].copy() if self._batched else float(vals[i, 0]) for i in range(n_iter))
+
+    def _stock_update_methods(self):
+        cls = type(self)
+        return (cls.update_source_model is GaussILRMA.update_source_model
+                and cls.update_spatial_model is GaussILRMA.update_spatial_model
+                and cls.normalize is ILRMABase.normalize)
+
+    def __repr__(self):
+        s = "GaussILRMA(n_basis={n_basis}, spatial_algorithm={spatial_algorithm}"
+        s += ", source_algorithm={source_algorithm}, domain={domain}, partitioning={partitioning}"
+        s += ", normalization={normalization}, scale_restoration={scale_restoration}, record_loss={record_loss}"
+        if self.scale_restoration:
+            s += ", reference_id={reference_id}"
+        return (s + ")").format(**self.__dict__)
+
+    def _reset(self, flooring_fn="self", **kwargs):
+        flooring_fn = choose_flooring_fn(flooring_fn, method=self)
+        super()._reset(flooring_fn=flooring_fn, **kwargs)
+        if self.spatial_algorithm in ["ISS", "ISS1", "ISS2", "IPA"]:
+            self.demix_filter = None  # state lives in self.output (ilrma.py:897-898)
+
+    def update_once(self, flooring_fn="self"):
+        """One iteration: source model, spatial model, normalisation (ilrma.py:900-922)."""
+        flooring_fn = choose_flooring_fn(flooring_fn, method=self)
+        if self._stock_update_methods():
+            self._set_flooring(flooring_fn)
+            self._plan_call("ssb_update_once")
+            return
+        self.update_source_model(flooring_fn=flooring_fn)
+        self.update_spatial_model(flooring_fn=flooring_fn)
+        if self.normalization:
+            self.normalize(flooring_fn=flooring_fn)
+
+    def update_source_model(self, flooring_fn="self"):
+        """MM / ME updates of basis then activation (ilrma.py:924-1005)."""
+        flooring_fn = choose_flooring_fn(flooring_fn, method=self)
+        if self.source_algorithm not in source_algorithms:
+            raise ValueError("{}-algorithm-based source model updates are not supported.".format(self.source_algorithm))
+        self._set_flooring(flooring_fn)
+        self._plan_call("ssb_update_source_model")
+
+    def update_spatial_model(self, flooring_fn="self"):
+        """IP1 / IP2 on the demixing filters or ISS1 on the spectrograms (ilrma.py:1403-1438)."""
+        flooring_fn = choose_flooring_fn(flooring_fn, method=self)
+        if self.spatial_algorithm not in _SPATIAL_ENUM:
+            raise NotImplementedError("Not support {}.".format(self.spatial_algorithm))
+        self._set_flooring(flooring_fn)
+        self._plan_call("ssb_update_spatial_model")
+
+    def compute_loss(self):
+        """Negative log-likelihood (ilrma.py:1910-1967): a ``float`` for a single mixture, an array of
+        shape (batch,) for batched input."""
+        return self._loss_from_device()

@@ -1,0 +1,84 @@
+// Internal launch-wrapper declarations shared by the translation units of libssb.so.
+// Every ssbk_* function enqueues kernels on `st` and returns 0 / non-zero (ssb_last_error()).
+#pragma once
+#include "ssb_common.cuh"
+
+#define SSB_DISPATCH_N(N_, ...)                                              \
+  switch (N_) {                                                              \
+    case 2: { constexpr int NN = 2; __VA_ARGS__; } break;                    \
+    case 3: { constexpr int NN = 3; __VA_ARGS__; } break;                    \
+    case 4: { constexpr int NN = 4; __VA_ARGS__; } break;                    \
+    case 5: { constexpr int NN = 5; __VA_ARGS__; } break;                    \
+    case 6: { constexpr int NN = 6; __VA_ARGS__; } break;                    \
+    case 7: { constexpr int NN = 7; __VA_ARGS__; } break;                    \
+    case 8: { constexpr int NN = 8; __VA_ARGS__; } break;                    \
+    default:                                                                 \
+      ssb_set_error("n_sources=%d unsupported (2..%d)", N_, SSB_MAX_SOURCES); \
+      return 1;                                                              \
+  }
+
+// K (n_basis) is padded up to a compile-time KP for the register-resident NMF kernels
+#define SSB_DISPATCH_K(K_, ...)                                            \
+  if ((K_) <= 8) { constexpr int KP = 8; __VA_ARGS__; }                    \
+  else if ((K_) <= 16) { constexpr int KP = 16; __VA_ARGS__; }             \
+  else if ((K_) <= 32) { constexpr int KP = 32; __VA_ARGS__; }             \
+  else if ((K_) <= 64) { constexpr int KP = 64; __VA_ARGS__; }             \
+  else {                                                                   \
+    ssb_set_error("n_basis=%d unsupported (1..%d)", K_, SSB_MAX_BASIS);    \
+    return 1;                                                              \
+  }
+
+static inline int blocks_for(long long items, int per_block) { return (int)((items + per_block - 1) / per_block); }
+
+// ---- ssb_spatial.cu ----------------------------------------------------------------------------
+int ssbk_separate(const cf* X, const cf* W, cf* Y, float* P, int B, int N, int I, int J, cudaStream_t st);
+int ssbk_abs2(const cf* Y, float* P, size_t n, cudaStream_t st);
+int ssbk_wcov(const cf* X, const float* phi, long long sb, long long sn, long long si, const int* src, int n_src,
+              cf* U, int B, int N, int I, int J, cudaStream_t st);
+int ssbk_ip1(cf* W, const cf* U, int n_mat, int N, int flooring, float eps, cudaStream_t st);
+// uidx (host, 2*n_pairs, may be NULL => U slice index = source index): which of the n_u slices of U
+// each pair member uses
+int ssbk_ip2(cf* W, const cf* U, int n_mat, int N, const int* pairs, int n_pairs, int n_u, const int* uidx,
+             int flooring, float eps, cudaStream_t st);
+int ssbk_iss1(cf* Y, const float* phi, long long sb, long long sn, long long si, int B, int N, int I, int J,
+              int flooring, float eps, cudaStream_t st);
+int ssbk_pb_w(const cf* W, cf* Wout, cf* scale_out, int n_mat, int N, int ref, cudaStream_t st);
+int ssbk_cross_solve(const cf* A, const cf* Bm, cf* S, int B, int N, int I, int J, cudaStream_t st);
+int ssbk_scale_rows(const cf* Y, const cf* S, cf* Yout, int B, int N, int I, int J, int ref, cudaStream_t st);
+int ssbk_logdet(const cf* W, double* out, int n_mat, int N, cudaStream_t st);
+
+// ---- ssb_nmf.cu --------------------------------------------------------------------------------
+// MM/ME multiplicative updates from the power spectrogram P[B,N,I,J] (ssspy/bss/ilrma.py:1116-1126,
+// :1192-1202, :1311-1323, :1387-1399)
+int ssbk_nmf_basis(const float* P, float* T, const float* V, int BN, int I, int J, int K, float p, int source,
+                   int flooring, float eps, cudaStream_t st);
+int ssbk_nmf_activation(const float* P, const float* T, float* V, int BN, int I, int J, int K, float p, int source,
+                        int flooring, float eps, cudaStream_t st);
+// phi[B,N,I,J] = (T V)^(-2/p)   (ilrma.py:1494-1498)
+int ssbk_nmf_phi(const float* T, const float* V, float* phi, int BN, int I, int J, int K, float p, cudaStream_t st);
+// rowloss[B,N,I] = mean_j( P / R^(2/p) + (2/p) log R ),  R = T V   (ilrma.py:1957-1964)
+int ssbk_nmf_rowloss(const float* P, const float* T, const float* V, double* rowloss, int BN, int I, int J, int K,
+                     float p, cudaStream_t st);
+// loss[b] = sum_{n,i} rowloss - 2 sum_i logdet   (ilrma.py:1964-1965)
+int ssbk_ilrma_loss_reduce(const double* rowloss, const double* logdet, double* loss, int B, int N, int I,
+                           cudaStream_t st);
+// power normalisation (ilrma.py:412-444)
+int ssbk_psi_from_cov(const cf* W, const cf* C, double* psi2, int B, int N, int I, cudaStream_t st);
+int ssbk_psi_from_y(const cf* Y, double* psi2, int B, int N, int I, int J, cudaStream_t st);
+int ssbk_apply_psi(const double* psi2, float* T, cf* W, cf* Y, int B, int N, int I, int J, int K, float p,
+                   int flooring, float eps, cudaStream_t st);
+// projection-back normalisation: T[b,n,i,:] *= |s[b,i,n]|^p, s with element stride (ilrma.py:510-514)
+int ssbk_scale_basis(float* T, const cf* s, long long s_mat_stride, long long s_src_stride, int B, int N, int I,
+                     int K, float p, cudaStream_t st);
+
+// ---- ssb_iva.cu --------------------------------------------------------------------------------
+// r2[b,s,j] = sum_i |y_{src[s]}|^2 with y = W x (W != NULL) or y = Y (iva.py:1787, :1903, :1962)
+int ssbk_iva_norm2(const cf* X, const cf* W, const cf* Y, const int* src, int n_src, float* r2, int B, int N, int I,
+                   int J, cudaStream_t st);
+// phi[b,s,j] = G'(r)/floor(2 r) (iva.py:1788-1789); Gauss uses variance[b,src[s],j] (iva.py:3273-3289);
+// set_variance: variance = r2 / I first (update_source_model, iva.py:3465-3473; needs all sources)
+int ssbk_iva_phi(const float* r2, float* variance, int set_variance, const int* src, int n_src, float* phi,
+                 int model, int B, int N, int I, int J, int flooring, float eps, cudaStream_t st);
+// loss[b] = sum_n mean_j G - 2 sum_i logdet (iva.py:215-220, :3093-3103, :3256-3271)
+int ssbk_iva_loss(const float* r2, const float* variance, const double* logdet, double* loss, int model, int B,
+                  int N, int I, int J, cudaStream_t st);

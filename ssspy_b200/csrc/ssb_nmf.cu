@@ -1,0 +1,357 @@
+// NMF source-model kernels of GaussILRMA (modular variants): MM / ME multiplicative updates of the
+// basis T[B,N,I,K] and activation V[B,N,K,J] from the power spectrogram P = |Y|^2, the IP/ISS weight
+// phi = (T V)^(-2/p), the per-row loss terms and the power / projection-back normalisation.
+// K is padded to a compile-time KP so that T row / V column / numerator / denominator live in
+// registers; contractions over K are plain FMA chains (the tensor-core variant is ssb_fused_*.cu).
+#include "ssb_kernels.h"
+
+namespace {
+
+constexpr int WPB = 4;
+enum { PM_MM2 = 0, PM_ME = 1, PM_GENERIC = 2 };
+
+__device__ __forceinline__ float upd_pow(float ratio, float bexp, int mode) {
+  if (mode == PM_MM2) return sqrtf(ratio);
+  if (mode == PM_ME) return ratio;
+  return powf(ratio, bexp);
+}
+
+// T <- floor(T * (sum_j V P / R^a / sum_j V / R)^b); one warp per (b,n,i) row, lanes over frames.
+template <int KP>
+__global__ void __launch_bounds__(WPB * 32) k_nmf_basis(const float* __restrict__ P, float* __restrict__ T,
+                                                        const float* __restrict__ V, int rows, int I, int J,
+                                                        int K, float aexp, float bexp, int mode, int flooring,
+                                                        float eps) {
+  const int row = blockIdx.x * WPB + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int bn = row / I;
+  float t[KP], num[KP], den[KP];
+#pragma unroll
+  for (int k = 0; k < KP; ++k) {
+    t[k] = k < K ? T[(size_t)row * K + k] : 0.f;
+    num[k] = den[k] = 0.f;
+  }
+  const float* Vb = V + (size_t)bn * K * J;
+  const float* Pr = P + (size_t)row * J;
+  for (int j = lane; j < J; j += 32) {
+    float v[KP];
+    float R = 0.f;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      v[k] = k < K ? Vb[(size_t)k * J + j] : 0.f;
+      R = fmaf(t[k], v[k], R);
+    }
+    const float inv = 1.0f / R;
+    const float p_ = Pr[j];
+    const float A = (mode == PM_GENERIC) ? p_ / powf(R, aexp) : p_ * inv * inv;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      num[k] = fmaf(v[k], A, num[k]);
+      den[k] = fmaf(v[k], inv, den[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < KP; ++k) {
+    if (k < K) {
+      float nu = warp_sum(num[k]), de = warp_sum(den[k]);
+      if ((k & 31) == lane) T[(size_t)row * K + k] = ssb_floor(upd_pow(nu / de, bexp, mode) * t[k], flooring, eps);
+    }
+  }
+}
+
+// V <- floor(V * (sum_i T P / R^a / sum_i T / R)^b); one block per (b,n, 32-frame tile), NW warps
+// split the bins, lane = frame; cross-warp reduction through shared memory in fixed order.
+constexpr int ACT_NW = 8;
+template <int KP>
+__global__ void __launch_bounds__(ACT_NW * 32) k_nmf_activation(const float* __restrict__ P,
+                                                               const float* __restrict__ T, float* __restrict__ V,
+                                                               int I, int J, int K, float aexp, float bexp,
+                                                               int mode, int flooring, float eps) {
+  __shared__ float s_acc[2 * KP][32];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int jt = blockIdx.x, bn = blockIdx.y;
+  const int j = jt * 32 + lane;
+  const bool valid = j < J;
+  float v[KP], num[KP], den[KP];
+#pragma unroll
+  for (int k = 0; k < KP; ++k) {
+    v[k] = (valid && k < K) ? V[((size_t)bn * K + k) * J + j] : 0.f;
+    num[k] = den[k] = 0.f;
+  }
+  for (int i = w; i < I; i += ACT_NW) {
+    const float* Tr = T + ((size_t)bn * I + i) * K;
+    float t[KP];
+    float R = 0.f;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      t[k] = k < K ? __ldg(Tr + k) : 0.f;
+      R = fmaf(t[k], v[k], R);
+    }
+    if (!valid) R = 1.f;
+    const float inv = 1.0f / R;
+    const float p_ = valid ? P[((size_t)bn * I + i) * J + j] : 0.f;
+    const float A = (mode == PM_GENERIC) ? p_ / powf(R, aexp) : p_ * inv * inv;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      num[k] = fmaf(t[k], A, num[k]);
+      den[k] = fmaf(t[k], inv, den[k]);
+    }
+  }
+  for (int ww = 0; ww < ACT_NW; ++ww) {
+    if (w == ww) {
+#pragma unroll
+      for (int k = 0; k < KP; ++k) {
+        if (ww == 0) {
+          s_acc[k][lane] = num[k];
+          s_acc[KP + k][lane] = den[k];
+        } else {
+          s_acc[k][lane] += num[k];
+          s_acc[KP + k][lane] += den[k];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (w == 0 && valid) {
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      if (k < K) {
+        float ratio = s_acc[k][lane] / s_acc[KP + k][lane];
+        V[((size_t)bn * K + k) * J + j] = ssb_floor(upd_pow(ratio, bexp, mode) * v[k], flooring, eps);
+      }
+    }
+  }
+}
+
+// phi = (T V)^(-2/p); one warp per row
+template <int KP>
+__global__ void __launch_bounds__(WPB * 32) k_nmf_phi(const float* __restrict__ T, const float* __restrict__ V,
+                                                      float* __restrict__ phi, int rows, int I, int J, int K,
+                                                      float p) {
+  const int row = blockIdx.x * WPB + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int bn = row / I;
+  float t[KP];
+#pragma unroll
+  for (int k = 0; k < KP; ++k) t[k] = k < K ? T[(size_t)row * K + k] : 0.f;
+  const float* Vb = V + (size_t)bn * K * J;
+  const bool p2 = (p == 2.0f);
+  const float e = -2.0f / p;
+  for (int j = lane; j < J; j += 32) {
+    float R = 0.f;
+#pragma unroll
+    for (int k = 0; k < KP; ++k)
+      if (k < K) R = fmaf(t[k], Vb[(size_t)k * J + j], R);
+    phi[(size_t)row * J + j] = p2 ? 1.0f / R : powf(R, e);
+  }
+}
+
+// rowloss[row] = mean_j( P / R^(2/p) + (2/p) log R )
+template <int KP>
+__global__ void __launch_bounds__(WPB * 32) k_nmf_rowloss(const float* __restrict__ P, const float* __restrict__ T,
+                                                          const float* __restrict__ V, double* __restrict__ rowloss,
+                                                          int rows, int I, int J, int K, float p) {
+  const int row = blockIdx.x * WPB + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int bn = row / I;
+  float t[KP];
+#pragma unroll
+  for (int k = 0; k < KP; ++k) t[k] = k < K ? T[(size_t)row * K + k] : 0.f;
+  const float* Vb = V + (size_t)bn * K * J;
+  const bool p2 = (p == 2.0f);
+  const float e = 2.0f / p;
+  double acc = 0.0;
+  for (int j = lane; j < J; j += 32) {
+    float R = 0.f;
+#pragma unroll
+    for (int k = 0; k < KP; ++k)
+      if (k < K) R = fmaf(t[k], Vb[(size_t)k * J + j], R);
+    const float pw = P[(size_t)row * J + j];
+    const float term = p2 ? pw / R + logf(R) : pw / powf(R, e) + e * logf(R);
+    acc += (double)term;
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) rowloss[row] = acc / (double)J;
+}
+
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (w == 0) {
+    r = lane < (int)(blockDim.x >> 5) ? sh[lane] : 0.0;
+    r = warp_sum(r);
+  }
+  __syncthreads();
+  return r;  // valid on warp 0
+}
+
+__global__ void k_ilrma_loss_reduce(const double* __restrict__ rowloss, const double* __restrict__ logdet,
+                                    double* __restrict__ loss, int N, int I) {
+  __shared__ double sh[32];
+  const int b = blockIdx.x;
+  double acc = 0.0;
+  for (int e = threadIdx.x; e < N * I; e += blockDim.x) acc += rowloss[(size_t)b * N * I + e];
+  for (int i = threadIdx.x; i < I; i += blockDim.x) acc -= 2.0 * logdet[(size_t)b * I + i];
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) loss[b] = acc;
+}
+
+// psi2[b,n] = mean_i Re( w_in^H-row C_i (w_in^H-row)^H ),  C_i = mean_j x x^H    
+__global__ void k_psi_from_cov(const cf* __restrict__ W, const cf* __restrict__ C, double* __restrict__ psi2, int N,
+                               int I) {
+  __shared__ double sh[32];
+  const int n = blockIdx.x, b = blockIdx.y;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < I; i += blockDim.x) {
+    const cf* w = W + (((size_t)b * I + i) * N + n) * N;
+    const cf* c = C + ((size_t)b * I + i) * N * N;
+    double s = 0.0;
+    for (int a = 0; a < N; ++a) {
+      cd wa = cf2cd(w[a]);
+      for (int cc = 0; cc < N; ++cc) {
+        cd t = cd_mul(wa, cf2cd(c[a * N + cc]));
+        s += cd_mulc(t, cf2cd(w[cc])).x;
+      }
+    }
+    acc += s;
+  }
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) psi2[b * N + n] = acc / (double)I;
+}
+
+__global__ void k_psi_from_y(const cf* __restrict__ Y, double* __restrict__ psi2, long long per_src) {
+  __shared__ double sh[32];
+  const int bn = blockIdx.x;
+  const cf* y = Y + (size_t)bn * per_src;
+  double acc = 0.0;
+  for (long long e = threadIdx.x; e < per_src; e += blockDim.x) {
+    cf v = y[e];
+    acc += (double)(v.x * v.x + v.y * v.y);
+  }
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) psi2[bn] = acc / (double)per_src;
+}
+
+// T[b,n,i,k] /= psi^p ; W[b,i,n,:] /= psi ; Y[b,n,:,:] /= psi      (ilrma.py:434-444)
+__global__ void k_apply_psi(const double* __restrict__ psi2, float* __restrict__ T, cf* __restrict__ W,
+                            cf* __restrict__ Y, int B, int N, int I, int J, int K, float p, int flooring, double eps) {
+  const size_t nT = (size_t)B * N * I * K;
+  const size_t nW = W ? (size_t)B * I * N * N : 0;
+  const size_t nY = Y ? (size_t)B * N * I * J : 0;
+  const size_t total = nT + nW + nY;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    if (e < nT) {
+      const int bn = (int)(e / ((size_t)I * K));
+      const double psi = ssb_floor(sqrt(psi2[bn]), flooring, eps);
+      const double sc = (p == 2.0f) ? psi * psi : pow(psi, (double)p);
+      T[e] = (float)((double)T[e] / sc);
+    } else if (e < nT + nW) {
+      const size_t q = e - nT;
+      const int n = (int)((q / N) % N);
+      const int b = (int)(q / ((size_t)I * N * N));
+      const double psi = ssb_floor(sqrt(psi2[b * N + n]), flooring, eps);
+      cf w = W[q];
+      W[q] = make_float2((float)(w.x / psi), (float)(w.y / psi));
+    } else {
+      const size_t q = e - nT - nW;
+      const int bn = (int)(q / ((size_t)I * J));
+      const double psi = ssb_floor(sqrt(psi2[bn]), flooring, eps);
+      cf y = Y[q];
+      Y[q] = make_float2((float)(y.x / psi), (float)(y.y / psi));
+    }
+  }
+}
+
+__global__ void k_scale_basis(float* __restrict__ T, const cf* __restrict__ s, long long s_mat, long long s_src,
+                              int N, int I, int K, float p, size_t total) {
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = e / K;  // (b, n, i)
+    const int i = (int)(row % I);
+    const int n = (int)((row / I) % N);
+    const int b = (int)(row / ((size_t)I * N));
+    cf sv = s[((size_t)b * I + i) * s_mat + (size_t)n * s_src];
+    double a = sqrt((double)sv.x * sv.x + (double)sv.y * sv.y);
+    double sc = (p == 2.0f) ? a * a : pow(a, (double)p);
+    T[e] = (float)((double)T[e] * sc);
+  }
+}
+
+int pmode(float p, int source) {
+  if (source == SSB_SOURCE_ME) return PM_ME;
+  return p == 2.0f ? PM_MM2 : PM_GENERIC;
+}
+
+}  // namespace
+
+int ssbk_nmf_basis(const float* P, float* T, const float* V, int BN, int I, int J, int K, float p, int source,
+                   int flooring, float eps, cudaStream_t st) {
+  const int rows = BN * I;
+  const int mode = pmode(p, source);
+  const float a = (p + 2.0f) / p, b = p / (p + 2.0f);
+  SSB_DISPATCH_K(K, k_nmf_basis<KP><<<blocks_for(rows, WPB), WPB * 32, 0, st>>>(P, T, V, rows, I, J, K, a, b, mode,
+                                                                                flooring, eps));
+  return ssb_check_launch("nmf_basis", st);
+}
+
+int ssbk_nmf_activation(const float* P, const float* T, float* V, int BN, int I, int J, int K, float p, int source,
+                        int flooring, float eps, cudaStream_t st) {
+  const int mode = pmode(p, source);
+  const float a = (p + 2.0f) / p, b = p / (p + 2.0f);
+  dim3 grid((J + 31) / 32, BN);
+  SSB_DISPATCH_K(K, k_nmf_activation<KP><<<grid, ACT_NW * 32, 0, st>>>(P, T, V, I, J, K, a, b, mode, flooring, eps));
+  return ssb_check_launch("nmf_activation", st);
+}
+
+int ssbk_nmf_phi(const float* T, const float* V, float* phi, int BN, int I, int J, int K, float p, cudaStream_t st) {
+  const int rows = BN * I;
+  SSB_DISPATCH_K(K, k_nmf_phi<KP><<<blocks_for(rows, WPB), WPB * 32, 0, st>>>(T, V, phi, rows, I, J, K, p));
+  return ssb_check_launch("nmf_phi", st);
+}
+
+int ssbk_nmf_rowloss(const float* P, const float* T, const float* V, double* rowloss, int BN, int I, int J, int K,
+                     float p, cudaStream_t st) {
+  const int rows = BN * I;
+  SSB_DISPATCH_K(K, k_nmf_rowloss<KP><<<blocks_for(rows, WPB), WPB * 32, 0, st>>>(P, T, V, rowloss, rows, I, J, K, p));
+  return ssb_check_launch("nmf_rowloss", st);
+}
+
+int ssbk_ilrma_loss_reduce(const double* rowloss, const double* logdet, double* loss, int B, int N, int I,
+                           cudaStream_t st) {
+  k_ilrma_loss_reduce<<<B, 256, 0, st>>>(rowloss, logdet, loss, N, I);
+  return ssb_check_launch("ilrma_loss_reduce", st);
+}
+
+int ssbk_psi_from_cov(const cf* W, const cf* C, double* psi2, int B, int N, int I, cudaStream_t st) {
+  dim3 grid(N, B);
+  k_psi_from_cov<<<grid, 256, 0, st>>>(W, C, psi2, N, I);
+  return ssb_check_launch("psi_from_cov", st);
+}
+
+int ssbk_psi_from_y(const cf* Y, double* psi2, int B, int N, int I, int J, cudaStream_t st) {
+  k_psi_from_y<<<B * N, 1024, 0, st>>>(Y, psi2, (long long)I * J);
+  return ssb_check_launch("psi_from_y", st);
+}
+
+int ssbk_apply_psi(const double* psi2, float* T, cf* W, cf* Y, int B, int N, int I, int J, int K, float p,
+                   int flooring, float eps, cudaStream_t st) {
+  size_t total = (size_t)B * N * I * K + (W ? (size_t)B * I * N * N : 0) + (Y ? (size_t)B * N * I * J : 0);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_apply_psi<<<blocks, 256, 0, st>>>(psi2, T, W, Y, B, N, I, J, K, p, flooring, (double)eps);
+  return ssb_check_launch("apply_psi", st);
+}
+
+int ssbk_scale_basis(float* T, const cf* s, long long s_mat_stride, long long s_src_stride, int B, int N, int I,
+                     int K, float p, cudaStream_t st) {
+  size_t total = (size_t)B * N * I * K;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_scale_basis<<<blocks, 256, 0, st>>>(T, s, s_mat_stride, s_src_stride, N, I, K, p, total);
+  return ssb_check_launch("scale_basis", st);
+}

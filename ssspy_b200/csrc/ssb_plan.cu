@@ -1,0 +1,528 @@
+// C-ABI of libssb.so: error plumbing, the plan object (= device-side state of one separator) and the
+// per-iteration orchestration that mirrors GaussILRMA.update_once / AuxIVA.update_once.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+
+#include "ssb_fused.h"
+#include "ssb_kernels.h"
+
+// ---- errors -------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void ssb_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ---- launch accounting + optional per-kernel timing ----------------------------------------------
+// Every kernel launch of the library goes through ssb_check_launch.  With profiling enabled an
+// event is recorded after each launch; kernels of one stream run back to back, so the gap between
+// consecutive events is that launch's device time (the first gap starts at ssb_profile_begin).
+#include <map>
+#include <string>
+#include <vector>
+static unsigned long long g_launches = 0;
+static bool g_prof_on = false;
+static std::vector<std::pair<const char*, cudaEvent_t>> g_prof_events;
+static cudaEvent_t g_prof_start = nullptr;
+
+int ssb_check_launch(const char* what, cudaStream_t st) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    ssb_set_error("CUDA launch of '%s' failed: %s", what, cudaGetErrorString(e));
+    return 1;
+  }
+  ++g_launches;
+  if (g_prof_on) {
+    cudaEvent_t ev;
+    if (cudaEventCreate(&ev) == cudaSuccess) {
+      cudaEventRecord(ev, st);
+      g_prof_events.push_back({what, ev});
+    }
+  }
+  return 0;
+}
+
+extern "C" int ssb_launch_count(unsigned long long* count) {
+  *count = g_launches;
+  return 0;
+}
+
+extern "C" int ssb_profile_begin(void* stream) {
+  for (auto& pe : g_prof_events) cudaEventDestroy(pe.second);
+  g_prof_events.clear();
+  if (!g_prof_start) SSB_CUDA(cudaEventCreate(&g_prof_start));
+  SSB_CUDA(cudaEventRecord(g_prof_start, (cudaStream_t)stream));
+  g_prof_on = true;
+  return 0;
+}
+
+// Stops profiling, synchronises, and writes "name count total_ms\n" lines (sorted by total time).
+extern "C" int ssb_profile_end(char* buf, size_t buf_bytes) {
+  g_prof_on = false;
+  std::map<std::string, std::pair<int, double>> agg;
+  cudaEvent_t prev = g_prof_start;
+  for (auto& pe : g_prof_events) {
+    SSB_CUDA(cudaEventSynchronize(pe.second));
+    float ms = 0.f;
+    SSB_CUDA(cudaEventElapsedTime(&ms, prev, pe.second));
+    auto& a = agg[pe.first];
+    a.first += 1;
+    a.second += ms;
+    prev = pe.second;
+  }
+  for (auto& pe : g_prof_events) cudaEventDestroy(pe.second);
+  g_prof_events.clear();
+  std::vector<std::pair<double, std::string>> order;
+  for (auto& kv : agg) order.push_back({-kv.second.second, kv.first});
+  std::sort(order.begin(), order.end());
+  size_t off = 0;
+  if (buf && buf_bytes) buf[0] = 0;
+  for (auto& o : order) {
+    auto& a = agg[o.second];
+    int n = snprintf(buf + off, buf_bytes > off ? buf_bytes - off : 0, "%s %d %.6f\n", o.second.c_str(), a.first,
+                     a.second);
+    if (n < 0 || off + n >= buf_bytes) break;
+    off += n;
+  }
+  return 0;
+}
+
+extern "C" const char* ssb_last_error(void) { return g_err; }
+extern "C" int ssb_version(void) { return SSB_VERSION; }
+extern "C" int ssb_device_count(int* count) {
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (e != cudaSuccess) {
+    c = 0;
+    cudaGetLastError();
+  }
+  *count = c;
+  return 0;
+}
+
+// ---- plan ---------------------------------------------------------------------------------------
+struct ssb_plan {
+  ssb_config cfg;
+  const cf* X = nullptr;
+  cf* W = nullptr;
+  cf* Y = nullptr;
+  float* T = nullptr;
+  float* V = nullptr;
+  float* variance = nullptr;
+  char* ws = nullptr;
+  size_t ws_bytes = 0;
+  // workspace carve-up
+  float* big = nullptr;     // [B,N,I,J] f32: power spectrogram P, later the weights phi (ILRMA)
+  float* phi_iva = nullptr; // [B,N,J]
+  float* r2 = nullptr;      // [B,N,J]
+  cf* U = nullptr;          // [B,I,N,N,N]
+  cf* C = nullptr;          // [B,I,N,N]  unweighted covariance (power normalisation)
+  cf* S = nullptr;          // [B,I,N,N]  cross-solve result / recovered W
+  cf* scale = nullptr;      // [B,I,N]
+  double* psi2 = nullptr;   // [B,N]
+  double* rowloss = nullptr;  // [B,N,I]
+  double* logdet = nullptr;   // [B,I]
+  ssb_fused_ws fused;       // extra scratch of the fused kernels
+  bool bound = false, prepared = false;
+  bool iss() const { return cfg.spatial == SSB_SPATIAL_ISS1; }
+  bool ilrma() const { return cfg.model == SSB_MODEL_ILRMA_GAUSS; }
+};
+
+namespace {
+
+size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct Carver {
+  char* base;
+  size_t off = 0;
+  template <typename T>
+  T* take(size_t n) {
+    T* p = base ? (T*)(base + off) : nullptr;
+    off += align_up(n * sizeof(T));
+    return p;
+  }
+};
+
+size_t carve(ssb_plan* p, char* base) {
+  const ssb_config& c = p->cfg;
+  const size_t B = c.n_batch, N = c.n_sources, I = c.n_bins, J = c.n_frames;
+  Carver cv{base};
+  p->big = p->ilrma() ? cv.take<float>(B * N * I * J) : nullptr;
+  p->phi_iva = cv.take<float>(B * N * J);
+  p->r2 = cv.take<float>(B * N * J);
+  p->U = cv.take<cf>(B * I * N * N * N);
+  p->C = cv.take<cf>(B * I * N * N);
+  p->S = cv.take<cf>(B * I * N * N);
+  p->scale = cv.take<cf>(B * I * N);
+  p->psi2 = cv.take<double>(B * N);
+  p->rowloss = cv.take<double>(B * N * I);
+  p->logdet = cv.take<double>(B * I);
+  cv.off += ssb_fused_carve(&p->fused, &c, base ? base + cv.off : nullptr);
+  return cv.off;
+}
+
+int validate(const ssb_config* c) {
+  SSB_REQUIRE(c != nullptr, "config is NULL");
+  SSB_REQUIRE(c->model >= 0 && c->model <= 2, "unknown model %d", c->model);
+  SSB_REQUIRE(c->spatial >= 0 && c->spatial <= 2, "Not support spatial algorithm id %d.", c->spatial);
+  SSB_REQUIRE(c->source == SSB_SOURCE_MM || c->source == SSB_SOURCE_ME, "Not support source algorithm id %d.",
+              c->source);
+  SSB_REQUIRE(c->n_batch >= 1, "n_batch must be >= 1");
+  SSB_REQUIRE(c->n_sources >= 2 && c->n_sources <= SSB_MAX_SOURCES, "n_sources=%d unsupported (2..%d)", c->n_sources,
+              SSB_MAX_SOURCES);
+  SSB_REQUIRE(c->n_bins >= 1 && c->n_frames >= 1, "empty input (n_bins=%d, n_frames=%d)", c->n_bins, c->n_frames);
+  if (c->model == SSB_MODEL_ILRMA_GAUSS) {
+    SSB_REQUIRE(c->n_basis >= 1 && c->n_basis <= SSB_MAX_BASIS, "n_basis=%d unsupported (1..%d)", c->n_basis,
+                SSB_MAX_BASIS);
+    SSB_REQUIRE(c->domain > 0.f && c->domain <= 2.f, "domain parameter should be chosen from [0, 2].");
+    SSB_REQUIRE(c->source != SSB_SOURCE_ME || c->domain == 2.f,
+                "domain parameter should be 2 when you specify ME algorithm.");
+    SSB_REQUIRE(c->normalization >= 0 && c->normalization <= 2, "Normalization %d is not implemented.",
+                c->normalization);
+  }
+  SSB_REQUIRE(c->flooring >= 0 && c->flooring <= 2, "unknown flooring mode %d", c->flooring);
+  SSB_REQUIRE(c->reference_id >= 0 && c->reference_id < c->n_sources, "reference_id=%d out of range",
+              c->reference_id);
+  if (c->spatial == SSB_SPATIAL_IP2) {
+    SSB_REQUIRE(c->n_pairs >= 0 && c->n_pairs <= SSB_MAX_PAIRS, "n_pairs=%d exceeds %d", c->n_pairs, SSB_MAX_PAIRS);
+    for (int q = 0; q < c->n_pairs; ++q) {
+      int m = c->pairs[2 * q], n = c->pairs[2 * q + 1];
+      SSB_REQUIRE(m >= 0 && m < c->n_sources && n >= 0 && n < c->n_sources && m != n,
+                  "invalid pair (%d, %d) for n_sources=%d", m, n, c->n_sources);
+    }
+  }
+  return 0;
+}
+
+#define TRY(x)            \
+  do {                    \
+    if (int rc_ = (x)) return rc_; \
+  } while (0)
+
+int require_bound(const ssb_plan* p) {
+  SSB_REQUIRE(p != nullptr, "plan is NULL");
+  SSB_REQUIRE(p->bound, "plan has no buffers bound (call ssb_plan_bind first)");
+  return 0;
+}
+
+// P <- |Y|^2 with Y = W X (W modes) or the stored Y (ISS modes)
+int power_spectrogram(ssb_plan* p, cudaStream_t st) {
+  const ssb_config& c = p->cfg;
+  if (p->iss()) return ssbk_abs2(p->Y, p->big, (size_t)c.n_batch * c.n_sources * c.n_bins * c.n_frames, st);
+  return ssbk_separate(p->X, p->W, nullptr, p->big, c.n_batch, c.n_sources, c.n_bins, c.n_frames, st);
+}
+
+// log|det W_i| for every (b,i); ISS modes first recover W = Y X^H (X X^H)^-1
+int logdets(ssb_plan* p, cudaStream_t st) {
+  const ssb_config& c = p->cfg;
+  const cf* W = p->W;
+  if (p->iss()) {
+    TRY(ssbk_cross_solve(p->Y, p->X, p->S, c.n_batch, c.n_sources, c.n_bins, c.n_frames, st));
+    W = p->S;
+  }
+  return ssbk_logdet(W, p->logdet, c.n_batch * c.n_bins, c.n_sources, st);
+}
+
+int ilrma_source(ssb_plan* p, cudaStream_t st) {
+  const ssb_config& c = p->cfg;
+  const int BN = c.n_batch * c.n_sources;
+  TRY(power_spectrogram(p, st));
+  TRY(ssbk_nmf_basis(p->big, p->T, p->V, BN, c.n_bins, c.n_frames, c.n_basis, c.domain, c.source, c.flooring, c.eps,
+                     st));
+  TRY(ssbk_nmf_activation(p->big, p->T, p->V, BN, c.n_bins, c.n_frames, c.n_basis, c.domain, c.source, c.flooring,
+                          c.eps, st));
+  return 0;
+}
+
+int ilrma_spatial(ssb_plan* p, cudaStream_t st) {
+  const ssb_config& c = p->cfg;
+  const int B = c.n_batch, N = c.n_sources, I = c.n_bins, J = c.n_frames;
+  TRY(ssbk_nmf_phi(p->T, p->V, p->big, B * N, I, J, c.n_basis, c.domain, st));
+  const long long sb = (long long)N * I * J, sn = (long long)I * J, si = J;
+  if (c.spatial == SSB_SPATIAL_ISS1) return ssbk_iss1(p->Y, p->big, sb, sn, si, B, N, I, J, c.flooring, c.eps, st);
+  TRY(ssbk_wcov(p->X, p->big, sb, sn, si, nullptr, N, p->U, B, N, I, J, st));
+  if (c.spatial == SSB_SPATIAL_IP1) return ssbk_ip1(p->W, p->U, B * I, N, c.flooring, c.eps, st);
+  return ssbk_ip2(p->W, p->U, B * I, N, c.pairs, c.n_pairs, N, nullptr, c.flooring, c.eps, st);
+}
+
+int ilrma_normalize(ssb_plan* p, cudaStream_t st) {
+  const ssb_config& c = p->cfg;
+  const int B = c.n_batch, N = c.n_sources, I = c.n_bins, J = c.n_frames, K = c.n_basis;
+  if (c.normalization == SSB_NORM_POWER) {
+    if (p->iss()) {
+      TRY(ssbk_psi_from_y(p->Y, p->psi2, B, N, I, J, st));
+      return ssbk_apply_psi(p->psi2, p->T, nullptr, p->Y, B, N, I, J, K, c.domain, c.flooring, c.eps, st);
+    }
+    SSB_REQUIRE(p->prepared, "plan not prepared (call ssb_plan_prepare after bind)");
+    TRY(ssbk_psi_from_cov(p->W, p->C, p->psi2, B, N, I, st));
+    return ssbk_apply_psi(p->psi2, p->T, p->W, nullptr, B, N, I, J, K, c.domain, c.flooring, c.eps, st);
+  }
+  if (c.normalization == SSB_NORM_PROJECTION_BACK) {
+    if (p->iss()) {
+      TRY(ssbk_cross_solve(p->X, p->Y, p->S, B, N, I, J, st));
+      TRY(ssbk_scale_rows(p->Y, p->S, p->Y, B, N, I, J, c.reference_id, st));
+      return ssbk_scale_basis(p->T, p->S + (size_t)c.reference_id * N, (long long)N * N, 1, B, N, I, K, c.domain, st);
+    }
+    TRY(ssbk_pb_w(p->W, p->W, p->scale, B * I, N, c.reference_id, st));
+    return ssbk_scale_basis(p->T, p->scale, N, 1, B, N, I, K, c.domain, st);
+  }
+  return 0;
+}
+
+int ilrma_loss(ssb_plan* p, double* loss, cudaStream_t st) {
+  const ssb_config& c = p->cfg;
+  const int B = c.n_batch, N = c.n_sources, I = c.n_bins, J = c.n_frames;
+  TRY(power_spectrogram(p, st));
+  TRY(logdets(p, st));
+  TRY(ssbk_nmf_rowloss(p->big, p->T, p->V, p->rowloss, B * N, I, J, c.n_basis, c.domain, st));
+  return ssbk_ilrma_loss_reduce(p->rowloss, p->logdet, loss, B, N, I, st);
+}
+
+// r2 over all sources from the current state
+int iva_norm_all(ssb_plan* p, cudaStream_t st) {
+  const ssb_config& c = p->cfg;
+  return ssbk_iva_norm2(p->X, p->iss() ? nullptr : p->W, p->Y, nullptr, c.n_sources, p->r2, c.n_batch, c.n_sources,
+                        c.n_bins, c.n_frames, st);
+}
+
+int iva_source(ssb_plan* p, cudaStream_t st) {
+  const ssb_config& c = p->cfg;
+  if (c.model != SSB_MODEL_IVA_GAUSS) return 0;
+  TRY(iva_norm_all(p, st));
+  return ssbk_iva_phi(p->r2, p->variance, 1, nullptr, c.n_sources, nullptr, c.model, c.n_batch, c.n_sources, c.n_bins,
+                      c.n_frames, c.flooring, c.eps, st);
+}
+
+int iva_spatial(ssb_plan* p, cudaStream_t st) {
+  const ssb_config& c = p->cfg;
+  const int B = c.n_batch, N = c.n_sources, I = c.n_bins, J = c.n_frames;
+  if (c.spatial == SSB_SPATIAL_IP2) {
+    for (int q = 0; q < c.n_pairs; ++q) {
+      const int pr[2] = {c.pairs[2 * q], c.pairs[2 * q + 1]};
+      const int uidx[2] = {0, 1};
+      TRY(ssbk_iva_norm2(p->X, p->W, nullptr, pr, 2, p->r2, B, N, I, J, st));
+      TRY(ssbk_iva_phi(p->r2, p->variance, 0, pr, 2, p->phi_iva, c.model, B, N, I, J, c.flooring, c.eps, st));
+      TRY(ssbk_wcov(p->X, p->phi_iva, 2LL * J, J, 0, nullptr, 2, p->U, B, N, I, J, st));
+      TRY(ssbk_ip2(p->W, p->U, B * I, N, pr, 1, 2, uidx, c.flooring, c.eps, st));
+    }
+    return 0;
+  }
+  TRY(iva_norm_all(p, st));
+  TRY(ssbk_iva_phi(p->r2, p->variance, 0, nullptr, N, p->phi_iva, c.model, B, N, I, J, c.flooring, c.eps, st));
+  if (c.spatial == SSB_SPATIAL_ISS1)
+    return ssbk_iss1(p->Y, p->phi_iva, (long long)N * J, J, 0, B, N, I, J, c.flooring, c.eps, st);
+  TRY(ssbk_wcov(p->X, p->phi_iva, (long long)N * J, J, 0, nullptr, N, p->U, B, N, I, J, st));
+  return ssbk_ip1(p->W, p->U, B * I, N, c.flooring, c.eps, st);
+}
+
+int iva_loss(ssb_plan* p, double* loss, cudaStream_t st) {
+  const ssb_config& c = p->cfg;
+  TRY(iva_norm_all(p, st));
+  TRY(logdets(p, st));
+  return ssbk_iva_loss(p->r2, p->variance, p->logdet, loss, c.model, c.n_batch, c.n_sources, c.n_bins, c.n_frames, st);
+}
+
+}  // namespace
+
+extern "C" int ssb_plan_create(const ssb_config* cfg, ssb_plan** plan) {
+  SSB_REQUIRE(plan != nullptr, "plan out-pointer is NULL");
+  TRY(validate(cfg));
+  ssb_plan* p = new (std::nothrow) ssb_plan();
+  SSB_REQUIRE(p != nullptr, "out of host memory");
+  p->cfg = *cfg;
+  *plan = p;
+  return 0;
+}
+
+extern "C" int ssb_plan_destroy(ssb_plan* plan) {
+  delete plan;
+  return 0;
+}
+
+extern "C" int ssb_plan_workspace_bytes(const ssb_plan* plan, size_t* bytes) {
+  SSB_REQUIRE(plan != nullptr && bytes != nullptr, "NULL argument");
+  ssb_plan tmp = *plan;
+  *bytes = carve(&tmp, nullptr);
+  return 0;
+}
+
+extern "C" int ssb_plan_bind(ssb_plan* p, const void* X, void* W, void* Y, void* T, void* V, void* variance,
+                             void* workspace, size_t workspace_bytes) {
+  SSB_REQUIRE(p != nullptr, "plan is NULL");
+  SSB_REQUIRE(X != nullptr && Y != nullptr, "X and Y must be bound");
+  SSB_REQUIRE(p->iss() || W != nullptr, "W must be bound unless spatial_algorithm is ISS");
+  SSB_REQUIRE(!p->ilrma() || (T != nullptr && V != nullptr), "T and V must be bound for ILRMA");
+  SSB_REQUIRE(p->cfg.model != SSB_MODEL_IVA_GAUSS || variance != nullptr, "variance must be bound for AuxGaussIVA");
+  size_t need = 0;
+  TRY(ssb_plan_workspace_bytes(p, &need));
+  SSB_REQUIRE(workspace != nullptr && workspace_bytes >= need, "workspace too small: %zu < %zu bytes", workspace_bytes,
+              need);
+  p->X = (const cf*)X;
+  p->W = (cf*)W;
+  p->Y = (cf*)Y;
+  p->T = (float*)T;
+  p->V = (float*)V;
+  p->variance = (float*)variance;
+  p->ws = (char*)workspace;
+  p->ws_bytes = workspace_bytes;
+  carve(p, p->ws);
+  p->bound = true;
+  p->prepared = false;
+  return 0;
+}
+
+extern "C" int ssb_plan_set_flooring(ssb_plan* p, int flooring, float eps) {
+  SSB_REQUIRE(p != nullptr, "plan is NULL");
+  SSB_REQUIRE(flooring >= 0 && flooring <= 2, "unknown flooring mode %d", flooring);
+  p->cfg.flooring = flooring;
+  p->cfg.eps = eps;
+  return 0;
+}
+
+extern "C" int ssb_plan_prepare(ssb_plan* p, void* stream) {
+  TRY(require_bound(p));
+  const ssb_config& c = p->cfg;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p->ilrma() && !p->iss()) {
+    // C_i = mean_j x x^H, constant over the iterations
+    TRY(ssbk_wcov(p->X, nullptr, 0, 0, 0, nullptr, 1, p->C, c.n_batch, c.n_sources, c.n_bins, c.n_frames, st));
+  }
+  TRY(ssb_fused_prepare(&p->fused, &c, p->X, st));
+  p->prepared = true;
+  return 0;
+}
+
+extern "C" int ssb_update_source_model(ssb_plan* p, void* stream) {
+  TRY(require_bound(p));
+  return p->ilrma() ? ilrma_source(p, (cudaStream_t)stream) : iva_source(p, (cudaStream_t)stream);
+}
+
+extern "C" int ssb_update_spatial_model(ssb_plan* p, void* stream) {
+  TRY(require_bound(p));
+  return p->ilrma() ? ilrma_spatial(p, (cudaStream_t)stream) : iva_spatial(p, (cudaStream_t)stream);
+}
+
+extern "C" int ssb_normalize(ssb_plan* p, void* stream) {
+  TRY(require_bound(p));
+  SSB_REQUIRE(p->ilrma(), "normalize is defined for ILRMA only");
+  return ilrma_normalize(p, (cudaStream_t)stream);
+}
+
+extern "C" int ssb_update_once(ssb_plan* p, void* stream) {
+  TRY(require_bound(p));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p->ilrma()) {
+    if (p->cfg.fast_path && ssb_fused_supported(&p->cfg)) {
+      SSB_REQUIRE(p->prepared, "plan not prepared (call ssb_plan_prepare after bind)");
+      return ssb_fused_update_once(&p->fused, &p->cfg, p->X, p->W, p->T, p->V, p->C, st);
+    }
+    TRY(ilrma_source(p, st));
+    TRY(ilrma_spatial(p, st));
+    if (p->cfg.normalization != SSB_NORM_NONE) TRY(ilrma_normalize(p, st));
+    return 0;
+  }
+  TRY(iva_source(p, st));
+  return iva_spatial(p, st);
+}
+
+extern "C" int ssb_compute_loss(ssb_plan* p, double* loss, void* stream) {
+  TRY(require_bound(p));
+  SSB_REQUIRE(loss != nullptr, "loss output is NULL");
+  return p->ilrma() ? ilrma_loss(p, loss, (cudaStream_t)stream) : iva_loss(p, loss, (cudaStream_t)stream);
+}
+
+extern "C" int ssb_run(ssb_plan* p, int n_iter, double* loss, void* stream) {
+  TRY(require_bound(p));
+  for (int it = 0; it < n_iter; ++it) {
+    TRY(ssb_update_once(p, stream));
+    if (loss) TRY(ssb_compute_loss(p, loss + (size_t)it * p->cfg.n_batch, stream));
+  }
+  return 0;
+}
+
+extern "C" int ssb_plan_separate(ssb_plan* p, void* stream) {
+  TRY(require_bound(p));
+  if (p->iss()) return 0;
+  const ssb_config& c = p->cfg;
+  return ssbk_separate(p->X, p->W, p->Y, nullptr, c.n_batch, c.n_sources, c.n_bins, c.n_frames, (cudaStream_t)stream);
+}
+
+extern "C" int ssb_restore_scale(ssb_plan* p, void* stream) {
+  TRY(require_bound(p));
+  const ssb_config& c = p->cfg;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = c.n_batch, N = c.n_sources, I = c.n_bins, J = c.n_frames;
+  if (p->iss()) {
+    TRY(ssbk_cross_solve(p->X, p->Y, p->S, B, N, I, J, st));
+    return ssbk_scale_rows(p->Y, p->S, p->Y, B, N, I, J, c.reference_id, st);
+  }
+  TRY(ssbk_pb_w(p->W, p->W, nullptr, B * I, N, c.reference_id, st));
+  return ssbk_separate(p->X, p->W, p->Y, nullptr, B, N, I, J, st);
+}
+
+// ---- standalone operators -----------------------------------------------------------------------
+extern "C" int ssb_separate(const void* X, const void* W, void* Y, int B, int N, int I, int J, void* stream) {
+  SSB_REQUIRE(X && W && Y, "NULL argument");
+  if (B <= 0 || I <= 0 || J <= 0) return 0;
+  return ssbk_separate((const cf*)X, (const cf*)W, (cf*)Y, nullptr, B, N, I, J, (cudaStream_t)stream);
+}
+
+extern "C" int ssb_weighted_covariance(const void* X, const float* phi, long long phi_sb, long long phi_sn,
+                                       long long phi_si, const int32_t* src, int n_src, void* U, int B, int N, int I,
+                                       int J, void* stream) {
+  SSB_REQUIRE(X && U, "NULL argument");
+  if (B <= 0 || I <= 0) return 0;
+  return ssbk_wcov((const cf*)X, phi, phi_sb, phi_sn, phi_si, src, n_src, (cf*)U, B, N, I, J, (cudaStream_t)stream);
+}
+
+extern "C" int ssb_update_by_ip1(void* W, const void* U, int n_mat, int N, int flooring, float eps, void* stream) {
+  SSB_REQUIRE(W && U, "NULL argument");
+  if (n_mat <= 0) return 0;
+  return ssbk_ip1((cf*)W, (const cf*)U, n_mat, N, flooring, eps, (cudaStream_t)stream);
+}
+
+extern "C" int ssb_update_by_ip2(void* W, const void* U, int n_mat, int N, const int32_t* pairs, int n_pairs,
+                                 int flooring, float eps, void* stream) {
+  SSB_REQUIRE(W && U && (pairs || n_pairs == 0), "NULL argument");
+  if (n_mat <= 0) return 0;
+  return ssbk_ip2((cf*)W, (const cf*)U, n_mat, N, pairs, n_pairs, N, nullptr, flooring, eps, (cudaStream_t)stream);
+}
+
+extern "C" int ssb_update_by_ip2_one_pair(void* W, const void* U_pair, int n_mat, int N, int m, int n, int flooring,
+                                          float eps, void* stream) {
+  SSB_REQUIRE(W && U_pair, "NULL argument");
+  if (n_mat <= 0) return 0;
+  const int pr[2] = {m, n};
+  const int uidx[2] = {0, 1};
+  return ssbk_ip2((cf*)W, (const cf*)U_pair, n_mat, N, pr, 1, 2, uidx, flooring, eps, (cudaStream_t)stream);
+}
+
+extern "C" int ssb_update_by_iss1(void* Y, const float* phi, long long phi_sb, long long phi_sn, long long phi_si,
+                                  int B, int N, int I, int J, int flooring, float eps, void* stream) {
+  SSB_REQUIRE(Y && phi, "NULL argument");
+  if (B <= 0 || I <= 0 || J <= 0) return 0;
+  return ssbk_iss1((cf*)Y, phi, phi_sb, phi_sn, phi_si, B, N, I, J, flooring, eps, (cudaStream_t)stream);
+}
+
+extern "C" int ssb_projection_back_w(const void* W, void* Wout, int n_mat, int N, int reference_id, void* stream) {
+  SSB_REQUIRE(W && Wout, "NULL argument");
+  if (n_mat <= 0) return 0;
+  return ssbk_pb_w((const cf*)W, (cf*)Wout, nullptr, n_mat, N, reference_id, (cudaStream_t)stream);
+}
+
+extern "C" int ssb_projection_back_y(const void* Y, const void* X, void* Yout, void* scale_out, int B, int N, int I,
+                                     int J, int reference_id, void* stream) {
+  SSB_REQUIRE(Y && X && scale_out, "NULL argument (scale_out is required scratch of B*I*N*N complex64)");
+  if (B <= 0 || I <= 0 || J <= 0) return 0;
+  TRY(ssbk_cross_solve((const cf*)X, (const cf*)Y, (cf*)scale_out, B, N, I, J, (cudaStream_t)stream));
+  if (Yout == nullptr) return 0;
+  return ssbk_scale_rows((const cf*)Y, (const cf*)scale_out, (cf*)Yout, B, N, I, J, reference_id,
+                         (cudaStream_t)stream);
+}

@@ -1,0 +1,576 @@
+// Per-bin spatial kernels of the ILRMA / AuxIVA path (modular variants): separate, weighted
+// covariance, IP1, IP2, ISS1, projection back, cross-solve (W recovery), log|det W|.
+// One warp owns one (mixture, bin); the N x N complex linear algebra is done in fp64 in shared
+// memory by the warp (ssb_common.cuh), the frame reductions in fp32 with a warp tree reduce.
+#include "ssb_kernels.h"
+
+namespace {
+
+constexpr int WPB = 4;  // warps (= bins) per block for the warp-per-bin kernels
+
+// ------------------------------------------------------------------------------------------------
+// separate: Y[b,n,i,j] = sum_m W[b,i,n,m] X[b,m,i,j]        (ssspy/bss/ilrma.py:292-295)
+// optionally P[b,n,i,j] = |Y|^2.  One block per (b,i); threads stride over frames.
+template <int N>
+__global__ void __launch_bounds__(128) k_separate(const cf* __restrict__ X, const cf* __restrict__ W,
+                                                  cf* __restrict__ Y, float* __restrict__ P, int I, int J) {
+  __shared__ cf w[N * N];
+  const int bi = blockIdx.x;
+  const int b = bi / I, i = bi - b * I;
+  if (threadIdx.x < N * N) w[threadIdx.x] = W[(size_t)bi * N * N + threadIdx.x];
+  __syncthreads();
+  const size_t base = ((size_t)b * N * I + i) * J;  // + m*I*J
+  const size_t cs = (size_t)I * J;
+  for (int j = threadIdx.x; j < J; j += blockDim.x) {
+    cf x[N];
+#pragma unroll
+    for (int m = 0; m < N; ++m) x[m] = X[base + m * cs + j];
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      float yr = 0.f, yi = 0.f;
+#pragma unroll
+      for (int m = 0; m < N; ++m) {
+        cf ww = w[n * N + m];
+        yr = fmaf(ww.x, x[m].x, fmaf(-ww.y, x[m].y, yr));
+        yi = fmaf(ww.x, x[m].y, fmaf(ww.y, x[m].x, yi));
+      }
+      if (Y) Y[base + n * cs + j] = make_float2(yr, yi);
+      if (P) P[base + n * cs + j] = yr * yr + yi * yi;
+    }
+  }
+}
+
+// P = |Y|^2 elementwise (ISS modes, where the state is Y itself)
+__global__ void k_abs2(const cf* __restrict__ Y, float* __restrict__ P, size_t n) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; t < n; t += stride) {
+    cf y = Y[t];
+    P[t] = y.x * y.x + y.y * y.y;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weighted covariance  U[b,i,s,a,c] = (1/J) sum_j phi[b,src[s],i,j] X[b,a,i,j] conj(X[b,c,i,j])
+// (ssspy/bss/ilrma.py:1500-1505, ssspy/bss/iva.py:1785-1791).  One warp per (b,i); NSB sources are
+// accumulated per pass over the bin's (channel x frame) slab; Hermitian => N^2 real accumulators
+// per source (upper triangle: re at [a][c], im at [c][a]).
+struct SrcList {
+  int n;
+  int idx[SSB_MAX_SOURCES];
+};
+
+template <int N>
+struct CovCfg {
+  static constexpr int raw = 64 / (N * N);
+  static constexpr int NSB = raw < 1 ? 1 : (raw > N ? N : raw);
+};
+
+template <int N>
+__global__ void __launch_bounds__(WPB * 32) k_wcov(const cf* __restrict__ X, const float* __restrict__ phi,
+                                                   long long sb, long long sn, long long si, SrcList src,
+                                                   cf* __restrict__ U, int B, int I, int J) {
+  constexpr int NSB = CovCfg<N>::NSB;
+  const int warp = blockIdx.x * WPB + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (warp >= B * I) return;
+  const int b = warp / I, i = warp - b * I;
+  const size_t base = ((size_t)b * N * I + i) * J;
+  const size_t cs = (size_t)I * J;
+  const float invJ = 1.0f / (float)J;
+  for (int s0 = 0; s0 < src.n; s0 += NSB) {
+    float acc[NSB][N * N];
+#pragma unroll
+    for (int s = 0; s < NSB; ++s)
+#pragma unroll
+      for (int e = 0; e < N * N; ++e) acc[s][e] = 0.f;
+    for (int j = lane; j < J; j += 32) {
+      cf x[N];
+#pragma unroll
+      for (int m = 0; m < N; ++m) x[m] = X[base + m * cs + j];
+#pragma unroll
+      for (int s = 0; s < NSB; ++s) {
+        if (s0 + s < src.n) {
+          float ph = phi ? phi[(size_t)b * sb + (size_t)src.idx[s0 + s] * sn + (size_t)i * si + j] : 1.0f;
+#pragma unroll
+          for (int a = 0; a < N; ++a) {
+            float xr = ph * x[a].x, xi = ph * x[a].y;
+            acc[s][a * N + a] = fmaf(xr, x[a].x, fmaf(xi, x[a].y, acc[s][a * N + a]));
+#pragma unroll
+            for (int c = a + 1; c < N; ++c) {
+              // x_a conj(x_c) = (ar cr + ai ci) + i (ai cr - ar ci)
+              acc[s][a * N + c] = fmaf(xr, x[c].x, fmaf(xi, x[c].y, acc[s][a * N + c]));
+              acc[s][c * N + a] = fmaf(xi, x[c].x, fmaf(-xr, x[c].y, acc[s][c * N + a]));
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < NSB; ++s) {
+      if (s0 + s < src.n) {
+#pragma unroll
+        for (int e = 0; e < N * N; ++e) acc[s][e] = warp_sum(acc[s][e]) * invJ;
+        cf* u = U + ((size_t)warp * src.n + (s0 + s)) * N * N;
+        if (lane == 0) {
+#pragma unroll
+          for (int a = 0; a < N; ++a) {
+            u[a * N + a] = make_float2(acc[s][a * N + a], 0.f);
+#pragma unroll
+            for (int c = a + 1; c < N; ++c) {
+              u[a * N + c] = make_float2(acc[s][a * N + c], acc[s][c * N + a]);
+              u[c * N + a] = make_float2(acc[s][a * N + c], -acc[s][c * N + a]);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// IP1 (ssspy/bss/_update_spatial_model.py:63-76).  One warp per matrix, Gauss-Seidel over sources.
+template <int N>
+__global__ void __launch_bounds__(WPB * 32) k_ip1(cf* __restrict__ W, const cf* __restrict__ U, int n_mat,
+                                                  int flooring, double eps) {
+  __shared__ cd sW[WPB][N * N];
+  __shared__ cd sU[WPB][N * N];
+  __shared__ cd sA[WPB][N * (N + 1)];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mat = blockIdx.x * WPB + wib;
+  if (mat >= n_mat) return;
+  cd* w = sW[wib];
+  cd* u = sU[wib];
+  cd* A = sA[wib];
+  for (int e = lane; e < N * N; e += 32) w[e] = cf2cd(W[(size_t)mat * N * N + e]);
+  for (int n = 0; n < N; ++n) {
+    __syncwarp();
+    for (int e = lane; e < N * N; e += 32) u[e] = cf2cd(U[((size_t)mat * N + n) * N * N + e]);
+    __syncwarp();
+    for (int e = lane; e < N * (N + 1); e += 32) {
+      int r = e / (N + 1), c = e - r * (N + 1);
+      cd s = cd_make(0, 0);
+      if (c < N) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) s = cd_fma(w[r * N + k], u[k * N + c], s);
+      } else {
+        s = cd_make(r == n ? 1.0 : 0.0, 0);
+      }
+      A[e] = s;
+    }
+    __syncwarp();
+    warp_gauss_jordan(A, N, 1, N + 1, lane);
+    // wUw = Re( w^H U_n w ), w[a] = A[a][N]
+    double part = 0.0;
+    for (int e = lane; e < N * N; e += 32) {
+      int a = e / N, c = e - a * N;
+      cd t = cd_mul(u[e], A[c * (N + 1) + N]);
+      part += cd_mulc(t, A[a * (N + 1) + N]).x;  // Re( conj(w_a) * U[a][c] w_c )
+    }
+    double wUw = warp_sum(part);
+    double d = ssb_floor(sqrt(fmax(wUw, 0.0)), flooring, eps);
+    __syncwarp();
+    if (lane < N) w[n * N + lane] = cd_scale(cd_conj(A[lane * (N + 1) + N]), 1.0 / d);
+  }
+  __syncwarp();
+  for (int e = lane; e < N * N; e += 32) W[(size_t)mat * N * N + e] = cd2cf(w[e]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// IP2 (ssspy/bss/_update_spatial_model.py:137-141, :353-395).  One warp per matrix; pairs in order.
+struct PairList {
+  int n;
+  int n_u;  // sources per matrix stored in U
+  short m[SSB_MAX_PAIRS], nn[SSB_MAX_PAIRS];    // rows of W
+  short um[SSB_MAX_PAIRS], un[SSB_MAX_PAIRS];   // which U slices
+};
+
+template <int N>
+__device__ __forceinline__ void quad2(const cd* __restrict__ P, const cd* __restrict__ u, int lane, cd G[4]) {
+  // G[r][c] = sum_{a,b} conj(P[a][r]) U[a][b] P[b][c],  P is N x 2 (row major, ld 2)
+#pragma unroll
+  for (int rc = 0; rc < 4; ++rc) {
+    const int r = rc >> 1, c = rc & 1;
+    double pr = 0.0, pi = 0.0;
+    for (int e = lane; e < N * N; e += 32) {
+      int a = e / N, bb = e - a * N;
+      cd t = cd_mul(u[e], P[bb * 2 + c]);
+      cd v = cd_mul(cd_conj(P[a * 2 + r]), t);
+      pr += v.x;
+      pi += v.y;
+    }
+    G[rc] = cd_make(warp_sum(pr), warp_sum(pi));
+  }
+}
+
+template <int N>
+__global__ void __launch_bounds__(WPB * 32) k_ip2(cf* __restrict__ W, const cf* __restrict__ U, int n_mat,
+                                                  PairList pl, int flooring, double eps) {
+  __shared__ cd sW[WPB][N * N];
+  __shared__ cd sUm[WPB][N * N];
+  __shared__ cd sUn[WPB][N * N];
+  __shared__ cd sA[WPB][N * (N + 2)];
+  __shared__ cd sPm[WPB][N * 2];
+  __shared__ cd sPn[WPB][N * 2];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mat = blockIdx.x * WPB + wib;
+  if (mat >= n_mat) return;
+  cd *w = sW[wib], *um = sUm[wib], *un = sUn[wib], *A = sA[wib], *Pm = sPm[wib], *Pn = sPn[wib];
+  for (int e = lane; e < N * N; e += 32) w[e] = cf2cd(W[(size_t)mat * N * N + e]);
+  for (int q = 0; q < pl.n; ++q) {
+    const int m = pl.m[q], n = pl.nn[q];
+    __syncwarp();
+    for (int e = lane; e < N * N; e += 32) {
+      um[e] = cf2cd(U[((size_t)mat * pl.n_u + pl.um[q]) * N * N + e]);
+      un[e] = cf2cd(U[((size_t)mat * pl.n_u + pl.un[q]) * N * N + e]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      const cd* u = which ? un : um;
+      cd* P = which ? Pn : Pm;
+      for (int e = lane; e < N * (N + 2); e += 32) {
+        int r = e / (N + 2), c = e - r * (N + 2);
+        cd s = cd_make(0, 0);
+        if (c < N) {
+#pragma unroll
+          for (int k = 0; k < N; ++k) s = cd_fma(w[r * N + k], u[k * N + c], s);
+        } else {
+          s = cd_make((c == N ? r == m : r == n) ? 1.0 : 0.0, 0);
+        }
+        A[e] = s;
+      }
+      __syncwarp();
+      warp_gauss_jordan(A, N, 2, N + 2, lane);
+      for (int e = lane; e < N * 2; e += 32) P[e] = A[(e >> 1) * (N + 2) + N + (e & 1)];
+      __syncwarp();
+    }
+    cd Gm[4], Gn[4];
+    quad2<N>(Pm, um, lane, Gm);
+    quad2<N>(Pn, un, lane, Gn);
+    // generalised eigenproblem Gm h = l Gn h  (ssspy/linalg/eigh.py:173-201), all lanes redundantly
+    const double b00 = Gn[0].x, b11 = Gn[3].x;
+    const cd b10 = Gn[2];
+    const double l00 = sqrt(b00);
+    const cd l10 = cd_scale(b10, 1.0 / l00);
+    const double l11 = sqrt(b11 - cd_abs2(l10));
+    // Linv = [[i00, 0], [i10, i11]]
+    const double i00 = 1.0 / l00, i11 = 1.0 / l11;
+    const cd i10 = cd_scale(l10, -i00 * i11);
+    const double a00 = Gm[0].x, a11 = Gm[3].x;
+    const cd a01 = Gm[1];
+    // C = Linv A Linv^H
+    const double c00 = i00 * a00 * i00;
+    // c01 = (Linv A)[0,:] . conj(Linv[1,:]) = i00*a00*conj(i10) + i00*a01*i11
+    const cd c01 = cd_add(cd_scale(cd_conj(i10), i00 * a00), cd_scale(a01, i00 * i11));
+    // c11 = i10 a00 conj(i10) + i10 a01 i11 + i11 conj(a01) conj(i10) + i11 a11 i11
+    const double c11 = cd_abs2(i10) * a00 + 2.0 * i11 * cd_mul(i10, a01).x + i11 * i11 * a11;
+    double lam[2];
+    cd y0[2], y1[2];
+    herm_eig2(c00, c11, c01, lam, y0, y1);
+    // z = Linv^H y ;  Linv^H = [[i00, conj(i10)], [0, i11]]
+    cd hm[2], hn[2];  // h_m <- larger eigenvalue, h_n <- smaller (_update_spatial_model.py:370-373)
+    hm[0] = cd_add(cd_scale(y1[0], i00), cd_mul(cd_conj(i10), y1[1]));
+    hm[1] = cd_scale(y1[1], i11);
+    hn[0] = cd_add(cd_scale(y0[0], i00), cd_mul(cd_conj(i10), y0[1]));
+    hn[1] = cd_scale(y0[1], i11);
+    // normalise: h / floor(sqrt(max(Re h^H G h, 0)))
+    auto quad = [](const cd* G, const cd* h) {
+      cd t0 = cd_add(cd_mul(G[0], h[0]), cd_mul(G[1], h[1]));
+      cd t1 = cd_add(cd_mul(G[2], h[0]), cd_mul(G[3], h[1]));
+      return cd_mulc(t0, h[0]).x + cd_mulc(t1, h[1]).x;
+    };
+    const double dm = ssb_floor(sqrt(fmax(quad(Gm, hm), 0.0)), flooring, eps);
+    const double dn = ssb_floor(sqrt(fmax(quad(Gn, hn), 0.0)), flooring, eps);
+    hm[0] = cd_scale(hm[0], 1.0 / dm);
+    hm[1] = cd_scale(hm[1], 1.0 / dm);
+    hn[0] = cd_scale(hn[0], 1.0 / dn);
+    hn[1] = cd_scale(hn[1], 1.0 / dn);
+    __syncwarp();
+    if (lane < N) {
+      cd wm = cd_add(cd_mul(Pm[lane * 2], hm[0]), cd_mul(Pm[lane * 2 + 1], hm[1]));
+      cd wn = cd_add(cd_mul(Pn[lane * 2], hn[0]), cd_mul(Pn[lane * 2 + 1], hn[1]));
+      w[m * N + lane] = cd_conj(wm);
+      w[n * N + lane] = cd_conj(wn);
+    }
+  }
+  __syncwarp();
+  for (int e = lane; e < N * N; e += 32) W[(size_t)mat * N * N + e] = cd2cf(w[e]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// ISS1 (ssspy/bss/_update_spatial_model.py:181-192).  One warp per (b,i), in place on Y; each of the
+// N sequential steps reads the bin's slab twice (statistics, then rank-1 update).
+template <int N>
+__global__ void __launch_bounds__(WPB * 32) k_iss1(cf* __restrict__ Y, const float* __restrict__ phi,
+                                                   long long sb, long long sn, long long si, int B, int I,
+                                                   int J, int flooring, float eps) {
+  const int warp = blockIdx.x * WPB + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (warp >= B * I) return;
+  const int b = warp / I, i = warp - b * I;
+  const size_t base = ((size_t)b * N * I + i) * J;
+  const size_t cs = (size_t)I * J;
+  const float* ph0 = phi + (size_t)b * sb + (size_t)i * si;
+  const float invJ = 1.0f / (float)J;
+  for (int n = 0; n < N; ++n) {
+    float nr[N], ni[N], dn[N];
+#pragma unroll
+    for (int m = 0; m < N; ++m) nr[m] = ni[m] = dn[m] = 0.f;
+    for (int j = lane; j < J; j += 32) {
+      cf yn = Y[base + n * cs + j];
+      float a2 = yn.x * yn.x + yn.y * yn.y;
+#pragma unroll
+      for (int m = 0; m < N; ++m) {
+        float ph = ph0[(size_t)m * sn + j];
+        cf ym = Y[base + m * cs + j];
+        float pr = ph * ym.x, pi = ph * ym.y;
+        nr[m] = fmaf(pr, yn.x, fmaf(pi, yn.y, nr[m]));   // Re(ph ym conj(yn))
+        ni[m] = fmaf(pi, yn.x, fmaf(-pr, yn.y, ni[m]));  // Im
+        dn[m] = fmaf(ph, a2, dn[m]);
+      }
+    }
+    cf v[N];
+#pragma unroll
+    for (int m = 0; m < N; ++m) {
+      float r_ = warp_sum(nr[m]) * invJ, i_ = warp_sum(ni[m]) * invJ;
+      float d_ = ssb_floor(warp_sum(dn[m]) * invJ, flooring, eps);
+      if (m == n)
+        v[m] = make_float2(1.0f - 1.0f / sqrtf(d_), 0.f);
+      else
+        v[m] = make_float2(r_ / d_, i_ / d_);
+    }
+    for (int j = lane; j < J; j += 32) {
+      cf yn = Y[base + n * cs + j];
+#pragma unroll
+      for (int m = 0; m < N; ++m) {
+        cf ym = Y[base + m * cs + j];
+        ym.x -= v[m].x * yn.x - v[m].y * yn.y;
+        ym.y -= v[m].x * yn.y + v[m].y * yn.x;
+        Y[base + m * cs + j] = ym;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// projection back, filter form (ssspy/algorithm/projection_back.py:87-99): one warp per matrix.
+// scale_out[mat*N + n] (optional) receives (W^-1)[ref, n] for the projection-back normalisation.
+template <int N>
+__global__ void __launch_bounds__(WPB * 32) k_pb_w(const cf* __restrict__ W, cf* __restrict__ Wout,
+                                                   cf* __restrict__ scale_out, int n_mat, int ref) {
+  __shared__ cd sA[WPB][N * 2 * N];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mat = blockIdx.x * WPB + wib;
+  if (mat >= n_mat) return;
+  cd* A = sA[wib];
+  for (int e = lane; e < N * 2 * N; e += 32) {
+    int r = e / (2 * N), c = e - r * 2 * N;
+    A[e] = c < N ? cf2cd(W[(size_t)mat * N * N + r * N + c]) : cd_make(c - N == r ? 1.0 : 0.0, 0);
+  }
+  __syncwarp();
+  warp_gauss_jordan(A, N, N, 2 * N, lane);
+  // scale[n] = Winv[ref][n] = A[ref][N + n]
+  for (int e = lane; e < N * N; e += 32) {
+    int n = e / N;
+    cd s = A[ref * 2 * N + N + n];
+    cd wv = cf2cd(W[(size_t)mat * N * N + e]);
+    Wout[(size_t)mat * N * N + e] = cd2cf(cd_mul(wv, s));
+  }
+  if (scale_out && lane < N) scale_out[(size_t)mat * N + lane] = cd2cf(A[ref * 2 * N + N + lane]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// cross-solve  S[b,i] = (A_i Bm_i^H) (Bm_i Bm_i^H)^-1  with A_i, Bm_i the (N x J) slabs of bin i.
+//   projection back, spectrogram form: A = X, Bm = Y (projection_back.py:104-110)
+//   W recovery for the ISS-mode loss:  A = Y, Bm = X (ilrma.py:1939-1944, iva.py:2180-2185)
+// One warp per (b,i); N+1 passes over the slab (Gram matrix, then one row of A Bm^H per pass).
+template <int N>
+__global__ void __launch_bounds__(WPB * 32) k_cross_solve(const cf* __restrict__ Am, const cf* __restrict__ Bm,
+                                                          cf* __restrict__ S, int B, int I, int J) {
+  __shared__ cd sG[WPB][N * 2 * N];  // [Gram | I] -> Gram^-1
+  __shared__ cd sC[WPB][N * N];      // A Bm^H
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = blockIdx.x * WPB + wib;
+  if (warp >= B * I) return;
+  const int b = warp / I, i = warp - b * I;
+  const size_t base = ((size_t)b * N * I + i) * J;
+  const size_t cs = (size_t)I * J;
+  cd* G = sG[wib];
+  cd* C = sC[wib];
+  {
+    float acc[N * N];
+#pragma unroll
+    for (int e = 0; e < N * N; ++e) acc[e] = 0.f;
+    for (int j = lane; j < J; j += 32) {
+      cf x[N];
+#pragma unroll
+      for (int m = 0; m < N; ++m) x[m] = Bm[base + m * cs + j];
+#pragma unroll
+      for (int a = 0; a < N; ++a) {
+        acc[a * N + a] = fmaf(x[a].x, x[a].x, fmaf(x[a].y, x[a].y, acc[a * N + a]));
+#pragma unroll
+        for (int c = a + 1; c < N; ++c) {
+          acc[a * N + c] = fmaf(x[a].x, x[c].x, fmaf(x[a].y, x[c].y, acc[a * N + c]));
+          acc[c * N + a] = fmaf(x[a].y, x[c].x, fmaf(-x[a].x, x[c].y, acc[c * N + a]));
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < N * N; ++e) acc[e] = warp_sum(acc[e]);
+    if (lane == 0) {
+#pragma unroll
+      for (int a = 0; a < N; ++a) {
+#pragma unroll
+        for (int c = 0; c < N; ++c) {
+          cd v;
+          if (a == c) v = cd_make(acc[a * N + a], 0);
+          else if (a < c) v = cd_make(acc[a * N + c], acc[c * N + a]);
+          else v = cd_make(acc[c * N + a], -acc[a * N + c]);
+          G[a * 2 * N + c] = v;
+          G[a * 2 * N + N + c] = cd_make(a == c ? 1.0 : 0.0, 0);
+        }
+      }
+    }
+  }
+  for (int r = 0; r < N; ++r) {
+    float cr[N], ci[N];
+#pragma unroll
+    for (int m = 0; m < N; ++m) cr[m] = ci[m] = 0.f;
+    for (int j = lane; j < J; j += 32) {
+      cf a = Am[base + r * cs + j];
+#pragma unroll
+      for (int m = 0; m < N; ++m) {
+        cf x = Bm[base + m * cs + j];
+        cr[m] = fmaf(a.x, x.x, fmaf(a.y, x.y, cr[m]));
+        ci[m] = fmaf(a.y, x.x, fmaf(-a.x, x.y, ci[m]));
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < N; ++m) {
+      float vr = warp_sum(cr[m]), vi = warp_sum(ci[m]);
+      if (lane == 0) C[r * N + m] = cd_make(vr, vi);
+    }
+  }
+  __syncwarp();
+  warp_gauss_jordan(G, N, N, 2 * N, lane);
+  for (int e = lane; e < N * N; e += 32) {
+    int r = e / N, c = e - r * N;
+    cd s = cd_make(0, 0);
+#pragma unroll
+    for (int k = 0; k < N; ++k) s = cd_fma(C[r * N + k], G[k * 2 * N + N + c], s);
+    S[(size_t)warp * N * N + e] = cd2cf(s);
+  }
+}
+
+// Yout[b,n,i,:] = Y[b,n,i,:] * S[b,i,ref,n]      (projection_back.py:117-119)
+__global__ void k_scale_rows(const cf* __restrict__ Y, const cf* __restrict__ S, cf* __restrict__ Yout, int N,
+                             int I, int J, int ref) {
+  const int row = blockIdx.x;  // (b, n, i)
+  const int i = row % I;
+  const int n = (row / I) % N;
+  const int b = row / (I * N);
+  const cf s = S[(((size_t)b * I + i) * N + ref) * N + n];
+  const size_t base = (size_t)row * J;
+  for (int j = threadIdx.x; j < J; j += blockDim.x) {
+    cf y = Y[base + j];
+    Yout[base + j] = make_float2(y.x * s.x - y.y * s.y, y.x * s.y + y.y * s.x);
+  }
+}
+
+// log|det W| per matrix (np.linalg.slogdet call sites ilrma.py:534, iva.py:234); one warp per matrix.
+template <int N>
+__global__ void __launch_bounds__(WPB * 32) k_logdet(const cf* __restrict__ W, double* __restrict__ out,
+                                                     int n_mat) {
+  __shared__ cd sA[WPB][N * N];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mat = blockIdx.x * WPB + wib;
+  if (mat >= n_mat) return;
+  cd* A = sA[wib];
+  for (int e = lane; e < N * N; e += 32) A[e] = cf2cd(W[(size_t)mat * N * N + e]);
+  __syncwarp();
+  double lad;
+  warp_gauss_jordan(A, N, 0, N, lane, &lad);
+  if (lane == 0) out[mat] = lad;
+}
+
+}  // namespace
+
+
+int ssbk_separate(const cf* X, const cf* W, cf* Y, float* P, int B, int N, int I, int J, cudaStream_t st) {
+  SSB_DISPATCH_N(N, k_separate<NN><<<B * I, 128, 0, st>>>(X, W, Y, P, I, J));
+  return ssb_check_launch("separate", st);
+}
+
+int ssbk_abs2(const cf* Y, float* P, size_t n, cudaStream_t st) {
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  k_abs2<<<blocks, 256, 0, st>>>(Y, P, n);
+  return ssb_check_launch("abs2", st);
+}
+
+int ssbk_wcov(const cf* X, const float* phi, long long sb, long long sn, long long si, const int* src, int n_src,
+              cf* U, int B, int N, int I, int J, cudaStream_t st) {
+  SSB_REQUIRE(n_src >= 1 && n_src <= SSB_MAX_SOURCES, "weighted_covariance: n_src=%d out of range", n_src);
+  SrcList sl;
+  sl.n = n_src;
+  for (int s = 0; s < n_src; ++s) sl.idx[s] = src ? src[s] : s;
+  SSB_DISPATCH_N(N, k_wcov<NN><<<blocks_for((long long)B * I, WPB), WPB * 32, 0, st>>>(X, phi, sb, sn, si, sl, U,
+                                                                                           B, I, J));
+  return ssb_check_launch("weighted_covariance", st);
+}
+
+int ssbk_ip1(cf* W, const cf* U, int n_mat, int N, int flooring, float eps, cudaStream_t st) {
+  SSB_DISPATCH_N(N, k_ip1<NN><<<blocks_for(n_mat, WPB), WPB * 32, 0, st>>>(W, U, n_mat, flooring, (double)eps));
+  return ssb_check_launch("update_by_ip1", st);
+}
+
+int ssbk_ip2(cf* W, const cf* U, int n_mat, int N, const int* pairs, int n_pairs, int n_u, const int* uidx,
+             int flooring, float eps, cudaStream_t st) {
+  SSB_REQUIRE(n_pairs >= 0 && n_pairs <= SSB_MAX_PAIRS, "update_by_ip2: n_pairs=%d exceeds %d", n_pairs,
+              SSB_MAX_PAIRS);
+  PairList pl;
+  pl.n = n_pairs;
+  pl.n_u = n_u;
+  for (int q = 0; q < n_pairs; ++q) {
+    int m = pairs[2 * q], n = pairs[2 * q + 1];
+    SSB_REQUIRE(m >= 0 && m < N && n >= 0 && n < N && m != n, "update_by_ip2: invalid pair (%d, %d) for N=%d", m, n, N);
+    pl.m[q] = (short)m;
+    pl.nn[q] = (short)n;
+    pl.um[q] = (short)(uidx ? uidx[2 * q] : m);
+    pl.un[q] = (short)(uidx ? uidx[2 * q + 1] : n);
+  }
+  if (n_pairs == 0) return 0;
+  SSB_DISPATCH_N(N, k_ip2<NN><<<blocks_for(n_mat, WPB), WPB * 32, 0, st>>>(W, U, n_mat, pl, flooring, (double)eps));
+  return ssb_check_launch("update_by_ip2", st);
+}
+
+int ssbk_iss1(cf* Y, const float* phi, long long sb, long long sn, long long si, int B, int N, int I, int J,
+              int flooring, float eps, cudaStream_t st) {
+  SSB_DISPATCH_N(N, k_iss1<NN><<<blocks_for((long long)B * I, WPB), WPB * 32, 0, st>>>(Y, phi, sb, sn, si, B, I, J,
+                                                                                           flooring, eps));
+  return ssb_check_launch("update_by_iss1", st);
+}
+
+int ssbk_pb_w(const cf* W, cf* Wout, cf* scale_out, int n_mat, int N, int ref, cudaStream_t st) {
+  SSB_REQUIRE(ref >= 0 && ref < N, "projection_back: reference_id=%d out of range for N=%d", ref, N);
+  SSB_DISPATCH_N(N, k_pb_w<NN><<<blocks_for(n_mat, WPB), WPB * 32, 0, st>>>(W, Wout, scale_out, n_mat, ref));
+  return ssb_check_launch("projection_back_w", st);
+}
+
+int ssbk_cross_solve(const cf* A, const cf* Bm, cf* S, int B, int N, int I, int J, cudaStream_t st) {
+  SSB_DISPATCH_N(N, k_cross_solve<NN><<<blocks_for((long long)B * I, WPB), WPB * 32, 0, st>>>(A, Bm, S, B, I, J));
+  return ssb_check_launch("cross_solve", st);
+}
+
+int ssbk_scale_rows(const cf* Y, const cf* S, cf* Yout, int B, int N, int I, int J, int ref, cudaStream_t st) {
+  SSB_REQUIRE(ref >= 0 && ref < N, "projection_back: reference_id=%d out of range for N=%d", ref, N);
+  k_scale_rows<<<B * N * I, 128, 0, st>>>(Y, S, Yout, N, I, J, ref);
+  return ssb_check_launch("scale_rows", st);
+}
+
+int ssbk_logdet(const cf* W, double* out, int n_mat, int N, cudaStream_t st) {
+  SSB_DISPATCH_N(N, k_logdet<NN><<<blocks_for(n_mat, WPB), WPB * 32, 0, st>>>(W, out, n_mat));
+  return ssb_check_launch("logdet", st);
+}

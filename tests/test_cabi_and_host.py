@@ -1,0 +1,124 @@
+"""CPU-only tests: the C-ABI library loads and exports every symbol include/ssb.h declares, the
+product path fails loudly without a GPU, and the host-side logic (flooring mapping, pair schedules)
+is exact."""
+import ctypes
+import functools
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from ssspy_b200 import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "ssb.h")).read()
+    declared = set(re.findall(r"\b(ssb_[a-z0-9_]+)\s*\(", header))
+    declared -= {"ssb_config", "ssb_plan"}
+    assert len(declared) >= 25
+    for name in sorted(declared):
+        assert hasattr(lib, name), "libssb.so does not export " + name
+    # the ctypes table covers the header
+    missing = declared - set(_lib.SIGNATURES) - {"ssb_last_error"}
+    assert not missing, "no ctypes signature for {}".format(missing)
+    assert lib.ssb_version() == 100
+
+
+def test_config_struct_layout_matches_header():
+    from ssspy_b200 import _lib
+    # 14 int32/float scalars + 128 pair slots + fast_path
+    assert ctypes.sizeof(_lib.SsbConfig) == 4 * (14 + 2 * _lib.SSB_MAX_PAIRS + 1)
+
+
+def test_plan_validation_runs_without_gpu():
+    from ssspy_b200 import _lib
+    cfg = _lib.SsbConfig()
+    cfg.model, cfg.spatial, cfg.n_batch, cfg.n_sources, cfg.n_bins, cfg.n_frames, cfg.n_basis = 0, 0, 1, 9, 4, 4, 2
+    cfg.domain, cfg.normalization = 2.0, 1
+    plan = ctypes.c_void_p()
+    with pytest.raises(_lib.SsbError, match="n_sources=9 unsupported"):
+        _lib.call("ssb_plan_create", ctypes.byref(cfg), ctypes.byref(plan))
+    cfg.n_sources, cfg.source, cfg.domain = 2, 1, 1.0
+    with pytest.raises(_lib.SsbError, match="domain parameter should be 2"):
+        _lib.call("ssb_plan_create", ctypes.byref(cfg), ctypes.byref(plan))
+    cfg.source, cfg.domain = 0, 2.0
+    _lib.call("ssb_plan_create", ctypes.byref(cfg), ctypes.byref(plan))
+    nbytes = ctypes.c_size_t(0)
+    _lib.call("ssb_plan_workspace_bytes", plan, ctypes.byref(nbytes))
+    assert nbytes.value > 0
+    with pytest.raises(_lib.SsbError, match="no buffers bound"):
+        _lib.call("ssb_update_once", plan, None)
+    _lib.call("ssb_plan_destroy", plan)
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from ssspy_b200.bss import AuxLaplaceIVA, GaussILRMA
+    from ssspy_b200.linalg import inv2
+    X = np.zeros((2, 5, 6), dtype=complex)
+    for fn in (lambda: GaussILRMA(n_basis=2)(X, n_iter=1), lambda: AuxLaplaceIVA()(X, n_iter=1),
+               lambda: inv2(np.eye(2)[None])):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            fn()
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "ssspy_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f + " imports the oracle"
+
+
+def test_flooring_mapping():
+    from ssspy_b200 import _lib
+    from ssspy_b200.special.flooring import add_flooring, identity, max_flooring
+    from ssspy_b200.utils.flooring import choose_flooring_fn, flooring_to_enum
+    assert flooring_to_enum(functools.partial(max_flooring, eps=1e-10)) == (_lib.FLOOR_MAX, 1e-10)
+    assert flooring_to_enum(max_flooring) == (_lib.FLOOR_MAX, 1e-10)
+    assert flooring_to_enum(functools.partial(add_flooring, eps=1e-3)) == (_lib.FLOOR_ADD, 1e-3)
+    assert flooring_to_enum(identity) == (_lib.FLOOR_NONE, 0.0)
+    assert flooring_to_enum(None) == (_lib.FLOOR_NONE, 0.0)
+    with pytest.raises(NotImplementedError):
+        flooring_to_enum(lambda x: x)
+
+    class M:
+        flooring_fn = staticmethod(max_flooring)
+    assert choose_flooring_fn("self", method=M()) is max_flooring
+    assert choose_flooring_fn(None) is identity
+    np.testing.assert_array_equal(max_flooring(np.array([0.0, 1.0])), [1e-10, 1.0])
+    np.testing.assert_array_equal(add_flooring(np.array([0.0, 1.0]), eps=0.5), [0.5, 1.5])
+
+
+def test_pair_selectors_bit_exact():
+    """ssspy/utils/select_pair.py:35-44,:72-76; tests/package/utils/test_select_pair.py."""
+    from ssspy_b200.utils.select_pair import combination_pair_selector, sequential_pair_selector, wrap_pairs
+    assert list(sequential_pair_selector(2)) == [(0, 1), (1, 0)]
+    assert list(sequential_pair_selector(4)) == [(0, 1), (1, 2), (2, 3), (3, 0)]
+    assert list(sequential_pair_selector(4, sort=True)) == [(0, 1), (1, 2), (2, 3), (0, 3)]
+    assert list(sequential_pair_selector(5, step=2)) == [(0, 1), (2, 3), (4, 0)]
+    assert list(sequential_pair_selector(3, stop=5)) == [(0, 1), (1, 2), (2, 0), (0, 1), (1, 2)]
+    assert list(combination_pair_selector(3)) == [(0, 1), (0, 2), (1, 2)]
+    assert all(m < n for m, n in combination_pair_selector(5, sort=True))
+    assert wrap_pairs([(-3, -2), (-1, 0)], 3) == [(0, 1), (2, 0)]
+    with pytest.raises(IndexError):
+        wrap_pairs([(0, 3)], 3)
+    from oracle.spatial import sequential_pairs
+    for n in range(2, 9):
+        assert list(sequential_pair_selector(n)) == sequential_pairs(n)
+
+
+def test_shard_range_partition():
+    from ssspy_b200.parallel import shard_range
+    for B in (1, 7, 64, 512):
+        for G in (1, 2, 3, 8):
+            spans = [shard_range(B, r, G) for r in range(G)]
+            assert spans[0][0] == 0 and spans[-1][1] == B
+            assert all(spans[r][1] == spans[r + 1][0] for r in range(G - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1

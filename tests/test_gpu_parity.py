@@ -1,0 +1,331 @@
+"""GPU parity tests: the CUDA path (through the separator classes -> ctypes -> libssb.so) against
+(1) the committed golden vectors produced by the unmodified reference and (2) the fp64 oracle on the
+same seeded inputs.  Tolerances (fp64 reference -> fp32 device state), per BASELINE.json north_star
+and SURVEY.md 8(c): Y (after projection back) rel-Frobenius <= 1e-4, T / V rel <= 1e-4, loss
+trajectory rel <= 1e-5 (+ 1e-4 absolute for values near zero), pair lists / shapes exact.
+"""
+import functools
+import itertools
+
+import numpy as np
+import pytest
+
+from helpers import FLOORS, golden_cases, load, norm_arg, phase_align_rows, relerr
+
+pytestmark = pytest.mark.gpu
+
+TOL_Y = 1e-4
+TOL_TV = 1e-4
+
+
+def _floor_fn(name):
+    from ssspy_b200.special.flooring import add_flooring, max_flooring
+    return {"max": functools.partial(max_flooring, eps=1e-10), "add": functools.partial(add_flooring, eps=1e-10),
+            "none": None}[name]
+
+
+def _pair_selector(pairs):
+    pairs = [tuple(int(v) for v in p) for p in pairs]
+    return lambda n: iter(pairs)
+
+
+def assert_loss_close(got, want):
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("name", golden_cases("ilrma_"))
+def test_gauss_ilrma_matches_reference(name):
+    from ssspy_b200.bss import GaussILRMA
+    g = load(name)
+    ref_id = None if int(g["reference_id"]) < 0 else int(g["reference_id"])
+    kwargs = dict(basis=g["T0"], activation=g["V0"])
+    if "W0" in g:
+        kwargs["demix_filter"] = g["W0"]
+    spatial = str(g["spatial"])
+    m = GaussILRMA(n_basis=g["T0"].shape[-1], spatial_algorithm=spatial, source_algorithm=str(g["source"]),
+                   domain=float(g["domain"]), flooring_fn=_floor_fn(str(g["flooring"])),
+                   pair_selector=_pair_selector(g["pairs"]) if spatial == "IP2" else None,
+                   normalization=norm_arg(g["normalization"]), scale_restoration=bool(g["scale_restoration"]),
+                   record_loss=True, reference_id=ref_id, rng=np.random.default_rng(0))
+    Y = m(g["X"], n_iter=int(g["n_iter"]), **kwargs)
+    assert Y.shape == g["Y"].shape and Y.dtype == np.complex128
+    assert type(m.loss[-1]) is float and len(m.loss) == int(g["n_iter"]) + 1
+    assert_loss_close(m.loss, g["loss"])
+    if bool(g["scale_restoration"]) or spatial != "IP2":
+        assert relerr(Y, g["Y"]) < TOL_Y
+    else:
+        assert relerr(np.abs(Y), np.abs(g["Y"])) < TOL_Y
+    assert relerr(m.basis, g["T"]) < TOL_TV
+    assert relerr(m.activation, g["V"]) < TOL_TV
+    if "W" in g:
+        W = m.demix_filter
+        assert relerr(phase_align_rows(W, g["W"]) if spatial == "IP2" else W, g["W"]) < TOL_Y
+    else:
+        assert m.demix_filter is None
+
+
+@pytest.mark.parametrize("name", golden_cases("iva_"))
+def test_aux_iva_matches_reference(name):
+    from ssspy_b200.bss import AuxGaussIVA, AuxLaplaceIVA
+    g = load(name)
+    spatial = str(g["spatial"])
+    cls = AuxLaplaceIVA if str(g["model"]) == "laplace" else AuxGaussIVA
+    kwargs = {"demix_filter": g["W0"]} if "W0" in g else {}
+    m = cls(spatial_algorithm=spatial, flooring_fn=_floor_fn(str(g["flooring"])),
+            pair_selector=_pair_selector(g["pairs"]) if spatial == "IP2" else None,
+            scale_restoration=bool(g["scale_restoration"]), record_loss=True, reference_id=int(g["reference_id"]))
+    Y = m(g["X"], n_iter=int(g["n_iter"]), **kwargs)
+    assert Y.shape == g["Y"].shape
+    assert_loss_close(m.loss, g["loss"])
+    assert relerr(Y, g["Y"]) < TOL_Y
+    if "W" in g:
+        W = m.demix_filter
+        assert relerr(phase_align_rows(W, g["W"]) if spatial == "IP2" else W, g["W"]) < TOL_Y
+    else:
+        assert m.demix_filter is None
+    if "variance" in g:
+        assert relerr(m.variance, g["variance"]) < TOL_TV
+
+
+@pytest.mark.parametrize("N", [2, 3, 4])
+def test_spatial_operators_match_reference(N):
+    """update_by_ip1 / ip2 / ip2_one_pair / iss1 on the reference's own smoke-test shapes
+    (tests/package/bss/test_update_spatial_model.py:45-171), incl. negative pair indices."""
+    from ssspy_b200.bss._update_spatial_model import (update_by_ip1, update_by_ip2, update_by_ip2_one_pair,
+                                                     update_by_iss1)
+    from ssspy_b200.utils.select_pair import combination_pair_selector
+    g = load("spatial_kernels")
+    X, phi, W, U = (g[f"N{N}_{k}"] for k in ("X", "phi", "W", "U"))
+    Y = np.einsum("inm,mij->nij", W, X)
+    for fl in ("max", "add", "none"):
+        out = update_by_ip1(W, U, flooring_fn=_floor_fn(fl), overwrite=False)
+        assert out.shape == W.shape and relerr(out, g[f"N{N}_ip1_{fl}"]) < 1e-5
+        out = update_by_ip2(W, U, flooring_fn=_floor_fn(fl), overwrite=False)
+        assert relerr(phase_align_rows(out, g[f"N{N}_ip2_{fl}"]), g[f"N{N}_ip2_{fl}"]) < 1e-5
+        out = update_by_iss1(Y, phi, flooring_fn=_floor_fn(fl))
+        assert out.shape == Y.shape and relerr(out, g[f"N{N}_iss1_{fl}"]) < 1e-5
+
+    def neg_sel(n):
+        for m in range(n):
+            yield m - n, (m + 1) % n - n
+    out = update_by_ip2(W, U, pair_selector=neg_sel, overwrite=False)
+    assert relerr(phase_align_rows(out, g[f"N{N}_ip2_negpairs"]), g[f"N{N}_ip2_negpairs"]) < 1e-5
+    out = update_by_ip2(W, U, pair_selector=combination_pair_selector, overwrite=False)
+    assert relerr(phase_align_rows(out, g[f"N{N}_ip2_comb"]), g[f"N{N}_ip2_comb"]) < 1e-5
+    out = update_by_ip2_one_pair(W, U[:, (0, 1)], pair=(0, 1))
+    assert out.shape == (W.shape[0], 2, N)
+    assert relerr(phase_align_rows(out, g[f"N{N}_ip2pair01"]), g[f"N{N}_ip2pair01"]) < 1e-5
+    # overwrite=True mutates the argument, as the reference does (_update_spatial_model.py:51-54)
+    W2 = W.copy()
+    ret = update_by_ip1(W2, U)
+    assert ret is W2 and relerr(W2, g[f"N{N}_ip1_max"]) < 1e-5
+
+
+def test_linalg_known_answers_and_identities():
+    """ssspy/linalg docstring known answers + the reference's property tests
+    (tests/package/linalg/test_eigh.py:13-130, test_inv.py:9-18)."""
+    from ssspy_b200.linalg import eigh, eigh2, inv2, solve
+    g = load("linalg")
+    np.testing.assert_allclose(inv2(g["inv2_in"]), g["inv2_out"], atol=1e-12)
+    A, B = g["eigh2_A"], g["eigh2_B"]
+    lam, z = eigh2(A)
+    np.testing.assert_allclose(lam, [-0.23606798, 4.23606798], atol=1e-8)
+    np.testing.assert_allclose(A @ z, lam * z, atol=1e-10)
+    for t in (1, 2, 3):
+        lam, z = eigh2(A, B, type=t)
+        np.testing.assert_allclose(lam, g[f"eigh2_lamb_t{t}"], atol=1e-10)
+        lhs = {1: A @ z, 2: A @ B @ z, 3: B @ A @ z}[t]
+        rhs = {1: lam * (B @ z), 2: lam * z, 3: lam * z}[t]
+        np.testing.assert_allclose(lhs, rhs, atol=1e-9)
+    for n in (2, 3, 4, 8):
+        a, rhs, Ah, Bh = g[f"n{n}_a"], g[f"n{n}_rhs"], g[f"n{n}_A"], g[f"n{n}_B"]
+        assert relerr(solve(a, rhs), g[f"n{n}_solve"]) < 1e-10
+        from ssspy_b200.linalg import inv
+        assert relerr(inv(a), g[f"n{n}_inv"]) < 1e-10
+        lam, z = eigh(Ah)
+        np.testing.assert_allclose(lam, g[f"n{n}_lamb_std"], rtol=1e-9, atol=1e-9)
+        assert relerr(Ah @ z, z * lam[:, None, :]) < 1e-9
+        for t in (1, 2, 3):
+            lam, z = eigh(Ah, Bh, type=t)
+            np.testing.assert_allclose(lam, g[f"n{n}_lamb_t{t}"], rtol=1e-9)
+            lhs = {1: Ah @ z, 2: Ah @ Bh @ z, 3: Bh @ Ah @ z}[t]
+            rhs_ = {1: (Bh @ z) * lam[:, None, :], 2: z * lam[:, None, :], 3: z * lam[:, None, :]}[t]
+            assert relerr(lhs, rhs_) < 1e-8
+    # real symmetric input stays real (tests/package/linalg/test_eigh.py real cases)
+    rng = np.random.default_rng(111)
+    a = rng.standard_normal((5, 3, 3))
+    S = a @ a.transpose(0, 2, 1)
+    lam, z = eigh(S)
+    assert not np.iscomplexobj(z)
+    assert relerr(S @ z, z * lam[:, None, :]) < 1e-9
+    with pytest.raises(ValueError):
+        eigh(S, S + 3 * np.eye(3), type=4)
+
+
+def test_projection_back_matches_reference():
+    from ssspy_b200.algorithm import projection_back
+    g = load("linalg")
+    for n in (2, 3, 4, 8):
+        a = g[f"n{n}_a"]
+        for ref, key in ((0, "ref0"), (1, "ref1"), (None, "refnone")):
+            out = projection_back(a, reference_id=ref)
+            assert out.shape == g[f"n{n}_pb_w_{key}"].shape
+            assert relerr(out, g[f"n{n}_pb_w_{key}"]) < 1e-5
+    for ref, key in ((0, "ref0"), (2, "ref2"), (None, "refnone")):
+        out = projection_back(g["pb_Y"], reference=g["pb_X"], reference_id=ref)
+        assert out.shape == g[f"pb_y_{key}"].shape
+        assert relerr(out, g[f"pb_y_{key}"]) < 1e-5
+
+
+@pytest.mark.parametrize("spatial", ["IP", "IP2", "ISS"])
+def test_batched_input_equals_per_mixture_oracle(spatial):
+    """Extension: (B, N, I, J) input = B independent mixtures; each must match the oracle run alone."""
+    from oracle import ilrma as oilrma
+    from ssspy_b200.bss import GaussILRMA
+    from ssspy_b200.utils.synth import make_batch, make_nmf_init
+    B, N, I, J, K, n_iter = 3, 3, 19, 37, 5, 6
+    X = make_batch(B, N, I, J, config_id=7, mode="mix")
+    TV = [make_nmf_init(N, I, J, K, seed=50 + b) for b in range(B)]
+    T = np.stack([t for t, _ in TV])
+    V = np.stack([v for _, v in TV])
+    m = GaussILRMA(n_basis=K, spatial_algorithm=spatial)
+    Y = m(X, n_iter=n_iter, basis=T, activation=V)
+    assert Y.shape == X.shape and np.asarray(m.loss).shape == (n_iter + 1, B)
+    for b in range(B):
+        st = oilrma.run(X[b], T[b], V[b], n_iter, spatial_algorithm=spatial)
+        assert relerr(Y[b], st["Y"]) < TOL_Y
+        assert_loss_close(np.asarray(m.loss)[:, b], st["loss"])
+        assert relerr(m.basis[b], st["T"]) < TOL_TV
+
+
+def test_rng_initialisation_order_matches_reference():
+    """T then V drawn from the caller's Generator (ssspy/bss/ilrma.py:256-268)."""
+    from oracle import ilrma as oilrma
+    from ssspy_b200.bss import GaussILRMA
+    from ssspy_b200.utils.synth import make_mixture
+    N, I, J, K = 2, 21, 30, 3
+    X = make_mixture(N, I, J, seed=3)
+    m = GaussILRMA(n_basis=K, rng=np.random.default_rng(123))
+    Y = m(X, n_iter=4)
+    rng = np.random.default_rng(123)
+    T = rng.random((N, I, K))
+    V = rng.random((N, K, J))
+    st = oilrma.run(X, T, V, 4)
+    assert relerr(Y, st["Y"]) < TOL_Y
+
+
+def test_callbacks_overrides_and_warm_start():
+    """base.py:48-77 semantics: callbacks before the loop and after each iteration see live state;
+    update_once stays overridable; a second call warm-starts and keeps appending to loss
+    (SURVEY.md 8(b) quirk 1)."""
+    from oracle import ilrma as oilrma
+    from ssspy_b200.bss import GaussILRMA
+    from ssspy_b200.utils.synth import make_mixture, make_nmf_init
+    N, I, J, K = 2, 17, 29, 4
+    X = make_mixture(N, I, J, seed=11)
+    T, V = make_nmf_init(N, I, J, K, seed=1)
+    seen = []
+
+    def cb(sep):
+        seen.append((sep.demix_filter.copy(), sep.basis.copy(), len(sep.loss)))
+
+    class Counting(GaussILRMA):
+        calls = 0
+
+        def update_once(self, flooring_fn="self"):
+            type(self).calls += 1
+            super().update_once(flooring_fn=flooring_fn)
+
+    m = Counting(n_basis=K, callbacks=cb)
+    Y = m(X, n_iter=3, basis=T, activation=V)
+    assert Counting.calls == 3 and len(seen) == 4 and [s[2] for s in seen] == [1, 2, 3, 4]
+    st = oilrma.run(X, T, V, 3, snapshots=True)
+    assert relerr(Y, st["Y"]) < TOL_Y
+    assert relerr(seen[1][0], st["snapshots"][0]["W"]) < TOL_Y
+    assert relerr(seen[1][1], st["snapshots"][0]["T"]) < TOL_TV
+    m(X, n_iter=2)
+    assert len(m.loss) == 4 + 3
+    m2 = GaussILRMA(n_basis=K, record_loss=False)
+    m2(X, n_iter=2, basis=T, activation=V, initial_call=False)
+    assert m2.loss is None
+
+
+def test_manual_phase_calls_equal_update_once():
+    """update_source_model + update_spatial_model + normalize == update_once (ilrma.py:900-922)."""
+    from ssspy_b200.bss import GaussILRMA
+    from ssspy_b200.utils.synth import make_mixture, make_nmf_init
+    N, I, J, K = 3, 15, 33, 4
+    X = make_mixture(N, I, J, seed=21)
+    T, V = make_nmf_init(N, I, J, K, seed=2)
+    a = GaussILRMA(n_basis=K, scale_restoration=False)
+    Ya = a(X, n_iter=2, basis=T, activation=V)
+    b = GaussILRMA(n_basis=K, scale_restoration=False)
+    b(X, n_iter=0, basis=T, activation=V)
+    for _ in range(2):
+        b.update_source_model()
+        b.update_spatial_model()
+        b.normalize()
+    Yb = b.separate(b.input, b.demix_filter)
+    assert relerr(Yb, Ya) < 1e-6
+    assert abs(b.compute_loss() - a.loss[-1]) <= 1e-5 * abs(a.loss[-1])
+
+
+def test_cuda_tensor_io_is_zero_copy_and_matches_numpy():
+    import torch
+    from ssspy_b200.bss import AuxLaplaceIVA
+    from ssspy_b200.utils.synth import make_batch
+    X = make_batch(2, 2, 33, 40, config_id=1)
+    Xt = torch.from_numpy(X.astype(np.complex64)).cuda()
+    mt = AuxLaplaceIVA()
+    Yt = mt(Xt, n_iter=5)
+    assert isinstance(Yt, torch.Tensor) and Yt.is_cuda and Yt.shape == Xt.shape
+    assert mt._dX.data_ptr() == Xt.data_ptr()
+    Yn = AuxLaplaceIVA()(X, n_iter=5)
+    assert relerr(Yt.cpu().numpy(), Yn) < 1e-5
+
+
+def test_error_paths_match_reference():
+    from ssspy_b200.bss import AuxLaplaceIVA, GaussILRMA
+    with pytest.raises(AssertionError, match="Not support"):
+        GaussILRMA(n_basis=2, spatial_algorithm="XYZ")
+    with pytest.raises(AssertionError, match="domain parameter should be 2"):
+        GaussILRMA(n_basis=2, source_algorithm="ME", domain=1)
+    with pytest.raises(ValueError, match="Specify 'reference_id'"):
+        GaussILRMA(n_basis=2, reference_id=None)
+    with pytest.raises(NotImplementedError):
+        GaussILRMA(n_basis=2, spatial_algorithm="IPA")
+    X = np.random.default_rng(0).standard_normal((2, 9, 12)) + 0j
+    m = AuxLaplaceIVA(spatial_algorithm="ISS")
+    m(X, n_iter=1)
+    assert m.demix_filter is None
+    with pytest.raises(ValueError, match="matmul"):
+        m(X, n_iter=1)  # second call in ISS mode fails in the reference too
+
+
+@pytest.mark.parametrize("N,spatial", [(2, "IP"), (2, "IP2"), (4, "ISS")])
+def test_full_size_properties_and_one_mixture_oracle(N, spatial):
+    """BASELINE.json config-2 bin/frame sizes (I=1025, J=512, K=16): one mixture against the oracle
+    (2 iterations), and size-independent properties on a small batch: monotone loss, projection-back
+    idempotence, W X == Y."""
+    from oracle import ilrma as oilrma
+    from ssspy_b200.algorithm import projection_back
+    from ssspy_b200.bss import GaussILRMA
+    from ssspy_b200.utils.synth import make_batch, make_nmf_init
+    I, J, K, B = 1025, 512, 16, 2
+    X = make_batch(B, N, I, J, config_id=2, mode="mix")
+    T, V = make_nmf_init(N, I, J, K, seed=42)
+    m = GaussILRMA(n_basis=K, spatial_algorithm=spatial)
+    Y = m(X, n_iter=12, basis=T, activation=V)
+    loss = np.asarray(m.loss)
+    assert np.all(np.isfinite(loss)) and np.all(np.diff(loss, axis=0) <= 1e-6 * np.abs(loss[:-1]))
+    if m.demix_filter is not None:
+        W = m.demix_filter
+        assert relerr(np.einsum("binm,bmij->bnij", W, X), Y) < 1e-5
+        assert relerr(projection_back(W.astype(np.complex64), reference_id=0), W) < 1e-5  # idempotent
+    m1 = GaussILRMA(n_basis=K, spatial_algorithm=spatial)
+    Y1 = m1(X[0], n_iter=2, basis=T, activation=V)
+    st = oilrma.run(X[0], T, V, 2, spatial_algorithm=spatial)
+    assert relerr(Y1, st["Y"]) < TOL_Y
+    assert_loss_close(m1.loss, st["loss"])
