@@ -1,15 +1,636 @@
-// Fused sm_100a fast path of the GaussILRMA iteration -- placeholder until the tensor-core sweep
-// kernels land; every configuration currently takes the modular kernels.
-#include "ssb_fused.h"
+// Fused tensor-core path of the GaussILRMA iteration (source_algorithm="MM", domain=2, IP1/IP2).
+//
+// The K-contractions of the MM update (R = T V, num = A V^T, den = B V^T and their transposes,
+// ssspy/bss/ilrma.py:1116-1123, :1192-1199, :1494-1498) are GEMMs with a tiny inner/outer dimension
+// (K = n_basis).  On CUDA cores the iteration is FMA-bound at ~40x the HBM floor (profiles/
+// r1_bench_v1_modular.json); here they run on the tensor pipe as mma.sync.m16n8k16 bf16 with an
+// fp32 -> (hi, lo) bf16 split and three products (hi*hi + hi*lo + lo*hi, fp32 accumulate), which keeps
+// ~16 mantissa bits (measured final-Y error 2e-6 vs 7e-4 for plain bf16).  The
+// elementwise stage between the GEMMs (|y|^2, 1/R, P/R^2) stays in registers: the accumulator
+// fragment of the first GEMM is re-packed as the A operand of the second (no shared-memory round
+// trip), and X is read straight from global memory as 16-byte vectors.
+//
+//   kf_basis      : one warp = 16 bins x all frames of one (mixture, source):  T <- T sqrt(num/den)
+//   kf_activation : one warp = 16 frames x all bins of one (mixture, source):  V <- V sqrt(num/den)
+//                   (owns its V entries completely: no partial sums, no atomics, deterministic)
+//   kf_phi_cov    : one warp = 16 bins x all frames, all sources: phi = 1/(T V) on the tensor pipe,
+//                   U[b,i,n] = mean_j phi x x^H accumulated in registers
+//   kf_ip1_n2     : closed-form 2x2 IP1 (fp64), one thread per bin
+// followed by the modular normalisation kernels.  Operation order is exactly the reference's.
+#include <cuda_bf16.h>
 
+#include "ssb_fused.h"
+#include "ssb_kernels.h"
+
+namespace {
+
+constexpr int FW = 8;      // warps per CTA
+constexpr int JC = 256;    // frames of V staged in shared memory at a time
+constexpr int PADH = 8;    // bf16 padding of shared-memory rows (bank-conflict-free fragment loads)
+
+struct Split {
+  uint32_t hi, lo;
+};
+
+// (a -> low half, b -> high half): hi = truncated bf16 pair, lo = bf16(rn) of the exact residuals
+__device__ __forceinline__ Split split2(float a, float b) {
+  const uint32_t ua = __float_as_uint(a), ub = __float_as_uint(b);
+  Split s;
+  s.hi = __byte_perm(ua, ub, 0x7632);
+  const float ra = a - __uint_as_float(ua & 0xffff0000u);
+  const float rb = b - __uint_as_float(ub & 0xffff0000u);
+  __nv_bfloat162 l = __floats2bfloat162_rn(ra, rb);
+  s.lo = *reinterpret_cast<uint32_t*>(&l);
+  return s;
+}
+
+__device__ __forceinline__ void split1(float a, __nv_bfloat16* hi, __nv_bfloat16* lo) {
+  const uint32_t ua = __float_as_uint(a);
+  const unsigned short h = (unsigned short)(ua >> 16);
+  *reinterpret_cast<unsigned short*>(hi) = h;
+  *lo = __float2bfloat16_rn(a - __uint_as_float(ua & 0xffff0000u));
+}
+
+// D += A(16x16, row) * B(16x8, col), bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// 3-term split product: c += (ah + al) * (bh + bl) without the al*bl term
+__device__ __forceinline__ void mma_split(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                          uint32_t bh0, uint32_t bh1, uint32_t bl0, uint32_t bl1) {
+  mma16816(c, ah, bh0, bh1);
+  mma16816(c, ah, bl0, bl1);
+  mma16816(c, al, bh0, bh1);
+}
+
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+__device__ __forceinline__ uint32_t lds32(const __nv_bfloat16* p) { return *reinterpret_cast<const uint32_t*>(p); }
+
+// |sum_m w[m] x[m]|^2 for two consecutive frames held in a float4 per channel
+template <int N>
+__device__ __forceinline__ void power2(const float4 (&x)[N], const cf (&w)[N], float& p0, float& p1) {
+  float r0 = 0.f, i0 = 0.f, r1 = 0.f, i1 = 0.f;
+#pragma unroll
+  for (int m = 0; m < N; ++m) {
+    r0 = fmaf(w[m].x, x[m].x, fmaf(-w[m].y, x[m].y, r0));
+    i0 = fmaf(w[m].x, x[m].y, fmaf(w[m].y, x[m].x, i0));
+    r1 = fmaf(w[m].x, x[m].z, fmaf(-w[m].y, x[m].w, r1));
+    i1 = fmaf(w[m].x, x[m].w, fmaf(w[m].y, x[m].z, i1));
+  }
+  p0 = fmaf(r0, r0, i0 * i0);
+  p1 = fmaf(r1, r1, i1 * i1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// kf_basis.  CTA = (bin group of FW*16 bins, source n, mixture b); warp = 16 bins.
+// Fragment conventions (PTX m16n8k16): g = lane/4, t = lane%4;
+//   C: c0,c1 = (row g, cols 2t,2t+1), c2,c3 = (row g+8, same cols)
+//   A: a0 = (row g, k 2t..), a1 = (row g+8, k 2t..), a2 = (row g, k 2t+8..), a3 = (row g+8, k 2t+8..)
+//   B: b0 = (k 2t.., n g), b1 = (k 2t+8.., n g)
+// Two C tiles over frames [j0, j0+8) and [j0+8, j0+16) are exactly the A operand of the next MMA.
+template <int N, int KS>
+__global__ void __launch_bounds__(FW * 32) kf_basis(const cf* __restrict__ X, const cf* __restrict__ W,
+                                                    float* __restrict__ T, const float* __restrict__ V, int I, int J,
+                                                    int K, int flooring, float eps) {
+  constexpr int KP = 16 * KS;
+  constexpr int JKS = KP + PADH;   // row stride (halfs) of the [frame][basis] layout
+  constexpr int KJS = JC + PADH;   // row stride (halfs) of the [basis][frame] layout
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __nv_bfloat16* vjk_hi = reinterpret_cast<__nv_bfloat16*>(smem_raw);
+  __nv_bfloat16* vjk_lo = vjk_hi + JC * JKS;
+  __nv_bfloat16* vkj_hi = vjk_lo + JC * JKS;
+  __nv_bfloat16* vkj_lo = vkj_hi + KP * KJS;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int n = blockIdx.y, b = blockIdx.z;
+  const int i0 = (blockIdx.x * FW + warp) * 16;
+  const bool warp_active = i0 < I;
+  const int row[2] = {i0 + g, i0 + g + 8};
+  const bool rvalid[2] = {row[0] < I, row[1] < I};
+  const int rowc[2] = {min(row[0], I - 1), min(row[1], I - 1)};
+  const size_t bn = (size_t)b * N + n;
+
+  // T tile -> A fragments (hi, lo), and the fp32 values needed for the final update
+  uint32_t Thi[KS][4], Tlo[KS][4];
+  float Told[KS][2][2][2];  // [ks][nb][rr][e]: basis ks*16 + nb*8 + 2t + e, row rr
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const float* tr = T + (bn * I + rowc[rr]) * K;
+#pragma unroll
+      for (int nb = 0; nb < 2; ++nb) {
+        const int k0 = ks * 16 + nb * 8 + 2 * t;
+        const float v0 = (k0 < K && rvalid[rr]) ? tr[k0] : 0.f;
+        const float v1 = (k0 + 1 < K && rvalid[rr]) ? tr[k0 + 1] : 0.f;
+        Told[ks][nb][rr][0] = v0;
+        Told[ks][nb][rr][1] = v1;
+        const Split s = split2(v0, v1);
+        Thi[ks][nb * 2 + rr] = s.hi;  // a0: (g, k lo) a1: (g+8, k lo) a2: (g, k hi) a3: (g+8, k hi)
+        Tlo[ks][nb * 2 + rr] = s.lo;
+      }
+    }
+  }
+  cf w[2][N];
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+    for (int m = 0; m < N; ++m) w[rr][m] = W[(((size_t)b * I + rowc[rr]) * N + n) * N + m];
+
+  float num[2 * KS][4], den[2 * KS][4];
+#pragma unroll
+  for (int q = 0; q < 2 * KS; ++q)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) num[q][c] = den[q][c] = 0.f;
+
+  const float* Vb = V + bn * K * J;
+  const size_t xrow[2] = {((size_t)b * N * I + rowc[0]) * J, ((size_t)b * N * I + rowc[1]) * J};
+  const size_t cs = (size_t)I * J;
+
+  for (int jc0 = 0; jc0 < J; jc0 += JC) {
+    __syncthreads();
+    // stage V[:, jc0 : jc0+JC] as bf16 hi/lo in both layouts
+    for (int e = threadIdx.x; e < KP * JC; e += FW * 32) {
+      const int k = e / JC, jj = e - k * JC;
+      const float v = (k < K && jc0 + jj < J) ? Vb[(size_t)k * J + jc0 + jj] : 0.f;
+      __nv_bfloat16 h, l;
+      split1(v, &h, &l);
+      vkj_hi[k * KJS + jj] = h;
+      vkj_lo[k * KJS + jj] = l;
+      vjk_hi[jj * JKS + k] = h;
+      vjk_lo[jj * JKS + k] = l;
+    }
+    __syncthreads();
+    if (!warp_active) continue;
+    const int jend = min(JC, J - jc0);
+    for (int jj = 0; jj < jend; jj += 16) {
+      // ---- GEMM1: R[16 bins x 16 frames] = T V ------------------------------------------------
+      float R[2][4];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) R[h][c] = 0.f;
+        const int fr = jj + 8 * h + g;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+          const uint32_t bh0 = lds32(vjk_hi + fr * JKS + ks * 16 + 2 * t);
+          const uint32_t bh1 = lds32(vjk_hi + fr * JKS + ks * 16 + 2 * t + 8);
+          const uint32_t bl0 = lds32(vjk_lo + fr * JKS + ks * 16 + 2 * t);
+          const uint32_t bl1 = lds32(vjk_lo + fr * JKS + ks * 16 + 2 * t + 8);
+          mma_split(R[h], Thi[ks], Tlo[ks], bh0, bh1, bl0, bl1);
+        }
+      }
+      // ---- elementwise: P = |w^H x|^2, A = P / R^2, B = 1 / R ----------------------------------
+      uint32_t Ahi[4], Alo[4], Bhi[4], Blo[4];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          float4 x[N];
+          const size_t off = xrow[rr] + jc0 + jj + 8 * h + 2 * t;
+#pragma unroll
+          for (int m = 0; m < N; ++m) x[m] = *reinterpret_cast<const float4*>(X + off + m * cs);
+          float p0, p1;
+          power2<N>(x, w[rr], p0, p1);
+          const float i0v = rvalid[rr] ? fast_rcp(R[h][rr * 2 + 0]) : 0.f;
+          const float i1v = rvalid[rr] ? fast_rcp(R[h][rr * 2 + 1]) : 0.f;
+          const Split sa = split2(p0 * i0v * i0v, p1 * i1v * i1v);
+          const Split sb = split2(i0v, i1v);
+          Ahi[h * 2 + rr] = sa.hi;
+          Alo[h * 2 + rr] = sa.lo;
+          Bhi[h * 2 + rr] = sb.hi;
+          Blo[h * 2 + rr] = sb.lo;
+        }
+      }
+      // ---- GEMM2: num += A V^T, den += B V^T  (contraction over the 16 frames) -------------------
+#pragma unroll
+      for (int q = 0; q < 2 * KS; ++q) {
+        const __nv_bfloat16* ph = vkj_hi + (q * 8 + g) * KJS + jj + 2 * t;
+        const __nv_bfloat16* pl = vkj_lo + (q * 8 + g) * KJS + jj + 2 * t;
+        const uint32_t vh0 = lds32(ph), vh1 = lds32(ph + 8), vl0 = lds32(pl), vl1 = lds32(pl + 8);
+        mma_split(num[q], Ahi, Alo, vh0, vh1, vl0, vl1);
+        mma_split(den[q], Bhi, Blo, vh0, vh1, vl0, vl1);
+      }
+    }
+  }
+  if (!warp_active) return;
+  // ---- T <- floor(T * sqrt(num / den))      (ilrma.py:1125-1126, p = 2) ----------------------------
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+    for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        if (!rvalid[rr]) continue;
+        const int q = ks * 2 + nb;
+        const int k0 = ks * 16 + nb * 8 + 2 * t;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          if (k0 + e < K) {
+            const float ratio = num[q][rr * 2 + e] / den[q][rr * 2 + e];
+            T[(bn * I + row[rr]) * K + k0 + e] = ssb_floor(sqrtf(ratio) * Told[ks][nb][rr][e], flooring, eps);
+          }
+        }
+      }
+}
+
+// ------------------------------------------------------------------------------------------------
+// kf_activation.  CTA = (frame group of FW*16 frames, source n, mixture b); warp = 16 frames; all
+// warps walk over the bins together, FW*16 bins of T staged in shared memory per round.
+// Orientation is transposed w.r.t. kf_basis: C rows = frames, C cols = bins, so that the
+// accumulator fragment of R^T = V^T T^T is the A operand of num^T += (P/R^2)^T T.
+constexpr int BCH = FW * 16;  // bins staged per round
+
+template <int N, int KS>
+__global__ void __launch_bounds__(FW * 32) kf_activation(const cf* __restrict__ X, const cf* __restrict__ W,
+                                                         const float* __restrict__ T, float* __restrict__ V, int I,
+                                                         int J, int K, int flooring, float eps) {
+  constexpr int KP = 16 * KS;
+  constexpr int BKS = KP + PADH;    // [bin][basis] row stride (halfs)
+  constexpr int KBS = BCH + PADH;   // [basis][bin] row stride (halfs)
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __nv_bfloat16* tbk_hi = reinterpret_cast<__nv_bfloat16*>(smem_raw);
+  __nv_bfloat16* tbk_lo = tbk_hi + BCH * BKS;
+  __nv_bfloat16* tkb_hi = tbk_lo + BCH * BKS;
+  __nv_bfloat16* tkb_lo = tkb_hi + KP * KBS;
+  cf* wsm = reinterpret_cast<cf*>(tkb_lo + KP * KBS);  // [BCH][N]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int n = blockIdx.y, b = blockIdx.z;
+  const int j0 = (blockIdx.x * FW + warp) * 16;
+  const bool warp_active = j0 < J;
+  const size_t bn = (size_t)b * N + n;
+  float* Vb = V + bn * K * J;
+  const int fr[2] = {min(j0 + g, J - 1), min(j0 + g + 8, J - 1)};
+  const bool fvalid[2] = {j0 + g < J, j0 + g + 8 < J};
+
+  // V^T tile (16 frames x KP) -> A fragments; fp32 copies for the final update
+  uint32_t Vhi[KS][4], Vlo[KS][4];
+  float Vold[KS][2][2][2];  // [ks][nb][rr][e]: basis ks*16+nb*8+2t+e, frame rr
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+    for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int k0 = ks * 16 + nb * 8 + 2 * t;
+        const float v0 = (k0 < K && fvalid[rr]) ? Vb[(size_t)k0 * J + fr[rr]] : 0.f;
+        const float v1 = (k0 + 1 < K && fvalid[rr]) ? Vb[(size_t)(k0 + 1) * J + fr[rr]] : 0.f;
+        Vold[ks][nb][rr][0] = v0;
+        Vold[ks][nb][rr][1] = v1;
+        const Split s = split2(v0, v1);
+        Vhi[ks][nb * 2 + rr] = s.hi;
+        Vlo[ks][nb * 2 + rr] = s.lo;
+      }
+
+  float num[2 * KS][4], den[2 * KS][4];
+#pragma unroll
+  for (int q = 0; q < 2 * KS; ++q)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) num[q][c] = den[q][c] = 0.f;
+
+  const size_t cs = (size_t)I * J;
+  const size_t xb = (size_t)b * N * I * J;
+
+  for (int ib0 = 0; ib0 < I; ib0 += BCH) {
+    __syncthreads();
+    // stage T[ib0 : ib0+BCH, :] (bf16 hi/lo, both layouts) and the W rows of source n
+    for (int e = threadIdx.x; e < BCH * KP; e += FW * 32) {
+      const int bi = e / KP, k = e - bi * KP;
+      const int i = ib0 + bi;
+      const float v = (i < I && k < K) ? T[(bn * I + i) * K + k] : 0.f;
+      __nv_bfloat16 h, l;
+      split1(v, &h, &l);
+      tbk_hi[bi * BKS + k] = h;
+      tbk_lo[bi * BKS + k] = l;
+      tkb_hi[k * KBS + bi] = h;
+      tkb_lo[k * KBS + bi] = l;
+    }
+    for (int e = threadIdx.x; e < BCH * N; e += FW * 32) {
+      const int bi = e / N, m = e - bi * N;
+      const int i = min(ib0 + bi, I - 1);
+      wsm[e] = W[(((size_t)b * I + i) * N + n) * N + m];
+    }
+    __syncthreads();
+    if (!warp_active) continue;
+    const int nbt = min(BCH, I - ib0);
+    for (int bb = 0; bb < nbt; bb += 16) {
+      // ---- GEMM1: R^T[16 frames x 16 bins] = V^T T^T ---------------------------------------------
+      float R[2][4];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {  // h: bins bb+8h .. bb+8h+7 (n-tile)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) R[h][c] = 0.f;
+        const int bi = bb + 8 * h + g;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+          const uint32_t bh0 = lds32(tbk_hi + bi * BKS + ks * 16 + 2 * t);
+          const uint32_t bh1 = lds32(tbk_hi + bi * BKS + ks * 16 + 2 * t + 8);
+          const uint32_t bl0 = lds32(tbk_lo + bi * BKS + ks * 16 + 2 * t);
+          const uint32_t bl1 = lds32(tbk_lo + bi * BKS + ks * 16 + 2 * t + 8);
+          mma_split(R[h], Vhi[ks], Vlo[ks], bh0, bh1, bl0, bl1);
+        }
+      }
+      // ---- elementwise at (frame rr, bin bb+8h+2t+e) -----------------------------------------------
+      uint32_t Ahi[4], Alo[4], Bhi[4], Blo[4];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          float a_[2], i_[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int bi = bb + 8 * h + 2 * t + e;
+            const int i = ib0 + bi;
+            const bool ok = (i < I) && fvalid[rr];
+            const size_t off = xb + (size_t)min(i, I - 1) * J + fr[rr];
+            float yr = 0.f, yi = 0.f;
+#pragma unroll
+            for (int m = 0; m < N; ++m) {
+              const cf x = X[off + m * cs];
+              const cf ww = wsm[bi * N + m];
+              yr = fmaf(ww.x, x.x, fmaf(-ww.y, x.y, yr));
+              yi = fmaf(ww.x, x.y, fmaf(ww.y, x.x, yi));
+            }
+            const float p = fmaf(yr, yr, yi * yi);
+            const float iv = ok ? fast_rcp(R[h][rr * 2 + e]) : 0.f;
+            i_[e] = iv;
+            a_[e] = p * iv * iv;
+          }
+          const Split sa = split2(a_[0], a_[1]);
+          const Split sb = split2(i_[0], i_[1]);
+          Ahi[h * 2 + rr] = sa.hi;
+          Alo[h * 2 + rr] = sa.lo;
+          Bhi[h * 2 + rr] = sb.hi;
+          Blo[h * 2 + rr] = sb.lo;
+        }
+      }
+      // ---- GEMM2: num^T += A^T T, den^T += B^T T  (contraction over the 16 bins) -----------------
+#pragma unroll
+      for (int q = 0; q < 2 * KS; ++q) {
+        const __nv_bfloat16* ph = tkb_hi + (q * 8 + g) * KBS + bb + 2 * t;
+        const __nv_bfloat16* pl = tkb_lo + (q * 8 + g) * KBS + bb + 2 * t;
+        const uint32_t th0 = lds32(ph), th1 = lds32(ph + 8), tl0 = lds32(pl), tl1 = lds32(pl + 8);
+        mma_split(num[q], Ahi, Alo, th0, th1, tl0, tl1);
+        mma_split(den[q], Bhi, Blo, th0, th1, tl0, tl1);
+      }
+    }
+  }
+  if (!warp_active) return;
+  // ---- V <- floor(V * sqrt(num / den))      (ilrma.py:1201-1202, p = 2) ----------------------------
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+    for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        if (!fvalid[rr]) continue;
+        const int q = ks * 2 + nb;
+        const int k0 = ks * 16 + nb * 8 + 2 * t;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          if (k0 + e < K) {
+            const float ratio = num[q][rr * 2 + e] / den[q][rr * 2 + e];
+            Vb[(size_t)(k0 + e) * J + fr[rr]] = ssb_floor(sqrtf(ratio) * Vold[ks][nb][rr][e], flooring, eps);
+          }
+        }
+      }
+}
+
+// ------------------------------------------------------------------------------------------------
+// kf_phi_cov.  CTA = (bin group of FW*16 bins, mixture b); warp = 16 bins; sources one at a time
+// (V of the current source staged in shared memory, [frame][basis] layout only).
+//   phi = 1 / (T V)                                   (ilrma.py:1494-1498, p = 2)
+//   U[b,i,n,a,c] = (1/J) sum_j phi[n,i,j] x_a conj(x_c) (ilrma.py:1500-1505)
+// Each thread accumulates its two rows' Hermitian N x N (N^2 reals per row) over its frames; the
+// four lanes of a row group are reduced with shuffles at the end.
+template <int N, int KS>
+__global__ void __launch_bounds__(FW * 32) kf_phi_cov(const cf* __restrict__ X, const float* __restrict__ T,
+                                                      const float* __restrict__ V, cf* __restrict__ U, int I, int J,
+                                                      int K) {
+  constexpr int KP = 16 * KS;
+  constexpr int JKS = KP + PADH;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __nv_bfloat16* vjk_hi = reinterpret_cast<__nv_bfloat16*>(smem_raw);
+  __nv_bfloat16* vjk_lo = vjk_hi + JC * JKS;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int b = blockIdx.y;
+  const int i0 = (blockIdx.x * FW + warp) * 16;
+  const bool warp_active = i0 < I;
+  const int row[2] = {i0 + g, i0 + g + 8};
+  const bool rvalid[2] = {row[0] < I, row[1] < I};
+  const int rowc[2] = {min(row[0], I - 1), min(row[1], I - 1)};
+  const size_t xrow[2] = {((size_t)b * N * I + rowc[0]) * J, ((size_t)b * N * I + rowc[1]) * J};
+  const size_t cs = (size_t)I * J;
+  const float invJ = 1.0f / (float)J;
+
+  for (int n = 0; n < N; ++n) {
+    const size_t bn = (size_t)b * N + n;
+    uint32_t Thi[KS][4], Tlo[KS][4];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const float* tr = T + (bn * I + rowc[rr]) * K;
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) {
+          const int k0 = ks * 16 + nb * 8 + 2 * t;
+          const float v0 = (k0 < K) ? tr[k0] : 0.f;
+          const float v1 = (k0 + 1 < K) ? tr[k0 + 1] : 0.f;
+          const Split s = split2(v0, v1);
+          Thi[ks][nb * 2 + rr] = s.hi;
+          Tlo[ks][nb * 2 + rr] = s.lo;
+        }
+      }
+    float acc[2][N * N];
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+      for (int e = 0; e < N * N; ++e) acc[rr][e] = 0.f;
+    const float* Vb = V + bn * K * J;
+
+    for (int jc0 = 0; jc0 < J; jc0 += JC) {
+      __syncthreads();
+      for (int e = threadIdx.x; e < KP * JC; e += FW * 32) {
+        const int k = e / JC, jj = e - k * JC;
+        const float v = (k < K && jc0 + jj < J) ? Vb[(size_t)k * J + jc0 + jj] : 0.f;
+        __nv_bfloat16 h, l;
+        split1(v, &h, &l);
+        vjk_hi[jj * JKS + k] = h;
+        vjk_lo[jj * JKS + k] = l;
+      }
+      __syncthreads();
+      if (!warp_active) continue;
+      const int jend = min(JC, J - jc0);
+      for (int jj = 0; jj < jend; jj += 8) {
+        float R[4] = {0.f, 0.f, 0.f, 0.f};
+        const int fr = jj + g;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+          const uint32_t bh0 = lds32(vjk_hi + fr * JKS + ks * 16 + 2 * t);
+          const uint32_t bh1 = lds32(vjk_hi + fr * JKS + ks * 16 + 2 * t + 8);
+          const uint32_t bl0 = lds32(vjk_lo + fr * JKS + ks * 16 + 2 * t);
+          const uint32_t bl1 = lds32(vjk_lo + fr * JKS + ks * 16 + 2 * t + 8);
+          mma_split(R, Thi[ks], Tlo[ks], bh0, bh1, bl0, bl1);
+        }
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          float4 x[N];
+          const size_t off = xrow[rr] + jc0 + jj + 2 * t;
+#pragma unroll
+          for (int m = 0; m < N; ++m) x[m] = *reinterpret_cast<const float4*>(X + off + m * cs);
+          const float ph0 = fast_rcp(R[rr * 2 + 0]), ph1 = fast_rcp(R[rr * 2 + 1]);
+#pragma unroll
+          for (int a = 0; a < N; ++a) {
+            const float ar0 = ph0 * x[a].x, ai0 = ph0 * x[a].y, ar1 = ph1 * x[a].z, ai1 = ph1 * x[a].w;
+            acc[rr][a * N + a] = fmaf(ar0, x[a].x, fmaf(ai0, x[a].y, fmaf(ar1, x[a].z, fmaf(ai1, x[a].w, acc[rr][a * N + a]))));
+#pragma unroll
+            for (int c = a + 1; c < N; ++c) {
+              acc[rr][a * N + c] = fmaf(ar0, x[c].x, fmaf(ai0, x[c].y, fmaf(ar1, x[c].z, fmaf(ai1, x[c].w, acc[rr][a * N + c]))));
+              acc[rr][c * N + a] = fmaf(ai0, x[c].x, fmaf(-ar0, x[c].y, fmaf(ai1, x[c].z, fmaf(-ar1, x[c].w, acc[rr][c * N + a]))));
+            }
+          }
+        }
+      }
+    }
+    if (warp_active) {
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+#pragma unroll
+        for (int e = 0; e < N * N; ++e) {
+          float v = acc[rr][e];
+          v += __shfl_xor_sync(SSB_FULL, v, 1);
+          v += __shfl_xor_sync(SSB_FULL, v, 2);
+          acc[rr][e] = v * invJ;
+        }
+        if (t == 0 && rvalid[rr]) {
+          cf* u = U + (((size_t)b * I + row[rr]) * N + n) * N * N;
+#pragma unroll
+          for (int a = 0; a < N; ++a) {
+            u[a * N + a] = make_float2(acc[rr][a * N + a], 0.f);
+#pragma unroll
+            for (int c = a + 1; c < N; ++c) {
+              u[a * N + c] = make_float2(acc[rr][a * N + c], acc[rr][c * N + a]);
+              u[c * N + a] = make_float2(acc[rr][a * N + c], -acc[rr][c * N + a]);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// kf_ip1_n2: IP1 for two sources in closed form, fp64, one thread per (mixture, bin)
+// (ssspy/bss/_update_spatial_model.py:63-76).  Also emits q[b,i,n] = Re(w_n^H-row C_i w_n-row^H), the
+// per-bin term of the power normalisation psi_n^2 = mean_i q.
+__global__ void __launch_bounds__(128) kf_ip1_n2(cf* __restrict__ W, const cf* __restrict__ U, int n_mat,
+                                                 int flooring, double eps) {
+  const int mat = blockIdx.x * blockDim.x + threadIdx.x;
+  if (mat >= n_mat) return;
+  cd w[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) w[e] = cf2cd(W[(size_t)mat * 4 + e]);
+#pragma unroll
+  for (int n = 0; n < 2; ++n) {
+    cd u[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) u[e] = cf2cd(U[((size_t)mat * 2 + n) * 4 + e]);
+    // A = W U_n
+    cd a00 = cd_add(cd_mul(w[0], u[0]), cd_mul(w[1], u[2]));
+    cd a01 = cd_add(cd_mul(w[0], u[1]), cd_mul(w[1], u[3]));
+    cd a10 = cd_add(cd_mul(w[2], u[0]), cd_mul(w[3], u[2]));
+    cd a11 = cd_add(cd_mul(w[2], u[1]), cd_mul(w[3], u[3]));
+    // x = A^-1 e_n  (adjugate / det)
+    cd det = cd_sub(cd_mul(a00, a11), cd_mul(a01, a10));
+    cd idet = cd_inv(det);
+    cd x0, x1;
+    if (n == 0) {
+      x0 = cd_mul(a11, idet);
+      x1 = cd_mul(cd_make(-a10.x, -a10.y), idet);
+    } else {
+      x0 = cd_mul(cd_make(-a01.x, -a01.y), idet);
+      x1 = cd_mul(a00, idet);
+    }
+    cd t0 = cd_add(cd_mul(u[0], x0), cd_mul(u[1], x1));
+    cd t1 = cd_add(cd_mul(u[2], x0), cd_mul(u[3], x1));
+    double q = cd_mulc(t0, x0).x + cd_mulc(t1, x1).x;
+    double d = ssb_floor(sqrt(fmax(q, 0.0)), flooring, eps);
+    w[n * 2 + 0] = cd_scale(cd_conj(x0), 1.0 / d);
+    w[n * 2 + 1] = cd_scale(cd_conj(x1), 1.0 / d);
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) W[(size_t)mat * 4 + e] = cd2cf(w[e]);
+}
+
+template <int N, int KS>
+int launch_all(const ssb_config* c, const cf* X, cf* W, float* T, float* V, cf* U, cudaStream_t st) {
+  const int B = c->n_batch, I = c->n_bins, J = c->n_frames, K = c->n_basis;
+  constexpr int KP = 16 * KS;
+  const size_t sm_basis = (size_t)(2 * JC * (KP + PADH) + 2 * KP * (JC + PADH)) * sizeof(__nv_bfloat16);
+  const size_t sm_act = (size_t)(2 * BCH * (KP + PADH) + 2 * KP * (BCH + PADH)) * sizeof(__nv_bfloat16) +
+                        (size_t)BCH * N * sizeof(cf);
+  const size_t sm_cov = (size_t)(2 * JC * (KP + PADH)) * sizeof(__nv_bfloat16);
+  static bool attr_set = false;
+  if (!attr_set) {
+    SSB_CUDA(cudaFuncSetAttribute(kf_basis<N, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_basis));
+    SSB_CUDA(cudaFuncSetAttribute(kf_activation<N, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_act));
+    SSB_CUDA(cudaFuncSetAttribute(kf_phi_cov<N, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_cov));
+    attr_set = true;
+  }
+  dim3 gb((I + FW * 16 - 1) / (FW * 16), N, B);
+  kf_basis<N, KS><<<gb, FW * 32, sm_basis, st>>>(X, W, T, V, I, J, K, c->flooring, c->eps);
+  if (ssb_check_launch("fused_basis", st)) return 1;
+  dim3 ga((J + FW * 16 - 1) / (FW * 16), N, B);
+  kf_activation<N, KS><<<ga, FW * 32, sm_act, st>>>(X, W, T, V, I, J, K, c->flooring, c->eps);
+  if (ssb_check_launch("fused_activation", st)) return 1;
+  dim3 gc((I + FW * 16 - 1) / (FW * 16), B);
+  kf_phi_cov<N, KS><<<gc, FW * 32, sm_cov, st>>>(X, T, V, U, I, J, K);
+  return ssb_check_launch("fused_phi_cov", st);
+}
+
+}  // namespace
+
+// ---- host side ------------------------------------------------------------------------------------
 size_t ssb_fused_carve(ssb_fused_ws* ws, const ssb_config*, char* base) {
   ws->base = base;
   ws->bytes = 0;
   return 0;
 }
-int ssb_fused_supported(const ssb_config*) { return 0; }
+
+int ssb_fused_supported(const ssb_config* c) {
+  return c->model == SSB_MODEL_ILRMA_GAUSS && c->source == SSB_SOURCE_MM && c->domain == 2.0f &&
+         (c->spatial == SSB_SPATIAL_IP1 || c->spatial == SSB_SPATIAL_IP2) && c->n_basis <= 32 &&
+         (c->n_frames % 16) == 0 && c->n_sources >= 2 && c->n_sources <= SSB_MAX_SOURCES;
+}
+
 int ssb_fused_prepare(ssb_fused_ws*, const ssb_config*, const cf*, cudaStream_t) { return 0; }
-int ssb_fused_update_once(ssb_fused_ws*, const ssb_config*, const cf*, cf*, float*, float*, const cf*, cudaStream_t) {
-  ssb_set_error("fused path not available");
-  return 1;
+
+// source model (T then V) + weighted covariance U with the tensor-core kernels
+int ssb_fused_source_and_cov(const ssb_config* c, const cf* X, cf* W, float* T, float* V, cf* U, cudaStream_t st) {
+  const int KS = c->n_basis <= 16 ? 1 : 2;
+  if (KS == 1) {
+    SSB_DISPATCH_N(c->n_sources, return (launch_all<NN, 1>(c, X, W, T, V, U, st)));
+  } else {
+    SSB_DISPATCH_N(c->n_sources, return (launch_all<NN, 2>(c, X, W, T, V, U, st)));
+  }
+  return 0;
+}
+
+int ssb_fused_ip1_n2(cf* W, const cf* U, int n_mat, int flooring, float eps, cudaStream_t st) {
+  kf_ip1_n2<<<blocks_for(n_mat, 128), 128, 0, st>>>(W, U, n_mat, flooring, (double)eps);
+  return ssb_check_launch("fused_ip1_n2", st);
 }

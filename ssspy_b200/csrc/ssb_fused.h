@@ -1,4 +1,4 @@
-// Fused sm_100a fast path of the GaussILRMA iteration (see ssb_fused.cu).
+// Fused tensor-core fast path of the GaussILRMA iteration (see ssb_fused.cu).
 #pragma once
 #include "ssb_common.cuh"
 
@@ -12,5 +12,7 @@ size_t ssb_fused_carve(ssb_fused_ws* ws, const ssb_config* cfg, char* base);
 // 1 if the configuration is covered by the fused kernels
 int ssb_fused_supported(const ssb_config* cfg);
 int ssb_fused_prepare(ssb_fused_ws* ws, const ssb_config* cfg, const cf* X, cudaStream_t st);
-int ssb_fused_update_once(ssb_fused_ws* ws, const ssb_config* cfg, const cf* X, cf* W, float* T, float* V,
-                          const cf* C, cudaStream_t st);
+// MM source model (T then V, p = 2) followed by phi = 1/(T V) and the weighted covariances U
+int ssb_fused_source_and_cov(const ssb_config* cfg, const cf* X, cf* W, float* T, float* V, cf* U, cudaStream_t st);
+// closed-form IP1 for two sources
+int ssb_fused_ip1_n2(cf* W, const cf* U, int n_mat, int flooring, float eps, cudaStream_t st);

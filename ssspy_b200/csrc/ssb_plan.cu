@@ -420,8 +420,17 @@ extern "C" int ssb_update_once(ssb_plan* p, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (p->ilrma()) {
     if (p->cfg.fast_path && ssb_fused_supported(&p->cfg)) {
-      SSB_REQUIRE(p->prepared, "plan not prepared (call ssb_plan_prepare after bind)");
-      return ssb_fused_update_once(&p->fused, &p->cfg, p->X, p->W, p->T, p->V, p->C, st);
+      const ssb_config& c = p->cfg;
+      TRY(ssb_fused_source_and_cov(&c, p->X, p->W, p->T, p->V, p->U, st));
+      if (c.spatial == SSB_SPATIAL_IP1) {
+        if (c.n_sources == 2) TRY(ssb_fused_ip1_n2(p->W, p->U, c.n_batch * c.n_bins, c.flooring, c.eps, st));
+        else TRY(ssbk_ip1(p->W, p->U, c.n_batch * c.n_bins, c.n_sources, c.flooring, c.eps, st));
+      } else {
+        TRY(ssbk_ip2(p->W, p->U, c.n_batch * c.n_bins, c.n_sources, c.pairs, c.n_pairs, c.n_sources, nullptr,
+                     c.flooring, c.eps, st));
+      }
+      if (c.normalization != SSB_NORM_NONE) TRY(ilrma_normalize(p, st));
+      return 0;
     }
     TRY(ilrma_source(p, st));
     TRY(ilrma_spatial(p, st));

@@ -181,7 +181,7 @@ def main():
     ilrma_case("ilrma_ip1_mm_n2", 2, 33, 40, 4, 10)
     ilrma_case("ilrma_ip1_mm_n3_winit", 3, 17, 23, 4, 5, w_init=True, seed=1)
     ilrma_case("ilrma_ip1_mm_n4", 4, 20, 36, 5, 8, seed=2)
-    ilrma_case("ilrma_ip1_mm_n8", 8, 9, 64, 3, 4, seed=3)
+    ilrma_case("ilrma_ip1_mm_n8", 8, 9, 160, 3, 4, seed=3)
     ilrma_case("ilrma_ip1_mm_p1", 3, 17, 23, 4, 5, domain=1, seed=4)
     ilrma_case("ilrma_ip1_me", 3, 17, 23, 4, 5, source="ME", seed=5)
     ilrma_case("ilrma_ip1_nonorm", 2, 17, 23, 4, 5, normalization=False, seed=6)
@@ -192,7 +192,7 @@ def main():
     ilrma_case("ilrma_ip2_mm_n3", 3, 17, 23, 4, 5, spatial="IP2", w_init=True, seed=11)
     ilrma_case("ilrma_ip2_mm_n4_comb", 4, 20, 36, 5, 6, spatial="IP2", pairs="combination", seed=12)
     ilrma_case("ilrma_ip2_p1", 3, 17, 23, 4, 5, spatial="IP2", domain=1, seed=13)
-    ilrma_case("ilrma_ip2_n8", 8, 9, 64, 3, 3, spatial="IP2", seed=14)
+    ilrma_case("ilrma_ip2_n8", 8, 9, 160, 3, 3, spatial="IP2", seed=14)
     ilrma_case("ilrma_iss1_mm_n2", 2, 33, 40, 4, 10, spatial="ISS", seed=15)
     ilrma_case("ilrma_iss1_mm_n3", 3, 17, 23, 4, 5, spatial="ISS", reference_id=2, seed=16)
     ilrma_case("ilrma_iss1_mm_n4_p1", 4, 20, 36, 5, 6, spatial="ISS", domain=1, seed=17)
@@ -207,7 +207,7 @@ def main():
         iva_case(f"iva_{model}_iss1_n2", 2, 33, 40, 10, model=model, spatial="ISS", seed=4)
         iva_case(f"iva_{model}_iss1_n4", 4, 20, 36, 6, model=model, spatial="ISS", reference_id=1, seed=5)
     iva_case("iva_laplace_ip1_addfloor_noscale", 3, 17, 23, 5, flooring="add", scale_restoration=False, seed=6)
-    iva_case("iva_laplace_ip1_n8", 8, 9, 64, 4, seed=7)
+    iva_case("iva_laplace_ip1_n8", 8, 9, 160, 4, seed=7)
 
 
 if __name__ == "__main__":
