@@ -73,46 +73,55 @@ def cpu_arm(wl, n_iter, workers):
 
 # ---- clocks ----------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock, power and throttle reasons through NVML every ~20 ms on a background thread
+    while the GPU is under the benchmark's load."""
 
     def __init__(self, gpu_index):
-        self.rows, self.proc, self.idx = [], None, gpu_index
+        self.idx, self.rows, self.stop_flag, self.th, self.err = gpu_index, [], False, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
-            self.th.start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+            return
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                util = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
+                self.rows.append((sm, reasons, util))
+            except Exception as e:  # pragma: no cover
+                self.err = repr(e)
+                return
+            time.sleep(0.02)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit())
-        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
-            if len(r) < 8:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self.stop_flag = True
+        if self.th is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML unavailable: %s" % self.err]}
+        self.th.join(timeout=2)
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        sm = sorted(r[0] for r in self.rows)
+        reasons = sorted(k for k, bit in names.items() if any(r[1] & bit for r in self.rows))
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_sm, "reasons": reasons,
+                "samples": len(sm)}
 
 
 def main():
@@ -208,7 +217,19 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
         dist.barrier()
+    if rank == 0:
+        # keep the identical load running while the clock sampler collects (the timed region itself can
+        # be shorter than one NVML sampling period); these extra steps are not timed
+        t_end = time.perf_counter() + 1.5
+        while time.perf_counter() < t_end:
+            for _ in range(steps):
+                sep.update_once()
+            torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks["window"] = "timed region + 1.5 s of the same steps"
+    if world > 1:
+        dist.barrier()
     ms_per_step = ms_total / steps
     value = B * world * steps / (ms_total / 1e3)
 

@@ -75,6 +75,26 @@ __device__ __forceinline__ float fast_rcp(float x) {
 
 __device__ __forceinline__ uint32_t lds32(const __nv_bfloat16* p) { return *reinterpret_cast<const uint32_t*>(p); }
 
+// ---- cp.async staging of the X tile a warp consumes one step later ---------------------------------
+// Each lane copies exactly the 16-byte (8-byte) vectors it will itself consume into a lane-private
+// slot of a warp-private ring in shared memory and reads them back after cp.async.wait_group, so no
+// warp-level barrier is needed; the global-load latency is overlapped with the MMAs of the current
+// step without holding the data in registers.
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int NPEND>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(NPEND) : "memory");
+}
+constexpr int XSTAGES = 2;
+
 // |sum_m w[m] x[m]|^2 for two consecutive frames held in a float4 per channel
 template <int N>
 __device__ __forceinline__ void power2(const float4 (&x)[N], const cf (&w)[N], float& p0, float& p1) {
@@ -97,7 +117,7 @@ __device__ __forceinline__ void power2(const float4 (&x)[N], const cf (&w)[N], f
 //   A: a0 = (row g, k 2t..), a1 = (row g+8, k 2t..), a2 = (row g, k 2t+8..), a3 = (row g+8, k 2t+8..)
 //   B: b0 = (k 2t.., n g), b1 = (k 2t+8.., n g)
 // Two C tiles over frames [j0, j0+8) and [j0+8, j0+16) are exactly the A operand of the next MMA.
-template <int N, int KS>
+template <int N, int KS, bool STG>
 __global__ void __launch_bounds__(FW * 32) kf_basis(const cf* __restrict__ X, const cf* __restrict__ W,
                                                     float* __restrict__ T, const float* __restrict__ V, int I, int J,
                                                     int K, int flooring, float eps) {
@@ -109,10 +129,13 @@ __global__ void __launch_bounds__(FW * 32) kf_basis(const cf* __restrict__ X, co
   __nv_bfloat16* vjk_lo = vjk_hi + JC * JKS;
   __nv_bfloat16* vkj_hi = vjk_lo + JC * JKS;
   __nv_bfloat16* vkj_lo = vkj_hi + KP * KJS;
+  constexpr int NLD = 4 * N;  // 16-byte vectors per lane per 16-frame step
+  float4* xring = reinterpret_cast<float4*>(vkj_lo + KP * KJS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int n = blockIdx.y, b = blockIdx.z;
+  float4* xw = xring + (size_t)warp * XSTAGES * NLD * 32 + lane;  // lane-private slots, stride 32
   const int i0 = (blockIdx.x * FW + warp) * 16;
   const bool warp_active = i0 < I;
   const int row[2] = {i0 + g, i0 + g + 8};
@@ -157,6 +180,22 @@ __global__ void __launch_bounds__(FW * 32) kf_basis(const cf* __restrict__ X, co
   const size_t xrow[2] = {((size_t)b * N * I + rowc[0]) * J, ((size_t)b * N * I + rowc[1]) * J};
   const size_t cs = (size_t)I * J;
 
+  // prefetch of the X tile of frames [f0, f0+16) into ring slot `stage`
+  auto issue = [&](int f0, int stage) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+        for (int m = 0; m < N; ++m)
+          cp_async16(xw + (stage * NLD + (h * 2 + rr) * N + m) * 32, X + xrow[rr] + f0 + 8 * h + 2 * t + m * cs);
+  };
+  int step = 0;
+  if (STG && warp_active) {
+    issue(0, 0);
+    cp_async_commit();
+  }
+
   for (int jc0 = 0; jc0 < J; jc0 += JC) {
     __syncthreads();
     // stage V[:, jc0 : jc0+JC] as bf16 hi/lo in both layouts
@@ -173,7 +212,11 @@ __global__ void __launch_bounds__(FW * 32) kf_basis(const cf* __restrict__ X, co
     __syncthreads();
     if (!warp_active) continue;
     const int jend = min(JC, J - jc0);
-    for (int jj = 0; jj < jend; jj += 16) {
+    for (int jj = 0; jj < jend; jj += 16, ++step) {
+      if (STG) {
+        if (jc0 + jj + 16 < J) issue(jc0 + jj + 16, (step + 1) & 1);
+        cp_async_commit();
+      }
       // ---- GEMM1: R[16 bins x 16 frames] = T V ------------------------------------------------
       float R[2][4];
 #pragma unroll
@@ -191,6 +234,7 @@ __global__ void __launch_bounds__(FW * 32) kf_basis(const cf* __restrict__ X, co
         }
       }
       // ---- elementwise: P = |w^H x|^2, A = P / R^2, B = 1 / R ----------------------------------
+      if (STG) cp_async_wait<1>();  // this step's tile has landed (only the next one may be in flight)
       uint32_t Ahi[4], Alo[4], Bhi[4], Blo[4];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -199,7 +243,9 @@ __global__ void __launch_bounds__(FW * 32) kf_basis(const cf* __restrict__ X, co
           float4 x[N];
           const size_t off = xrow[rr] + jc0 + jj + 8 * h + 2 * t;
 #pragma unroll
-          for (int m = 0; m < N; ++m) x[m] = *reinterpret_cast<const float4*>(X + off + m * cs);
+          for (int m = 0; m < N; ++m)
+            x[m] = STG ? xw[((step & 1) * NLD + (h * 2 + rr) * N + m) * 32]
+                       : *reinterpret_cast<const float4*>(X + off + m * cs);
           float p0, p1;
           power2<N>(x, w[rr], p0, p1);
           const float i0v = rvalid[rr] ? fast_rcp(R[h][rr * 2 + 0]) : 0.f;
@@ -251,7 +297,7 @@ __global__ void __launch_bounds__(FW * 32) kf_basis(const cf* __restrict__ X, co
 // accumulator fragment of R^T = V^T T^T is the A operand of num^T += (P/R^2)^T T.
 constexpr int BCH = FW * 16;  // bins staged per round
 
-template <int N, int KS>
+template <int N, int KS, bool STG>
 __global__ void __launch_bounds__(FW * 32) kf_activation(const cf* __restrict__ X, const cf* __restrict__ W,
                                                          const float* __restrict__ T, float* __restrict__ V, int I,
                                                          int J, int K, int flooring, float eps) {
@@ -264,10 +310,13 @@ __global__ void __launch_bounds__(FW * 32) kf_activation(const cf* __restrict__ 
   __nv_bfloat16* tkb_hi = tbk_lo + BCH * BKS;
   __nv_bfloat16* tkb_lo = tkb_hi + KP * KBS;
   cf* wsm = reinterpret_cast<cf*>(tkb_lo + KP * KBS);  // [BCH][N]
+  constexpr int NLD = 8 * N;  // 8-byte vectors per lane per 16-bin step
+  cf* xring = wsm + BCH * N;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int n = blockIdx.y, b = blockIdx.z;
+  cf* xw = xring + (size_t)warp * XSTAGES * NLD * 32 + lane;
   const int j0 = (blockIdx.x * FW + warp) * 16;
   const bool warp_active = j0 < J;
   const size_t bn = (size_t)b * N + n;
@@ -303,6 +352,26 @@ __global__ void __launch_bounds__(FW * 32) kf_activation(const cf* __restrict__ 
   const size_t cs = (size_t)I * J;
   const size_t xb = (size_t)b * N * I * J;
 
+  // prefetch of the X tile of bins [ibase, ibase+16) x this warp's 16 frames into ring slot `stage`
+  auto issue = [&](int ibase, int stage) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int i = min(ibase + 8 * h + 2 * t + e, I - 1);
+#pragma unroll
+          for (int m = 0; m < N; ++m)
+            cp_async8(xw + (stage * NLD + ((h * 2 + rr) * 2 + e) * N + m) * 32, X + xb + m * cs + (size_t)i * J + fr[rr]);
+        }
+  };
+  int step = 0;
+  if (STG && warp_active) {
+    issue(0, 0);
+    cp_async_commit();
+  }
+
   for (int ib0 = 0; ib0 < I; ib0 += BCH) {
     __syncthreads();
     // stage T[ib0 : ib0+BCH, :] (bf16 hi/lo, both layouts) and the W rows of source n
@@ -325,7 +394,11 @@ __global__ void __launch_bounds__(FW * 32) kf_activation(const cf* __restrict__ 
     __syncthreads();
     if (!warp_active) continue;
     const int nbt = min(BCH, I - ib0);
-    for (int bb = 0; bb < nbt; bb += 16) {
+    for (int bb = 0; bb < nbt; bb += 16, ++step) {
+      if (STG) {
+        if (ib0 + bb + 16 < I) issue(ib0 + bb + 16, (step + 1) & 1);
+        cp_async_commit();
+      }
       // ---- GEMM1: R^T[16 frames x 16 bins] = V^T T^T ---------------------------------------------
       float R[2][4];
 #pragma unroll
@@ -343,6 +416,7 @@ __global__ void __launch_bounds__(FW * 32) kf_activation(const cf* __restrict__ 
         }
       }
       // ---- elementwise at (frame rr, bin bb+8h+2t+e) -----------------------------------------------
+      if (STG) cp_async_wait<1>();
       uint32_t Ahi[4], Alo[4], Bhi[4], Blo[4];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -358,7 +432,7 @@ __global__ void __launch_bounds__(FW * 32) kf_activation(const cf* __restrict__ 
             float yr = 0.f, yi = 0.f;
 #pragma unroll
             for (int m = 0; m < N; ++m) {
-              const cf x = X[off + m * cs];
+              const cf x = STG ? xw[((step & 1) * NLD + ((h * 2 + rr) * 2 + e) * N + m) * 32] : X[off + m * cs];
               const cf ww = wsm[bi * N + m];
               yr = fmaf(ww.x, x.x, fmaf(-ww.y, x.y, yr));
               yi = fmaf(ww.x, x.y, fmaf(ww.y, x.x, yi));
@@ -409,25 +483,41 @@ __global__ void __launch_bounds__(FW * 32) kf_activation(const cf* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
-// kf_phi_cov.  CTA = (bin group of FW*16 bins, mixture b); warp = 16 bins; sources one at a time
-// (V of the current source staged in shared memory, [frame][basis] layout only).
+// kf_phi_cov.  CTA = (bin group of FW*16 bins, mixture b); warp = 16 bins x all frames.  G sources
+// are handled per pass over the bins' X slab (their V staged side by side in shared memory), so for
+// N <= 4 the slab is read at most twice; RS splits the two row groups of the tile into separate
+// passes when 2 N^2 accumulators per source would not fit the register file (N >= 6).
 //   phi = 1 / (T V)                                   (ilrma.py:1494-1498, p = 2)
 //   U[b,i,n,a,c] = (1/J) sum_j phi[n,i,j] x_a conj(x_c) (ilrma.py:1500-1505)
-// Each thread accumulates its two rows' Hermitian N x N (N^2 reals per row) over its frames; the
-// four lanes of a row group are reduced with shuffles at the end.
+// Each thread accumulates its rows' Hermitian N x N (N^2 reals per row) over its frames; the four
+// lanes of a row group are reduced with shuffles at the end.
+template <int N>
+struct CovShape {
+  static constexpr int G = (N == 2 || N == 4) ? 2 : (N == 3 ? 3 : 1);
+  static constexpr bool RS = N >= 6;
+  static constexpr bool STG = N <= 3;
+};
+
 template <int N, int KS>
 __global__ void __launch_bounds__(FW * 32) kf_phi_cov(const cf* __restrict__ X, const float* __restrict__ T,
                                                       const float* __restrict__ V, cf* __restrict__ U, int I, int J,
                                                       int K) {
   constexpr int KP = 16 * KS;
   constexpr int JKS = KP + PADH;
+  constexpr int G = CovShape<N>::G;
+  constexpr bool RS = CovShape<N>::RS;
+  constexpr bool STG = CovShape<N>::STG;
+  constexpr int NR = RS ? 1 : 2;   // row groups accumulated per pass
+  constexpr int NLD = 4 * N;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __nv_bfloat16* vjk_hi = reinterpret_cast<__nv_bfloat16*>(smem_raw);
-  __nv_bfloat16* vjk_lo = vjk_hi + JC * JKS;
+  __nv_bfloat16* vjk_hi = reinterpret_cast<__nv_bfloat16*>(smem_raw);  // [G][JC][JKS]
+  __nv_bfloat16* vjk_lo = vjk_hi + G * JC * JKS;
+  float4* xring = reinterpret_cast<float4*>(vjk_lo + G * JC * JKS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int b = blockIdx.y;
+  float4* xw = xring + (size_t)warp * XSTAGES * NLD * 32 + lane;
   const int i0 = (blockIdx.x * FW + warp) * 16;
   const bool warp_active = i0 < I;
   const int row[2] = {i0 + g, i0 + g + 8};
@@ -437,94 +527,140 @@ __global__ void __launch_bounds__(FW * 32) kf_phi_cov(const cf* __restrict__ X, 
   const size_t cs = (size_t)I * J;
   const float invJ = 1.0f / (float)J;
 
-  for (int n = 0; n < N; ++n) {
-    const size_t bn = (size_t)b * N + n;
-    uint32_t Thi[KS][4], Tlo[KS][4];
+  auto issue = [&](int f0, int stage) {
 #pragma unroll
-    for (int ks = 0; ks < KS; ++ks)
+    for (int h = 0; h < 2; ++h)
 #pragma unroll
-      for (int rr = 0; rr < 2; ++rr) {
-        const float* tr = T + (bn * I + rowc[rr]) * K;
+      for (int rr = 0; rr < 2; ++rr)
 #pragma unroll
-        for (int nb = 0; nb < 2; ++nb) {
-          const int k0 = ks * 16 + nb * 8 + 2 * t;
-          const float v0 = (k0 < K) ? tr[k0] : 0.f;
-          const float v1 = (k0 + 1 < K) ? tr[k0 + 1] : 0.f;
-          const Split s = split2(v0, v1);
-          Thi[ks][nb * 2 + rr] = s.hi;
-          Tlo[ks][nb * 2 + rr] = s.lo;
-        }
-      }
-    float acc[2][N * N];
-#pragma unroll
-    for (int rr = 0; rr < 2; ++rr)
-#pragma unroll
-      for (int e = 0; e < N * N; ++e) acc[rr][e] = 0.f;
-    const float* Vb = V + bn * K * J;
+        for (int m = 0; m < N; ++m)
+          cp_async16(xw + (stage * NLD + (h * 2 + rr) * N + m) * 32, X + xrow[rr] + f0 + 8 * h + 2 * t + m * cs);
+  };
 
-    for (int jc0 = 0; jc0 < J; jc0 += JC) {
-      __syncthreads();
-      for (int e = threadIdx.x; e < KP * JC; e += FW * 32) {
-        const int k = e / JC, jj = e - k * JC;
-        const float v = (k < K && jc0 + jj < J) ? Vb[(size_t)k * J + jc0 + jj] : 0.f;
-        __nv_bfloat16 h, l;
-        split1(v, &h, &l);
-        vjk_hi[jj * JKS + k] = h;
-        vjk_lo[jj * JKS + k] = l;
+  for (int n0 = 0; n0 < N; n0 += G) {
+    for (int rs = 0; rs < (RS ? 2 : 1); ++rs) {
+      uint32_t Thi[G][KS][4], Tlo[G][KS][4];
+#pragma unroll
+      for (int gs = 0; gs < G; ++gs) {
+        const int n = min(n0 + gs, N - 1);
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr) {
+            const float* tr = T + (((size_t)b * N + n) * I + rowc[rr]) * K;
+#pragma unroll
+            for (int nb = 0; nb < 2; ++nb) {
+              const int k0 = ks * 16 + nb * 8 + 2 * t;
+              const float v0 = (k0 < K) ? tr[k0] : 0.f;
+              const float v1 = (k0 + 1 < K) ? tr[k0 + 1] : 0.f;
+              const Split s = split2(v0, v1);
+              Thi[gs][ks][nb * 2 + rr] = s.hi;
+              Tlo[gs][ks][nb * 2 + rr] = s.lo;
+            }
+          }
       }
-      __syncthreads();
-      if (!warp_active) continue;
-      const int jend = min(JC, J - jc0);
-      for (int jj = 0; jj < jend; jj += 8) {
-        float R[4] = {0.f, 0.f, 0.f, 0.f};
-        const int fr = jj + g;
+      float acc[G][NR][N * N];
 #pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-          const uint32_t bh0 = lds32(vjk_hi + fr * JKS + ks * 16 + 2 * t);
-          const uint32_t bh1 = lds32(vjk_hi + fr * JKS + ks * 16 + 2 * t + 8);
-          const uint32_t bl0 = lds32(vjk_lo + fr * JKS + ks * 16 + 2 * t);
-          const uint32_t bl1 = lds32(vjk_lo + fr * JKS + ks * 16 + 2 * t + 8);
-          mma_split(R, Thi[ks], Tlo[ks], bh0, bh1, bl0, bl1);
+      for (int gs = 0; gs < G; ++gs)
+#pragma unroll
+        for (int r = 0; r < NR; ++r)
+#pragma unroll
+          for (int e = 0; e < N * N; ++e) acc[gs][r][e] = 0.f;
+
+      int step = 0;
+      if (STG && warp_active) {
+        issue(0, 0);
+        cp_async_commit();
+      }
+      for (int jc0 = 0; jc0 < J; jc0 += JC) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < G * KP * JC; e += FW * 32) {
+          const int gs = e / (KP * JC), r = e - gs * (KP * JC);
+          const int k = r / JC, jj = r - k * JC;
+          const int n = n0 + gs;
+          const float v = (n < N && k < K && jc0 + jj < J) ? V[(((size_t)b * N + n) * K + k) * J + jc0 + jj] : 0.f;
+          __nv_bfloat16 h, l;
+          split1(v, &h, &l);
+          vjk_hi[(gs * JC + jj) * JKS + k] = h;
+          vjk_lo[(gs * JC + jj) * JKS + k] = l;
         }
+        __syncthreads();
+        if (!warp_active) continue;
+        const int jend = min(JC, J - jc0);
+        for (int jj = 0; jj < jend; jj += 16, ++step) {
+          if (STG) {
+            if (jc0 + jj + 16 < J) issue(jc0 + jj + 16, (step + 1) & 1);
+            cp_async_commit();
+            cp_async_wait<1>();
+          }
 #pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-          float4 x[N];
-          const size_t off = xrow[rr] + jc0 + jj + 2 * t;
+          for (int h = 0; h < 2; ++h) {
+            // X for this half step: rows (g, g+8) x frames (2t, 2t+1) of frames [jj+8h, jj+8h+8)
+            float4 x[NR][N];
 #pragma unroll
-          for (int m = 0; m < N; ++m) x[m] = *reinterpret_cast<const float4*>(X + off + m * cs);
-          const float ph0 = fast_rcp(R[rr * 2 + 0]), ph1 = fast_rcp(R[rr * 2 + 1]);
+            for (int r = 0; r < NR; ++r) {
+              const int rr = RS ? rs : r;
 #pragma unroll
-          for (int a = 0; a < N; ++a) {
-            const float ar0 = ph0 * x[a].x, ai0 = ph0 * x[a].y, ar1 = ph1 * x[a].z, ai1 = ph1 * x[a].w;
-            acc[rr][a * N + a] = fmaf(ar0, x[a].x, fmaf(ai0, x[a].y, fmaf(ar1, x[a].z, fmaf(ai1, x[a].w, acc[rr][a * N + a]))));
+              for (int m = 0; m < N; ++m)
+                x[r][m] = STG ? xw[((step & 1) * NLD + (h * 2 + rr) * N + m) * 32]
+                              : *reinterpret_cast<const float4*>(X + xrow[rr] + jc0 + jj + 8 * h + 2 * t + m * cs);
+            }
+            const int fr = jj + 8 * h + g;
 #pragma unroll
-            for (int c = a + 1; c < N; ++c) {
-              acc[rr][a * N + c] = fmaf(ar0, x[c].x, fmaf(ai0, x[c].y, fmaf(ar1, x[c].z, fmaf(ai1, x[c].w, acc[rr][a * N + c]))));
-              acc[rr][c * N + a] = fmaf(ai0, x[c].x, fmaf(-ar0, x[c].y, fmaf(ai1, x[c].z, fmaf(-ar1, x[c].w, acc[rr][c * N + a]))));
+            for (int gs = 0; gs < G; ++gs) {
+              float R[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+              for (int ks = 0; ks < KS; ++ks) {
+                const __nv_bfloat16* ph = vjk_hi + (gs * JC + fr) * JKS + ks * 16 + 2 * t;
+                const __nv_bfloat16* pl = vjk_lo + (gs * JC + fr) * JKS + ks * 16 + 2 * t;
+                mma_split(R, Thi[gs][ks], Tlo[gs][ks], lds32(ph), lds32(ph + 8), lds32(pl), lds32(pl + 8));
+              }
+#pragma unroll
+              for (int r = 0; r < NR; ++r) {
+                const int rr = RS ? rs : r;
+                const float ph0 = fast_rcp(R[rr * 2 + 0]), ph1 = fast_rcp(R[rr * 2 + 1]);
+                float* ac = acc[gs][r];
+#pragma unroll
+                for (int a = 0; a < N; ++a) {
+                  const float ar0 = ph0 * x[r][a].x, ai0 = ph0 * x[r][a].y, ar1 = ph1 * x[r][a].z, ai1 = ph1 * x[r][a].w;
+                  ac[a * N + a] = fmaf(ar0, x[r][a].x, fmaf(ai0, x[r][a].y, fmaf(ar1, x[r][a].z, fmaf(ai1, x[r][a].w, ac[a * N + a]))));
+#pragma unroll
+                  for (int c = a + 1; c < N; ++c) {
+                    ac[a * N + c] = fmaf(ar0, x[r][c].x, fmaf(ai0, x[r][c].y, fmaf(ar1, x[r][c].z, fmaf(ai1, x[r][c].w, ac[a * N + c]))));
+                    ac[c * N + a] = fmaf(ai0, x[r][c].x, fmaf(-ar0, x[r][c].y, fmaf(ai1, x[r][c].z, fmaf(-ar1, x[r][c].w, ac[c * N + a]))));
+                  }
+                }
+              }
             }
           }
         }
       }
-    }
-    if (warp_active) {
+      if (STG) cp_async_wait<0>();
+      if (warp_active) {
 #pragma unroll
-      for (int rr = 0; rr < 2; ++rr) {
+        for (int gs = 0; gs < G; ++gs) {
+          const int n = n0 + gs;
 #pragma unroll
-        for (int e = 0; e < N * N; ++e) {
-          float v = acc[rr][e];
-          v += __shfl_xor_sync(SSB_FULL, v, 1);
-          v += __shfl_xor_sync(SSB_FULL, v, 2);
-          acc[rr][e] = v * invJ;
-        }
-        if (t == 0 && rvalid[rr]) {
-          cf* u = U + (((size_t)b * I + row[rr]) * N + n) * N * N;
+          for (int r = 0; r < NR; ++r) {
+            const int rr = RS ? rs : r;
 #pragma unroll
-          for (int a = 0; a < N; ++a) {
-            u[a * N + a] = make_float2(acc[rr][a * N + a], 0.f);
+            for (int e = 0; e < N * N; ++e) {
+              float v = acc[gs][r][e];
+              v += __shfl_xor_sync(SSB_FULL, v, 1);
+              v += __shfl_xor_sync(SSB_FULL, v, 2);
+              acc[gs][r][e] = v * invJ;
+            }
+            if (t == 0 && rvalid[rr] && n < N) {
+              cf* u = U + (((size_t)b * I + row[rr]) * N + n) * N * N;
 #pragma unroll
-            for (int c = a + 1; c < N; ++c) {
-              u[a * N + c] = make_float2(acc[rr][a * N + c], acc[rr][c * N + a]);
-              u[c * N + a] = make_float2(acc[rr][a * N + c], -acc[rr][c * N + a]);
+              for (int a = 0; a < N; ++a) {
+                u[a * N + a] = make_float2(acc[gs][r][a * N + a], 0.f);
+#pragma unroll
+                for (int c = a + 1; c < N; ++c) {
+                  u[a * N + c] = make_float2(acc[gs][r][a * N + c], acc[gs][r][c * N + a]);
+                  u[c * N + a] = make_float2(acc[gs][r][a * N + c], -acc[gs][r][c * N + a]);
+                }
+              }
             }
           }
         }
@@ -580,22 +716,26 @@ template <int N, int KS>
 int launch_all(const ssb_config* c, const cf* X, cf* W, float* T, float* V, cf* U, cudaStream_t st) {
   const int B = c->n_batch, I = c->n_bins, J = c->n_frames, K = c->n_basis;
   constexpr int KP = 16 * KS;
-  const size_t sm_basis = (size_t)(2 * JC * (KP + PADH) + 2 * KP * (JC + PADH)) * sizeof(__nv_bfloat16);
+  constexpr bool STG = N <= 2;  // cp.async staging of X in the source-model kernels
+  constexpr int G = CovShape<N>::G;
+  const size_t ring16 = (size_t)FW * XSTAGES * 4 * N * 32 * sizeof(float4);
+  const size_t sm_basis = (size_t)(2 * JC * (KP + PADH) + 2 * KP * (JC + PADH)) * sizeof(__nv_bfloat16) +
+                          (STG ? ring16 : 0);
   const size_t sm_act = (size_t)(2 * BCH * (KP + PADH) + 2 * KP * (BCH + PADH)) * sizeof(__nv_bfloat16) +
-                        (size_t)BCH * N * sizeof(cf);
-  const size_t sm_cov = (size_t)(2 * JC * (KP + PADH)) * sizeof(__nv_bfloat16);
+                        (size_t)BCH * N * sizeof(cf) + (STG ? (size_t)FW * XSTAGES * 8 * N * 32 * sizeof(cf) : 0);
+  const size_t sm_cov = (size_t)(2 * G * JC * (KP + PADH)) * sizeof(__nv_bfloat16) + (CovShape<N>::STG ? ring16 : 0);
   static bool attr_set = false;
   if (!attr_set) {
-    SSB_CUDA(cudaFuncSetAttribute(kf_basis<N, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_basis));
-    SSB_CUDA(cudaFuncSetAttribute(kf_activation<N, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_act));
+    SSB_CUDA(cudaFuncSetAttribute(kf_basis<N, KS, STG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_basis));
+    SSB_CUDA(cudaFuncSetAttribute(kf_activation<N, KS, STG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_act));
     SSB_CUDA(cudaFuncSetAttribute(kf_phi_cov<N, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_cov));
     attr_set = true;
   }
   dim3 gb((I + FW * 16 - 1) / (FW * 16), N, B);
-  kf_basis<N, KS><<<gb, FW * 32, sm_basis, st>>>(X, W, T, V, I, J, K, c->flooring, c->eps);
+  kf_basis<N, KS, STG><<<gb, FW * 32, sm_basis, st>>>(X, W, T, V, I, J, K, c->flooring, c->eps);
   if (ssb_check_launch("fused_basis", st)) return 1;
   dim3 ga((J + FW * 16 - 1) / (FW * 16), N, B);
-  kf_activation<N, KS><<<ga, FW * 32, sm_act, st>>>(X, W, T, V, I, J, K, c->flooring, c->eps);
+  kf_activation<N, KS, STG><<<ga, FW * 32, sm_act, st>>>(X, W, T, V, I, J, K, c->flooring, c->eps);
   if (ssb_check_launch("fused_activation", st)) return 1;
   dim3 gc((I + FW * 16 - 1) / (FW * 16), B);
   kf_phi_cov<N, KS><<<gc, FW * 32, sm_cov, st>>>(X, T, V, U, I, J, K);
