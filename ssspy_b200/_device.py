@@ -25,6 +25,8 @@ def to_device(x, dtype):
     """NumPy array or tensor -> contiguous CUDA tensor of ``dtype`` (copy unless already one)."""
     dev = require_cuda()
     if is_tensor(x):
+        if x.is_cuda and x.dtype == dtype and x.is_contiguous():
+            return x  # zero-copy
         return x.to(device=dev, dtype=dtype).contiguous()
     arr = np.ascontiguousarray(x)
     if np.iscomplexobj(arr):

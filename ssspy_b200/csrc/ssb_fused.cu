@@ -119,8 +119,9 @@ __device__ __forceinline__ void power2(const float4 (&x)[N], const cf (&w)[N], f
 // Two C tiles over frames [j0, j0+8) and [j0+8, j0+16) are exactly the A operand of the next MMA.
 template <int N, int KS, bool STG>
 __global__ void __launch_bounds__(FW * 32) kf_basis(const cf* __restrict__ X, const cf* __restrict__ W,
-                                                    float* __restrict__ T, const float* __restrict__ V, int I, int J,
-                                                    int K, int flooring, float eps) {
+                                                    float* __restrict__ T, const float* __restrict__ V,
+                                                    float* __restrict__ Pout, int I, int J, int K, int flooring,
+                                                    float eps) {
   constexpr int KP = 16 * KS;
   constexpr int JKS = KP + PADH;   // row stride (halfs) of the [frame][basis] layout
   constexpr int KJS = JC + PADH;   // row stride (halfs) of the [basis][frame] layout
@@ -248,6 +249,9 @@ __global__ void __launch_bounds__(FW * 32) kf_basis(const cf* __restrict__ X, co
                        : *reinterpret_cast<const float4*>(X + off + m * cs);
           float p0, p1;
           power2<N>(x, w[rr], p0, p1);
+          // the power spectrogram is kept for the activation update (same W => same P, ilrma.py:1169-1172)
+          if (rvalid[rr])
+            *reinterpret_cast<float2*>(Pout + (bn * I + row[rr]) * J + jc0 + jj + 8 * h + 2 * t) = make_float2(p0, p1);
           const float i0v = rvalid[rr] ? fast_rcp(R[h][rr * 2 + 0]) : 0.f;
           const float i1v = rvalid[rr] ? fast_rcp(R[h][rr * 2 + 1]) : 0.f;
           const Split sa = split2(p0 * i0v * i0v, p1 * i1v * i1v);
@@ -292,35 +296,41 @@ __global__ void __launch_bounds__(FW * 32) kf_basis(const cf* __restrict__ X, co
 
 // ------------------------------------------------------------------------------------------------
 // kf_activation.  CTA = (frame group of FW*16 frames, source n, mixture b); warp = 16 frames; all
-// warps walk over the bins together, FW*16 bins of T staged in shared memory per round.
+// warps walk over the bins together, FW*16 bins of T staged in shared memory per round.  P = |y|^2 was
+// written by kf_basis (the demixing filters do not change between the two updates).
 // Orientation is transposed w.r.t. kf_basis: C rows = frames, C cols = bins, so that the
 // accumulator fragment of R^T = V^T T^T is the A operand of num^T += (P/R^2)^T T.
 constexpr int BCH = FW * 16;  // bins staged per round
 
-template <int N, int KS, bool STG>
-__global__ void __launch_bounds__(FW * 32) kf_activation(const cf* __restrict__ X, const cf* __restrict__ W,
-                                                         const float* __restrict__ T, float* __restrict__ V, int I,
-                                                         int J, int K, int flooring, float eps) {
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
+}
+
+template <int KS>
+__global__ void __launch_bounds__(FW * 32) kf_activation(const float* __restrict__ P, const float* __restrict__ T,
+                                                         float* __restrict__ V, int NS, int I, int J, int K,
+                                                         int flooring, float eps) {
   constexpr int KP = 16 * KS;
   constexpr int BKS = KP + PADH;    // [bin][basis] row stride (halfs)
   constexpr int KBS = BCH + PADH;   // [basis][bin] row stride (halfs)
+  constexpr int NLD = 8;            // 4-byte P values per lane per 16-bin step
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __nv_bfloat16* tbk_hi = reinterpret_cast<__nv_bfloat16*>(smem_raw);
   __nv_bfloat16* tbk_lo = tbk_hi + BCH * BKS;
   __nv_bfloat16* tkb_hi = tbk_lo + BCH * BKS;
   __nv_bfloat16* tkb_lo = tkb_hi + KP * KBS;
-  cf* wsm = reinterpret_cast<cf*>(tkb_lo + KP * KBS);  // [BCH][N]
-  constexpr int NLD = 8 * N;  // 8-byte vectors per lane per 16-bin step
-  cf* xring = wsm + BCH * N;
+  float* pring = reinterpret_cast<float*>(tkb_lo + KP * KBS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int n = blockIdx.y, b = blockIdx.z;
-  cf* xw = xring + (size_t)warp * XSTAGES * NLD * 32 + lane;
+  float* pw = pring + (size_t)warp * XSTAGES * NLD * 32 + lane;
   const int j0 = (blockIdx.x * FW + warp) * 16;
   const bool warp_active = j0 < J;
-  const size_t bn = (size_t)b * N + n;
+  const size_t bn = (size_t)b * NS + n;
   float* Vb = V + bn * K * J;
+  const float* Pb = P + bn * I * J;
   const int fr[2] = {min(j0 + g, J - 1), min(j0 + g + 8, J - 1)};
   const bool fvalid[2] = {j0 + g < J, j0 + g + 8 < J};
 
@@ -349,10 +359,7 @@ __global__ void __launch_bounds__(FW * 32) kf_activation(const cf* __restrict__ 
 #pragma unroll
     for (int c = 0; c < 4; ++c) num[q][c] = den[q][c] = 0.f;
 
-  const size_t cs = (size_t)I * J;
-  const size_t xb = (size_t)b * N * I * J;
-
-  // prefetch of the X tile of bins [ibase, ibase+16) x this warp's 16 frames into ring slot `stage`
+  // prefetch of P for bins [ibase, ibase+16) x this warp's 16 frames into ring slot `stage`
   auto issue = [&](int ibase, int stage) {
 #pragma unroll
     for (int h = 0; h < 2; ++h)
@@ -361,20 +368,18 @@ __global__ void __launch_bounds__(FW * 32) kf_activation(const cf* __restrict__ 
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int i = min(ibase + 8 * h + 2 * t + e, I - 1);
-#pragma unroll
-          for (int m = 0; m < N; ++m)
-            cp_async8(xw + (stage * NLD + ((h * 2 + rr) * 2 + e) * N + m) * 32, X + xb + m * cs + (size_t)i * J + fr[rr]);
+          cp_async4(pw + (stage * NLD + (h * 2 + rr) * 2 + e) * 32, Pb + (size_t)i * J + fr[rr]);
         }
   };
   int step = 0;
-  if (STG && warp_active) {
+  if (warp_active) {
     issue(0, 0);
     cp_async_commit();
   }
 
   for (int ib0 = 0; ib0 < I; ib0 += BCH) {
     __syncthreads();
-    // stage T[ib0 : ib0+BCH, :] (bf16 hi/lo, both layouts) and the W rows of source n
+    // stage T[ib0 : ib0+BCH, :] (bf16 hi/lo, both layouts)
     for (int e = threadIdx.x; e < BCH * KP; e += FW * 32) {
       const int bi = e / KP, k = e - bi * KP;
       const int i = ib0 + bi;
@@ -386,19 +391,12 @@ __global__ void __launch_bounds__(FW * 32) kf_activation(const cf* __restrict__ 
       tkb_hi[k * KBS + bi] = h;
       tkb_lo[k * KBS + bi] = l;
     }
-    for (int e = threadIdx.x; e < BCH * N; e += FW * 32) {
-      const int bi = e / N, m = e - bi * N;
-      const int i = min(ib0 + bi, I - 1);
-      wsm[e] = W[(((size_t)b * I + i) * N + n) * N + m];
-    }
     __syncthreads();
     if (!warp_active) continue;
     const int nbt = min(BCH, I - ib0);
     for (int bb = 0; bb < nbt; bb += 16, ++step) {
-      if (STG) {
-        if (ib0 + bb + 16 < I) issue(ib0 + bb + 16, (step + 1) & 1);
-        cp_async_commit();
-      }
+      if (ib0 + bb + 16 < I) issue(ib0 + bb + 16, (step + 1) & 1);
+      cp_async_commit();
       // ---- GEMM1: R^T[16 frames x 16 bins] = V^T T^T ---------------------------------------------
       float R[2][4];
 #pragma unroll
@@ -416,7 +414,7 @@ __global__ void __launch_bounds__(FW * 32) kf_activation(const cf* __restrict__ 
         }
       }
       // ---- elementwise at (frame rr, bin bb+8h+2t+e) -----------------------------------------------
-      if (STG) cp_async_wait<1>();
+      cp_async_wait<1>();
       uint32_t Ahi[4], Alo[4], Bhi[4], Blo[4];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -425,22 +423,11 @@ __global__ void __launch_bounds__(FW * 32) kf_activation(const cf* __restrict__ 
           float a_[2], i_[2];
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
-            const int bi = bb + 8 * h + 2 * t + e;
-            const int i = ib0 + bi;
-            const bool ok = (i < I) && fvalid[rr];
-            const size_t off = xb + (size_t)min(i, I - 1) * J + fr[rr];
-            float yr = 0.f, yi = 0.f;
-#pragma unroll
-            for (int m = 0; m < N; ++m) {
-              const cf x = STG ? xw[((step & 1) * NLD + ((h * 2 + rr) * 2 + e) * N + m) * 32] : X[off + m * cs];
-              const cf ww = wsm[bi * N + m];
-              yr = fmaf(ww.x, x.x, fmaf(-ww.y, x.y, yr));
-              yi = fmaf(ww.x, x.y, fmaf(ww.y, x.x, yi));
-            }
-            const float p = fmaf(yr, yr, yi * yi);
+            const bool ok = (ib0 + bb + 8 * h + 2 * t + e < I) && fvalid[rr];
+            const float p = pw[((step & 1) * NLD + (h * 2 + rr) * 2 + e) * 32];
             const float iv = ok ? fast_rcp(R[h][rr * 2 + e]) : 0.f;
             i_[e] = iv;
-            a_[e] = p * iv * iv;
+            a_[e] = ok ? p * iv * iv : 0.f;
           }
           const Split sa = split2(a_[0], a_[1]);
           const Split sb = split2(i_[0], i_[1]);
@@ -713,7 +700,7 @@ __global__ void __launch_bounds__(128) kf_ip1_n2(cf* __restrict__ W, const cf* _
 }
 
 template <int N, int KS>
-int launch_all(const ssb_config* c, const cf* X, cf* W, float* T, float* V, cf* U, cudaStream_t st) {
+int launch_all(const ssb_config* c, const cf* X, cf* W, float* T, float* V, float* P, cf* U, cudaStream_t st) {
   const int B = c->n_batch, I = c->n_bins, J = c->n_frames, K = c->n_basis;
   constexpr int KP = 16 * KS;
   constexpr bool STG = N <= 2;  // cp.async staging of X in the source-model kernels
@@ -722,20 +709,20 @@ int launch_all(const ssb_config* c, const cf* X, cf* W, float* T, float* V, cf* 
   const size_t sm_basis = (size_t)(2 * JC * (KP + PADH) + 2 * KP * (JC + PADH)) * sizeof(__nv_bfloat16) +
                           (STG ? ring16 : 0);
   const size_t sm_act = (size_t)(2 * BCH * (KP + PADH) + 2 * KP * (BCH + PADH)) * sizeof(__nv_bfloat16) +
-                        (size_t)BCH * N * sizeof(cf) + (STG ? (size_t)FW * XSTAGES * 8 * N * 32 * sizeof(cf) : 0);
+                        (size_t)FW * XSTAGES * 8 * 32 * sizeof(float);
   const size_t sm_cov = (size_t)(2 * G * JC * (KP + PADH)) * sizeof(__nv_bfloat16) + (CovShape<N>::STG ? ring16 : 0);
   static bool attr_set = false;
   if (!attr_set) {
     SSB_CUDA(cudaFuncSetAttribute(kf_basis<N, KS, STG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_basis));
-    SSB_CUDA(cudaFuncSetAttribute(kf_activation<N, KS, STG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_act));
+    SSB_CUDA(cudaFuncSetAttribute(kf_activation<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_act));
     SSB_CUDA(cudaFuncSetAttribute(kf_phi_cov<N, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_cov));
     attr_set = true;
   }
   dim3 gb((I + FW * 16 - 1) / (FW * 16), N, B);
-  kf_basis<N, KS, STG><<<gb, FW * 32, sm_basis, st>>>(X, W, T, V, I, J, K, c->flooring, c->eps);
+  kf_basis<N, KS, STG><<<gb, FW * 32, sm_basis, st>>>(X, W, T, V, P, I, J, K, c->flooring, c->eps);
   if (ssb_check_launch("fused_basis", st)) return 1;
   dim3 ga((J + FW * 16 - 1) / (FW * 16), N, B);
-  kf_activation<N, KS, STG><<<ga, FW * 32, sm_act, st>>>(X, W, T, V, I, J, K, c->flooring, c->eps);
+  kf_activation<KS><<<ga, FW * 32, sm_act, st>>>(P, T, V, N, I, J, K, c->flooring, c->eps);
   if (ssb_check_launch("fused_activation", st)) return 1;
   dim3 gc((I + FW * 16 - 1) / (FW * 16), B);
   kf_phi_cov<N, KS><<<gc, FW * 32, sm_cov, st>>>(X, T, V, U, I, J, K);
@@ -760,12 +747,13 @@ int ssb_fused_supported(const ssb_config* c) {
 int ssb_fused_prepare(ssb_fused_ws*, const ssb_config*, const cf*, cudaStream_t) { return 0; }
 
 // source model (T then V) + weighted covariance U with the tensor-core kernels
-int ssb_fused_source_and_cov(const ssb_config* c, const cf* X, cf* W, float* T, float* V, cf* U, cudaStream_t st) {
+int ssb_fused_source_and_cov(const ssb_config* c, const cf* X, cf* W, float* T, float* V, float* P, cf* U,
+                             cudaStream_t st) {
   const int KS = c->n_basis <= 16 ? 1 : 2;
   if (KS == 1) {
-    SSB_DISPATCH_N(c->n_sources, return (launch_all<NN, 1>(c, X, W, T, V, U, st)));
+    SSB_DISPATCH_N(c->n_sources, return (launch_all<NN, 1>(c, X, W, T, V, P, U, st)));
   } else {
-    SSB_DISPATCH_N(c->n_sources, return (launch_all<NN, 2>(c, X, W, T, V, U, st)));
+    SSB_DISPATCH_N(c->n_sources, return (launch_all<NN, 2>(c, X, W, T, V, P, U, st)));
   }
   return 0;
 }

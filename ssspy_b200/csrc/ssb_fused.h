@@ -13,6 +13,8 @@ size_t ssb_fused_carve(ssb_fused_ws* ws, const ssb_config* cfg, char* base);
 int ssb_fused_supported(const ssb_config* cfg);
 int ssb_fused_prepare(ssb_fused_ws* ws, const ssb_config* cfg, const cf* X, cudaStream_t st);
 // MM source model (T then V, p = 2) followed by phi = 1/(T V) and the weighted covariances U
-int ssb_fused_source_and_cov(const ssb_config* cfg, const cf* X, cf* W, float* T, float* V, cf* U, cudaStream_t st);
+// P[B,N,I,J] f32 is scratch (power spectrogram handed from the basis to the activation update)
+int ssb_fused_source_and_cov(const ssb_config* cfg, const cf* X, cf* W, float* T, float* V, float* P, cf* U,
+                             cudaStream_t st);
 // closed-form IP1 for two sources
 int ssb_fused_ip1_n2(cf* W, const cf* U, int n_mat, int flooring, float eps, cudaStream_t st);

@@ -421,7 +421,7 @@ extern "C" int ssb_update_once(ssb_plan* p, void* stream) {
   if (p->ilrma()) {
     if (p->cfg.fast_path && ssb_fused_supported(&p->cfg)) {
       const ssb_config& c = p->cfg;
-      TRY(ssb_fused_source_and_cov(&c, p->X, p->W, p->T, p->V, p->U, st));
+      TRY(ssb_fused_source_and_cov(&c, p->X, p->W, p->T, p->V, p->big, p->U, st));
       if (c.spatial == SSB_SPATIAL_IP1) {
         if (c.n_sources == 2) TRY(ssb_fused_ip1_n2(p->W, p->U, c.n_batch * c.n_bins, c.flooring, c.eps, st));
         else TRY(ssbk_ip1(p->W, p->U, c.n_batch * c.n_bins, c.n_sources, c.flooring, c.eps, st));
