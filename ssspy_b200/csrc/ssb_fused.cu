@@ -18,6 +18,7 @@
 //   kf_ip1_n2     : closed-form 2x2 IP1 (fp64), one thread per bin
 // followed by the modular normalisation kernels.  Operation order is exactly the reference's.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "ssb_fused.h"
 #include "ssb_kernels.h"
@@ -117,7 +118,7 @@ __device__ __forceinline__ void power2(const float4 (&x)[N], const cf (&w)[N], f
 //   A: a0 = (row g, k 2t..), a1 = (row g+8, k 2t..), a2 = (row g, k 2t+8..), a3 = (row g+8, k 2t+8..)
 //   B: b0 = (k 2t.., n g), b1 = (k 2t+8.., n g)
 // Two C tiles over frames [j0, j0+8) and [j0+8, j0+16) are exactly the A operand of the next MMA.
-template <int N, int KS, bool STG>
+template <int N, int KS, bool STG, int PFD>
 __global__ void __launch_bounds__(FW * 32) kf_basis(const cf* __restrict__ X, const cf* __restrict__ W,
                                                     float* __restrict__ T, const float* __restrict__ V,
                                                     float* __restrict__ Pout, int I, int J, int K, int flooring,
@@ -191,24 +192,50 @@ __global__ void __launch_bounds__(FW * 32) kf_basis(const cf* __restrict__ X, co
         for (int m = 0; m < N; ++m)
           cp_async16(xw + (stage * NLD + (h * 2 + rr) * N + m) * 32, X + xrow[rr] + f0 + 8 * h + 2 * t + m * cs);
   };
+  // L1 prefetch of the X tile of frames [f0, f0+16): 16 rows x N channels, one 128-byte line each
+  auto prefetch = [&](int f0) {
+#pragma unroll
+    for (int q = lane; q < 16 * N; q += 32) {
+      const int i = min(i0 + (q & 15), I - 1);
+      const cf* p = X + (((size_t)b * N + (q >> 4)) * I + i) * J + f0;
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+    }
+  };
   int step = 0;
   if (STG && warp_active) {
     issue(0, 0);
     cp_async_commit();
   }
+  if (PFD > 0 && warp_active) {
+#pragma unroll
+    for (int d = 0; d < PFD; ++d)
+      if (16 * d < J) prefetch(16 * d);
+  }
 
   for (int jc0 = 0; jc0 < J; jc0 += JC) {
     __syncthreads();
     // stage V[:, jc0 : jc0+JC] as bf16 hi/lo in both layouts
-    for (int e = threadIdx.x; e < KP * JC; e += FW * 32) {
-      const int k = e / JC, jj = e - k * JC;
-      const float v = (k < K && jc0 + jj < J) ? Vb[(size_t)k * J + jc0 + jj] : 0.f;
-      __nv_bfloat16 h, l;
-      split1(v, &h, &l);
-      vkj_hi[k * KJS + jj] = h;
-      vkj_lo[k * KJS + jj] = l;
-      vjk_hi[jj * JKS + k] = h;
-      vjk_lo[jj * JKS + k] = l;
+    {
+      // all loads first (independent, one L2 round trip), then split + scatter into both layouts
+      constexpr int NIT = KP * JC / (FW * 32);
+      float vals[NIT];
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) {
+        const int e = threadIdx.x + it * FW * 32;
+        const int k = e / JC, jj = e - k * JC;
+        vals[it] = (k < K && jc0 + jj < J) ? __ldg(Vb + (size_t)k * J + jc0 + jj) : 0.f;
+      }
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) {
+        const int e = threadIdx.x + it * FW * 32;
+        const int k = e / JC, jj = e - k * JC;
+        __nv_bfloat16 h, l;
+        split1(vals[it], &h, &l);
+        vkj_hi[k * KJS + jj] = h;
+        vkj_lo[k * KJS + jj] = l;
+        vjk_hi[jj * JKS + k] = h;
+        vjk_lo[jj * JKS + k] = l;
+      }
     }
     __syncthreads();
     if (!warp_active) continue;
@@ -218,6 +245,7 @@ __global__ void __launch_bounds__(FW * 32) kf_basis(const cf* __restrict__ X, co
         if (jc0 + jj + 16 < J) issue(jc0 + jj + 16, (step + 1) & 1);
         cp_async_commit();
       }
+      if (PFD > 0 && jc0 + jj + 16 * PFD < J) prefetch(jc0 + jj + 16 * PFD);
       // ---- GEMM1: R[16 bins x 16 frames] = T V ------------------------------------------------
       float R[2][4];
 #pragma unroll
@@ -380,16 +408,27 @@ __global__ void __launch_bounds__(FW * 32) kf_activation(const float* __restrict
   for (int ib0 = 0; ib0 < I; ib0 += BCH) {
     __syncthreads();
     // stage T[ib0 : ib0+BCH, :] (bf16 hi/lo, both layouts)
-    for (int e = threadIdx.x; e < BCH * KP; e += FW * 32) {
-      const int bi = e / KP, k = e - bi * KP;
-      const int i = ib0 + bi;
-      const float v = (i < I && k < K) ? T[(bn * I + i) * K + k] : 0.f;
-      __nv_bfloat16 h, l;
-      split1(v, &h, &l);
-      tbk_hi[bi * BKS + k] = h;
-      tbk_lo[bi * BKS + k] = l;
-      tkb_hi[k * KBS + bi] = h;
-      tkb_lo[k * KBS + bi] = l;
+    {
+      constexpr int NIT = BCH * KP / (FW * 32);
+      float vals[NIT];
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) {
+        const int e = threadIdx.x + it * FW * 32;
+        const int bi = e / KP, k = e - bi * KP;
+        const int i = ib0 + bi;
+        vals[it] = (i < I && k < K) ? __ldg(T + (bn * I + i) * K + k) : 0.f;
+      }
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) {
+        const int e = threadIdx.x + it * FW * 32;
+        const int bi = e / KP, k = e - bi * KP;
+        __nv_bfloat16 h, l;
+        split1(vals[it], &h, &l);
+        tbk_hi[bi * BKS + k] = h;
+        tbk_lo[bi * BKS + k] = l;
+        tkb_hi[k * KBS + bi] = h;
+        tkb_lo[k * KBS + bi] = l;
+      }
     }
     __syncthreads();
     if (!warp_active) continue;
@@ -561,15 +600,26 @@ __global__ void __launch_bounds__(FW * 32) kf_phi_cov(const cf* __restrict__ X, 
       }
       for (int jc0 = 0; jc0 < J; jc0 += JC) {
         __syncthreads();
-        for (int e = threadIdx.x; e < G * KP * JC; e += FW * 32) {
-          const int gs = e / (KP * JC), r = e - gs * (KP * JC);
-          const int k = r / JC, jj = r - k * JC;
+#pragma unroll
+        for (int gs = 0; gs < G; ++gs) {
+          constexpr int NIT = KP * JC / (FW * 32);
           const int n = n0 + gs;
-          const float v = (n < N && k < K && jc0 + jj < J) ? V[(((size_t)b * N + n) * K + k) * J + jc0 + jj] : 0.f;
-          __nv_bfloat16 h, l;
-          split1(v, &h, &l);
-          vjk_hi[(gs * JC + jj) * JKS + k] = h;
-          vjk_lo[(gs * JC + jj) * JKS + k] = l;
+          float vals[NIT];
+#pragma unroll
+          for (int it = 0; it < NIT; ++it) {
+            const int r = threadIdx.x + it * FW * 32;
+            const int k = r / JC, jj = r - k * JC;
+            vals[it] = (n < N && k < K && jc0 + jj < J) ? __ldg(V + (((size_t)b * N + n) * K + k) * J + jc0 + jj) : 0.f;
+          }
+#pragma unroll
+          for (int it = 0; it < NIT; ++it) {
+            const int r = threadIdx.x + it * FW * 32;
+            const int k = r / JC, jj = r - k * JC;
+            __nv_bfloat16 h, l;
+            split1(vals[it], &h, &l);
+            vjk_hi[(gs * JC + jj) * JKS + k] = h;
+            vjk_lo[(gs * JC + jj) * JKS + k] = l;
+          }
         }
         __syncthreads();
         if (!warp_active) continue;
@@ -658,9 +708,11 @@ __global__ void __launch_bounds__(FW * 32) kf_phi_cov(const cf* __restrict__ X, 
 
 // ------------------------------------------------------------------------------------------------
 // kf_ip1_n2: IP1 for two sources in closed form, fp64, one thread per (mixture, bin)
-// (ssspy/bss/_update_spatial_model.py:63-76).  Also emits q[b,i,n] = Re(w_n^H-row C_i w_n-row^H), the
-// per-bin term of the power normalisation psi_n^2 = mean_i q.
-__global__ void __launch_bounds__(128) kf_ip1_n2(cf* __restrict__ W, const cf* __restrict__ U, int n_mat,
+// (ssspy/bss/_update_spatial_model.py:63-76).  When C (unweighted per-bin covariance) is given it
+// also emits q[mat, n] = Re(w_n C_i w_n^H), the per-bin term of the power normalisation
+// psi_n^2 = mean_{i,j} |y|^2 = mean_i q, so normalisation needs no pass over X.
+__global__ void __launch_bounds__(128) kf_ip1_n2(cf* __restrict__ W, const cf* __restrict__ U,
+                                                 const cf* __restrict__ C, double* __restrict__ q, int n_mat,
                                                  int flooring, double eps) {
   const int mat = blockIdx.x * blockDim.x + threadIdx.x;
   if (mat >= n_mat) return;
@@ -690,13 +742,61 @@ __global__ void __launch_bounds__(128) kf_ip1_n2(cf* __restrict__ W, const cf* _
     }
     cd t0 = cd_add(cd_mul(u[0], x0), cd_mul(u[1], x1));
     cd t1 = cd_add(cd_mul(u[2], x0), cd_mul(u[3], x1));
-    double q = cd_mulc(t0, x0).x + cd_mulc(t1, x1).x;
-    double d = ssb_floor(sqrt(fmax(q, 0.0)), flooring, eps);
+    double qq = cd_mulc(t0, x0).x + cd_mulc(t1, x1).x;
+    double d = ssb_floor(sqrt(fmax(qq, 0.0)), flooring, eps);
     w[n * 2 + 0] = cd_scale(cd_conj(x0), 1.0 / d);
     w[n * 2 + 1] = cd_scale(cd_conj(x1), 1.0 / d);
   }
+  cf wf[4];
 #pragma unroll
-  for (int e = 0; e < 4; ++e) W[(size_t)mat * 4 + e] = cd2cf(w[e]);
+  for (int e = 0; e < 4; ++e) {
+    wf[e] = cd2cf(w[e]);
+    W[(size_t)mat * 4 + e] = wf[e];
+  }
+  if (C != nullptr) {
+    cd c[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) c[e] = cf2cd(C[(size_t)mat * 4 + e]);
+#pragma unroll
+    for (int n = 0; n < 2; ++n) {
+      // the stored (complex64) filter is what the normalisation sees
+      const cd r0 = cf2cd(wf[n * 2]), r1 = cf2cd(wf[n * 2 + 1]);
+      const cd s0 = cd_add(cd_mul(r0, c[0]), cd_mul(r1, c[2]));
+      const cd s1 = cd_add(cd_mul(r0, c[1]), cd_mul(r1, c[3]));
+      q[(size_t)mat * 2 + n] = cd_mulc(s0, r0).x + cd_mulc(s1, r1).x;
+    }
+  }
+}
+
+// kf_normalize: psi_n = floor(sqrt(mean_i q[b,i,n])), T[b,n] /= psi^p, W[b,:,n,:] /= psi
+// (ssspy/bss/ilrma.py:412-444); one block per (mixture, source).
+__global__ void __launch_bounds__(256) kf_normalize(const double* __restrict__ q, float* __restrict__ T,
+                                                    cf* __restrict__ W, int N, int I, int K, float p, int flooring,
+                                                    double eps) {
+  __shared__ double sh[8];
+  __shared__ double s_psi;
+  const int n = blockIdx.x, b = blockIdx.y;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < I; i += blockDim.x) acc += q[((size_t)b * I + i) * N + n];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
+    s_psi = ssb_floor(sqrt(t / (double)I), flooring, eps);
+  }
+  __syncthreads();
+  const double psi = s_psi;
+  const float it = (float)(1.0 / ((p == 2.0f) ? psi * psi : pow(psi, (double)p)));
+  const float iw = (float)(1.0 / psi);
+  float* Tb = T + ((size_t)b * N + n) * I * K;
+  for (int e = threadIdx.x; e < I * K; e += blockDim.x) Tb[e] *= it;
+  for (int e = threadIdx.x; e < I * N; e += blockDim.x) {
+    const int i = e / N, m = e - i * N;
+    cf* w = W + (((size_t)b * I + i) * N + n) * N + m;
+    *w = make_float2(w->x * iw, w->y * iw);
+  }
 }
 
 template <int N, int KS>
@@ -711,15 +811,31 @@ int launch_all(const ssb_config* c, const cf* X, cf* W, float* T, float* V, floa
   const size_t sm_act = (size_t)(2 * BCH * (KP + PADH) + 2 * KP * (BCH + PADH)) * sizeof(__nv_bfloat16) +
                         (size_t)FW * XSTAGES * 8 * 32 * sizeof(float);
   const size_t sm_cov = (size_t)(2 * G * JC * (KP + PADH)) * sizeof(__nv_bfloat16) + (CovShape<N>::STG ? ring16 : 0);
+  static int xmode = -1;  // SSB_XMODE: 0 direct loads, 1 cp.async ring, 2/3 L1 prefetch 2/4 steps ahead
+  if (xmode < 0) {
+    const char* e = getenv("SSB_XMODE");
+    xmode = e ? atoi(e) : (STG ? 1 : 0);
+  }
+  const size_t sm_basis_nostg = sm_basis - (STG ? ring16 : 0);
   static bool attr_set = false;
   if (!attr_set) {
-    SSB_CUDA(cudaFuncSetAttribute(kf_basis<N, KS, STG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_basis));
+    SSB_CUDA(cudaFuncSetAttribute(kf_basis<N, KS, STG, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_basis));
+    SSB_CUDA(cudaFuncSetAttribute(kf_basis<N, KS, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_basis_nostg));
+    SSB_CUDA(cudaFuncSetAttribute(kf_basis<N, KS, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_basis_nostg));
+    SSB_CUDA(cudaFuncSetAttribute(kf_basis<N, KS, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_basis_nostg));
     SSB_CUDA(cudaFuncSetAttribute(kf_activation<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_act));
     SSB_CUDA(cudaFuncSetAttribute(kf_phi_cov<N, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_cov));
     attr_set = true;
   }
   dim3 gb((I + FW * 16 - 1) / (FW * 16), N, B);
-  kf_basis<N, KS, STG><<<gb, FW * 32, sm_basis, st>>>(X, W, T, V, P, I, J, K, c->flooring, c->eps);
+  if (xmode == 2)
+    kf_basis<N, KS, false, 2><<<gb, FW * 32, sm_basis_nostg, st>>>(X, W, T, V, P, I, J, K, c->flooring, c->eps);
+  else if (xmode == 3)
+    kf_basis<N, KS, false, 4><<<gb, FW * 32, sm_basis_nostg, st>>>(X, W, T, V, P, I, J, K, c->flooring, c->eps);
+  else if (xmode == 0)
+    kf_basis<N, KS, false, 0><<<gb, FW * 32, sm_basis_nostg, st>>>(X, W, T, V, P, I, J, K, c->flooring, c->eps);
+  else
+    kf_basis<N, KS, STG, 0><<<gb, FW * 32, sm_basis, st>>>(X, W, T, V, P, I, J, K, c->flooring, c->eps);
   if (ssb_check_launch("fused_basis", st)) return 1;
   dim3 ga((J + FW * 16 - 1) / (FW * 16), N, B);
   kf_activation<KS><<<ga, FW * 32, sm_act, st>>>(P, T, V, N, I, J, K, c->flooring, c->eps);
@@ -758,7 +874,15 @@ int ssb_fused_source_and_cov(const ssb_config* c, const cf* X, cf* W, float* T, 
   return 0;
 }
 
-int ssb_fused_ip1_n2(cf* W, const cf* U, int n_mat, int flooring, float eps, cudaStream_t st) {
-  kf_ip1_n2<<<blocks_for(n_mat, 128), 128, 0, st>>>(W, U, n_mat, flooring, (double)eps);
+int ssb_fused_ip1_n2(cf* W, const cf* U, const cf* C, double* q, int n_mat, int flooring, float eps,
+                     cudaStream_t st) {
+  kf_ip1_n2<<<blocks_for(n_mat, 128), 128, 0, st>>>(W, U, C, q, n_mat, flooring, (double)eps);
   return ssb_check_launch("fused_ip1_n2", st);
+}
+
+int ssb_fused_normalize(const double* q, float* T, cf* W, int B, int N, int I, int K, float p, int flooring,
+                        float eps, cudaStream_t st) {
+  dim3 grid(N, B);
+  kf_normalize<<<grid, 256, 0, st>>>(q, T, W, N, I, K, p, flooring, (double)eps);
+  return ssb_check_launch("fused_normalize", st);
 }

@@ -16,5 +16,9 @@ int ssb_fused_prepare(ssb_fused_ws* ws, const ssb_config* cfg, const cf* X, cuda
 // P[B,N,I,J] f32 is scratch (power spectrogram handed from the basis to the activation update)
 int ssb_fused_source_and_cov(const ssb_config* cfg, const cf* X, cf* W, float* T, float* V, float* P, cf* U,
                              cudaStream_t st);
-// closed-form IP1 for two sources
-int ssb_fused_ip1_n2(cf* W, const cf* U, int n_mat, int flooring, float eps, cudaStream_t st);
+// closed-form IP1 for two sources; with C != NULL also q[mat,n] = Re(w_n C w_n^H) for the normalisation
+int ssb_fused_ip1_n2(cf* W, const cf* U, const cf* C, double* q, int n_mat, int flooring, float eps,
+                     cudaStream_t st);
+// power normalisation from the per-bin terms q: psi_n = floor(sqrt(mean_i q)), T /= psi^p, W /= psi
+int ssb_fused_normalize(const double* q, float* T, cf* W, int B, int N, int I, int K, float p, int flooring,
+                        float eps, cudaStream_t st);

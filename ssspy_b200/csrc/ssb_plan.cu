@@ -423,8 +423,16 @@ extern "C" int ssb_update_once(ssb_plan* p, void* stream) {
       const ssb_config& c = p->cfg;
       TRY(ssb_fused_source_and_cov(&c, p->X, p->W, p->T, p->V, p->big, p->U, st));
       if (c.spatial == SSB_SPATIAL_IP1) {
-        if (c.n_sources == 2) TRY(ssb_fused_ip1_n2(p->W, p->U, c.n_batch * c.n_bins, c.flooring, c.eps, st));
-        else TRY(ssbk_ip1(p->W, p->U, c.n_batch * c.n_bins, c.n_sources, c.flooring, c.eps, st));
+        if (c.n_sources == 2) {
+          const bool pw = c.normalization == SSB_NORM_POWER;
+          SSB_REQUIRE(!pw || p->prepared, "plan not prepared (call ssb_plan_prepare after bind)");
+          TRY(ssb_fused_ip1_n2(p->W, p->U, pw ? p->C : nullptr, p->rowloss, c.n_batch * c.n_bins, c.flooring, c.eps, st));
+          if (pw)
+            return ssb_fused_normalize(p->rowloss, p->T, p->W, c.n_batch, 2, c.n_bins, c.n_basis, c.domain, c.flooring,
+                                       c.eps, st);
+        } else {
+          TRY(ssbk_ip1(p->W, p->U, c.n_batch * c.n_bins, c.n_sources, c.flooring, c.eps, st));
+        }
       } else {
         TRY(ssbk_ip2(p->W, p->U, c.n_batch * c.n_bins, c.n_sources, c.pairs, c.n_pairs, c.n_sources, nullptr,
                      c.flooring, c.eps, st));

@@ -292,11 +292,13 @@ def test_cuda_tensor_io_is_zero_copy_and_matches_numpy():
     from ssspy_b200.bss import AuxLaplaceIVA
     from ssspy_b200.utils.synth import make_batch
     X = make_batch(2, 2, 33, 40, config_id=1)
-    Xt = torch.from_numpy(X.astype(np.complex64)).cuda()
+    Xt = torch.from_numpy(np.ascontiguousarray(X.astype(np.complex64))).cuda()  # contiguous => bound zero-copy
     mt = AuxLaplaceIVA()
+    mt.input = Xt
+    assert mt._dX.data_ptr() == Xt.data_ptr(), "input setter copied: %s %s %s %s" % (Xt.dtype, Xt.is_contiguous(), Xt.is_cuda, mt._dX.shape)
     Yt = mt(Xt, n_iter=5)
     assert isinstance(Yt, torch.Tensor) and Yt.is_cuda and Yt.shape == Xt.shape
-    assert mt._dX.data_ptr() == Xt.data_ptr()
+    assert mt._dX.data_ptr() == Xt.data_ptr(), "__call__ copied"
     Yn = AuxLaplaceIVA()(X, n_iter=5)
     assert relerr(Yt.cpu().numpy(), Yn) < 1e-5
 
