@@ -791,8 +791,10 @@ __global__ void __launch_bounds__(256) kf_normalize(const double* __restrict__ q
   const float it = (float)(1.0 / ((p == 2.0f) ? psi * psi : pow(psi, (double)p)));
   const float iw = (float)(1.0 / psi);
   float* Tb = T + ((size_t)b * N + n) * I * K;
-  for (int e = threadIdx.x; e < I * K; e += blockDim.x) Tb[e] *= it;
-  for (int e = threadIdx.x; e < I * N; e += blockDim.x) {
+  // every z-slice of the grid recomputes psi (1 K doubles) and scales its share of T and W
+  const int tid = blockIdx.z * blockDim.x + threadIdx.x, nth = gridDim.z * blockDim.x;
+  for (int e = tid; e < I * K; e += nth) Tb[e] *= it;
+  for (int e = tid; e < I * N; e += nth) {
     const int i = e / N, m = e - i * N;
     cf* w = W + (((size_t)b * I + i) * N + n) * N + m;
     *w = make_float2(w->x * iw, w->y * iw);
@@ -882,7 +884,7 @@ int ssb_fused_ip1_n2(cf* W, const cf* U, const cf* C, double* q, int n_mat, int 
 
 int ssb_fused_normalize(const double* q, float* T, cf* W, int B, int N, int I, int K, float p, int flooring,
                         float eps, cudaStream_t st) {
-  dim3 grid(N, B);
+  dim3 grid(N, B, 8);
   kf_normalize<<<grid, 256, 0, st>>>(q, T, W, N, I, K, p, flooring, (double)eps);
   return ssb_check_launch("fused_normalize", st);
 }
