@@ -192,13 +192,15 @@ __global__ void __launch_bounds__(FW * 32) kf_basis(const cf* __restrict__ X, co
         for (int m = 0; m < N; ++m)
           cp_async16(xw + (stage * NLD + (h * 2 + rr) * N + m) * 32, X + xrow[rr] + f0 + 8 * h + 2 * t + m * cs);
   };
-  // L1 prefetch of the X tile of frames [f0, f0+16): 16 rows x N channels, one 128-byte line each
+  // software prefetch (discarded 4-byte L2-level loads, one per 128-byte line) of the X tile of frames
+  // [f0, f0+16): 16 rows x N channels; the cp.async of that step then hits L2
   auto prefetch = [&](int f0) {
 #pragma unroll
     for (int q = lane; q < 16 * N; q += 32) {
       const int i = min(i0 + (q & 15), I - 1);
       const cf* p = X + (((size_t)b * N + (q >> 4)) * I + i) * J + f0;
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+      unsigned dummy;
+      asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(dummy) : "l"(p));
     }
   };
   int step = 0;
@@ -707,6 +709,147 @@ __global__ void __launch_bounds__(FW * 32) kf_phi_cov(const cf* __restrict__ X, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// kf_cov_w: weighted covariance with the weights given as an array phi[b, s, j] (AuxIVA: phi depends on
+// (source, frame) only, ssspy/bss/iva.py:1785-1791).  Same tiling, staging and Hermitian register
+// accumulation as kf_phi_cov, without the tensor-core stage.  `src` lists the source slots of phi / U.
+struct CovSrc {
+  int n;
+};
+
+template <int N>
+__global__ void __launch_bounds__(FW * 32) kf_cov_w(const cf* __restrict__ X, const float* __restrict__ phi,
+                                                    long long sb, long long sn, int n_src, cf* __restrict__ U,
+                                                    int I, int J) {
+  constexpr int G = CovShape<N>::G;
+  constexpr bool RS = CovShape<N>::RS;
+  constexpr bool STG = CovShape<N>::STG;
+  constexpr int NR = RS ? 1 : 2;
+  constexpr int NLD = 4 * N;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* xring = reinterpret_cast<float4*>(smem_raw);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int b = blockIdx.y;
+  float4* xw = xring + (size_t)warp * XSTAGES * NLD * 32 + lane;
+  const int i0 = (blockIdx.x * FW + warp) * 16;
+  if (i0 >= I) return;
+  const int row[2] = {i0 + g, i0 + g + 8};
+  const bool rvalid[2] = {row[0] < I, row[1] < I};
+  const int rowc[2] = {min(row[0], I - 1), min(row[1], I - 1)};
+  const size_t xrow[2] = {((size_t)b * N * I + rowc[0]) * J, ((size_t)b * N * I + rowc[1]) * J};
+  const size_t cs = (size_t)I * J;
+  const float invJ = 1.0f / (float)J;
+
+  auto issue = [&](int f0, int stage) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+        for (int m = 0; m < N; ++m)
+          cp_async16(xw + (stage * NLD + (h * 2 + rr) * N + m) * 32, X + xrow[rr] + f0 + 8 * h + 2 * t + m * cs);
+  };
+
+  for (int s0 = 0; s0 < n_src; s0 += G) {
+    for (int rs = 0; rs < (RS ? 2 : 1); ++rs) {
+      float acc[G][NR][N * N];
+#pragma unroll
+      for (int gs = 0; gs < G; ++gs)
+#pragma unroll
+        for (int r = 0; r < NR; ++r)
+#pragma unroll
+          for (int e = 0; e < N * N; ++e) acc[gs][r][e] = 0.f;
+      int step = 0;
+      if (STG) {
+        issue(0, 0);
+        cp_async_commit();
+      }
+      for (int jj = 0; jj < J; jj += 16, ++step) {
+        if (STG) {
+          if (jj + 16 < J) issue(jj + 16, (step + 1) & 1);
+          cp_async_commit();
+          cp_async_wait<1>();
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float4 x[NR][N];
+#pragma unroll
+          for (int r = 0; r < NR; ++r) {
+            const int rr = RS ? rs : r;
+#pragma unroll
+            for (int m = 0; m < N; ++m)
+              x[r][m] = STG ? xw[((step & 1) * NLD + (h * 2 + rr) * N + m) * 32]
+                            : *reinterpret_cast<const float4*>(X + xrow[rr] + jj + 8 * h + 2 * t + m * cs);
+          }
+#pragma unroll
+          for (int gs = 0; gs < G; ++gs) {
+            const int s = min(s0 + gs, n_src - 1);
+            const float2 ph = *reinterpret_cast<const float2*>(phi + (size_t)b * sb + (size_t)s * sn + jj + 8 * h + 2 * t);
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+              float* ac = acc[gs][r];
+#pragma unroll
+              for (int a = 0; a < N; ++a) {
+                const float ar0 = ph.x * x[r][a].x, ai0 = ph.x * x[r][a].y, ar1 = ph.y * x[r][a].z, ai1 = ph.y * x[r][a].w;
+                ac[a * N + a] = fmaf(ar0, x[r][a].x, fmaf(ai0, x[r][a].y, fmaf(ar1, x[r][a].z, fmaf(ai1, x[r][a].w, ac[a * N + a]))));
+#pragma unroll
+                for (int c = a + 1; c < N; ++c) {
+                  ac[a * N + c] = fmaf(ar0, x[r][c].x, fmaf(ai0, x[r][c].y, fmaf(ar1, x[r][c].z, fmaf(ai1, x[r][c].w, ac[a * N + c]))));
+                  ac[c * N + a] = fmaf(ai0, x[r][c].x, fmaf(-ar0, x[r][c].y, fmaf(ai1, x[r][c].z, fmaf(-ar1, x[r][c].w, ac[c * N + a]))));
+                }
+              }
+            }
+          }
+        }
+      }
+      if (STG) cp_async_wait<0>();
+#pragma unroll
+      for (int gs = 0; gs < G; ++gs) {
+        const int s = s0 + gs;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          const int rr = RS ? rs : r;
+#pragma unroll
+          for (int e = 0; e < N * N; ++e) {
+            float v = acc[gs][r][e];
+            v += __shfl_xor_sync(SSB_FULL, v, 1);
+            v += __shfl_xor_sync(SSB_FULL, v, 2);
+            acc[gs][r][e] = v * invJ;
+          }
+          if (t == 0 && rvalid[rr] && s < n_src) {
+            cf* u = U + (((size_t)b * I + row[rr]) * n_src + s) * N * N;
+#pragma unroll
+            for (int a = 0; a < N; ++a) {
+              u[a * N + a] = make_float2(acc[gs][r][a * N + a], 0.f);
+#pragma unroll
+              for (int c = a + 1; c < N; ++c) {
+                u[a * N + c] = make_float2(acc[gs][r][a * N + c], acc[gs][r][c * N + a]);
+                u[c * N + a] = make_float2(acc[gs][r][a * N + c], -acc[gs][r][c * N + a]);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int N>
+int launch_cov_w(const cf* X, const float* phi, long long sb, long long sn, int n_src, cf* U, int B, int I, int J,
+                 cudaStream_t st) {
+  const size_t sm = CovShape<N>::STG ? (size_t)FW * XSTAGES * 4 * N * 32 * sizeof(float4) : 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SSB_CUDA(cudaFuncSetAttribute(kf_cov_w<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    attr_set = true;
+  }
+  dim3 grid((I + FW * 16 - 1) / (FW * 16), B);
+  kf_cov_w<N><<<grid, FW * 32, sm, st>>>(X, phi, sb, sn, n_src, U, I, J);
+  return ssb_check_launch("fused_cov_w", st);
+}
+
+// ------------------------------------------------------------------------------------------------
 // kf_ip1_n2: IP1 for two sources in closed form, fp64, one thread per (mixture, bin)
 // (ssspy/bss/_update_spatial_model.py:63-76).  When C (unweighted per-bin covariance) is given it
 // also emits q[mat, n] = Re(w_n C_i w_n^H), the per-bin term of the power normalisation
@@ -825,6 +968,8 @@ int launch_all(const ssb_config* c, const cf* X, cf* W, float* T, float* V, floa
     SSB_CUDA(cudaFuncSetAttribute(kf_basis<N, KS, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_basis_nostg));
     SSB_CUDA(cudaFuncSetAttribute(kf_basis<N, KS, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_basis_nostg));
     SSB_CUDA(cudaFuncSetAttribute(kf_basis<N, KS, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_basis_nostg));
+    SSB_CUDA(cudaFuncSetAttribute(kf_basis<N, KS, STG, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_basis));
+    SSB_CUDA(cudaFuncSetAttribute(kf_basis<N, KS, STG, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_basis));
     SSB_CUDA(cudaFuncSetAttribute(kf_activation<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_act));
     SSB_CUDA(cudaFuncSetAttribute(kf_phi_cov<N, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_cov));
     attr_set = true;
@@ -836,6 +981,10 @@ int launch_all(const ssb_config* c, const cf* X, cf* W, float* T, float* V, floa
     kf_basis<N, KS, false, 4><<<gb, FW * 32, sm_basis_nostg, st>>>(X, W, T, V, P, I, J, K, c->flooring, c->eps);
   else if (xmode == 0)
     kf_basis<N, KS, false, 0><<<gb, FW * 32, sm_basis_nostg, st>>>(X, W, T, V, P, I, J, K, c->flooring, c->eps);
+  else if (xmode == 4)
+    kf_basis<N, KS, STG, 3><<<gb, FW * 32, sm_basis, st>>>(X, W, T, V, P, I, J, K, c->flooring, c->eps);
+  else if (xmode == 5)
+    kf_basis<N, KS, STG, 5><<<gb, FW * 32, sm_basis, st>>>(X, W, T, V, P, I, J, K, c->flooring, c->eps);
   else
     kf_basis<N, KS, STG, 0><<<gb, FW * 32, sm_basis, st>>>(X, W, T, V, P, I, J, K, c->flooring, c->eps);
   if (ssb_check_launch("fused_basis", st)) return 1;
@@ -873,6 +1022,14 @@ int ssb_fused_source_and_cov(const ssb_config* c, const cf* X, cf* W, float* T, 
   } else {
     SSB_DISPATCH_N(c->n_sources, return (launch_all<NN, 2>(c, X, W, T, V, P, U, st)));
   }
+  return 0;
+}
+
+// weighted covariance with array weights phi[b*sb + s*sn + j] (n_frames % 16 == 0 required)
+int ssb_fused_cov_w(const cf* X, const float* phi, long long sb, long long sn, int n_src, cf* U, int B, int N, int I,
+                    int J, cudaStream_t st) {
+  SSB_REQUIRE((J % 16) == 0, "fused_cov_w needs n_frames %% 16 == 0");
+  SSB_DISPATCH_N(N, return (launch_cov_w<NN>(X, phi, sb, sn, n_src, U, B, I, J, st)));
   return 0;
 }
 

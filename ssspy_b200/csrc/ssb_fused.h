@@ -22,3 +22,7 @@ int ssb_fused_ip1_n2(cf* W, const cf* U, const cf* C, double* q, int n_mat, int 
 // power normalisation from the per-bin terms q: psi_n = floor(sqrt(mean_i q)), T /= psi^p, W /= psi
 int ssb_fused_normalize(const double* q, float* T, cf* W, int B, int N, int I, int K, float p, int flooring,
                         float eps, cudaStream_t st);
+// weighted covariance with array weights phi[b*sb + s*sn + j] for s < n_src (AuxIVA); U[B,I,n_src,N,N];
+// requires n_frames % 16 == 0
+int ssb_fused_cov_w(const cf* X, const float* phi, long long sb, long long sn, int n_src, cf* U, int B, int N, int I,
+                    int J, cudaStream_t st);

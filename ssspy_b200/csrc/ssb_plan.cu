@@ -309,7 +309,8 @@ int iva_spatial(ssb_plan* p, cudaStream_t st) {
       const int uidx[2] = {0, 1};
       TRY(ssbk_iva_norm2(p->X, p->W, nullptr, pr, 2, p->r2, B, N, I, J, st));
       TRY(ssbk_iva_phi(p->r2, p->variance, 0, pr, 2, p->phi_iva, c.model, B, N, I, J, c.flooring, c.eps, st));
-      TRY(ssbk_wcov(p->X, p->phi_iva, 2LL * J, J, 0, nullptr, 2, p->U, B, N, I, J, st));
+      if (c.fast_path && (J % 16) == 0) TRY(ssb_fused_cov_w(p->X, p->phi_iva, 2LL * J, J, 2, p->U, B, N, I, J, st));
+      else TRY(ssbk_wcov(p->X, p->phi_iva, 2LL * J, J, 0, nullptr, 2, p->U, B, N, I, J, st));
       TRY(ssbk_ip2(p->W, p->U, B * I, N, pr, 1, 2, uidx, c.flooring, c.eps, st));
     }
     return 0;
@@ -318,7 +319,8 @@ int iva_spatial(ssb_plan* p, cudaStream_t st) {
   TRY(ssbk_iva_phi(p->r2, p->variance, 0, nullptr, N, p->phi_iva, c.model, B, N, I, J, c.flooring, c.eps, st));
   if (c.spatial == SSB_SPATIAL_ISS1)
     return ssbk_iss1(p->Y, p->phi_iva, (long long)N * J, J, 0, B, N, I, J, c.flooring, c.eps, st);
-  TRY(ssbk_wcov(p->X, p->phi_iva, (long long)N * J, J, 0, nullptr, N, p->U, B, N, I, J, st));
+  if (c.fast_path && (J % 16) == 0) TRY(ssb_fused_cov_w(p->X, p->phi_iva, (long long)N * J, J, N, p->U, B, N, I, J, st));
+  else TRY(ssbk_wcov(p->X, p->phi_iva, (long long)N * J, J, 0, nullptr, N, p->U, B, N, I, J, st));
   return ssbk_ip1(p->W, p->U, B * I, N, c.flooring, c.eps, st);
 }
 

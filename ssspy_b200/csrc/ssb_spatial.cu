@@ -2,6 +2,7 @@
 // covariance, IP1, IP2, ISS1, projection back, cross-solve (W recovery), log|det W|.
 // One warp owns one (mixture, bin); the N x N complex linear algebra is done in fp64 in shared
 // memory by the warp (ssb_common.cuh), the frame reductions in fp32 with a warp tree reduce.
+#include "ssb_group.cuh"
 #include "ssb_kernels.h"
 
 namespace {
@@ -299,6 +300,177 @@ __global__ void __launch_bounds__(WPB * 32) k_ip2(cf* __restrict__ W, const cf* 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Lane-group IP1 / IP2: GS lanes own one bin, lane r holds row r of W (and of every intermediate)
+// in fp64 registers (ssb_group.cuh); U_n is staged per group in shared memory for broadcast reads.
+constexpr int QW = 4;  // warps per block
+
+template <int N>
+__device__ __forceinline__ void group_load_u(cf* su, const cf* __restrict__ Ug, int r) {
+  constexpr int GS = GroupShape<N>::GS;
+#pragma unroll
+  for (int e = r; e < N * N; e += GS) su[e] = Ug[e];
+}
+
+// a[c] = sum_k wrow[k] * U[k][c]  (row r of W U)
+template <int N>
+__device__ __forceinline__ void group_row_times(const cd (&wrow)[N], const cf* su, cd (&a)[N]) {
+#pragma unroll
+  for (int c = 0; c < N; ++c) {
+    cd s = cd_make(0, 0);
+#pragma unroll
+    for (int k = 0; k < N; ++k) s = cd_fma(wrow[k], cf2cd(su[k * N + c]), s);
+    a[c] = s;
+  }
+}
+
+template <int N>
+__global__ void __launch_bounds__(QW * 32) kq_ip1(cf* __restrict__ W, const cf* __restrict__ U, int n_mat,
+                                                  int flooring, double eps) {
+  constexpr int GS = GroupShape<N>::GS, GW = GroupShape<N>::GW;
+  __shared__ cf s_u[QW][GW][N * N];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = lane / GS, r = lane - grp * GS, gbase = grp * GS;
+  const int mat_raw = (blockIdx.x * QW + warp) * GW + grp;
+  const bool valid = mat_raw < n_mat;
+  const int mat = valid ? mat_raw : n_mat - 1;
+  cf* su = s_u[warp][grp];
+  cd wrow[N];
+#pragma unroll
+  for (int c = 0; c < N; ++c) wrow[c] = (r < N) ? cf2cd(W[((size_t)mat * N + r) * N + c]) : cd_make(0, 0);
+#pragma unroll 1
+  for (int n = 0; n < N; ++n) {
+    __syncwarp();
+    group_load_u<N>(su, U + ((size_t)mat * N + n) * N * N, r);
+    __syncwarp();
+    cd a[N], rhs[1];
+    group_row_times<N>(wrow, su, a);
+    rhs[0] = cd_make(r == n ? 1.0 : 0.0, 0);
+    group_solve<N, 1, GS>(a, rhs, r, gbase);
+    // w = rhs (component r on lane r);  wUw = Re(w^H U_n w)
+    cd t = cd_make(0, 0);
+#pragma unroll
+    for (int c = 0; c < N; ++c) {
+      const cd wc = shfl_cd(rhs[0], gbase + c);
+      if (r < N) t = cd_fma(cf2cd(su[r * N + c]), wc, t);
+    }
+    const double part = (r < N) ? cd_mulc(t, rhs[0]).x : 0.0;
+    const double wUw = group_sum<GS>(part);
+    const double d = ssb_floor(sqrt(fmax(wUw, 0.0)), flooring, eps);
+    const cd mine = cd_scale(cd_conj(rhs[0]), 1.0 / d);
+#pragma unroll
+    for (int c = 0; c < N; ++c) {
+      const cd v = shfl_cd(mine, gbase + c);
+      if (r == n) wrow[c] = v;
+    }
+  }
+  if (valid && r < N) {
+#pragma unroll
+    for (int c = 0; c < N; ++c) W[((size_t)mat * N + r) * N + c] = cd2cf(wrow[c]);
+  }
+}
+
+// G[x][y] = sum_{a,c} conj(P[a][x]) U[a][c] P[c][y] with P row-distributed (lane a holds P[a][0..1])
+template <int N, int GS>
+__device__ __forceinline__ void group_quad2(const cd (&P)[2], const cf* su, int r, int gbase, cd (&G)[4]) {
+  cd t[2] = {cd_make(0, 0), cd_make(0, 0)};
+#pragma unroll
+  for (int c = 0; c < N; ++c) {
+    const cd p0 = shfl_cd(P[0], gbase + c), p1 = shfl_cd(P[1], gbase + c);
+    if (r < N) {
+      const cd u = cf2cd(su[r * N + c]);
+      t[0] = cd_fma(u, p0, t[0]);
+      t[1] = cd_fma(u, p1, t[1]);
+    }
+  }
+#pragma unroll
+  for (int x = 0; x < 2; ++x)
+#pragma unroll
+    for (int y = 0; y < 2; ++y) {
+      const cd v = (r < N) ? cd_mul(cd_conj(P[x]), t[y]) : cd_make(0, 0);
+      G[x * 2 + y] = cd_make(group_sum<GS>(v.x), group_sum<GS>(v.y));
+    }
+}
+
+template <int N>
+__global__ void __launch_bounds__(QW * 32) kq_ip2(cf* __restrict__ W, const cf* __restrict__ U, int n_mat,
+                                                  PairList pl, int flooring, double eps) {
+  constexpr int GS = GroupShape<N>::GS, GW = GroupShape<N>::GW;
+  __shared__ cf s_um[QW][GW][N * N];
+  __shared__ cf s_un[QW][GW][N * N];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = lane / GS, r = lane - grp * GS, gbase = grp * GS;
+  const int mat_raw = (blockIdx.x * QW + warp) * GW + grp;
+  const bool valid = mat_raw < n_mat;
+  const int mat = valid ? mat_raw : n_mat - 1;
+  cf* sum_ = s_um[warp][grp];
+  cf* sun_ = s_un[warp][grp];
+  cd wrow[N];
+#pragma unroll
+  for (int c = 0; c < N; ++c) wrow[c] = (r < N) ? cf2cd(W[((size_t)mat * N + r) * N + c]) : cd_make(0, 0);
+#pragma unroll 1
+  for (int q = 0; q < pl.n; ++q) {
+    const int m = pl.m[q], n = pl.nn[q];
+    __syncwarp();
+    group_load_u<N>(sum_, U + ((size_t)mat * pl.n_u + pl.um[q]) * N * N, r);
+    group_load_u<N>(sun_, U + ((size_t)mat * pl.n_u + pl.un[q]) * N * N, r);
+    __syncwarp();
+    cd a[N], Pm[2], Pn[2];
+    group_row_times<N>(wrow, sum_, a);
+    Pm[0] = cd_make(r == m ? 1.0 : 0.0, 0);
+    Pm[1] = cd_make(r == n ? 1.0 : 0.0, 0);
+    group_solve<N, 2, GS>(a, Pm, r, gbase);
+    group_row_times<N>(wrow, sun_, a);
+    Pn[0] = cd_make(r == m ? 1.0 : 0.0, 0);
+    Pn[1] = cd_make(r == n ? 1.0 : 0.0, 0);
+    group_solve<N, 2, GS>(a, Pn, r, gbase);
+    cd Gm[4], Gn[4];
+    group_quad2<N, GS>(Pm, sum_, r, gbase, Gm);
+    group_quad2<N, GS>(Pn, sun_, r, gbase, Gn);
+    // generalised eigenproblem Gm h = l Gn h (ssspy/linalg/eigh.py:173-201), redundantly on every lane
+    const double b00 = Gn[0].x, b11 = Gn[3].x;
+    const cd b10 = Gn[2];
+    const double l00 = sqrt(b00);
+    const cd l10 = cd_scale(b10, 1.0 / l00);
+    const double l11 = sqrt(b11 - cd_abs2(l10));
+    const double i00 = 1.0 / l00, i11 = 1.0 / l11;
+    const cd i10 = cd_scale(l10, -i00 * i11);
+    const double a00 = Gm[0].x, a11 = Gm[3].x;
+    const cd a01 = Gm[1];
+    const double c00 = i00 * a00 * i00;
+    const cd c01 = cd_add(cd_scale(cd_conj(i10), i00 * a00), cd_scale(a01, i00 * i11));
+    const double c11 = cd_abs2(i10) * a00 + 2.0 * i11 * cd_mul(i10, a01).x + i11 * i11 * a11;
+    double lam[2];
+    cd y0[2], y1[2];
+    herm_eig2(c00, c11, c01, lam, y0, y1);
+    cd hm[2], hn[2];  // h_m <- larger eigenvalue, h_n <- smaller (_update_spatial_model.py:370-373)
+    hm[0] = cd_add(cd_scale(y1[0], i00), cd_mul(cd_conj(i10), y1[1]));
+    hm[1] = cd_scale(y1[1], i11);
+    hn[0] = cd_add(cd_scale(y0[0], i00), cd_mul(cd_conj(i10), y0[1]));
+    hn[1] = cd_scale(y0[1], i11);
+    auto quad = [](const cd* G, const cd* h) {
+      cd t0 = cd_add(cd_mul(G[0], h[0]), cd_mul(G[1], h[1]));
+      cd t1 = cd_add(cd_mul(G[2], h[0]), cd_mul(G[3], h[1]));
+      return cd_mulc(t0, h[0]).x + cd_mulc(t1, h[1]).x;
+    };
+    const double dm = 1.0 / ssb_floor(sqrt(fmax(quad(Gm, hm), 0.0)), flooring, eps);
+    const double dn = 1.0 / ssb_floor(sqrt(fmax(quad(Gn, hn), 0.0)), flooring, eps);
+    // w_m = P_m h_m / d_m (component r on lane r); rows m, n of W are their conjugates
+    const cd wm = cd_conj(cd_scale(cd_add(cd_mul(Pm[0], hm[0]), cd_mul(Pm[1], hm[1])), dm));
+    const cd wn = cd_conj(cd_scale(cd_add(cd_mul(Pn[0], hn[0]), cd_mul(Pn[1], hn[1])), dn));
+#pragma unroll
+    for (int c = 0; c < N; ++c) {
+      const cd vm = shfl_cd(wm, gbase + c), vn = shfl_cd(wn, gbase + c);
+      if (r == m) wrow[c] = vm;
+      if (r == n) wrow[c] = vn;
+    }
+  }
+  if (valid && r < N) {
+#pragma unroll
+    for (int c = 0; c < N; ++c) W[((size_t)mat * N + r) * N + c] = cd2cf(wrow[c]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // ISS1 (ssspy/bss/_update_spatial_model.py:181-192).  One warp per (b,i), in place on Y; each of the
 // N sequential steps reads the bin's slab twice (statistics, then rank-1 update).
 template <int N>
@@ -522,7 +694,8 @@ int ssbk_wcov(const cf* X, const float* phi, long long sb, long long sn, long lo
 }
 
 int ssbk_ip1(cf* W, const cf* U, int n_mat, int N, int flooring, float eps, cudaStream_t st) {
-  SSB_DISPATCH_N(N, k_ip1<NN><<<blocks_for(n_mat, WPB), WPB * 32, 0, st>>>(W, U, n_mat, flooring, (double)eps));
+  SSB_DISPATCH_N(N, kq_ip1<NN><<<blocks_for(n_mat, QW * GroupShape<NN>::GW), QW * 32, 0, st>>>(W, U, n_mat, flooring,
+                                                                                                 (double)eps));
   return ssb_check_launch("update_by_ip1", st);
 }
 
@@ -542,7 +715,8 @@ int ssbk_ip2(cf* W, const cf* U, int n_mat, int N, const int* pairs, int n_pairs
     pl.un[q] = (short)(uidx ? uidx[2 * q + 1] : n);
   }
   if (n_pairs == 0) return 0;
-  SSB_DISPATCH_N(N, k_ip2<NN><<<blocks_for(n_mat, WPB), WPB * 32, 0, st>>>(W, U, n_mat, pl, flooring, (double)eps));
+  SSB_DISPATCH_N(N, kq_ip2<NN><<<blocks_for(n_mat, QW * GroupShape<NN>::GW), QW * 32, 0, st>>>(W, U, n_mat, pl, flooring,
+                                                                                                 (double)eps));
   return ssb_check_launch("update_by_ip2", st);
 }
 

@@ -380,3 +380,26 @@ def test_fused_tensor_core_path_matches_oracle_and_modular(N, I, J, K, spatial):
             np.testing.assert_allclose(np.asarray(fused.loss)[:, b], st["loss"], rtol=1e-3)
         else:
             assert_loss_close(np.asarray(fused.loss)[:, b], st["loss"])
+
+
+@pytest.mark.parametrize("model", ["laplace", "gauss"])
+@pytest.mark.parametrize("N,I,J,spatial", [(2, 37, 64, "IP"), (3, 21, 48, "IP2"), (4, 33, 80, "IP"), (5, 9, 96, "IP"),
+                                           (8, 12, 160, "IP2"), (4, 19, 64, "ISS")])
+def test_aux_iva_fused_covariance_and_group_solvers(model, N, I, J, spatial):
+    """AuxIVA on frame counts that take the vectorised covariance kernel (n_frames % 16 == 0) and the
+    lane-group IP1/IP2 solvers (N = 2..8), against the fp64 oracle; batched."""
+    from oracle import iva as oiva
+    from ssspy_b200.bss import AuxGaussIVA, AuxLaplaceIVA
+    from ssspy_b200.utils.synth import make_batch
+    B, n_iter = 2, 6
+    X = make_batch(B, N, I, J, config_id=11, mode="mix")
+    cls = AuxLaplaceIVA if model == "laplace" else AuxGaussIVA
+    m = cls(spatial_algorithm=spatial)
+    Y = m(X, n_iter=n_iter)
+    for b in range(B):
+        st = oiva.run(X[b], n_iter, spatial_algorithm=spatial, model=model)
+        assert relerr(Y[b], st["Y"]) < tol_seeded(spatial)
+        if spatial == "IP2":
+            np.testing.assert_allclose(np.asarray(m.loss)[:, b], st["loss"], rtol=1e-3, atol=1e-3)
+        else:
+            assert_loss_close(np.asarray(m.loss)[:, b], st["loss"])
