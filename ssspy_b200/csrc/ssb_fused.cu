@@ -170,7 +170,8 @@ __global__ void __launch_bounds__(FW * 32) kf_basis(const cf* __restrict__ X, co
 #pragma unroll
   for (int rr = 0; rr < 2; ++rr)
 #pragma unroll
-    for (int m = 0; m < N; ++m) w[rr][m] = W[(((size_t)b * I + rowc[rr]) * N + n) * N + m];
+    for (int m = 0; m < N; ++m)
+      w[rr][m] = W ? W[(((size_t)b * I + rowc[rr]) * N + n) * N + m] : make_float2(m == n ? 1.f : 0.f, 0.f);
 
   float num[2 * KS][4], den[2 * KS][4];
 #pragma unroll
@@ -322,6 +323,82 @@ __global__ void __launch_bounds__(FW * 32) kf_basis(const cf* __restrict__ X, co
           }
         }
       }
+}
+
+// ------------------------------------------------------------------------------------------------
+// kf_phi: phi[b,n,i,j] = 1 / (T V) written out (ISS modes consume the weights as an array,
+// ssspy/bss/ilrma.py:1690-1696).  Same tiling as kf_basis, R on the tensor pipe.
+template <int KS>
+__global__ void __launch_bounds__(FW * 32) kf_phi(const float* __restrict__ T, const float* __restrict__ V,
+                                                  float* __restrict__ phi, int I, int J, int K) {
+  constexpr int KP = 16 * KS;
+  constexpr int JKS = KP + PADH;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __nv_bfloat16* vjk_hi = reinterpret_cast<__nv_bfloat16*>(smem_raw);
+  __nv_bfloat16* vjk_lo = vjk_hi + JC * JKS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const size_t bn = blockIdx.y;
+  const int i0 = (blockIdx.x * FW + warp) * 16;
+  const bool warp_active = i0 < I;
+  const int row[2] = {i0 + g, i0 + g + 8};
+  const bool rvalid[2] = {row[0] < I, row[1] < I};
+  const int rowc[2] = {min(row[0], I - 1), min(row[1], I - 1)};
+  uint32_t Thi[KS][4], Tlo[KS][4];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const float* tr = T + (bn * I + rowc[rr]) * K;
+#pragma unroll
+      for (int nb = 0; nb < 2; ++nb) {
+        const int k0 = ks * 16 + nb * 8 + 2 * t;
+        const Split s = split2((k0 < K) ? tr[k0] : 0.f, (k0 + 1 < K) ? tr[k0 + 1] : 0.f);
+        Thi[ks][nb * 2 + rr] = s.hi;
+        Tlo[ks][nb * 2 + rr] = s.lo;
+      }
+    }
+  const float* Vb = V + bn * K * J;
+  for (int jc0 = 0; jc0 < J; jc0 += JC) {
+    __syncthreads();
+    {
+      constexpr int NIT = KP * JC / (FW * 32);
+      float vals[NIT];
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) {
+        const int e = threadIdx.x + it * FW * 32;
+        const int k = e / JC, jj = e - k * JC;
+        vals[it] = (k < K && jc0 + jj < J) ? __ldg(Vb + (size_t)k * J + jc0 + jj) : 0.f;
+      }
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) {
+        const int e = threadIdx.x + it * FW * 32;
+        const int k = e / JC, jj = e - k * JC;
+        __nv_bfloat16 h, l;
+        split1(vals[it], &h, &l);
+        vjk_hi[jj * JKS + k] = h;
+        vjk_lo[jj * JKS + k] = l;
+      }
+    }
+    __syncthreads();
+    if (!warp_active) continue;
+    const int jend = min(JC, J - jc0);
+    for (int jj = 0; jj < jend; jj += 8) {
+      float R[4] = {0.f, 0.f, 0.f, 0.f};
+      const int fr = jj + g;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const __nv_bfloat16* ph = vjk_hi + fr * JKS + ks * 16 + 2 * t;
+        const __nv_bfloat16* pl = vjk_lo + fr * JKS + ks * 16 + 2 * t;
+        mma_split(R, Thi[ks], Tlo[ks], lds32(ph), lds32(ph + 8), lds32(pl), lds32(pl + 8));
+      }
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr)
+        if (rvalid[rr])
+          *reinterpret_cast<float2*>(phi + (bn * I + row[rr]) * J + jc0 + jj + 2 * t) =
+              make_float2(1.0f / R[rr * 2], 1.0f / R[rr * 2 + 1]);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -521,9 +598,10 @@ __global__ void __launch_bounds__(FW * 32) kf_activation(const float* __restrict
 // lanes of a row group are reduced with shuffles at the end.
 template <int N>
 struct CovShape {
-  static constexpr int G = (N == 2 || N == 4) ? 2 : (N == 3 ? 3 : 1);
-  static constexpr bool RS = N >= 6;
-  static constexpr bool STG = N <= 3;
+  static constexpr int G = N == 2 ? 2 : (N == 3 ? 3 : (N == 4 ? 4 : 1));   // sources per CTA
+  static constexpr bool RS = N >= 4;   // one row group (8 bins) of the warp tile per pass over the frames
+  static constexpr bool STG = N <= 3;  // cp.async ring for X in kf_phi_cov (shared memory permitting)
+  static constexpr bool STG_W = N <= 4;  // ... in kf_cov_w (no V tile in shared memory there)
 };
 
 template <int N, int KS>
@@ -536,7 +614,7 @@ __global__ void __launch_bounds__(FW * 32) kf_phi_cov(const cf* __restrict__ X, 
   constexpr bool RS = CovShape<N>::RS;
   constexpr bool STG = CovShape<N>::STG;
   constexpr int NR = RS ? 1 : 2;   // row groups accumulated per pass
-  constexpr int NLD = 4 * N;
+  constexpr int NLD = 2 * NR * N;  // 16-byte vectors per lane per step (rows of this pass only)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __nv_bfloat16* vjk_hi = reinterpret_cast<__nv_bfloat16*>(smem_raw);  // [G][JC][JKS]
   __nv_bfloat16* vjk_lo = vjk_hi + G * JC * JKS;
@@ -544,9 +622,9 @@ __global__ void __launch_bounds__(FW * 32) kf_phi_cov(const cf* __restrict__ X, 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int b = blockIdx.y;
+  const int b = blockIdx.z;
   float4* xw = xring + (size_t)warp * XSTAGES * NLD * 32 + lane;
-  const int i0 = (blockIdx.x * FW + warp) * 16;
+  const int i0 = (blockIdx.y * FW + warp) * 16;
   const bool warp_active = i0 < I;
   const int row[2] = {i0 + g, i0 + g + 8};
   const bool rvalid[2] = {row[0] < I, row[1] < I};
@@ -555,17 +633,21 @@ __global__ void __launch_bounds__(FW * 32) kf_phi_cov(const cf* __restrict__ X, 
   const size_t cs = (size_t)I * J;
   const float invJ = 1.0f / (float)J;
 
-  auto issue = [&](int f0, int stage) {
+  auto issue = [&](int f0, int stage, int rs) {
 #pragma unroll
     for (int h = 0; h < 2; ++h)
 #pragma unroll
-      for (int rr = 0; rr < 2; ++rr)
+      for (int r = 0; r < NR; ++r) {
+        const int rr = RS ? rs : r;
 #pragma unroll
         for (int m = 0; m < N; ++m)
-          cp_async16(xw + (stage * NLD + (h * 2 + rr) * N + m) * 32, X + xrow[rr] + f0 + 8 * h + 2 * t + m * cs);
+          cp_async16(xw + (stage * NLD + (h * NR + r) * N + m) * 32, X + xrow[rr] + f0 + 8 * h + 2 * t + m * cs);
+      }
   };
 
-  for (int n0 = 0; n0 < N; n0 += G) {
+  // source groups are spread over blockIdx.x (adjacent CTAs share the X tile through L2)
+  {
+    const int n0 = blockIdx.x * G;
     for (int rs = 0; rs < (RS ? 2 : 1); ++rs) {
       uint32_t Thi[G][KS][4], Tlo[G][KS][4];
 #pragma unroll
@@ -597,7 +679,7 @@ __global__ void __launch_bounds__(FW * 32) kf_phi_cov(const cf* __restrict__ X, 
 
       int step = 0;
       if (STG && warp_active) {
-        issue(0, 0);
+        issue(0, 0, rs);
         cp_async_commit();
       }
       for (int jc0 = 0; jc0 < J; jc0 += JC) {
@@ -628,7 +710,7 @@ __global__ void __launch_bounds__(FW * 32) kf_phi_cov(const cf* __restrict__ X, 
         const int jend = min(JC, J - jc0);
         for (int jj = 0; jj < jend; jj += 16, ++step) {
           if (STG) {
-            if (jc0 + jj + 16 < J) issue(jc0 + jj + 16, (step + 1) & 1);
+            if (jc0 + jj + 16 < J) issue(jc0 + jj + 16, (step + 1) & 1, rs);
             cp_async_commit();
             cp_async_wait<1>();
           }
@@ -641,7 +723,7 @@ __global__ void __launch_bounds__(FW * 32) kf_phi_cov(const cf* __restrict__ X, 
               const int rr = RS ? rs : r;
 #pragma unroll
               for (int m = 0; m < N; ++m)
-                x[r][m] = STG ? xw[((step & 1) * NLD + (h * 2 + rr) * N + m) * 32]
+                x[r][m] = STG ? xw[((step & 1) * NLD + (h * NR + r) * N + m) * 32]
                               : *reinterpret_cast<const float4*>(X + xrow[rr] + jc0 + jj + 8 * h + 2 * t + m * cs);
             }
             const int fr = jj + 8 * h + g;
@@ -722,17 +804,17 @@ __global__ void __launch_bounds__(FW * 32) kf_cov_w(const cf* __restrict__ X, co
                                                     int I, int J) {
   constexpr int G = CovShape<N>::G;
   constexpr bool RS = CovShape<N>::RS;
-  constexpr bool STG = CovShape<N>::STG;
+  constexpr bool STG = CovShape<N>::STG_W;
   constexpr int NR = RS ? 1 : 2;
-  constexpr int NLD = 4 * N;
+  constexpr int NLD = 2 * NR * N;  // 16-byte vectors per lane per step (rows of this pass only)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* xring = reinterpret_cast<float4*>(smem_raw);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int b = blockIdx.y;
+  const int b = blockIdx.z;
   float4* xw = xring + (size_t)warp * XSTAGES * NLD * 32 + lane;
-  const int i0 = (blockIdx.x * FW + warp) * 16;
+  const int i0 = (blockIdx.y * FW + warp) * 16;
   if (i0 >= I) return;
   const int row[2] = {i0 + g, i0 + g + 8};
   const bool rvalid[2] = {row[0] < I, row[1] < I};
@@ -741,17 +823,20 @@ __global__ void __launch_bounds__(FW * 32) kf_cov_w(const cf* __restrict__ X, co
   const size_t cs = (size_t)I * J;
   const float invJ = 1.0f / (float)J;
 
-  auto issue = [&](int f0, int stage) {
+  auto issue = [&](int f0, int stage, int rs) {
 #pragma unroll
     for (int h = 0; h < 2; ++h)
 #pragma unroll
-      for (int rr = 0; rr < 2; ++rr)
+      for (int r = 0; r < NR; ++r) {
+        const int rr = RS ? rs : r;
 #pragma unroll
         for (int m = 0; m < N; ++m)
-          cp_async16(xw + (stage * NLD + (h * 2 + rr) * N + m) * 32, X + xrow[rr] + f0 + 8 * h + 2 * t + m * cs);
+          cp_async16(xw + (stage * NLD + (h * NR + r) * N + m) * 32, X + xrow[rr] + f0 + 8 * h + 2 * t + m * cs);
+      }
   };
 
-  for (int s0 = 0; s0 < n_src; s0 += G) {
+  {
+    const int s0 = blockIdx.x * G;
     for (int rs = 0; rs < (RS ? 2 : 1); ++rs) {
       float acc[G][NR][N * N];
 #pragma unroll
@@ -762,12 +847,12 @@ __global__ void __launch_bounds__(FW * 32) kf_cov_w(const cf* __restrict__ X, co
           for (int e = 0; e < N * N; ++e) acc[gs][r][e] = 0.f;
       int step = 0;
       if (STG) {
-        issue(0, 0);
+        issue(0, 0, rs);
         cp_async_commit();
       }
       for (int jj = 0; jj < J; jj += 16, ++step) {
         if (STG) {
-          if (jj + 16 < J) issue(jj + 16, (step + 1) & 1);
+          if (jj + 16 < J) issue(jj + 16, (step + 1) & 1, rs);
           cp_async_commit();
           cp_async_wait<1>();
         }
@@ -779,7 +864,7 @@ __global__ void __launch_bounds__(FW * 32) kf_cov_w(const cf* __restrict__ X, co
             const int rr = RS ? rs : r;
 #pragma unroll
             for (int m = 0; m < N; ++m)
-              x[r][m] = STG ? xw[((step & 1) * NLD + (h * 2 + rr) * N + m) * 32]
+              x[r][m] = STG ? xw[((step & 1) * NLD + (h * NR + r) * N + m) * 32]
                             : *reinterpret_cast<const float4*>(X + xrow[rr] + jj + 8 * h + 2 * t + m * cs);
           }
 #pragma unroll
@@ -838,13 +923,15 @@ __global__ void __launch_bounds__(FW * 32) kf_cov_w(const cf* __restrict__ X, co
 template <int N>
 int launch_cov_w(const cf* X, const float* phi, long long sb, long long sn, int n_src, cf* U, int B, int I, int J,
                  cudaStream_t st) {
-  const size_t sm = CovShape<N>::STG ? (size_t)FW * XSTAGES * 4 * N * 32 * sizeof(float4) : 0;
+  constexpr int NRC = CovShape<N>::RS ? 1 : 2;
+  constexpr int G = CovShape<N>::G;
+  const size_t sm = CovShape<N>::STG_W ? (size_t)FW * XSTAGES * 2 * NRC * N * 32 * sizeof(float4) : 0;
   static bool attr_set = false;
   if (!attr_set) {
     SSB_CUDA(cudaFuncSetAttribute(kf_cov_w<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     attr_set = true;
   }
-  dim3 grid((I + FW * 16 - 1) / (FW * 16), B);
+  dim3 grid((n_src + G - 1) / G, (I + FW * 16 - 1) / (FW * 16), B);
   kf_cov_w<N><<<grid, FW * 32, sm, st>>>(X, phi, sb, sn, n_src, U, I, J);
   return ssb_check_launch("fused_cov_w", st);
 }
@@ -955,7 +1042,9 @@ int launch_all(const ssb_config* c, const cf* X, cf* W, float* T, float* V, floa
                           (STG ? ring16 : 0);
   const size_t sm_act = (size_t)(2 * BCH * (KP + PADH) + 2 * KP * (BCH + PADH)) * sizeof(__nv_bfloat16) +
                         (size_t)FW * XSTAGES * 8 * 32 * sizeof(float);
-  const size_t sm_cov = (size_t)(2 * G * JC * (KP + PADH)) * sizeof(__nv_bfloat16) + (CovShape<N>::STG ? ring16 : 0);
+  constexpr int NRC = CovShape<N>::RS ? 1 : 2;
+  const size_t ring_cov = (size_t)FW * XSTAGES * 2 * NRC * N * 32 * sizeof(float4);
+  const size_t sm_cov = (size_t)(2 * G * JC * (KP + PADH)) * sizeof(__nv_bfloat16) + (CovShape<N>::STG ? ring_cov : 0);
   static int xmode = -1;  // SSB_XMODE: 0 direct loads, 1 cp.async ring, 2/3 L1 prefetch 2/4 steps ahead
   if (xmode < 0) {
     const char* e = getenv("SSB_XMODE");
@@ -991,7 +1080,7 @@ int launch_all(const ssb_config* c, const cf* X, cf* W, float* T, float* V, floa
   dim3 ga((J + FW * 16 - 1) / (FW * 16), N, B);
   kf_activation<KS><<<ga, FW * 32, sm_act, st>>>(P, T, V, N, I, J, K, c->flooring, c->eps);
   if (ssb_check_launch("fused_activation", st)) return 1;
-  dim3 gc((I + FW * 16 - 1) / (FW * 16), B);
+  dim3 gc((N + G - 1) / G, (I + FW * 16 - 1) / (FW * 16), B);
   kf_phi_cov<N, KS><<<gc, FW * 32, sm_cov, st>>>(X, T, V, U, I, J, K);
   return ssb_check_launch("fused_phi_cov", st);
 }
@@ -1007,7 +1096,7 @@ size_t ssb_fused_carve(ssb_fused_ws* ws, const ssb_config*, char* base) {
 
 int ssb_fused_supported(const ssb_config* c) {
   return c->model == SSB_MODEL_ILRMA_GAUSS && c->source == SSB_SOURCE_MM && c->domain == 2.0f &&
-         (c->spatial == SSB_SPATIAL_IP1 || c->spatial == SSB_SPATIAL_IP2) && c->n_basis <= 32 &&
+         c->n_basis <= 32 &&
          (c->n_frames % 16) == 0 && c->n_sources >= 2 && c->n_sources <= SSB_MAX_SOURCES;
 }
 
@@ -1023,6 +1112,49 @@ int ssb_fused_source_and_cov(const ssb_config* c, const cf* X, cf* W, float* T, 
     SSB_DISPATCH_N(c->n_sources, return (launch_all<NN, 2>(c, X, W, T, V, P, U, st)));
   }
   return 0;
+}
+
+template <int KS>
+int launch_source_iss(const ssb_config* c, const cf* Y, float* T, float* V, float* P, cudaStream_t st) {
+  const int BN = c->n_batch * c->n_sources, I = c->n_bins, J = c->n_frames, K = c->n_basis;
+  constexpr int KP = 16 * KS;
+  const size_t ring16 = (size_t)FW * XSTAGES * 4 * 32 * sizeof(float4);
+  const size_t sm_basis = (size_t)(2 * JC * (KP + PADH) + 2 * KP * (JC + PADH)) * sizeof(__nv_bfloat16) + ring16;
+  const size_t sm_act = (size_t)(2 * BCH * (KP + PADH) + 2 * KP * (BCH + PADH)) * sizeof(__nv_bfloat16) +
+                        (size_t)FW * XSTAGES * 8 * 32 * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    SSB_CUDA(cudaFuncSetAttribute(kf_basis<1, KS, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_basis));
+    SSB_CUDA(cudaFuncSetAttribute(kf_activation<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_act));
+    attr_set = true;
+  }
+  // every (mixture, source) spectrogram is a one-channel "mixture" with the identity filter
+  dim3 gb((I + FW * 16 - 1) / (FW * 16), 1, BN);
+  kf_basis<1, KS, true, 0><<<gb, FW * 32, sm_basis, st>>>(Y, nullptr, T, V, P, I, J, K, c->flooring, c->eps);
+  if (ssb_check_launch("fused_basis", st)) return 1;
+  dim3 ga((J + FW * 16 - 1) / (FW * 16), 1, BN);
+  kf_activation<KS><<<ga, FW * 32, sm_act, st>>>(P, T, V, 1, I, J, K, c->flooring, c->eps);
+  return ssb_check_launch("fused_activation", st);
+}
+
+// MM source model (p = 2) for the ISS modes: P = |Y|^2 from the stored spectrograms
+int ssb_fused_source_iss(const ssb_config* c, const cf* Y, float* T, float* V, float* P, cudaStream_t st) {
+  if (c->n_basis <= 16) return launch_source_iss<1>(c, Y, T, V, P, st);
+  return launch_source_iss<2>(c, Y, T, V, P, st);
+}
+
+// phi[B*N, I, J] = 1 / (T V)
+int ssb_fused_phi(const ssb_config* c, const float* T, const float* V, float* phi, cudaStream_t st) {
+  const int BN = c->n_batch * c->n_sources, I = c->n_bins, J = c->n_frames, K = c->n_basis;
+  dim3 grid((I + FW * 16 - 1) / (FW * 16), BN);
+  if (K <= 16) {
+    const size_t sm = (size_t)(2 * JC * (16 + PADH)) * sizeof(__nv_bfloat16);
+    kf_phi<1><<<grid, FW * 32, sm, st>>>(T, V, phi, I, J, K);
+  } else {
+    const size_t sm = (size_t)(2 * JC * (32 + PADH)) * sizeof(__nv_bfloat16);
+    kf_phi<2><<<grid, FW * 32, sm, st>>>(T, V, phi, I, J, K);
+  }
+  return ssb_check_launch("fused_phi", st);
 }
 
 // weighted covariance with array weights phi[b*sb + s*sn + j] (n_frames % 16 == 0 required)

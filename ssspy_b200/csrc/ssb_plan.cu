@@ -421,6 +421,15 @@ extern "C" int ssb_update_once(ssb_plan* p, void* stream) {
   TRY(require_bound(p));
   cudaStream_t st = (cudaStream_t)stream;
   if (p->ilrma()) {
+    if (p->cfg.fast_path && ssb_fused_supported(&p->cfg) && p->iss()) {
+      const ssb_config& c = p->cfg;
+      const int B = c.n_batch, N = c.n_sources, I = c.n_bins, J = c.n_frames;
+      TRY(ssb_fused_source_iss(&c, p->Y, p->T, p->V, p->big, st));
+      TRY(ssb_fused_phi(&c, p->T, p->V, p->big, st));
+      TRY(ssbk_iss1(p->Y, p->big, (long long)N * I * J, (long long)I * J, J, B, N, I, J, c.flooring, c.eps, st));
+      if (c.normalization != SSB_NORM_NONE) TRY(ilrma_normalize(p, st));
+      return 0;
+    }
     if (p->cfg.fast_path && ssb_fused_supported(&p->cfg)) {
       const ssb_config& c = p->cfg;
       TRY(ssb_fused_source_and_cov(&c, p->X, p->W, p->T, p->V, p->big, p->U, st));

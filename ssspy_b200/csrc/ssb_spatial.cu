@@ -526,6 +526,72 @@ __global__ void __launch_bounds__(WPB * 32) k_iss1(cf* __restrict__ Y, const flo
   }
 }
 
+// ISS1 with the bin's (source x frame) slab of Y and of the weights resident in shared memory: Y is read
+// and written once per iteration instead of 2N times.  One warp per (b,i); dynamic shared memory
+// holds WPBS slabs of N*J complex64 + N*J float.
+template <int N>
+__global__ void k_iss1_smem(cf* __restrict__ Y, const float* __restrict__ phi, long long sb, long long sn,
+                            long long si, int B, int I, int J, int flooring, float eps, int wpb) {
+  extern __shared__ __align__(16) unsigned char iss_smem[];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = blockIdx.x * wpb + wib;
+  if (warp >= B * I) return;
+  cf* ys = reinterpret_cast<cf*>(iss_smem) + (size_t)wib * N * J;
+  float* ps = reinterpret_cast<float*>(reinterpret_cast<cf*>(iss_smem) + (size_t)wpb * N * J) + (size_t)wib * N * J;
+  const int b = warp / I, i = warp - b * I;
+  const size_t base = ((size_t)b * N * I + i) * J;
+  const size_t cs = (size_t)I * J;
+  const float* ph0 = phi + (size_t)b * sb + (size_t)i * si;
+  const float invJ = 1.0f / (float)J;
+#pragma unroll
+  for (int m = 0; m < N; ++m)
+    for (int j = lane; j < J; j += 32) {
+      ys[m * J + j] = Y[base + m * cs + j];
+      ps[m * J + j] = ph0[(size_t)m * sn + j];
+    }
+  __syncwarp();
+  for (int n = 0; n < N; ++n) {
+    float nr[N], ni[N], dn[N];
+#pragma unroll
+    for (int m = 0; m < N; ++m) nr[m] = ni[m] = dn[m] = 0.f;
+    for (int j = lane; j < J; j += 32) {
+      const cf yn = ys[n * J + j];
+      const float a2 = yn.x * yn.x + yn.y * yn.y;
+#pragma unroll
+      for (int m = 0; m < N; ++m) {
+        const float ph = ps[m * J + j];
+        const cf ym = ys[m * J + j];
+        const float pr = ph * ym.x, pi = ph * ym.y;
+        nr[m] = fmaf(pr, yn.x, fmaf(pi, yn.y, nr[m]));
+        ni[m] = fmaf(pi, yn.x, fmaf(-pr, yn.y, ni[m]));
+        dn[m] = fmaf(ph, a2, dn[m]);
+      }
+    }
+    cf v[N];
+#pragma unroll
+    for (int m = 0; m < N; ++m) {
+      const float r_ = warp_sum(nr[m]) * invJ, i_ = warp_sum(ni[m]) * invJ;
+      const float d_ = ssb_floor(warp_sum(dn[m]) * invJ, flooring, eps);
+      if (m == n) v[m] = make_float2(1.0f - 1.0f / sqrtf(d_), 0.f);
+      else v[m] = make_float2(r_ / d_, i_ / d_);
+    }
+    for (int j = lane; j < J; j += 32) {
+      const cf yn = ys[n * J + j];
+#pragma unroll
+      for (int m = 0; m < N; ++m) {
+        cf ym = ys[m * J + j];
+        ym.x -= v[m].x * yn.x - v[m].y * yn.y;
+        ym.y -= v[m].x * yn.y + v[m].y * yn.x;
+        ys[m * J + j] = ym;
+      }
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int m = 0; m < N; ++m)
+    for (int j = lane; j < J; j += 32) Y[base + m * cs + j] = ys[m * J + j];
+}
+
 // ------------------------------------------------------------------------------------------------
 // projection back, filter form (ssspy/algorithm/projection_back.py:87-99): one warp per matrix.
 // scale_out[mat*N + n] (optional) receives (W^-1)[ref, n] for the projection-back normalisation.
@@ -722,6 +788,24 @@ int ssbk_ip2(cf* W, const cf* U, int n_mat, int N, const int* pairs, int n_pairs
 
 int ssbk_iss1(cf* Y, const float* phi, long long sb, long long sn, long long si, int B, int N, int I, int J,
               int flooring, float eps, cudaStream_t st) {
+  // shared-memory slab variant when at least one (source x frame) slab of Y + weights fits
+  const size_t per_warp = (size_t)N * J * (sizeof(cf) + sizeof(float));
+  const size_t budget = 100 * 1024;  // two CTAs per SM
+  int wpb = (int)(budget / per_warp);
+  if (wpb > 8) wpb = 8;
+  if (wpb >= 1) {
+    const size_t sm = per_warp * wpb;
+    SSB_DISPATCH_N(N, {
+      static bool attr_set = false;
+      if (!attr_set) {
+        SSB_CUDA(cudaFuncSetAttribute(k_iss1_smem<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+      }
+      k_iss1_smem<NN><<<blocks_for((long long)B * I, wpb), wpb * 32, sm, st>>>(Y, phi, sb, sn, si, B, I, J, flooring, eps,
+                                                                             wpb);
+    });
+    return ssb_check_launch("update_by_iss1", st);
+  }
   SSB_DISPATCH_N(N, k_iss1<NN><<<blocks_for((long long)B * I, WPB), WPB * 32, 0, st>>>(Y, phi, sb, sn, si, B, I, J,
                                                                                            flooring, eps));
   return ssb_check_launch("update_by_iss1", st);

@@ -352,7 +352,9 @@ def test_full_size_properties_and_one_mixture_oracle(N, spatial):
 
 
 @pytest.mark.parametrize("N,I,J,K,spatial", [(2, 37, 48, 5, "IP"), (3, 130, 272, 16, "IP"), (4, 20, 32, 20, "IP2"),
-                                             (2, 257, 512, 16, "IP"), (8, 17, 64, 3, "IP"), (5, 33, 80, 32, "IP")])
+                                             (2, 257, 512, 16, "IP"), (8, 17, 64, 3, "IP"), (5, 33, 80, 32, "IP"),
+                                             (3, 40, 64, 6, "ISS"), (4, 33, 272, 20, "ISS"), (6, 18, 48, 4, "IP2"),
+                                             (7, 10, 32, 16, "IP")])
 def test_fused_tensor_core_path_matches_oracle_and_modular(N, I, J, K, spatial):
     """The fused mma.sync kernels (bf16 hi/lo split, n_frames % 16 == 0, K <= 32) against the fp64 oracle
     and against the modular CUDA-core kernels (fast_path=False); covers ragged bin tiles (I % 16 != 0),
