@@ -136,6 +136,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--modular", action="store_true", help="disable the fused fast path")
+    ap.add_argument("--chunk", type=int, default=0, help="mixtures per chunk plan (0 = library default)")
+    ap.add_argument("--streams", type=int, default=0, help="chunk streams (0 = library default)")
     args = ap.parse_args()
     wl = dict(WORKLOAD, batch=args.batch, n_sources=args.sources, spatial=args.spatial)
     N, I, J, K, B = wl["n_sources"], wl["n_bins"], wl["n_frames"], wl["n_basis"], wl["batch"]
@@ -145,7 +147,8 @@ def main():
     steps, warmup = args.steps, max(args.warmup, 3) if args.impl == "b200" else args.warmup
     config = {"workload": "GaussILRMA-%s n_sources=%d n_bins=%d n_frames=%d n_basis=%d batch=%d per GPU (BASELINE configs[1])"
               % (wl["spatial"], N, I, J, K, B), "global_batch": B * max(args.gpus, 1), "parallelism": "batch-sharded dp%d" % args.gpus,
-              "l2_policy": "inputs larger than L2 (X is %.0f MB per GPU)" % (8.0 * B * N * I * J / 1e6)}
+              "l2_policy": "inputs larger than L2 (X is %.0f MB per GPU)" % (8.0 * B * N * I * J / 1e6),
+              "chunking": "chunk=%s streams=%s (0 = library default)" % (args.chunk, args.streams)}
 
     if args.impl == "reference":
         # CPU arm: the reference path's NumPy restatement on all host cores; rank 0 only.
@@ -189,13 +192,16 @@ def main():
         m = GaussILRMA(n_basis=K, spatial_algorithm=wl["spatial"], record_loss=False, **kw)
         if args.modular:
             m.fast_path = False
+        if args.chunk:
+            m.chunk_size = args.chunk
+        if args.streams:
+            m.n_streams = args.streams
         return m
 
     # ---- device-resident throughput ("value") -------------------------------------------------
     sep = make_sep(scale_restoration=False)
     sep(Xd, n_iter=0, basis=T0, activation=V0)  # binds the plan; state stays on the device
-    for _ in range(warmup):
-        sep.update_once()
+    sep.run_iterations(warmup)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -206,8 +212,9 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     ev0.record()
-    for _ in range(steps):
-        sep.update_once()
+    # K steps = K x update_once over every mixture of the batch (ssspy/bss/base.py:68-77); the engine runs
+    # them chunk-major (mixtures are independent), see ssspy_b200/bss/_engine.py
+    sep.run_iterations(steps)
     ev1.record()
     torch.cuda.synchronize()
     ms_total = ev0.elapsed_time(ev1)
@@ -222,8 +229,7 @@ def main():
         # be shorter than one NVML sampling period); these extra steps are not timed
         t_end = time.perf_counter() + 1.5
         while time.perf_counter() < t_end:
-            for _ in range(steps):
-                sep.update_once()
+            sep.run_iterations(steps)
             torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     if clocks is not None:

@@ -10,6 +10,7 @@ Extension over the reference: ``input`` may be ``(B, N, I, J)`` -- a batch of in
 mixtures -- and may be a CUDA ``torch.Tensor`` (zero-copy in, tensors out).
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -31,6 +32,10 @@ def _state_property(name):
         if name not in self._state:
             raise AttributeError(name)
         val = self._state[name]
+        if name == "output" and self._host_output is not None:
+            return self._host_output if self._batched else self._host_output[0]
+        if _device.is_tensor(val) and val.is_cuda:
+            self._join()
         if val is None or not _device.is_tensor(val) or self._tensor_io:
             if _device.is_tensor(val) and self._cpu_tensor_io:
                 host = torch.empty(val.shape, dtype=val.dtype, pin_memory=True)
@@ -68,10 +73,14 @@ class DeviceSeparatorMixin:
         self._cpu_tensor_io = False  # CPU (pinned) torch tensors in -> CPU tensors out
         self._dX = None
         self._input_host = None
-        self._plan = None
+        self._chunks = []
+        self._streams = []
+        self._ws_slots = []
         self._plan_key = None
-        self._ws = None
         self._loss_buf = None
+        self._pending_h2d = None   # host tensor whose upload is enqueued per chunk by _ensure_plan
+        self._host_output = None   # pinned host copy of `output` filled per chunk by __call__
+        self._host_out_buf = None
 
     # ---- input -----------------------------------------------------------------------------------
     @property
@@ -94,7 +103,14 @@ class DeviceSeparatorMixin:
             raise ValueError("input must have shape (n_channels, n_bins, n_frames) or "
                              "(batch, n_channels, n_bins, n_frames), but given {}.".format(tuple(value.shape)))
         self._batched = value.ndim == 4
-        if self._tensor_io:
+        self._host_output = None
+        self._pending_h2d = None
+        if self._cpu_tensor_io and value.dtype == torch.complex64 and value.is_contiguous():
+            # upload is deferred to the chunk streams so that it overlaps the iterations of earlier chunks
+            x = _device.empty(tuple(value.shape), torch.complex64)
+            self._pending_h2d = value if value.dim() == 4 else value.unsqueeze(0)
+            self._input_host = None
+        elif self._tensor_io:
             x = _device.to_device(value, torch.complex64)
             self._input_host = None
         else:
@@ -116,8 +132,10 @@ class DeviceSeparatorMixin:
         batched_rank = {"demix_filter": 4, "output": 4, "basis": 4, "activation": 4, "variance": 3}[name]
         if t.dim() == batched_rank - 1:
             t = t.unsqueeze(0)
+        if name == "output":
+            self._host_output = None
         cur = self._state.get(name)
-        if _device.is_tensor(cur) and cur.is_cuda and cur.shape == t.shape and self._plan is not None:
+        if _device.is_tensor(cur) and cur.is_cuda and cur.shape == t.shape and self._chunks:
             cur.copy_(t)  # keep the pointer the plan is bound to
         else:
             self._state[name] = t.clone() if t.data_ptr() == (value.data_ptr() if _device.is_tensor(value) else 0) else t
@@ -137,36 +155,109 @@ class DeviceSeparatorMixin:
     def _has(self, name):
         return name in self._state
 
-    # ---- plan ------------------------------------------------------------------------------------
+    # ---- plans: one ssb_plan per sub-batch ("chunk") of mixtures -----------------------------------
+    # Mixtures are independent, so the batch may be cut into chunks that run to completion on their own
+    # CUDA streams: host<->device copies of one chunk overlap the iterations of another, and a chunk
+    # that fits the 126 MB L2 (X + P scratch) is re-read from L2 instead of HBM on every iteration.
+    # ``chunk_size`` (mixtures per chunk; None = one plan over the whole batch) and ``n_streams`` are
+    # plain attributes; ``SSB_CHUNK`` / ``SSB_STREAMS`` override them.
+    chunk_size = None
+    n_streams = 3
+
     def _dims(self):
         B, N, I, J = self._dX.shape
         return int(B), int(N), int(I), int(J)
 
+    def _chunk_layout(self):
+        B = self._dims()[0]
+        cs = os.environ.get("SSB_CHUNK")
+        cs = int(cs) if cs else self.chunk_size
+        if not cs or cs >= B:
+            return [(0, B)]
+        return [(b0, min(b0 + cs, B)) for b0 in range(0, B, cs)]
+
+    def _chunk_streams(self, layout):
+        """Stream of every chunk (None = the current stream when there is a single chunk)."""
+        if len(layout) == 1:
+            return [None]
+        ns = int(os.environ.get("SSB_STREAMS", self.n_streams))
+        if len(self._streams) < ns:
+            self._streams = [torch.cuda.Stream() for _ in range(ns)]
+        return [self._streams[ci % ns] for ci in range(len(layout))]
+
+    def _initial_separate(self, W, Y):
+        """Y = W X chunk by chunk (after the chunk's pending host->device copy of X, if any)."""
+        B, N, I, J = self._dims()
+        layout = self._chunk_layout()
+        streams = self._chunk_streams(layout)
+        cur = torch.cuda.current_stream()
+        fork = None
+        if len(layout) > 1:
+            fork = torch.cuda.Event()
+            fork.record(cur)
+        for (b0, b1), st in zip(layout, streams):
+            st = cur if st is None else st
+            if fork is not None:
+                st.wait_event(fork)
+            with torch.cuda.stream(st):
+                if self._pending_h2d is not None:
+                    self._dX[b0:b1].copy_(self._pending_h2d[b0:b1], non_blocking=True)
+                _lib.call("ssb_separate", self._dX[b0:b1].data_ptr(), W[b0:b1].data_ptr(), Y[b0:b1].data_ptr(), b1 - b0,
+                          N, I, J, st.cuda_stream)
+        self._pending_h2d = None
+
     def _ensure_plan(self):
-        """(Re)create and bind the ssb_plan when shapes, options or buffers changed."""
+        """(Re)create and bind the chunk plans when shapes, options or buffers changed.  Pending
+        host->device copies of the input are enqueued chunk by chunk on the chunk streams."""
         cfg = self._plan_config()
-        ptrs = tuple(_device.ptr(self._dev(k)) for k in ("demix_filter", "output", "basis", "activation", "variance"))
-        key = (bytes(cfg), self._dX.data_ptr()) + ptrs
-        if self._plan is not None and key == self._plan_key:
+        names = ("demix_filter", "output", "basis", "activation", "variance")
+        tens = [self._dev(k) for k in names]
+        layout = self._chunk_layout()
+        key = (bytes(cfg), self._dX.data_ptr(), tuple(layout)) + tuple(_device.ptr(t) for t in tens)
+        if self._chunks and key == self._plan_key:
             return
         self._destroy_plan()
-        plan = ctypes.c_void_p()
-        _lib.call("ssb_plan_create", ctypes.byref(cfg), ctypes.byref(plan))
-        self._plan = plan
-        nbytes = ctypes.c_size_t(0)
-        _lib.call("ssb_plan_workspace_bytes", plan, ctypes.byref(nbytes))
-        if self._ws is None or self._ws.numel() < nbytes.value:
-            self._ws = _device.empty((max(nbytes.value, 256),), torch.uint8)
-        _lib.call("ssb_plan_bind", plan, self._dX.data_ptr(), ptrs[0], ptrs[1], ptrs[2], ptrs[3], ptrs[4],
-                  self._ws.data_ptr(), self._ws.numel())
-        _lib.call("ssb_plan_prepare", plan, _device.stream_ptr())
+        multi = len(layout) > 1
+        ns = int(os.environ.get("SSB_STREAMS", self.n_streams)) if multi else 1
+        streams = self._chunk_streams(layout)
+        cur = torch.cuda.current_stream()
+        fork = None
+        if multi:
+            fork = torch.cuda.Event()
+            fork.record(cur)
+        ws_need = 0
+        for ci, (b0, b1) in enumerate(layout):
+            ccfg = self._plan_config()
+            ccfg.n_batch = b1 - b0
+            plan = ctypes.c_void_p()
+            _lib.call("ssb_plan_create", ctypes.byref(ccfg), ctypes.byref(plan))
+            nbytes = ctypes.c_size_t(0)
+            _lib.call("ssb_plan_workspace_bytes", plan, ctypes.byref(nbytes))
+            ws_need = max(ws_need, nbytes.value, 256)
+            self._chunks.append({"b0": b0, "b1": b1, "plan": plan, "slot": ci % ns, "stream": streams[ci]})
+        if len(self._ws_slots) < ns or any(w.numel() < ws_need for w in self._ws_slots[:ns]):
+            self._ws_slots = [_device.empty((ws_need,), torch.uint8) for _ in range(ns)]
+        for ch in self._chunks:
+            b0, b1 = ch["b0"], ch["b1"]
+            st = ch["stream"] if ch["stream"] is not None else cur
+            if fork is not None:
+                st.wait_event(fork)
+            with torch.cuda.stream(st):
+                if self._pending_h2d is not None:
+                    self._dX[b0:b1].copy_(self._pending_h2d[b0:b1], non_blocking=True)
+                ws = self._ws_slots[ch["slot"]]
+                ptrs = [0 if t is None else t[b0:b1].data_ptr() for t in tens]
+                _lib.call("ssb_plan_bind", ch["plan"], self._dX[b0:b1].data_ptr(), ptrs[0], ptrs[1], ptrs[2], ptrs[3],
+                          ptrs[4], ws.data_ptr(), ws.numel())
+                _lib.call("ssb_plan_prepare", ch["plan"], st.cuda_stream)
+        self._pending_h2d = None
         self._plan_key = key
 
     def _destroy_plan(self):
-        if getattr(self, "_plan", None) is not None:
-            _lib.call("ssb_plan_destroy", self._plan)
-            self._plan = None
-            self._plan_key = None
+        for ch in getattr(self, "_chunks", []):
+            _lib.call("ssb_plan_destroy", ch["plan"])
+        self._chunks = []
+        self._plan_key = None
 
     def __del__(self):
         try:
@@ -174,22 +265,109 @@ class DeviceSeparatorMixin:
         except Exception:
             pass
 
-    def _plan_call(self, fn, *extra):
+    def _join(self):
+        """Make the current stream wait for everything enqueued on the chunk streams."""
+        if len(self._chunks) > 1:
+            cur = torch.cuda.current_stream()
+            for st in {id(c["stream"]): c["stream"] for c in self._chunks}.values():
+                ev = torch.cuda.Event()
+                ev.record(st)
+                cur.wait_event(ev)
+
+    def _for_chunks(self, fn, fork=True):
+        """Enqueue ``fn(chunk, stream_ptr)`` for every chunk on its stream (after the current stream's
+        work when ``fork``)."""
         self._ensure_plan()
-        _lib.call(fn, self._plan, *extra, _device.stream_ptr())
+        if len(self._chunks) == 1:
+            fn(self._chunks[0], _device.stream_ptr())
+            return
+        if fork:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            for st in {id(c["stream"]): c["stream"] for c in self._chunks}.values():
+                st.wait_event(ev)
+        for ch in self._chunks:
+            with torch.cuda.stream(ch["stream"]):
+                fn(ch, ch["stream"].cuda_stream)
+
+    def _plan_call(self, fn, *extra):
+        self._for_chunks(lambda ch, sp: _lib.call(fn, ch["plan"], *extra, sp))
+        self._join()
 
     def _set_flooring(self, flooring_fn):
         mode, eps = flooring_to_enum(flooring_fn)
         self._ensure_plan()
-        _lib.call("ssb_plan_set_flooring", self._plan, mode, eps)
+        for ch in self._chunks:
+            _lib.call("ssb_plan_set_flooring", ch["plan"], mode, eps)
 
     def _loss_from_device(self):
         B = self._dims()[0]
         if self._loss_buf is None or self._loss_buf.numel() < B:
             self._loss_buf = _device.empty((B,), torch.float64)
-        self._plan_call("ssb_compute_loss", self._loss_buf.data_ptr())
-        vals = self._loss_buf[:B].cpu().numpy()
+        buf = self._loss_buf
+        self._for_chunks(lambda ch, sp: _lib.call("ssb_compute_loss", ch["plan"], buf[ch["b0"]:].data_ptr(), sp))
+        self._join()
+        vals = buf[:B].cpu().numpy()
         return vals.copy() if self._batched else float(vals[0])
+
+    def _run_iterations(self, n_iter, record_loss, initial_loss=False, tail=None):
+        """n_iter x update_once for every chunk, chunk-major (each chunk runs to completion on its
+        stream); ``tail(chunk, stream_ptr)`` is enqueued right behind a chunk's iterations.  Returns
+        the (n_rows, B) loss array (row 0 = loss before the loop when ``initial_loss``)."""
+        B = self._dims()[0]
+        n_rows = (n_iter if record_loss else 0) + (1 if initial_loss else 0)
+        bufs = {}
+
+        def work(ch, sp):
+            nb = ch["b1"] - ch["b0"]
+            buf = None
+            if n_rows:
+                buf = bufs[ch["b0"]] = _device.empty((n_rows, nb), torch.float64)
+            if initial_loss:
+                _lib.call("ssb_compute_loss", ch["plan"], buf.data_ptr(), sp)
+            if n_iter > 0:
+                lp = buf[1 if initial_loss else 0:].data_ptr() if record_loss else 0
+                _lib.call("ssb_run", ch["plan"], int(n_iter), lp, sp)
+            if tail is not None:
+                tail(ch, sp)
+
+        self._for_chunks(work)
+        self._join()
+        if not n_rows:
+            return None
+        out = np.empty((n_rows, B))
+        for b0, t in bufs.items():
+            out[:, b0:b0 + t.shape[1]] = t.cpu().numpy()
+        return out
+
+    def _stock_pipeline(self, n_iter, initial_call, pb):
+        """The whole stock ``__call__`` after ``_reset`` as one pipeline per chunk: [initial loss] ->
+        n_iter x update_once -> scale restoration / final separate -> device->host copy of the chunk's
+        output (pinned host tensors in => pinned host tensor out)."""
+        self._set_flooring(self.flooring_fn)
+        Y = self._dev("output")
+        host = None
+        if self._cpu_tensor_io:
+            if self._host_out_buf is None or self._host_out_buf.shape != Y.shape:
+                self._host_out_buf = torch.empty(Y.shape, dtype=Y.dtype, pin_memory=True)
+            host = self._host_out_buf
+        has_w = self._state.get("demix_filter") is not None
+
+        def tail(ch, sp):
+            if pb:
+                _lib.call("ssb_restore_scale", ch["plan"], sp)
+            elif has_w:
+                _lib.call("ssb_plan_separate", ch["plan"], sp)
+            if host is not None:
+                host[ch["b0"]:ch["b1"]].copy_(Y[ch["b0"]:ch["b1"]], non_blocking=True)
+
+        rec = bool(self.record_loss)
+        losses = self._run_iterations(n_iter, rec, initial_loss=bool(initial_call and rec), tail=tail)
+        if host is not None:
+            torch.cuda.current_stream().synchronize()  # the joins above made it wait for every chunk
+            self._host_output = host
+        if losses is not None:
+            self.loss.extend(losses[i].copy() if self._batched else float(losses[i, 0]) for i in range(losses.shape[0]))
 
     # ---- separate --------------------------------------------------------------------------------
     def separate(self, input, demix_filter):

@@ -90,8 +90,9 @@ class ILRMABase(DeviceSeparatorMixin, IterativeMethodBase):
         if W is None:
             self.separate(self.input, demix_filter=None)  # raises like the reference (None @ ndarray)
         Y = torch.empty_like(self._dX)
-        _lib.call("ssb_separate", self._dX.data_ptr(), W.data_ptr(), Y.data_ptr(), B, N, I, J, _device.stream_ptr())
+        self._initial_separate(W, Y)
         self._state["output"] = Y
+        self._host_output = None
         self._init_nmf(flooring_fn=flooring_fn, rng=self.rng)
         self._plan_key = None
 
@@ -245,33 +246,33 @@ class GaussILRMA(ILRMABase):
         """Separate ``input`` of shape (n_channels, n_bins, n_frames) [or (batch, ...)] (ilrma.py:820-855)."""
         self.input = input
         self._reset(flooring_fn=self.flooring_fn, **kwargs)
-        self._iterate(n_iter=n_iter, initial_call=initial_call)
+        if self._stock_call():
+            # base.py:48-77 + scale restoration + output copy as one pipeline per chunk of mixtures
+            self._stock_pipeline(n_iter, initial_call, pb=bool(self.scale_restoration))
+            return self.output
+        IterativeMethodBase.__call__(self, n_iter=n_iter, initial_call=initial_call)
         if self.scale_restoration:
             self.restore_scale()
         elif self._state.get("demix_filter") is not None:
             self._plan_call("ssb_plan_separate")
         return self.output
 
-    def _iterate(self, n_iter, initial_call):
-        """base.py:48-77.  Without callbacks or user overrides the whole loop is one C call."""
-        cls = type(self)
-        stock = (self.callbacks is None and cls.update_once is GaussILRMA.update_once
-                 and cls.compute_loss is GaussILRMA.compute_loss and self._stock_update_methods())
-        if not stock:
-            IterativeMethodBase.__call__(self, n_iter=n_iter, initial_call=initial_call)
-            return
-        if initial_call and self.record_loss:
-            self.loss.append(self.compute_loss())
-        if n_iter <= 0:
-            return
+    def run_iterations(self, n_iter):
+        """``n_iter`` x ``update_once`` on the current state without loss recording, callbacks or scale
+        restoration (the loop of ssspy/bss/base.py:68-77).  Chunks of the batch run concurrently."""
         self._set_flooring(self.flooring_fn)
-        B = self._dims()[0]
-        buf = _device.empty((n_iter, B), torch.float64) if self.record_loss else None
-        self._ensure_plan()
-        _lib.call("ssb_run", self._plan, int(n_iter), _device.ptr(buf), _device.stream_ptr())
-        if self.record_loss:
-            vals = buf.cpu().numpy()
-            self.loss.extend(vals[i].copy() if self._batched else float(vals[i, 0]) for i in range(n_iter))
+        self._run_iterations(int(n_iter), False)
+
+    def _stock_call(self):
+        """True when nothing user-defined has to run between iterations: no callbacks, no overridden
+        update / loss / scale-restoration methods, projection-back (or no) scale restoration."""
+        cls = type(self)
+        sr = self.scale_restoration
+        return (self.callbacks is None and cls.update_once is GaussILRMA.update_once
+                and cls.compute_loss is GaussILRMA.compute_loss and self._stock_update_methods()
+                and cls.restore_scale is ILRMABase.restore_scale
+                and cls.apply_projection_back is ILRMABase.apply_projection_back
+                and (type(sr) is bool or sr in PROJECTION_BACK_KEYWORDS))
 
     def _stock_update_methods(self):
         cls = type(self)

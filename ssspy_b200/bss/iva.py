@@ -66,8 +66,9 @@ class IVABase(DeviceSeparatorMixin, IterativeMethodBase):
         if W is None:
             self.separate(self.input, demix_filter=None)  # raises like the reference
         Y = torch.empty_like(self._dX)
-        _lib.call("ssb_separate", self._dX.data_ptr(), W.data_ptr(), Y.data_ptr(), B, N, I, J, _device.stream_ptr())
+        self._initial_separate(W, Y)
         self._state["output"] = Y
+        self._host_output = None
         self._plan_key = None
 
     def compute_loss(self):
@@ -135,33 +136,31 @@ class AuxIVA(AuxIVABase):
             _not_on_device("AuxIVA with user-defined contrast functions (use AuxLaplaceIVA / AuxGaussIVA)")
         self.input = input
         self._reset(**kwargs)
-        self._iterate(n_iter=n_iter, initial_call=initial_call)
+        if self._stock_call():
+            self._stock_pipeline(n_iter, initial_call, pb=bool(self.scale_restoration))
+            return self.output
+        IterativeMethodBase.__call__(self, n_iter=n_iter, initial_call=initial_call)
         if self.scale_restoration:
             self.restore_scale()
         elif self._state.get("demix_filter") is not None:
             self._plan_call("ssb_plan_separate")
         return self.output
 
-    def _iterate(self, n_iter, initial_call):
-        cls = type(self)
-        stock = (self.callbacks is None and cls.update_once in (AuxIVA.update_once, AuxGaussIVA.update_once)
-                 and cls.compute_loss is IVABase.compute_loss
-                 and cls.update_source_model in (AuxIVA.update_source_model, AuxGaussIVA.update_source_model))
-        if not stock:
-            IterativeMethodBase.__call__(self, n_iter=n_iter, initial_call=initial_call)
-            return
-        if initial_call and self.record_loss:
-            self.loss.append(self.compute_loss())
-        if n_iter <= 0:
-            return
+    def run_iterations(self, n_iter):
+        """``n_iter`` x ``update_once`` on the current state (ssspy/bss/base.py:68-77) without loss
+        recording, callbacks or scale restoration."""
         self._set_flooring(self.flooring_fn)
-        B = self._dims()[0]
-        buf = _device.empty((n_iter, B), torch.float64) if self.record_loss else None
-        self._ensure_plan()
-        _lib.call("ssb_run", self._plan, int(n_iter), _device.ptr(buf), _device.stream_ptr())
-        if self.record_loss:
-            vals = buf.cpu().numpy()
-            self.loss.extend(vals[i].copy() if self._batched else float(vals[i, 0]) for i in range(n_iter))
+        self._run_iterations(int(n_iter), False)
+
+    def _stock_call(self):
+        cls = type(self)
+        sr = self.scale_restoration
+        return (self.callbacks is None and cls.update_once in (AuxIVA.update_once, AuxGaussIVA.update_once)
+                and cls.compute_loss is IVABase.compute_loss
+                and cls.update_source_model in (AuxIVA.update_source_model, AuxGaussIVA.update_source_model)
+                and cls.restore_scale is IVABase.restore_scale
+                and cls.apply_projection_back is IVABase.apply_projection_back
+                and (type(sr) is bool or sr in PROJECTION_BACK_KEYWORDS))
 
     def __repr__(self):
         s = "AuxIVA(spatial_algorithm={spatial_algorithm}, scale_restoration={scale_restoration}"
