@@ -133,13 +133,14 @@ def main():
     ap.add_argument("--batch", type=int, default=WORKLOAD["batch"], help="mixtures per GPU")
     ap.add_argument("--sources", type=int, default=WORKLOAD["n_sources"])
     ap.add_argument("--spatial", default=WORKLOAD["spatial"])
+    ap.add_argument("--frames", type=int, default=WORKLOAD["n_frames"], help="n_frames (experiments only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--modular", action="store_true", help="disable the fused fast path")
     ap.add_argument("--chunk", type=int, default=0, help="mixtures per chunk plan (0 = library default)")
     ap.add_argument("--streams", type=int, default=0, help="chunk streams (0 = library default)")
     args = ap.parse_args()
-    wl = dict(WORKLOAD, batch=args.batch, n_sources=args.sources, spatial=args.spatial)
+    wl = dict(WORKLOAD, batch=args.batch, n_sources=args.sources, spatial=args.spatial, n_frames=args.frames)
     N, I, J, K, B = wl["n_sources"], wl["n_bins"], wl["n_frames"], wl["n_basis"], wl["batch"]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

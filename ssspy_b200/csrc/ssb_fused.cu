@@ -466,23 +466,30 @@ __global__ void __launch_bounds__(FW * 32) kf_activation(const float* __restrict
 #pragma unroll
     for (int c = 0; c < 4; ++c) num[q][c] = den[q][c] = 0.f;
 
-  // prefetch of P for bins [ibase, ibase+16) x this warp's 16 frames into ring slot `stage`
+  // prefetch of P for bins [ibase, ibase+16) x this warp's 16 frames into ring slot `stage`.  The P
+  // scratch is padded by 16 rows, so the (masked) rows past the last bin need no clamping; all
+  // per-lane offsets are loop invariant.
+  int poff[8];
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) poff[(h * 2 + rr) * 2 + e] = (8 * h + 2 * t + e) * J + fr[rr];
+  const uint32_t pw_s = (uint32_t)__cvta_generic_to_shared(pw);
   auto issue = [&](int ibase, int stage) {
+    const float* p = Pb + (size_t)ibase * J;
+    const uint32_t d = pw_s + stage * (NLD * 32 * 4);
 #pragma unroll
-    for (int h = 0; h < 2; ++h)
-#pragma unroll
-      for (int rr = 0; rr < 2; ++rr)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int i = min(ibase + 8 * h + 2 * t + e, I - 1);
-          cp_async4(pw + (stage * NLD + (h * 2 + rr) * 2 + e) * 32, Pb + (size_t)i * J + fr[rr]);
-        }
+    for (int k = 0; k < 8; ++k)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + k * 128), "l"(p + poff[k]) : "memory");
   };
   int step = 0;
   if (warp_active) {
     issue(0, 0);
     cp_async_commit();
   }
+  const bool frames_full = fvalid[0] && fvalid[1];
 
   for (int ib0 = 0; ib0 < I; ib0 += BCH) {
     __syncthreads();
@@ -534,26 +541,43 @@ __global__ void __launch_bounds__(FW * 32) kf_activation(const float* __restrict
       // ---- elementwise at (frame rr, bin bb+8h+2t+e) -----------------------------------------------
       cp_async_wait<1>();
       uint32_t Ahi[4], Alo[4], Bhi[4], Blo[4];
+      const float* pst = pw + (step & 1) * (NLD * 32);
+      const int lim = I - (ib0 + bb);  // valid bins in this 16-bin step
+      if (lim >= 16 && frames_full) {
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < 2; ++h)
 #pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-          float a_[2], i_[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const bool ok = (ib0 + bb + 8 * h + 2 * t + e < I) && fvalid[rr];
-            const float p = pw[((step & 1) * NLD + (h * 2 + rr) * 2 + e) * 32];
-            const float iv = ok ? fast_rcp(R[h][rr * 2 + e]) : 0.f;
-            i_[e] = iv;
-            a_[e] = ok ? p * iv * iv : 0.f;
+          for (int rr = 0; rr < 2; ++rr) {
+            const float iv0 = fast_rcp(R[h][rr * 2]), iv1 = fast_rcp(R[h][rr * 2 + 1]);
+            const float p0 = pst[((h * 2 + rr) * 2) * 32], p1 = pst[((h * 2 + rr) * 2 + 1) * 32];
+            const Split sa = split2(p0 * iv0 * iv0, p1 * iv1 * iv1);
+            const Split sb = split2(iv0, iv1);
+            Ahi[h * 2 + rr] = sa.hi;
+            Alo[h * 2 + rr] = sa.lo;
+            Bhi[h * 2 + rr] = sb.hi;
+            Blo[h * 2 + rr] = sb.lo;
           }
-          const Split sa = split2(a_[0], a_[1]);
-          const Split sb = split2(i_[0], i_[1]);
-          Ahi[h * 2 + rr] = sa.hi;
-          Alo[h * 2 + rr] = sa.lo;
-          Bhi[h * 2 + rr] = sb.hi;
-          Blo[h * 2 + rr] = sb.lo;
-        }
+      } else {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr) {
+            float a_[2], i_[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const bool ok = (8 * h + 2 * t + e < lim) && fvalid[rr];
+              const float p = pst[((h * 2 + rr) * 2 + e) * 32];
+              const float iv = ok ? fast_rcp(R[h][rr * 2 + e]) : 0.f;
+              i_[e] = iv;
+              a_[e] = ok ? p * iv * iv : 0.f;
+            }
+            const Split sa = split2(a_[0], a_[1]);
+            const Split sb = split2(i_[0], i_[1]);
+            Ahi[h * 2 + rr] = sa.hi;
+            Alo[h * 2 + rr] = sa.lo;
+            Bhi[h * 2 + rr] = sb.hi;
+            Blo[h * 2 + rr] = sb.lo;
+          }
       }
       // ---- GEMM2: num^T += A^T T, den^T += B^T T  (contraction over the 16 bins) -----------------
 #pragma unroll

@@ -154,7 +154,8 @@ size_t carve(ssb_plan* p, char* base) {
   const ssb_config& c = p->cfg;
   const size_t B = c.n_batch, N = c.n_sources, I = c.n_bins, J = c.n_frames;
   Carver cv{base};
-  p->big = p->ilrma() ? cv.take<float>(B * N * I * J) : nullptr;
+  // + 16 rows of slack: the fused activation kernel prefetches whole 16-bin tiles of P without clamping
+  p->big = p->ilrma() ? cv.take<float>(B * N * I * J + 16 * J) : nullptr;
   p->phi_iva = cv.take<float>(B * N * J);
   p->r2 = cv.take<float>(B * N * J);
   p->U = cv.take<cf>(B * I * N * N * N);

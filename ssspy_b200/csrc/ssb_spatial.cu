@@ -592,6 +592,90 @@ __global__ void k_iss1_smem(cf* __restrict__ Y, const float* __restrict__ phi, l
     for (int j = lane; j < J; j += 32) Y[base + m * cs + j] = ys[m * J + j];
 }
 
+// ISS1, one CTA (ISS_NW warps) per (b,i): the bin's Y and weight slabs live in shared memory, the
+// frames are split over all threads and the 3N statistics of each of the N sequential steps are
+// combined through shared memory (one __syncthreads per step).  Small per-CTA footprint (N*J*12 bytes)
+// => many resident warps, unlike the warp-per-bin variant above.
+constexpr int ISS_NW = 4;
+template <int N>
+__global__ void __launch_bounds__(ISS_NW * 32) k_iss1_cta(cf* __restrict__ Y, const float* __restrict__ phi,
+                                                          long long sb, long long sn, long long si, int I, int J,
+                                                          int flooring, float eps) {
+  extern __shared__ __align__(16) unsigned char iss_smem[];
+  __shared__ float red[2][ISS_NW][3 * N];
+  cf* ys = reinterpret_cast<cf*>(iss_smem);
+  float* ps = reinterpret_cast<float*>(ys + (size_t)N * J);
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int bi = blockIdx.x;
+  const int b = bi / I, i = bi - b * I;
+  const size_t base = ((size_t)b * N * I + i) * J;
+  const size_t cs = (size_t)I * J;
+  const float* ph0 = phi + (size_t)b * sb + (size_t)i * si;
+  const float invJ = 1.0f / (float)J;
+#pragma unroll
+  for (int m = 0; m < N; ++m)
+    for (int j = tid; j < J; j += ISS_NW * 32) {
+      ys[m * J + j] = Y[base + m * cs + j];
+      ps[m * J + j] = ph0[(size_t)m * sn + j];
+    }
+  // every thread only ever touches its own frames of the slab, so no barrier is needed for ys/ps
+  for (int n = 0; n < N; ++n) {
+    float nr[N], ni[N], dn[N];
+#pragma unroll
+    for (int m = 0; m < N; ++m) nr[m] = ni[m] = dn[m] = 0.f;
+    for (int j = tid; j < J; j += ISS_NW * 32) {
+      const cf yn = ys[n * J + j];
+      const float a2 = yn.x * yn.x + yn.y * yn.y;
+#pragma unroll
+      for (int m = 0; m < N; ++m) {
+        const float ph = ps[m * J + j];
+        const cf ym = ys[m * J + j];
+        const float pr = ph * ym.x, pi = ph * ym.y;
+        nr[m] = fmaf(pr, yn.x, fmaf(pi, yn.y, nr[m]));
+        ni[m] = fmaf(pi, yn.x, fmaf(-pr, yn.y, ni[m]));
+        dn[m] = fmaf(ph, a2, dn[m]);
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < N; ++m) {
+      const float a = warp_sum(nr[m]), c = warp_sum(ni[m]), d = warp_sum(dn[m]);
+      if (lane == 0) {
+        red[n & 1][w][3 * m] = a;
+        red[n & 1][w][3 * m + 1] = c;
+        red[n & 1][w][3 * m + 2] = d;
+      }
+    }
+    __syncthreads();
+    cf v[N];
+#pragma unroll
+    for (int m = 0; m < N; ++m) {
+      float a = 0.f, c = 0.f, d = 0.f;
+#pragma unroll
+      for (int ww = 0; ww < ISS_NW; ++ww) {  // fixed order: deterministic
+        a += red[n & 1][ww][3 * m];
+        c += red[n & 1][ww][3 * m + 1];
+        d += red[n & 1][ww][3 * m + 2];
+      }
+      const float d_ = ssb_floor(d * invJ, flooring, eps);
+      if (m == n) v[m] = make_float2(1.0f - 1.0f / sqrtf(d_), 0.f);
+      else v[m] = make_float2(a * invJ / d_, c * invJ / d_);
+    }
+    for (int j = tid; j < J; j += ISS_NW * 32) {
+      const cf yn = ys[n * J + j];
+#pragma unroll
+      for (int m = 0; m < N; ++m) {
+        cf ym = ys[m * J + j];
+        ym.x -= v[m].x * yn.x - v[m].y * yn.y;
+        ym.y -= v[m].x * yn.y + v[m].y * yn.x;
+        ys[m * J + j] = ym;
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < N; ++m)
+    for (int j = tid; j < J; j += ISS_NW * 32) Y[base + m * cs + j] = ys[m * J + j];
+}
+
 // ------------------------------------------------------------------------------------------------
 // projection back, filter form (ssspy/algorithm/projection_back.py:87-99): one warp per matrix.
 // scale_out[mat*N + n] (optional) receives (W^-1)[ref, n] for the projection-back normalisation.
@@ -788,21 +872,16 @@ int ssbk_ip2(cf* W, const cf* U, int n_mat, int N, const int* pairs, int n_pairs
 
 int ssbk_iss1(cf* Y, const float* phi, long long sb, long long sn, long long si, int B, int N, int I, int J,
               int flooring, float eps, cudaStream_t st) {
-  // shared-memory slab variant when at least one (source x frame) slab of Y + weights fits
-  const size_t per_warp = (size_t)N * J * (sizeof(cf) + sizeof(float));
-  const size_t budget = 100 * 1024;  // two CTAs per SM
-  int wpb = (int)(budget / per_warp);
-  if (wpb > 8) wpb = 8;
-  if (wpb >= 1) {
-    const size_t sm = per_warp * wpb;
+  // CTA-per-bin shared-memory variant when the (source x frame) slab of Y + weights fits one CTA
+  const size_t slab = (size_t)N * J * (sizeof(cf) + sizeof(float));
+  if (slab <= 200 * 1024) {
     SSB_DISPATCH_N(N, {
       static bool attr_set = false;
       if (!attr_set) {
-        SSB_CUDA(cudaFuncSetAttribute(k_iss1_smem<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SSB_CUDA(cudaFuncSetAttribute(k_iss1_cta<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
       }
-      k_iss1_smem<NN><<<blocks_for((long long)B * I, wpb), wpb * 32, sm, st>>>(Y, phi, sb, sn, si, B, I, J, flooring, eps,
-                                                                             wpb);
+      k_iss1_cta<NN><<<B * I, ISS_NW * 32, slab, st>>>(Y, phi, sb, sn, si, I, J, flooring, eps);
     });
     return ssb_check_launch("update_by_iss1", st);
   }
