@@ -1059,7 +1059,7 @@ template <int N, int KS>
 int launch_all(const ssb_config* c, const cf* X, cf* W, float* T, float* V, float* P, cf* U, cudaStream_t st) {
   const int B = c->n_batch, I = c->n_bins, J = c->n_frames, K = c->n_basis;
   constexpr int KP = 16 * KS;
-  constexpr bool STG = N <= 2;  // cp.async staging of X in the source-model kernels
+  constexpr bool STG = N <= 4;  // cp.async staging of X in the source-model kernels
   constexpr int G = CovShape<N>::G;
   const size_t ring16 = (size_t)FW * XSTAGES * 4 * N * 32 * sizeof(float4);
   const size_t sm_basis = (size_t)(2 * JC * (KP + PADH) + 2 * KP * (JC + PADH)) * sizeof(__nv_bfloat16) +
