@@ -251,12 +251,30 @@ def main():
     abytes_step = algorithmic_bytes_per_mixture_iteration(N, I, J, K) * B
     peak, peak_src = hbm_peak()
     achieved = abytes_step / (ms_per_step / 1e3) / 1e9
+    # dominant kernel on its own: its compulsory bytes (what it must read/write even in a perfectly fused
+    # iteration: X once + the small T/V/W state) over its average launch duration, and the DRAM traffic
+    # ncu measured for one launch of it (profiles/r1_ncu_traffic.json, same workload)
+    dom_alg = {"fused_basis": 8 * N * I * J + 4 * (2 * N * I * K + N * K * J),
+               "fused_phi_cov": 8 * N * I * J + 4 * (N * I * K + N * K * J) + 8 * N * N * N * I,
+               "fused_activation": 4 * N * I * J + 4 * (N * I * K + 2 * N * K * J)}.get(dom[0])
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")) as f:
+            tj = json.load(f)
+        if (N, I, J, K, B) == (2, 1025, 512, 16, 64):
+            traffic = tj["dram_bytes_per_launch"].get("k" + dom[0][1:].replace("used", "", 1) if False else {"fused_basis": "kf_basis", "fused_activation": "kf_activation", "fused_phi_cov": "kf_phi_cov"}.get(dom[0], ""))
+    except Exception:
+        traffic = None
+    dom_ms = dom[2] / max(dom[1], 1)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src,
-                "scope": "one update_once step over the per-GPU batch (%d launches); algorithmic bytes/step = %.1f MB"
-                         % (launches // steps, abytes_step / 1e6),
-                "dominant_kernel": dom[0], "dominant_kernel_ms": dom[2] / max(dom[1], 1),
+                "traffic": traffic, "peak_source": peak_src,
+                "scope": "achieved/frac: algorithmic bytes of one whole update_once step over the per-GPU batch "
+                         "(SURVEY.md 8(d): %.1f MB, %d launches) / step time; traffic: ncu DRAM bytes of one launch of the "
+                         "dominant kernel" % (abytes_step / 1e6, launches // steps),
+                "dominant_kernel": dom[0], "dominant_kernel_ms": dom_ms,
                 "dominant_kernel_share": dom[2] / total_prof,
+                "dominant_kernel_achieved": (dom_alg * B / (dom_ms / 1e3) / 1e9) if dom_alg else None,
+                "dominant_kernel_frac": (dom_alg * B / (dom_ms / 1e3) / 1e9 / peak) if dom_alg else None,
                 "kernels_ms_per_step": {k[0]: round(k[2] / prof_steps, 4) for k in kernels}}
 
     # ---- end to end through the public API with host buffers ------------------------------------
