@@ -262,7 +262,8 @@ def main():
         with open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")) as f:
             tj = json.load(f)
         if (N, I, J, K, B) == (2, 1025, 512, 16, 64):
-            traffic = tj["dram_bytes_per_launch"].get("k" + dom[0][1:].replace("used", "", 1) if False else {"fused_basis": "kf_basis", "fused_activation": "kf_activation", "fused_phi_cov": "kf_phi_cov"}.get(dom[0], ""))
+            traffic = tj["dram_bytes_per_launch"].get({"fused_basis": "kf_basis", "fused_activation": "kf_activation",
+                                                       "fused_phi_cov": "kf_phi_cov"}.get(dom[0], ""))
     except Exception:
         traffic = None
     dom_ms = dom[2] / max(dom[1], 1)

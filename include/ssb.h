@@ -37,7 +37,12 @@ extern "C" {
 enum {
   SSB_MODEL_ILRMA_GAUSS = 0, /* ssspy/bss/ilrma.py:582 GaussILRMA      */
   SSB_MODEL_IVA_LAPLACE = 1, /* ssspy/bss/iva.py:2976 AuxLaplaceIVA    */
-  SSB_MODEL_IVA_GAUSS = 2    /* ssspy/bss/iva.py:3131 AuxGaussIVA      */
+  SSB_MODEL_IVA_GAUSS = 2,   /* ssspy/bss/iva.py:3131 AuxGaussIVA      */
+  SSB_MODEL_FASTMNMF_GAUSS = 3 /* ssspy/bss/mnmf.py:1076 FastGaussMNMF (n_sources == n_channels): the W slot of
+                                  ssb_plan_bind holds the diagonaliser Q[B,I,N,N] c64 (mnmf.py:557-559), the
+                                  `variance` slot the spatial property D[B,I,N,N] f32 (mnmf.py:594-596);
+                                  `spatial` selects the diagonaliser algorithm IP1 / IP2 (mnmf.py:1430-1447);
+                                  ssb_plan_separate is the multichannel Wiener filter (mnmf.py:1174-1217) */
 };
 /* spatial_algorithm (ssspy/bss/ilrma.py:27, ssspy/bss/iva.py:44) */
 enum { SSB_SPATIAL_IP1 = 0, SSB_SPATIAL_IP2 = 1, SSB_SPATIAL_ISS1 = 2 };

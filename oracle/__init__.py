@@ -13,6 +13,7 @@ the reference path named in SURVEY.md section 8(a):
 * ``oracle.projection_back``  <- ssspy/algorithm/projection_back.py
 * ``oracle.ilrma``            <- ssspy/bss/ilrma.py (GaussILRMA, MM/ME, IP1/IP2/ISS1)
 * ``oracle.iva``              <- ssspy/bss/iva.py  (AuxLaplaceIVA / AuxGaussIVA)
+* ``oracle.mnmf``             <- ssspy/bss/mnmf.py (FastGaussMNMF, IP1/IP2 diagonaliser)
 
 Unlike the reference it never materialises the (I,N,N,N,J) broadcast
 temporaries (ssspy/bss/ilrma.py:1500-1505); contractions are einsum/matmul.
@@ -26,6 +27,6 @@ committed as ``tests/golden/*.npz``) and by the docstring known-answer values of
 ``tests/test_oracle_golden.py`` checks every fixture.
 """
 
-from . import ilrma, iva, linalg, projection_back, spatial  # noqa: F401
+from . import ilrma, iva, linalg, mnmf, projection_back, spatial  # noqa: F401
 
 EPS = 1e-10

@@ -13,7 +13,7 @@ SSB_MAX_SOURCES = 8
 SSB_MAX_BASIS = 64
 SSB_MAX_PAIRS = 64
 
-MODEL_ILRMA_GAUSS, MODEL_IVA_LAPLACE, MODEL_IVA_GAUSS = 0, 1, 2
+MODEL_ILRMA_GAUSS, MODEL_IVA_LAPLACE, MODEL_IVA_GAUSS, MODEL_FASTMNMF_GAUSS = 0, 1, 2, 3
 SPATIAL_IP1, SPATIAL_IP2, SPATIAL_ISS1 = 0, 1, 2
 SOURCE_MM, SOURCE_ME = 0, 1
 FLOOR_MAX, FLOOR_ADD, FLOOR_NONE = 0, 1, 2

@@ -24,7 +24,11 @@ _STATE_DTYPES = {
     "basis": torch.float32,
     "activation": torch.float32,
     "variance": torch.float32,
+    "diagonalizer": torch.complex64,
+    "spatial": torch.float32,
 }
+_STATE_RANKS = {"demix_filter": 4, "output": 4, "basis": 4, "activation": 4, "variance": 3, "diagonalizer": 4,
+                "spatial": 4}
 
 
 def _state_property(name):
@@ -65,6 +69,10 @@ class DeviceSeparatorMixin:
     basis = _state_property("basis")
     activation = _state_property("activation")
     variance = _state_property("variance")
+    diagonalizer = _state_property("diagonalizer")
+    spatial = _state_property("spatial")
+    # which state entries fill the (W, Y, T, V, variance) slots of ssb_plan_bind
+    _plan_slots = ("demix_filter", "output", "basis", "activation", "variance")
 
     def _init_device_state(self):
         self._state = {}
@@ -129,7 +137,7 @@ class DeviceSeparatorMixin:
             self._state[name] = value if _device.is_tensor(value) else np.array(value)
             return
         t = _device.to_device(value, _STATE_DTYPES[name])
-        batched_rank = {"demix_filter": 4, "output": 4, "basis": 4, "activation": 4, "variance": 3}[name]
+        batched_rank = _STATE_RANKS[name]
         if t.dim() == batched_rank - 1:
             t = t.unsqueeze(0)
         if name == "output":
@@ -216,8 +224,7 @@ class DeviceSeparatorMixin:
         """(Re)create and bind the chunk plans when shapes, options or buffers changed.  Pending
         host->device copies of the input are enqueued chunk by chunk on the chunk streams."""
         cfg = self._plan_config()
-        names = ("demix_filter", "output", "basis", "activation", "variance")
-        tens = [self._dev(k) for k in names]
+        tens = [self._dev(k) for k in self._plan_slots]
         layout = self._chunk_layout()
         key = (bytes(cfg), self._dX.data_ptr(), tuple(layout)) + tuple(_device.ptr(t) for t in tens)
         if self._chunks and key == self._plan_key:

@@ -198,3 +198,50 @@ __device__ __forceinline__ void herm_eig2(double c00, double c11, cd c01, double
   y0[0] = cd_make(-a1.x, a1.y);
   y0[1] = cd_conj(a0);
 }
+
+// Hermitian eigendecomposition by cyclic Jacobi: A (N x N, overwritten) -> eigenvalues on the
+// diagonal, Vv accumulates the eigenvectors (columns).
+__device__ __forceinline__ void jacobi_herm(cd* A, cd* Vv, int N) {
+  for (int r = 0; r < N; ++r)
+    for (int c = 0; c < N; ++c) Vv[r * N + c] = cd_make(r == c ? 1.0 : 0.0, 0.0);
+  for (int sweep = 0; sweep < 40; ++sweep) {
+    double off = 0.0, dia = 0.0;
+    for (int r = 0; r < N; ++r)
+      for (int c = 0; c < N; ++c) {
+        if (r == c) dia += A[r * N + c].x * A[r * N + c].x;
+        else off += cd_abs2(A[r * N + c]);
+      }
+    if (off <= 1e-32 * (dia + off) || off == 0.0) break;
+    for (int p = 0; p < N - 1; ++p)
+      for (int q = p + 1; q < N; ++q) {
+        const cd apq = A[p * N + q];
+        const double mag = sqrt(cd_abs2(apq));
+        if (mag == 0.0) continue;
+        const cd ph = cd_scale(apq, 1.0 / mag);  // e^{i phi}
+        const double theta = (A[q * N + q].x - A[p * N + p].x) / (2.0 * mag);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+        // J = D R, D = diag(1, e^{-i phi}) on (p,q), R = [[c, s], [-s, c]]
+        const cd Jpp = cd_make(c, 0), Jpq = cd_make(s, 0);
+        const cd Jqp = cd_scale(cd_conj(ph), -s), Jqq = cd_scale(cd_conj(ph), c);
+        for (int k = 0; k < N; ++k) {  // A <- A J (columns p, q)
+          cd akp = A[k * N + p], akq = A[k * N + q];
+          A[k * N + p] = cd_add(cd_mul(akp, Jpp), cd_mul(akq, Jqp));
+          A[k * N + q] = cd_add(cd_mul(akp, Jpq), cd_mul(akq, Jqq));
+          cd vkp = Vv[k * N + p], vkq = Vv[k * N + q];
+          Vv[k * N + p] = cd_add(cd_mul(vkp, Jpp), cd_mul(vkq, Jqp));
+          Vv[k * N + q] = cd_add(cd_mul(vkp, Jpq), cd_mul(vkq, Jqq));
+        }
+        for (int k = 0; k < N; ++k) {  // A <- J^H A (rows p, q)
+          cd apk = A[p * N + k], aqk = A[q * N + k];
+          A[p * N + k] = cd_add(cd_mul(cd_conj(Jpp), apk), cd_mul(cd_conj(Jqp), aqk));
+          A[q * N + k] = cd_add(cd_mul(cd_conj(Jpq), apk), cd_mul(cd_conj(Jqq), aqk));
+        }
+        A[p * N + q] = cd_make(0, 0);
+        A[q * N + p] = cd_make(0, 0);
+        A[p * N + p].y = 0.0;
+        A[q * N + q].y = 0.0;
+      }
+  }
+}
+

@@ -1,0 +1,369 @@
+// FastGaussMNMF (ssspy/bss/mnmf.py:1076-1675), determined case n_sources == n_channels == N.
+// State per mixture: T[N,I,K], V[N,K,J] (NMF), Q[I,N,N] complex64 (diagonaliser, rows q_m^H),
+// D[I,N,N] f32 (spatial[i, source n, channel m]).  With Lambda = T V, L[i,j,m] = sum_n Lambda_n D[n,m],
+// Z2[i,j,m] = |q_m^H x|^2:
+//   basis / activation : multiplicative updates with G_n = sum_m D[n,m] Z2/L^2, H_n = sum_m D[n,m]/L
+//   diagonaliser       : U[i,m] = mean_j x x^H / L[:,m], then the same IP1 / IP2 as ILRMA on Q
+//   spatial            : D <- D sqrt(sum_j Lambda Z2/L^2 / sum_j Lambda/L)
+//   normalisation, loss, and the multichannel Wiener filter with a per-(bin, frame) Hermitian
+//   eigendecomposition (to_psd) in `separate`.
+// One warp per (mixture, bin) with lanes over frames for the update kernels (correctness-first
+// CUDA-core kernels; the K-contractions are plain FMA chains), one thread per (bin, frame) for the
+// Wiener filter.
+#include "ssb_group.cuh"
+#include "ssb_kernels.h"
+
+namespace {
+
+constexpr int MW = 4;  // warps (bins) per block
+
+// per-warp shared-memory context of one bin
+template <int N>
+struct BinCtx {
+  float T[N][SSB_MAX_BASIS];
+  cf Q[N][N];
+  float D[N][N];
+};
+
+template <int N>
+__device__ __forceinline__ void load_ctx(BinCtx<N>& c, const float* __restrict__ T, const cf* __restrict__ Q,
+                                         const float* __restrict__ D, int b, int i, int I, int K, int lane) {
+  for (int e = lane; e < N * K; e += 32) {
+    const int n = e / K, k = e - n * K;
+    c.T[n][k] = T[(((size_t)b * N + n) * I + i) * K + k];
+  }
+  for (int e = lane; e < N * N; e += 32) {
+    c.Q[e / N][e % N] = Q[((size_t)b * I + i) * N * N + e];
+    c.D[e / N][e % N] = D[((size_t)b * I + i) * N * N + e];
+  }
+  __syncwarp();
+}
+
+// Lambda_n, L_m and Z2_m of one (bin, frame)
+template <int N>
+__device__ __forceinline__ void frame_stats(const BinCtx<N>& c, const cf* __restrict__ X, const float* __restrict__ V,
+                                            int b, int i, int j, int I, int J, int K, float (&lam)[N], float (&L)[N],
+                                            float (&Z2)[N]) {
+  cf x[N];
+#pragma unroll
+  for (int m = 0; m < N; ++m) x[m] = X[(((size_t)b * N + m) * I + i) * J + j];
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+    const float* v = V + ((size_t)b * N + n) * K * J + j;
+    float s = 0.f;
+    for (int k = 0; k < K; ++k) s = fmaf(c.T[n][k], v[(size_t)k * J], s);
+    lam[n] = s;
+  }
+#pragma unroll
+  for (int m = 0; m < N; ++m) {
+    float l = 0.f, zr = 0.f, zi = 0.f;
+#pragma unroll
+    for (int n = 0; n < N; ++n) l = fmaf(lam[n], c.D[n][m], l);
+#pragma unroll
+    for (int cc = 0; cc < N; ++cc) {
+      const cf q = c.Q[m][cc];
+      zr = fmaf(q.x, x[cc].x, fmaf(-q.y, x[cc].y, zr));
+      zi = fmaf(q.x, x[cc].y, fmaf(q.y, x[cc].x, zi));
+    }
+    L[m] = l;
+    Z2[m] = zr * zr + zi * zi;
+  }
+}
+
+// G[b,n,i,j] = sum_m D[n,m] Z2_m / L_m^2,  H[b,n,i,j] = sum_m D[n,m] / L_m     (mnmf.py:1348-1350)
+template <int N>
+__global__ void __launch_bounds__(MW * 32) km_gh(const cf* __restrict__ X, const float* __restrict__ T,
+                                                 const float* __restrict__ V, const cf* __restrict__ Q,
+                                                 const float* __restrict__ D, float* __restrict__ G,
+                                                 float* __restrict__ H, int B, int I, int J, int K) {
+  __shared__ BinCtx<N> ctx[MW];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bin = blockIdx.x * MW + wib;
+  if (bin >= B * I) return;
+  const int b = bin / I, i = bin - b * I;
+  BinCtx<N>& c = ctx[wib];
+  load_ctx<N>(c, T, Q, D, b, i, I, K, lane);
+  for (int j = lane; j < J; j += 32) {
+    float lam[N], L[N], Z2[N];
+    frame_stats<N>(c, X, V, b, i, j, I, J, K, lam, L, Z2);
+    float r[N], r2[N];
+#pragma unroll
+    for (int m = 0; m < N; ++m) {
+      r[m] = 1.0f / L[m];
+      r2[m] = Z2[m] * r[m] * r[m];
+    }
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      float g = 0.f, h = 0.f;
+#pragma unroll
+      for (int m = 0; m < N; ++m) {
+        g = fmaf(c.D[n][m], r2[m], g);
+        h = fmaf(c.D[n][m], r[m], h);
+      }
+      const size_t o = (((size_t)b * N + n) * I + i) * J + j;
+      G[o] = g;
+      H[o] = h;
+    }
+  }
+}
+
+// phi[b,m,i,j] = 1 / L[i,j,m]      (mnmf.py:1504-1510)
+template <int N>
+__global__ void __launch_bounds__(MW * 32) km_phi(const cf* __restrict__ X, const float* __restrict__ T,
+                                                  const float* __restrict__ V, const cf* __restrict__ Q,
+                                                  const float* __restrict__ D, float* __restrict__ phi, int B, int I,
+                                                  int J, int K) {
+  __shared__ BinCtx<N> ctx[MW];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bin = blockIdx.x * MW + wib;
+  if (bin >= B * I) return;
+  const int b = bin / I, i = bin - b * I;
+  BinCtx<N>& c = ctx[wib];
+  load_ctx<N>(c, T, Q, D, b, i, I, K, lane);
+  for (int j = lane; j < J; j += 32) {
+    float lam[N], L[N], Z2[N];
+    frame_stats<N>(c, X, V, b, i, j, I, J, K, lam, L, Z2);
+#pragma unroll
+    for (int m = 0; m < N; ++m) phi[(((size_t)b * N + m) * I + i) * J + j] = 1.0f / L[m];
+  }
+}
+
+// spatial update (mnmf.py:1660-1675) and the per-bin sums zsum[b,i,m] = sum_j Z2_m for the normalisation;
+// one source per pass over the frames keeps the accumulators in registers.  update_d = 0: zsum only.
+template <int N>
+__global__ void __launch_bounds__(MW * 32) km_spatial(const cf* __restrict__ X, const float* __restrict__ T,
+                                                      const float* __restrict__ V, const cf* __restrict__ Q,
+                                                      float* __restrict__ D, double* __restrict__ zsum, int B, int I,
+                                                      int J, int K, int update_d) {
+  __shared__ BinCtx<N> ctx[MW];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bin = blockIdx.x * MW + wib;
+  if (bin >= B * I) return;
+  const int b = bin / I, i = bin - b * I;
+  BinCtx<N>& c = ctx[wib];
+  load_ctx<N>(c, T, Q, D, b, i, I, K, lane);
+  float newD[N];  // lane n < N... each lane keeps the row it will write: computed per source below
+  for (int n = 0; n < (update_d ? N : 1); ++n) {
+    float num[N], den[N], zs[N];
+#pragma unroll
+    for (int m = 0; m < N; ++m) num[m] = den[m] = zs[m] = 0.f;
+    for (int j = lane; j < J; j += 32) {
+      float lam[N], L[N], Z2[N];
+      frame_stats<N>(c, X, V, b, i, j, I, J, K, lam, L, Z2);
+      float ln = lam[0];
+#pragma unroll
+      for (int q = 1; q < N; ++q) ln = (q == n) ? lam[q] : ln;
+#pragma unroll
+      for (int m = 0; m < N; ++m) {
+        const float r = 1.0f / L[m];
+        num[m] = fmaf(ln * r * r, Z2[m], num[m]);
+        den[m] = fmaf(ln, r, den[m]);
+        zs[m] += Z2[m];
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < N; ++m) {
+      const float nu = warp_sum(num[m]), de = warp_sum(den[m]), z = warp_sum(zs[m]);
+      if (update_d) newD[m] = sqrtf(nu / de) * c.D[n][m];
+      if (n == 0 && lane == 0) zsum[((size_t)b * I + i) * N + m] = (double)z;
+    }
+    if (update_d && lane == 0) {
+#pragma unroll
+      for (int m = 0; m < N; ++m) D[(((size_t)b * I + i) * N + n) * N + m] = newD[m];
+    }
+  }
+}
+
+// psi_m = floor(sqrt(mean_ij Z2_m)); Q[:,m,:] /= psi_m; D[:,:,m] /= psi_m^2   (mnmf.py:666-678)
+__global__ void km_normalize(const double* __restrict__ zsum, cf* __restrict__ Q, float* __restrict__ D, int N, int I,
+                             int J, int flooring, double eps) {
+  __shared__ double sh[8];
+  __shared__ double s_psi[SSB_MAX_SOURCES];
+  const int b = blockIdx.x;
+  for (int m = 0; m < N; ++m) {
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < I; i += blockDim.x) acc += zsum[((size_t)b * I + i) * N + m];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
+      s_psi[m] = ssb_floor(sqrt(t / ((double)I * (double)J)), flooring, eps);
+    }
+    __syncthreads();
+  }
+  for (int e = threadIdx.x; e < I * N * N; e += blockDim.x) {
+    const int r = (e / N) % N, cc = e % N;  // Q[i, m=r, c], D[i, n=r, m=cc]
+    const size_t o = (size_t)b * I * N * N + e;
+    const double pq = s_psi[r], pd = s_psi[cc];
+    cf q = Q[o];
+    Q[o] = make_float2((float)(q.x / pq), (float)(q.y / pq));
+    D[o] = (float)((double)D[o] / (pd * pd));
+  }
+}
+
+// rowloss[b,i] = mean_j sum_m (Z2/L + log L)     (mnmf.py:1255-1258)
+template <int N>
+__global__ void __launch_bounds__(MW * 32) km_rowloss(const cf* __restrict__ X, const float* __restrict__ T,
+                                                      const float* __restrict__ V, const cf* __restrict__ Q,
+                                                      const float* __restrict__ D, double* __restrict__ rowloss, int B,
+                                                      int I, int J, int K) {
+  __shared__ BinCtx<N> ctx[MW];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bin = blockIdx.x * MW + wib;
+  if (bin >= B * I) return;
+  const int b = bin / I, i = bin - b * I;
+  BinCtx<N>& c = ctx[wib];
+  load_ctx<N>(c, T, Q, D, b, i, I, K, lane);
+  double acc = 0.0;
+  for (int j = lane; j < J; j += 32) {
+    float lam[N], L[N], Z2[N];
+    frame_stats<N>(c, X, V, b, i, j, I, J, K, lam, L, Z2);
+    float s = 0.f;
+#pragma unroll
+    for (int m = 0; m < N; ++m) s += Z2[m] / L[m] + logf(L[m]);
+    acc += (double)s;
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) rowloss[bin] = acc / (double)J;
+}
+
+// Qinv[b,i] = Q[b,i]^-1 (complex128), one lane group per bin
+template <int N>
+__global__ void __launch_bounds__(MW * 32) km_qinv(const cf* __restrict__ Q, cd* __restrict__ Qinv, int n_mat) {
+  constexpr int GS = GroupShape<N>::GS, GW = GroupShape<N>::GW;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = lane / GS, r = lane - grp * GS, gbase = grp * GS;
+  const int mat_raw = (blockIdx.x * MW + warp) * GW + grp;
+  const bool valid = mat_raw < n_mat;
+  const int mat = valid ? mat_raw : n_mat - 1;
+  cd a[N], rhs[N];
+#pragma unroll
+  for (int c = 0; c < N; ++c) {
+    a[c] = (r < N) ? cf2cd(Q[((size_t)mat * N + r) * N + c]) : cd_make(0, 0);
+    rhs[c] = cd_make(r == c ? 1.0 : 0.0, 0);
+  }
+  group_solve<N, N, GS>(a, rhs, r, gbase);
+  if (valid && r < N) {
+#pragma unroll
+    for (int c = 0; c < N; ++c) Qinv[((size_t)mat * N + r) * N + c] = rhs[c];
+  }
+}
+
+// Multichannel Wiener filter (mnmf.py:1186-1217), one thread per (bin, frame), one block per bin:
+//   R = Qinv diag(L) Qinv^H -> to_psd (Hermitian eigendecomposition, eigenvalues floored, rebuilt)
+//   u_n = R^-1 R_n[:, ref],  R_n[:, ref] = Qinv diag(Lambda_n D[n,:]) conj(Qinv[ref, :])
+//   y_n = u_n^H x
+template <int N>
+__global__ void __launch_bounds__(128) km_separate(const cf* __restrict__ X, const float* __restrict__ T,
+                                                   const float* __restrict__ V, const float* __restrict__ D,
+                                                   const cd* __restrict__ Qinv, cf* __restrict__ Y, int I, int J,
+                                                   int K, int ref, int flooring, double eps) {
+  __shared__ float sT[N][SSB_MAX_BASIS];
+  __shared__ float sD[N][N];
+  __shared__ cd sQi[N][N];
+  const int bin = blockIdx.x;
+  const int b = bin / I, i = bin - b * I;
+  for (int e = threadIdx.x; e < N * K; e += blockDim.x) {
+    const int n = e / K, k = e - n * K;
+    sT[n][k] = T[(((size_t)b * N + n) * I + i) * K + k];
+  }
+  for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
+    sD[e / N][e % N] = D[(size_t)bin * N * N + e];
+    sQi[e / N][e % N] = Qinv[(size_t)bin * N * N + e];
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < J; j += blockDim.x) {
+    double lam[N], L[N];
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      const float* v = V + ((size_t)b * N + n) * K * J + j;
+      float s = 0.f;
+      for (int k = 0; k < K; ++k) s = fmaf(sT[n][k], v[(size_t)k * J], s);
+      lam[n] = (double)s;
+    }
+#pragma unroll
+    for (int m = 0; m < N; ++m) {
+      double l = 0.0;
+#pragma unroll
+      for (int n = 0; n < N; ++n) l += lam[n] * (double)sD[n][m];
+      L[m] = l;
+    }
+    cd R[N * N], P[N * N];
+    for (int a = 0; a < N; ++a)
+      for (int c = a; c < N; ++c) {
+        cd s = cd_make(0, 0);
+        for (int m = 0; m < N; ++m) s = cd_add(s, cd_scale(cd_mulc(sQi[a][m], sQi[c][m]), L[m]));
+        if (a == c) s.y = 0.0;
+        R[a * N + c] = s;
+        R[c * N + a] = cd_conj(s);
+      }
+    jacobi_herm(R, P, N);  // eigenvalues on the diagonal of R, eigenvectors in the columns of P
+    double il[N];
+    for (int m = 0; m < N; ++m) il[m] = 1.0 / ssb_floor(R[m * N + m].x, flooring, eps);
+    cd x[N];
+#pragma unroll
+    for (int m = 0; m < N; ++m) x[m] = cf2cd(X[(((size_t)b * N + m) * I + i) * J + j]);
+    // px = P^H x ; for each source: y_n = r_n^H R^-1 x = sum_e conj(P^H r_n)_e (1/lambda_e) (P^H x)_e
+    cd px[N];
+    for (int e = 0; e < N; ++e) {
+      cd s = cd_make(0, 0);
+      for (int a = 0; a < N; ++a) s = cd_add(s, cd_mul(cd_conj(P[a * N + e]), x[a]));
+      px[e] = s;
+    }
+    for (int n = 0; n < N; ++n) {
+      cd rn[N];  // R_n[:, ref]
+      for (int a = 0; a < N; ++a) {
+        cd s = cd_make(0, 0);
+        for (int m = 0; m < N; ++m) s = cd_add(s, cd_scale(cd_mulc(sQi[a][m], sQi[ref][m]), lam[n] * (double)sD[n][m]));
+        rn[a] = s;
+      }
+      cd y = cd_make(0, 0);
+      for (int e = 0; e < N; ++e) {
+        cd pr = cd_make(0, 0);
+        for (int a = 0; a < N; ++a) pr = cd_add(pr, cd_mul(cd_conj(P[a * N + e]), rn[a]));
+        y = cd_add(y, cd_scale(cd_mul(cd_conj(pr), px[e]), il[e]));
+      }
+      Y[(((size_t)b * N + n) * I + i) * J + j] = cd2cf(y);
+    }
+  }
+}
+
+}  // namespace
+
+int ssbk_mnmf_gh(const cf* X, const float* T, const float* V, const cf* Q, const float* D, float* G, float* H, int B,
+                 int N, int I, int J, int K, cudaStream_t st) {
+  SSB_DISPATCH_N(N, km_gh<NN><<<blocks_for((long long)B * I, MW), MW * 32, 0, st>>>(X, T, V, Q, D, G, H, B, I, J, K));
+  return ssb_check_launch("mnmf_gh", st);
+}
+int ssbk_mnmf_phi(const cf* X, const float* T, const float* V, const cf* Q, const float* D, float* phi, int B, int N,
+                  int I, int J, int K, cudaStream_t st) {
+  SSB_DISPATCH_N(N, km_phi<NN><<<blocks_for((long long)B * I, MW), MW * 32, 0, st>>>(X, T, V, Q, D, phi, B, I, J, K));
+  return ssb_check_launch("mnmf_phi", st);
+}
+int ssbk_mnmf_spatial(const cf* X, const float* T, const float* V, const cf* Q, float* D, double* zsum, int B, int N,
+                      int I, int J, int K, int update_d, cudaStream_t st) {
+  SSB_DISPATCH_N(N, km_spatial<NN><<<blocks_for((long long)B * I, MW), MW * 32, 0, st>>>(X, T, V, Q, D, zsum, B, I, J,
+                                                                                          K, update_d));
+  return ssb_check_launch("mnmf_spatial", st);
+}
+int ssbk_mnmf_normalize(const double* zsum, cf* Q, float* D, int B, int N, int I, int J, int flooring, float eps,
+                        cudaStream_t st) {
+  km_normalize<<<B, 256, 0, st>>>(zsum, Q, D, N, I, J, flooring, (double)eps);
+  return ssb_check_launch("mnmf_normalize", st);
+}
+int ssbk_mnmf_rowloss(const cf* X, const float* T, const float* V, const cf* Q, const float* D, double* rowloss, int B,
+                      int N, int I, int J, int K, cudaStream_t st) {
+  SSB_DISPATCH_N(N, km_rowloss<NN><<<blocks_for((long long)B * I, MW), MW * 32, 0, st>>>(X, T, V, Q, D, rowloss, B, I,
+                                                                                          J, K));
+  return ssb_check_launch("mnmf_rowloss", st);
+}
+int ssbk_mnmf_separate(const cf* X, const float* T, const float* V, const cf* Q, const float* D, cd* Qinv, cf* Y, int B,
+                       int N, int I, int J, int K, int ref, int flooring, float eps, cudaStream_t st) {
+  SSB_REQUIRE(ref >= 0 && ref < N, "reference_id=%d out of range for N=%d", ref, N);
+  SSB_DISPATCH_N(N, km_qinv<NN><<<blocks_for((long long)B * I, MW * GroupShape<NN>::GW), MW * 32, 0, st>>>(Q, Qinv, B * I));
+  if (ssb_check_launch("mnmf_qinv", st)) return 1;
+  SSB_DISPATCH_N(N, km_separate<NN><<<B * I, 128, 0, st>>>(X, T, V, D, Qinv, Y, I, J, K, ref, flooring, (double)eps));
+  return ssb_check_launch("mnmf_separate", st);
+}

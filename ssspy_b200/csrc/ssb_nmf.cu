@@ -8,6 +8,7 @@
 namespace {
 
 constexpr int WPB = 4;
+constexpr int ACT_NW = 8;
 enum { PM_MM2 = 0, PM_ME = 1, PM_GENERIC = 2 };
 
 __device__ __forceinline__ float upd_pow(float ratio, float bexp, int mode) {
@@ -62,7 +63,6 @@ __global__ void __launch_bounds__(WPB * 32) k_nmf_basis(const float* __restrict_
 
 // V <- floor(V * (sum_i T P / R^a / sum_i T / R)^b); one block per (b,n, 32-frame tile), NW warps
 // split the bins, lane = frame; cross-warp reduction through shared memory in fixed order.
-constexpr int ACT_NW = 8;
 template <int KP>
 __global__ void __launch_bounds__(ACT_NW * 32) k_nmf_activation(const float* __restrict__ P,
                                                                const float* __restrict__ T, float* __restrict__ V,
@@ -119,6 +119,91 @@ __global__ void __launch_bounds__(ACT_NW * 32) k_nmf_activation(const float* __r
       if (k < K) {
         float ratio = s_acc[k][lane] / s_acc[KP + k][lane];
         V[((size_t)bn * K + k) * J + j] = ssb_floor(upd_pow(ratio, bexp, mode) * v[k], flooring, eps);
+      }
+    }
+  }
+}
+
+// Variants with the two elementwise factors given as arrays (FastGaussMNMF, ssspy/bss/mnmf.py:1351-1358,
+// :1408-1415):  T <- floor(T sqrt(sum_j V A / sum_j V Bm)),  V <- floor(V sqrt(sum_i T A / sum_i T Bm)).
+template <int KP>
+__global__ void __launch_bounds__(WPB * 32) k_nmf_basis_ab(const float* __restrict__ A, const float* __restrict__ Bm,
+                                                           float* __restrict__ T, const float* __restrict__ V,
+                                                           int rows, int I, int J, int K, int flooring, float eps) {
+  const int row = blockIdx.x * WPB + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int bn = row / I;
+  float num[KP], den[KP];
+#pragma unroll
+  for (int k = 0; k < KP; ++k) num[k] = den[k] = 0.f;
+  const float* Vb = V + (size_t)bn * K * J;
+  for (int j = lane; j < J; j += 32) {
+    const float a = A[(size_t)row * J + j], bb = Bm[(size_t)row * J + j];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      const float v = k < K ? Vb[(size_t)k * J + j] : 0.f;
+      num[k] = fmaf(v, a, num[k]);
+      den[k] = fmaf(v, bb, den[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < KP; ++k) {
+    if (k < K) {
+      float nu = warp_sum(num[k]), de = warp_sum(den[k]);
+      if ((k & 31) == lane) {
+        const float t = T[(size_t)row * K + k];
+        T[(size_t)row * K + k] = ssb_floor(t * sqrtf(nu / de), flooring, eps);
+      }
+    }
+  }
+}
+
+template <int KP>
+__global__ void __launch_bounds__(ACT_NW * 32) k_nmf_activation_ab(const float* __restrict__ A,
+                                                                  const float* __restrict__ Bm,
+                                                                  const float* __restrict__ T, float* __restrict__ V,
+                                                                  int I, int J, int K, int flooring, float eps) {
+  __shared__ float s_acc[2 * KP][32];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int jt = blockIdx.x, bn = blockIdx.y;
+  const int j = jt * 32 + lane;
+  const bool valid = j < J;
+  float num[KP], den[KP];
+#pragma unroll
+  for (int k = 0; k < KP; ++k) num[k] = den[k] = 0.f;
+  for (int i = w; i < I; i += ACT_NW) {
+    const float* Tr = T + ((size_t)bn * I + i) * K;
+    const float a = valid ? A[((size_t)bn * I + i) * J + j] : 0.f;
+    const float bb = valid ? Bm[((size_t)bn * I + i) * J + j] : 0.f;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      const float t = k < K ? __ldg(Tr + k) : 0.f;
+      num[k] = fmaf(t, a, num[k]);
+      den[k] = fmaf(t, bb, den[k]);
+    }
+  }
+  for (int ww = 0; ww < ACT_NW; ++ww) {
+    if (w == ww) {
+#pragma unroll
+      for (int k = 0; k < KP; ++k) {
+        if (ww == 0) {
+          s_acc[k][lane] = num[k];
+          s_acc[KP + k][lane] = den[k];
+        } else {
+          s_acc[k][lane] += num[k];
+          s_acc[KP + k][lane] += den[k];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (w == 0 && valid) {
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      if (k < K) {
+        const float v = V[((size_t)bn * K + k) * J + j];
+        V[((size_t)bn * K + k) * J + j] = ssb_floor(v * sqrtf(s_acc[k][lane] / s_acc[KP + k][lane]), flooring, eps);
       }
     }
   }
@@ -306,6 +391,21 @@ int ssbk_nmf_activation(const float* P, const float* T, float* V, int BN, int I,
   dim3 grid((J + 31) / 32, BN);
   SSB_DISPATCH_K(K, k_nmf_activation<KP><<<grid, ACT_NW * 32, 0, st>>>(P, T, V, I, J, K, a, b, mode, flooring, eps));
   return ssb_check_launch("nmf_activation", st);
+}
+
+int ssbk_nmf_basis_ab(const float* A, const float* Bm, float* T, const float* V, int BN, int I, int J, int K,
+                      int flooring, float eps, cudaStream_t st) {
+  const int rows = BN * I;
+  SSB_DISPATCH_K(K, k_nmf_basis_ab<KP><<<blocks_for(rows, WPB), WPB * 32, 0, st>>>(A, Bm, T, V, rows, I, J, K, flooring,
+                                                                                    eps));
+  return ssb_check_launch("nmf_basis_ab", st);
+}
+
+int ssbk_nmf_activation_ab(const float* A, const float* Bm, const float* T, float* V, int BN, int I, int J, int K,
+                           int flooring, float eps, cudaStream_t st) {
+  dim3 grid((J + 31) / 32, BN);
+  SSB_DISPATCH_K(K, k_nmf_activation_ab<KP><<<grid, ACT_NW * 32, 0, st>>>(A, Bm, T, V, I, J, K, flooring, eps));
+  return ssb_check_launch("nmf_activation_ab", st);
 }
 
 int ssbk_nmf_phi(const float* T, const float* V, float* phi, int BN, int I, int J, int K, float p, cudaStream_t st) {

@@ -131,7 +131,10 @@ struct ssb_plan {
   double* logdet = nullptr;   // [B,I]
   ssb_fused_ws fused;       // extra scratch of the fused kernels
   bool bound = false, prepared = false;
-  bool iss() const { return cfg.spatial == SSB_SPATIAL_ISS1; }
+  float* big2 = nullptr;    // [B,N,I,J] f32 second elementwise scratch (FastGaussMNMF: H)
+  cd* qinv = nullptr;       // [B,I,N,N] c128 (FastGaussMNMF separate)
+  bool mnmf() const { return cfg.model == SSB_MODEL_FASTMNMF_GAUSS; }
+  bool iss() const { return cfg.spatial == SSB_SPATIAL_ISS1 && !mnmf(); }
   bool ilrma() const { return cfg.model == SSB_MODEL_ILRMA_GAUSS; }
 };
 
@@ -155,7 +158,9 @@ size_t carve(ssb_plan* p, char* base) {
   const size_t B = c.n_batch, N = c.n_sources, I = c.n_bins, J = c.n_frames;
   Carver cv{base};
   // + 16 rows of slack: the fused activation kernel prefetches whole 16-bin tiles of P without clamping
-  p->big = p->ilrma() ? cv.take<float>(B * N * I * J + 16 * J) : nullptr;
+  p->big = (p->ilrma() || p->mnmf()) ? cv.take<float>(B * N * I * J + 16 * J) : nullptr;
+  p->big2 = p->mnmf() ? cv.take<float>(B * N * I * J) : nullptr;
+  p->qinv = p->mnmf() ? cv.take<cd>(B * I * N * N) : nullptr;
   p->phi_iva = cv.take<float>(B * N * J);
   p->r2 = cv.take<float>(B * N * J);
   p->U = cv.take<cf>(B * I * N * N * N);
@@ -171,7 +176,7 @@ size_t carve(ssb_plan* p, char* base) {
 
 int validate(const ssb_config* c) {
   SSB_REQUIRE(c != nullptr, "config is NULL");
-  SSB_REQUIRE(c->model >= 0 && c->model <= 2, "unknown model %d", c->model);
+  SSB_REQUIRE(c->model >= 0 && c->model <= 3, "unknown model %d", c->model);
   SSB_REQUIRE(c->spatial >= 0 && c->spatial <= 2, "Not support spatial algorithm id %d.", c->spatial);
   SSB_REQUIRE(c->source == SSB_SOURCE_MM || c->source == SSB_SOURCE_ME, "Not support source algorithm id %d.",
               c->source);
@@ -179,6 +184,14 @@ int validate(const ssb_config* c) {
   SSB_REQUIRE(c->n_sources >= 2 && c->n_sources <= SSB_MAX_SOURCES, "n_sources=%d unsupported (2..%d)", c->n_sources,
               SSB_MAX_SOURCES);
   SSB_REQUIRE(c->n_bins >= 1 && c->n_frames >= 1, "empty input (n_bins=%d, n_frames=%d)", c->n_bins, c->n_frames);
+  if (c->model == SSB_MODEL_FASTMNMF_GAUSS) {
+    SSB_REQUIRE(c->n_basis >= 1 && c->n_basis <= SSB_MAX_BASIS, "n_basis=%d unsupported (1..%d)", c->n_basis,
+                SSB_MAX_BASIS);
+    SSB_REQUIRE(c->spatial == SSB_SPATIAL_IP1 || c->spatial == SSB_SPATIAL_IP2, "Not support diagonalizer algorithm id %d.",
+                c->spatial);
+    SSB_REQUIRE(c->normalization == SSB_NORM_NONE || c->normalization == SSB_NORM_POWER,
+                "Normalization %d is not implemented.", c->normalization);
+  }
   if (c->model == SSB_MODEL_ILRMA_GAUSS) {
     SSB_REQUIRE(c->n_basis >= 1 && c->n_basis <= SSB_MAX_BASIS, "n_basis=%d unsupported (1..%d)", c->n_basis,
                 SSB_MAX_BASIS);
@@ -332,6 +345,41 @@ int iva_loss(ssb_plan* p, double* loss, cudaStream_t st) {
   return ssbk_iva_loss(p->r2, p->variance, p->logdet, loss, c.model, c.n_batch, c.n_sources, c.n_bins, c.n_frames, st);
 }
 
+// ---- FastGaussMNMF: W slot = diagonaliser Q[B,I,N,N] c64, variance slot = spatial D[B,I,N,N] f32 ----------
+int mnmf_source(ssb_plan* p, cudaStream_t st) {
+  const ssb_config& c = p->cfg;
+  const int B = c.n_batch, N = c.n_sources, I = c.n_bins, J = c.n_frames, K = c.n_basis;
+  TRY(ssbk_mnmf_gh(p->X, p->T, p->V, p->W, p->variance, p->big, p->big2, B, N, I, J, K, st));
+  TRY(ssbk_nmf_basis_ab(p->big, p->big2, p->T, p->V, B * N, I, J, K, c.flooring, c.eps, st));
+  TRY(ssbk_mnmf_gh(p->X, p->T, p->V, p->W, p->variance, p->big, p->big2, B, N, I, J, K, st));
+  return ssbk_nmf_activation_ab(p->big, p->big2, p->T, p->V, B * N, I, J, K, c.flooring, c.eps, st);
+}
+
+int mnmf_spatial(ssb_plan* p, cudaStream_t st) {
+  const ssb_config& c = p->cfg;
+  const int B = c.n_batch, N = c.n_sources, I = c.n_bins, J = c.n_frames, K = c.n_basis;
+  TRY(ssbk_mnmf_phi(p->X, p->T, p->V, p->W, p->variance, p->big, B, N, I, J, K, st));
+  TRY(ssbk_wcov(p->X, p->big, (long long)N * I * J, (long long)I * J, J, nullptr, N, p->U, B, N, I, J, st));
+  if (c.spatial == SSB_SPATIAL_IP1) TRY(ssbk_ip1(p->W, p->U, B * I, N, c.flooring, c.eps, st));
+  else TRY(ssbk_ip2(p->W, p->U, B * I, N, c.pairs, c.n_pairs, N, nullptr, c.flooring, c.eps, st));
+  return ssbk_mnmf_spatial(p->X, p->T, p->V, p->W, p->variance, p->rowloss, B, N, I, J, K, 1, st);
+}
+
+int mnmf_normalize(ssb_plan* p, bool have_zsum, cudaStream_t st) {
+  const ssb_config& c = p->cfg;
+  const int B = c.n_batch, N = c.n_sources, I = c.n_bins, J = c.n_frames, K = c.n_basis;
+  if (!have_zsum) TRY(ssbk_mnmf_spatial(p->X, p->T, p->V, p->W, p->variance, p->rowloss, B, N, I, J, K, 0, st));
+  return ssbk_mnmf_normalize(p->rowloss, p->W, p->variance, B, N, I, J, c.flooring, c.eps, st);
+}
+
+int mnmf_loss(ssb_plan* p, double* loss, cudaStream_t st) {
+  const ssb_config& c = p->cfg;
+  const int B = c.n_batch, N = c.n_sources, I = c.n_bins, J = c.n_frames, K = c.n_basis;
+  TRY(ssbk_mnmf_rowloss(p->X, p->T, p->V, p->W, p->variance, p->rowloss, B, N, I, J, K, st));
+  TRY(ssbk_logdet(p->W, p->logdet, B * I, N, st));
+  return ssbk_ilrma_loss_reduce(p->rowloss, p->logdet, loss, B, 1, I, st);
+}
+
 }  // namespace
 
 extern "C" int ssb_plan_create(const ssb_config* cfg, ssb_plan** plan) {
@@ -361,8 +409,9 @@ extern "C" int ssb_plan_bind(ssb_plan* p, const void* X, void* W, void* Y, void*
   SSB_REQUIRE(p != nullptr, "plan is NULL");
   SSB_REQUIRE(X != nullptr && Y != nullptr, "X and Y must be bound");
   SSB_REQUIRE(p->iss() || W != nullptr, "W must be bound unless spatial_algorithm is ISS");
-  SSB_REQUIRE(!p->ilrma() || (T != nullptr && V != nullptr), "T and V must be bound for ILRMA");
+  SSB_REQUIRE(!(p->ilrma() || p->mnmf()) || (T != nullptr && V != nullptr), "T and V must be bound for ILRMA / MNMF");
   SSB_REQUIRE(p->cfg.model != SSB_MODEL_IVA_GAUSS || variance != nullptr, "variance must be bound for AuxGaussIVA");
+  SSB_REQUIRE(!p->mnmf() || variance != nullptr, "spatial (D) must be bound in the variance slot for FastGaussMNMF");
   size_t need = 0;
   TRY(ssb_plan_workspace_bytes(p, &need));
   SSB_REQUIRE(workspace != nullptr && workspace_bytes >= need, "workspace too small: %zu < %zu bytes", workspace_bytes,
@@ -393,6 +442,10 @@ extern "C" int ssb_plan_prepare(ssb_plan* p, void* stream) {
   TRY(require_bound(p));
   const ssb_config& c = p->cfg;
   cudaStream_t st = (cudaStream_t)stream;
+  if (p->mnmf()) {
+    p->prepared = true;
+    return 0;
+  }
   if (p->ilrma() && !p->iss()) {
     // C_i = mean_j x x^H, constant over the iterations
     TRY(ssbk_wcov(p->X, nullptr, 0, 0, 0, nullptr, 1, p->C, c.n_batch, c.n_sources, c.n_bins, c.n_frames, st));
@@ -404,16 +457,19 @@ extern "C" int ssb_plan_prepare(ssb_plan* p, void* stream) {
 
 extern "C" int ssb_update_source_model(ssb_plan* p, void* stream) {
   TRY(require_bound(p));
+  if (p->mnmf()) return mnmf_source(p, (cudaStream_t)stream);
   return p->ilrma() ? ilrma_source(p, (cudaStream_t)stream) : iva_source(p, (cudaStream_t)stream);
 }
 
 extern "C" int ssb_update_spatial_model(ssb_plan* p, void* stream) {
   TRY(require_bound(p));
+  if (p->mnmf()) return mnmf_spatial(p, (cudaStream_t)stream);
   return p->ilrma() ? ilrma_spatial(p, (cudaStream_t)stream) : iva_spatial(p, (cudaStream_t)stream);
 }
 
 extern "C" int ssb_normalize(ssb_plan* p, void* stream) {
   TRY(require_bound(p));
+  if (p->mnmf()) return mnmf_normalize(p, false, (cudaStream_t)stream);
   SSB_REQUIRE(p->ilrma(), "normalize is defined for ILRMA only");
   return ilrma_normalize(p, (cudaStream_t)stream);
 }
@@ -421,6 +477,12 @@ extern "C" int ssb_normalize(ssb_plan* p, void* stream) {
 extern "C" int ssb_update_once(ssb_plan* p, void* stream) {
   TRY(require_bound(p));
   cudaStream_t st = (cudaStream_t)stream;
+  if (p->mnmf()) {  // mnmf.py:1278-1303
+    TRY(mnmf_source(p, st));
+    TRY(mnmf_spatial(p, st));
+    if (p->cfg.normalization != SSB_NORM_NONE) TRY(mnmf_normalize(p, true, st));
+    return 0;
+  }
   if (p->ilrma()) {
     if (p->cfg.fast_path && ssb_fused_supported(&p->cfg) && p->iss()) {
       const ssb_config& c = p->cfg;
@@ -464,6 +526,7 @@ extern "C" int ssb_update_once(ssb_plan* p, void* stream) {
 extern "C" int ssb_compute_loss(ssb_plan* p, double* loss, void* stream) {
   TRY(require_bound(p));
   SSB_REQUIRE(loss != nullptr, "loss output is NULL");
+  if (p->mnmf()) return mnmf_loss(p, loss, (cudaStream_t)stream);
   return p->ilrma() ? ilrma_loss(p, loss, (cudaStream_t)stream) : iva_loss(p, loss, (cudaStream_t)stream);
 }
 
@@ -478,6 +541,11 @@ extern "C" int ssb_run(ssb_plan* p, int n_iter, double* loss, void* stream) {
 
 extern "C" int ssb_plan_separate(ssb_plan* p, void* stream) {
   TRY(require_bound(p));
+  if (p->mnmf()) {  // multichannel Wiener filter, mnmf.py:1174-1217
+    const ssb_config& c = p->cfg;
+    return ssbk_mnmf_separate(p->X, p->T, p->V, p->W, p->variance, p->qinv, p->Y, c.n_batch, c.n_sources, c.n_bins,
+                              c.n_frames, c.n_basis, c.reference_id, c.flooring, c.eps, (cudaStream_t)stream);
+  }
   if (p->iss()) return 0;
   const ssb_config& c = p->cfg;
   return ssbk_separate(p->X, p->W, p->Y, nullptr, c.n_batch, c.n_sources, c.n_bins, c.n_frames, (cudaStream_t)stream);
@@ -485,6 +553,7 @@ extern "C" int ssb_plan_separate(ssb_plan* p, void* stream) {
 
 extern "C" int ssb_restore_scale(ssb_plan* p, void* stream) {
   TRY(require_bound(p));
+  SSB_REQUIRE(!p->mnmf(), "FastGaussMNMF has no scale restoration (its separate() is the Wiener filter)");
   const ssb_config& c = p->cfg;
   cudaStream_t st = (cudaStream_t)stream;
   const int B = c.n_batch, N = c.n_sources, I = c.n_bins, J = c.n_frames;

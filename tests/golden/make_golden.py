@@ -22,6 +22,7 @@ from ssspy.bss._update_spatial_model import (  # noqa: E402
     update_by_ip1, update_by_ip2, update_by_ip2_one_pair, update_by_iss1)
 from ssspy.bss.ilrma import GaussILRMA  # noqa: E402
 from ssspy.bss.iva import AuxGaussIVA, AuxLaplaceIVA  # noqa: E402
+from ssspy.bss.mnmf import FastGaussMNMF  # noqa: E402
 from ssspy.linalg import eigh, eigh2, inv2  # noqa: E402
 from ssspy.linalg._solve import solve  # noqa: E402
 from ssspy.special.flooring import add_flooring, max_flooring  # noqa: E402
@@ -102,6 +103,28 @@ def iva_case(name, N, I, J, n_iter, model="laplace", spatial="IP", flooring="max
     if model == "gauss":
         out["variance"] = m.variance
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "loss", m.loss[0], "->", m.loss[-1])
+
+
+def mnmf_case(name, N, I, J, K, n_iter, algorithm="IP", flooring="max", reference_id=0, pairs=None, normalization=True,
+              seed=0):
+    """FastGaussMNMF with injected state (tests/regression/bss/test_mnmf.py:108-133 pattern)."""
+    X = make_mixture(N, I, J, seed=200 + seed, mode="mix")
+    rng = np.random.default_rng(300 + seed)
+    T = rng.random((N, I, K))
+    V = rng.random((N, K, J))
+    D = rng.random((I, N, N))
+    Q = rand_w(rng, I, N) if seed % 2 else np.tile(np.eye(N, dtype=np.complex128), (I, 1, 1))
+    sel = combination_pair_selector if pairs == "combination" else None
+    m = FastGaussMNMF(n_basis=K, n_sources=N, diagonalizer_algorithm=algorithm, flooring_fn=FLOOR[flooring],
+                      pair_selector=sel, normalization=normalization, record_loss=True, reference_id=reference_id,
+                      rng=np.random.default_rng(0))
+    Y = m(X, n_iter=n_iter, basis=T, activation=V, spatial=D, diagonalizer=Q)
+    pair_list = np.array(list((sel or sequential_pair_selector)(N)), dtype=np.int32)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), kind="mnmf", X=X, T0=T, V0=V, D0=D, Q0=Q, Y=Y,
+                        T=m.basis, V=m.activation, D=m.spatial, Q=m.diagonalizer, loss=np.array(m.loss),
+                        n_iter=n_iter, algorithm=algorithm, flooring=flooring, reference_id=reference_id,
+                        normalization=normalization, pairs=pair_list)
     print(name, "loss", m.loss[0], "->", m.loss[-1])
 
 
@@ -208,6 +231,13 @@ def main():
         iva_case(f"iva_{model}_iss1_n4", 4, 20, 36, 6, model=model, spatial="ISS", reference_id=1, seed=5)
     iva_case("iva_laplace_ip1_addfloor_noscale", 3, 17, 23, 5, flooring="add", scale_restoration=False, seed=6)
     iva_case("iva_laplace_ip1_n8", 8, 9, 160, 4, seed=7)
+    # FastGaussMNMF (config 5 family)
+    mnmf_case("mnmf_ip1_n2", 2, 17, 24, 3, 5)
+    mnmf_case("mnmf_ip1_n3_qinit", 3, 13, 20, 4, 4, seed=1)
+    mnmf_case("mnmf_ip1_n4_ref1", 4, 11, 32, 3, 4, reference_id=1, seed=2)
+    mnmf_case("mnmf_ip2_n2", 2, 17, 24, 3, 5, algorithm="IP2", seed=3)
+    mnmf_case("mnmf_ip2_n4_comb", 4, 11, 32, 3, 4, algorithm="IP2", pairs="combination", seed=4)
+    mnmf_case("mnmf_ip1_addfloor_nonorm", 3, 13, 20, 4, 4, flooring="add", normalization=False, seed=5)
 
 
 if __name__ == "__main__":

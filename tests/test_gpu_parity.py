@@ -405,3 +405,55 @@ def test_aux_iva_fused_covariance_and_group_solvers(model, N, I, J, spatial):
             np.testing.assert_allclose(np.asarray(m.loss)[:, b], st["loss"], rtol=1e-3, atol=1e-3)
         else:
             assert_loss_close(np.asarray(m.loss)[:, b], st["loss"])
+
+
+@pytest.mark.parametrize("name", golden_cases("mnmf_"))
+def test_fast_gauss_mnmf_matches_reference(name):
+    """FastGaussMNMF (BASELINE config 5 family) with injected state, against the reference's outputs
+    (regression-test pattern of tests/regression/bss/test_mnmf.py:108-133)."""
+    from ssspy_b200.bss import FastGaussMNMF
+    g = load(name)
+    alg = str(g["algorithm"])
+    m = FastGaussMNMF(n_basis=g["T0"].shape[-1], n_sources=g["X"].shape[0], diagonalizer_algorithm=alg,
+                      flooring_fn=_floor_fn(str(g["flooring"])),
+                      pair_selector=_pair_selector(g["pairs"]) if alg == "IP2" else None,
+                      normalization=bool(g["normalization"]), record_loss=True, reference_id=int(g["reference_id"]))
+    Y = m(g["X"], n_iter=int(g["n_iter"]), basis=g["T0"], activation=g["V0"], spatial=g["D0"], diagonalizer=g["Q0"])
+    assert Y.shape == g["Y"].shape and type(m.loss[-1]) is float
+    assert_loss_close(m.loss, g["loss"])
+    assert relerr(Y, g["Y"]) < TOL_Y
+    assert relerr(m.basis, g["T"]) < TOL_TV and relerr(m.activation, g["V"]) < TOL_TV
+    assert relerr(m.spatial, g["D"]) < TOL_TV
+    Q = m.diagonalizer
+    assert relerr(phase_align_rows(Q, g["Q"]) if alg == "IP2" else Q, g["Q"]) < 3 * TOL_Y
+
+
+@pytest.mark.parametrize("alg", ["IP", "IP2"])
+def test_fast_gauss_mnmf_batched_vs_oracle_and_rng(alg):
+    from oracle import mnmf as omnmf
+    from ssspy_b200.bss import FastGaussMNMF
+    from ssspy_b200.utils.synth import make_batch
+    B, N, I, J, K, n_iter = 2, 3, 14, 40, 4, 4
+    X = make_batch(B, N, I, J, config_id=5, mode="mix")
+    m = FastGaussMNMF(n_basis=K, diagonalizer_algorithm=alg, rng=np.random.default_rng(77))
+    Y = m(X, n_iter=n_iter)
+    rng = np.random.default_rng(77)
+    for b in range(B):
+        T = rng.random((N, I, K))
+        V = rng.random((N, K, J))
+        D = rng.random((I, N, N))
+        Q = np.tile(np.eye(N, dtype=np.complex128), (I, 1, 1))
+        st = omnmf.run(X[b], T, V, Q, D, n_iter, algorithm=alg)
+        assert relerr(Y[b], st["Y"]) < tol_seeded(alg)
+        np.testing.assert_allclose(np.asarray(m.loss)[:, b], st["loss"], rtol=1e-3 if alg == "IP2" else 1e-5, atol=1e-4)
+    # update_once through the split phase calls gives the same state as the fused call
+    a = FastGaussMNMF(n_basis=K, diagonalizer_algorithm=alg, rng=np.random.default_rng(5))
+    a(X[0], n_iter=2)
+    b2 = FastGaussMNMF(n_basis=K, diagonalizer_algorithm=alg, rng=np.random.default_rng(5))
+    b2(X[0], n_iter=0)
+    for _ in range(2):
+        b2.update_source_model()
+        b2.update_spatial_model()
+        b2.normalize()
+    assert relerr(b2.basis, a.basis) < 1e-5 and relerr(b2.spatial, a.spatial) < 1e-5
+    assert abs(b2.compute_loss() - a.loss[-1]) <= 1e-5 * abs(a.loss[-1])

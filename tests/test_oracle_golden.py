@@ -114,3 +114,19 @@ def test_projection_back_y_form():
         out = projection_back(g["pb_Y"], reference=g["pb_X"], reference_id=ref)
         assert out.shape == g[f"pb_y_{key}"].shape
         assert relerr(out, g[f"pb_y_{key}"]) < 1e-12
+
+
+@pytest.mark.parametrize("name", golden_cases("mnmf_"))
+def test_fast_gauss_mnmf_oracle_matches_reference(name):
+    from oracle import mnmf as omnmf
+    g = load(name)
+    st = omnmf.run(g["X"], g["T0"], g["V0"], g["Q0"], g["D0"], int(g["n_iter"]), floor=FLOORS[str(g["flooring"])],
+                   algorithm=str(g["algorithm"]), pairs=[tuple(p) for p in g["pairs"]],
+                   normalization=bool(g["normalization"]), reference_id=int(g["reference_id"]))
+    np.testing.assert_allclose(st["loss"], g["loss"], rtol=1e-10, atol=1e-9)
+    assert relerr(st["T"], g["T"]) < TOL and relerr(st["V"], g["V"]) < TOL and relerr(st["D"], g["D"]) < TOL
+    Q = st["Q"]
+    if str(g["algorithm"]) == "IP2":
+        Q = phase_align_rows(Q, g["Q"])
+    assert relerr(Q, g["Q"]) < TOL
+    assert relerr(st["Y"], g["Y"]) < 1e-8
