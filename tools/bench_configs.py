@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
 from ssspy_b200 import _lib  # noqa: E402
-from ssspy_b200.bss import AuxGaussIVA, AuxLaplaceIVA, GaussILRMA  # noqa: E402
+from ssspy_b200.bss import AuxGaussIVA, AuxLaplaceIVA, FastGaussMNMF, GaussILRMA  # noqa: E402
 
 
 def bytes_ilrma(N, I, J, K):
@@ -93,6 +93,10 @@ def main():
     cfgs.append(("c4 GaussILRMA-IP2 N=8 I=2049 J=1024 K=32 B=64 (one GPU's shard of B=512)",
                  lambda: GaussILRMA(32, "IP2", record_loss=False, scale_restoration=False), (64, 8, 2049, 1024), 32,
                  bytes_ilrma(8, 2049, 1024, 32)))
+    cfgs.append(("c5 FastGaussMNMF-IP N=4 I=1025 J=512 K=16 B=256", lambda: FastGaussMNMF(16, diagonalizer_algorithm="IP", record_loss=False),
+                 (256, 4, 1025, 512), 16, bytes_ilrma(4, 1025, 512, 16) + 2 * 4 * 1025 * 4 * 4))
+    cfgs.append(("c5b FastGaussMNMF-IP2 N=4 I=1025 J=512 K=16 B=256", lambda: FastGaussMNMF(16, diagonalizer_algorithm="IP2", record_loss=False),
+                 (256, 4, 1025, 512), 16, bytes_ilrma(4, 1025, 512, 16) + 2 * 4 * 1025 * 4 * 4))
     for name, make, shape, K, ab in cfgs:
         if args.only and args.only not in name:
             continue
