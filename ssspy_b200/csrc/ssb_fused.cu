@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(FW * 32) kf_basis(const cf* __restrict__ X, co
 // ------------------------------------------------------------------------------------------------
 // kf_phi: phi[b,n,i,j] = 1 / (T V) written out (ISS modes consume the weights as an array,
 // ssspy/bss/ilrma.py:1690-1696).  Same tiling as kf_basis, R on the tensor pipe.
-template <int KS>
+template <int KS, bool INV>
 __global__ void __launch_bounds__(FW * 32) kf_phi(const float* __restrict__ T, const float* __restrict__ V,
                                                   float* __restrict__ phi, int I, int J, int K) {
   constexpr int KP = 16 * KS;
@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(FW * 32) kf_phi(const float* __restrict__ T, c
       for (int rr = 0; rr < 2; ++rr)
         if (rvalid[rr])
           *reinterpret_cast<float2*>(phi + (bn * I + row[rr]) * J + jc0 + jj + 2 * t) =
-              make_float2(1.0f / R[rr * 2], 1.0f / R[rr * 2 + 1]);
+              INV ? make_float2(1.0f / R[rr * 2], 1.0f / R[rr * 2 + 1]) : make_float2(R[rr * 2], R[rr * 2 + 1]);
     }
   }
 }
@@ -824,8 +824,8 @@ struct CovSrc {
 
 template <int N>
 __global__ void __launch_bounds__(FW * 32) kf_cov_w(const cf* __restrict__ X, const float* __restrict__ phi,
-                                                    long long sb, long long sn, int n_src, cf* __restrict__ U,
-                                                    int I, int J) {
+                                                    long long sb, long long sn, long long si, int n_src,
+                                                    cf* __restrict__ U, int I, int J) {
   constexpr int G = CovShape<N>::G;
   constexpr bool RS = CovShape<N>::RS;
   constexpr bool STG = CovShape<N>::STG_W;
@@ -894,9 +894,10 @@ __global__ void __launch_bounds__(FW * 32) kf_cov_w(const cf* __restrict__ X, co
 #pragma unroll
           for (int gs = 0; gs < G; ++gs) {
             const int s = min(s0 + gs, n_src - 1);
-            const float2 ph = *reinterpret_cast<const float2*>(phi + (size_t)b * sb + (size_t)s * sn + jj + 8 * h + 2 * t);
 #pragma unroll
             for (int r = 0; r < NR; ++r) {
+              const float2 ph = *reinterpret_cast<const float2*>(phi + (size_t)b * sb + (size_t)s * sn +
+                                                                 (size_t)rowc[RS ? rs : r] * si + jj + 8 * h + 2 * t);
               float* ac = acc[gs][r];
 #pragma unroll
               for (int a = 0; a < N; ++a) {
@@ -945,8 +946,8 @@ __global__ void __launch_bounds__(FW * 32) kf_cov_w(const cf* __restrict__ X, co
 }
 
 template <int N>
-int launch_cov_w(const cf* X, const float* phi, long long sb, long long sn, int n_src, cf* U, int B, int I, int J,
-                 cudaStream_t st) {
+int launch_cov_w(const cf* X, const float* phi, long long sb, long long sn, long long si, int n_src, cf* U, int B,
+                 int I, int J, cudaStream_t st) {
   constexpr int NRC = CovShape<N>::RS ? 1 : 2;
   constexpr int G = CovShape<N>::G;
   const size_t sm = CovShape<N>::STG_W ? (size_t)FW * XSTAGES * 2 * NRC * N * 32 * sizeof(float4) : 0;
@@ -956,7 +957,7 @@ int launch_cov_w(const cf* X, const float* phi, long long sb, long long sn, int 
     attr_set = true;
   }
   dim3 grid((n_src + G - 1) / G, (I + FW * 16 - 1) / (FW * 16), B);
-  kf_cov_w<N><<<grid, FW * 32, sm, st>>>(X, phi, sb, sn, n_src, U, I, J);
+  kf_cov_w<N><<<grid, FW * 32, sm, st>>>(X, phi, sb, sn, si, n_src, U, I, J);
   return ssb_check_launch("fused_cov_w", st);
 }
 
@@ -1167,25 +1168,27 @@ int ssb_fused_source_iss(const ssb_config* c, const cf* Y, float* T, float* V, f
   return launch_source_iss<2>(c, Y, T, V, P, st);
 }
 
-// phi[B*N, I, J] = 1 / (T V)
-int ssb_fused_phi(const ssb_config* c, const float* T, const float* V, float* phi, cudaStream_t st) {
+// phi[B*N, I, J] = 1 / (T V)  (inverse = 1)  or  Lambda = T V  (inverse = 0)
+int ssb_fused_phi(const ssb_config* c, const float* T, const float* V, float* phi, int inverse, cudaStream_t st) {
   const int BN = c->n_batch * c->n_sources, I = c->n_bins, J = c->n_frames, K = c->n_basis;
   dim3 grid((I + FW * 16 - 1) / (FW * 16), BN);
   if (K <= 16) {
     const size_t sm = (size_t)(2 * JC * (16 + PADH)) * sizeof(__nv_bfloat16);
-    kf_phi<1><<<grid, FW * 32, sm, st>>>(T, V, phi, I, J, K);
+    if (inverse) kf_phi<1, true><<<grid, FW * 32, sm, st>>>(T, V, phi, I, J, K);
+    else kf_phi<1, false><<<grid, FW * 32, sm, st>>>(T, V, phi, I, J, K);
   } else {
     const size_t sm = (size_t)(2 * JC * (32 + PADH)) * sizeof(__nv_bfloat16);
-    kf_phi<2><<<grid, FW * 32, sm, st>>>(T, V, phi, I, J, K);
+    if (inverse) kf_phi<2, true><<<grid, FW * 32, sm, st>>>(T, V, phi, I, J, K);
+    else kf_phi<2, false><<<grid, FW * 32, sm, st>>>(T, V, phi, I, J, K);
   }
-  return ssb_check_launch("fused_phi", st);
+  return ssb_check_launch(inverse ? "fused_phi" : "fused_lambda", st);
 }
 
 // weighted covariance with array weights phi[b*sb + s*sn + j] (n_frames % 16 == 0 required)
-int ssb_fused_cov_w(const cf* X, const float* phi, long long sb, long long sn, int n_src, cf* U, int B, int N, int I,
-                    int J, cudaStream_t st) {
+int ssb_fused_cov_w(const cf* X, const float* phi, long long sb, long long sn, long long si, int n_src, cf* U, int B,
+                    int N, int I, int J, cudaStream_t st) {
   SSB_REQUIRE((J % 16) == 0, "fused_cov_w needs n_frames %% 16 == 0");
-  SSB_DISPATCH_N(N, return (launch_cov_w<NN>(X, phi, sb, sn, n_src, U, B, I, J, st)));
+  SSB_DISPATCH_N(N, return (launch_cov_w<NN>(X, phi, sb, sn, si, n_src, U, B, I, J, st)));
   return 0;
 }
 

@@ -22,10 +22,12 @@ int ssb_fused_ip1_n2(cf* W, const cf* U, const cf* C, double* q, int n_mat, int 
 // power normalisation from the per-bin terms q: psi_n = floor(sqrt(mean_i q)), T /= psi^p, W /= psi
 int ssb_fused_normalize(const double* q, float* T, cf* W, int B, int N, int I, int K, float p, int flooring,
                         float eps, cudaStream_t st);
-// weighted covariance with array weights phi[b*sb + s*sn + j] for s < n_src (AuxIVA); U[B,I,n_src,N,N];
+// weighted covariance with array weights phi[b*sb + s*sn + i*si + j] for s < n_src (AuxIVA: si = 0;
+// FastGaussMNMF: per-bin weights); U[B,I,n_src,N,N];
 // requires n_frames % 16 == 0
-int ssb_fused_cov_w(const cf* X, const float* phi, long long sb, long long sn, int n_src, cf* U, int B, int N, int I,
-                    int J, cudaStream_t st);
+int ssb_fused_cov_w(const cf* X, const float* phi, long long sb, long long sn, long long si, int n_src, cf* U, int B,
+                    int N, int I, int J, cudaStream_t st);
 // ISS modes: MM source model (T then V, p = 2) with P = |Y|^2, and phi = 1/(T V) as an array
 int ssb_fused_source_iss(const ssb_config* cfg, const cf* Y, float* T, float* V, float* P, cudaStream_t st);
-int ssb_fused_phi(const ssb_config* cfg, const float* T, const float* V, float* phi, cudaStream_t st);
+// inverse = 1: phi = 1/(T V); inverse = 0: Lambda = T V
+int ssb_fused_phi(const ssb_config* cfg, const float* T, const float* V, float* phi, int inverse, cudaStream_t st);

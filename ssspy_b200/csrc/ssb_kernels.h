@@ -88,15 +88,15 @@ int ssbk_nmf_basis_ab(const float* A, const float* Bm, float* T, const float* V,
                       int flooring, float eps, cudaStream_t st);
 int ssbk_nmf_activation_ab(const float* A, const float* Bm, const float* T, float* V, int BN, int I, int J, int K,
                            int flooring, float eps, cudaStream_t st);
-int ssbk_mnmf_gh(const cf* X, const float* T, const float* V, const cf* Q, const float* D, float* G, float* H, int B,
+int ssbk_mnmf_gh(const cf* X, const float* T, const float* V, const float* Lam, const cf* Q, const float* D, float* G, float* H, int B,
                  int N, int I, int J, int K, cudaStream_t st);
-int ssbk_mnmf_phi(const cf* X, const float* T, const float* V, const cf* Q, const float* D, float* phi, int B, int N,
+int ssbk_mnmf_phi(const cf* X, const float* T, const float* V, const float* Lam, const cf* Q, const float* D, float* phi, int B, int N,
                   int I, int J, int K, cudaStream_t st);
-int ssbk_mnmf_spatial(const cf* X, const float* T, const float* V, const cf* Q, float* D, double* zsum, int B, int N,
+int ssbk_mnmf_spatial(const cf* X, const float* T, const float* V, const float* Lam, const cf* Q, float* D, double* zsum, int B, int N,
                       int I, int J, int K, int update_d, cudaStream_t st);
 int ssbk_mnmf_normalize(const double* zsum, cf* Q, float* D, int B, int N, int I, int J, int flooring, float eps,
                         cudaStream_t st);
-int ssbk_mnmf_rowloss(const cf* X, const float* T, const float* V, const cf* Q, const float* D, double* rowloss, int B,
+int ssbk_mnmf_rowloss(const cf* X, const float* T, const float* V, const float* Lam, const cf* Q, const float* D, double* rowloss, int B,
                       int N, int I, int J, int K, cudaStream_t st);
 int ssbk_mnmf_separate(const cf* X, const float* T, const float* V, const cf* Q, const float* D, cd* Qinv, cf* Y, int B,
                        int N, int I, int J, int K, int ref, int flooring, float eps, cudaStream_t st);

@@ -42,17 +42,21 @@ __device__ __forceinline__ void load_ctx(BinCtx<N>& c, const float* __restrict__
 // Lambda_n, L_m and Z2_m of one (bin, frame)
 template <int N>
 __device__ __forceinline__ void frame_stats(const BinCtx<N>& c, const cf* __restrict__ X, const float* __restrict__ V,
-                                            int b, int i, int j, int I, int J, int K, float (&lam)[N], float (&L)[N],
-                                            float (&Z2)[N]) {
+                                            const float* __restrict__ Lam, int b, int i, int j, int I, int J, int K,
+                                            float (&lam)[N], float (&L)[N], float (&Z2)[N]) {
   cf x[N];
 #pragma unroll
   for (int m = 0; m < N; ++m) x[m] = X[(((size_t)b * N + m) * I + i) * J + j];
 #pragma unroll
   for (int n = 0; n < N; ++n) {
-    const float* v = V + ((size_t)b * N + n) * K * J + j;
-    float s = 0.f;
-    for (int k = 0; k < K; ++k) s = fmaf(c.T[n][k], v[(size_t)k * J], s);
-    lam[n] = s;
+    if (Lam != nullptr) {  // Lambda = T V precomputed on the tensor pipe
+      lam[n] = Lam[(((size_t)b * N + n) * I + i) * J + j];
+    } else {
+      const float* v = V + ((size_t)b * N + n) * K * J + j;
+      float s = 0.f;
+      for (int k = 0; k < K; ++k) s = fmaf(c.T[n][k], v[(size_t)k * J], s);
+      lam[n] = s;
+    }
   }
 #pragma unroll
   for (int m = 0; m < N; ++m) {
@@ -73,7 +77,8 @@ __device__ __forceinline__ void frame_stats(const BinCtx<N>& c, const cf* __rest
 // G[b,n,i,j] = sum_m D[n,m] Z2_m / L_m^2,  H[b,n,i,j] = sum_m D[n,m] / L_m     (mnmf.py:1348-1350)
 template <int N>
 __global__ void __launch_bounds__(MW * 32) km_gh(const cf* __restrict__ X, const float* __restrict__ T,
-                                                 const float* __restrict__ V, const cf* __restrict__ Q,
+                                                 const float* __restrict__ V, const float* __restrict__ Lam,
+                                                 const cf* __restrict__ Q,
                                                  const float* __restrict__ D, float* __restrict__ G,
                                                  float* __restrict__ H, int B, int I, int J, int K) {
   __shared__ BinCtx<N> ctx[MW];
@@ -85,7 +90,7 @@ __global__ void __launch_bounds__(MW * 32) km_gh(const cf* __restrict__ X, const
   load_ctx<N>(c, T, Q, D, b, i, I, K, lane);
   for (int j = lane; j < J; j += 32) {
     float lam[N], L[N], Z2[N];
-    frame_stats<N>(c, X, V, b, i, j, I, J, K, lam, L, Z2);
+    frame_stats<N>(c, X, V, Lam, b, i, j, I, J, K, lam, L, Z2);
     float r[N], r2[N];
 #pragma unroll
     for (int m = 0; m < N; ++m) {
@@ -110,7 +115,8 @@ __global__ void __launch_bounds__(MW * 32) km_gh(const cf* __restrict__ X, const
 // phi[b,m,i,j] = 1 / L[i,j,m]      (mnmf.py:1504-1510)
 template <int N>
 __global__ void __launch_bounds__(MW * 32) km_phi(const cf* __restrict__ X, const float* __restrict__ T,
-                                                  const float* __restrict__ V, const cf* __restrict__ Q,
+                                                  const float* __restrict__ V, const float* __restrict__ Lam,
+                                                 const cf* __restrict__ Q,
                                                   const float* __restrict__ D, float* __restrict__ phi, int B, int I,
                                                   int J, int K) {
   __shared__ BinCtx<N> ctx[MW];
@@ -122,7 +128,7 @@ __global__ void __launch_bounds__(MW * 32) km_phi(const cf* __restrict__ X, cons
   load_ctx<N>(c, T, Q, D, b, i, I, K, lane);
   for (int j = lane; j < J; j += 32) {
     float lam[N], L[N], Z2[N];
-    frame_stats<N>(c, X, V, b, i, j, I, J, K, lam, L, Z2);
+    frame_stats<N>(c, X, V, Lam, b, i, j, I, J, K, lam, L, Z2);
 #pragma unroll
     for (int m = 0; m < N; ++m) phi[(((size_t)b * N + m) * I + i) * J + j] = 1.0f / L[m];
   }
@@ -132,7 +138,8 @@ __global__ void __launch_bounds__(MW * 32) km_phi(const cf* __restrict__ X, cons
 // one source per pass over the frames keeps the accumulators in registers.  update_d = 0: zsum only.
 template <int N>
 __global__ void __launch_bounds__(MW * 32) km_spatial(const cf* __restrict__ X, const float* __restrict__ T,
-                                                      const float* __restrict__ V, const cf* __restrict__ Q,
+                                                      const float* __restrict__ V, const float* __restrict__ Lam,
+                                                 const cf* __restrict__ Q,
                                                       float* __restrict__ D, double* __restrict__ zsum, int B, int I,
                                                       int J, int K, int update_d) {
   __shared__ BinCtx<N> ctx[MW];
@@ -149,7 +156,7 @@ __global__ void __launch_bounds__(MW * 32) km_spatial(const cf* __restrict__ X, 
     for (int m = 0; m < N; ++m) num[m] = den[m] = zs[m] = 0.f;
     for (int j = lane; j < J; j += 32) {
       float lam[N], L[N], Z2[N];
-      frame_stats<N>(c, X, V, b, i, j, I, J, K, lam, L, Z2);
+      frame_stats<N>(c, X, V, Lam, b, i, j, I, J, K, lam, L, Z2);
       float ln = lam[0];
 #pragma unroll
       for (int q = 1; q < N; ++q) ln = (q == n) ? lam[q] : ln;
@@ -206,7 +213,8 @@ __global__ void km_normalize(const double* __restrict__ zsum, cf* __restrict__ Q
 // rowloss[b,i] = mean_j sum_m (Z2/L + log L)     (mnmf.py:1255-1258)
 template <int N>
 __global__ void __launch_bounds__(MW * 32) km_rowloss(const cf* __restrict__ X, const float* __restrict__ T,
-                                                      const float* __restrict__ V, const cf* __restrict__ Q,
+                                                      const float* __restrict__ V, const float* __restrict__ Lam,
+                                                 const cf* __restrict__ Q,
                                                       const float* __restrict__ D, double* __restrict__ rowloss, int B,
                                                       int I, int J, int K) {
   __shared__ BinCtx<N> ctx[MW];
@@ -219,7 +227,7 @@ __global__ void __launch_bounds__(MW * 32) km_rowloss(const cf* __restrict__ X, 
   double acc = 0.0;
   for (int j = lane; j < J; j += 32) {
     float lam[N], L[N], Z2[N];
-    frame_stats<N>(c, X, V, b, i, j, I, J, K, lam, L, Z2);
+    frame_stats<N>(c, X, V, Lam, b, i, j, I, J, K, lam, L, Z2);
     float s = 0.f;
 #pragma unroll
     for (int m = 0; m < N; ++m) s += Z2[m] / L[m] + logf(L[m]);
@@ -332,20 +340,20 @@ __global__ void __launch_bounds__(128) km_separate(const cf* __restrict__ X, con
 
 }  // namespace
 
-int ssbk_mnmf_gh(const cf* X, const float* T, const float* V, const cf* Q, const float* D, float* G, float* H, int B,
+int ssbk_mnmf_gh(const cf* X, const float* T, const float* V, const float* Lam, const cf* Q, const float* D, float* G, float* H, int B,
                  int N, int I, int J, int K, cudaStream_t st) {
-  SSB_DISPATCH_N(N, km_gh<NN><<<blocks_for((long long)B * I, MW), MW * 32, 0, st>>>(X, T, V, Q, D, G, H, B, I, J, K));
+  SSB_DISPATCH_N(N, km_gh<NN><<<blocks_for((long long)B * I, MW), MW * 32, 0, st>>>(X, T, V, Lam, Q, D, G, H, B, I, J, K));
   return ssb_check_launch("mnmf_gh", st);
 }
-int ssbk_mnmf_phi(const cf* X, const float* T, const float* V, const cf* Q, const float* D, float* phi, int B, int N,
+int ssbk_mnmf_phi(const cf* X, const float* T, const float* V, const float* Lam, const cf* Q, const float* D, float* phi, int B, int N,
                   int I, int J, int K, cudaStream_t st) {
-  SSB_DISPATCH_N(N, km_phi<NN><<<blocks_for((long long)B * I, MW), MW * 32, 0, st>>>(X, T, V, Q, D, phi, B, I, J, K));
+  SSB_DISPATCH_N(N, km_phi<NN><<<blocks_for((long long)B * I, MW), MW * 32, 0, st>>>(X, T, V, Lam, Q, D, phi, B, I, J, K));
   return ssb_check_launch("mnmf_phi", st);
 }
-int ssbk_mnmf_spatial(const cf* X, const float* T, const float* V, const cf* Q, float* D, double* zsum, int B, int N,
+int ssbk_mnmf_spatial(const cf* X, const float* T, const float* V, const float* Lam, const cf* Q, float* D, double* zsum, int B, int N,
                       int I, int J, int K, int update_d, cudaStream_t st) {
-  SSB_DISPATCH_N(N, km_spatial<NN><<<blocks_for((long long)B * I, MW), MW * 32, 0, st>>>(X, T, V, Q, D, zsum, B, I, J,
-                                                                                          K, update_d));
+  SSB_DISPATCH_N(N, km_spatial<NN><<<blocks_for((long long)B * I, MW), MW * 32, 0, st>>>(X, T, V, Lam, Q, D, zsum, B, I,
+                                                                                          J, K, update_d));
   return ssb_check_launch("mnmf_spatial", st);
 }
 int ssbk_mnmf_normalize(const double* zsum, cf* Q, float* D, int B, int N, int I, int J, int flooring, float eps,
@@ -353,10 +361,10 @@ int ssbk_mnmf_normalize(const double* zsum, cf* Q, float* D, int B, int N, int I
   km_normalize<<<B, 256, 0, st>>>(zsum, Q, D, N, I, J, flooring, (double)eps);
   return ssb_check_launch("mnmf_normalize", st);
 }
-int ssbk_mnmf_rowloss(const cf* X, const float* T, const float* V, const cf* Q, const float* D, double* rowloss, int B,
+int ssbk_mnmf_rowloss(const cf* X, const float* T, const float* V, const float* Lam, const cf* Q, const float* D, double* rowloss, int B,
                       int N, int I, int J, int K, cudaStream_t st) {
-  SSB_DISPATCH_N(N, km_rowloss<NN><<<blocks_for((long long)B * I, MW), MW * 32, 0, st>>>(X, T, V, Q, D, rowloss, B, I,
-                                                                                          J, K));
+  SSB_DISPATCH_N(N, km_rowloss<NN><<<blocks_for((long long)B * I, MW), MW * 32, 0, st>>>(X, T, V, Lam, Q, D, rowloss, B,
+                                                                                          I, J, K));
   return ssb_check_launch("mnmf_rowloss", st);
 }
 int ssbk_mnmf_separate(const cf* X, const float* T, const float* V, const cf* Q, const float* D, cd* Qinv, cf* Y, int B,

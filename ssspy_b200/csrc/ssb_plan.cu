@@ -133,6 +133,7 @@ struct ssb_plan {
   bool bound = false, prepared = false;
   float* big2 = nullptr;    // [B,N,I,J] f32 second elementwise scratch (FastGaussMNMF: H)
   cd* qinv = nullptr;       // [B,I,N,N] c128 (FastGaussMNMF separate)
+  float* big3 = nullptr;    // [B,N,I,J] f32 Lambda = T V (FastGaussMNMF, tensor-core kernel)
   bool mnmf() const { return cfg.model == SSB_MODEL_FASTMNMF_GAUSS; }
   bool iss() const { return cfg.spatial == SSB_SPATIAL_ISS1 && !mnmf(); }
   bool ilrma() const { return cfg.model == SSB_MODEL_ILRMA_GAUSS; }
@@ -161,6 +162,7 @@ size_t carve(ssb_plan* p, char* base) {
   p->big = (p->ilrma() || p->mnmf()) ? cv.take<float>(B * N * I * J + 16 * J) : nullptr;
   p->big2 = p->mnmf() ? cv.take<float>(B * N * I * J) : nullptr;
   p->qinv = p->mnmf() ? cv.take<cd>(B * I * N * N) : nullptr;
+  p->big3 = p->mnmf() ? cv.take<float>(B * N * I * J) : nullptr;
   p->phi_iva = cv.take<float>(B * N * J);
   p->r2 = cv.take<float>(B * N * J);
   p->U = cv.take<cf>(B * I * N * N * N);
@@ -323,7 +325,7 @@ int iva_spatial(ssb_plan* p, cudaStream_t st) {
       const int uidx[2] = {0, 1};
       TRY(ssbk_iva_norm2(p->X, p->W, nullptr, pr, 2, p->r2, B, N, I, J, st));
       TRY(ssbk_iva_phi(p->r2, p->variance, 0, pr, 2, p->phi_iva, c.model, B, N, I, J, c.flooring, c.eps, st));
-      if (c.fast_path && (J % 16) == 0) TRY(ssb_fused_cov_w(p->X, p->phi_iva, 2LL * J, J, 2, p->U, B, N, I, J, st));
+      if (c.fast_path && (J % 16) == 0) TRY(ssb_fused_cov_w(p->X, p->phi_iva, 2LL * J, J, 0, 2, p->U, B, N, I, J, st));
       else TRY(ssbk_wcov(p->X, p->phi_iva, 2LL * J, J, 0, nullptr, 2, p->U, B, N, I, J, st));
       TRY(ssbk_ip2(p->W, p->U, B * I, N, pr, 1, 2, uidx, c.flooring, c.eps, st));
     }
@@ -333,7 +335,7 @@ int iva_spatial(ssb_plan* p, cudaStream_t st) {
   TRY(ssbk_iva_phi(p->r2, p->variance, 0, nullptr, N, p->phi_iva, c.model, B, N, I, J, c.flooring, c.eps, st));
   if (c.spatial == SSB_SPATIAL_ISS1)
     return ssbk_iss1(p->Y, p->phi_iva, (long long)N * J, J, 0, B, N, I, J, c.flooring, c.eps, st);
-  if (c.fast_path && (J % 16) == 0) TRY(ssb_fused_cov_w(p->X, p->phi_iva, (long long)N * J, J, N, p->U, B, N, I, J, st));
+  if (c.fast_path && (J % 16) == 0) TRY(ssb_fused_cov_w(p->X, p->phi_iva, (long long)N * J, J, 0, N, p->U, B, N, I, J, st));
   else TRY(ssbk_wcov(p->X, p->phi_iva, (long long)N * J, J, 0, nullptr, N, p->U, B, N, I, J, st));
   return ssbk_ip1(p->W, p->U, B * I, N, c.flooring, c.eps, st);
 }
@@ -346,36 +348,58 @@ int iva_loss(ssb_plan* p, double* loss, cudaStream_t st) {
 }
 
 // ---- FastGaussMNMF: W slot = diagonaliser Q[B,I,N,N] c64, variance slot = spatial D[B,I,N,N] f32 ----------
+// Lambda = T V on the tensor pipe when the fused kernel covers the shape, else NULL (the consumers then
+// contract over K themselves)
+int mnmf_lambda(ssb_plan* p, const float** lam, cudaStream_t st) {
+  const ssb_config& c = p->cfg;
+  *lam = nullptr;
+  if (c.fast_path && c.n_basis <= 32 && (c.n_frames % 16) == 0) {
+    TRY(ssb_fused_phi(&c, p->T, p->V, p->big3, 0, st));
+    *lam = p->big3;
+  }
+  return 0;
+}
+
 int mnmf_source(ssb_plan* p, cudaStream_t st) {
   const ssb_config& c = p->cfg;
   const int B = c.n_batch, N = c.n_sources, I = c.n_bins, J = c.n_frames, K = c.n_basis;
-  TRY(ssbk_mnmf_gh(p->X, p->T, p->V, p->W, p->variance, p->big, p->big2, B, N, I, J, K, st));
+  const float* lam;
+  TRY(mnmf_lambda(p, &lam, st));
+  TRY(ssbk_mnmf_gh(p->X, p->T, p->V, lam, p->W, p->variance, p->big, p->big2, B, N, I, J, K, st));
   TRY(ssbk_nmf_basis_ab(p->big, p->big2, p->T, p->V, B * N, I, J, K, c.flooring, c.eps, st));
-  TRY(ssbk_mnmf_gh(p->X, p->T, p->V, p->W, p->variance, p->big, p->big2, B, N, I, J, K, st));
+  TRY(mnmf_lambda(p, &lam, st));
+  TRY(ssbk_mnmf_gh(p->X, p->T, p->V, lam, p->W, p->variance, p->big, p->big2, B, N, I, J, K, st));
   return ssbk_nmf_activation_ab(p->big, p->big2, p->T, p->V, B * N, I, J, K, c.flooring, c.eps, st);
 }
 
 int mnmf_spatial(ssb_plan* p, cudaStream_t st) {
   const ssb_config& c = p->cfg;
   const int B = c.n_batch, N = c.n_sources, I = c.n_bins, J = c.n_frames, K = c.n_basis;
-  TRY(ssbk_mnmf_phi(p->X, p->T, p->V, p->W, p->variance, p->big, B, N, I, J, K, st));
-  TRY(ssbk_wcov(p->X, p->big, (long long)N * I * J, (long long)I * J, J, nullptr, N, p->U, B, N, I, J, st));
+  const float* lam;
+  TRY(mnmf_lambda(p, &lam, st));
+  TRY(ssbk_mnmf_phi(p->X, p->T, p->V, lam, p->W, p->variance, p->big, B, N, I, J, K, st));
+  if (c.fast_path && (J % 16) == 0)
+    TRY(ssb_fused_cov_w(p->X, p->big, (long long)N * I * J, (long long)I * J, J, N, p->U, B, N, I, J, st));
+  else
+    TRY(ssbk_wcov(p->X, p->big, (long long)N * I * J, (long long)I * J, J, nullptr, N, p->U, B, N, I, J, st));
   if (c.spatial == SSB_SPATIAL_IP1) TRY(ssbk_ip1(p->W, p->U, B * I, N, c.flooring, c.eps, st));
   else TRY(ssbk_ip2(p->W, p->U, B * I, N, c.pairs, c.n_pairs, N, nullptr, c.flooring, c.eps, st));
-  return ssbk_mnmf_spatial(p->X, p->T, p->V, p->W, p->variance, p->rowloss, B, N, I, J, K, 1, st);
+  return ssbk_mnmf_spatial(p->X, p->T, p->V, lam, p->W, p->variance, p->rowloss, B, N, I, J, K, 1, st);
 }
 
 int mnmf_normalize(ssb_plan* p, bool have_zsum, cudaStream_t st) {
   const ssb_config& c = p->cfg;
   const int B = c.n_batch, N = c.n_sources, I = c.n_bins, J = c.n_frames, K = c.n_basis;
-  if (!have_zsum) TRY(ssbk_mnmf_spatial(p->X, p->T, p->V, p->W, p->variance, p->rowloss, B, N, I, J, K, 0, st));
+  if (!have_zsum) TRY(ssbk_mnmf_spatial(p->X, p->T, p->V, nullptr, p->W, p->variance, p->rowloss, B, N, I, J, K, 0, st));
   return ssbk_mnmf_normalize(p->rowloss, p->W, p->variance, B, N, I, J, c.flooring, c.eps, st);
 }
 
 int mnmf_loss(ssb_plan* p, double* loss, cudaStream_t st) {
   const ssb_config& c = p->cfg;
   const int B = c.n_batch, N = c.n_sources, I = c.n_bins, J = c.n_frames, K = c.n_basis;
-  TRY(ssbk_mnmf_rowloss(p->X, p->T, p->V, p->W, p->variance, p->rowloss, B, N, I, J, K, st));
+  const float* lam;
+  TRY(mnmf_lambda(p, &lam, st));
+  TRY(ssbk_mnmf_rowloss(p->X, p->T, p->V, lam, p->W, p->variance, p->rowloss, B, N, I, J, K, st));
   TRY(ssbk_logdet(p->W, p->logdet, B * I, N, st));
   return ssbk_ilrma_loss_reduce(p->rowloss, p->logdet, loss, B, 1, I, st);
 }
@@ -488,7 +512,7 @@ extern "C" int ssb_update_once(ssb_plan* p, void* stream) {
       const ssb_config& c = p->cfg;
       const int B = c.n_batch, N = c.n_sources, I = c.n_bins, J = c.n_frames;
       TRY(ssb_fused_source_iss(&c, p->Y, p->T, p->V, p->big, st));
-      TRY(ssb_fused_phi(&c, p->T, p->V, p->big, st));
+      TRY(ssb_fused_phi(&c, p->T, p->V, p->big, 1, st));
       TRY(ssbk_iss1(p->Y, p->big, (long long)N * I * J, (long long)I * J, J, B, N, I, J, c.flooring, c.eps, st));
       if (c.normalization != SSB_NORM_NONE) TRY(ilrma_normalize(p, st));
       return 0;
