@@ -44,13 +44,21 @@ def run(name, make, X, abytes, steps, peak, **state):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
+    extra = {}
+    if isinstance(sep, FastGaussMNMF):  # the per-(bin, frame) eigendecomposition path of config 5
+        e0.record()
+        sep._plan_call("ssb_plan_separate")
+        e1.record()
+        torch.cuda.synchronize()
+        extra["separate_ms (Wiener filter, I*J Hermitian eigh per mixture)"] = round(e0.elapsed_time(e1), 3)
+        extra["eigh_per_sec"] = round(X.shape[0] * X.shape[2] * X.shape[3] / (e0.elapsed_time(e1) * 1e-3), 0)
     B = X.shape[0]
     gbs = abytes * B / (ms * 1e-3) / 1e9
     print(json.dumps({"config": name, "batch": B, "ms_per_step": round(ms, 4),
                       "mixture_iterations_per_sec": round(B / (ms * 1e-3), 1),
                       "algorithmic_MB_per_step": round(abytes * B / 1e6, 1), "achieved_GBps": round(gbs, 1),
                       "hbm_frac": round(gbs / peak, 4),
-                      "kernels_ms_per_step": {k[0]: round(k[2] / 2, 4) for k in kern}}), flush=True)
+                      "kernels_ms_per_step": {k[0]: round(k[2] / 2, 4) for k in kern}, **extra}), flush=True)
     del sep
     torch.cuda.empty_cache()
 
