@@ -126,6 +126,9 @@ int ssb_compute_loss(ssb_plan* plan, double* loss, void* stream);
 /* restore_scale / apply_projection_back: ilrma.py:538-565,1969-1979; iva.py:238-267,2194-2204.
  * W-modes: W <- projection_back(W), Y <- W X.  ISS modes: Y <- projection_back(Y, X). */
 int ssb_restore_scale(ssb_plan* plan, void* stream);
+/* restore_scale with scale_restoration="minimal_distortion_principle" (ilrma.py:567-579,1981-1989; iva.py:269-281,
+ * 2206-2214): Y <- mdp(Y | W X, X); in W modes W is refitted as Y X^H (X X^H)^-1 */
+int ssb_restore_scale_mdp(ssb_plan* plan, void* stream);
 /* Y <- W X with the plan's current W (ilrma.py:272-295); no-op in ISS modes */
 int ssb_plan_separate(ssb_plan* plan, void* stream);
 
@@ -162,6 +165,11 @@ int ssb_projection_back_w(const void* W, void* Wout, int n_mat, int N, int refer
  * (the reference_id=None case reads it); Yout may be NULL to compute only the scale. */
 int ssb_projection_back_y(const void* Y, const void* X, void* Yout, void* scale_out, int B, int N, int I,
                           int J, int reference_id, void* stream);
+
+/* minimal_distortion_principle (ssspy/algorithm/minimal_distortion_principle.py:6-43): Yout[b,n,i,:] =
+ * conj(z) Y[b,n,i,:], z = sum_j Y conj(X[b,ref,i,:]) / sum_j |Y|^2; Yout may alias Y */
+int ssb_minimal_distortion_principle(const void* Y, const void* X, void* Yout, int B, int N, int I, int J,
+                                     int reference_id, void* stream);
 
 /* ---- ssspy.linalg helpers, batched over n_mat small matrices, complex128 in/out -------------- */
 /* inv2 (ssspy/linalg/inv.py:4-54) generalised to N x N (np.linalg.inv call sites:

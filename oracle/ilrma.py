@@ -10,7 +10,7 @@ Restated from SURVEY.md Appendix A.1 = ssspy/bss/ilrma.py:900-922 (update_once),
 import numpy as np
 
 from . import spatial
-from .projection_back import projection_back
+from .projection_back import minimal_distortion_principle, projection_back
 
 
 def separate(X, W):
@@ -127,8 +127,19 @@ def compute_loss(st, p=2):
     return float((np.sum(loss.mean(axis=-1), axis=0) - 2 * logdet).sum())
 
 
-def restore_scale(st, reference_id=0):
-    """ssspy/bss/ilrma.py:557-565 (W-form) / :1971-1977 (Y-form)."""
+def restore_scale(st, reference_id=0, method=True):
+    """Projection back: ssspy/bss/ilrma.py:557-565 (W-form) / :1971-1977 (Y-form); minimal distortion
+    principle: :567-579 / :1981-1989."""
+    if isinstance(method, str) and method in ("minimal_distortion_principle", "minimal-distortion-principle", "MDP"):
+        X = st["X"]
+        Y = st["Y"] if st["W"] is None else separate(X, st["W"])
+        st["Y"] = minimal_distortion_principle(Y, X, reference_id)
+        if st["W"] is not None:
+            Xi, Yi = X.transpose(1, 0, 2), st["Y"].transpose(1, 0, 2)
+            XH = np.conj(Xi.transpose(0, 2, 1))
+            st["W"] = Yi @ XH @ np.linalg.inv(Xi @ XH)
+            st["Y"] = separate(X, st["W"])
+        return
     if st["W"] is None:
         st["Y"] = projection_back(st["Y"], reference=st["X"], reference_id=reference_id)
     else:
@@ -151,7 +162,7 @@ def run(X, T, V, n_iter, W=None, p=2, floor=spatial.max_flooring, spatial_algori
         if snapshots:
             snaps.append({k: (None if v is None else v.copy()) for k, v in st.items() if k != "X"})
     if scale_restoration:
-        restore_scale(st, reference_id)
+        restore_scale(st, reference_id, scale_restoration)
     elif st["W"] is not None:
         st["Y"] = separate(st["X"], st["W"])
     st["loss"] = loss

@@ -22,3 +22,14 @@ def projection_back(data_or_filter, reference=None, reference_id=0):
         return (Y * scale[..., np.newaxis]).swapaxes(-3, -2)  # (N_ch, N_src, I, J)
     scale = scale[..., reference_id, :]
     return (Y * scale[..., np.newaxis]).swapaxes(-3, -2)
+
+
+def minimal_distortion_principle(estimated, reference, reference_id=0):
+    """z = sum_j y conj(x_ref) / sum_j |y|^2; output = conj(z) y
+    (ssspy/algorithm/minimal_distortion_principle.py:31-43)."""
+    Y, Xc = estimated, np.conj(reference)
+    if reference_id is None:
+        num = np.sum(Y * Xc[:, np.newaxis, :, :], axis=-1, keepdims=True)
+    else:
+        num = np.sum(Y * Xc[reference_id], axis=-1, keepdims=True)
+    return np.conj(num / np.sum(np.abs(Y) ** 2, axis=-1, keepdims=True)) * Y

@@ -55,6 +55,8 @@ SIGNATURES = {
     "ssb_compute_loss": [_vp, _vp, _vp],
     "ssb_restore_scale": [_vp, _vp],
     "ssb_plan_separate": [_vp, _vp],
+    "ssb_restore_scale_mdp": [_vp, _vp],
+    "ssb_minimal_distortion_principle": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "ssb_separate": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "ssb_weighted_covariance": [_vp, _vp, _ll, _ll, _ll, _i32p, _i, _vp, _i, _i, _i, _i, _vp],
     "ssb_update_by_ip1": [_vp, _vp, _i, _i, _i, _f, _vp],

@@ -209,7 +209,9 @@ class ILRMABase(DeviceSeparatorMixin, IterativeMethodBase):
         self._plan_call("ssb_restore_scale")
 
     def apply_minimal_distortion_principle(self):
-        _not_on_device("scale_restoration='minimal_distortion_principle'")
+        """Y <- mdp(Y, X); W modes refit W = Y X^H (X X^H)^-1 (ssspy/bss/ilrma.py:567-579, iva.py:269-281)."""
+        assert self.scale_restoration, "Set self.scale_restoration=True."
+        self._plan_call("ssb_restore_scale_mdp")
 
 
 class GaussILRMA(ILRMABase):
@@ -321,6 +323,29 @@ class GaussILRMA(ILRMABase):
             raise NotImplementedError("Not support {}.".format(self.spatial_algorithm))
         self._set_flooring(flooring_fn)
         self._plan_call("ssb_update_spatial_model")
+
+    # the reference's per-algorithm entry points (ilrma.py:980-1005, :1440-1696) dispatch to the same kernels
+    def update_source_model_mm(self, flooring_fn="self"):
+        assert self.source_algorithm == "MM", "This separator was built with source_algorithm={}.".format(self.source_algorithm)
+        self.update_source_model(flooring_fn=flooring_fn)
+
+    def update_source_model_me(self, flooring_fn="self"):
+        if self.domain != 2:
+            raise ValueError("Domain parameter is expected 2, but given {}.".format(self.domain))
+        assert self.source_algorithm == "ME", "This separator was built with source_algorithm={}.".format(self.source_algorithm)
+        self.update_source_model(flooring_fn=flooring_fn)
+
+    def update_spatial_model_ip1(self, flooring_fn="self"):
+        assert self.spatial_algorithm in ["IP", "IP1"]
+        self.update_spatial_model(flooring_fn=flooring_fn)
+
+    def update_spatial_model_ip2(self, flooring_fn="self"):
+        assert self.spatial_algorithm == "IP2"
+        self.update_spatial_model(flooring_fn=flooring_fn)
+
+    def update_spatial_model_iss1(self, flooring_fn="self"):
+        assert self.spatial_algorithm in ["ISS", "ISS1"]
+        self.update_spatial_model(flooring_fn=flooring_fn)
 
     def compute_loss(self):
         """Negative log-likelihood (ilrma.py:1910-1967): a ``float`` for a single mixture, an array of

@@ -93,7 +93,9 @@ class IVABase(DeviceSeparatorMixin, IterativeMethodBase):
         self._plan_call("ssb_restore_scale")
 
     def apply_minimal_distortion_principle(self):
-        _not_on_device("scale_restoration='minimal_distortion_principle'")
+        """Y <- mdp(Y, X); W modes refit W = Y X^H (X X^H)^-1 (ssspy/bss/ilrma.py:567-579, iva.py:269-281)."""
+        assert self.scale_restoration, "Set self.scale_restoration=True."
+        self._plan_call("ssb_restore_scale_mdp")
 
 
 class AuxIVABase(IVABase):

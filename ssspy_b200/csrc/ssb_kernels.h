@@ -46,6 +46,7 @@ int ssbk_pb_w(const cf* W, cf* Wout, cf* scale_out, int n_mat, int N, int ref, c
 int ssbk_cross_solve(const cf* A, const cf* Bm, cf* S, int B, int N, int I, int J, cudaStream_t st);
 int ssbk_scale_rows(const cf* Y, const cf* S, cf* Yout, int B, int N, int I, int J, int ref, cudaStream_t st);
 int ssbk_logdet(const cf* W, double* out, int n_mat, int N, cudaStream_t st);
+int ssbk_mdp(const cf* Y, const cf* X, cf* Yout, int B, int N, int I, int J, int ref, cudaStream_t st);
 
 // ---- ssb_nmf.cu --------------------------------------------------------------------------------
 // MM/ME multiplicative updates from the power spectrogram P[B,N,I,J] (ssspy/bss/ilrma.py:1116-1126,

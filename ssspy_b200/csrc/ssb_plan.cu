@@ -589,7 +589,28 @@ extern "C" int ssb_restore_scale(ssb_plan* p, void* stream) {
   return ssbk_separate(p->X, p->W, p->Y, nullptr, B, N, I, J, st);
 }
 
+// restore_scale with the minimal distortion principle (ilrma.py:567-579, :1981-1989; iva.py:269-281,
+// :2206-2214): Y <- mdp(W X | Y, X); W modes also refit W = Y X^H (X X^H)^-1
+extern "C" int ssb_restore_scale_mdp(ssb_plan* p, void* stream) {
+  TRY(require_bound(p));
+  SSB_REQUIRE(!p->mnmf(), "FastGaussMNMF has no scale restoration");
+  const ssb_config& c = p->cfg;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = c.n_batch, N = c.n_sources, I = c.n_bins, J = c.n_frames;
+  if (!p->iss()) TRY(ssbk_separate(p->X, p->W, p->Y, nullptr, B, N, I, J, st));
+  TRY(ssbk_mdp(p->Y, p->X, p->Y, B, N, I, J, c.reference_id, st));
+  if (!p->iss()) TRY(ssbk_cross_solve(p->Y, p->X, p->W, B, N, I, J, st));
+  return 0;
+}
+
 // ---- standalone operators -----------------------------------------------------------------------
+extern "C" int ssb_minimal_distortion_principle(const void* Y, const void* X, void* Yout, int B, int N, int I, int J,
+                                                int reference_id, void* stream) {
+  SSB_REQUIRE(Y && X && Yout, "NULL argument");
+  if (B <= 0 || I <= 0 || J <= 0) return 0;
+  return ssbk_mdp((const cf*)Y, (const cf*)X, (cf*)Yout, B, N, I, J, reference_id, (cudaStream_t)stream);
+}
+
 extern "C" int ssb_separate(const void* X, const void* W, void* Y, int B, int N, int I, int J, void* stream) {
   SSB_REQUIRE(X && W && Y, "NULL argument");
   if (B <= 0 || I <= 0 || J <= 0) return 0;

@@ -801,6 +801,35 @@ __global__ void k_scale_rows(const cf* __restrict__ Y, const cf* __restrict__ S,
   }
 }
 
+// minimal distortion principle (ssspy/algorithm/minimal_distortion_principle.py:31-43): per (b,n,i) row
+//   z = sum_j y conj(x_ref) / sum_j |y|^2,  y <- conj(z) y.     One warp per row; ref < 0 is invalid.
+__global__ void __launch_bounds__(WPB * 32) k_mdp(const cf* __restrict__ Y, const cf* __restrict__ X,
+                                                  cf* __restrict__ Yout, int rows, int N, int I, int J, int ref) {
+  const int row = blockIdx.x * WPB + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int i = row % I;
+  const int b = row / (I * N);
+  const cf* y = Y + (size_t)row * J;
+  const cf* x = X + (((size_t)b * N + ref) * I + i) * J;
+  float nr = 0.f, ni = 0.f, de = 0.f;
+  for (int j = lane; j < J; j += 32) {
+    const cf a = y[j], c = x[j];
+    nr = fmaf(a.x, c.x, fmaf(a.y, c.y, nr));   // Re(y conj(x))
+    ni = fmaf(a.y, c.x, fmaf(-a.x, c.y, ni));  // Im
+    de = fmaf(a.x, a.x, fmaf(a.y, a.y, de));
+  }
+  nr = warp_sum(nr);
+  ni = warp_sum(ni);
+  de = warp_sum(de);
+  const float zr = nr / de, zi = ni / de;  // z; the scale applied is conj(z)
+  cf* o = Yout + (size_t)row * J;
+  for (int j = lane; j < J; j += 32) {
+    const cf a = y[j];
+    o[j] = make_float2(zr * a.x + zi * a.y, zr * a.y - zi * a.x);
+  }
+}
+
 // log|det W| per matrix (np.linalg.slogdet call sites ilrma.py:534, iva.py:234); one warp per matrix.
 template <int N>
 __global__ void __launch_bounds__(WPB * 32) k_logdet(const cf* __restrict__ W, double* __restrict__ out,
@@ -905,6 +934,13 @@ int ssbk_scale_rows(const cf* Y, const cf* S, cf* Yout, int B, int N, int I, int
   SSB_REQUIRE(ref >= 0 && ref < N, "projection_back: reference_id=%d out of range for N=%d", ref, N);
   k_scale_rows<<<B * N * I, 128, 0, st>>>(Y, S, Yout, N, I, J, ref);
   return ssb_check_launch("scale_rows", st);
+}
+
+int ssbk_mdp(const cf* Y, const cf* X, cf* Yout, int B, int N, int I, int J, int ref, cudaStream_t st) {
+  SSB_REQUIRE(ref >= 0 && ref < N, "minimal_distortion_principle: reference_id=%d out of range for N=%d", ref, N);
+  const int rows = B * N * I;
+  k_mdp<<<blocks_for(rows, WPB), WPB * 32, 0, st>>>(Y, X, Yout, rows, N, I, J, ref);
+  return ssb_check_launch("minimal_distortion_principle", st);
 }
 
 int ssbk_logdet(const cf* W, double* out, int n_mat, int N, cudaStream_t st) {

@@ -196,9 +196,26 @@ def linalg_cases():
     print("linalg done")
 
 
+def mdp_cases():
+    """minimal_distortion_principle standalone + as scale_restoration of GaussILRMA / AuxLaplaceIVA."""
+    from ssspy.algorithm import minimal_distortion_principle
+    out = {}
+    X = make_mixture(3, 9, 14, seed=5)
+    Y = make_mixture(3, 9, 14, seed=6)
+    out["X"], out["Y"] = X, Y
+    out["mdp_ref0"] = minimal_distortion_principle(Y, reference=X, reference_id=0)
+    out["mdp_ref2"] = minimal_distortion_principle(Y, reference=X, reference_id=2)
+    out["mdp_refnone"] = minimal_distortion_principle(Y, reference=X, reference_id=None)
+    np.savez_compressed(os.path.join(HERE, "mdp.npz"), **out)
+    ilrma_case("ilrma_ip1_mdp", 3, 17, 23, 4, 5, scale_restoration="minimal_distortion_principle", reference_id=1, seed=20)
+    ilrma_case("ilrma_iss1_mdp", 3, 17, 23, 4, 5, spatial="ISS", scale_restoration="MDP", seed=21)
+    print("mdp done")
+
+
 def main():
     linalg_cases()
     kernel_cases()
+    mdp_cases()
     # GaussILRMA: spatial x source x domain x normalisation x flooring grid (regression-test pattern,
     # tests/regression/bss/test_ilrma.py:48-62: inject basis/activation, fixed n_iter, compare).
     ilrma_case("ilrma_ip1_mm_n2", 2, 33, 40, 4, 10)

@@ -35,3 +35,9 @@ def phase_align_rows(W, Wref):
 def norm_arg(s):
     s = str(s)
     return {"True": True, "False": False}.get(s, s)
+
+
+def sr_arg(v):
+    """scale_restoration stored in a fixture: bool or keyword string."""
+    v = np.asarray(v)
+    return bool(v) if v.dtype == bool else str(v)

@@ -10,7 +10,7 @@ import itertools
 import numpy as np
 import pytest
 
-from helpers import FLOORS, golden_cases, load, norm_arg, phase_align_rows, relerr
+from helpers import FLOORS, golden_cases, load, norm_arg, phase_align_rows, relerr, sr_arg
 
 pytestmark = pytest.mark.gpu
 
@@ -57,13 +57,13 @@ def test_gauss_ilrma_matches_reference(name):
     m = GaussILRMA(n_basis=g["T0"].shape[-1], spatial_algorithm=spatial, source_algorithm=str(g["source"]),
                    domain=float(g["domain"]), flooring_fn=_floor_fn(str(g["flooring"])),
                    pair_selector=_pair_selector(g["pairs"]) if spatial == "IP2" else None,
-                   normalization=norm_arg(g["normalization"]), scale_restoration=bool(g["scale_restoration"]),
+                   normalization=norm_arg(g["normalization"]), scale_restoration=sr_arg(g["scale_restoration"]),
                    record_loss=True, reference_id=ref_id, rng=np.random.default_rng(0))
     Y = m(g["X"], n_iter=int(g["n_iter"]), **kwargs)
     assert Y.shape == g["Y"].shape and Y.dtype == np.complex128
     assert type(m.loss[-1]) is float and len(m.loss) == int(g["n_iter"]) + 1
     assert_loss_close(m.loss, g["loss"])
-    if bool(g["scale_restoration"]) or spatial != "IP2":
+    if sr_arg(g["scale_restoration"]) or spatial != "IP2":
         assert relerr(Y, g["Y"]) < TOL_Y
     else:
         assert relerr(np.abs(Y), np.abs(g["Y"])) < TOL_Y
@@ -87,7 +87,7 @@ def test_aux_iva_matches_reference(name):
     kwargs = {"demix_filter": g["W0"]} if "W0" in g else {}
     m = cls(spatial_algorithm=spatial, flooring_fn=_floor_fn(str(g["flooring"])),
             pair_selector=_pair_selector(g["pairs"]) if spatial == "IP2" else None,
-            scale_restoration=bool(g["scale_restoration"]), record_loss=True, reference_id=int(g["reference_id"]))
+            scale_restoration=sr_arg(g["scale_restoration"]), record_loss=True, reference_id=int(g["reference_id"]))
     Y = m(g["X"], n_iter=int(g["n_iter"]), **kwargs)
     assert Y.shape == g["Y"].shape
     assert_loss_close(m.loss, g["loss"])
@@ -457,3 +457,12 @@ def test_fast_gauss_mnmf_batched_vs_oracle_and_rng(alg):
         b2.normalize()
     assert relerr(b2.basis, a.basis) < 1e-5 and relerr(b2.spatial, a.spatial) < 1e-5
     assert abs(b2.compute_loss() - a.loss[-1]) <= 1e-5 * abs(a.loss[-1])
+
+
+def test_minimal_distortion_principle_matches_reference():
+    from ssspy_b200.algorithm import minimal_distortion_principle
+    g = load("mdp")
+    for ref, key in ((0, "ref0"), (2, "ref2"), (None, "refnone")):
+        out = minimal_distortion_principle(g["Y"], reference=g["X"], reference_id=ref)
+        assert out.shape == g["mdp_" + key].shape
+        assert relerr(out, g["mdp_" + key]) < 1e-5

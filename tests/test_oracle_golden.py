@@ -9,7 +9,7 @@ from oracle import linalg as olinalg
 from oracle import spatial as ospatial
 from oracle.projection_back import projection_back
 
-from helpers import FLOORS, golden_cases, load, norm_arg, phase_align_rows, relerr
+from helpers import FLOORS, golden_cases, load, norm_arg, phase_align_rows, relerr, sr_arg
 
 TOL = 1e-9
 
@@ -22,7 +22,7 @@ def test_ilrma_oracle_matches_reference(name):
                     floor=FLOORS[str(g["flooring"])], spatial_algorithm=str(g["spatial"]),
                     source_algorithm=str(g["source"]), normalization=norm_arg(g["normalization"]),
                     pairs=[tuple(p) for p in g["pairs"]], reference_id=ref_id,
-                    scale_restoration=bool(g["scale_restoration"]), snapshots=True)
+                    scale_restoration=sr_arg(g["scale_restoration"]), snapshots=True)
     assert relerr(st["Y"], g["Y"]) < TOL
     assert relerr(st["T"], g["T"]) < TOL
     assert relerr(st["V"], g["V"]) < TOL
@@ -43,7 +43,7 @@ def test_iva_oracle_matches_reference(name):
     st = oiva.run(g["X"], int(g["n_iter"]), W=g.get("W0"), floor=FLOORS[str(g["flooring"])],
                   spatial_algorithm=str(g["spatial"]), model=str(g["model"]),
                   pairs=[tuple(p) for p in g["pairs"]], reference_id=int(g["reference_id"]),
-                  scale_restoration=bool(g["scale_restoration"]))
+                  scale_restoration=sr_arg(g["scale_restoration"]))
     assert relerr(st["Y"], g["Y"]) < TOL
     np.testing.assert_allclose(st["loss"], g["loss"], rtol=1e-10, atol=1e-9)
     if "W" in g:
@@ -130,3 +130,10 @@ def test_fast_gauss_mnmf_oracle_matches_reference(name):
         Q = phase_align_rows(Q, g["Q"])
     assert relerr(Q, g["Q"]) < TOL
     assert relerr(st["Y"], g["Y"]) < 1e-8
+
+
+def test_minimal_distortion_principle_oracle():
+    from oracle.projection_back import minimal_distortion_principle
+    g = load("mdp")
+    for ref, key in ((0, "ref0"), (2, "ref2"), (None, "refnone")):
+        assert relerr(minimal_distortion_principle(g["Y"], g["X"], ref), g["mdp_" + key]) < 1e-12
