@@ -43,6 +43,11 @@ enum {
                                   `variance` slot the spatial property D[B,I,N,N] f32 (mnmf.py:594-596);
                                   `spatial` selects the diagonaliser algorithm IP1 / IP2 (mnmf.py:1430-1447);
                                   ssb_plan_separate is the multichannel Wiener filter (mnmf.py:1174-1217) */
+  ,
+  SSB_MODEL_ILRMA_T = 4,  /* ssspy/bss/ilrma.py:1992 TILRMA: Student-t source model, model_param = dof nu > 0
+                             (MM and ME source updates, IP1 / IP2 / ISS1) */
+  SSB_MODEL_ILRMA_GGD = 5 /* ssspy/bss/ilrma.py:3337 GGDILRMA: generalised Gaussian, model_param = beta in (0, 2)
+                             (MM only, IP1 / IP2 / ISS1) */
 };
 /* spatial_algorithm (ssspy/bss/ilrma.py:27, ssspy/bss/iva.py:44) */
 enum { SSB_SPATIAL_IP1 = 0, SSB_SPATIAL_IP2 = 1, SSB_SPATIAL_ISS1 = 2 };
@@ -77,6 +82,8 @@ typedef struct ssb_config {
                                        NumPy indexing does, tests/package/bss/test_update_spatial_model.py:19-24) */
   int32_t fast_path; /* 1: use the fused sm_100a kernels where the configuration allows (default),
                         0: always the modular kernels */
+  float model_param; /* TILRMA: degree of freedom nu (ilrma.py:2160); GGDILRMA: shape beta (ilrma.py:3496);
+                        ignored by the other models */
 } ssb_config;
 
 typedef struct ssb_plan ssb_plan;

@@ -35,33 +35,60 @@ def _Y(st):
     return st["Y"] if st["W"] is None else separate(st["X"], st["W"])
 
 
-def update_basis(st, p=2, floor=spatial.max_flooring, source_algorithm="MM"):
-    """T <- floor(T (sum_j V P/R^a / sum_j V/R)^b), a=(p+2)/p, b=p/(p+2) for MM
-    (ssspy/bss/ilrma.py:1116-1126); ME: a=2, b=1, p==2 (:1311-1323)."""
+def _source_weights(P, R, p, source_algorithm, dist):
+    """Elementwise factors of the multiplicative update: num = sum (.) A, den = sum (.) / R, exponent b.
+    Gauss MM: A = P/R^((p+2)/p), b = p/(p+2) (ilrma.py:1116-1126); Gauss ME: A = P/R^2, b = 1 (:1311-1323).
+    Student-t (dof nu): R~ = nu/(nu+2) R^(2/p) + 2/(nu+2) P, A = P/(R~ R), b = p/(p+2) (MM, :2620-2640) or 1
+    (ME, p = 2, :2868-2886).  GGD (beta): A = (beta/2) |y|^beta / R^((beta+p)/p), b = p/(beta+p) (:3700-3720)."""
+    kind, prm = dist
+    if kind == "gauss":
+        return (P / R ** ((p + 2) / p), p / (p + 2)) if source_algorithm == "MM" else (P / R ** 2, 1.0)
+    if kind == "t":
+        nn = prm / (prm + 2)
+        Rt = nn * R ** (2 / p) + (1 - nn) * P
+        return P / (Rt * R), (p / (p + 2) if source_algorithm == "MM" else 1.0)
+    if kind == "ggd":
+        return prm / 2 * P ** (prm / 2) / R ** ((prm + p) / p), p / (prm + p)
+    raise ValueError(kind)
+
+
+def update_basis(st, p=2, floor=spatial.max_flooring, source_algorithm="MM", dist=("gauss", None)):
+    """T <- floor(T (sum_j V A / sum_j V/R)^b)."""
     P = np.abs(_Y(st)) ** 2
     T, V = st["T"], st["V"]
     R = T @ V
-    a, b = ((p + 2) / p, p / (p + 2)) if source_algorithm == "MM" else (2.0, 1.0)
-    num = np.einsum("nkj,nij->nik", V, P / R ** a)
+    A, b = _source_weights(P, R, p, source_algorithm, dist)
+    num = np.einsum("nkj,nij->nik", V, A)
     den = np.einsum("nkj,nij->nik", V, 1 / R)
     st["T"] = floor(((num / den) ** b) * T)
 
 
-def update_activation(st, p=2, floor=spatial.max_flooring, source_algorithm="MM"):
+def update_activation(st, p=2, floor=spatial.max_flooring, source_algorithm="MM", dist=("gauss", None)):
     """Same with the new T, reduced over bins (ssspy/bss/ilrma.py:1192-1202; ME :1387-1399)."""
     P = np.abs(_Y(st)) ** 2
     T, V = st["T"], st["V"]
     R = T @ V
-    a, b = ((p + 2) / p, p / (p + 2)) if source_algorithm == "MM" else (2.0, 1.0)
-    num = np.einsum("nik,nij->nkj", T, P / R ** a)
+    A, b = _source_weights(P, R, p, source_algorithm, dist)
+    num = np.einsum("nik,nij->nkj", T, A)
     den = np.einsum("nik,nij->nkj", T, 1 / R)
     st["V"] = floor(((num / den) ** b) * V)
 
 
-def update_spatial(st, p=2, floor=spatial.max_flooring, spatial_algorithm="IP", pairs=None):
+def update_spatial(st, p=2, floor=spatial.max_flooring, spatial_algorithm="IP", pairs=None, dist=("gauss", None)):
     """phi = 1/(T V)^(2/p) (no floor), then IP1 / IP2 on W or ISS1 on Y
-    (ssspy/bss/ilrma.py:1494-1507, :1618-1633, :1690-1696)."""
-    phi = 1 / (st["T"] @ st["V"]) ** (2 / p)
+    (ssspy/bss/ilrma.py:1494-1507, :1618-1633, :1690-1696).  Student-t: phi = 1/R~ (ilrma.py:2920-2934);
+    GGD: phi = 1/((2/beta) floor(|y|^(2-beta)) R^(beta/p)) (:3992-4010)."""
+    R = st["T"] @ st["V"]
+    kind, prm = dist
+    if kind == "gauss":
+        phi = 1 / R ** (2 / p)
+    else:
+        P = np.abs(_Y(st)) ** 2
+        if kind == "t":
+            nn = prm / (prm + 2)
+            phi = 1 / (nn * R ** (2 / p) + (1 - nn) * P)
+        else:
+            phi = 1 / (2 / prm * floor(P ** ((2 - prm) / 2)) * R ** (prm / p))
     if spatial_algorithm in ("IP", "IP1"):
         st["W"] = spatial.update_by_ip1(st["W"], spatial.weighted_covariance(st["X"], phi), floor)
     elif spatial_algorithm == "IP2":
@@ -101,16 +128,16 @@ def normalize(st, p=2, floor=spatial.max_flooring, normalization=True, reference
 
 
 def update_once(st, p=2, floor=spatial.max_flooring, spatial_algorithm="IP", source_algorithm="MM",
-                normalization=True, pairs=None, reference_id=0):
+                normalization=True, pairs=None, reference_id=0, dist=("gauss", None)):
     """ssspy/bss/ilrma.py:900-922."""
-    update_basis(st, p, floor, source_algorithm)
-    update_activation(st, p, floor, source_algorithm)
-    update_spatial(st, p, floor, spatial_algorithm, pairs)
+    update_basis(st, p, floor, source_algorithm, dist)
+    update_activation(st, p, floor, source_algorithm, dist)
+    update_spatial(st, p, floor, spatial_algorithm, pairs, dist)
     if normalization:
         normalize(st, p, floor, normalization, reference_id)
 
 
-def compute_loss(st, p=2):
+def compute_loss(st, p=2, dist=("gauss", None)):
     """sum_i( sum_n mean_j(P/R^(2/p) + (2/p) log TV) - 2 log|det W_i| )
     (ssspy/bss/ilrma.py:1936-1967); W-free form recovers W = Y X^H (X X^H)^-1 (:1939-1944)."""
     if st["W"] is None:
@@ -122,7 +149,13 @@ def compute_loss(st, p=2):
         W = st["W"]
         Y = separate(st["X"], W)
     TV = st["T"] @ st["V"]
-    loss = np.abs(Y) ** 2 / TV ** (2 / p) + (2 / p) * np.log(TV)
+    kind, prm = dist
+    if kind == "gauss":
+        loss = np.abs(Y) ** 2 / TV ** (2 / p) + (2 / p) * np.log(TV)
+    elif kind == "t":  # ilrma.py:3265-3280
+        loss = (1 + prm / 2) * np.log(1 + 2 / prm * np.abs(Y) ** 2 / TV ** (2 / p)) + (2 / p) * np.log(TV)
+    else:  # ilrma.py:4340-4355
+        loss = np.abs(Y) ** prm / TV ** (prm / p) + (2 / p) * np.log(TV)
     _, logdet = np.linalg.slogdet(W)
     return float((np.sum(loss.mean(axis=-1), axis=0) - 2 * logdet).sum())
 
@@ -149,16 +182,16 @@ def restore_scale(st, reference_id=0, method=True):
 
 def run(X, T, V, n_iter, W=None, p=2, floor=spatial.max_flooring, spatial_algorithm="IP",
         source_algorithm="MM", normalization=True, pairs=None, reference_id=0,
-        scale_restoration=True, record_loss=True, snapshots=False):
+        scale_restoration=True, record_loss=True, snapshots=False, dist=("gauss", None)):
     """GaussILRMA.__call__ (ssspy/bss/ilrma.py:820-855 + ssspy/bss/base.py:48-77)."""
     st = init_state(X, T, V, W, spatial_algorithm)
     loss, snaps = [], []
     if record_loss:
-        loss.append(compute_loss(st, p))
+        loss.append(compute_loss(st, p, dist))
     for _ in range(n_iter):
-        update_once(st, p, floor, spatial_algorithm, source_algorithm, normalization, pairs, reference_id)
+        update_once(st, p, floor, spatial_algorithm, source_algorithm, normalization, pairs, reference_id, dist)
         if record_loss:
-            loss.append(compute_loss(st, p))
+            loss.append(compute_loss(st, p, dist))
         if snapshots:
             snaps.append({k: (None if v is None else v.copy()) for k, v in st.items() if k != "X"})
     if scale_restoration:

@@ -14,6 +14,7 @@ SSB_MAX_BASIS = 64
 SSB_MAX_PAIRS = 64
 
 MODEL_ILRMA_GAUSS, MODEL_IVA_LAPLACE, MODEL_IVA_GAUSS, MODEL_FASTMNMF_GAUSS = 0, 1, 2, 3
+MODEL_ILRMA_T, MODEL_ILRMA_GGD = 4, 5
 SPATIAL_IP1, SPATIAL_IP2, SPATIAL_ISS1 = 0, 1, 2
 SOURCE_MM, SOURCE_ME = 0, 1
 FLOOR_MAX, FLOOR_ADD, FLOOR_NONE = 0, 1, 2
@@ -28,6 +29,7 @@ class SsbConfig(ctypes.Structure):
         ("flooring", ctypes.c_int32), ("eps", ctypes.c_float), ("normalization", ctypes.c_int32),
         ("reference_id", ctypes.c_int32), ("n_pairs", ctypes.c_int32),
         ("pairs", ctypes.c_int32 * (2 * SSB_MAX_PAIRS)), ("fast_path", ctypes.c_int32),
+        ("model_param", ctypes.c_float),
     ]
 
 

@@ -1,4 +1,4 @@
 from . import ilrma, iva, mnmf  # noqa: F401
-from .ilrma import GaussILRMA  # noqa: F401
+from .ilrma import GGDILRMA, TILRMA, GaussILRMA  # noqa: F401
 from .iva import AuxGaussIVA, AuxIVA, AuxLaplaceIVA  # noqa: F401
 from .mnmf import FastGaussMNMF  # noqa: F401

@@ -1,5 +1,5 @@
-"""GaussILRMA on the device (host mirror of ssspy/bss/ilrma.py: ILRMABase :32-579, GaussILRMA
-:582-1989).  Same constructor, ``__call__``, ``update_once`` / ``update_source_model`` /
+"""GaussILRMA, TILRMA and GGDILRMA on the device (host mirror of ssspy/bss/ilrma.py: ILRMABase :32-579,
+GaussILRMA :582-1989, TILRMA :1992-3334, GGDILRMA :3337-4410).  Same constructor, ``__call__``, ``update_once`` / ``update_source_model`` /
 ``update_spatial_model`` / ``normalize`` / ``compute_loss`` / ``restore_scale`` /
 ``apply_projection_back`` and attribute names; all arithmetic runs in libssb.so's CUDA kernels.
 
@@ -21,7 +21,7 @@ from ..utils.select_pair import sequential_pair_selector, wrap_pairs
 from ._engine import DeviceSeparatorMixin
 from .base import IterativeMethodBase
 
-__all__ = ["GaussILRMA"]
+__all__ = ["GaussILRMA", "TILRMA", "GGDILRMA"]
 
 spatial_algorithms = ["IP", "IP1", "IP2", "ISS", "ISS1", "ISS2", "IPA"]
 source_algorithms = ["MM", "ME"]
@@ -129,7 +129,8 @@ class ILRMABase(DeviceSeparatorMixin, IterativeMethodBase):
     def _plan_config(self):
         B, N, I, J = self._dims()
         cfg = _lib.SsbConfig()
-        cfg.model = _lib.MODEL_ILRMA_GAUSS
+        cfg.model = self._model
+        cfg.model_param = self._model_param()
         cfg.spatial = _SPATIAL_ENUM[self.spatial_algorithm]
         cfg.source = _lib.SOURCE_MM if self.source_algorithm == "MM" else _lib.SOURCE_ME
         cfg.n_batch, cfg.n_sources, cfg.n_bins, cfg.n_frames, cfg.n_basis = B, N, I, J, self.n_basis
@@ -214,20 +215,17 @@ class ILRMABase(DeviceSeparatorMixin, IterativeMethodBase):
         self._plan_call("ssb_restore_scale_mdp")
 
 
-class GaussILRMA(ILRMABase):
-    """ssspy/bss/ilrma.py:582-1989 (signature :752-772)."""
+class _DeviceILRMA(ILRMABase):
+    """Everything GaussILRMA (ilrma.py:582), TILRMA (:1992) and GGDILRMA (:3337) share on the device: the three
+    differ only in the elementwise source-model factors, which libssb.so selects from ``cfg.model`` /
+    ``cfg.model_param``."""
 
-    def __init__(self, n_basis, spatial_algorithm="IP", source_algorithm="MM", domain=2, partitioning=False,
-                 flooring_fn=functools.partial(max_flooring, eps=EPS), pair_selector=None, callbacks=None,
-                 normalization=True, scale_restoration=True, record_loss=True, reference_id=0, rng=None, **kwargs):
-        super().__init__(n_basis=n_basis, partitioning=partitioning, flooring_fn=flooring_fn, callbacks=callbacks,
-                         scale_restoration=scale_restoration, record_loss=record_loss, reference_id=reference_id,
-                         rng=rng)
-        assert spatial_algorithm in spatial_algorithms, "Not support {}.".format(spatial_algorithm)
-        assert source_algorithm in source_algorithms, "Not support {}.".format(source_algorithm)
-        assert 0 < domain <= 2, "domain parameter should be chosen from [0, 2]."
-        if source_algorithm == "ME":
-            assert domain == 2, "domain parameter should be 2 when you specify ME algorithm."
+    _model = _lib.MODEL_ILRMA_GAUSS
+
+    def _model_param(self):
+        return 0.0
+
+    def _init_algorithms(self, spatial_algorithm, source_algorithm, domain, partitioning, normalization, pair_selector):
         if spatial_algorithm not in _SPATIAL_ENUM:
             _not_on_device("spatial_algorithm={!r}".format(spatial_algorithm))
         if partitioning:
@@ -241,8 +239,14 @@ class GaussILRMA(ILRMABase):
                 self.pair_selector = sequential_pair_selector
         else:
             self.pair_selector = pair_selector
-        invalid_keys = set(kwargs)  # IPA-only keywords are the only valid extras (ilrma.py:802-812)
-        assert invalid_keys == set(), "Invalid keywords {} are given.".format(invalid_keys)
+
+    def _repr_fields(self, name, extra):
+        s = name + "(n_basis={n_basis}" + extra + ", spatial_algorithm={spatial_algorithm}"
+        s += ", source_algorithm={source_algorithm}, domain={domain}, partitioning={partitioning}"
+        s += ", normalization={normalization}, scale_restoration={scale_restoration}, record_loss={record_loss}"
+        if self.scale_restoration:
+            s += ", reference_id={reference_id}"
+        return (s + ")").format(**self.__dict__)
 
     def __call__(self, input, n_iter=100, initial_call=True, **kwargs):
         """Separate ``input`` of shape (n_channels, n_bins, n_frames) [or (batch, ...)] (ilrma.py:820-855)."""
@@ -270,25 +274,17 @@ class GaussILRMA(ILRMABase):
         update / loss / scale-restoration methods, projection-back (or no) scale restoration."""
         cls = type(self)
         sr = self.scale_restoration
-        return (self.callbacks is None and cls.update_once is GaussILRMA.update_once
-                and cls.compute_loss is GaussILRMA.compute_loss and self._stock_update_methods()
+        return (self.callbacks is None and cls.update_once is _DeviceILRMA.update_once
+                and cls.compute_loss is _DeviceILRMA.compute_loss and self._stock_update_methods()
                 and cls.restore_scale is ILRMABase.restore_scale
                 and cls.apply_projection_back is ILRMABase.apply_projection_back
                 and (type(sr) is bool or sr in PROJECTION_BACK_KEYWORDS))
 
     def _stock_update_methods(self):
         cls = type(self)
-        return (cls.update_source_model is GaussILRMA.update_source_model
-                and cls.update_spatial_model is GaussILRMA.update_spatial_model
+        return (cls.update_source_model is _DeviceILRMA.update_source_model
+                and cls.update_spatial_model is _DeviceILRMA.update_spatial_model
                 and cls.normalize is ILRMABase.normalize)
-
-    def __repr__(self):
-        s = "GaussILRMA(n_basis={n_basis}, spatial_algorithm={spatial_algorithm}"
-        s += ", source_algorithm={source_algorithm}, domain={domain}, partitioning={partitioning}"
-        s += ", normalization={normalization}, scale_restoration={scale_restoration}, record_loss={record_loss}"
-        if self.scale_restoration:
-            s += ", reference_id={reference_id}"
-        return (s + ")").format(**self.__dict__)
 
     def _reset(self, flooring_fn="self", **kwargs):
         flooring_fn = choose_flooring_fn(flooring_fn, method=self)
@@ -351,3 +347,84 @@ class GaussILRMA(ILRMABase):
         """Negative log-likelihood (ilrma.py:1910-1967): a ``float`` for a single mixture, an array of
         shape (batch,) for batched input."""
         return self._loss_from_device()
+
+
+class GaussILRMA(_DeviceILRMA):
+    """ssspy/bss/ilrma.py:582-1989 (signature :752-772)."""
+
+    def __init__(self, n_basis, spatial_algorithm="IP", source_algorithm="MM", domain=2, partitioning=False,
+                 flooring_fn=functools.partial(max_flooring, eps=EPS), pair_selector=None, callbacks=None,
+                 normalization=True, scale_restoration=True, record_loss=True, reference_id=0, rng=None, **kwargs):
+        super().__init__(n_basis=n_basis, partitioning=partitioning, flooring_fn=flooring_fn, callbacks=callbacks,
+                         scale_restoration=scale_restoration, record_loss=record_loss, reference_id=reference_id,
+                         rng=rng)
+        assert spatial_algorithm in spatial_algorithms, "Not support {}.".format(spatial_algorithm)
+        assert source_algorithm in source_algorithms, "Not support {}.".format(source_algorithm)
+        assert 0 < domain <= 2, "domain parameter should be chosen from [0, 2]."
+        if source_algorithm == "ME":
+            assert domain == 2, "domain parameter should be 2 when you specify ME algorithm."
+        self._init_algorithms(spatial_algorithm, source_algorithm, domain, partitioning, normalization, pair_selector)
+        invalid_keys = set(kwargs)  # IPA-only keywords are the only valid extras (ilrma.py:802-812)
+        assert invalid_keys == set(), "Invalid keywords {} are given.".format(invalid_keys)
+
+    def __repr__(self):
+        return self._repr_fields("GaussILRMA", "")
+
+
+class TILRMA(_DeviceILRMA):
+    """Student-t ILRMA, ssspy/bss/ilrma.py:1992-3334 (signature :2145-2165): ``dof`` is the degree of freedom nu;
+    nu -> inf recovers GaussILRMA.  MM and ME source updates (ilrma.py:2384-2827), IP1 / IP2 / ISS1 with the weight
+    1 / (nu/(nu+2) (TV)^(2/p) + 2/(nu+2) |y|^2) (ilrma.py:2863-3145), loss :3252-3312."""
+
+    _model = _lib.MODEL_ILRMA_T
+
+    def __init__(self, n_basis, dof, spatial_algorithm="IP", source_algorithm="MM", domain=2, partitioning=False,
+                 flooring_fn=functools.partial(max_flooring, eps=EPS), pair_selector=None, callbacks=None,
+                 normalization=True, scale_restoration=True, record_loss=True, reference_id=0, rng=None):
+        super().__init__(n_basis=n_basis, partitioning=partitioning, flooring_fn=flooring_fn, callbacks=callbacks,
+                         scale_restoration=scale_restoration, record_loss=record_loss, reference_id=reference_id,
+                         rng=rng)
+        assert spatial_algorithm in spatial_algorithms, "Not support {}.".format(spatial_algorithms)
+        assert source_algorithm in source_algorithms, "Not support {}.".format(source_algorithm)
+        assert 0 < domain <= 2, "domain parameter should be chosen from [0, 2]."
+        if spatial_algorithm == "IPA":
+            raise ValueError("IPA is not supported for t-ILRMA.")
+        if source_algorithm == "ME":
+            assert domain == 2, "domain parameter should be 2 when you specify ME algorithm."
+        self.dof = dof
+        self._init_algorithms(spatial_algorithm, source_algorithm, domain, partitioning, normalization, pair_selector)
+
+    def _model_param(self):
+        return float(self.dof)
+
+    def __repr__(self):
+        return self._repr_fields("TILRMA", ", dof={dof}")
+
+
+class GGDILRMA(_DeviceILRMA):
+    """Generalised-Gaussian ILRMA, ssspy/bss/ilrma.py:3337-4410 (signature :3490-3510): ``beta`` in (0, 2) is the
+    shape parameter (beta -> 2 is the Gaussian case).  MM source updates only (ilrma.py:3698-3905), IP1 / IP2 / ISS1
+    with the weight 1 / ((2/beta) floor(|y|^(2-beta)) (TV)^(beta/p)) (ilrma.py:3941-4222), loss :4329-4388."""
+
+    _model = _lib.MODEL_ILRMA_GGD
+
+    def __init__(self, n_basis, beta, spatial_algorithm="IP", source_algorithm="MM", domain=2, partitioning=False,
+                 flooring_fn=functools.partial(max_flooring, eps=EPS), pair_selector=None, callbacks=None,
+                 normalization=True, scale_restoration=True, record_loss=True, reference_id=0, rng=None):
+        super().__init__(n_basis=n_basis, partitioning=partitioning, flooring_fn=flooring_fn, callbacks=callbacks,
+                         scale_restoration=scale_restoration, record_loss=record_loss, reference_id=reference_id,
+                         rng=rng)
+        assert 0 < beta < 2, "Shape parameter {} shoule be chosen from (0, 2).".format(beta)
+        assert spatial_algorithm in spatial_algorithms, "Not support {}.".format(spatial_algorithms)
+        assert source_algorithm == "MM", "Not support {}.".format(source_algorithm)
+        assert 0 < domain <= 2, "domain parameter should be chosen from [0, 2]."
+        if spatial_algorithm == "IPA":
+            raise ValueError("IPA is not supported for GGD-ILRMA.")
+        self.beta = beta
+        self._init_algorithms(spatial_algorithm, source_algorithm, domain, partitioning, normalization, pair_selector)
+
+    def _model_param(self):
+        return float(self.beta)
+
+    def __repr__(self):
+        return self._repr_fields("GGDILRMA", ", beta={beta}")

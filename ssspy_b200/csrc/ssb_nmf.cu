@@ -9,20 +9,46 @@ namespace {
 
 constexpr int WPB = 4;
 constexpr int ACT_NW = 8;
-enum { PM_MM2 = 0, PM_ME = 1, PM_GENERIC = 2 };
+// elementwise numerator factor A(P, R) of the multiplicative updates (the denominator factor is 1/R for all)
+//   PM_MM2     Gauss MM, p = 2 : P / R^2                      exponent 1/2
+//   PM_ME      Gauss ME (p = 2): P / R^2                      exponent 1
+//   PM_GENERIC Gauss MM, any p : P / R^((p+2)/p)              exponent p/(p+2)
+//   PM_T       Student-t       : P / (R~ R), R~ = c0 R^(2/p) + c1 P, c0 = nu/(nu+2), c1 = 2/(nu+2)
+//   PM_GGD     GGD             : (beta/2) P^(beta/2) / R^((beta+p)/p)      exponent p/(beta+p)
+enum { PM_MM2 = 0, PM_ME = 1, PM_GENERIC = 2, PM_T = 3, PM_GGD = 4 };
 
-__device__ __forceinline__ float upd_pow(float ratio, float bexp, int mode) {
-  if (mode == PM_MM2) return sqrtf(ratio);
-  if (mode == PM_ME) return ratio;
-  return powf(ratio, bexp);
+struct SrcParam {
+  int mode;
+  float aexp;  // PM_GENERIC: (p+2)/p;  PM_T: 2/p;  PM_GGD: (beta+p)/p
+  float bexp;  // exponent of the ratio
+  float c0, c1;  // PM_T: nu/(nu+2), 2/(nu+2);  PM_GGD: c0 = beta/2
+};
+
+__device__ __forceinline__ float upd_pow(float ratio, const SrcParam& sp) {
+  if (sp.bexp == 0.5f) return sqrtf(ratio);
+  if (sp.bexp == 1.0f) return ratio;
+  return powf(ratio, sp.bexp);
 }
+
+__device__ __forceinline__ float src_factor(float P, float R, float inv, const SrcParam& sp) {
+  switch (sp.mode) {
+    case PM_MM2:
+    case PM_ME: return P * inv * inv;
+    case PM_GENERIC: return P / powf(R, sp.aexp);
+    case PM_T: {
+      const float r2p = sp.aexp == 1.0f ? R : powf(R, sp.aexp);
+      return P * inv / fmaf(sp.c0, r2p, sp.c1 * P);
+    }
+    default: return sp.c0 * powf(P, sp.c0) / powf(R, sp.aexp);
+  }
+}
+
 
 // T <- floor(T * (sum_j V P / R^a / sum_j V / R)^b); one warp per (b,n,i) row, lanes over frames.
 template <int KP>
 __global__ void __launch_bounds__(WPB * 32) k_nmf_basis(const float* __restrict__ P, float* __restrict__ T,
                                                         const float* __restrict__ V, int rows, int I, int J,
-                                                        int K, float aexp, float bexp, int mode, int flooring,
-                                                        float eps) {
+                                                        int K, SrcParam sp, int flooring, float eps) {
   const int row = blockIdx.x * WPB + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -45,7 +71,7 @@ __global__ void __launch_bounds__(WPB * 32) k_nmf_basis(const float* __restrict_
     }
     const float inv = 1.0f / R;
     const float p_ = Pr[j];
-    const float A = (mode == PM_GENERIC) ? p_ / powf(R, aexp) : p_ * inv * inv;
+    const float A = src_factor(p_, R, inv, sp);
 #pragma unroll
     for (int k = 0; k < KP; ++k) {
       num[k] = fmaf(v[k], A, num[k]);
@@ -56,7 +82,7 @@ __global__ void __launch_bounds__(WPB * 32) k_nmf_basis(const float* __restrict_
   for (int k = 0; k < KP; ++k) {
     if (k < K) {
       float nu = warp_sum(num[k]), de = warp_sum(den[k]);
-      if ((k & 31) == lane) T[(size_t)row * K + k] = ssb_floor(upd_pow(nu / de, bexp, mode) * t[k], flooring, eps);
+      if ((k & 31) == lane) T[(size_t)row * K + k] = ssb_floor(upd_pow(nu / de, sp) * t[k], flooring, eps);
     }
   }
 }
@@ -66,8 +92,8 @@ __global__ void __launch_bounds__(WPB * 32) k_nmf_basis(const float* __restrict_
 template <int KP>
 __global__ void __launch_bounds__(ACT_NW * 32) k_nmf_activation(const float* __restrict__ P,
                                                                const float* __restrict__ T, float* __restrict__ V,
-                                                               int I, int J, int K, float aexp, float bexp,
-                                                               int mode, int flooring, float eps) {
+                                                               int I, int J, int K, SrcParam sp, int flooring,
+                                                               float eps) {
   __shared__ float s_acc[2 * KP][32];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int jt = blockIdx.x, bn = blockIdx.y;
@@ -91,7 +117,7 @@ __global__ void __launch_bounds__(ACT_NW * 32) k_nmf_activation(const float* __r
     if (!valid) R = 1.f;
     const float inv = 1.0f / R;
     const float p_ = valid ? P[((size_t)bn * I + i) * J + j] : 0.f;
-    const float A = (mode == PM_GENERIC) ? p_ / powf(R, aexp) : p_ * inv * inv;
+    const float A = src_factor(p_, R, inv, sp);
 #pragma unroll
     for (int k = 0; k < KP; ++k) {
       num[k] = fmaf(t[k], A, num[k]);
@@ -118,7 +144,7 @@ __global__ void __launch_bounds__(ACT_NW * 32) k_nmf_activation(const float* __r
     for (int k = 0; k < KP; ++k) {
       if (k < K) {
         float ratio = s_acc[k][lane] / s_acc[KP + k][lane];
-        V[((size_t)bn * K + k) * J + j] = ssb_floor(upd_pow(ratio, bexp, mode) * v[k], flooring, eps);
+        V[((size_t)bn * K + k) * J + j] = ssb_floor(upd_pow(ratio, sp) * v[k], flooring, eps);
       }
     }
   }
@@ -209,11 +235,12 @@ __global__ void __launch_bounds__(ACT_NW * 32) k_nmf_activation_ab(const float* 
   }
 }
 
-// phi = (T V)^(-2/p); one warp per row
+// phi = (T V)^(-2/p) (Gauss), 1/R~ (Student-t), 1/((2/beta) floor(P^((2-beta)/2)) R^(beta/p)) (GGD); one warp per
+// row.  P and phi may be the same buffer (each element is read then written by the same thread).
 template <int KP>
 __global__ void __launch_bounds__(WPB * 32) k_nmf_phi(const float* __restrict__ T, const float* __restrict__ V,
-                                                      float* __restrict__ phi, int rows, int I, int J, int K,
-                                                      float p) {
+                                                      const float* P, float* phi, int rows, int I, int J, int K,
+                                                      float p, int model, float prm, int flooring, float eps) {
   const int row = blockIdx.x * WPB + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -229,7 +256,19 @@ __global__ void __launch_bounds__(WPB * 32) k_nmf_phi(const float* __restrict__ 
 #pragma unroll
     for (int k = 0; k < KP; ++k)
       if (k < K) R = fmaf(t[k], Vb[(size_t)k * J + j], R);
-    phi[(size_t)row * J + j] = p2 ? 1.0f / R : powf(R, e);
+    float out;
+    if (model == SSB_MODEL_ILRMA_GAUSS) {
+      out = p2 ? 1.0f / R : powf(R, e);
+    } else {
+      const float pw = P[(size_t)row * J + j];
+      if (model == SSB_MODEL_ILRMA_T) {
+        const float c0 = prm / (prm + 2.0f);
+        out = 1.0f / fmaf(c0, p2 ? R : powf(R, -e), (1.0f - c0) * pw);
+      } else {
+        out = 1.0f / ((2.0f / prm) * ssb_floor(powf(pw, 0.5f * (2.0f - prm)), flooring, eps) * powf(R, prm / p));
+      }
+    }
+    phi[(size_t)row * J + j] = out;
   }
 }
 
@@ -237,7 +276,8 @@ __global__ void __launch_bounds__(WPB * 32) k_nmf_phi(const float* __restrict__ 
 template <int KP>
 __global__ void __launch_bounds__(WPB * 32) k_nmf_rowloss(const float* __restrict__ P, const float* __restrict__ T,
                                                           const float* __restrict__ V, double* __restrict__ rowloss,
-                                                          int rows, int I, int J, int K, float p) {
+                                                          int rows, int I, int J, int K, float p, int model,
+                                                          float prm) {
   const int row = blockIdx.x * WPB + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -255,7 +295,14 @@ __global__ void __launch_bounds__(WPB * 32) k_nmf_rowloss(const float* __restric
     for (int k = 0; k < KP; ++k)
       if (k < K) R = fmaf(t[k], Vb[(size_t)k * J + j], R);
     const float pw = P[(size_t)row * J + j];
-    const float term = p2 ? pw / R + logf(R) : pw / powf(R, e) + e * logf(R);
+    float term;
+    if (model == SSB_MODEL_ILRMA_GAUSS) {
+      term = p2 ? pw / R + logf(R) : pw / powf(R, e) + e * logf(R);
+    } else if (model == SSB_MODEL_ILRMA_T) {
+      term = (1.0f + 0.5f * prm) * log1pf((2.0f / prm) * pw / (p2 ? R : powf(R, e))) + e * logf(R);
+    } else {
+      term = powf(pw, 0.5f * prm) / powf(R, prm / p) + e * logf(R);
+    }
     acc += (double)term;
   }
   acc = warp_sum(acc);
@@ -367,29 +414,44 @@ __global__ void k_scale_basis(float* __restrict__ T, const cf* __restrict__ s, l
   }
 }
 
-int pmode(float p, int source) {
-  if (source == SSB_SOURCE_ME) return PM_ME;
-  return p == 2.0f ? PM_MM2 : PM_GENERIC;
+SrcParam src_param(float p, int source, int model, float prm) {
+  SrcParam sp{};
+  const bool me = source == SSB_SOURCE_ME;
+  if (model == SSB_MODEL_ILRMA_T) {
+    sp.mode = PM_T;
+    sp.aexp = 2.0f / p;
+    sp.bexp = me ? 1.0f : p / (p + 2.0f);
+    sp.c0 = prm / (prm + 2.0f);
+    sp.c1 = 2.0f / (prm + 2.0f);
+  } else if (model == SSB_MODEL_ILRMA_GGD) {
+    sp.mode = PM_GGD;
+    sp.aexp = (prm + p) / p;
+    sp.bexp = p / (prm + p);
+    sp.c0 = 0.5f * prm;
+  } else {
+    sp.mode = me ? PM_ME : (p == 2.0f ? PM_MM2 : PM_GENERIC);
+    sp.aexp = (p + 2.0f) / p;
+    sp.bexp = me ? 1.0f : p / (p + 2.0f);
+  }
+  return sp;
 }
 
 }  // namespace
 
 int ssbk_nmf_basis(const float* P, float* T, const float* V, int BN, int I, int J, int K, float p, int source,
-                   int flooring, float eps, cudaStream_t st) {
+                   int model, float prm, int flooring, float eps, cudaStream_t st) {
   const int rows = BN * I;
-  const int mode = pmode(p, source);
-  const float a = (p + 2.0f) / p, b = p / (p + 2.0f);
-  SSB_DISPATCH_K(K, k_nmf_basis<KP><<<blocks_for(rows, WPB), WPB * 32, 0, st>>>(P, T, V, rows, I, J, K, a, b, mode,
-                                                                                flooring, eps));
+  const SrcParam sp = src_param(p, source, model, prm);
+  SSB_DISPATCH_K(K, k_nmf_basis<KP><<<blocks_for(rows, WPB), WPB * 32, 0, st>>>(P, T, V, rows, I, J, K, sp, flooring,
+                                                                                eps));
   return ssb_check_launch("nmf_basis", st);
 }
 
 int ssbk_nmf_activation(const float* P, const float* T, float* V, int BN, int I, int J, int K, float p, int source,
-                        int flooring, float eps, cudaStream_t st) {
-  const int mode = pmode(p, source);
-  const float a = (p + 2.0f) / p, b = p / (p + 2.0f);
+                        int model, float prm, int flooring, float eps, cudaStream_t st) {
+  const SrcParam sp = src_param(p, source, model, prm);
   dim3 grid((J + 31) / 32, BN);
-  SSB_DISPATCH_K(K, k_nmf_activation<KP><<<grid, ACT_NW * 32, 0, st>>>(P, T, V, I, J, K, a, b, mode, flooring, eps));
+  SSB_DISPATCH_K(K, k_nmf_activation<KP><<<grid, ACT_NW * 32, 0, st>>>(P, T, V, I, J, K, sp, flooring, eps));
   return ssb_check_launch("nmf_activation", st);
 }
 
@@ -408,16 +470,19 @@ int ssbk_nmf_activation_ab(const float* A, const float* Bm, const float* T, floa
   return ssb_check_launch("nmf_activation_ab", st);
 }
 
-int ssbk_nmf_phi(const float* T, const float* V, float* phi, int BN, int I, int J, int K, float p, cudaStream_t st) {
+int ssbk_nmf_phi(const float* T, const float* V, const float* P, float* phi, int BN, int I, int J, int K, float p,
+                 int model, float prm, int flooring, float eps, cudaStream_t st) {
   const int rows = BN * I;
-  SSB_DISPATCH_K(K, k_nmf_phi<KP><<<blocks_for(rows, WPB), WPB * 32, 0, st>>>(T, V, phi, rows, I, J, K, p));
+  SSB_DISPATCH_K(K, k_nmf_phi<KP><<<blocks_for(rows, WPB), WPB * 32, 0, st>>>(T, V, P, phi, rows, I, J, K, p, model,
+                                                                              prm, flooring, eps));
   return ssb_check_launch("nmf_phi", st);
 }
 
 int ssbk_nmf_rowloss(const float* P, const float* T, const float* V, double* rowloss, int BN, int I, int J, int K,
-                     float p, cudaStream_t st) {
+                     float p, int model, float prm, cudaStream_t st) {
   const int rows = BN * I;
-  SSB_DISPATCH_K(K, k_nmf_rowloss<KP><<<blocks_for(rows, WPB), WPB * 32, 0, st>>>(P, T, V, rowloss, rows, I, J, K, p));
+  SSB_DISPATCH_K(K, k_nmf_rowloss<KP><<<blocks_for(rows, WPB), WPB * 32, 0, st>>>(P, T, V, rowloss, rows, I, J, K, p,
+                                                                                  model, prm));
   return ssb_check_launch("nmf_rowloss", st);
 }
 

@@ -136,7 +136,9 @@ struct ssb_plan {
   float* big3 = nullptr;    // [B,N,I,J] f32 Lambda = T V (FastGaussMNMF, tensor-core kernel)
   bool mnmf() const { return cfg.model == SSB_MODEL_FASTMNMF_GAUSS; }
   bool iss() const { return cfg.spatial == SSB_SPATIAL_ISS1 && !mnmf(); }
-  bool ilrma() const { return cfg.model == SSB_MODEL_ILRMA_GAUSS; }
+  bool ilrma() const {
+    return cfg.model == SSB_MODEL_ILRMA_GAUSS || cfg.model == SSB_MODEL_ILRMA_T || cfg.model == SSB_MODEL_ILRMA_GGD;
+  }
 };
 
 namespace {
@@ -178,7 +180,7 @@ size_t carve(ssb_plan* p, char* base) {
 
 int validate(const ssb_config* c) {
   SSB_REQUIRE(c != nullptr, "config is NULL");
-  SSB_REQUIRE(c->model >= 0 && c->model <= 3, "unknown model %d", c->model);
+  SSB_REQUIRE(c->model >= 0 && c->model <= 5, "unknown model %d", c->model);
   SSB_REQUIRE(c->spatial >= 0 && c->spatial <= 2, "Not support spatial algorithm id %d.", c->spatial);
   SSB_REQUIRE(c->source == SSB_SOURCE_MM || c->source == SSB_SOURCE_ME, "Not support source algorithm id %d.",
               c->source);
@@ -194,7 +196,12 @@ int validate(const ssb_config* c) {
     SSB_REQUIRE(c->normalization == SSB_NORM_NONE || c->normalization == SSB_NORM_POWER,
                 "Normalization %d is not implemented.", c->normalization);
   }
-  if (c->model == SSB_MODEL_ILRMA_GAUSS) {
+  if (c->model == SSB_MODEL_ILRMA_T) SSB_REQUIRE(c->model_param > 0.f, "dof must be positive (got %g)", c->model_param);
+  if (c->model == SSB_MODEL_ILRMA_GGD) {
+    SSB_REQUIRE(c->model_param > 0.f && c->model_param < 2.f, "Shape parameter 2 shoule be chosen from (0, 2).");
+    SSB_REQUIRE(c->source == SSB_SOURCE_MM, "Not support source algorithm id %d for GGDILRMA.", c->source);
+  }
+  if (c->model == SSB_MODEL_ILRMA_GAUSS || c->model == SSB_MODEL_ILRMA_T || c->model == SSB_MODEL_ILRMA_GGD) {
     SSB_REQUIRE(c->n_basis >= 1 && c->n_basis <= SSB_MAX_BASIS, "n_basis=%d unsupported (1..%d)", c->n_basis,
                 SSB_MAX_BASIS);
     SSB_REQUIRE(c->domain > 0.f && c->domain <= 2.f, "domain parameter should be chosen from [0, 2].");
@@ -250,17 +257,20 @@ int ilrma_source(ssb_plan* p, cudaStream_t st) {
   const ssb_config& c = p->cfg;
   const int BN = c.n_batch * c.n_sources;
   TRY(power_spectrogram(p, st));
-  TRY(ssbk_nmf_basis(p->big, p->T, p->V, BN, c.n_bins, c.n_frames, c.n_basis, c.domain, c.source, c.flooring, c.eps,
-                     st));
-  TRY(ssbk_nmf_activation(p->big, p->T, p->V, BN, c.n_bins, c.n_frames, c.n_basis, c.domain, c.source, c.flooring,
-                          c.eps, st));
+  TRY(ssbk_nmf_basis(p->big, p->T, p->V, BN, c.n_bins, c.n_frames, c.n_basis, c.domain, c.source, c.model,
+                     c.model_param, c.flooring, c.eps, st));
+  TRY(ssbk_nmf_activation(p->big, p->T, p->V, BN, c.n_bins, c.n_frames, c.n_basis, c.domain, c.source, c.model,
+                          c.model_param, c.flooring, c.eps, st));
   return 0;
 }
 
 int ilrma_spatial(ssb_plan* p, cudaStream_t st) {
   const ssb_config& c = p->cfg;
   const int B = c.n_batch, N = c.n_sources, I = c.n_bins, J = c.n_frames;
-  TRY(ssbk_nmf_phi(p->T, p->V, p->big, B * N, I, J, c.n_basis, c.domain, st));
+  // the Student-t / GGD weights depend on the current power spectrogram (ilrma.py:2920-2934, :3992-4010)
+  if (c.model != SSB_MODEL_ILRMA_GAUSS) TRY(power_spectrogram(p, st));
+  TRY(ssbk_nmf_phi(p->T, p->V, p->big, p->big, B * N, I, J, c.n_basis, c.domain, c.model, c.model_param, c.flooring,
+                   c.eps, st));
   const long long sb = (long long)N * I * J, sn = (long long)I * J, si = J;
   if (c.spatial == SSB_SPATIAL_ISS1) return ssbk_iss1(p->Y, p->big, sb, sn, si, B, N, I, J, c.flooring, c.eps, st);
   TRY(ssbk_wcov(p->X, p->big, sb, sn, si, nullptr, N, p->U, B, N, I, J, st));
@@ -297,7 +307,7 @@ int ilrma_loss(ssb_plan* p, double* loss, cudaStream_t st) {
   const int B = c.n_batch, N = c.n_sources, I = c.n_bins, J = c.n_frames;
   TRY(power_spectrogram(p, st));
   TRY(logdets(p, st));
-  TRY(ssbk_nmf_rowloss(p->big, p->T, p->V, p->rowloss, B * N, I, J, c.n_basis, c.domain, st));
+  TRY(ssbk_nmf_rowloss(p->big, p->T, p->V, p->rowloss, B * N, I, J, c.n_basis, c.domain, c.model, c.model_param, st));
   return ssbk_ilrma_loss_reduce(p->rowloss, p->logdet, loss, B, N, I, st);
 }
 

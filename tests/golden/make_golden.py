@@ -20,7 +20,7 @@ sys.path.insert(0, os.path.join(HERE, "..", ".."))
 from ssspy.algorithm import projection_back  # noqa: E402
 from ssspy.bss._update_spatial_model import (  # noqa: E402
     update_by_ip1, update_by_ip2, update_by_ip2_one_pair, update_by_iss1)
-from ssspy.bss.ilrma import GaussILRMA  # noqa: E402
+from ssspy.bss.ilrma import GGDILRMA, TILRMA, GaussILRMA  # noqa: E402
 from ssspy.bss.iva import AuxGaussIVA, AuxLaplaceIVA  # noqa: E402
 from ssspy.bss.mnmf import FastGaussMNMF  # noqa: E402
 from ssspy.linalg import eigh, eigh2, inv2  # noqa: E402
@@ -40,7 +40,8 @@ def rand_w(rng, I, N):
 
 
 def ilrma_case(name, N, I, J, K, n_iter, spatial="IP", source="MM", domain=2, normalization=True,
-               flooring="max", reference_id=0, scale_restoration=True, pairs=None, w_init=False, seed=0):
+               flooring="max", reference_id=0, scale_restoration=True, pairs=None, w_init=False, seed=0,
+               dist="gauss", dist_param=0.0):
     X = make_mixture(N, I, J, seed=seed, mode="mix")
     T, V = make_nmf_init(N, I, J, K, seed=42 + seed)
     kwargs = dict(basis=T, activation=V)
@@ -58,10 +59,15 @@ def ilrma_case(name, N, I, J, K, n_iter, spatial="IP", source="MM", domain=2, no
         sel = combination_pair_selector
     elif pairs == "sequential_sorted":
         sel = functools.partial(sequential_pair_selector, sort=True)
-    m = GaussILRMA(n_basis=K, spatial_algorithm=spatial, source_algorithm=source, domain=domain,
-                   flooring_fn=FLOOR[flooring], pair_selector=sel, callbacks=cb,
-                   normalization=normalization, scale_restoration=scale_restoration,
-                   record_loss=True, reference_id=reference_id, rng=np.random.default_rng(0))
+    common = dict(spatial_algorithm=spatial, source_algorithm=source, domain=domain, flooring_fn=FLOOR[flooring],
+                  pair_selector=sel, callbacks=cb, normalization=normalization, scale_restoration=scale_restoration,
+                  record_loss=True, reference_id=reference_id, rng=np.random.default_rng(0))
+    if dist == "t":
+        m = TILRMA(n_basis=K, dof=dist_param, **common)
+    elif dist == "ggd":
+        m = GGDILRMA(n_basis=K, beta=dist_param, **common)
+    else:
+        m = GaussILRMA(n_basis=K, **common)
     Y = m(X, n_iter=n_iter, **kwargs)
     pair_list = np.array(list((sel or sequential_pair_selector)(N)), dtype=np.int32)
     out = dict(kind="ilrma", X=X, T0=T, V0=V, Y=Y, T=m.basis, V=m.activation, loss=np.array(m.loss),
@@ -69,7 +75,7 @@ def ilrma_case(name, N, I, J, K, n_iter, spatial="IP", source="MM", domain=2, no
                n_iter=n_iter, spatial=spatial, source=source, domain=float(domain),
                normalization=str(normalization), flooring=flooring,
                reference_id=-1 if reference_id is None else reference_id,
-               scale_restoration=scale_restoration, pairs=pair_list)
+               scale_restoration=scale_restoration, pairs=pair_list, dist=dist, dist_param=float(dist_param))
     if W0 is not None:
         out["W0"] = W0
     if m.demix_filter is not None:
@@ -196,6 +202,20 @@ def linalg_cases():
     print("linalg done")
 
 
+def tggd_cases():
+    """TILRMA (ssspy/bss/ilrma.py:1992-3334) and GGDILRMA (:3337-4410)."""
+    ilrma_case("tilrma_ip1_mm", 3, 17, 23, 4, 5, dist="t", dist_param=5.0, seed=30)
+    ilrma_case("tilrma_ip1_mm_p1_n2", 2, 21, 30, 3, 6, domain=1, dist="t", dist_param=100.0, seed=31)
+    ilrma_case("tilrma_ip1_me", 3, 17, 23, 4, 5, source="ME", dist="t", dist_param=10.0, seed=32)
+    ilrma_case("tilrma_ip2_mm", 3, 17, 23, 4, 5, spatial="IP2", dist="t", dist_param=5.0, w_init=True, seed=33)
+    ilrma_case("tilrma_iss1_mm", 3, 17, 23, 4, 5, spatial="ISS", dist="t", dist_param=5.0, seed=34)
+    ilrma_case("ggdilrma_ip1_b1", 3, 17, 23, 4, 5, dist="ggd", dist_param=1.0, seed=35)
+    ilrma_case("ggdilrma_ip1_b19_p1", 2, 21, 30, 3, 6, domain=1, dist="ggd", dist_param=1.9, seed=36)
+    ilrma_case("ggdilrma_ip2_b15", 3, 20, 48, 5, 4, spatial="IP2", dist="ggd", dist_param=1.5, seed=37)
+    ilrma_case("ggdilrma_iss1_b1_pbnorm", 3, 17, 23, 4, 5, spatial="ISS", normalization="projection_back", dist="ggd",
+               dist_param=1.0, seed=38)
+
+
 def mdp_cases():
     """minimal_distortion_principle standalone + as scale_restoration of GaussILRMA / AuxLaplaceIVA."""
     from ssspy.algorithm import minimal_distortion_principle
@@ -216,6 +236,7 @@ def main():
     linalg_cases()
     kernel_cases()
     mdp_cases()
+    tggd_cases()
     # GaussILRMA: spatial x source x domain x normalisation x flooring grid (regression-test pattern,
     # tests/regression/bss/test_ilrma.py:48-62: inject basis/activation, fixed n_iter, compare).
     ilrma_case("ilrma_ip1_mm_n2", 2, 33, 40, 4, 10)

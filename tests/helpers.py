@@ -41,3 +41,9 @@ def sr_arg(v):
     """scale_restoration stored in a fixture: bool or keyword string."""
     v = np.asarray(v)
     return bool(v) if v.dtype == bool else str(v)
+
+
+def dist_arg(g):
+    """(kind, parameter) of the source distribution stored in an ILRMA fixture (Gauss when absent)."""
+    kind = str(g["dist"]) if "dist" in g else "gauss"
+    return (kind, float(g["dist_param"]) if kind != "gauss" else None)

@@ -29,8 +29,8 @@ def test_library_exports_every_declared_symbol():
 
 def test_config_struct_layout_matches_header():
     from ssspy_b200 import _lib
-    # 14 int32/float scalars + 128 pair slots + fast_path
-    assert ctypes.sizeof(_lib.SsbConfig) == 4 * (14 + 2 * _lib.SSB_MAX_PAIRS + 1)
+    # 14 int32/float scalars + 128 pair slots + fast_path + model_param
+    assert ctypes.sizeof(_lib.SsbConfig) == 4 * (14 + 2 * _lib.SSB_MAX_PAIRS + 2)
 
 
 def test_plan_validation_runs_without_gpu():
@@ -122,3 +122,33 @@ def test_shard_range_partition():
             assert all(spans[r][1] == spans[r + 1][0] for r in range(G - 1))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_t_and_ggd_constructor_checks():
+    from ssspy_b200.bss import GGDILRMA, TILRMA
+    with pytest.raises(AssertionError, match="Shape parameter"):
+        GGDILRMA(n_basis=2, beta=2.0)
+    with pytest.raises(AssertionError, match="Not support ME"):
+        GGDILRMA(n_basis=2, beta=1.0, source_algorithm="ME")
+    with pytest.raises(ValueError, match="IPA is not supported for t-ILRMA"):
+        TILRMA(n_basis=2, dof=3, spatial_algorithm="IPA")
+    with pytest.raises(AssertionError, match="domain parameter should be 2"):
+        TILRMA(n_basis=2, dof=3, source_algorithm="ME", domain=1)
+    assert repr(TILRMA(n_basis=2, dof=3)).startswith("TILRMA(n_basis=2, dof=3, spatial_algorithm=IP")
+    assert repr(GGDILRMA(n_basis=2, beta=1.5)).startswith("GGDILRMA(n_basis=2, beta=1.5, spatial_algorithm=IP")
+
+
+def test_t_and_ggd_plan_validation():
+    from ssspy_b200 import _lib
+    cfg = _lib.SsbConfig()
+    cfg.model, cfg.spatial, cfg.n_batch, cfg.n_sources, cfg.n_bins, cfg.n_frames, cfg.n_basis = 4, 0, 1, 2, 4, 4, 2
+    cfg.domain, cfg.normalization, cfg.model_param = 2.0, 1, 0.0
+    plan = ctypes.c_void_p()
+    with pytest.raises(_lib.SsbError, match="dof must be positive"):
+        _lib.call("ssb_plan_create", ctypes.byref(cfg), ctypes.byref(plan))
+    cfg.model, cfg.model_param = 5, 2.5
+    with pytest.raises(_lib.SsbError, match="Shape parameter"):
+        _lib.call("ssb_plan_create", ctypes.byref(cfg), ctypes.byref(plan))
+    cfg.model_param = 1.0
+    _lib.call("ssb_plan_create", ctypes.byref(cfg), ctypes.byref(plan))
+    _lib.call("ssb_plan_destroy", plan)

@@ -10,7 +10,7 @@ import itertools
 import numpy as np
 import pytest
 
-from helpers import FLOORS, golden_cases, load, norm_arg, phase_align_rows, relerr, sr_arg
+from helpers import FLOORS, dist_arg, golden_cases, load, norm_arg, phase_align_rows, relerr, sr_arg
 
 pytestmark = pytest.mark.gpu
 
@@ -45,20 +45,33 @@ def assert_loss_close(got, want):
     np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-4)
 
 
-@pytest.mark.parametrize("name", golden_cases("ilrma_"))
-def test_gauss_ilrma_matches_reference(name):
-    from ssspy_b200.bss import GaussILRMA
-    g = load(name)
+def _make_ilrma(g, **over):
+    """GaussILRMA / TILRMA / GGDILRMA as the fixture `g` was generated."""
+    from ssspy_b200.bss import GGDILRMA, TILRMA, GaussILRMA
     ref_id = None if int(g["reference_id"]) < 0 else int(g["reference_id"])
+    spatial = str(g["spatial"])
+    kw = dict(n_basis=g["T0"].shape[-1], spatial_algorithm=spatial, source_algorithm=str(g["source"]),
+              domain=float(g["domain"]), flooring_fn=_floor_fn(str(g["flooring"])),
+              pair_selector=_pair_selector(g["pairs"]) if spatial == "IP2" else None,
+              normalization=norm_arg(g["normalization"]), scale_restoration=sr_arg(g["scale_restoration"]),
+              record_loss=True, reference_id=ref_id, rng=np.random.default_rng(0))
+    kw.update(over)
+    kind, prm = dist_arg(g)
+    if kind == "t":
+        return TILRMA(dof=prm, **kw)
+    if kind == "ggd":
+        return GGDILRMA(beta=prm, **kw)
+    return GaussILRMA(**kw)
+
+
+@pytest.mark.parametrize("name", golden_cases("ilrma_") + golden_cases("tilrma_") + golden_cases("ggdilrma_"))
+def test_gauss_ilrma_matches_reference(name):
+    g = load(name)
     kwargs = dict(basis=g["T0"], activation=g["V0"])
     if "W0" in g:
         kwargs["demix_filter"] = g["W0"]
     spatial = str(g["spatial"])
-    m = GaussILRMA(n_basis=g["T0"].shape[-1], spatial_algorithm=spatial, source_algorithm=str(g["source"]),
-                   domain=float(g["domain"]), flooring_fn=_floor_fn(str(g["flooring"])),
-                   pair_selector=_pair_selector(g["pairs"]) if spatial == "IP2" else None,
-                   normalization=norm_arg(g["normalization"]), scale_restoration=sr_arg(g["scale_restoration"]),
-                   record_loss=True, reference_id=ref_id, rng=np.random.default_rng(0))
+    m = _make_ilrma(g)
     Y = m(g["X"], n_iter=int(g["n_iter"]), **kwargs)
     assert Y.shape == g["Y"].shape and Y.dtype == np.complex128
     assert type(m.loss[-1]) is float and len(m.loss) == int(g["n_iter"]) + 1
@@ -466,3 +479,41 @@ def test_minimal_distortion_principle_matches_reference():
         out = minimal_distortion_principle(g["Y"], reference=g["X"], reference_id=ref)
         assert out.shape == g["mdp_" + key].shape
         assert relerr(out, g["mdp_" + key]) < 1e-5
+
+
+@pytest.mark.parametrize("kind,prm,spatial,source,domain", [("t", 3.0, "IP", "MM", 2), ("t", 50.0, "ISS", "ME", 2),
+                                                            ("t", 8.0, "IP2", "MM", 1.0), ("ggd", 1.0, "IP", "MM", 2),
+                                                            ("ggd", 1.6, "ISS", "MM", 1.5), ("ggd", 0.7, "IP2", "MM", 2)])
+def test_t_and_ggd_ilrma_batched_vs_oracle(kind, prm, spatial, source, domain):
+    """TILRMA / GGDILRMA on seeded batched input against the fp64 oracle (per mixture), including the manual
+    update_source_model / update_spatial_model / normalize sequence and compute_loss."""
+    from oracle import ilrma as oilrma
+    from ssspy_b200.bss import GGDILRMA, TILRMA
+    from ssspy_b200.utils.synth import make_batch, make_nmf_init
+    B, N, I, J, K, n_iter = 3, 3, 33, 80, 6, 4
+    X = make_batch(B, N, I, J, config_id=9, mode="mix")
+    TV = [make_nmf_init(N, I, J, K, seed=70 + b) for b in range(B)]
+    T0, V0 = np.stack([t for t, _ in TV]), np.stack([v for _, v in TV])
+    cls, key = (TILRMA, "dof") if kind == "t" else (GGDILRMA, "beta")
+    mk = lambda **kw: cls(n_basis=K, spatial_algorithm=spatial, source_algorithm=source, domain=domain,  # noqa: E731
+                          **{key: prm}, **kw)
+    m = mk()
+    Y = m(X, n_iter=n_iter, basis=T0, activation=V0)
+    # (projection back of the initial identity filter would zero every non-reference source, as in the reference)
+    m2 = mk(scale_restoration=False)
+    m2(X, n_iter=0, basis=T0, activation=V0)
+    for _ in range(n_iter):
+        m2.update_source_model()
+        m2.update_spatial_model()
+        m2.normalize()
+    np.testing.assert_allclose(np.asarray(m2.compute_loss()), np.asarray(m.loss)[-1], rtol=1e-6)
+    loss = np.asarray(m.loss)
+    assert loss.shape == (n_iter + 1, B)
+    pairs = [(n, (n + 1) % N) for n in range(N)]
+    for b in range(B):
+        st = oilrma.run(X[b], T0[b], V0[b], n_iter=n_iter, p=domain, spatial_algorithm=spatial,
+                        source_algorithm=source, pairs=pairs if spatial == "IP2" else None, dist=(kind, prm))
+        np.testing.assert_allclose(loss[:, b], st["loss"], rtol=2e-5 if spatial != "IP2" else 1e-3, atol=1e-4)
+        assert relerr(Y[b], st["Y"]) < tol_seeded(spatial)
+        # T carries psi^p of the normalisation, i.e. twice the relative error of W (the contract is on Y)
+        assert relerr(m.basis[b], st["T"]) < 3 * tol_seeded(spatial)

@@ -9,12 +9,12 @@ from oracle import linalg as olinalg
 from oracle import spatial as ospatial
 from oracle.projection_back import projection_back
 
-from helpers import FLOORS, golden_cases, load, norm_arg, phase_align_rows, relerr, sr_arg
+from helpers import FLOORS, dist_arg, golden_cases, load, norm_arg, phase_align_rows, relerr, sr_arg
 
 TOL = 1e-9
 
 
-@pytest.mark.parametrize("name", golden_cases("ilrma_"))
+@pytest.mark.parametrize("name", golden_cases("ilrma_") + golden_cases("tilrma_") + golden_cases("ggdilrma_"))
 def test_ilrma_oracle_matches_reference(name):
     g = load(name)
     ref_id = None if int(g["reference_id"]) < 0 else int(g["reference_id"])
@@ -22,7 +22,7 @@ def test_ilrma_oracle_matches_reference(name):
                     floor=FLOORS[str(g["flooring"])], spatial_algorithm=str(g["spatial"]),
                     source_algorithm=str(g["source"]), normalization=norm_arg(g["normalization"]),
                     pairs=[tuple(p) for p in g["pairs"]], reference_id=ref_id,
-                    scale_restoration=sr_arg(g["scale_restoration"]), snapshots=True)
+                    scale_restoration=sr_arg(g["scale_restoration"]), snapshots=True, dist=dist_arg(g))
     assert relerr(st["Y"], g["Y"]) < TOL
     assert relerr(st["T"], g["T"]) < TOL
     assert relerr(st["V"], g["V"]) < TOL
