@@ -84,6 +84,9 @@ typedef struct ssb_config {
                         0: always the modular kernels */
   float model_param; /* TILRMA: degree of freedom nu (ilrma.py:2160); GGDILRMA: shape beta (ilrma.py:3496);
                         ignored by the other models */
+  int32_t partitioning; /* ILRMA family only, 1: partitioning function (ilrma.py:201-245): T is [B,I,K] and V is
+                           [B,K,J], shared by the sources, and the `variance` slot of ssb_plan_bind holds the
+                           latent variable Z[B,N,K] f32 (ilrma.py:219-226); power normalisation only */
 } ssb_config;
 
 typedef struct ssb_plan ssb_plan;

@@ -3,9 +3,9 @@
 Restated from SURVEY.md Appendix A.1 = ssspy/bss/ilrma.py:900-922 (update_once),
 :1051-1204 (MM basis/activation), :1249-1401 (ME), :1440-1696 (IP1/IP2/ISS1),
 :365-514 (normalisation), :1910-1967 (loss), :538-565 / :1969-1979 (scale).
-``partitioning=False`` only.  State is a plain dict:
-``X[N,I,J]`` c128, ``W[I,N,N]`` c128 or None (ISS), ``Y[N,I,J]``, ``T[N,I,K]``,
-``V[N,K,J]``.
+State is a plain dict: ``X[N,I,J]`` c128, ``W[I,N,N]`` c128 or None (ISS), ``Y[N,I,J]``,
+``T[N,I,K]``, ``V[N,K,J]``; with the partitioning function (ilrma.py:201-245, :297-331) ``Z[N,K]``, ``T[I,K]``,
+``V[K,J]`` are shared by the sources.
 """
 import numpy as np
 
@@ -18,7 +18,7 @@ def separate(X, W):
     return (W @ X.transpose(1, 0, 2)).transpose(1, 0, 2)
 
 
-def init_state(X, T, V, W=None, spatial_algorithm="IP"):
+def init_state(X, T, V, W=None, spatial_algorithm="IP", Z=None):
     """ssspy/bss/ilrma.py:186-199, :897-898."""
     N, I, J = X.shape
     if W is None:
@@ -26,9 +26,28 @@ def init_state(X, T, V, W=None, spatial_algorithm="IP"):
     st = dict(X=X.astype(np.complex128), W=W.astype(np.complex128).copy(),
               T=T.astype(np.float64).copy(), V=V.astype(np.float64).copy())
     st["Y"] = separate(st["X"], st["W"])
+    st["Z"] = None if Z is None else Z.astype(np.float64).copy()
     if spatial_algorithm in ("ISS", "ISS1"):
         st["W"] = None
     return st
+
+
+def reconstruct(st):
+    """R[n,i,j] = sum_k T V, or sum_k z_nk t_ik v_kj with the partitioning function (ilrma.py:297-331)."""
+    if st.get("Z") is None:
+        return st["T"] @ st["V"]
+    return np.einsum("nk,ik,kj->nij", st["Z"], st["T"], st["V"])
+
+
+def update_latent(st, p=2, source_algorithm="MM", dist=("gauss", None)):
+    """Z <- Z (sum_ij t v A / sum_ij t v / R)^b, then Z /= sum_n Z (ilrma.py:1007-1049; ME :1206-1247;
+    t :2384-2432; GGD :3698-3743).  No flooring."""
+    P = np.abs(_Y(st)) ** 2
+    A, b = _source_weights(P, reconstruct(st), p, source_algorithm, dist)
+    num = np.einsum("ik,kj,nij->nk", st["T"], st["V"], A)
+    den = np.einsum("ik,kj,nij->nk", st["T"], st["V"], 1 / reconstruct(st))
+    Z = (num / den) ** b * st["Z"]
+    st["Z"] = Z / Z.sum(axis=0)
 
 
 def _Y(st):
@@ -56,10 +75,14 @@ def update_basis(st, p=2, floor=spatial.max_flooring, source_algorithm="MM", dis
     """T <- floor(T (sum_j V A / sum_j V/R)^b)."""
     P = np.abs(_Y(st)) ** 2
     T, V = st["T"], st["V"]
-    R = T @ V
+    R = reconstruct(st)
     A, b = _source_weights(P, R, p, source_algorithm, dist)
-    num = np.einsum("nkj,nij->nik", V, A)
-    den = np.einsum("nkj,nij->nik", V, 1 / R)
+    if st.get("Z") is not None:  # ilrma.py:1098-1113
+        num = np.einsum("nk,kj,nij->ik", st["Z"], V, A)
+        den = np.einsum("nk,kj,nij->ik", st["Z"], V, 1 / R)
+    else:
+        num = np.einsum("nkj,nij->nik", V, A)
+        den = np.einsum("nkj,nij->nik", V, 1 / R)
     st["T"] = floor(((num / den) ** b) * T)
 
 
@@ -67,10 +90,14 @@ def update_activation(st, p=2, floor=spatial.max_flooring, source_algorithm="MM"
     """Same with the new T, reduced over bins (ssspy/bss/ilrma.py:1192-1202; ME :1387-1399)."""
     P = np.abs(_Y(st)) ** 2
     T, V = st["T"], st["V"]
-    R = T @ V
+    R = reconstruct(st)
     A, b = _source_weights(P, R, p, source_algorithm, dist)
-    num = np.einsum("nik,nij->nkj", T, A)
-    den = np.einsum("nik,nij->nkj", T, 1 / R)
+    if st.get("Z") is not None:  # ilrma.py:1174-1189
+        num = np.einsum("nk,ik,nij->kj", st["Z"], T, A)
+        den = np.einsum("nk,ik,nij->kj", st["Z"], T, 1 / R)
+    else:
+        num = np.einsum("nik,nij->nkj", T, A)
+        den = np.einsum("nik,nij->nkj", T, 1 / R)
     st["V"] = floor(((num / den) ** b) * V)
 
 
@@ -78,7 +105,7 @@ def update_spatial(st, p=2, floor=spatial.max_flooring, spatial_algorithm="IP", 
     """phi = 1/(T V)^(2/p) (no floor), then IP1 / IP2 on W or ISS1 on Y
     (ssspy/bss/ilrma.py:1494-1507, :1618-1633, :1690-1696).  Student-t: phi = 1/R~ (ilrma.py:2920-2934);
     GGD: phi = 1/((2/beta) floor(|y|^(2-beta)) R^(beta/p)) (:3992-4010)."""
-    R = st["T"] @ st["V"]
+    R = reconstruct(st)
     kind, prm = dist
     if kind == "gauss":
         phi = 1 / R ** (2 / p)
@@ -106,13 +133,21 @@ def normalize(st, p=2, floor=spatial.max_flooring, normalization=True, reference
     if normalization is True or normalization == "power":
         Y = _Y(st)
         psi = floor(np.sqrt(np.mean(np.abs(Y) ** 2, axis=(-2, -1))))
-        st["T"] = st["T"] / psi[:, None, None] ** p
+        if st.get("Z") is not None:  # ilrma.py:424-430
+            Zp = st["Z"] / psi[:, None] ** p
+            scale = Zp.sum(axis=0)
+            st["T"] = st["T"] * scale[None, :]
+            st["Z"] = Zp / scale
+        else:
+            st["T"] = st["T"] / psi[:, None, None] ** p
         if st["W"] is None:
             st["Y"] = Y / psi[:, None, None]
         else:
             st["W"] = st["W"] / psi[None, :, None]
     elif normalization == "projection_back":
         ref = 0 if reference_id is None else reference_id
+        if st.get("Z") is not None:  # ilrma.py:466-470
+            raise NotImplementedError("Projection-back-based normalization is not applicable with partitioning function.")
         if st["W"] is None:
             Y = st["Y"].transpose(1, 0, 2)
             X = st["X"].transpose(1, 0, 2)
@@ -130,6 +165,8 @@ def normalize(st, p=2, floor=spatial.max_flooring, normalization=True, reference
 def update_once(st, p=2, floor=spatial.max_flooring, spatial_algorithm="IP", source_algorithm="MM",
                 normalization=True, pairs=None, reference_id=0, dist=("gauss", None)):
     """ssspy/bss/ilrma.py:900-922."""
+    if st.get("Z") is not None:  # ilrma.py:972-973
+        update_latent(st, p, source_algorithm, dist)
     update_basis(st, p, floor, source_algorithm, dist)
     update_activation(st, p, floor, source_algorithm, dist)
     update_spatial(st, p, floor, spatial_algorithm, pairs, dist)
@@ -148,7 +185,7 @@ def compute_loss(st, p=2, dist=("gauss", None)):
     else:
         W = st["W"]
         Y = separate(st["X"], W)
-    TV = st["T"] @ st["V"]
+    TV = reconstruct(st)
     kind, prm = dist
     if kind == "gauss":
         loss = np.abs(Y) ** 2 / TV ** (2 / p) + (2 / p) * np.log(TV)
@@ -182,9 +219,9 @@ def restore_scale(st, reference_id=0, method=True):
 
 def run(X, T, V, n_iter, W=None, p=2, floor=spatial.max_flooring, spatial_algorithm="IP",
         source_algorithm="MM", normalization=True, pairs=None, reference_id=0,
-        scale_restoration=True, record_loss=True, snapshots=False, dist=("gauss", None)):
+        scale_restoration=True, record_loss=True, snapshots=False, dist=("gauss", None), Z=None):
     """GaussILRMA.__call__ (ssspy/bss/ilrma.py:820-855 + ssspy/bss/base.py:48-77)."""
-    st = init_state(X, T, V, W, spatial_algorithm)
+    st = init_state(X, T, V, W, spatial_algorithm, Z)
     loss, snaps = [], []
     if record_loss:
         loss.append(compute_loss(st, p, dist))

@@ -29,7 +29,7 @@ class SsbConfig(ctypes.Structure):
         ("flooring", ctypes.c_int32), ("eps", ctypes.c_float), ("normalization", ctypes.c_int32),
         ("reference_id", ctypes.c_int32), ("n_pairs", ctypes.c_int32),
         ("pairs", ctypes.c_int32 * (2 * SSB_MAX_PAIRS)), ("fast_path", ctypes.c_int32),
-        ("model_param", ctypes.c_float),
+        ("model_param", ctypes.c_float), ("partitioning", ctypes.c_int32),
     ]
 
 

@@ -24,11 +24,12 @@ _STATE_DTYPES = {
     "basis": torch.float32,
     "activation": torch.float32,
     "variance": torch.float32,
+    "latent": torch.float32,
     "diagonalizer": torch.complex64,
     "spatial": torch.float32,
 }
-_STATE_RANKS = {"demix_filter": 4, "output": 4, "basis": 4, "activation": 4, "variance": 3, "diagonalizer": 4,
-                "spatial": 4}
+_STATE_RANKS = {"demix_filter": 4, "output": 4, "basis": 4, "activation": 4, "variance": 3, "latent": 3,
+                "diagonalizer": 4, "spatial": 4}
 
 
 def _state_property(name):
@@ -69,6 +70,7 @@ class DeviceSeparatorMixin:
     basis = _state_property("basis")
     activation = _state_property("activation")
     variance = _state_property("variance")
+    latent = _state_property("latent")
     diagonalizer = _state_property("diagonalizer")
     spatial = _state_property("spatial")
     # which state entries fill the (W, Y, T, V, variance) slots of ssb_plan_bind
@@ -137,7 +139,7 @@ class DeviceSeparatorMixin:
             self._state[name] = value if _device.is_tensor(value) else np.array(value)
             return
         t = _device.to_device(value, _STATE_DTYPES[name])
-        batched_rank = _STATE_RANKS[name]
+        batched_rank = self._state_rank(name)
         if t.dim() == batched_rank - 1:
             t = t.unsqueeze(0)
         if name == "output":
@@ -148,6 +150,10 @@ class DeviceSeparatorMixin:
         else:
             self._state[name] = t.clone() if t.data_ptr() == (value.data_ptr() if _device.is_tensor(value) else 0) else t
             self._plan_key = None  # rebinding needed
+
+    def _state_rank(self, name):
+        """Rank of the batched device layout of a state entry."""
+        return _STATE_RANKS[name]
 
     def _dev(self, name):
         """Device tensor of a state entry (uploading a pending host value first)."""

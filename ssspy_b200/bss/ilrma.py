@@ -1,12 +1,14 @@
 """GaussILRMA, TILRMA and GGDILRMA on the device (host mirror of ssspy/bss/ilrma.py: ILRMABase :32-579,
-GaussILRMA :582-1989, TILRMA :1992-3334, GGDILRMA :3337-4410).  Same constructor, ``__call__``, ``update_once`` / ``update_source_model`` /
-``update_spatial_model`` / ``normalize`` / ``compute_loss`` / ``restore_scale`` /
-``apply_projection_back`` and attribute names; all arithmetic runs in libssb.so's CUDA kernels.
+GaussILRMA :582-1989, TILRMA :1992-3334, GGDILRMA :3337-4410).  Same constructors, ``__call__``,
+``update_once`` / ``update_source_model`` / ``update_spatial_model`` / ``normalize`` / ``compute_loss`` /
+``restore_scale`` / ``apply_projection_back`` / ``apply_minimal_distortion_principle`` and attribute names
+(``basis``, ``activation``, ``latent``, ``demix_filter``, ``output``, ``loss``); all arithmetic runs in
+libssb.so's CUDA kernels.
 
-Covered: spatial_algorithm IP / IP1 / IP2 / ISS / ISS1, source_algorithm MM /
-ME, any ``domain`` in (0, 2], ``partitioning=False``, normalization True / "power" /
-"projection_back" / False, projection-back scale restoration.  ISS2, IPA, partitioning and the
-minimal-distortion principle are "next" rows and raise NotImplementedError (no CPU fallback).
+Covered: spatial_algorithm IP / IP1 / IP2 / ISS / ISS1, source_algorithm MM / ME, any ``domain`` in (0, 2],
+``partitioning`` False / True (latent variable Z), normalization True / "power" / "projection_back" / False,
+projection-back and minimal-distortion-principle scale restoration.  ISS2 and IPA raise NotImplementedError
+(no CPU fallback).
 """
 import ctypes
 import functools
@@ -102,12 +104,13 @@ class ILRMABase(DeviceSeparatorMixin, IterativeMethodBase):
         flooring_fn = choose_flooring_fn(flooring_fn, method=self)
         if rng is None:
             rng = np.random.default_rng()
-        if self.partitioning:
-            _not_on_device("partitioning=True")
         B, N, I, J = self._dims()
         K = self.n_basis
         if not (1 <= K <= _lib.SSB_MAX_BASIS):
             raise NotImplementedError("n_basis={} is outside the supported range 1..{}.".format(K, _lib.SSB_MAX_BASIS))
+        if self.partitioning:
+            self._init_nmf_partitioned(flooring_fn, rng)
+            return
         need_T, need_V = not self._has("basis"), not self._has("activation")
         T = np.empty((B, N, I, K)) if need_T else None
         V = np.empty((B, N, K, J)) if need_V else None
@@ -124,6 +127,38 @@ class ILRMABase(DeviceSeparatorMixin, IterativeMethodBase):
             self._state["activation"] = _device.to_device(V, torch.float32)
         else:
             self._batchify("activation", (N, K, J))
+
+    def _init_nmf_partitioned(self, flooring_fn, rng):
+        """Z[N,K] (unit column sums, then floored), T[I,K], V[K,J] shared by the sources, drawn in this order
+        (ilrma.py:219-245)."""
+        B, N, I, J = self._dims()
+        K = self.n_basis
+        need = {name: not self._has(name) for name in ("latent", "basis", "activation")}
+        shapes = {"latent": (N, K), "basis": (I, K), "activation": (K, J)}
+        host = {name: np.empty((B,) + shapes[name]) for name in shapes if need[name]}
+        for b in range(B):
+            for name in ("latent", "basis", "activation"):
+                if not need[name]:
+                    continue
+                x = rng.random(shapes[name])
+                if name == "latent":
+                    x = x / x.sum(axis=0)
+                host[name][b] = flooring_fn(x)
+        for name in shapes:
+            if need[name]:
+                self._state[name] = _device.to_device(host[name], torch.float32)
+            else:
+                self._batchify(name, shapes[name])
+
+    def _state_rank(self, name):
+        if self.partitioning and name in ("basis", "activation"):
+            return 3
+        return super()._state_rank(name)
+
+    @property
+    def _plan_slots(self):
+        # the latent variable travels in the `variance` slot of ssb_plan_bind (include/ssb.h)
+        return ("demix_filter", "output", "basis", "activation", "latent" if self.partitioning else "variance")
 
     # ---- C-ABI plan ------------------------------------------------------------------------------
     def _plan_config(self):
@@ -155,6 +190,7 @@ class ILRMABase(DeviceSeparatorMixin, IterativeMethodBase):
         for q, (m, n) in enumerate(pairs):
             cfg.pairs[2 * q], cfg.pairs[2 * q + 1] = m, n
         cfg.fast_path = 1 if getattr(self, "fast_path", True) else 0
+        cfg.partitioning = 1 if self.partitioning else 0
         return cfg
 
     # ---- normalisation (ilrma.py:333-514) ----------------------------------------------------------
@@ -176,6 +212,8 @@ class ILRMABase(DeviceSeparatorMixin, IterativeMethodBase):
         self._with_normalization("power", flooring_fn)
 
     def normalize_by_projection_back(self):
+        if self.partitioning:  # ilrma.py:466-470
+            raise NotImplementedError("Projection-back-based normalization is not applicable with partitioning function.")
         self._with_normalization("projection_back", self.flooring_fn)
 
     def _with_normalization(self, kind, flooring_fn):
@@ -228,8 +266,6 @@ class _DeviceILRMA(ILRMABase):
     def _init_algorithms(self, spatial_algorithm, source_algorithm, domain, partitioning, normalization, pair_selector):
         if spatial_algorithm not in _SPATIAL_ENUM:
             _not_on_device("spatial_algorithm={!r}".format(spatial_algorithm))
-        if partitioning:
-            _not_on_device("partitioning=True")
         self.spatial_algorithm = spatial_algorithm
         self.source_algorithm = source_algorithm
         self.domain = domain

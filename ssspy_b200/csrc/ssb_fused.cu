@@ -1120,7 +1120,7 @@ size_t ssb_fused_carve(ssb_fused_ws* ws, const ssb_config*, char* base) {
 }
 
 int ssb_fused_supported(const ssb_config* c) {
-  return c->model == SSB_MODEL_ILRMA_GAUSS && c->source == SSB_SOURCE_MM && c->domain == 2.0f &&
+  return c->model == SSB_MODEL_ILRMA_GAUSS && !c->partitioning && c->source == SSB_SOURCE_MM && c->domain == 2.0f &&
          c->n_basis <= 32 &&
          (c->n_frames % 16) == 0 && c->n_sources >= 2 && c->n_sources <= SSB_MAX_SOURCES;
 }

@@ -53,19 +53,33 @@ int ssbk_mdp(const cf* Y, const cf* X, cf* Yout, int B, int N, int I, int J, int
 // :1192-1202, :1311-1323, :1387-1399)
 // `model` = SSB_MODEL_ILRMA_{GAUSS,T,GGD}, `prm` = nu (TILRMA, ilrma.py:2620-2640, :2868-2886) or beta
 // (GGDILRMA, ilrma.py:3700-3720)
+// vdiv = 1: V[BN,K,J] per source; vdiv = N: V[B,K,J] shared by the sources (partitioning function).  With
+// num_out / den_out the raw sums are written ([BN,I,K] resp. [BN,K,J]) instead of updating T / V.
 int ssbk_nmf_basis(const float* P, float* T, const float* V, int BN, int I, int J, int K, float p, int source,
-                   int model, float prm, int flooring, float eps, cudaStream_t st);
+                   int model, float prm, int flooring, float eps, cudaStream_t st, int vdiv = 1,
+                   float* num_out = nullptr, float* den_out = nullptr);
 int ssbk_nmf_activation(const float* P, const float* T, float* V, int BN, int I, int J, int K, float p, int source,
-                        int model, float prm, int flooring, float eps, cudaStream_t st);
+                        int model, float prm, int flooring, float eps, cudaStream_t st, int vdiv = 1,
+                        float* num_out = nullptr, float* den_out = nullptr);
+// partitioning function (ilrma.py:201-245, :1007-1049, :1098-1126, :1174-1202, :424-430)
+int ssbk_part_teff(const float* Z, const float* T, float* Teff, int B, int N, int I, int K, cudaStream_t st);
+int ssbk_part_latent(const float* gnum, const float* gden, const float* T, float* Z, int B, int N, int I, int K,
+                     float p, int source, int model, float prm, cudaStream_t st);
+int ssbk_part_basis(const float* gnum, const float* gden, const float* Z, float* T, int B, int N, int I, int K, float p,
+                    int source, int model, float prm, int flooring, float eps, cudaStream_t st);
+int ssbk_part_activation(const float* hnum, const float* hden, float* V, int B, int N, int K, int J, float p,
+                         int source, int model, float prm, int flooring, float eps, cudaStream_t st);
+int ssbk_part_normalize(const double* psi2, float* Z, float* T, int B, int N, int I, int K, float p, int flooring,
+                        float eps, cudaStream_t st);
 // phi[B,N,I,J] = (T V)^(-2/p)   (ilrma.py:1494-1498); Student-t: 1/(nu/(nu+2) R^(2/p) + 2/(nu+2) P)
 // (ilrma.py:2920-2934); GGD: 1/((2/beta) floor(P^((2-beta)/2)) R^(beta/p)) (ilrma.py:3992-4010).  P (only read for
 // T / GGD) may alias phi.
 int ssbk_nmf_phi(const float* T, const float* V, const float* P, float* phi, int BN, int I, int J, int K, float p,
-                 int model, float prm, int flooring, float eps, cudaStream_t st);
+                 int model, float prm, int flooring, float eps, cudaStream_t st, int vdiv = 1);
 // rowloss[B,N,I] = mean_j( P / R^(2/p) + (2/p) log R ),  R = T V   (ilrma.py:1957-1964; t :3265-3280;
 // GGD :4340-4355)
 int ssbk_nmf_rowloss(const float* P, const float* T, const float* V, double* rowloss, int BN, int I, int J, int K,
-                     float p, int model, float prm, cudaStream_t st);
+                     float p, int model, float prm, cudaStream_t st, int vdiv = 1);
 // loss[b] = sum_{n,i} rowloss - 2 sum_i logdet   (ilrma.py:1964-1965)
 int ssbk_ilrma_loss_reduce(const double* rowloss, const double* logdet, double* loss, int B, int N, int I,
                            cudaStream_t st);

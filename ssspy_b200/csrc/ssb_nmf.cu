@@ -48,7 +48,9 @@ __device__ __forceinline__ float src_factor(float P, float R, float inv, const S
 template <int KP>
 __global__ void __launch_bounds__(WPB * 32) k_nmf_basis(const float* __restrict__ P, float* __restrict__ T,
                                                         const float* __restrict__ V, int rows, int I, int J,
-                                                        int K, SrcParam sp, int flooring, float eps) {
+                                                        int K, SrcParam sp, int flooring, float eps, int vdiv,
+                                                        float* __restrict__ num_out,
+                                                        float* __restrict__ den_out) {
   const int row = blockIdx.x * WPB + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -59,7 +61,7 @@ __global__ void __launch_bounds__(WPB * 32) k_nmf_basis(const float* __restrict_
     t[k] = k < K ? T[(size_t)row * K + k] : 0.f;
     num[k] = den[k] = 0.f;
   }
-  const float* Vb = V + (size_t)bn * K * J;
+  const float* Vb = V + (size_t)(bn / vdiv) * K * J;  // vdiv = N: V shared by the sources (partitioning)
   const float* Pr = P + (size_t)row * J;
   for (int j = lane; j < J; j += 32) {
     float v[KP];
@@ -82,7 +84,14 @@ __global__ void __launch_bounds__(WPB * 32) k_nmf_basis(const float* __restrict_
   for (int k = 0; k < KP; ++k) {
     if (k < K) {
       float nu = warp_sum(num[k]), de = warp_sum(den[k]);
-      if ((k & 31) == lane) T[(size_t)row * K + k] = ssb_floor(upd_pow(nu / de, sp) * t[k], flooring, eps);
+      if ((k & 31) == lane) {
+        if (num_out) {  // raw sums for the partitioned updates (combined over sources / bins later)
+          num_out[(size_t)row * K + k] = nu;
+          den_out[(size_t)row * K + k] = de;
+        } else {
+          T[(size_t)row * K + k] = ssb_floor(upd_pow(nu / de, sp) * t[k], flooring, eps);
+        }
+      }
     }
   }
 }
@@ -93,7 +102,8 @@ template <int KP>
 __global__ void __launch_bounds__(ACT_NW * 32) k_nmf_activation(const float* __restrict__ P,
                                                                const float* __restrict__ T, float* __restrict__ V,
                                                                int I, int J, int K, SrcParam sp, int flooring,
-                                                               float eps) {
+                                                               float eps, int vdiv, float* __restrict__ num_out,
+                                                               float* __restrict__ den_out) {
   __shared__ float s_acc[2 * KP][32];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int jt = blockIdx.x, bn = blockIdx.y;
@@ -102,7 +112,7 @@ __global__ void __launch_bounds__(ACT_NW * 32) k_nmf_activation(const float* __r
   float v[KP], num[KP], den[KP];
 #pragma unroll
   for (int k = 0; k < KP; ++k) {
-    v[k] = (valid && k < K) ? V[((size_t)bn * K + k) * J + j] : 0.f;
+    v[k] = (valid && k < K) ? V[((size_t)(bn / vdiv) * K + k) * J + j] : 0.f;
     num[k] = den[k] = 0.f;
   }
   for (int i = w; i < I; i += ACT_NW) {
@@ -143,8 +153,13 @@ __global__ void __launch_bounds__(ACT_NW * 32) k_nmf_activation(const float* __r
 #pragma unroll
     for (int k = 0; k < KP; ++k) {
       if (k < K) {
-        float ratio = s_acc[k][lane] / s_acc[KP + k][lane];
-        V[((size_t)bn * K + k) * J + j] = ssb_floor(upd_pow(ratio, sp) * v[k], flooring, eps);
+        if (num_out) {
+          num_out[((size_t)bn * K + k) * J + j] = s_acc[k][lane];
+          den_out[((size_t)bn * K + k) * J + j] = s_acc[KP + k][lane];
+        } else {
+          float ratio = s_acc[k][lane] / s_acc[KP + k][lane];
+          V[((size_t)bn * K + k) * J + j] = ssb_floor(upd_pow(ratio, sp) * v[k], flooring, eps);
+        }
       }
     }
   }
@@ -240,7 +255,8 @@ __global__ void __launch_bounds__(ACT_NW * 32) k_nmf_activation_ab(const float* 
 template <int KP>
 __global__ void __launch_bounds__(WPB * 32) k_nmf_phi(const float* __restrict__ T, const float* __restrict__ V,
                                                       const float* P, float* phi, int rows, int I, int J, int K,
-                                                      float p, int model, float prm, int flooring, float eps) {
+                                                      float p, int model, float prm, int flooring, float eps,
+                                                      int vdiv) {
   const int row = blockIdx.x * WPB + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -248,7 +264,7 @@ __global__ void __launch_bounds__(WPB * 32) k_nmf_phi(const float* __restrict__ 
   float t[KP];
 #pragma unroll
   for (int k = 0; k < KP; ++k) t[k] = k < K ? T[(size_t)row * K + k] : 0.f;
-  const float* Vb = V + (size_t)bn * K * J;
+  const float* Vb = V + (size_t)(bn / vdiv) * K * J;
   const bool p2 = (p == 2.0f);
   const float e = -2.0f / p;
   for (int j = lane; j < J; j += 32) {
@@ -277,7 +293,7 @@ template <int KP>
 __global__ void __launch_bounds__(WPB * 32) k_nmf_rowloss(const float* __restrict__ P, const float* __restrict__ T,
                                                           const float* __restrict__ V, double* __restrict__ rowloss,
                                                           int rows, int I, int J, int K, float p, int model,
-                                                          float prm) {
+                                                          float prm, int vdiv) {
   const int row = blockIdx.x * WPB + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -285,7 +301,7 @@ __global__ void __launch_bounds__(WPB * 32) k_nmf_rowloss(const float* __restric
   float t[KP];
 #pragma unroll
   for (int k = 0; k < KP; ++k) t[k] = k < K ? T[(size_t)row * K + k] : 0.f;
-  const float* Vb = V + (size_t)bn * K * J;
+  const float* Vb = V + (size_t)(bn / vdiv) * K * J;
   const bool p2 = (p == 2.0f);
   const float e = 2.0f / p;
   double acc = 0.0;
@@ -373,7 +389,7 @@ __global__ void k_psi_from_y(const cf* __restrict__ Y, double* __restrict__ psi2
 // T[b,n,i,k] /= psi^p ; W[b,i,n,:] /= psi ; Y[b,n,:,:] /= psi      (ilrma.py:434-444)
 __global__ void k_apply_psi(const double* __restrict__ psi2, float* __restrict__ T, cf* __restrict__ W,
                             cf* __restrict__ Y, int B, int N, int I, int J, int K, float p, int flooring, double eps) {
-  const size_t nT = (size_t)B * N * I * K;
+  const size_t nT = T ? (size_t)B * N * I * K : 0;
   const size_t nW = W ? (size_t)B * I * N * N : 0;
   const size_t nY = Y ? (size_t)B * N * I * J : 0;
   const size_t total = nT + nW + nY;
@@ -414,6 +430,118 @@ __global__ void k_scale_basis(float* __restrict__ T, const cf* __restrict__ s, l
   }
 }
 
+// ---- partitioning function (latent Z[B,N,K], shared T[B,I,K], V[B,K,J]; ilrma.py:201-245, :297-331) ----------
+// The per-source model is R_n = Teff_n V with Teff[b,n,i,k] = z_nk t_ik, so the sweeps above are reused with
+// Teff as the basis and V shared (vdiv = N); they emit the raw sums and the kernels below combine them.
+__global__ void k_part_teff(const float* __restrict__ Z, const float* __restrict__ T, float* __restrict__ Teff, int N,
+                            int I, int K, size_t total) {
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(e % K);
+    const int i = (int)((e / K) % I);
+    const size_t bn = e / ((size_t)K * I);
+    const size_t b = bn / N;
+    Teff[e] = Z[bn * K + k] * T[(b * I + i) * K + k];
+  }
+}
+
+// Z <- Z (sum_i t_ik gnum[n,i,k] / sum_i t_ik gden[n,i,k])^b, then Z /= sum_n Z (ilrma.py:1007-1049): one block per
+// mixture, one warp per (n, k)
+__global__ void __launch_bounds__(256) k_part_latent(const float* __restrict__ gnum, const float* __restrict__ gden,
+                                                     const float* __restrict__ T, float* __restrict__ Z, int N, int I,
+                                                     int K, float bexp) {
+  __shared__ float zs[SSB_MAX_SOURCES * SSB_MAX_BASIS];
+  const int b = blockIdx.x, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int pair = w; pair < N * K; pair += 8) {
+    const int n = pair / K, k = pair - n * K;
+    float nu = 0.f, de = 0.f;
+    for (int i = lane; i < I; i += 32) {
+      const float t = T[((size_t)b * I + i) * K + k];
+      const size_t g = (((size_t)b * N + n) * I + i) * K + k;
+      nu = fmaf(t, gnum[g], nu);
+      de = fmaf(t, gden[g], de);
+    }
+    nu = warp_sum(nu);
+    de = warp_sum(de);
+    if (lane == 0) {
+      const float r = nu / de;
+      zs[pair] = Z[((size_t)b * N + n) * K + k] * (bexp == 0.5f ? sqrtf(r) : bexp == 1.0f ? r : powf(r, bexp));
+    }
+  }
+  __syncthreads();
+  for (int pair = threadIdx.x; pair < N * K; pair += blockDim.x) {
+    const int k = pair % K;
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s += zs[n * K + k];
+    Z[(size_t)b * N * K + pair] = zs[pair] / s;
+  }
+}
+
+// T[b,i,k] <- floor(T (sum_n z_nk gnum / sum_n z_nk gden)^b)   (ilrma.py:1098-1126)
+__global__ void k_part_basis(const float* __restrict__ gnum, const float* __restrict__ gden,
+                             const float* __restrict__ Z, float* __restrict__ T, int N, int I, int K, float bexp,
+                             int flooring, float eps, size_t total) {
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(e % K);
+    const int i = (int)((e / K) % I);
+    const size_t b = e / ((size_t)K * I);
+    float nu = 0.f, de = 0.f;
+    for (int n = 0; n < N; ++n) {
+      const float z = Z[(b * N + n) * K + k];
+      const size_t g = ((b * N + n) * I + i) * K + k;
+      nu = fmaf(z, gnum[g], nu);
+      de = fmaf(z, gden[g], de);
+    }
+    const float r = nu / de;
+    T[e] = ssb_floor(T[e] * (bexp == 0.5f ? sqrtf(r) : bexp == 1.0f ? r : powf(r, bexp)), flooring, eps);
+  }
+}
+
+// V[b,k,j] <- floor(V (sum_n hnum[n,k,j] / sum_n hden[n,k,j])^b), hnum = sum_i z_nk t_ik A (ilrma.py:1174-1202)
+__global__ void k_part_activation(const float* __restrict__ hnum, const float* __restrict__ hden,
+                                  float* __restrict__ V, int N, int K, int J, float bexp, int flooring, float eps,
+                                  size_t total) {
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t kj = e % ((size_t)K * J);
+    const size_t b = e / ((size_t)K * J);
+    float nu = 0.f, de = 0.f;
+    for (int n = 0; n < N; ++n) {
+      const size_t g = (b * N + n) * (size_t)K * J + kj;
+      nu += hnum[g];
+      de += hden[g];
+    }
+    const float r = nu / de;
+    V[e] = ssb_floor(V[e] * (bexp == 0.5f ? sqrtf(r) : bexp == 1.0f ? r : powf(r, bexp)), flooring, eps);
+  }
+}
+
+// power normalisation with the partitioning function (ilrma.py:424-430): Zp = Z / psi^p, scale_k = sum_n Zp,
+// T[:,k] *= scale_k, Z = Zp / scale_k.  One block per mixture.
+__global__ void __launch_bounds__(256) k_part_normalize(const double* __restrict__ psi2, float* __restrict__ Z,
+                                                        float* __restrict__ T, int N, int I, int K, float p,
+                                                        int flooring, double eps) {
+  __shared__ double zp[SSB_MAX_SOURCES * SSB_MAX_BASIS];
+  __shared__ double scale[SSB_MAX_BASIS];
+  const int b = blockIdx.x;
+  for (int pair = threadIdx.x; pair < N * K; pair += blockDim.x) {
+    const int n = pair / K;
+    const double psi = ssb_floor(sqrt(psi2[b * N + n]), flooring, eps);
+    zp[pair] = (double)Z[(size_t)b * N * K + pair] / ((p == 2.0f) ? psi * psi : pow(psi, (double)p));
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    double s = 0.0;
+    for (int n = 0; n < N; ++n) s += zp[n * K + k];
+    scale[k] = s;
+  }
+  __syncthreads();
+  for (int pair = threadIdx.x; pair < N * K; pair += blockDim.x)
+    Z[(size_t)b * N * K + pair] = (float)(zp[pair] / scale[pair % K]);
+  for (int e = threadIdx.x; e < I * K; e += blockDim.x) {
+    float* t = T + (size_t)b * I * K + e;
+    *t = (float)((double)*t * scale[e % K]);
+  }
+}
+
 SrcParam src_param(float p, int source, int model, float prm) {
   SrcParam sp{};
   const bool me = source == SSB_SOURCE_ME;
@@ -439,19 +567,22 @@ SrcParam src_param(float p, int source, int model, float prm) {
 }  // namespace
 
 int ssbk_nmf_basis(const float* P, float* T, const float* V, int BN, int I, int J, int K, float p, int source,
-                   int model, float prm, int flooring, float eps, cudaStream_t st) {
+                   int model, float prm, int flooring, float eps, cudaStream_t st, int vdiv, float* num_out,
+                   float* den_out) {
   const int rows = BN * I;
   const SrcParam sp = src_param(p, source, model, prm);
   SSB_DISPATCH_K(K, k_nmf_basis<KP><<<blocks_for(rows, WPB), WPB * 32, 0, st>>>(P, T, V, rows, I, J, K, sp, flooring,
-                                                                                eps));
+                                                                                eps, vdiv, num_out, den_out));
   return ssb_check_launch("nmf_basis", st);
 }
 
 int ssbk_nmf_activation(const float* P, const float* T, float* V, int BN, int I, int J, int K, float p, int source,
-                        int model, float prm, int flooring, float eps, cudaStream_t st) {
+                        int model, float prm, int flooring, float eps, cudaStream_t st, int vdiv, float* num_out,
+                        float* den_out) {
   const SrcParam sp = src_param(p, source, model, prm);
   dim3 grid((J + 31) / 32, BN);
-  SSB_DISPATCH_K(K, k_nmf_activation<KP><<<grid, ACT_NW * 32, 0, st>>>(P, T, V, I, J, K, sp, flooring, eps));
+  SSB_DISPATCH_K(K, k_nmf_activation<KP><<<grid, ACT_NW * 32, 0, st>>>(P, T, V, I, J, K, sp, flooring, eps, vdiv,
+                                                                       num_out, den_out));
   return ssb_check_launch("nmf_activation", st);
 }
 
@@ -471,19 +602,58 @@ int ssbk_nmf_activation_ab(const float* A, const float* Bm, const float* T, floa
 }
 
 int ssbk_nmf_phi(const float* T, const float* V, const float* P, float* phi, int BN, int I, int J, int K, float p,
-                 int model, float prm, int flooring, float eps, cudaStream_t st) {
+                 int model, float prm, int flooring, float eps, cudaStream_t st, int vdiv) {
   const int rows = BN * I;
   SSB_DISPATCH_K(K, k_nmf_phi<KP><<<blocks_for(rows, WPB), WPB * 32, 0, st>>>(T, V, P, phi, rows, I, J, K, p, model,
-                                                                              prm, flooring, eps));
+                                                                              prm, flooring, eps, vdiv));
   return ssb_check_launch("nmf_phi", st);
 }
 
 int ssbk_nmf_rowloss(const float* P, const float* T, const float* V, double* rowloss, int BN, int I, int J, int K,
-                     float p, int model, float prm, cudaStream_t st) {
+                     float p, int model, float prm, cudaStream_t st, int vdiv) {
   const int rows = BN * I;
   SSB_DISPATCH_K(K, k_nmf_rowloss<KP><<<blocks_for(rows, WPB), WPB * 32, 0, st>>>(P, T, V, rowloss, rows, I, J, K, p,
-                                                                                  model, prm));
+                                                                                  model, prm, vdiv));
   return ssb_check_launch("nmf_rowloss", st);
+}
+
+static int grid_for(size_t total) {
+  size_t blocks = (total + 255) / 256;
+  return (int)(blocks > 148 * 16 ? 148 * 16 : (blocks ? blocks : 1));
+}
+
+int ssbk_part_teff(const float* Z, const float* T, float* Teff, int B, int N, int I, int K, cudaStream_t st) {
+  const size_t total = (size_t)B * N * I * K;
+  k_part_teff<<<grid_for(total), 256, 0, st>>>(Z, T, Teff, N, I, K, total);
+  return ssb_check_launch("part_teff", st);
+}
+
+int ssbk_part_latent(const float* gnum, const float* gden, const float* T, float* Z, int B, int N, int I, int K,
+                     float p, int source, int model, float prm, cudaStream_t st) {
+  k_part_latent<<<B, 256, 0, st>>>(gnum, gden, T, Z, N, I, K, src_param(p, source, model, prm).bexp);
+  return ssb_check_launch("part_latent", st);
+}
+
+int ssbk_part_basis(const float* gnum, const float* gden, const float* Z, float* T, int B, int N, int I, int K, float p,
+                    int source, int model, float prm, int flooring, float eps, cudaStream_t st) {
+  const size_t total = (size_t)B * I * K;
+  k_part_basis<<<grid_for(total), 256, 0, st>>>(gnum, gden, Z, T, N, I, K, src_param(p, source, model, prm).bexp,
+                                                 flooring, eps, total);
+  return ssb_check_launch("part_basis", st);
+}
+
+int ssbk_part_activation(const float* hnum, const float* hden, float* V, int B, int N, int K, int J, float p,
+                         int source, int model, float prm, int flooring, float eps, cudaStream_t st) {
+  const size_t total = (size_t)B * K * J;
+  k_part_activation<<<grid_for(total), 256, 0, st>>>(hnum, hden, V, N, K, J, src_param(p, source, model, prm).bexp,
+                                                      flooring, eps, total);
+  return ssb_check_launch("part_activation", st);
+}
+
+int ssbk_part_normalize(const double* psi2, float* Z, float* T, int B, int N, int I, int K, float p, int flooring,
+                        float eps, cudaStream_t st) {
+  k_part_normalize<<<B, 256, 0, st>>>(psi2, Z, T, N, I, K, p, flooring, (double)eps);
+  return ssb_check_launch("part_normalize", st);
 }
 
 int ssbk_ilrma_loss_reduce(const double* rowloss, const double* logdet, double* loss, int B, int N, int I,
@@ -505,7 +675,7 @@ int ssbk_psi_from_y(const cf* Y, double* psi2, int B, int N, int I, int J, cudaS
 
 int ssbk_apply_psi(const double* psi2, float* T, cf* W, cf* Y, int B, int N, int I, int J, int K, float p,
                    int flooring, float eps, cudaStream_t st) {
-  size_t total = (size_t)B * N * I * K + (W ? (size_t)B * I * N * N : 0) + (Y ? (size_t)B * N * I * J : 0);
+  size_t total = (T ? (size_t)B * N * I * K : 0) + (W ? (size_t)B * I * N * N : 0) + (Y ? (size_t)B * N * I * J : 0);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   k_apply_psi<<<blocks, 256, 0, st>>>(psi2, T, W, Y, B, N, I, J, K, p, flooring, (double)eps);

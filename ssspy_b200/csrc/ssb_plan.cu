@@ -134,6 +134,11 @@ struct ssb_plan {
   float* big2 = nullptr;    // [B,N,I,J] f32 second elementwise scratch (FastGaussMNMF: H)
   cd* qinv = nullptr;       // [B,I,N,N] c128 (FastGaussMNMF separate)
   float* big3 = nullptr;    // [B,N,I,J] f32 Lambda = T V (FastGaussMNMF, tensor-core kernel)
+  // partitioning function: Teff[B,N,I,K] = z t, raw sums of the basis- / activation-type sweeps
+  float* teff = nullptr;
+  float *gnum = nullptr, *gden = nullptr;  // [B,N,I,K]
+  float *hnum = nullptr, *hden = nullptr;  // [B,N,K,J]
+  bool part() const { return cfg.partitioning != 0; }
   bool mnmf() const { return cfg.model == SSB_MODEL_FASTMNMF_GAUSS; }
   bool iss() const { return cfg.spatial == SSB_SPATIAL_ISS1 && !mnmf(); }
   bool ilrma() const {
@@ -174,6 +179,14 @@ size_t carve(ssb_plan* p, char* base) {
   p->psi2 = cv.take<double>(B * N);
   p->rowloss = cv.take<double>(B * N * I);
   p->logdet = cv.take<double>(B * I);
+  if (p->part()) {
+    const size_t K = c.n_basis;
+    p->teff = cv.take<float>(B * N * I * K);
+    p->gnum = cv.take<float>(B * N * I * K);
+    p->gden = cv.take<float>(B * N * I * K);
+    p->hnum = cv.take<float>(B * N * K * J);
+    p->hden = cv.take<float>(B * N * K * J);
+  }
   cv.off += ssb_fused_carve(&p->fused, &c, base ? base + cv.off : nullptr);
   return cv.off;
 }
@@ -209,6 +222,12 @@ int validate(const ssb_config* c) {
                 "domain parameter should be 2 when you specify ME algorithm.");
     SSB_REQUIRE(c->normalization >= 0 && c->normalization <= 2, "Normalization %d is not implemented.",
                 c->normalization);
+  }
+  if (c->partitioning) {
+    SSB_REQUIRE(c->model == SSB_MODEL_ILRMA_GAUSS || c->model == SSB_MODEL_ILRMA_T || c->model == SSB_MODEL_ILRMA_GGD,
+                "the partitioning function is defined for the ILRMA family only");
+    SSB_REQUIRE(c->normalization != SSB_NORM_PROJECTION_BACK,
+                "Projection-back-based normalization is not applicable with partitioning function.");
   }
   SSB_REQUIRE(c->flooring >= 0 && c->flooring <= 2, "unknown flooring mode %d", c->flooring);
   SSB_REQUIRE(c->reference_id >= 0 && c->reference_id < c->n_sources, "reference_id=%d out of range",
@@ -253,9 +272,33 @@ int logdets(ssb_plan* p, cudaStream_t st) {
   return ssbk_logdet(W, p->logdet, c.n_batch * c.n_bins, c.n_sources, st);
 }
 
+// partitioning function: latent, basis, activation in this order, each from a fresh sweep over P with the
+// model R_n = Teff_n V (ilrma.py:972-975)
+int ilrma_source_part(ssb_plan* p, cudaStream_t st) {
+  const ssb_config& c = p->cfg;
+  const int B = c.n_batch, N = c.n_sources, I = c.n_bins, J = c.n_frames, K = c.n_basis;
+  float* Z = p->variance;
+  TRY(power_spectrogram(p, st));
+  TRY(ssbk_part_teff(Z, p->T, p->teff, B, N, I, K, st));
+  TRY(ssbk_nmf_basis(p->big, p->teff, p->V, B * N, I, J, K, c.domain, c.source, c.model, c.model_param, c.flooring,
+                     c.eps, st, N, p->gnum, p->gden));
+  TRY(ssbk_part_latent(p->gnum, p->gden, p->T, Z, B, N, I, K, c.domain, c.source, c.model, c.model_param, st));
+  TRY(ssbk_part_teff(Z, p->T, p->teff, B, N, I, K, st));
+  TRY(ssbk_nmf_basis(p->big, p->teff, p->V, B * N, I, J, K, c.domain, c.source, c.model, c.model_param, c.flooring,
+                     c.eps, st, N, p->gnum, p->gden));
+  TRY(ssbk_part_basis(p->gnum, p->gden, Z, p->T, B, N, I, K, c.domain, c.source, c.model, c.model_param, c.flooring,
+                      c.eps, st));
+  TRY(ssbk_part_teff(Z, p->T, p->teff, B, N, I, K, st));
+  TRY(ssbk_nmf_activation(p->big, p->teff, p->V, B * N, I, J, K, c.domain, c.source, c.model, c.model_param,
+                          c.flooring, c.eps, st, N, p->hnum, p->hden));
+  return ssbk_part_activation(p->hnum, p->hden, p->V, B, N, K, J, c.domain, c.source, c.model, c.model_param,
+                              c.flooring, c.eps, st);
+}
+
 int ilrma_source(ssb_plan* p, cudaStream_t st) {
   const ssb_config& c = p->cfg;
   const int BN = c.n_batch * c.n_sources;
+  if (p->part()) return ilrma_source_part(p, st);
   TRY(power_spectrogram(p, st));
   TRY(ssbk_nmf_basis(p->big, p->T, p->V, BN, c.n_bins, c.n_frames, c.n_basis, c.domain, c.source, c.model,
                      c.model_param, c.flooring, c.eps, st));
@@ -269,8 +312,9 @@ int ilrma_spatial(ssb_plan* p, cudaStream_t st) {
   const int B = c.n_batch, N = c.n_sources, I = c.n_bins, J = c.n_frames;
   // the Student-t / GGD weights depend on the current power spectrogram (ilrma.py:2920-2934, :3992-4010)
   if (c.model != SSB_MODEL_ILRMA_GAUSS) TRY(power_spectrogram(p, st));
-  TRY(ssbk_nmf_phi(p->T, p->V, p->big, p->big, B * N, I, J, c.n_basis, c.domain, c.model, c.model_param, c.flooring,
-                   c.eps, st));
+  if (p->part()) TRY(ssbk_part_teff(p->variance, p->T, p->teff, B, N, I, c.n_basis, st));
+  TRY(ssbk_nmf_phi(p->part() ? p->teff : p->T, p->V, p->big, p->big, B * N, I, J, c.n_basis, c.domain, c.model,
+                   c.model_param, c.flooring, c.eps, st, p->part() ? N : 1));
   const long long sb = (long long)N * I * J, sn = (long long)I * J, si = J;
   if (c.spatial == SSB_SPATIAL_ISS1) return ssbk_iss1(p->Y, p->big, sb, sn, si, B, N, I, J, c.flooring, c.eps, st);
   TRY(ssbk_wcov(p->X, p->big, sb, sn, si, nullptr, N, p->U, B, N, I, J, st));
@@ -282,13 +326,18 @@ int ilrma_normalize(ssb_plan* p, cudaStream_t st) {
   const ssb_config& c = p->cfg;
   const int B = c.n_batch, N = c.n_sources, I = c.n_bins, J = c.n_frames, K = c.n_basis;
   if (c.normalization == SSB_NORM_POWER) {
+    // partitioning: psi rescales Z and T through k_part_normalize (ilrma.py:424-430), not T[n] directly
+    float* Tn = p->part() ? nullptr : p->T;
     if (p->iss()) {
       TRY(ssbk_psi_from_y(p->Y, p->psi2, B, N, I, J, st));
-      return ssbk_apply_psi(p->psi2, p->T, nullptr, p->Y, B, N, I, J, K, c.domain, c.flooring, c.eps, st);
+      TRY(ssbk_apply_psi(p->psi2, Tn, nullptr, p->Y, B, N, I, J, K, c.domain, c.flooring, c.eps, st));
+    } else {
+      SSB_REQUIRE(p->prepared, "plan not prepared (call ssb_plan_prepare after bind)");
+      TRY(ssbk_psi_from_cov(p->W, p->C, p->psi2, B, N, I, st));
+      TRY(ssbk_apply_psi(p->psi2, Tn, p->W, nullptr, B, N, I, J, K, c.domain, c.flooring, c.eps, st));
     }
-    SSB_REQUIRE(p->prepared, "plan not prepared (call ssb_plan_prepare after bind)");
-    TRY(ssbk_psi_from_cov(p->W, p->C, p->psi2, B, N, I, st));
-    return ssbk_apply_psi(p->psi2, p->T, p->W, nullptr, B, N, I, J, K, c.domain, c.flooring, c.eps, st);
+    if (p->part()) return ssbk_part_normalize(p->psi2, p->variance, p->T, B, N, I, K, c.domain, c.flooring, c.eps, st);
+    return 0;
   }
   if (c.normalization == SSB_NORM_PROJECTION_BACK) {
     if (p->iss()) {
@@ -307,7 +356,9 @@ int ilrma_loss(ssb_plan* p, double* loss, cudaStream_t st) {
   const int B = c.n_batch, N = c.n_sources, I = c.n_bins, J = c.n_frames;
   TRY(power_spectrogram(p, st));
   TRY(logdets(p, st));
-  TRY(ssbk_nmf_rowloss(p->big, p->T, p->V, p->rowloss, B * N, I, J, c.n_basis, c.domain, c.model, c.model_param, st));
+  if (p->part()) TRY(ssbk_part_teff(p->variance, p->T, p->teff, B, N, I, c.n_basis, st));
+  TRY(ssbk_nmf_rowloss(p->big, p->part() ? p->teff : p->T, p->V, p->rowloss, B * N, I, J, c.n_basis, c.domain, c.model,
+                       c.model_param, st, p->part() ? N : 1));
   return ssbk_ilrma_loss_reduce(p->rowloss, p->logdet, loss, B, N, I, st);
 }
 
@@ -446,6 +497,7 @@ extern "C" int ssb_plan_bind(ssb_plan* p, const void* X, void* W, void* Y, void*
   SSB_REQUIRE(!(p->ilrma() || p->mnmf()) || (T != nullptr && V != nullptr), "T and V must be bound for ILRMA / MNMF");
   SSB_REQUIRE(p->cfg.model != SSB_MODEL_IVA_GAUSS || variance != nullptr, "variance must be bound for AuxGaussIVA");
   SSB_REQUIRE(!p->mnmf() || variance != nullptr, "spatial (D) must be bound in the variance slot for FastGaussMNMF");
+  SSB_REQUIRE(!p->part() || variance != nullptr, "latent (Z) must be bound in the variance slot with partitioning");
   size_t need = 0;
   TRY(ssb_plan_workspace_bytes(p, &need));
   SSB_REQUIRE(workspace != nullptr && workspace_bytes >= need, "workspace too small: %zu < %zu bytes", workspace_bytes,

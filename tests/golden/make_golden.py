@@ -41,10 +41,17 @@ def rand_w(rng, I, N):
 
 def ilrma_case(name, N, I, J, K, n_iter, spatial="IP", source="MM", domain=2, normalization=True,
                flooring="max", reference_id=0, scale_restoration=True, pairs=None, w_init=False, seed=0,
-               dist="gauss", dist_param=0.0):
+               dist="gauss", dist_param=0.0, partitioning=False):
     X = make_mixture(N, I, J, seed=seed, mode="mix")
     T, V = make_nmf_init(N, I, J, K, seed=42 + seed)
     kwargs = dict(basis=T, activation=V)
+    Z0 = None
+    if partitioning:  # shared T[I,K], V[K,J] + latent Z[N,K] with unit column sums (ilrma.py:219-245)
+        prng = np.random.default_rng(99 + seed)
+        Z0 = prng.random((N, K)) + 0.1
+        Z0 = Z0 / Z0.sum(axis=0)
+        T, V = T[0].copy(), V[0].copy()
+        kwargs = dict(basis=T, activation=V, latent=Z0)
     rng = np.random.default_rng(7 + seed)
     W0 = rand_w(rng, I, N) if w_init else None
     if W0 is not None:
@@ -60,6 +67,7 @@ def ilrma_case(name, N, I, J, K, n_iter, spatial="IP", source="MM", domain=2, no
     elif pairs == "sequential_sorted":
         sel = functools.partial(sequential_pair_selector, sort=True)
     common = dict(spatial_algorithm=spatial, source_algorithm=source, domain=domain, flooring_fn=FLOOR[flooring],
+                  partitioning=partitioning,
                   pair_selector=sel, callbacks=cb, normalization=normalization, scale_restoration=scale_restoration,
                   record_loss=True, reference_id=reference_id, rng=np.random.default_rng(0))
     if dist == "t":
@@ -78,6 +86,8 @@ def ilrma_case(name, N, I, J, K, n_iter, spatial="IP", source="MM", domain=2, no
                scale_restoration=scale_restoration, pairs=pair_list, dist=dist, dist_param=float(dist_param))
     if W0 is not None:
         out["W0"] = W0
+    if partitioning:
+        out["Z0"], out["Z"] = Z0, m.latent
     if m.demix_filter is not None:
         out["W"] = m.demix_filter
         out["W_first_iter"] = snaps[1][0]
@@ -104,6 +114,8 @@ def iva_case(name, N, I, J, n_iter, model="laplace", spatial="IP", flooring="max
                pairs=pair_list)
     if W0 is not None:
         out["W0"] = W0
+    if partitioning:
+        out["Z0"], out["Z"] = Z0, m.latent
     if m.demix_filter is not None:
         out["W"] = m.demix_filter
     if model == "gauss":
@@ -216,6 +228,18 @@ def tggd_cases():
                dist_param=1.0, seed=38)
 
 
+def partitioning_cases():
+    """partitioning=True (latent Z; ilrma.py:201-245, :1007-1049, :1098-1113, :1174-1189, :424-430)."""
+    ilrma_case("ilrma_part_ip1_mm", 3, 17, 23, 4, 5, partitioning=True, seed=40)
+    ilrma_case("ilrma_part_ip2_me_n2", 2, 21, 30, 5, 5, spatial="IP2", source="ME", partitioning=True, seed=41)
+    ilrma_case("ilrma_part_iss1_p1", 3, 17, 23, 4, 5, spatial="ISS", domain=1, partitioning=True, seed=42)
+    ilrma_case("ilrma_part_ip1_nonorm", 4, 12, 40, 6, 4, normalization=False, partitioning=True, seed=43)
+    ilrma_case("tilrma_part_ip1_mm", 3, 17, 23, 4, 5, dist="t", dist_param=4.0, partitioning=True, seed=44)
+    ilrma_case("tilrma_part_iss1_me", 3, 17, 23, 4, 5, spatial="ISS", source="ME", dist="t", dist_param=20.0,
+               partitioning=True, seed=45)
+    ilrma_case("ggdilrma_part_ip1_b1", 3, 17, 23, 4, 5, dist="ggd", dist_param=1.0, partitioning=True, seed=46)
+
+
 def mdp_cases():
     """minimal_distortion_principle standalone + as scale_restoration of GaussILRMA / AuxLaplaceIVA."""
     from ssspy.algorithm import minimal_distortion_principle
@@ -237,6 +261,7 @@ def main():
     kernel_cases()
     mdp_cases()
     tggd_cases()
+    partitioning_cases()
     # GaussILRMA: spatial x source x domain x normalisation x flooring grid (regression-test pattern,
     # tests/regression/bss/test_ilrma.py:48-62: inject basis/activation, fixed n_iter, compare).
     ilrma_case("ilrma_ip1_mm_n2", 2, 33, 40, 4, 10)

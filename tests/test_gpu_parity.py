@@ -54,7 +54,7 @@ def _make_ilrma(g, **over):
               domain=float(g["domain"]), flooring_fn=_floor_fn(str(g["flooring"])),
               pair_selector=_pair_selector(g["pairs"]) if spatial == "IP2" else None,
               normalization=norm_arg(g["normalization"]), scale_restoration=sr_arg(g["scale_restoration"]),
-              record_loss=True, reference_id=ref_id, rng=np.random.default_rng(0))
+              record_loss=True, reference_id=ref_id, rng=np.random.default_rng(0), partitioning="Z0" in g)
     kw.update(over)
     kind, prm = dist_arg(g)
     if kind == "t":
@@ -70,6 +70,8 @@ def test_gauss_ilrma_matches_reference(name):
     kwargs = dict(basis=g["T0"], activation=g["V0"])
     if "W0" in g:
         kwargs["demix_filter"] = g["W0"]
+    if "Z0" in g:
+        kwargs["latent"] = g["Z0"]
     spatial = str(g["spatial"])
     m = _make_ilrma(g)
     Y = m(g["X"], n_iter=int(g["n_iter"]), **kwargs)
@@ -82,6 +84,9 @@ def test_gauss_ilrma_matches_reference(name):
         assert relerr(np.abs(Y), np.abs(g["Y"])) < TOL_Y
     assert relerr(m.basis, g["T"]) < TOL_TV
     assert relerr(m.activation, g["V"]) < TOL_TV
+    if "Z" in g:
+        assert m.latent.shape == g["Z"].shape and relerr(m.latent, g["Z"]) < TOL_TV
+        np.testing.assert_allclose(m.latent.sum(axis=0), 1.0, rtol=1e-5)
     if "W" in g:
         # the contract is on Y; W is c64 state and is checked with a looser bound (N = 8 IP2 on 9 bins is
         # the worst-conditioned fixture: 1.2e-4)
@@ -517,3 +522,40 @@ def test_t_and_ggd_ilrma_batched_vs_oracle(kind, prm, spatial, source, domain):
         assert relerr(Y[b], st["Y"]) < tol_seeded(spatial)
         # T carries psi^p of the normalisation, i.e. twice the relative error of W (the contract is on Y)
         assert relerr(m.basis[b], st["T"]) < 3 * tol_seeded(spatial)
+
+
+@pytest.mark.parametrize("spatial,source", [("IP", "MM"), ("ISS", "ME"), ("IP2", "MM")])
+def test_partitioning_batched_rng_and_manual_phases(spatial, source):
+    """partitioning=True on batched input: latent / basis / activation drawn from the caller's Generator in the
+    reference's order (ilrma.py:219-245) per mixture, result equal to the per-mixture oracle, and the manual
+    update_source_model / update_spatial_model / normalize sequence equal to update_once."""
+    from oracle import ilrma as oilrma
+    from ssspy_b200.bss import GaussILRMA
+    from ssspy_b200.utils.synth import make_batch
+    B, N, I, J, K, n_iter = 2, 3, 25, 64, 5, 4
+    X = make_batch(B, N, I, J, config_id=13, mode="mix")
+    m = GaussILRMA(n_basis=K, spatial_algorithm=spatial, source_algorithm=source, partitioning=True,
+                   rng=np.random.default_rng(77))
+    Y = m(X, n_iter=n_iter)
+    rng = np.random.default_rng(77)
+    for b in range(B):
+        Z0 = rng.random((N, K))
+        Z0 = np.maximum(Z0 / Z0.sum(axis=0), 1e-10)
+        T0 = np.maximum(rng.random((I, K)), 1e-10)
+        V0 = np.maximum(rng.random((K, J)), 1e-10)
+        st = oilrma.run(X[b], T0, V0, n_iter, spatial_algorithm=spatial, source_algorithm=source, Z=Z0)
+        assert relerr(Y[b], st["Y"]) < tol_seeded(spatial)
+        assert relerr(m.latent[b], st["Z"]) < 3 * tol_seeded(spatial)
+        np.testing.assert_allclose(np.asarray(m.loss)[:, b], st["loss"], rtol=2e-5 if spatial != "IP2" else 1e-3,
+                                   atol=1e-4)
+    assert m.basis.shape == (B, I, K) and m.activation.shape == (B, K, J) and m.latent.shape == (B, N, K)
+    m2 = GaussILRMA(n_basis=K, spatial_algorithm=spatial, source_algorithm=source, partitioning=True,
+                    scale_restoration=False, rng=np.random.default_rng(77))
+    m2(X, n_iter=0)
+    for _ in range(n_iter):
+        m2.update_source_model()
+        m2.update_spatial_model()
+        m2.normalize()
+    np.testing.assert_allclose(np.asarray(m2.compute_loss()), np.asarray(m.loss)[-1], rtol=1e-6)
+    with pytest.raises(NotImplementedError, match="not applicable with partitioning"):
+        m2.normalize_by_projection_back()

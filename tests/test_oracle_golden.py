@@ -22,7 +22,10 @@ def test_ilrma_oracle_matches_reference(name):
                     floor=FLOORS[str(g["flooring"])], spatial_algorithm=str(g["spatial"]),
                     source_algorithm=str(g["source"]), normalization=norm_arg(g["normalization"]),
                     pairs=[tuple(p) for p in g["pairs"]], reference_id=ref_id,
-                    scale_restoration=sr_arg(g["scale_restoration"]), snapshots=True, dist=dist_arg(g))
+                    scale_restoration=sr_arg(g["scale_restoration"]), snapshots=True, dist=dist_arg(g),
+                    Z=g.get("Z0"))
+    if "Z" in g:
+        assert relerr(st["Z"], g["Z"]) < TOL
     assert relerr(st["Y"], g["Y"]) < TOL
     assert relerr(st["T"], g["T"]) < TOL
     assert relerr(st["V"], g["V"]) < TOL
