@@ -50,7 +50,8 @@ enum {
                              (MM only, IP1 / IP2 / ISS1) */
 };
 /* spatial_algorithm (ssspy/bss/ilrma.py:27, ssspy/bss/iva.py:44) */
-enum { SSB_SPATIAL_IP1 = 0, SSB_SPATIAL_IP2 = 1, SSB_SPATIAL_ISS1 = 2 };
+enum { SSB_SPATIAL_IP1 = 0, SSB_SPATIAL_IP2 = 1, SSB_SPATIAL_ISS1 = 2,
+       SSB_SPATIAL_ISS2 = 3 /* pairwise ISS, ssspy/bss/_update_spatial_model.py:197-314; uses `pairs` */ };
 /* source_algorithm (ssspy/bss/ilrma.py:28) */
 enum { SSB_SOURCE_MM = 0, SSB_SOURCE_ME = 1 };
 /* flooring_fn (ssspy/special/flooring.py:6-18): max(x,eps) | x+eps | identity */
@@ -166,6 +167,10 @@ int ssb_update_by_ip2_one_pair(void* W, const void* U_pair, int n_mat, int N, in
  * ssb_weighted_covariance */
 int ssb_update_by_iss1(void* Y, const float* phi, long long phi_sb, long long phi_sn, long long phi_si,
                        int B, int N, int I, int J, int flooring, float eps, void* stream);
+/* update_by_iss2 (_update_spatial_model.py:197-314): pairwise ISS on Y[B,N,I,J] in place; pairs[2*n_pairs] on the host,
+ * indices already wrapped into [0, N) (the reference's default is (0,1),(2,3),..., :233-234) */
+int ssb_update_by_iss2(void* Y, const float* phi, long long phi_sb, long long phi_sn, long long phi_si, int B, int N,
+                       int I, int J, const int32_t* pairs, int n_pairs, int flooring, float eps, void* stream);
 /* projection_back, filter form (ssspy/algorithm/projection_back.py:87-99):
  * Wout[m,n,:] = W[m,n,:] * (W[m]^-1)[ref, n]; Wout may alias W. */
 int ssb_projection_back_w(const void* W, void* Wout, int n_mat, int N, int reference_id, void* stream);

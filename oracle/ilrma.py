@@ -27,7 +27,7 @@ def init_state(X, T, V, W=None, spatial_algorithm="IP", Z=None):
               T=T.astype(np.float64).copy(), V=V.astype(np.float64).copy())
     st["Y"] = separate(st["X"], st["W"])
     st["Z"] = None if Z is None else Z.astype(np.float64).copy()
-    if spatial_algorithm in ("ISS", "ISS1"):
+    if spatial_algorithm in ("ISS", "ISS1", "ISS2"):
         st["W"] = None
     return st
 
@@ -122,6 +122,9 @@ def update_spatial(st, p=2, floor=spatial.max_flooring, spatial_algorithm="IP", 
         st["W"] = spatial.update_by_ip2(st["W"], spatial.weighted_covariance(st["X"], phi), floor, pairs)
     elif spatial_algorithm in ("ISS", "ISS1"):
         st["Y"] = spatial.update_by_iss1(st["Y"], phi, floor)
+    elif spatial_algorithm == "ISS2":  # ilrma.py:1698-1811; class default = all sequential pairs
+        st["Y"] = spatial.update_by_iss2(st["Y"], phi, floor, pairs if pairs is not None else
+                                         spatial.sequential_pairs(st["Y"].shape[0]))
     else:
         raise NotImplementedError(spatial_algorithm)
 

@@ -18,7 +18,7 @@ def init_state(X, W=None, spatial_algorithm="IP", model="laplace"):
         W = np.tile(np.eye(N, dtype=np.complex128), (I, 1, 1))
     st = dict(X=X.astype(np.complex128), W=W.astype(np.complex128).copy())
     st["Y"] = separate(st["X"], st["W"])
-    if spatial_algorithm in ("ISS", "ISS1"):
+    if spatial_algorithm in ("ISS", "ISS1", "ISS2"):
         st["W"] = None
     if model == "gauss":
         st["variance"] = np.ones((N, J))  # ssspy/bss/iva.py:3317
@@ -59,6 +59,11 @@ def update_once(st, floor=spatial.max_flooring, spatial_algorithm="IP", model="l
         r = np.linalg.norm(st["Y"], axis=1)
         phi = _weight(r, floor, model, var)
         st["Y"] = spatial.update_by_iss1(st["Y"], phi[:, np.newaxis, :], floor)
+    elif spatial_algorithm == "ISS2":  # iva.py:1968-2066: weights once, then all pairs
+        r = np.linalg.norm(st["Y"], axis=1)
+        phi = _weight(r, floor, model, var)
+        st["Y"] = spatial.update_by_iss2(st["Y"], phi[:, np.newaxis, :], floor, pairs if pairs is not None else
+                                         spatial.sequential_pairs(st["Y"].shape[0]))
     else:
         raise NotImplementedError(spatial_algorithm)
 

@@ -123,3 +123,41 @@ def update_by_iss1(Y, phi, floor=max_flooring):
         v[n] = 1 - 1 / np.sqrt(den[n])
         Y = Y - v[:, :, np.newaxis] * Yn
     return Y
+
+
+def update_by_iss2(Y, phi, floor=max_flooring, pairs=None):
+    """Pairwise iterative source steering (ssspy/bss/_update_spatial_model.py:197-314).  For every pair (m, n), with
+    u = (y_m, y_n) of the *current* Y (pair order as given, :241-261):
+      other sources s: G_s = mean_j phi_s u u^H, f_s = mean_j phi_s u conj(y_s), q_s = -G_s^-1 f_s,
+                       y_s <- y_s + q_s^H u                                            (:263-283)
+      pair: G_m h = l G_n h (ascending, NOT flipped, :288-290); a = 0 -> (h_0, G_m), a = 1 -> (h_1, G_n);
+            p_a = h_a / floor(sqrt(max(Re h_a^H G_a h_a, 0))); y_a <- p_a^H u           (:291-303)
+    Default pairs: (0,1), (2,3), ... (sequential selector with step 2, :233-234).  phi broadcastable to (N,I,J)."""
+    from .linalg import eigh2, inv2
+    Y = Y.copy()
+    N = Y.shape[0]
+    phi = np.broadcast_to(phi, Y.shape)
+    if pairs is None:
+        pairs = sequential_pairs(N, stop=N, step=2)
+    for m, n in pairs:
+        m, n = m % N, n % N
+        u = np.stack([Y[m], Y[n]], axis=0)                                   # (2, I, J)
+        uu = (u[:, None] * u[None].conj()).transpose(2, 0, 1, 3)               # (I, 2, 2, J)
+        new = Y.copy()
+        for s in range(N):
+            if s in (m, n):
+                continue
+            G = np.mean(phi[s][:, None, None, :] * uu, axis=-1)               # (I, 2, 2)
+            f = np.mean(phi[s][:, None, :] * (u * Y[s].conj()[None]).transpose(1, 0, 2), axis=-1)  # (I, 2)
+            q = -(inv2(G) @ f[..., None])[..., 0]
+            new[s] = Y[s] + np.einsum("ic,cij->ij", q.conj(), u)
+        Gm = np.mean(phi[m][:, None, None, :] * uu, axis=-1)
+        Gn = np.mean(phi[n][:, None, None, :] * uu, axis=-1)
+        _, H = eigh2(Gm, Gn)
+        for a, (G, dst) in enumerate(((Gm, m), (Gn, n))):
+            h = H[..., a]
+            d = floor(np.sqrt(np.maximum(np.real(np.einsum("ia,iab,ib->i", h.conj(), G, h)), 0)))
+            pa = h / d[:, None]
+            new[dst] = np.einsum("ic,cij->ij", pa.conj(), u)
+        Y = new
+    return Y

@@ -15,7 +15,7 @@ SSB_MAX_PAIRS = 64
 
 MODEL_ILRMA_GAUSS, MODEL_IVA_LAPLACE, MODEL_IVA_GAUSS, MODEL_FASTMNMF_GAUSS = 0, 1, 2, 3
 MODEL_ILRMA_T, MODEL_ILRMA_GGD = 4, 5
-SPATIAL_IP1, SPATIAL_IP2, SPATIAL_ISS1 = 0, 1, 2
+SPATIAL_IP1, SPATIAL_IP2, SPATIAL_ISS1, SPATIAL_ISS2 = 0, 1, 2, 3
 SOURCE_MM, SOURCE_ME = 0, 1
 FLOOR_MAX, FLOOR_ADD, FLOOR_NONE = 0, 1, 2
 NORM_NONE, NORM_POWER, NORM_PROJECTION_BACK = 0, 1, 2
@@ -65,6 +65,7 @@ SIGNATURES = {
     "ssb_update_by_ip2": [_vp, _vp, _i, _i, _i32p, _i, _i, _f, _vp],
     "ssb_update_by_ip2_one_pair": [_vp, _vp, _i, _i, _i, _i, _i, _f, _vp],
     "ssb_update_by_iss1": [_vp, _vp, _ll, _ll, _ll, _i, _i, _i, _i, _i, _f, _vp],
+    "ssb_update_by_iss2": [_vp, _vp, _ll, _ll, _ll, _i, _i, _i, _i, _i32p, _i, _i, _f, _vp],
     "ssb_projection_back_w": [_vp, _vp, _i, _i, _i, _vp],
     "ssb_projection_back_y": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "ssb_inv": [_vp, _vp, _i, _i, _vp],

@@ -1,6 +1,6 @@
 """Standalone spatial-update operators on the device (host mirror of
 ssspy/bss/_update_spatial_model.py: update_by_ip1 :17-78, update_by_ip2 :81-143,
-update_by_ip2_one_pair :317-395, update_by_iss1 :146-194).
+update_by_ip2_one_pair :317-395, update_by_iss1 :146-194, update_by_iss2 :197-314).
 
 Same argument meaning as the reference; leading batch axes are allowed.  NumPy in -> NumPy
 (complex128) out, CUDA tensors in -> CUDA tensors out.  ``overwrite=True`` writes the result back
@@ -91,6 +91,35 @@ def update_by_iss1(separated, weight, flooring_fn=_DEFAULT_FLOOR):
         sb, sn, si = N * I * J, I * J, J
     _lib.call("ssb_update_by_iss1", Yb.data_ptr(), phi.data_ptr(), sb, sn, si, B, N, I, J, mode, eps,
               _device.stream_ptr())
+    if _device.is_tensor(separated):
+        return Y.to(separated.dtype)
+    return Y.cpu().numpy().astype(np.complex128)
+
+
+def update_by_iss2(separated, weight, flooring_fn=_DEFAULT_FLOOR, pair_selector=None):
+    """Pairwise iterative source steering (ssspy/bss/_update_spatial_model.py:197-314).  ``separated`` (N, I, J) [or
+    (B, N, I, J)], ``weight`` broadcastable to its shape; the default selector yields (0, 1), (2, 3), ...
+    (``sequential_pair_selector(N, stop=N, step=2)``, :233-234); negative indices wrap as in the reference."""
+    mode, eps = flooring_to_enum(flooring_fn)
+    Y = _device.to_device(separated, torch.complex64).clone()
+    batched = Y.dim() == 4
+    Yb = Y if batched else Y.unsqueeze(0)
+    B, N, I, J = Yb.shape
+    if pair_selector is None:
+        pair_selector = functools.partial(sequential_pair_selector, stop=N, step=2)
+    pairs = wrap_pairs(pair_selector(N), N)
+    phi = _device.to_device(weight, torch.float32)
+    phi = phi if batched else phi.unsqueeze(0)
+    if phi.shape[-2] == 1:
+        phi = phi.expand(B, N, 1, J).contiguous()
+        sb, sn, si = N * J, J, 0
+    else:
+        phi = phi.expand(B, N, I, J).contiguous()
+        sb, sn, si = N * I * J, I * J, J
+    for q0 in range(0, len(pairs), _lib.SSB_MAX_PAIRS):
+        chunk = pairs[q0:q0 + _lib.SSB_MAX_PAIRS]
+        _lib.call("ssb_update_by_iss2", Yb.data_ptr(), phi.data_ptr(), sb, sn, si, B, N, I, J,
+                  _lib.pairs_array(chunk), len(chunk), mode, eps, _device.stream_ptr())
     if _device.is_tensor(separated):
         return Y.to(separated.dtype)
     return Y.cpu().numpy().astype(np.complex128)

@@ -5,9 +5,9 @@ GaussILRMA :582-1989, TILRMA :1992-3334, GGDILRMA :3337-4410).  Same constructor
 (``basis``, ``activation``, ``latent``, ``demix_filter``, ``output``, ``loss``); all arithmetic runs in
 libssb.so's CUDA kernels.
 
-Covered: spatial_algorithm IP / IP1 / IP2 / ISS / ISS1, source_algorithm MM / ME, any ``domain`` in (0, 2],
+Covered: spatial_algorithm IP / IP1 / IP2 / ISS / ISS1 / ISS2, source_algorithm MM / ME, any ``domain`` in (0, 2],
 ``partitioning`` False / True (latent variable Z), normalization True / "power" / "projection_back" / False,
-projection-back and minimal-distortion-principle scale restoration.  ISS2 and IPA raise NotImplementedError
+projection-back and minimal-distortion-principle scale restoration, ISS2 included.  IPA raises NotImplementedError
 (no CPU fallback).
 """
 import ctypes
@@ -31,7 +31,7 @@ PROJECTION_BACK_KEYWORDS = ["projection_back", "projection-back", "PB"]
 MINIMAL_DISTORTION_PRINCIPLE_KEYWORDS = ["minimal_distortion_principle", "minimal-distortion-principle", "MDP"]
 
 _SPATIAL_ENUM = {"IP": _lib.SPATIAL_IP1, "IP1": _lib.SPATIAL_IP1, "IP2": _lib.SPATIAL_IP2,
-                 "ISS": _lib.SPATIAL_ISS1, "ISS1": _lib.SPATIAL_ISS1}
+                 "ISS": _lib.SPATIAL_ISS1, "ISS1": _lib.SPATIAL_ISS1, "ISS2": _lib.SPATIAL_ISS2}
 
 
 def _not_on_device(what):
@@ -182,7 +182,7 @@ class ILRMABase(DeviceSeparatorMixin, IterativeMethodBase):
             raise NotImplementedError("Normalization {} is not implemented.".format(norm))
         cfg.reference_id = 0 if self.reference_id is None else int(self.reference_id)
         pairs = []
-        if cfg.spatial == _lib.SPATIAL_IP2:
+        if cfg.spatial in (_lib.SPATIAL_IP2, _lib.SPATIAL_ISS2):
             pairs = wrap_pairs(self.pair_selector(N), N)
             if len(pairs) > _lib.SSB_MAX_PAIRS:
                 raise NotImplementedError("more than {} pairs per iteration".format(_lib.SSB_MAX_PAIRS))
@@ -377,6 +377,11 @@ class _DeviceILRMA(ILRMABase):
 
     def update_spatial_model_iss1(self, flooring_fn="self"):
         assert self.spatial_algorithm in ["ISS", "ISS1"]
+        self.update_spatial_model(flooring_fn=flooring_fn)
+
+    def update_spatial_model_iss2(self, flooring_fn="self"):
+        """Pairwise ISS over ``pair_selector(n_sources)`` (ilrma.py:1698-1811)."""
+        assert self.spatial_algorithm == "ISS2"
         self.update_spatial_model(flooring_fn=flooring_fn)
 
     def compute_loss(self):

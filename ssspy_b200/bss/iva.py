@@ -1,7 +1,7 @@
 """Auxiliary-function IVA on the device (host mirror of ssspy/bss/iva.py: IVABase :48-281,
 AuxIVABase :553-641, AuxIVA :1403-2214, AuxLaplaceIVA :2976-3128, AuxGaussIVA :3131-3473).
 
-Covered: spatial_algorithm IP / IP1 / IP2 / ISS / ISS1 with the Laplace and Gauss contrasts.  The
+Covered: spatial_algorithm IP / IP1 / IP2 / ISS / ISS1 / ISS2 with the Laplace and Gauss contrasts.  The
 contrast functions are arbitrary Python callables in the reference; on the device they are an
 enum, so the generic ``AuxIVA`` accepts only the two known contrasts (no CPU fallback).
 """
@@ -188,7 +188,7 @@ class AuxIVA(AuxIVABase):
         cfg.normalization = _lib.NORM_NONE
         cfg.reference_id = 0 if self.reference_id is None else int(self.reference_id)
         pairs = []
-        if cfg.spatial == _lib.SPATIAL_IP2:
+        if cfg.spatial in (_lib.SPATIAL_IP2, _lib.SPATIAL_ISS2):
             pairs = wrap_pairs(self.pair_selector(N), N)
             if len(pairs) > _lib.SSB_MAX_PAIRS:
                 raise NotImplementedError("more than {} pairs per iteration".format(_lib.SSB_MAX_PAIRS))
@@ -219,6 +219,11 @@ class AuxIVA(AuxIVABase):
 
     def update_once_iss1(self, flooring_fn="self"):
         assert self.spatial_algorithm in ["ISS", "ISS1"]
+        AuxIVA.update_once(self, flooring_fn=flooring_fn)
+
+    def update_once_iss2(self, flooring_fn="self"):
+        """Pairwise ISS over ``pair_selector(n_sources)`` with weights from the current output (iva.py:1968-2066)."""
+        assert self.spatial_algorithm == "ISS2"
         AuxIVA.update_once(self, flooring_fn=flooring_fn)
 
 

@@ -199,6 +199,37 @@ __device__ __forceinline__ void herm_eig2(double c00, double c11, cd c01, double
   y0[1] = cd_conj(a0);
 }
 
+// Generalised 2x2 Hermitian eigenproblem Gm h = l Gn h (row-major 2x2 inputs), ssspy/linalg/eigh.py:173-201:
+// h_small / h_large are the eigenvectors of the smaller / larger eigenvalue (z = L^-H y, Gn = L L^H).
+__device__ __forceinline__ void gen_eig2(const cd* Gm, const cd* Gn, cd* h_small, cd* h_large) {
+  const double b00 = Gn[0].x, b11 = Gn[3].x;
+  const cd b10 = Gn[2];
+  const double l00 = sqrt(b00);
+  const cd l10 = cd_scale(b10, 1.0 / l00);
+  const double l11 = sqrt(b11 - cd_abs2(l10));
+  const double i00 = 1.0 / l00, i11 = 1.0 / l11;
+  const cd i10 = cd_scale(l10, -i00 * i11);
+  const double a00 = Gm[0].x, a11 = Gm[3].x;
+  const cd a01 = Gm[1];
+  const double c00 = i00 * a00 * i00;
+  const cd c01 = cd_add(cd_scale(cd_conj(i10), i00 * a00), cd_scale(a01, i00 * i11));
+  const double c11 = cd_abs2(i10) * a00 + 2.0 * i11 * cd_mul(i10, a01).x + i11 * i11 * a11;
+  double lam[2];
+  cd y0[2], y1[2];
+  herm_eig2(c00, c11, c01, lam, y0, y1);
+  h_large[0] = cd_add(cd_scale(y1[0], i00), cd_mul(cd_conj(i10), y1[1]));
+  h_large[1] = cd_scale(y1[1], i11);
+  h_small[0] = cd_add(cd_scale(y0[0], i00), cd_mul(cd_conj(i10), y0[1]));
+  h_small[1] = cd_scale(y0[1], i11);
+}
+
+// Re(h^H G h) for a row-major 2x2 G
+__device__ __forceinline__ double quad2(const cd* G, const cd* h) {
+  const cd t0 = cd_add(cd_mul(G[0], h[0]), cd_mul(G[1], h[1]));
+  const cd t1 = cd_add(cd_mul(G[2], h[0]), cd_mul(G[3], h[1]));
+  return cd_mulc(t0, h[0]).x + cd_mulc(t1, h[1]).x;
+}
+
 // Hermitian eigendecomposition by cyclic Jacobi: A (N x N, overwritten) -> eigenvalues on the
 // diagonal, Vv accumulates the eigenvectors (columns).
 __device__ __forceinline__ void jacobi_herm(cd* A, cd* Vv, int N) {

@@ -140,7 +140,7 @@ struct ssb_plan {
   float *hnum = nullptr, *hden = nullptr;  // [B,N,K,J]
   bool part() const { return cfg.partitioning != 0; }
   bool mnmf() const { return cfg.model == SSB_MODEL_FASTMNMF_GAUSS; }
-  bool iss() const { return cfg.spatial == SSB_SPATIAL_ISS1 && !mnmf(); }
+  bool iss() const { return (cfg.spatial == SSB_SPATIAL_ISS1 || cfg.spatial == SSB_SPATIAL_ISS2) && !mnmf(); }
   bool ilrma() const {
     return cfg.model == SSB_MODEL_ILRMA_GAUSS || cfg.model == SSB_MODEL_ILRMA_T || cfg.model == SSB_MODEL_ILRMA_GGD;
   }
@@ -194,7 +194,7 @@ size_t carve(ssb_plan* p, char* base) {
 int validate(const ssb_config* c) {
   SSB_REQUIRE(c != nullptr, "config is NULL");
   SSB_REQUIRE(c->model >= 0 && c->model <= 5, "unknown model %d", c->model);
-  SSB_REQUIRE(c->spatial >= 0 && c->spatial <= 2, "Not support spatial algorithm id %d.", c->spatial);
+  SSB_REQUIRE(c->spatial >= 0 && c->spatial <= 3, "Not support spatial algorithm id %d.", c->spatial);
   SSB_REQUIRE(c->source == SSB_SOURCE_MM || c->source == SSB_SOURCE_ME, "Not support source algorithm id %d.",
               c->source);
   SSB_REQUIRE(c->n_batch >= 1, "n_batch must be >= 1");
@@ -232,7 +232,7 @@ int validate(const ssb_config* c) {
   SSB_REQUIRE(c->flooring >= 0 && c->flooring <= 2, "unknown flooring mode %d", c->flooring);
   SSB_REQUIRE(c->reference_id >= 0 && c->reference_id < c->n_sources, "reference_id=%d out of range",
               c->reference_id);
-  if (c->spatial == SSB_SPATIAL_IP2) {
+  if (c->spatial == SSB_SPATIAL_IP2 || c->spatial == SSB_SPATIAL_ISS2) {
     SSB_REQUIRE(c->n_pairs >= 0 && c->n_pairs <= SSB_MAX_PAIRS, "n_pairs=%d exceeds %d", c->n_pairs, SSB_MAX_PAIRS);
     for (int q = 0; q < c->n_pairs; ++q) {
       int m = c->pairs[2 * q], n = c->pairs[2 * q + 1];
@@ -317,6 +317,8 @@ int ilrma_spatial(ssb_plan* p, cudaStream_t st) {
                    c.model_param, c.flooring, c.eps, st, p->part() ? N : 1));
   const long long sb = (long long)N * I * J, sn = (long long)I * J, si = J;
   if (c.spatial == SSB_SPATIAL_ISS1) return ssbk_iss1(p->Y, p->big, sb, sn, si, B, N, I, J, c.flooring, c.eps, st);
+  if (c.spatial == SSB_SPATIAL_ISS2)
+    return ssbk_iss2(p->Y, p->big, sb, sn, si, B, N, I, J, c.pairs, c.n_pairs, c.flooring, c.eps, st);
   TRY(ssbk_wcov(p->X, p->big, sb, sn, si, nullptr, N, p->U, B, N, I, J, st));
   if (c.spatial == SSB_SPATIAL_IP1) return ssbk_ip1(p->W, p->U, B * I, N, c.flooring, c.eps, st);
   return ssbk_ip2(p->W, p->U, B * I, N, c.pairs, c.n_pairs, N, nullptr, c.flooring, c.eps, st);
@@ -396,6 +398,8 @@ int iva_spatial(ssb_plan* p, cudaStream_t st) {
   TRY(ssbk_iva_phi(p->r2, p->variance, 0, nullptr, N, p->phi_iva, c.model, B, N, I, J, c.flooring, c.eps, st));
   if (c.spatial == SSB_SPATIAL_ISS1)
     return ssbk_iss1(p->Y, p->phi_iva, (long long)N * J, J, 0, B, N, I, J, c.flooring, c.eps, st);
+  if (c.spatial == SSB_SPATIAL_ISS2)  // iva.py:1968-2066: weights once, then every pair
+    return ssbk_iss2(p->Y, p->phi_iva, (long long)N * J, J, 0, B, N, I, J, c.pairs, c.n_pairs, c.flooring, c.eps, st);
   if (c.fast_path && (J % 16) == 0) TRY(ssb_fused_cov_w(p->X, p->phi_iva, (long long)N * J, J, 0, N, p->U, B, N, I, J, st));
   else TRY(ssbk_wcov(p->X, p->phi_iva, (long long)N * J, J, 0, nullptr, N, p->U, B, N, I, J, st));
   return ssbk_ip1(p->W, p->U, B * I, N, c.flooring, c.eps, st);
@@ -575,7 +579,11 @@ extern "C" int ssb_update_once(ssb_plan* p, void* stream) {
       const int B = c.n_batch, N = c.n_sources, I = c.n_bins, J = c.n_frames;
       TRY(ssb_fused_source_iss(&c, p->Y, p->T, p->V, p->big, st));
       TRY(ssb_fused_phi(&c, p->T, p->V, p->big, 1, st));
-      TRY(ssbk_iss1(p->Y, p->big, (long long)N * I * J, (long long)I * J, J, B, N, I, J, c.flooring, c.eps, st));
+      if (c.spatial == SSB_SPATIAL_ISS2)
+        TRY(ssbk_iss2(p->Y, p->big, (long long)N * I * J, (long long)I * J, J, B, N, I, J, c.pairs, c.n_pairs,
+                      c.flooring, c.eps, st));
+      else
+        TRY(ssbk_iss1(p->Y, p->big, (long long)N * I * J, (long long)I * J, J, B, N, I, J, c.flooring, c.eps, st));
       if (c.normalization != SSB_NORM_NONE) TRY(ilrma_normalize(p, st));
       return 0;
     }
@@ -714,6 +722,15 @@ extern "C" int ssb_update_by_iss1(void* Y, const float* phi, long long phi_sb, l
   SSB_REQUIRE(Y && phi, "NULL argument");
   if (B <= 0 || I <= 0 || J <= 0) return 0;
   return ssbk_iss1((cf*)Y, phi, phi_sb, phi_sn, phi_si, B, N, I, J, flooring, eps, (cudaStream_t)stream);
+}
+
+extern "C" int ssb_update_by_iss2(void* Y, const float* phi, long long phi_sb, long long phi_sn, long long phi_si,
+                                  int B, int N, int I, int J, const int32_t* pairs, int n_pairs, int flooring,
+                                  float eps, void* stream) {
+  SSB_REQUIRE(Y && phi && (pairs || n_pairs == 0), "NULL argument");
+  if (B <= 0 || I <= 0 || J <= 0 || n_pairs == 0) return 0;
+  return ssbk_iss2((cf*)Y, phi, phi_sb, phi_sn, phi_si, B, N, I, J, pairs, n_pairs, flooring, eps,
+                   (cudaStream_t)stream);
 }
 
 extern "C" int ssb_projection_back_w(const void* W, void* Wout, int n_mat, int N, int reference_id, void* stream) {

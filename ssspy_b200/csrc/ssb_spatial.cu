@@ -677,6 +677,151 @@ __global__ void __launch_bounds__(ISS_NW * 32) k_iss1_cta(cf* __restrict__ Y, co
 }
 
 // ------------------------------------------------------------------------------------------------
+// ISS2 (ssspy/bss/_update_spatial_model.py:197-314): pairwise iterative source steering, one CTA per (b,i).
+// For every pair (m, n), u = (y_m, y_n):
+//   all sources s:   G_s = mean_j phi_s u u^H                                   (2x2 Hermitian)
+//   s not in pair:   f_s = mean_j phi_s u conj(y_s),  q_s = -G_s^-1 f_s,  y_s += q_s^H u       (:263-283)
+//   pair:            G_m h = l G_n h; y_m <- p_0^H u with the smaller-eigenvalue vector normalised by G_m,
+//                    y_n <- p_1^H u with the larger one normalised by G_n      (:288-303)
+// Like k_iss1_cta every thread owns its frames of the (source x frame) slab, which lives in shared memory when it
+// fits (ys / ps point into it) and is updated in place in global memory otherwise; the 8N statistics of a pair are
+// combined through shared memory in a fixed order.
+struct Iss2Pairs {
+  int n_pairs;
+  int m[SSB_MAX_PAIRS], n[SSB_MAX_PAIRS];
+};
+
+template <int N>
+__global__ void __launch_bounds__(ISS_NW * 32) k_iss2_cta(cf* __restrict__ Y, const float* __restrict__ phi,
+                                                          long long sb, long long sn, long long si, int I, int J,
+                                                          int flooring, float eps, Iss2Pairs pl, int use_smem) {
+  extern __shared__ __align__(16) unsigned char iss_smem[];
+  __shared__ float red[2][ISS_NW][8 * N];
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int bi = blockIdx.x;
+  const int b = bi / I, i = bi - b * I;
+  const size_t base = ((size_t)b * N * I + i) * J;
+  const size_t cs = (size_t)I * J;
+  const float* ph0 = phi + (size_t)b * sb + (size_t)i * si;
+  const double invJ = 1.0 / (double)J;
+  cf* ys = Y + base;           // row stride ystr
+  const float* ps = ph0;       // row stride pstr
+  size_t ystr = cs, pstr = (size_t)sn;
+  if (use_smem) {
+    cf* ys_s = reinterpret_cast<cf*>(iss_smem);
+    float* ps_s = reinterpret_cast<float*>(ys_s + (size_t)N * J);
+#pragma unroll
+    for (int m = 0; m < N; ++m)
+      for (int j = tid; j < J; j += ISS_NW * 32) {
+        ys_s[m * J + j] = Y[base + m * cs + j];
+        ps_s[m * J + j] = ph0[(size_t)m * sn + j];
+      }
+    ys = ys_s;
+    ps = ps_s;
+    ystr = pstr = (size_t)J;
+  }
+  for (int q = 0; q < pl.n_pairs; ++q) {
+    const int pm = pl.m[q], pn = pl.n[q];
+    float st[N][8];
+#pragma unroll
+    for (int s_ = 0; s_ < N; ++s_)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) st[s_][e] = 0.f;
+    for (int j = tid; j < J; j += ISS_NW * 32) {
+      const cf u0 = ys[pm * ystr + j], u1 = ys[pn * ystr + j];
+      const float a00 = u0.x * u0.x + u0.y * u0.y, a11 = u1.x * u1.x + u1.y * u1.y;
+      const float a01r = u0.x * u1.x + u0.y * u1.y, a01i = u0.y * u1.x - u0.x * u1.y;  // u0 conj(u1)
+#pragma unroll
+      for (int s_ = 0; s_ < N; ++s_) {
+        const float ph = ps[s_ * pstr + j];
+        const cf y = ys[s_ * ystr + j];
+        st[s_][0] = fmaf(ph, a00, st[s_][0]);
+        st[s_][1] = fmaf(ph, a11, st[s_][1]);
+        st[s_][2] = fmaf(ph, a01r, st[s_][2]);
+        st[s_][3] = fmaf(ph, a01i, st[s_][3]);
+        const float pr = ph * y.x, pi = ph * y.y;  // phi conj(y_s) = (pr, -pi)
+        st[s_][4] = fmaf(u0.x, pr, fmaf(u0.y, pi, st[s_][4]));
+        st[s_][5] = fmaf(u0.y, pr, fmaf(-u0.x, pi, st[s_][5]));
+        st[s_][6] = fmaf(u1.x, pr, fmaf(u1.y, pi, st[s_][6]));
+        st[s_][7] = fmaf(u1.y, pr, fmaf(-u1.x, pi, st[s_][7]));
+      }
+    }
+#pragma unroll
+    for (int s_ = 0; s_ < N; ++s_)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float v = warp_sum(st[s_][e]);
+        if (lane == 0) red[q & 1][w][s_ * 8 + e] = v;
+      }
+    __syncthreads();
+    // coefficients: y_s' = keep_s y_s + conj(c0_s) u0 + conj(c1_s) u1
+    cf c0[N], c1[N];
+    cd Gm[4], Gn[4];
+#pragma unroll
+    for (int s_ = 0; s_ < N; ++s_) {
+      double t[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float a = 0.f;
+#pragma unroll
+        for (int ww = 0; ww < ISS_NW; ++ww) a += red[q & 1][ww][s_ * 8 + e];  // fixed order: deterministic
+        t[e] = (double)a * invJ;
+      }
+      if (s_ == pm || s_ == pn) {
+        cd* G = s_ == pm ? Gm : Gn;
+        G[0] = cd_make(t[0], 0);
+        G[1] = cd_make(t[2], t[3]);
+        G[2] = cd_make(t[2], -t[3]);
+        G[3] = cd_make(t[1], 0);
+        c0[s_] = c1[s_] = make_float2(0.f, 0.f);
+      } else {
+        // q = -G^-1 f with G = [[g00, g01], [conj(g01), g11]]
+        const cd g01 = cd_make(t[2], t[3]), f0 = cd_make(t[4], t[5]), f1 = cd_make(t[6], t[7]);
+        const double det = t[0] * t[1] - cd_abs2(g01);
+        const double idet = -1.0 / det;
+        const cd q0 = cd_scale(cd_sub(cd_scale(f0, t[1]), cd_mul(g01, f1)), idet);
+        const cd q1 = cd_scale(cd_sub(cd_scale(f1, t[0]), cd_mul(cd_conj(g01), f0)), idet);
+        c0[s_] = cd2cf(q0);
+        c1[s_] = cd2cf(q1);
+      }
+    }
+    {
+      cd hs[2], hl[2];
+      gen_eig2(Gm, Gn, hs, hl);
+      const double dm = 1.0 / ssb_floor(sqrt(fmax(quad2(Gm, hs), 0.0)), flooring, (double)eps);
+      const double dn = 1.0 / ssb_floor(sqrt(fmax(quad2(Gn, hl), 0.0)), flooring, (double)eps);
+#pragma unroll
+      for (int s_ = 0; s_ < N; ++s_) {
+        if (s_ == pm) {
+          c0[s_] = cd2cf(cd_scale(hs[0], dm));
+          c1[s_] = cd2cf(cd_scale(hs[1], dm));
+        } else if (s_ == pn) {
+          c0[s_] = cd2cf(cd_scale(hl[0], dn));
+          c1[s_] = cd2cf(cd_scale(hl[1], dn));
+        }
+      }
+    }
+    for (int j = tid; j < J; j += ISS_NW * 32) {
+      const cf u0 = ys[pm * ystr + j], u1 = ys[pn * ystr + j];
+#pragma unroll
+      for (int s_ = 0; s_ < N; ++s_) {
+        cf y = ys[s_ * ystr + j];
+        if (s_ == pm || s_ == pn) y = make_float2(0.f, 0.f);
+        // conj(c) u = (c.x u.x + c.y u.y, c.x u.y - c.y u.x)
+        y.x += c0[s_].x * u0.x + c0[s_].y * u0.y + c1[s_].x * u1.x + c1[s_].y * u1.y;
+        y.y += c0[s_].x * u0.y - c0[s_].y * u0.x + c1[s_].x * u1.y - c1[s_].y * u1.x;
+        ys[s_ * ystr + j] = y;
+      }
+    }
+  }
+  if (use_smem) {
+#pragma unroll
+    for (int m = 0; m < N; ++m)
+      for (int j = tid; j < J; j += ISS_NW * 32) Y[base + m * cs + j] = ys[m * J + j];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // projection back, filter form (ssspy/algorithm/projection_back.py:87-99): one warp per matrix.
 // scale_out[mat*N + n] (optional) receives (W^-1)[ref, n] for the projection-back normalisation.
 template <int N>
@@ -917,6 +1062,31 @@ int ssbk_iss1(cf* Y, const float* phi, long long sb, long long sn, long long si,
   SSB_DISPATCH_N(N, k_iss1<NN><<<blocks_for((long long)B * I, WPB), WPB * 32, 0, st>>>(Y, phi, sb, sn, si, B, I, J,
                                                                                            flooring, eps));
   return ssb_check_launch("update_by_iss1", st);
+}
+
+int ssbk_iss2(cf* Y, const float* phi, long long sb, long long sn, long long si, int B, int N, int I, int J,
+              const int* pairs, int n_pairs, int flooring, float eps, cudaStream_t st) {
+  SSB_REQUIRE(n_pairs >= 0 && n_pairs <= SSB_MAX_PAIRS, "n_pairs=%d exceeds %d", n_pairs, SSB_MAX_PAIRS);
+  Iss2Pairs pl{};
+  pl.n_pairs = n_pairs;
+  for (int q = 0; q < n_pairs; ++q) {
+    pl.m[q] = pairs[2 * q];
+    pl.n[q] = pairs[2 * q + 1];
+    SSB_REQUIRE(pl.m[q] >= 0 && pl.m[q] < N && pl.n[q] >= 0 && pl.n[q] < N && pl.m[q] != pl.n[q],
+                "invalid pair (%d, %d) for n_sources=%d", pl.m[q], pl.n[q], N);
+  }
+  const size_t slab = (size_t)N * J * (sizeof(cf) + sizeof(float));
+  const int use_smem = slab <= 200 * 1024;
+  SSB_DISPATCH_N(N, {
+    static bool attr_set = false;
+    if (!attr_set) {
+      SSB_CUDA(cudaFuncSetAttribute(k_iss2_cta<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_set = true;
+    }
+    k_iss2_cta<NN><<<B * I, ISS_NW * 32, use_smem ? slab : 0, st>>>(Y, phi, sb, sn, si, I, J, flooring, eps, pl,
+                                                                      use_smem);
+  });
+  return ssb_check_launch("update_by_iss2", st);
 }
 
 int ssbk_pb_w(const cf* W, cf* Wout, cf* scale_out, int n_mat, int N, int ref, cudaStream_t st) {

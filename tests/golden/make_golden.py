@@ -19,7 +19,7 @@ sys.path.insert(0, os.path.join(HERE, "..", ".."))
 
 from ssspy.algorithm import projection_back  # noqa: E402
 from ssspy.bss._update_spatial_model import (  # noqa: E402
-    update_by_ip1, update_by_ip2, update_by_ip2_one_pair, update_by_iss1)
+    update_by_ip1, update_by_ip2, update_by_ip2_one_pair, update_by_iss1, update_by_iss2)
 from ssspy.bss.ilrma import GGDILRMA, TILRMA, GaussILRMA  # noqa: E402
 from ssspy.bss.iva import AuxGaussIVA, AuxLaplaceIVA  # noqa: E402
 from ssspy.bss.mnmf import FastGaussMNMF  # noqa: E402
@@ -114,8 +114,6 @@ def iva_case(name, N, I, J, n_iter, model="laplace", spatial="IP", flooring="max
                pairs=pair_list)
     if W0 is not None:
         out["W0"] = W0
-    if partitioning:
-        out["Z0"], out["Z"] = Z0, m.latent
     if m.demix_filter is not None:
         out["W"] = m.demix_filter
     if model == "gauss":
@@ -164,6 +162,7 @@ def kernel_cases():
             out[f"N{N}_ip2_{fl}"] = update_by_ip2(W, U, flooring_fn=FLOOR[fl], overwrite=False)
             Y = (W @ X.transpose(1, 0, 2)).transpose(1, 0, 2)
             out[f"N{N}_iss1_{fl}"] = update_by_iss1(Y, phi, flooring_fn=FLOOR[fl])
+            out[f"N{N}_iss2_{fl}"] = update_by_iss2(Y, phi, flooring_fn=FLOOR[fl])
         # pair selector with negative indices (test_update_spatial_model.py:19-24)
         def neg_sel(n):
             for m in range(n):
@@ -171,6 +170,9 @@ def kernel_cases():
         out[f"N{N}_ip2_negpairs"] = update_by_ip2(W, U, pair_selector=neg_sel, overwrite=False)
         out[f"N{N}_ip2_comb"] = update_by_ip2(W, U, pair_selector=combination_pair_selector, overwrite=False)
         out[f"N{N}_ip2pair01"] = update_by_ip2_one_pair(W, U[:, (0, 1)], pair=(0, 1))
+        out[f"N{N}_iss2_seq"] = update_by_iss2(Y, phi, pair_selector=sequential_pair_selector)  # incl. (N-1, 0)
+        out[f"N{N}_iss2_negpairs"] = update_by_iss2(Y, phi, pair_selector=neg_sel)
+        out[f"N{N}_iss2_comb"] = update_by_iss2(Y, phi, pair_selector=combination_pair_selector)
     np.savez_compressed(os.path.join(HERE, "spatial_kernels.npz"), **out)
     print("spatial_kernels done")
 
@@ -240,6 +242,20 @@ def partitioning_cases():
     ilrma_case("ggdilrma_part_ip1_b1", 3, 17, 23, 4, 5, dist="ggd", dist_param=1.0, partitioning=True, seed=46)
 
 
+def iss2_cases():
+    """spatial_algorithm="ISS2" through the classes (ilrma.py:1698-1811, iva.py:1968-2066): default pair selector =
+    sequential (all N pairs incl. the wrapping (N-1, 0))."""
+    ilrma_case("ilrma_iss2", 3, 17, 23, 4, 5, spatial="ISS2", seed=50)
+    ilrma_case("ilrma_iss2_n2_p1", 2, 21, 30, 3, 5, spatial="ISS2", domain=1, seed=51)
+    ilrma_case("ilrma_iss2_n4_comb_pb", 4, 12, 40, 5, 4, spatial="ISS2", pairs="combination",
+               normalization="projection_back", seed=52)
+    ilrma_case("tilrma_iss2", 3, 17, 23, 4, 5, spatial="ISS2", dist="t", dist_param=6.0, seed=53)
+    ilrma_case("ggdilrma_iss2_part", 3, 17, 23, 4, 5, spatial="ISS2", dist="ggd", dist_param=1.2, partitioning=True, seed=54)
+    iva_case("iva_laplace_iss2", 3, 17, 23, 6, spatial="ISS2", seed=55)
+    iva_case("iva_gauss_iss2_n4", 4, 12, 40, 5, model="gauss", spatial="ISS2", seed=56)
+    iva_case("iva_laplace_iss2_n2_comb", 2, 21, 30, 6, spatial="ISS2", pairs="combination", seed=57)
+
+
 def mdp_cases():
     """minimal_distortion_principle standalone + as scale_restoration of GaussILRMA / AuxLaplaceIVA."""
     from ssspy.algorithm import minimal_distortion_principle
@@ -262,6 +278,7 @@ def main():
     mdp_cases()
     tggd_cases()
     partitioning_cases()
+    iss2_cases()
     # GaussILRMA: spatial x source x domain x normalisation x flooring grid (regression-test pattern,
     # tests/regression/bss/test_ilrma.py:48-62: inject basis/activation, fixed n_iter, compare).
     ilrma_case("ilrma_ip1_mm_n2", 2, 33, 40, 4, 10)

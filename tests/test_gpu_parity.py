@@ -52,7 +52,7 @@ def _make_ilrma(g, **over):
     spatial = str(g["spatial"])
     kw = dict(n_basis=g["T0"].shape[-1], spatial_algorithm=spatial, source_algorithm=str(g["source"]),
               domain=float(g["domain"]), flooring_fn=_floor_fn(str(g["flooring"])),
-              pair_selector=_pair_selector(g["pairs"]) if spatial == "IP2" else None,
+              pair_selector=_pair_selector(g["pairs"]) if spatial in ("IP2", "ISS2") else None,
               normalization=norm_arg(g["normalization"]), scale_restoration=sr_arg(g["scale_restoration"]),
               record_loss=True, reference_id=ref_id, rng=np.random.default_rng(0), partitioning="Z0" in g)
     kw.update(over)
@@ -104,7 +104,7 @@ def test_aux_iva_matches_reference(name):
     cls = AuxLaplaceIVA if str(g["model"]) == "laplace" else AuxGaussIVA
     kwargs = {"demix_filter": g["W0"]} if "W0" in g else {}
     m = cls(spatial_algorithm=spatial, flooring_fn=_floor_fn(str(g["flooring"])),
-            pair_selector=_pair_selector(g["pairs"]) if spatial == "IP2" else None,
+            pair_selector=_pair_selector(g["pairs"]) if spatial in ("IP2", "ISS2") else None,
             scale_restoration=sr_arg(g["scale_restoration"]), record_loss=True, reference_id=int(g["reference_id"]))
     Y = m(g["X"], n_iter=int(g["n_iter"]), **kwargs)
     assert Y.shape == g["Y"].shape
@@ -124,8 +124,8 @@ def test_spatial_operators_match_reference(N):
     """update_by_ip1 / ip2 / ip2_one_pair / iss1 on the reference's own smoke-test shapes
     (tests/package/bss/test_update_spatial_model.py:45-171), incl. negative pair indices."""
     from ssspy_b200.bss._update_spatial_model import (update_by_ip1, update_by_ip2, update_by_ip2_one_pair,
-                                                     update_by_iss1)
-    from ssspy_b200.utils.select_pair import combination_pair_selector
+                                                     update_by_iss1, update_by_iss2)
+    from ssspy_b200.utils.select_pair import combination_pair_selector, sequential_pair_selector
     g = load("spatial_kernels")
     X, phi, W, U = (g[f"N{N}_{k}"] for k in ("X", "phi", "W", "U"))
     Y = np.einsum("inm,mij->nij", W, X)
@@ -136,6 +136,9 @@ def test_spatial_operators_match_reference(N):
         assert relerr(phase_align_rows(out, g[f"N{N}_ip2_{fl}"]), g[f"N{N}_ip2_{fl}"]) < 1e-5
         out = update_by_iss1(Y, phi, flooring_fn=_floor_fn(fl))
         assert out.shape == Y.shape and relerr(out, g[f"N{N}_iss1_{fl}"]) < 1e-5
+        out = update_by_iss2(Y, phi, flooring_fn=_floor_fn(fl))  # default pairs (0,1),(2,3),...
+        assert out.shape == Y.shape
+        assert relerr(phase_align_rows(out, g[f"N{N}_iss2_{fl}"]), g[f"N{N}_iss2_{fl}"]) < 2e-5
 
     def neg_sel(n):
         for m in range(n):
@@ -144,6 +147,10 @@ def test_spatial_operators_match_reference(N):
     assert relerr(phase_align_rows(out, g[f"N{N}_ip2_negpairs"]), g[f"N{N}_ip2_negpairs"]) < 1e-5
     out = update_by_ip2(W, U, pair_selector=combination_pair_selector, overwrite=False)
     assert relerr(phase_align_rows(out, g[f"N{N}_ip2_comb"]), g[f"N{N}_ip2_comb"]) < 1e-5
+    # ISS2 with wrapping / negative / all-combination pairs (rows of a pair carry the eigenvector's free phase)
+    for key, sel in (("seq", sequential_pair_selector), ("negpairs", neg_sel), ("comb", combination_pair_selector)):
+        out = update_by_iss2(Y, phi, pair_selector=sel)
+        assert relerr(phase_align_rows(out, g[f"N{N}_iss2_{key}"]), g[f"N{N}_iss2_{key}"]) < 5e-5
     out = update_by_ip2_one_pair(W, U[:, (0, 1)], pair=(0, 1))
     assert out.shape == (W.shape[0], 2, N)
     assert relerr(phase_align_rows(out, g[f"N{N}_ip2pair01"]), g[f"N{N}_ip2pair01"]) < 1e-5
@@ -559,3 +566,39 @@ def test_partitioning_batched_rng_and_manual_phases(spatial, source):
     np.testing.assert_allclose(np.asarray(m2.compute_loss()), np.asarray(m.loss)[-1], rtol=1e-6)
     with pytest.raises(NotImplementedError, match="not applicable with partitioning"):
         m2.normalize_by_projection_back()
+
+
+@pytest.mark.parametrize("cls_name,N,J", [("GaussILRMA", 4, 96), ("AuxLaplaceIVA", 5, 64), ("AuxGaussIVA", 8, 48),
+                                          ("TILRMA", 2, 80)])
+def test_iss2_seeded_batched_vs_oracle(cls_name, N, J):
+    """spatial_algorithm="ISS2" on batched seeded input against the per-mixture oracle (projection back fixes the
+    eigenvector phase), including update_once driven from Python and the manual spatial phase."""
+    from oracle import ilrma as oilrma
+    from oracle import iva as oiva
+    import ssspy_b200.bss as bss
+    from ssspy_b200.utils.synth import make_batch, make_nmf_init
+    B, I, K, n_iter = 2, 21, 4, 3
+    X = make_batch(B, N, I, J, config_id=17, mode="mix")
+    cls = getattr(bss, cls_name)
+    if "ILRMA" in cls_name:
+        TV = [make_nmf_init(N, I, J, K, seed=90 + b) for b in range(B)]
+        T0, V0 = np.stack([t for t, _ in TV]), np.stack([v for _, v in TV])
+        extra = {"dof": 5.0} if cls_name == "TILRMA" else {}
+        m = cls(n_basis=K, spatial_algorithm="ISS2", **extra)
+        Y = m(X, n_iter=n_iter, basis=T0, activation=V0)
+        m2 = cls(n_basis=K, spatial_algorithm="ISS2", callbacks=lambda self: None, **extra)  # Python-driven loop
+        Y2 = m2(X, n_iter=n_iter, basis=T0, activation=V0)
+        dist = ("t", 5.0) if cls_name == "TILRMA" else ("gauss", None)
+        ref = [oilrma.run(X[b], T0[b], V0[b], n_iter, spatial_algorithm="ISS2", dist=dist) for b in range(B)]
+    else:
+        m = cls(spatial_algorithm="ISS2")
+        Y = m(X, n_iter=n_iter)
+        m2 = cls(spatial_algorithm="ISS2", callbacks=lambda self: None)
+        Y2 = m2(X, n_iter=n_iter)
+        ref = [oiva.run(X[b], n_iter, spatial_algorithm="ISS2", model="laplace" if "Laplace" in cls_name else "gauss")
+               for b in range(B)]
+    assert m.demix_filter is None
+    assert relerr(Y2, Y) < 1e-6
+    for b in range(B):
+        assert relerr(Y[b], ref[b]["Y"]) < tol_seeded("IP2")
+        np.testing.assert_allclose(np.asarray(m.loss)[:, b], ref[b]["loss"], rtol=1e-3, atol=1e-3)

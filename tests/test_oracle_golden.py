@@ -70,12 +70,18 @@ def test_spatial_kernels_oracle(N):
         assert _ip2_err(ospatial.update_by_ip2(W, U, FLOORS[fl]), g[f"N{N}_ip2_{fl}"]) < TOL
         Y = oilrma.separate(X, W)
         assert relerr(ospatial.update_by_iss1(Y, phi, FLOORS[fl]), g[f"N{N}_iss1_{fl}"]) < TOL
+        assert _ip2_err(ospatial.update_by_iss2(Y, phi, FLOORS[fl]), g[f"N{N}_iss2_{fl}"]) < TOL
     neg = [(m - N, (m + 1) % N - N) for m in range(N)]
     assert _ip2_err(ospatial.update_by_ip2(W, U, pairs=neg), g[f"N{N}_ip2_negpairs"]) < TOL
     import itertools
     comb = list(itertools.combinations(range(N), 2))
     assert _ip2_err(ospatial.update_by_ip2(W, U, pairs=comb), g[f"N{N}_ip2_comb"]) < TOL
     assert _ip2_err(ospatial.update_by_ip2_one_pair(W, U[:, (0, 1)], (0, 1)), g[f"N{N}_ip2pair01"]) < TOL
+    # ISS2: rows of the updated pair carry the eigenvector's free phase per bin
+    seq = [(m, (m + 1) % N) for m in range(N)]
+    assert _ip2_err(ospatial.update_by_iss2(Y, phi, pairs=seq), g[f"N{N}_iss2_seq"]) < TOL
+    assert _ip2_err(ospatial.update_by_iss2(Y, phi, pairs=neg), g[f"N{N}_iss2_negpairs"]) < TOL
+    assert _ip2_err(ospatial.update_by_iss2(Y, phi, pairs=comb), g[f"N{N}_iss2_comb"]) < TOL
 
 
 def test_linalg_known_answers():
