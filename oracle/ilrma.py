@@ -27,7 +27,7 @@ def init_state(X, T, V, W=None, spatial_algorithm="IP", Z=None):
               T=T.astype(np.float64).copy(), V=V.astype(np.float64).copy())
     st["Y"] = separate(st["X"], st["W"])
     st["Z"] = None if Z is None else Z.astype(np.float64).copy()
-    if spatial_algorithm in ("ISS", "ISS1", "ISS2"):
+    if spatial_algorithm in ("ISS", "ISS1", "ISS2", "IPA"):
         st["W"] = None
     return st
 
@@ -101,7 +101,8 @@ def update_activation(st, p=2, floor=spatial.max_flooring, source_algorithm="MM"
     st["V"] = floor(((num / den) ** b) * V)
 
 
-def update_spatial(st, p=2, floor=spatial.max_flooring, spatial_algorithm="IP", pairs=None, dist=("gauss", None)):
+def update_spatial(st, p=2, floor=spatial.max_flooring, spatial_algorithm="IP", pairs=None, dist=("gauss", None),
+                   ipa=(True, 1)):
     """phi = 1/(T V)^(2/p) (no floor), then IP1 / IP2 on W or ISS1 on Y
     (ssspy/bss/ilrma.py:1494-1507, :1618-1633, :1690-1696).  Student-t: phi = 1/R~ (ilrma.py:2920-2934);
     GGD: phi = 1/((2/beta) floor(|y|^(2-beta)) R^(beta/p)) (:3992-4010)."""
@@ -125,6 +126,8 @@ def update_spatial(st, p=2, floor=spatial.max_flooring, spatial_algorithm="IP", 
     elif spatial_algorithm == "ISS2":  # ilrma.py:1698-1811; class default = all sequential pairs
         st["Y"] = spatial.update_by_iss2(st["Y"], phi, floor, pairs if pairs is not None else
                                          spatial.sequential_pairs(st["Y"].shape[0]))
+    elif spatial_algorithm == "IPA":  # ilrma.py:1813-1908 (lqpqm_normalization, newton_iter)
+        st["Y"] = spatial.update_by_ipa(st["Y"], phi, floor, normalization=ipa[0], max_iter=ipa[1])
     else:
         raise NotImplementedError(spatial_algorithm)
 
@@ -166,13 +169,13 @@ def normalize(st, p=2, floor=spatial.max_flooring, normalization=True, reference
 
 
 def update_once(st, p=2, floor=spatial.max_flooring, spatial_algorithm="IP", source_algorithm="MM",
-                normalization=True, pairs=None, reference_id=0, dist=("gauss", None)):
+                normalization=True, pairs=None, reference_id=0, dist=("gauss", None), ipa=(True, 1)):
     """ssspy/bss/ilrma.py:900-922."""
     if st.get("Z") is not None:  # ilrma.py:972-973
         update_latent(st, p, source_algorithm, dist)
     update_basis(st, p, floor, source_algorithm, dist)
     update_activation(st, p, floor, source_algorithm, dist)
-    update_spatial(st, p, floor, spatial_algorithm, pairs, dist)
+    update_spatial(st, p, floor, spatial_algorithm, pairs, dist, ipa)
     if normalization:
         normalize(st, p, floor, normalization, reference_id)
 
@@ -222,14 +225,14 @@ def restore_scale(st, reference_id=0, method=True):
 
 def run(X, T, V, n_iter, W=None, p=2, floor=spatial.max_flooring, spatial_algorithm="IP",
         source_algorithm="MM", normalization=True, pairs=None, reference_id=0,
-        scale_restoration=True, record_loss=True, snapshots=False, dist=("gauss", None), Z=None):
+        scale_restoration=True, record_loss=True, snapshots=False, dist=("gauss", None), Z=None, ipa=(True, 1)):
     """GaussILRMA.__call__ (ssspy/bss/ilrma.py:820-855 + ssspy/bss/base.py:48-77)."""
     st = init_state(X, T, V, W, spatial_algorithm, Z)
     loss, snaps = [], []
     if record_loss:
         loss.append(compute_loss(st, p, dist))
     for _ in range(n_iter):
-        update_once(st, p, floor, spatial_algorithm, source_algorithm, normalization, pairs, reference_id, dist)
+        update_once(st, p, floor, spatial_algorithm, source_algorithm, normalization, pairs, reference_id, dist, ipa)
         if record_loss:
             loss.append(compute_loss(st, p, dist))
         if snapshots:

@@ -18,7 +18,7 @@ def init_state(X, W=None, spatial_algorithm="IP", model="laplace"):
         W = np.tile(np.eye(N, dtype=np.complex128), (I, 1, 1))
     st = dict(X=X.astype(np.complex128), W=W.astype(np.complex128).copy())
     st["Y"] = separate(st["X"], st["W"])
-    if spatial_algorithm in ("ISS", "ISS1", "ISS2"):
+    if spatial_algorithm in ("ISS", "ISS1", "ISS2", "IPA"):
         st["W"] = None
     if model == "gauss":
         st["variance"] = np.ones((N, J))  # ssspy/bss/iva.py:3317
@@ -31,7 +31,7 @@ def _weight(r, floor, model, variance=None):
     return dG / floor(2 * r)
 
 
-def update_once(st, floor=spatial.max_flooring, spatial_algorithm="IP", model="laplace", pairs=None):
+def update_once(st, floor=spatial.max_flooring, spatial_algorithm="IP", model="laplace", pairs=None, ipa=(True, 1)):
     X = st["X"]
     N = X.shape[0]
     if model == "gauss":
@@ -64,6 +64,10 @@ def update_once(st, floor=spatial.max_flooring, spatial_algorithm="IP", model="l
         phi = _weight(r, floor, model, var)
         st["Y"] = spatial.update_by_iss2(st["Y"], phi[:, np.newaxis, :], floor, pairs if pairs is not None else
                                          spatial.sequential_pairs(st["Y"].shape[0]))
+    elif spatial_algorithm == "IPA":  # iva.py:2068-2176
+        r = np.linalg.norm(st["Y"], axis=1)
+        phi = _weight(r, floor, model, var)
+        st["Y"] = spatial.update_by_ipa(st["Y"], phi[:, np.newaxis, :], floor, normalization=ipa[0], max_iter=ipa[1])
     else:
         raise NotImplementedError(spatial_algorithm)
 
@@ -98,14 +102,14 @@ def restore_scale(st, reference_id=0):
 
 
 def run(X, n_iter, W=None, floor=spatial.max_flooring, spatial_algorithm="IP", model="laplace",
-        pairs=None, reference_id=0, scale_restoration=True, record_loss=True, snapshots=False):
+        pairs=None, reference_id=0, scale_restoration=True, record_loss=True, snapshots=False, ipa=(True, 1)):
     """AuxIVA.__call__ (ssspy/bss/iva.py:1637-1672 + ssspy/bss/base.py:48-77)."""
     st = init_state(X, W, spatial_algorithm, model)
     loss, snaps = [], []
     if record_loss:
         loss.append(compute_loss(st, model))
     for _ in range(n_iter):
-        update_once(st, floor, spatial_algorithm, model, pairs)
+        update_once(st, floor, spatial_algorithm, model, pairs, ipa)
         if record_loss:
             loss.append(compute_loss(st, model))
         if snapshots:

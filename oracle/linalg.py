@@ -61,3 +61,85 @@ def eigh2(A, B=None, type=1):
     if B is None:
         return np.linalg.eigh(A)
     return eigh(A, B, type=type, _inv=inv2)
+
+
+def to_psd(X, floor):
+    """Hermitian-symmetrise, floor the eigenvalues, rebuild (ssspy/special/psd.py:11-71)."""
+    X = (X + np.conj(np.swapaxes(X, -2, -1))) / 2
+    lam, P = np.linalg.eigh(X)
+    X = (P * floor(lam)[..., None, :]) @ np.conj(np.swapaxes(P, -2, -1))
+    return (X + np.conj(np.swapaxes(X, -2, -1))) / 2
+
+
+def psd_inv(X, floor):
+    """P diag(1 / floor(lam)) P^H (ssspy/bss/_update_spatial_model.py:611-645)."""
+    lam, P = np.linalg.eigh(X)
+    return (P * (1 / floor(lam))[..., None, :]) @ np.conj(np.swapaxes(P, -2, -1))
+
+
+def find_largest_root(A, B, C):
+    """Largest real root of x^3 + A x^2 + B x + C by Cardano (ssspy/linalg/lqpqm.py:222-292)."""
+    P = -A ** 2 / 3 + B
+    Q = 2 * A ** 3 / 27 - A * B / 3 + C
+    om = (-1 + 1j * np.sqrt(3)) / 2
+    disc = ((Q / 2) ** 2 + (P / 3) ** 3).astype(np.complex128)
+    w = -Q / 2 + np.sqrt(disc)
+    U = np.cbrt(np.abs(w)) * np.exp(1j * np.angle(w) / 3)
+    sing = U == 0
+    U = np.where(sing, 1, U)
+    V = -P / (3 * U)
+    X1 = np.where(sing, np.cbrt(-Q), U + V)
+    X2 = np.real(U * om + V * np.conj(om))
+    X3 = np.real(U * np.conj(om) + V * om)
+    roots = np.real(np.stack([X1, X2, X3], axis=-1))
+    mono = P >= 0
+    drop = mono | (~mono & (np.real(disc) > 0))  # a single real root
+    roots[..., 1:] = np.where(drop[..., None], -np.inf, roots[..., 1:])
+    return roots.max(axis=-1) - A / 3
+
+
+def solve_equation(phi, v, z, floor, max_iter=10):
+    """Largest root of f(l) = l^2 sum phi |v|^2 / (l - phi)^2 - l + z by Newton-Raphson from the cubic obtained
+    with the dominant term only; coefficients normalised by phi_max (ssspy/linalg/lqpqm.py:122-219)."""
+    mask = phi * np.abs(v) ** 2 >= floor(0)
+    phi, v = mask * phi, mask * v
+    idx = np.argmax(phi, axis=-1)
+    rows = np.arange(phi.shape[0])
+    phi_max = floor(phi[rows, idx])
+    v_max = v[rows, idx] / phi_max
+    phi, v, z = phi / phi_max[:, None], v / phi_max[:, None], z / phi_max
+    A = -(np.abs(v_max) ** 2 + 2 + z)
+    B = 1 + 2 * z
+    C = -z
+    lamb = find_largest_root(A, B, C)
+    lamb = np.where(lamb > 1, lamb, 1 + floor(0))
+    lamb = np.maximum(lamb, z)
+    for _ in range(max_iter):
+        f = lamb ** 2 * np.sum(phi * np.abs(v) ** 2 / (lamb[:, None] - phi) ** 2, axis=-1) - lamb + z
+        if np.all(np.abs(f) <= floor(0)):
+            break
+        df = -2 * lamb * np.sum((phi * np.abs(v)) ** 2 / (lamb[:, None] - phi) ** 3, axis=-1) - 1
+        mu = lamb - f / df
+        lamb = np.where(mu > 1, mu, (1 + lamb) / 2)
+    return lamb * phi_max
+
+
+def lqpqm2(H, v, z, floor, max_iter=10):
+    """argmax-side stationary point of the log-quadratically penalised quadratic minimisation, type 2
+    (ssspy/linalg/lqpqm.py:13-119), singular_fn = (x < floor(0)) as update_by_ipa calls it
+    (_update_spatial_model.py:484-490).  H (*, M, M) Hermitian PSD, v (*, M), z (*,)."""
+    phi, sigma = np.linalg.eigh(H)
+    sing = np.linalg.norm(v, axis=-1) < floor(0)
+    y = np.zeros_like(v)
+    if np.any(sing):
+        ps, ss, zs = phi[sing], sigma[sing], z[sing]
+        lam = np.maximum(zs, ps[:, -1])
+        scale = np.sqrt(np.maximum((lam - zs) / ps[:, -1], 0))
+        y[sing] = scale[:, None] * ss[:, :, -1]
+    ns = ~sing
+    if np.any(ns):
+        pn, sn, vn, zn = phi[ns], sigma[ns], v[ns], z[ns]
+        vt = np.sum(np.conj(sn) * vn[:, :, None], axis=-2)
+        lam = solve_equation(pn, vt, zn, floor, max_iter)
+        y[ns] = np.sum(sn * (pn * vt / (lam[:, None] - pn))[:, None, :], axis=-1)
+    return y

@@ -161,3 +161,54 @@ def update_by_iss2(Y, phi, floor=max_flooring, pairs=None):
             new[dst] = np.einsum("ic,cij->ij", pa.conj(), u)
         Y = new
     return Y
+
+
+def update_by_ipa(Y, phi, floor=max_flooring, normalization=True, max_iter=1):
+    """Iterative projection with adjustment (ssspy/bss/_update_spatial_model.py:398-513).  For n = 0..N-1 on the
+    current Y, per bin (s runs over the other sources, "\\n" = row / column n removed):
+      U_s = to_psd(mean_j phi_s y y^H) for every s (:441-445);   Uinv = psd_inv(U_n) (:451)
+      a_s = Re U_s[n,n], b_s = U_s[n,s] (:453-458);   C = conj(Uinv)\\n, d = conj(Uinv)[\\n, n] (:460-462)
+      z = Re Uinv[n,n] - Re d^H C^-1 d (:464-470);   H = C / (sqrt(a_s) sqrt(a_s')), v = -b/sqrt(a) - sqrt(a) C^-1 d
+      (:472-475), both divided by tr H when ``normalization`` (:477-481)
+      q = lqpqm2(H, v, z) / sqrt(a) - b / a (:483-492);   qt = e_n - E conj(q);  u = U_n^-1 qt,
+      p = u / floor(sqrt(max(Re qt^H u, 0))) (:494-503)
+      y_n <- p^H y,  y_s <- y_s + conj(q_s) y_n(old) (:505-511).
+    phi broadcastable to (N, I, J)."""
+    from .linalg import lqpqm2, psd_inv, solve, to_psd
+    Y = Y.copy()
+    N, I, J = Y.shape
+    phi = np.broadcast_to(phi, Y.shape)
+    for n in range(N):
+        others = [s for s in range(N) if s != n]
+        YY = Y[:, None] * Y[None].conj()                                         # (a, b, I, J)
+        U = np.mean(phi[:, None, None] * YY[None], axis=-1).transpose(3, 0, 1, 2)   # (I, s, a, b)
+        U = to_psd(U, floor)
+        Un = U[:, n]
+        Uinv = psd_inv(Un, floor)
+        a = np.real(U[:, others, n, n])                                           # (I, M)
+        b = np.stack([U[:, s, n, s] for s in others], axis=-1)
+        Cc = np.conj(Uinv)
+        C = Cc[:, others][:, :, others]
+        d = Cc[:, others, n]
+        Cd = solve(C, d)
+        z = np.real(Uinv[:, n, n]) - np.real(np.sum(d.conj() * Cd, axis=-1))
+        sa = np.sqrt(a)
+        H = C / (sa[:, :, None] * sa[:, None, :])
+        v = -b / sa - sa * Cd
+        if normalization:
+            tr = np.real(np.trace(H, axis1=-2, axis2=-1))
+            H = H / tr[:, None, None]
+            z = z / tr
+        q = lqpqm2(H, v, z, floor, max_iter) / sa - b / a
+        Eq = np.zeros((I, N), dtype=np.complex128)
+        Eq[:, others] = q.conj()
+        qt = -Eq
+        qt[:, n] += 1
+        Uq = solve(Un, qt)
+        den = floor(np.sqrt(np.maximum(np.real(np.sum(qt.conj() * Uq, axis=-1, keepdims=True)), 0)))
+        p = Uq / den
+        Yn = Y[n].copy()
+        new_n = np.einsum("is,sij->ij", p.conj(), Y)
+        Y = Y + Eq.T[:, :, None] * Yn[None]
+        Y[n] = new_n
+    return Y

@@ -19,7 +19,7 @@ sys.path.insert(0, os.path.join(HERE, "..", ".."))
 
 from ssspy.algorithm import projection_back  # noqa: E402
 from ssspy.bss._update_spatial_model import (  # noqa: E402
-    update_by_ip1, update_by_ip2, update_by_ip2_one_pair, update_by_iss1, update_by_iss2)
+    update_by_ip1, update_by_ip2, update_by_ip2_one_pair, update_by_ipa, update_by_iss1, update_by_iss2)
 from ssspy.bss.ilrma import GGDILRMA, TILRMA, GaussILRMA  # noqa: E402
 from ssspy.bss.iva import AuxGaussIVA, AuxLaplaceIVA  # noqa: E402
 from ssspy.bss.mnmf import FastGaussMNMF  # noqa: E402
@@ -41,7 +41,7 @@ def rand_w(rng, I, N):
 
 def ilrma_case(name, N, I, J, K, n_iter, spatial="IP", source="MM", domain=2, normalization=True,
                flooring="max", reference_id=0, scale_restoration=True, pairs=None, w_init=False, seed=0,
-               dist="gauss", dist_param=0.0, partitioning=False):
+               dist="gauss", dist_param=0.0, partitioning=False, ipa=None):
     X = make_mixture(N, I, J, seed=seed, mode="mix")
     T, V = make_nmf_init(N, I, J, K, seed=42 + seed)
     kwargs = dict(basis=T, activation=V)
@@ -70,6 +70,8 @@ def ilrma_case(name, N, I, J, K, n_iter, spatial="IP", source="MM", domain=2, no
                   partitioning=partitioning,
                   pair_selector=sel, callbacks=cb, normalization=normalization, scale_restoration=scale_restoration,
                   record_loss=True, reference_id=reference_id, rng=np.random.default_rng(0))
+    if ipa is not None:
+        common.update(lqpqm_normalization=ipa[0], newton_iter=ipa[1])
     if dist == "t":
         m = TILRMA(n_basis=K, dof=dist_param, **common)
     elif dist == "ggd":
@@ -83,7 +85,8 @@ def ilrma_case(name, N, I, J, K, n_iter, spatial="IP", source="MM", domain=2, no
                n_iter=n_iter, spatial=spatial, source=source, domain=float(domain),
                normalization=str(normalization), flooring=flooring,
                reference_id=-1 if reference_id is None else reference_id,
-               scale_restoration=scale_restoration, pairs=pair_list, dist=dist, dist_param=float(dist_param))
+               scale_restoration=scale_restoration, pairs=pair_list, dist=dist, dist_param=float(dist_param),
+               ipa_normalization=True if ipa is None else bool(ipa[0]), ipa_newton_iter=1 if ipa is None else int(ipa[1]))
     if W0 is not None:
         out["W0"] = W0
     if partitioning:
@@ -96,7 +99,7 @@ def ilrma_case(name, N, I, J, K, n_iter, spatial="IP", source="MM", domain=2, no
 
 
 def iva_case(name, N, I, J, n_iter, model="laplace", spatial="IP", flooring="max", reference_id=0,
-             scale_restoration=True, pairs=None, w_init=False, seed=0):
+             scale_restoration=True, pairs=None, w_init=False, seed=0, ipa=None):
     X = make_mixture(N, I, J, seed=100 + seed, mode="mix")
     rng = np.random.default_rng(9 + seed)
     kwargs = {}
@@ -105,13 +108,15 @@ def iva_case(name, N, I, J, n_iter, model="laplace", spatial="IP", flooring="max
         kwargs["demix_filter"] = W0
     sel = combination_pair_selector if pairs == "combination" else None
     cls = AuxLaplaceIVA if model == "laplace" else AuxGaussIVA
+    extra = {} if ipa is None else dict(lqpqm_normalization=ipa[0], newton_iter=ipa[1])
     m = cls(spatial_algorithm=spatial, flooring_fn=FLOOR[flooring], pair_selector=sel,
-            scale_restoration=scale_restoration, record_loss=True, reference_id=reference_id)
+            scale_restoration=scale_restoration, record_loss=True, reference_id=reference_id, **extra)
     Y = m(X, n_iter=n_iter, **kwargs)
     pair_list = np.array(list((sel or sequential_pair_selector)(N)), dtype=np.int32)
     out = dict(kind="iva", X=X, Y=Y, loss=np.array(m.loss), n_iter=n_iter, model=model, spatial=spatial,
                flooring=flooring, reference_id=reference_id, scale_restoration=scale_restoration,
-               pairs=pair_list)
+               pairs=pair_list, ipa_normalization=True if ipa is None else bool(ipa[0]),
+               ipa_newton_iter=1 if ipa is None else int(ipa[1]))
     if W0 is not None:
         out["W0"] = W0
     if m.demix_filter is not None:
@@ -163,6 +168,7 @@ def kernel_cases():
             Y = (W @ X.transpose(1, 0, 2)).transpose(1, 0, 2)
             out[f"N{N}_iss1_{fl}"] = update_by_iss1(Y, phi, flooring_fn=FLOOR[fl])
             out[f"N{N}_iss2_{fl}"] = update_by_iss2(Y, phi, flooring_fn=FLOOR[fl])
+            out[f"N{N}_ipa_{fl}"] = update_by_ipa(Y, phi, flooring_fn=FLOOR[fl])
         # pair selector with negative indices (test_update_spatial_model.py:19-24)
         def neg_sel(n):
             for m in range(n):
@@ -170,6 +176,8 @@ def kernel_cases():
         out[f"N{N}_ip2_negpairs"] = update_by_ip2(W, U, pair_selector=neg_sel, overwrite=False)
         out[f"N{N}_ip2_comb"] = update_by_ip2(W, U, pair_selector=combination_pair_selector, overwrite=False)
         out[f"N{N}_ip2pair01"] = update_by_ip2_one_pair(W, U[:, (0, 1)], pair=(0, 1))
+        out[f"N{N}_ipa_nonorm_it5"] = update_by_ipa(Y, phi, normalization=False, max_iter=5)
+        out[f"N{N}_ipa_frameweights"] = update_by_ipa(Y, phi[:, :1, :].transpose(0, 1, 2), max_iter=2)
         out[f"N{N}_iss2_seq"] = update_by_iss2(Y, phi, pair_selector=sequential_pair_selector)  # incl. (N-1, 0)
         out[f"N{N}_iss2_negpairs"] = update_by_iss2(Y, phi, pair_selector=neg_sel)
         out[f"N{N}_iss2_comb"] = update_by_iss2(Y, phi, pair_selector=combination_pair_selector)
@@ -256,6 +264,16 @@ def iss2_cases():
     iva_case("iva_laplace_iss2_n2_comb", 2, 21, 30, 6, spatial="ISS2", pairs="combination", seed=57)
 
 
+def ipa_cases():
+    """spatial_algorithm="IPA" (ilrma.py:1813-1908, iva.py:2068-2176)."""
+    ilrma_case("ilrma_ipa", 3, 17, 23, 4, 5, spatial="IPA", seed=60)
+    ilrma_case("ilrma_ipa_n2_p1_it3", 2, 21, 30, 3, 5, spatial="IPA", domain=1, ipa=(True, 3), seed=61)
+    ilrma_case("ilrma_ipa_n4_nonorm_part", 4, 12, 40, 5, 4, spatial="IPA", ipa=(False, 2), partitioning=True, seed=62)
+    iva_case("iva_laplace_ipa", 3, 17, 23, 6, spatial="IPA", seed=63)
+    iva_case("iva_gauss_ipa_n4", 4, 12, 40, 5, model="gauss", spatial="IPA", ipa=(True, 2), seed=64)
+    iva_case("iva_laplace_ipa_n2", 2, 21, 30, 6, spatial="IPA", ipa=(False, 1), seed=65)
+
+
 def mdp_cases():
     """minimal_distortion_principle standalone + as scale_restoration of GaussILRMA / AuxLaplaceIVA."""
     from ssspy.algorithm import minimal_distortion_principle
@@ -279,6 +297,7 @@ def main():
     tggd_cases()
     partitioning_cases()
     iss2_cases()
+    ipa_cases()
     # GaussILRMA: spatial x source x domain x normalisation x flooring grid (regression-test pattern,
     # tests/regression/bss/test_ilrma.py:48-62: inject basis/activation, fixed n_iter, compare).
     ilrma_case("ilrma_ip1_mm_n2", 2, 33, 40, 4, 10)

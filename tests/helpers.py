@@ -47,3 +47,9 @@ def dist_arg(g):
     """(kind, parameter) of the source distribution stored in an ILRMA fixture (Gauss when absent)."""
     kind = str(g["dist"]) if "dist" in g else "gauss"
     return (kind, float(g["dist_param"]) if kind != "gauss" else None)
+
+
+def ipa_arg(g):
+    """(lqpqm_normalization, newton_iter) stored in a fixture (the reference's defaults when absent)."""
+    return (bool(g["ipa_normalization"]) if "ipa_normalization" in g else True,
+            int(g["ipa_newton_iter"]) if "ipa_newton_iter" in g else 1)

@@ -9,7 +9,7 @@ from oracle import linalg as olinalg
 from oracle import spatial as ospatial
 from oracle.projection_back import projection_back
 
-from helpers import FLOORS, dist_arg, golden_cases, load, norm_arg, phase_align_rows, relerr, sr_arg
+from helpers import FLOORS, dist_arg, golden_cases, ipa_arg, load, norm_arg, phase_align_rows, relerr, sr_arg
 
 TOL = 1e-9
 
@@ -23,7 +23,7 @@ def test_ilrma_oracle_matches_reference(name):
                     source_algorithm=str(g["source"]), normalization=norm_arg(g["normalization"]),
                     pairs=[tuple(p) for p in g["pairs"]], reference_id=ref_id,
                     scale_restoration=sr_arg(g["scale_restoration"]), snapshots=True, dist=dist_arg(g),
-                    Z=g.get("Z0"))
+                    Z=g.get("Z0"), ipa=ipa_arg(g))
     if "Z" in g:
         assert relerr(st["Z"], g["Z"]) < TOL
     assert relerr(st["Y"], g["Y"]) < TOL
@@ -46,7 +46,7 @@ def test_iva_oracle_matches_reference(name):
     st = oiva.run(g["X"], int(g["n_iter"]), W=g.get("W0"), floor=FLOORS[str(g["flooring"])],
                   spatial_algorithm=str(g["spatial"]), model=str(g["model"]),
                   pairs=[tuple(p) for p in g["pairs"]], reference_id=int(g["reference_id"]),
-                  scale_restoration=sr_arg(g["scale_restoration"]))
+                  scale_restoration=sr_arg(g["scale_restoration"]), ipa=ipa_arg(g))
     assert relerr(st["Y"], g["Y"]) < TOL
     np.testing.assert_allclose(st["loss"], g["loss"], rtol=1e-10, atol=1e-9)
     if "W" in g:
@@ -71,12 +71,15 @@ def test_spatial_kernels_oracle(N):
         Y = oilrma.separate(X, W)
         assert relerr(ospatial.update_by_iss1(Y, phi, FLOORS[fl]), g[f"N{N}_iss1_{fl}"]) < TOL
         assert _ip2_err(ospatial.update_by_iss2(Y, phi, FLOORS[fl]), g[f"N{N}_iss2_{fl}"]) < TOL
+        assert relerr(ospatial.update_by_ipa(Y, phi, FLOORS[fl]), g[f"N{N}_ipa_{fl}"]) < TOL
     neg = [(m - N, (m + 1) % N - N) for m in range(N)]
     assert _ip2_err(ospatial.update_by_ip2(W, U, pairs=neg), g[f"N{N}_ip2_negpairs"]) < TOL
     import itertools
     comb = list(itertools.combinations(range(N), 2))
     assert _ip2_err(ospatial.update_by_ip2(W, U, pairs=comb), g[f"N{N}_ip2_comb"]) < TOL
     assert _ip2_err(ospatial.update_by_ip2_one_pair(W, U[:, (0, 1)], (0, 1)), g[f"N{N}_ip2pair01"]) < TOL
+    assert relerr(ospatial.update_by_ipa(Y, phi, normalization=False, max_iter=5), g[f"N{N}_ipa_nonorm_it5"]) < TOL
+    assert relerr(ospatial.update_by_ipa(Y, phi[:, :1, :], max_iter=2), g[f"N{N}_ipa_frameweights"]) < TOL
     # ISS2: rows of the updated pair carry the eigenvector's free phase per bin
     seq = [(m, (m + 1) % N) for m in range(N)]
     assert _ip2_err(ospatial.update_by_iss2(Y, phi, pairs=seq), g[f"N{N}_iss2_seq"]) < TOL
