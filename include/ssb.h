@@ -51,7 +51,9 @@ enum {
 };
 /* spatial_algorithm (ssspy/bss/ilrma.py:27, ssspy/bss/iva.py:44) */
 enum { SSB_SPATIAL_IP1 = 0, SSB_SPATIAL_IP2 = 1, SSB_SPATIAL_ISS1 = 2,
-       SSB_SPATIAL_ISS2 = 3 /* pairwise ISS, ssspy/bss/_update_spatial_model.py:197-314; uses `pairs` */ };
+       SSB_SPATIAL_ISS2 = 3 /* pairwise ISS, ssspy/bss/_update_spatial_model.py:197-314; uses `pairs` */,
+       SSB_SPATIAL_IPA = 4 /* iterative projection with adjustment, _update_spatial_model.py:398-513; state in Y like
+                              ISS; uses `ipa_normalization` / `ipa_newton_iter` (GaussILRMA and AuxIVA only) */ };
 /* source_algorithm (ssspy/bss/ilrma.py:28) */
 enum { SSB_SOURCE_MM = 0, SSB_SOURCE_ME = 1 };
 /* flooring_fn (ssspy/special/flooring.py:6-18): max(x,eps) | x+eps | identity */
@@ -88,6 +90,8 @@ typedef struct ssb_config {
   int32_t partitioning; /* ILRMA family only, 1: partitioning function (ilrma.py:201-245): T is [B,I,K] and V is
                            [B,K,J], shared by the sources, and the `variance` slot of ssb_plan_bind holds the
                            latent variable Z[B,N,K] f32 (ilrma.py:219-226); power normalisation only */
+  int32_t ipa_normalization; /* IPA: lqpqm_normalization (ilrma.py:749, iva.py:1579; default 1) */
+  int32_t ipa_newton_iter;   /* IPA: newton_iter, Newton-Raphson updates of the LQPQM root (default 1) */
 } ssb_config;
 
 typedef struct ssb_plan ssb_plan;
@@ -171,6 +175,11 @@ int ssb_update_by_iss1(void* Y, const float* phi, long long phi_sb, long long ph
  * indices already wrapped into [0, N) (the reference's default is (0,1),(2,3),..., :233-234) */
 int ssb_update_by_iss2(void* Y, const float* phi, long long phi_sb, long long phi_sn, long long phi_si, int B, int N,
                        int I, int J, const int32_t* pairs, int n_pairs, int flooring, float eps, void* stream);
+/* update_by_ipa (_update_spatial_model.py:398-513, ssspy/linalg/lqpqm.py:13-292): iterative projection with
+ * adjustment on Y[B,N,I,J] in place; phi addressed as in ssb_weighted_covariance; normalization / max_iter are the
+ * reference's `normalization` and `max_iter` arguments */
+int ssb_update_by_ipa(void* Y, const float* phi, long long phi_sb, long long phi_sn, long long phi_si, int B, int N,
+                      int I, int J, int normalization, int max_iter, int flooring, float eps, void* stream);
 /* projection_back, filter form (ssspy/algorithm/projection_back.py:87-99):
  * Wout[m,n,:] = W[m,n,:] * (W[m]^-1)[ref, n]; Wout may alias W. */
 int ssb_projection_back_w(const void* W, void* Wout, int n_mat, int N, int reference_id, void* stream);

@@ -15,7 +15,7 @@ SSB_MAX_PAIRS = 64
 
 MODEL_ILRMA_GAUSS, MODEL_IVA_LAPLACE, MODEL_IVA_GAUSS, MODEL_FASTMNMF_GAUSS = 0, 1, 2, 3
 MODEL_ILRMA_T, MODEL_ILRMA_GGD = 4, 5
-SPATIAL_IP1, SPATIAL_IP2, SPATIAL_ISS1, SPATIAL_ISS2 = 0, 1, 2, 3
+SPATIAL_IP1, SPATIAL_IP2, SPATIAL_ISS1, SPATIAL_ISS2, SPATIAL_IPA = 0, 1, 2, 3, 4
 SOURCE_MM, SOURCE_ME = 0, 1
 FLOOR_MAX, FLOOR_ADD, FLOOR_NONE = 0, 1, 2
 NORM_NONE, NORM_POWER, NORM_PROJECTION_BACK = 0, 1, 2
@@ -30,6 +30,7 @@ class SsbConfig(ctypes.Structure):
         ("reference_id", ctypes.c_int32), ("n_pairs", ctypes.c_int32),
         ("pairs", ctypes.c_int32 * (2 * SSB_MAX_PAIRS)), ("fast_path", ctypes.c_int32),
         ("model_param", ctypes.c_float), ("partitioning", ctypes.c_int32),
+        ("ipa_normalization", ctypes.c_int32), ("ipa_newton_iter", ctypes.c_int32),
     ]
 
 
@@ -66,6 +67,7 @@ SIGNATURES = {
     "ssb_update_by_ip2_one_pair": [_vp, _vp, _i, _i, _i, _i, _i, _f, _vp],
     "ssb_update_by_iss1": [_vp, _vp, _ll, _ll, _ll, _i, _i, _i, _i, _i, _f, _vp],
     "ssb_update_by_iss2": [_vp, _vp, _ll, _ll, _ll, _i, _i, _i, _i, _i32p, _i, _i, _f, _vp],
+    "ssb_update_by_ipa": [_vp, _vp, _ll, _ll, _ll, _i, _i, _i, _i, _i, _i, _i, _f, _vp],
     "ssb_projection_back_w": [_vp, _vp, _i, _i, _i, _vp],
     "ssb_projection_back_y": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "ssb_inv": [_vp, _vp, _i, _i, _vp],

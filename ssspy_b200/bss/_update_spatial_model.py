@@ -1,6 +1,6 @@
 """Standalone spatial-update operators on the device (host mirror of
 ssspy/bss/_update_spatial_model.py: update_by_ip1 :17-78, update_by_ip2 :81-143,
-update_by_ip2_one_pair :317-395, update_by_iss1 :146-194, update_by_iss2 :197-314).
+update_by_ip2_one_pair :317-395, update_by_iss1 :146-194, update_by_iss2 :197-314, update_by_ipa :398-513).
 
 Same argument meaning as the reference; leading batch axes are allowed.  NumPy in -> NumPy
 (complex128) out, CUDA tensors in -> CUDA tensors out.  ``overwrite=True`` writes the result back
@@ -120,6 +120,30 @@ def update_by_iss2(separated, weight, flooring_fn=_DEFAULT_FLOOR, pair_selector=
         chunk = pairs[q0:q0 + _lib.SSB_MAX_PAIRS]
         _lib.call("ssb_update_by_iss2", Yb.data_ptr(), phi.data_ptr(), sb, sn, si, B, N, I, J,
                   _lib.pairs_array(chunk), len(chunk), mode, eps, _device.stream_ptr())
+    if _device.is_tensor(separated):
+        return Y.to(separated.dtype)
+    return Y.cpu().numpy().astype(np.complex128)
+
+
+def update_by_ipa(separated, weight, normalization=True, flooring_fn=_DEFAULT_FLOOR, max_iter=1):
+    """Iterative projection with adjustment (ssspy/bss/_update_spatial_model.py:398-513): ``separated`` (N, I, J) [or
+    (B, N, I, J)], ``weight`` broadcastable to its shape, ``normalization`` / ``max_iter`` as in the reference (trace
+    normalisation of the LQPQM and number of Newton-Raphson updates, ssspy/linalg/lqpqm.py:13-219)."""
+    mode, eps = flooring_to_enum(flooring_fn)
+    Y = _device.to_device(separated, torch.complex64).clone()
+    batched = Y.dim() == 4
+    Yb = Y if batched else Y.unsqueeze(0)
+    B, N, I, J = Yb.shape
+    phi = _device.to_device(weight, torch.float32)
+    phi = phi if batched else phi.unsqueeze(0)
+    if phi.shape[-2] == 1 and I != 1:
+        phi = phi.expand(B, N, 1, J).contiguous()
+        sb, sn, si = N * J, J, 0
+    else:
+        phi = phi.expand(B, N, I, J).contiguous()
+        sb, sn, si = N * I * J, I * J, J
+    _lib.call("ssb_update_by_ipa", Yb.data_ptr(), phi.data_ptr(), sb, sn, si, B, N, I, J, int(bool(normalization)),
+              int(max_iter), mode, eps, _device.stream_ptr())
     if _device.is_tensor(separated):
         return Y.to(separated.dtype)
     return Y.cpu().numpy().astype(np.complex128)

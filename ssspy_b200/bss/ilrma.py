@@ -31,7 +31,8 @@ PROJECTION_BACK_KEYWORDS = ["projection_back", "projection-back", "PB"]
 MINIMAL_DISTORTION_PRINCIPLE_KEYWORDS = ["minimal_distortion_principle", "minimal-distortion-principle", "MDP"]
 
 _SPATIAL_ENUM = {"IP": _lib.SPATIAL_IP1, "IP1": _lib.SPATIAL_IP1, "IP2": _lib.SPATIAL_IP2,
-                 "ISS": _lib.SPATIAL_ISS1, "ISS1": _lib.SPATIAL_ISS1, "ISS2": _lib.SPATIAL_ISS2}
+                 "ISS": _lib.SPATIAL_ISS1, "ISS1": _lib.SPATIAL_ISS1, "ISS2": _lib.SPATIAL_ISS2,
+                 "IPA": _lib.SPATIAL_IPA}
 
 
 def _not_on_device(what):
@@ -191,6 +192,8 @@ class ILRMABase(DeviceSeparatorMixin, IterativeMethodBase):
             cfg.pairs[2 * q], cfg.pairs[2 * q + 1] = m, n
         cfg.fast_path = 1 if getattr(self, "fast_path", True) else 0
         cfg.partitioning = 1 if self.partitioning else 0
+        cfg.ipa_normalization = 1 if getattr(self, "lqpqm_normalization", True) else 0
+        cfg.ipa_newton_iter = int(getattr(self, "newton_iter", 1))
         return cfg
 
     # ---- normalisation (ilrma.py:333-514) ----------------------------------------------------------
@@ -384,6 +387,12 @@ class _DeviceILRMA(ILRMABase):
         assert self.spatial_algorithm == "ISS2"
         self.update_spatial_model(flooring_fn=flooring_fn)
 
+    def update_spatial_model_ipa(self, flooring_fn="self"):
+        """Iterative projection with adjustment with ``self.lqpqm_normalization`` / ``self.newton_iter``
+        (ilrma.py:1813-1908)."""
+        assert self.spatial_algorithm == "IPA"
+        self.update_spatial_model(flooring_fn=flooring_fn)
+
     def compute_loss(self):
         """Negative log-likelihood (ilrma.py:1910-1967): a ``float`` for a single mixture, an array of
         shape (batch,) for batched input."""
@@ -392,6 +401,9 @@ class _DeviceILRMA(ILRMABase):
 
 class GaussILRMA(_DeviceILRMA):
     """ssspy/bss/ilrma.py:582-1989 (signature :752-772)."""
+
+    _ipa_default_kwargs = {"lqpqm_normalization": True, "newton_iter": 1}  # ilrma.py:749-750
+    _default_kwargs = _ipa_default_kwargs
 
     def __init__(self, n_basis, spatial_algorithm="IP", source_algorithm="MM", domain=2, partitioning=False,
                  flooring_fn=functools.partial(max_flooring, eps=EPS), pair_selector=None, callbacks=None,
@@ -405,8 +417,15 @@ class GaussILRMA(_DeviceILRMA):
         if source_algorithm == "ME":
             assert domain == 2, "domain parameter should be 2 when you specify ME algorithm."
         self._init_algorithms(spatial_algorithm, source_algorithm, domain, partitioning, normalization, pair_selector)
-        invalid_keys = set(kwargs)  # IPA-only keywords are the only valid extras (ilrma.py:802-812)
+        # IPA-only keywords are the only valid extras (ilrma.py:802-818)
+        valid_keys = set(self._ipa_default_kwargs) if spatial_algorithm == "IPA" else set()
+        invalid_keys = set(kwargs) - valid_keys
         assert invalid_keys == set(), "Invalid keywords {} are given.".format(invalid_keys)
+        for key, value in kwargs.items():
+            setattr(self, key, value)
+        for key in valid_keys:
+            if not hasattr(self, key):
+                setattr(self, key, self._default_kwargs[key])
 
     def __repr__(self):
         return self._repr_fields("GaussILRMA", "")

@@ -113,6 +113,8 @@ class AuxIVA(AuxIVABase):
     """ssspy/bss/iva.py:1403-2214 (signature :1582-1598)."""
 
     _model = None  # set by the Laplace / Gauss subclasses
+    _ipa_default_kwargs = {"lqpqm_normalization": True, "newton_iter": 1}  # iva.py:1579-1580
+    _default_kwargs = _ipa_default_kwargs
 
     def __init__(self, spatial_algorithm="IP", contrast_fn=None, d_contrast_fn=None,
                  flooring_fn=functools.partial(max_flooring, eps=EPS), pair_selector=None, callbacks=None,
@@ -129,8 +131,15 @@ class AuxIVA(AuxIVABase):
                 self.pair_selector = sequential_pair_selector
         else:
             self.pair_selector = pair_selector
-        invalid_keys = set(kwargs)
+        # IPA-only keywords are the only valid extras (iva.py:1619-1635)
+        valid_keys = set(self._ipa_default_kwargs) if spatial_algorithm == "IPA" else set()
+        invalid_keys = set(kwargs) - valid_keys
         assert invalid_keys == set(), "Invalid keywords {} are given.".format(invalid_keys)
+        for key, value in kwargs.items():
+            setattr(self, key, value)
+        for key in valid_keys:
+            if not hasattr(self, key):
+                setattr(self, key, self._default_kwargs[key])
 
     def __call__(self, input, n_iter=100, initial_call=True, **kwargs):
         """iva.py:1637-1672."""
@@ -196,6 +205,8 @@ class AuxIVA(AuxIVABase):
         for q, (m, n) in enumerate(pairs):
             cfg.pairs[2 * q], cfg.pairs[2 * q + 1] = m, n
         cfg.fast_path = 1 if getattr(self, "fast_path", True) else 0
+        cfg.ipa_normalization = 1 if getattr(self, "lqpqm_normalization", True) else 0
+        cfg.ipa_newton_iter = int(getattr(self, "newton_iter", 1))
         return cfg
 
     def update_source_model(self):
@@ -224,6 +235,11 @@ class AuxIVA(AuxIVABase):
     def update_once_iss2(self, flooring_fn="self"):
         """Pairwise ISS over ``pair_selector(n_sources)`` with weights from the current output (iva.py:1968-2066)."""
         assert self.spatial_algorithm == "ISS2"
+        AuxIVA.update_once(self, flooring_fn=flooring_fn)
+
+    def update_once_ipa(self, flooring_fn="self"):
+        """Iterative projection with adjustment with weights from the current output (iva.py:2068-2176)."""
+        assert self.spatial_algorithm == "IPA"
         AuxIVA.update_once(self, flooring_fn=flooring_fn)
 
 

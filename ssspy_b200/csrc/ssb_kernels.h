@@ -45,6 +45,8 @@ int ssbk_iss1(cf* Y, const float* phi, long long sb, long long sn, long long si,
 // pairs (host, 2*n_pairs, already wrapped into [0, N)); _update_spatial_model.py:197-314
 int ssbk_iss2(cf* Y, const float* phi, long long sb, long long sn, long long si, int B, int N, int I, int J,
               const int* pairs, int n_pairs, int flooring, float eps, cudaStream_t st);
+int ssbk_ipa(cf* Y, const float* phi, long long sb, long long sn, long long si, int B, int N, int I, int J,
+             int normalization, int max_iter, int flooring, float eps, cudaStream_t st);
 int ssbk_pb_w(const cf* W, cf* Wout, cf* scale_out, int n_mat, int N, int ref, cudaStream_t st);
 int ssbk_cross_solve(const cf* A, const cf* Bm, cf* S, int B, int N, int I, int J, cudaStream_t st);
 int ssbk_scale_rows(const cf* Y, const cf* S, cf* Yout, int B, int N, int I, int J, int ref, cudaStream_t st);

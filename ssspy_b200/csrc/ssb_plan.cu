@@ -140,7 +140,11 @@ struct ssb_plan {
   float *hnum = nullptr, *hden = nullptr;  // [B,N,K,J]
   bool part() const { return cfg.partitioning != 0; }
   bool mnmf() const { return cfg.model == SSB_MODEL_FASTMNMF_GAUSS; }
-  bool iss() const { return (cfg.spatial == SSB_SPATIAL_ISS1 || cfg.spatial == SSB_SPATIAL_ISS2) && !mnmf(); }
+  // modes whose state lives in Y (no demixing filter): ISS1 / ISS2 / IPA
+  bool iss() const {
+    return (cfg.spatial == SSB_SPATIAL_ISS1 || cfg.spatial == SSB_SPATIAL_ISS2 || cfg.spatial == SSB_SPATIAL_IPA) &&
+           !mnmf();
+  }
   bool ilrma() const {
     return cfg.model == SSB_MODEL_ILRMA_GAUSS || cfg.model == SSB_MODEL_ILRMA_T || cfg.model == SSB_MODEL_ILRMA_GGD;
   }
@@ -194,7 +198,12 @@ size_t carve(ssb_plan* p, char* base) {
 int validate(const ssb_config* c) {
   SSB_REQUIRE(c != nullptr, "config is NULL");
   SSB_REQUIRE(c->model >= 0 && c->model <= 5, "unknown model %d", c->model);
-  SSB_REQUIRE(c->spatial >= 0 && c->spatial <= 3, "Not support spatial algorithm id %d.", c->spatial);
+  SSB_REQUIRE(c->spatial >= 0 && c->spatial <= 4, "Not support spatial algorithm id %d.", c->spatial);
+  if (c->spatial == SSB_SPATIAL_IPA) {
+    SSB_REQUIRE(c->model != SSB_MODEL_ILRMA_T, "IPA is not supported for t-ILRMA.");
+    SSB_REQUIRE(c->model != SSB_MODEL_ILRMA_GGD, "IPA is not supported for GGD-ILRMA.");
+    SSB_REQUIRE(c->ipa_newton_iter >= 0, "newton_iter=%d must be non-negative", c->ipa_newton_iter);
+  }
   SSB_REQUIRE(c->source == SSB_SOURCE_MM || c->source == SSB_SOURCE_ME, "Not support source algorithm id %d.",
               c->source);
   SSB_REQUIRE(c->n_batch >= 1, "n_batch must be >= 1");
@@ -319,6 +328,8 @@ int ilrma_spatial(ssb_plan* p, cudaStream_t st) {
   if (c.spatial == SSB_SPATIAL_ISS1) return ssbk_iss1(p->Y, p->big, sb, sn, si, B, N, I, J, c.flooring, c.eps, st);
   if (c.spatial == SSB_SPATIAL_ISS2)
     return ssbk_iss2(p->Y, p->big, sb, sn, si, B, N, I, J, c.pairs, c.n_pairs, c.flooring, c.eps, st);
+  if (c.spatial == SSB_SPATIAL_IPA)  // ilrma.py:1813-1908
+    return ssbk_ipa(p->Y, p->big, sb, sn, si, B, N, I, J, c.ipa_normalization, c.ipa_newton_iter, c.flooring, c.eps, st);
   TRY(ssbk_wcov(p->X, p->big, sb, sn, si, nullptr, N, p->U, B, N, I, J, st));
   if (c.spatial == SSB_SPATIAL_IP1) return ssbk_ip1(p->W, p->U, B * I, N, c.flooring, c.eps, st);
   return ssbk_ip2(p->W, p->U, B * I, N, c.pairs, c.n_pairs, N, nullptr, c.flooring, c.eps, st);
@@ -400,6 +411,9 @@ int iva_spatial(ssb_plan* p, cudaStream_t st) {
     return ssbk_iss1(p->Y, p->phi_iva, (long long)N * J, J, 0, B, N, I, J, c.flooring, c.eps, st);
   if (c.spatial == SSB_SPATIAL_ISS2)  // iva.py:1968-2066: weights once, then every pair
     return ssbk_iss2(p->Y, p->phi_iva, (long long)N * J, J, 0, B, N, I, J, c.pairs, c.n_pairs, c.flooring, c.eps, st);
+  if (c.spatial == SSB_SPATIAL_IPA)  // iva.py:2068-2176
+    return ssbk_ipa(p->Y, p->phi_iva, (long long)N * J, J, 0, B, N, I, J, c.ipa_normalization, c.ipa_newton_iter,
+                    c.flooring, c.eps, st);
   if (c.fast_path && (J % 16) == 0) TRY(ssb_fused_cov_w(p->X, p->phi_iva, (long long)N * J, J, 0, N, p->U, B, N, I, J, st));
   else TRY(ssbk_wcov(p->X, p->phi_iva, (long long)N * J, J, 0, nullptr, N, p->U, B, N, I, J, st));
   return ssbk_ip1(p->W, p->U, B * I, N, c.flooring, c.eps, st);
@@ -582,6 +596,9 @@ extern "C" int ssb_update_once(ssb_plan* p, void* stream) {
       if (c.spatial == SSB_SPATIAL_ISS2)
         TRY(ssbk_iss2(p->Y, p->big, (long long)N * I * J, (long long)I * J, J, B, N, I, J, c.pairs, c.n_pairs,
                       c.flooring, c.eps, st));
+      else if (c.spatial == SSB_SPATIAL_IPA)
+        TRY(ssbk_ipa(p->Y, p->big, (long long)N * I * J, (long long)I * J, J, B, N, I, J, c.ipa_normalization,
+                     c.ipa_newton_iter, c.flooring, c.eps, st));
       else
         TRY(ssbk_iss1(p->Y, p->big, (long long)N * I * J, (long long)I * J, J, B, N, I, J, c.flooring, c.eps, st));
       if (c.normalization != SSB_NORM_NONE) TRY(ilrma_normalize(p, st));
@@ -731,6 +748,15 @@ extern "C" int ssb_update_by_iss2(void* Y, const float* phi, long long phi_sb, l
   if (B <= 0 || I <= 0 || J <= 0 || n_pairs == 0) return 0;
   return ssbk_iss2((cf*)Y, phi, phi_sb, phi_sn, phi_si, B, N, I, J, pairs, n_pairs, flooring, eps,
                    (cudaStream_t)stream);
+}
+
+extern "C" int ssb_update_by_ipa(void* Y, const float* phi, long long phi_sb, long long phi_sn, long long phi_si,
+                                 int B, int N, int I, int J, int normalization, int max_iter, int flooring, float eps,
+                                 void* stream) {
+  SSB_REQUIRE(Y && phi, "NULL argument");
+  if (B <= 0 || I <= 0 || J <= 0) return 0;
+  return ssbk_ipa((cf*)Y, phi, phi_sb, phi_sn, phi_si, B, N, I, J, normalization, max_iter, flooring, eps,
+                  (cudaStream_t)stream);
 }
 
 extern "C" int ssb_projection_back_w(const void* W, void* Wout, int n_mat, int N, int reference_id, void* stream) {

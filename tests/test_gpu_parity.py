@@ -10,7 +10,7 @@ import itertools
 import numpy as np
 import pytest
 
-from helpers import FLOORS, dist_arg, golden_cases, load, norm_arg, phase_align_rows, relerr, sr_arg
+from helpers import FLOORS, dist_arg, golden_cases, ipa_arg, load, norm_arg, phase_align_rows, relerr, sr_arg
 
 pytestmark = pytest.mark.gpu
 
@@ -55,6 +55,8 @@ def _make_ilrma(g, **over):
               pair_selector=_pair_selector(g["pairs"]) if spatial in ("IP2", "ISS2") else None,
               normalization=norm_arg(g["normalization"]), scale_restoration=sr_arg(g["scale_restoration"]),
               record_loss=True, reference_id=ref_id, rng=np.random.default_rng(0), partitioning="Z0" in g)
+    if spatial == "IPA":
+        kw.update(lqpqm_normalization=ipa_arg(g)[0], newton_iter=ipa_arg(g)[1])
     kw.update(over)
     kind, prm = dist_arg(g)
     if kind == "t":
@@ -103,9 +105,11 @@ def test_aux_iva_matches_reference(name):
     spatial = str(g["spatial"])
     cls = AuxLaplaceIVA if str(g["model"]) == "laplace" else AuxGaussIVA
     kwargs = {"demix_filter": g["W0"]} if "W0" in g else {}
+    extra = dict(lqpqm_normalization=ipa_arg(g)[0], newton_iter=ipa_arg(g)[1]) if spatial == "IPA" else {}
     m = cls(spatial_algorithm=spatial, flooring_fn=_floor_fn(str(g["flooring"])),
             pair_selector=_pair_selector(g["pairs"]) if spatial in ("IP2", "ISS2") else None,
-            scale_restoration=sr_arg(g["scale_restoration"]), record_loss=True, reference_id=int(g["reference_id"]))
+            scale_restoration=sr_arg(g["scale_restoration"]), record_loss=True, reference_id=int(g["reference_id"]),
+            **extra)
     Y = m(g["X"], n_iter=int(g["n_iter"]), **kwargs)
     assert Y.shape == g["Y"].shape
     assert_loss_close(m.loss, g["loss"])
@@ -124,7 +128,7 @@ def test_spatial_operators_match_reference(N):
     """update_by_ip1 / ip2 / ip2_one_pair / iss1 on the reference's own smoke-test shapes
     (tests/package/bss/test_update_spatial_model.py:45-171), incl. negative pair indices."""
     from ssspy_b200.bss._update_spatial_model import (update_by_ip1, update_by_ip2, update_by_ip2_one_pair,
-                                                     update_by_iss1, update_by_iss2)
+                                                     update_by_ipa, update_by_iss1, update_by_iss2)
     from ssspy_b200.utils.select_pair import combination_pair_selector, sequential_pair_selector
     g = load("spatial_kernels")
     X, phi, W, U = (g[f"N{N}_{k}"] for k in ("X", "phi", "W", "U"))
@@ -139,6 +143,12 @@ def test_spatial_operators_match_reference(N):
         out = update_by_iss2(Y, phi, flooring_fn=_floor_fn(fl))  # default pairs (0,1),(2,3),...
         assert out.shape == Y.shape
         assert relerr(phase_align_rows(out, g[f"N{N}_iss2_{fl}"]), g[f"N{N}_iss2_{fl}"]) < 2e-5
+        out = update_by_ipa(Y, phi, flooring_fn=_floor_fn(fl))
+        assert out.shape == Y.shape and relerr(out, g[f"N{N}_ipa_{fl}"]) < 2e-5
+    out = update_by_ipa(Y, phi, normalization=False, max_iter=5)
+    assert relerr(out, g[f"N{N}_ipa_nonorm_it5"]) < 2e-5
+    out = update_by_ipa(Y, phi[:, :1, :], max_iter=2)  # weights shared by the bins (the AuxIVA case)
+    assert relerr(out, g[f"N{N}_ipa_frameweights"]) < 2e-5
 
     def neg_sel(n):
         for m in range(n):
@@ -336,8 +346,10 @@ def test_error_paths_match_reference():
         GaussILRMA(n_basis=2, source_algorithm="ME", domain=1)
     with pytest.raises(ValueError, match="Specify 'reference_id'"):
         GaussILRMA(n_basis=2, reference_id=None)
-    with pytest.raises(NotImplementedError):
-        GaussILRMA(n_basis=2, spatial_algorithm="IPA")
+    with pytest.raises(AssertionError, match="Invalid keywords"):
+        GaussILRMA(n_basis=2, spatial_algorithm="IP", newton_iter=2)  # IPA-only keyword (ilrma.py:802-809)
+    ipa = GaussILRMA(n_basis=2, spatial_algorithm="IPA", newton_iter=3)
+    assert ipa.newton_iter == 3 and ipa.lqpqm_normalization is True
     X = np.random.default_rng(0).standard_normal((2, 9, 12)) + 0j
     m = AuxLaplaceIVA(spatial_algorithm="ISS")
     m(X, n_iter=1)

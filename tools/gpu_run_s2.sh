@@ -1,0 +1,5 @@
+set -x
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -25 > gpurun_out/r1s2_gputests.log
+cat gpurun_out/r1s2_gputests.log
