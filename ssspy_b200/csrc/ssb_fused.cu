@@ -111,6 +111,86 @@ __device__ __forceinline__ void power2(const float4 (&x)[N], const cf (&w)[N], f
   p1 = fmaf(r1, r1, i1 * i1);
 }
 
+
+// ---- Hermitian rank-one accumulation shared by the covariance kernels -------------------------------
+// U_s += phi_s x x^H for G sources of one (bin, frame): the N(N-1)/2 complex products x_a conj(x_c) and the N
+// powers |x_a|^2 are formed once and shared by the G sources; each accumulator is a (re, im) [or a pair of
+// diagonal entries] float2 updated with one packed FFMA2 (fma.rn.f32x2, sm_100+), i.e. N^2/2 issue slots per
+// source instead of 2N^2 + 2N scalar FMA/MUL.
+template <int N, int G>
+struct HermAcc {
+  static constexpr int NO = N * (N - 1) / 2, ND = (N + 1) / 2;
+  float2 o[G][NO], d[G][ND];
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int gs = 0; gs < G; ++gs) {
+#pragma unroll
+      for (int e = 0; e < NO; ++e) o[gs][e] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < ND; ++k) d[gs][k] = make_float2(0.f, 0.f);
+    }
+  }
+  __device__ __forceinline__ void add(const float (&xr)[N], const float (&xi)[N], const float (&ph)[G]) {
+    float2 pp[G];
+#pragma unroll
+    for (int gs = 0; gs < G; ++gs) pp[gs] = make_float2(ph[gs], ph[gs]);
+    int e = 0;
+#pragma unroll
+    for (int a = 0; a < N; ++a)
+#pragma unroll
+      for (int c = a + 1; c < N; ++c, ++e) {
+        // x_a conj(x_c)
+        const float2 pr = make_float2(fmaf(xr[a], xr[c], xi[a] * xi[c]), fmaf(xi[a], xr[c], -(xr[a] * xi[c])));
+#pragma unroll
+        for (int gs = 0; gs < G; ++gs) o[gs][e] = __ffma2_rn(pp[gs], pr, o[gs][e]);
+      }
+#pragma unroll
+    for (int k = 0; k < ND; ++k) {
+      const int a = 2 * k, c = (2 * k + 1 < N) ? 2 * k + 1 : 2 * k;
+      const float2 pr = make_float2(fmaf(xr[a], xr[a], xi[a] * xi[a]),
+                                    (2 * k + 1 < N) ? fmaf(xr[c], xr[c], xi[c] * xi[c]) : 0.f);
+#pragma unroll
+      for (int gs = 0; gs < G; ++gs) d[gs][k] = __ffma2_rn(pp[gs], pr, d[gs][k]);
+    }
+  }
+  // sum over the four lanes of a row group (xor 1, 2), scale, and write U[N x N] of source slot gs
+  __device__ __forceinline__ void reduce4(float scale) {
+#pragma unroll
+    for (int gs = 0; gs < G; ++gs) {
+#pragma unroll
+      for (int e = 0; e < NO; ++e) {
+        float2 v = o[gs][e];
+        v.x += __shfl_xor_sync(SSB_FULL, v.x, 1);
+        v.y += __shfl_xor_sync(SSB_FULL, v.y, 1);
+        v.x += __shfl_xor_sync(SSB_FULL, v.x, 2);
+        v.y += __shfl_xor_sync(SSB_FULL, v.y, 2);
+        o[gs][e] = make_float2(v.x * scale, v.y * scale);
+      }
+#pragma unroll
+      for (int k = 0; k < ND; ++k) {
+        float2 v = d[gs][k];
+        v.x += __shfl_xor_sync(SSB_FULL, v.x, 1);
+        v.y += __shfl_xor_sync(SSB_FULL, v.y, 1);
+        v.x += __shfl_xor_sync(SSB_FULL, v.x, 2);
+        v.y += __shfl_xor_sync(SSB_FULL, v.y, 2);
+        d[gs][k] = make_float2(v.x * scale, v.y * scale);
+      }
+    }
+  }
+  __device__ __forceinline__ void store(int gs, cf* u) const {
+    int e = 0;
+#pragma unroll
+    for (int a = 0; a < N; ++a) {
+      u[a * N + a] = make_float2((a & 1) ? d[gs][a >> 1].y : d[gs][a >> 1].x, 0.f);
+#pragma unroll
+      for (int c = a + 1; c < N; ++c, ++e) {
+        u[a * N + c] = o[gs][e];
+        u[c * N + a] = make_float2(o[gs][e].x, -o[gs][e].y);
+      }
+    }
+  }
+};
+
 // ------------------------------------------------------------------------------------------------
 // kf_basis.  CTA = (bin group of FW*16 bins, source n, mixture b); warp = 16 bins.
 // Fragment conventions (PTX m16n8k16): g = lane/4, t = lane%4;
@@ -622,10 +702,12 @@ __global__ void __launch_bounds__(FW * 32) kf_activation(const float* __restrict
 // lanes of a row group are reduced with shuffles at the end.
 template <int N>
 struct CovShape {
-  static constexpr int G = N == 2 ? 2 : (N == 3 ? 3 : (N == 4 ? 4 : 1));   // sources per CTA
+  static constexpr int G = N <= 4 ? N : 2;   // sources per pass (they share the Hermitian products of a frame)
   static constexpr bool RS = N >= 4;   // one row group (8 bins) of the warp tile per pass over the frames
-  static constexpr bool STG = N <= 3;  // cp.async ring for X in kf_phi_cov (shared memory permitting)
-  static constexpr bool STG_W = N <= 4;  // ... in kf_cov_w (no V tile in shared memory there)
+  static constexpr bool STG = true;    // cp.async ring for X in kf_phi_cov (direct loads leave the HBM latency exposed)
+  static constexpr bool STG_W = true;  // ... in kf_cov_w
+  // frames of V staged at a time in kf_phi_cov: G sources side by side must fit next to the X ring
+  static constexpr int jcc(int KP) { return G * KP >= 128 ? 64 : (G * KP >= 64 ? 128 : 256); }
 };
 
 template <int N, int KS>
@@ -635,14 +717,15 @@ __global__ void __launch_bounds__(FW * 32) kf_phi_cov(const cf* __restrict__ X, 
   constexpr int KP = 16 * KS;
   constexpr int JKS = KP + PADH;
   constexpr int G = CovShape<N>::G;
+  constexpr int JCC = CovShape<N>::jcc(KP);
   constexpr bool RS = CovShape<N>::RS;
   constexpr bool STG = CovShape<N>::STG;
   constexpr int NR = RS ? 1 : 2;   // row groups accumulated per pass
   constexpr int NLD = 2 * NR * N;  // 16-byte vectors per lane per step (rows of this pass only)
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __nv_bfloat16* vjk_hi = reinterpret_cast<__nv_bfloat16*>(smem_raw);  // [G][JC][JKS]
-  __nv_bfloat16* vjk_lo = vjk_hi + G * JC * JKS;
-  float4* xring = reinterpret_cast<float4*>(vjk_lo + G * JC * JKS);
+  __nv_bfloat16* vjk_hi = reinterpret_cast<__nv_bfloat16*>(smem_raw);  // [G][JCC][JKS]
+  __nv_bfloat16* vjk_lo = vjk_hi + G * JCC * JKS;
+  float4* xring = reinterpret_cast<float4*>(vjk_lo + G * JCC * JKS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -693,45 +776,41 @@ __global__ void __launch_bounds__(FW * 32) kf_phi_cov(const cf* __restrict__ X, 
             }
           }
       }
-      float acc[G][NR][N * N];
+      HermAcc<N, G> acc[NR];
 #pragma unroll
-      for (int gs = 0; gs < G; ++gs)
-#pragma unroll
-        for (int r = 0; r < NR; ++r)
-#pragma unroll
-          for (int e = 0; e < N * N; ++e) acc[gs][r][e] = 0.f;
+      for (int r = 0; r < NR; ++r) acc[r].zero();
 
       int step = 0;
       if (STG && warp_active) {
         issue(0, 0, rs);
         cp_async_commit();
       }
-      for (int jc0 = 0; jc0 < J; jc0 += JC) {
+      for (int jc0 = 0; jc0 < J; jc0 += JCC) {
         __syncthreads();
 #pragma unroll
         for (int gs = 0; gs < G; ++gs) {
-          constexpr int NIT = KP * JC / (FW * 32);
+          constexpr int NIT = KP * JCC / (FW * 32);
           const int n = n0 + gs;
           float vals[NIT];
 #pragma unroll
           for (int it = 0; it < NIT; ++it) {
             const int r = threadIdx.x + it * FW * 32;
-            const int k = r / JC, jj = r - k * JC;
+            const int k = r / JCC, jj = r - k * JCC;
             vals[it] = (n < N && k < K && jc0 + jj < J) ? __ldg(V + (((size_t)b * N + n) * K + k) * J + jc0 + jj) : 0.f;
           }
 #pragma unroll
           for (int it = 0; it < NIT; ++it) {
             const int r = threadIdx.x + it * FW * 32;
-            const int k = r / JC, jj = r - k * JC;
+            const int k = r / JCC, jj = r - k * JCC;
             __nv_bfloat16 h, l;
             split1(vals[it], &h, &l);
-            vjk_hi[(gs * JC + jj) * JKS + k] = h;
-            vjk_lo[(gs * JC + jj) * JKS + k] = l;
+            vjk_hi[(gs * JCC + jj) * JKS + k] = h;
+            vjk_lo[(gs * JCC + jj) * JKS + k] = l;
           }
         }
         __syncthreads();
         if (!warp_active) continue;
-        const int jend = min(JC, J - jc0);
+        const int jend = min(JCC, J - jc0);
         for (int jj = 0; jj < jend; jj += 16, ++step) {
           if (STG) {
             if (jc0 + jj + 16 < J) issue(jc0 + jj + 16, (step + 1) & 1, rs);
@@ -751,31 +830,39 @@ __global__ void __launch_bounds__(FW * 32) kf_phi_cov(const cf* __restrict__ X, 
                               : *reinterpret_cast<const float4*>(X + xrow[rr] + jc0 + jj + 8 * h + 2 * t + m * cs);
             }
             const int fr = jj + 8 * h + g;
+            // phi for every source of the pass: R = T V on the tensor pipe, then 1 / R
+            float phv[NR][2][G];
 #pragma unroll
             for (int gs = 0; gs < G; ++gs) {
               float R[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
               for (int ks = 0; ks < KS; ++ks) {
-                const __nv_bfloat16* ph = vjk_hi + (gs * JC + fr) * JKS + ks * 16 + 2 * t;
-                const __nv_bfloat16* pl = vjk_lo + (gs * JC + fr) * JKS + ks * 16 + 2 * t;
+                const __nv_bfloat16* ph = vjk_hi + (gs * JCC + fr) * JKS + ks * 16 + 2 * t;
+                const __nv_bfloat16* pl = vjk_lo + (gs * JCC + fr) * JKS + ks * 16 + 2 * t;
                 mma_split(R, Thi[gs][ks], Tlo[gs][ks], lds32(ph), lds32(ph + 8), lds32(pl), lds32(pl + 8));
               }
 #pragma unroll
               for (int r = 0; r < NR; ++r) {
                 const int rr = RS ? rs : r;
-                const float ph0 = fast_rcp(R[rr * 2 + 0]), ph1 = fast_rcp(R[rr * 2 + 1]);
-                float* ac = acc[gs][r];
-#pragma unroll
-                for (int a = 0; a < N; ++a) {
-                  const float ar0 = ph0 * x[r][a].x, ai0 = ph0 * x[r][a].y, ar1 = ph1 * x[r][a].z, ai1 = ph1 * x[r][a].w;
-                  ac[a * N + a] = fmaf(ar0, x[r][a].x, fmaf(ai0, x[r][a].y, fmaf(ar1, x[r][a].z, fmaf(ai1, x[r][a].w, ac[a * N + a]))));
-#pragma unroll
-                  for (int c = a + 1; c < N; ++c) {
-                    ac[a * N + c] = fmaf(ar0, x[r][c].x, fmaf(ai0, x[r][c].y, fmaf(ar1, x[r][c].z, fmaf(ai1, x[r][c].w, ac[a * N + c]))));
-                    ac[c * N + a] = fmaf(ai0, x[r][c].x, fmaf(-ar0, x[r][c].y, fmaf(ai1, x[r][c].z, fmaf(-ar1, x[r][c].w, ac[c * N + a]))));
-                  }
-                }
+                phv[r][0][gs] = fast_rcp(R[rr * 2 + 0]);
+                phv[r][1][gs] = fast_rcp(R[rr * 2 + 1]);
               }
+            }
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+              float xr[N], xi[N];
+#pragma unroll
+              for (int m = 0; m < N; ++m) {
+                xr[m] = x[r][m].x;
+                xi[m] = x[r][m].y;
+              }
+              acc[r].add(xr, xi, phv[r][0]);
+#pragma unroll
+              for (int m = 0; m < N; ++m) {
+                xr[m] = x[r][m].z;
+                xi[m] = x[r][m].w;
+              }
+              acc[r].add(xr, xi, phv[r][1]);
             }
           }
         }
@@ -783,30 +870,13 @@ __global__ void __launch_bounds__(FW * 32) kf_phi_cov(const cf* __restrict__ X, 
       if (STG) cp_async_wait<0>();
       if (warp_active) {
 #pragma unroll
-        for (int gs = 0; gs < G; ++gs) {
-          const int n = n0 + gs;
+        for (int r = 0; r < NR; ++r) {
+          const int rr = RS ? rs : r;
+          acc[r].reduce4(invJ);
 #pragma unroll
-          for (int r = 0; r < NR; ++r) {
-            const int rr = RS ? rs : r;
-#pragma unroll
-            for (int e = 0; e < N * N; ++e) {
-              float v = acc[gs][r][e];
-              v += __shfl_xor_sync(SSB_FULL, v, 1);
-              v += __shfl_xor_sync(SSB_FULL, v, 2);
-              acc[gs][r][e] = v * invJ;
-            }
-            if (t == 0 && rvalid[rr] && n < N) {
-              cf* u = U + (((size_t)b * I + row[rr]) * N + n) * N * N;
-#pragma unroll
-              for (int a = 0; a < N; ++a) {
-                u[a * N + a] = make_float2(acc[gs][r][a * N + a], 0.f);
-#pragma unroll
-                for (int c = a + 1; c < N; ++c) {
-                  u[a * N + c] = make_float2(acc[gs][r][a * N + c], acc[gs][r][c * N + a]);
-                  u[c * N + a] = make_float2(acc[gs][r][a * N + c], -acc[gs][r][c * N + a]);
-                }
-              }
-            }
+          for (int gs = 0; gs < G; ++gs) {
+            const int n = n0 + gs;
+            if (t == 0 && rvalid[rr] && n < N) acc[r].store(gs, U + (((size_t)b * I + row[rr]) * N + n) * N * N);
           }
         }
       }
@@ -862,13 +932,9 @@ __global__ void __launch_bounds__(FW * 32) kf_cov_w(const cf* __restrict__ X, co
   {
     const int s0 = blockIdx.x * G;
     for (int rs = 0; rs < (RS ? 2 : 1); ++rs) {
-      float acc[G][NR][N * N];
+      HermAcc<N, G> acc[NR];
 #pragma unroll
-      for (int gs = 0; gs < G; ++gs)
-#pragma unroll
-        for (int r = 0; r < NR; ++r)
-#pragma unroll
-          for (int e = 0; e < N * N; ++e) acc[gs][r][e] = 0.f;
+      for (int r = 0; r < NR; ++r) acc[r].zero();
       int step = 0;
       if (STG) {
         issue(0, 0, rs);
@@ -892,53 +958,41 @@ __global__ void __launch_bounds__(FW * 32) kf_cov_w(const cf* __restrict__ X, co
                             : *reinterpret_cast<const float4*>(X + xrow[rr] + jj + 8 * h + 2 * t + m * cs);
           }
 #pragma unroll
-          for (int gs = 0; gs < G; ++gs) {
-            const int s = min(s0 + gs, n_src - 1);
+          for (int r = 0; r < NR; ++r) {
+            float ph0[G], ph1[G];
 #pragma unroll
-            for (int r = 0; r < NR; ++r) {
+            for (int gs = 0; gs < G; ++gs) {
+              const int s = min(s0 + gs, n_src - 1);
               const float2 ph = *reinterpret_cast<const float2*>(phi + (size_t)b * sb + (size_t)s * sn +
                                                                  (size_t)rowc[RS ? rs : r] * si + jj + 8 * h + 2 * t);
-              float* ac = acc[gs][r];
-#pragma unroll
-              for (int a = 0; a < N; ++a) {
-                const float ar0 = ph.x * x[r][a].x, ai0 = ph.x * x[r][a].y, ar1 = ph.y * x[r][a].z, ai1 = ph.y * x[r][a].w;
-                ac[a * N + a] = fmaf(ar0, x[r][a].x, fmaf(ai0, x[r][a].y, fmaf(ar1, x[r][a].z, fmaf(ai1, x[r][a].w, ac[a * N + a]))));
-#pragma unroll
-                for (int c = a + 1; c < N; ++c) {
-                  ac[a * N + c] = fmaf(ar0, x[r][c].x, fmaf(ai0, x[r][c].y, fmaf(ar1, x[r][c].z, fmaf(ai1, x[r][c].w, ac[a * N + c]))));
-                  ac[c * N + a] = fmaf(ai0, x[r][c].x, fmaf(-ar0, x[r][c].y, fmaf(ai1, x[r][c].z, fmaf(-ar1, x[r][c].w, ac[c * N + a]))));
-                }
-              }
+              ph0[gs] = ph.x;
+              ph1[gs] = ph.y;
             }
+            float xr[N], xi[N];
+#pragma unroll
+            for (int m = 0; m < N; ++m) {
+              xr[m] = x[r][m].x;
+              xi[m] = x[r][m].y;
+            }
+            acc[r].add(xr, xi, ph0);
+#pragma unroll
+            for (int m = 0; m < N; ++m) {
+              xr[m] = x[r][m].z;
+              xi[m] = x[r][m].w;
+            }
+            acc[r].add(xr, xi, ph1);
           }
         }
       }
       if (STG) cp_async_wait<0>();
 #pragma unroll
-      for (int gs = 0; gs < G; ++gs) {
-        const int s = s0 + gs;
+      for (int r = 0; r < NR; ++r) {
+        const int rr = RS ? rs : r;
+        acc[r].reduce4(invJ);
 #pragma unroll
-        for (int r = 0; r < NR; ++r) {
-          const int rr = RS ? rs : r;
-#pragma unroll
-          for (int e = 0; e < N * N; ++e) {
-            float v = acc[gs][r][e];
-            v += __shfl_xor_sync(SSB_FULL, v, 1);
-            v += __shfl_xor_sync(SSB_FULL, v, 2);
-            acc[gs][r][e] = v * invJ;
-          }
-          if (t == 0 && rvalid[rr] && s < n_src) {
-            cf* u = U + (((size_t)b * I + row[rr]) * n_src + s) * N * N;
-#pragma unroll
-            for (int a = 0; a < N; ++a) {
-              u[a * N + a] = make_float2(acc[gs][r][a * N + a], 0.f);
-#pragma unroll
-              for (int c = a + 1; c < N; ++c) {
-                u[a * N + c] = make_float2(acc[gs][r][a * N + c], acc[gs][r][c * N + a]);
-                u[c * N + a] = make_float2(acc[gs][r][a * N + c], -acc[gs][r][c * N + a]);
-              }
-            }
-          }
+        for (int gs = 0; gs < G; ++gs) {
+          const int s = s0 + gs;
+          if (t == 0 && rvalid[rr] && s < n_src) acc[r].store(gs, U + (((size_t)b * I + row[rr]) * n_src + s) * N * N);
         }
       }
     }
@@ -1069,7 +1123,7 @@ int launch_all(const ssb_config* c, const cf* X, cf* W, float* T, float* V, floa
                         (size_t)FW * XSTAGES * 8 * 32 * sizeof(float);
   constexpr int NRC = CovShape<N>::RS ? 1 : 2;
   const size_t ring_cov = (size_t)FW * XSTAGES * 2 * NRC * N * 32 * sizeof(float4);
-  const size_t sm_cov = (size_t)(2 * G * JC * (KP + PADH)) * sizeof(__nv_bfloat16) + (CovShape<N>::STG ? ring_cov : 0);
+  const size_t sm_cov = (size_t)(2 * G * CovShape<N>::jcc(KP) * (KP + PADH)) * sizeof(__nv_bfloat16) + (CovShape<N>::STG ? ring_cov : 0);
   static int xmode = -1;  // SSB_XMODE: 0 direct loads, 1 cp.async ring, 2/3 L1 prefetch 2/4 steps ahead
   if (xmode < 0) {
     const char* e = getenv("SSB_XMODE");

@@ -57,6 +57,53 @@ __global__ void k_ffma(float* out, int iters, float x) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// packed fp32x2 FMA (FFMA2, sm_100+): does one issue slot buy two FMAs per lane?
+template <int ILP>
+__global__ void k_ffma2(float* out, int iters, float x) {
+  float2 c[ILP];
+#pragma unroll
+  for (int i = 0; i < ILP; ++i) c[i] = make_float2(threadIdx.x + i, threadIdx.x - i);
+  const float2 xx = make_float2(x, x), one = make_float2(1.0f, 1.0f);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) c[i] = __ffma2_rn(c[i], xx, one);
+  }
+  float s = 0;
+#pragma unroll
+  for (int i = 0; i < ILP; ++i) s += c[i].x + c[i].y;
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// FFMA2 interleaved 1:1 with integer ALU work: the issue-bound regime of the covariance kernels
+template <int ILP, bool PACKED>
+__global__ void k_mix(float* out, int iters, float x) {
+  float2 c[ILP];
+  unsigned u[ILP];
+#pragma unroll
+  for (int i = 0; i < ILP; ++i) {
+    c[i] = make_float2(threadIdx.x + i, threadIdx.x - i);
+    u[i] = threadIdx.x * 2654435761u + i;
+  }
+  const float2 xx = make_float2(x, x), one = make_float2(1.0f, 1.0f);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) {
+      if (PACKED) {
+        c[i] = __ffma2_rn(c[i], xx, one);
+      } else {
+        c[i].x = fmaf(c[i].x, x, 1.0f);
+        c[i].y = fmaf(c[i].y, x, 1.0f);
+      }
+      u[i] = (u[i] ^ (u[i] >> 7)) + 0x9e3779b9u;
+      u[i] = (u[i] ^ (u[i] << 3)) + it;
+    }
+  }
+  float s = 0;
+#pragma unroll
+  for (int i = 0; i < ILP; ++i) s += c[i].x + c[i].y + (float)u[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <typename F>
 float time_ms(F f) {
   cudaEvent_t a, b;
@@ -89,6 +136,11 @@ int main() {
     printf("bf16 m16n8k16 warps/SM=%2d : %8.1f TFLOP/s\n", warps, nw * iters * 8 * (2.0 * 16 * 8 * 16) / ms / 1e9);
     ms = time_ms([&] { k_ffma<8><<<blocks, threads>>>(out, iters * 8, 1.0001f); });
     printf("fp32 FFMA     warps/SM=%2d : %8.1f TFLOP/s\n", warps, nw * 32 * iters * 8.0 * 8 * 2 / ms / 1e9);
+    ms = time_ms([&] { k_ffma2<8><<<blocks, threads>>>(out, iters * 8, 1.0001f); });
+    printf("fp32 FFMA2    warps/SM=%2d : %8.1f TFLOP/s\n", warps, nw * 32 * iters * 8.0 * 8 * 4 / ms / 1e9);
+    ms = time_ms([&] { k_mix<8, false><<<blocks, threads>>>(out, iters * 4, 1.0001f); });
+    const float ms2 = time_ms([&] { k_mix<8, true><<<blocks, threads>>>(out, iters * 4, 1.0001f); });
+    printf("2 FFMA + 4 int ALU vs 1 FFMA2 + 4 int ALU, warps/SM=%2d : %.3f ms vs %.3f ms\n", warps, ms, ms2);
   }
   printf("SMs=%d clock=%d MHz\n", sms, p.clockRate / 1000);
   return 0;
