@@ -1111,7 +1111,8 @@ __global__ void __launch_bounds__(256) kf_normalize(const double* __restrict__ q
 }
 
 template <int N, int KS>
-int launch_all(const ssb_config* c, const cf* X, cf* W, float* T, float* V, float* P, cf* U, cudaStream_t st) {
+int launch_all(const ssb_config* c, const cf* X, cf* W, float* T, float* V, float* P, cf* U, void* vs,
+               cudaStream_t st) {
   const int B = c->n_batch, I = c->n_bins, J = c->n_frames, K = c->n_basis;
   constexpr int KP = 16 * KS;
   constexpr bool STG = N <= 4;  // cp.async staging of X in the source-model kernels
@@ -1124,38 +1125,26 @@ int launch_all(const ssb_config* c, const cf* X, cf* W, float* T, float* V, floa
   constexpr int NRC = CovShape<N>::RS ? 1 : 2;
   const size_t ring_cov = (size_t)FW * XSTAGES * 2 * NRC * N * 32 * sizeof(float4);
   const size_t sm_cov = (size_t)(2 * G * CovShape<N>::jcc(KP) * (KP + PADH)) * sizeof(__nv_bfloat16) + (CovShape<N>::STG ? ring_cov : 0);
-  static int xmode = -1;  // SSB_XMODE: 0 direct loads, 1 cp.async ring, 2/3 L1 prefetch 2/4 steps ahead
-  if (xmode < 0) {
-    const char* e = getenv("SSB_XMODE");
-    xmode = e ? atoi(e) : (STG ? 1 : 0);
+  // SSB_COOP: 1 (default) cooperative basis kernel (ssb_coop.cu), 0 one CTA per (mixture, source)
+  static int coop = -1;
+  if (coop < 0) {
+    const char* e = getenv("SSB_COOP");
+    coop = e ? atoi(e) : 1;
   }
-  const size_t sm_basis_nostg = sm_basis - (STG ? ring16 : 0);
   static bool attr_set = false;
   if (!attr_set) {
     SSB_CUDA(cudaFuncSetAttribute(kf_basis<N, KS, STG, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_basis));
-    SSB_CUDA(cudaFuncSetAttribute(kf_basis<N, KS, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_basis_nostg));
-    SSB_CUDA(cudaFuncSetAttribute(kf_basis<N, KS, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_basis_nostg));
-    SSB_CUDA(cudaFuncSetAttribute(kf_basis<N, KS, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_basis_nostg));
-    SSB_CUDA(cudaFuncSetAttribute(kf_basis<N, KS, STG, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_basis));
-    SSB_CUDA(cudaFuncSetAttribute(kf_basis<N, KS, STG, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_basis));
     SSB_CUDA(cudaFuncSetAttribute(kf_activation<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_act));
     SSB_CUDA(cudaFuncSetAttribute(kf_phi_cov<N, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_cov));
     attr_set = true;
   }
-  dim3 gb((I + FW * 16 - 1) / (FW * 16), N, B);
-  if (xmode == 2)
-    kf_basis<N, KS, false, 2><<<gb, FW * 32, sm_basis_nostg, st>>>(X, W, T, V, P, I, J, K, c->flooring, c->eps);
-  else if (xmode == 3)
-    kf_basis<N, KS, false, 4><<<gb, FW * 32, sm_basis_nostg, st>>>(X, W, T, V, P, I, J, K, c->flooring, c->eps);
-  else if (xmode == 0)
-    kf_basis<N, KS, false, 0><<<gb, FW * 32, sm_basis_nostg, st>>>(X, W, T, V, P, I, J, K, c->flooring, c->eps);
-  else if (xmode == 4)
-    kf_basis<N, KS, STG, 3><<<gb, FW * 32, sm_basis, st>>>(X, W, T, V, P, I, J, K, c->flooring, c->eps);
-  else if (xmode == 5)
-    kf_basis<N, KS, STG, 5><<<gb, FW * 32, sm_basis, st>>>(X, W, T, V, P, I, J, K, c->flooring, c->eps);
-  else
+  if (coop && vs != nullptr && W != nullptr) {
+    if (ssb_coop_basis(c, X, W, T, V, P, vs, st)) return 1;
+  } else {
+    dim3 gb((I + FW * 16 - 1) / (FW * 16), N, B);
     kf_basis<N, KS, STG, 0><<<gb, FW * 32, sm_basis, st>>>(X, W, T, V, P, I, J, K, c->flooring, c->eps);
-  if (ssb_check_launch("fused_basis", st)) return 1;
+    if (ssb_check_launch("fused_basis", st)) return 1;
+  }
   dim3 ga((J + FW * 16 - 1) / (FW * 16), N, B);
   kf_activation<KS><<<ga, FW * 32, sm_act, st>>>(P, T, V, N, I, J, K, c->flooring, c->eps);
   if (ssb_check_launch("fused_activation", st)) return 1;
@@ -1167,10 +1156,10 @@ int launch_all(const ssb_config* c, const cf* X, cf* W, float* T, float* V, floa
 }  // namespace
 
 // ---- host side ------------------------------------------------------------------------------------
-size_t ssb_fused_carve(ssb_fused_ws* ws, const ssb_config*, char* base) {
+size_t ssb_fused_carve(ssb_fused_ws* ws, const ssb_config* c, char* base) {
   ws->base = base;
-  ws->bytes = 0;
-  return 0;
+  ws->bytes = ssb_fused_supported(c) ? ((ssb_coop_ws_bytes(c) + 255) & ~(size_t)255) : 0;
+  return ws->bytes;
 }
 
 int ssb_fused_supported(const ssb_config* c) {
@@ -1182,13 +1171,14 @@ int ssb_fused_supported(const ssb_config* c) {
 int ssb_fused_prepare(ssb_fused_ws*, const ssb_config*, const cf*, cudaStream_t) { return 0; }
 
 // source model (T then V) + weighted covariance U with the tensor-core kernels
-int ssb_fused_source_and_cov(const ssb_config* c, const cf* X, cf* W, float* T, float* V, float* P, cf* U,
-                             cudaStream_t st) {
+int ssb_fused_source_and_cov(const ssb_config* c, const ssb_fused_ws* ws, const cf* X, cf* W, float* T, float* V,
+                             float* P, cf* U, cudaStream_t st) {
   const int KS = c->n_basis <= 16 ? 1 : 2;
+  void* vs = (ws && ws->bytes) ? ws->base : nullptr;
   if (KS == 1) {
-    SSB_DISPATCH_N(c->n_sources, return (launch_all<NN, 1>(c, X, W, T, V, P, U, st)));
+    SSB_DISPATCH_N(c->n_sources, return (launch_all<NN, 1>(c, X, W, T, V, P, U, vs, st)));
   } else {
-    SSB_DISPATCH_N(c->n_sources, return (launch_all<NN, 2>(c, X, W, T, V, P, U, st)));
+    SSB_DISPATCH_N(c->n_sources, return (launch_all<NN, 2>(c, X, W, T, V, P, U, vs, st)));
   }
   return 0;
 }

@@ -606,7 +606,7 @@ extern "C" int ssb_update_once(ssb_plan* p, void* stream) {
     }
     if (p->cfg.fast_path && ssb_fused_supported(&p->cfg)) {
       const ssb_config& c = p->cfg;
-      TRY(ssb_fused_source_and_cov(&c, p->X, p->W, p->T, p->V, p->big, p->U, st));
+      TRY(ssb_fused_source_and_cov(&c, &p->fused, p->X, p->W, p->T, p->V, p->big, p->U, st));
       if (c.spatial == SSB_SPATIAL_IP1) {
         if (c.n_sources == 2) {
           const bool pw = c.normalization == SSB_NORM_POWER;
