@@ -82,6 +82,16 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
   return v;
 }
+// keep a loop-invariant per-lane offset in a register (ptxas otherwise rematerialises it from %tid inside the loop)
+__device__ __forceinline__ uint32_t pin(uint32_t v) {
+  asm volatile("" : "+r"(v));
+  return v;
+}
+template <typename T>
+__device__ __forceinline__ T* pin_ptr(T* p) {
+  asm volatile("" : "+l"(p));
+  return p;
+}
 // named barrier of tile bt (ids 1..4 as immediates, so that ptxas reserves only the barriers in use)
 template <int NT>
 __device__ __forceinline__ void bar_sync_tile(int bt) {
@@ -115,6 +125,8 @@ template <int KS>
 __global__ void __launch_bounds__(128) kf_vsplit(const float* __restrict__ V, __nv_bfloat16* __restrict__ Vs, int J,
                                                  int K, int nchunk) {
   constexpr int KP = 16 * KS, JKS = KP + PADH, KG = KP / 4;
+  constexpr int CHH = 2 * JCV * JKS;  // halfs per chunk
+  __shared__ __align__(16) __nv_bfloat16 tile[CHH];
   const int chunk = blockIdx.x;
   const size_t bn = blockIdx.y;
   const int fr = threadIdx.x & 31, kg = threadIdx.x >> 5;
@@ -125,7 +137,7 @@ __global__ void __launch_bounds__(128) kf_vsplit(const float* __restrict__ V, __
     const int k = kg * KG + e;
     v[e] = (k < K && j < J) ? __ldg(V + (bn * K + k) * J + j) : 0.f;
   }
-  __nv_bfloat16* hi = Vs + (bn * nchunk + chunk) * (size_t)(2 * JCV * JKS) + fr * JKS + kg * KG;
+  __nv_bfloat16* hi = tile + fr * JKS + kg * KG;
   __nv_bfloat16* lo = hi + JCV * JKS;
 #pragma unroll
   for (int e = 0; e < KG; e += 2) {
@@ -133,6 +145,17 @@ __global__ void __launch_bounds__(128) kf_vsplit(const float* __restrict__ V, __
     *reinterpret_cast<uint32_t*>(hi + e) = s.hi;
     *reinterpret_cast<uint32_t*>(lo + e) = s.lo;
   }
+  if (kg == 0) {  // the padding columns travel with the cp.async copies: keep them defined
+#pragma unroll
+    for (int e = 0; e < PADH; e += 2) {
+      *reinterpret_cast<uint32_t*>(tile + fr * JKS + KP + e) = 0u;
+      *reinterpret_cast<uint32_t*>(tile + JCV * JKS + fr * JKS + KP + e) = 0u;
+    }
+  }
+  __syncthreads();
+  uint4* dst = reinterpret_cast<uint4*>(Vs + (bn * nchunk + chunk) * (size_t)CHH);
+  const uint4* src = reinterpret_cast<const uint4*>(tile);
+  for (int c = threadIdx.x; c < CHH / 8; c += 128) dst[c] = src[c];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -145,8 +168,8 @@ __global__ void __launch_bounds__(128) kf_vsplit(const float* __restrict__ V, __
 template <int N, int KS>
 __global__ void __launch_bounds__(CoopShape<N>::NW * 32)
     kf_basis_coop(const cf* __restrict__ X, const cf* __restrict__ W, float* __restrict__ T,
-                  const __nv_bfloat16* __restrict__ Vs, float* __restrict__ Pout, int I, int J, int K, int nchunk,
-                  int flooring, float eps) {
+                  const __nv_bfloat16* __restrict__ Vs, float* __restrict__ Pout, __nv_bfloat16* __restrict__ Ts, int I,
+                  int J, int K, int nchunk, int nchunk_i, int flooring, float eps) {
   constexpr int BT = CoopShape<N>::BT;
   constexpr int KP = 16 * KS, JKS = KP + PADH;
   constexpr int CHB = 2 * JCV * JKS * 2;  // bytes of one V chunk (hi + lo)
@@ -175,8 +198,8 @@ __global__ void __launch_bounds__(CoopShape<N>::NW * 32)
 #pragma unroll
       for (int nb = 0; nb < 2; ++nb) {
         const int k0 = ks * 16 + nb * 8 + 2 * t;
-        const float v0 = (k0 < K && rvalid[rr]) ? tr[k0] : 0.f;
-        const float v1 = (k0 + 1 < K && rvalid[rr]) ? tr[k0 + 1] : 0.f;
+        const float v0 = (k0 < K) ? tr[k0] : 0.f;
+        const float v1 = (k0 + 1 < K) ? tr[k0 + 1] : 0.f;
         Told[ks][nb][rr][0] = v0;
         Told[ks][nb][rr][1] = v1;
         const Split s = split2(v0, v1);
@@ -203,45 +226,59 @@ __global__ void __launch_bounds__(CoopShape<N>::NW * 32)
   for (int it = 0; it < 4; ++it) {
     const int c = it * 32 + lane, r = c >> 3, ch = c & 7;
     xsrc[it] = X + (bn * I + min(i0 + r, I - 1)) * (size_t)J + 2 * ch;
-    xdst[it] = xs_s + bt * XTB + (n * 16 + r) * 128 + ((ch ^ ((r & 1) << 2)) << 4);
+    xdst[it] = pin(xs_s + bt * XTB + (n * 16 + r) * 128 + ((ch ^ ((r & 1) << 2)) << 4));
   }
-  auto issue_x = [&](int step, int slot) {
+  // stages are requested in step order: the source pointers simply advance
+  auto issue_x = [&](uint32_t slot_bytes) {
 #pragma unroll
-    for (int it = 0; it < 4; ++it) cp_async16(xdst[it] + slot * (BT * XTB), xsrc[it] + step * 16);
+    for (int it = 0; it < 4; ++it) {
+      cp_async16(xdst[it] + slot_bytes, xsrc[it]);
+      xsrc[it] += 16;
+    }
   };
   const unsigned char* vsrc = reinterpret_cast<const unsigned char*>(Vs) + bn * (size_t)nchunk * CHB;
-  auto issue_v = [&](int chunk, int buf) {
+  const uint32_t vdst = pin(vs_s + lane * 16);
+  vsrc += lane * 16;
+  // chunks are requested in order as well
+  auto issue_v = [&](int buf) {
 #pragma unroll
-    for (int c = lane; c < CHB / 16; c += 32) cp_async16(vs_s + buf * CHB + c * 16, vsrc + (size_t)chunk * CHB + c * 16);
+    for (int c = 0; c < CHB / 16; c += 32) cp_async16(vdst + buf * CHB + c * 16, vsrc + c * 16);
+    vsrc += CHB;
   };
   // per-lane shared-memory offsets of the X fragments and of the ldmatrix rows
-  uint32_t xoff[2][2];
-#pragma unroll
-  for (int h = 0; h < 2; ++h)
-#pragma unroll
-    for (int rr = 0; rr < 2; ++rr) xoff[h][rr] = (g + 8 * rr) * 128 + (((4 * h + t) ^ ((g & 1) << 2)) << 4);
+  // (row g + 8rr, frames 8h + 2t..): the swizzle only flips the 64-byte half, so h selects between two lane bases
+  const uint32_t xlane[2] = {pin(xs_s + bt * XTB + g * 128 + ((t ^ ((g & 1) << 2)) << 4)),
+                             pin(xs_s + bt * XTB + g * 128 + (((4 + t) ^ ((g & 1) << 2)) << 4))};
   const int mid = lane >> 3, mrow = lane & 7;
   // GEMM1 (non-trans): matrices (hi k0-7, hi k8-15, lo k0-7, lo k8-15) of frames [.., +8)
-  const uint32_t l1off = (mid >> 1) * (JCV * JKS * 2) + (mrow * JKS + (mid & 1) * 8) * 2;
+  const uint32_t l1base = pin(vs_s + (mid >> 1) * (JCV * JKS * 2) + (mrow * JKS + (mid & 1) * 8) * 2);
   // GEMM2 (trans): matrices (hi frames 0-7, hi frames 8-15, lo 0-7, lo 8-15) of basis [.., +8)
-  const uint32_t l2off = (mid >> 1) * (JCV * JKS * 2) + (((mid & 1) * 8 + mrow) * JKS) * 2;
+  const uint32_t l2base = pin(vs_s + (mid >> 1) * (JCV * JKS * 2) + (((mid & 1) * 8 + mrow) * JKS) * 2);
 
   const int nsteps = J >> 4;
-  issue_v(0, 0);
-  issue_x(0, 0);
+  static_assert(XST == 3, "the V chunk of steps 2c, 2c+1 is requested at step 2c - 2: XST - 1 must be 2");
+  issue_v(0);
+  issue_x(0);
   cp_async_commit();
-  if (nsteps > 1) issue_x(1, 1);
+  if (nsteps > 1) issue_x(BT * XTB);
   cp_async_commit();
 
+  // rows past the last bin (last tile only) work on a clamped copy of row I-1: their accumulator rows are separate
+  // and never stored, so the loop needs no masking beyond the P store
+  float* pout[2] = {pin_ptr(Pout + (bn * I + rowc[0]) * (size_t)J + 2 * t), pin_ptr(Pout + (bn * I + rowc[1]) * (size_t)J + 2 * t)};
+  uint32_t rd_slot = 0, wr_slot = 2 * (BT * XTB);  // byte offsets of the X stage read / refilled this step
   for (int s = 0; s < nsteps; ++s) {
     cp_async_wait<XST - 2>();
     bar_sync_tile<N * 32>(bt);
-    if (s + 2 < nsteps) issue_x(s + 2, (s + 2) % XST);
-    if ((s & 1) == 0 && (s >> 1) + 1 < nchunk) issue_v((s >> 1) + 1, ((s >> 1) + 1) & 1);
+    if (s + 2 < nsteps) issue_x(wr_slot);
+    if ((s & 1) == 0 && (s >> 1) + 1 < nchunk) issue_v(((s >> 1) + 1) & 1);
     cp_async_commit();
 
-    const uint32_t vb = vs_s + ((s >> 1) & 1) * CHB + (s & 1) * (16 * JKS * 2);
-    const uint32_t xb = xs_s + (s % XST) * (BT * XTB) + bt * XTB;
+    const uint32_t voff = ((s >> 1) & 1) * CHB + (s & 1) * (16 * JKS * 2);
+    const uint32_t vb1 = l1base + voff, vb2 = l2base + voff;
+    const uint32_t xb0 = xlane[0] + rd_slot, xb1 = xlane[1] + rd_slot;
+    rd_slot = rd_slot + BT * XTB == XST * BT * XTB ? 0 : rd_slot + BT * XTB;
+    wr_slot = wr_slot + BT * XTB == XST * BT * XTB ? 0 : wr_slot + BT * XTB;
     // ---- GEMM1: R[16 bins x 16 frames] = T V ---------------------------------------------------------
     float R[2][4];
 #pragma unroll
@@ -251,7 +288,7 @@ __global__ void __launch_bounds__(CoopShape<N>::NW * 32)
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
         uint32_t bh0, bh1, bl0, bl1;
-        ldsm_x4(bh0, bh1, bl0, bl1, vb + l1off + (8 * h * JKS + ks * 16) * 2);
+        ldsm_x4(bh0, bh1, bl0, bl1, vb1 + (8 * h * JKS + ks * 16) * 2);
         mma_split(R[h], Thi[ks], Tlo[ks], bh0, bh1, bl0, bl1);
       }
     }
@@ -263,14 +300,13 @@ __global__ void __launch_bounds__(CoopShape<N>::NW * 32)
       for (int rr = 0; rr < 2; ++rr) {
         float4 x[N];
 #pragma unroll
-        for (int m = 0; m < N; ++m) x[m] = lds128(xb + m * 2048 + xoff[h][rr]);
+        for (int m = 0; m < N; ++m) x[m] = lds128((h ? xb1 : xb0) + m * 2048 + rr * 1024);
         float p0, p1;
         power2<N>(x, w[rr], p0, p1);
         // the power spectrogram is kept for the activation update (same W => same P, ilrma.py:1169-1172)
-        if (rvalid[rr])
-          *reinterpret_cast<float2*>(Pout + (bn * I + row[rr]) * (size_t)J + s * 16 + 8 * h + 2 * t) = make_float2(p0, p1);
-        const float i0v = rvalid[rr] ? fast_rcp(R[h][rr * 2 + 0]) : 0.f;
-        const float i1v = rvalid[rr] ? fast_rcp(R[h][rr * 2 + 1]) : 0.f;
+        if (rvalid[rr]) *reinterpret_cast<float2*>(pout[rr] + 8 * h) = make_float2(p0, p1);
+        const float i0v = fast_rcp(R[h][rr * 2 + 0]);
+        const float i1v = fast_rcp(R[h][rr * 2 + 1]);
         const Split sa = split2(p0 * i0v * i0v, p1 * i1v * i1v);
         const Split sb = split2(i0v, i1v);
         Ahi[h * 2 + rr] = sa.hi;
@@ -278,16 +314,20 @@ __global__ void __launch_bounds__(CoopShape<N>::NW * 32)
         Bhi[h * 2 + rr] = sb.hi;
         Blo[h * 2 + rr] = sb.lo;
       }
+    pout[0] += 16;
+    pout[1] += 16;
     // ---- GEMM2: num += A V^T, den += B V^T  (contraction over the 16 frames) ---------------------------
 #pragma unroll
     for (int q = 0; q < 2 * KS; ++q) {
       uint32_t vh0, vh1, vl0, vl1;
-      ldsm_x4_t(vh0, vh1, vl0, vl1, vb + l2off + q * 16);
+      ldsm_x4_t(vh0, vh1, vl0, vl1, vb2 + q * 16);
       mma_split(num[q], Ahi, Alo, vh0, vh1, vl0, vl1);
       mma_split(den[q], Bhi, Blo, vh0, vh1, vl0, vl1);
     }
   }
   // ---- T <- floor(T * sqrt(num / den))      (ilrma.py:1125-1126, p = 2) --------------------------------
+  // The new basis is also written pre-split (bf16 hi, lo; [bin][basis] chunks of 32 bins) for the activation
+  // update of the same call (kf_activation_coop); rows >= I and columns >= K of Ts stay zero.
 #pragma unroll
   for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
@@ -297,54 +337,299 @@ __global__ void __launch_bounds__(CoopShape<N>::NW * 32)
         if (!rvalid[rr]) continue;
         const int q = ks * 2 + nb;
         const int k0 = ks * 16 + nb * 8 + 2 * t;
+        float tn[2];
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
+          tn[e] = 0.f;
           if (k0 + e < K) {
             const float ratio = num[q][rr * 2 + e] / den[q][rr * 2 + e];
-            T[(bn * I + row[rr]) * K + k0 + e] = ssb_floor(sqrtf(ratio) * Told[ks][nb][rr][e], flooring, eps);
+            tn[e] = ssb_floor(sqrtf(ratio) * Told[ks][nb][rr][e], flooring, eps);
+            T[(bn * I + row[rr]) * K + k0 + e] = tn[e];
           }
         }
+        const Split sp = split2(tn[0], tn[1]);
+        __nv_bfloat16* th = Ts + (bn * nchunk_i + (row[rr] >> 5)) * (size_t)(2 * JCV * JKS) + (row[rr] & 31) * JKS + k0;
+        *reinterpret_cast<uint32_t*>(th) = sp.hi;
+        *reinterpret_cast<uint32_t*>(th + JCV * JKS) = sp.lo;
+      }
+}
+
+// ------------------------------------------------------------------------------------------------
+// kf_activation_coop:  V <- V sqrt( sum_i T P / R^2  /  sum_i T / R ),  R = T V with the new T
+// (ssspy/bss/ilrma.py:1130-1204).  CTA = (group of AW*16 frames, source, mixture); warp = 16 frames and owns its V
+// entries completely (no partial sums, no atomics: deterministic).  All warps walk over the bins together: the
+// pre-split basis chunks Ts (32 bins, written by kf_basis_coop) go through a CTA-wide double buffer, every warp
+// streams its own 16-bin x 16-frame tiles of P (written by the basis kernel with the same W) through a private
+// 3-stage cp.async ring.  Orientation is transposed w.r.t. the basis kernel (C rows = frames, C cols = bins), so the
+// accumulator fragment of R^T = V^T T^T is the A operand of num^T += (P / R^2)^T T; both B operands come from the one
+// [bin][basis] layout by ldmatrix / ldmatrix.trans.  The new V is also written pre-split (Vs) for kf_basis_coop /
+// the covariance kernel of the following phases.
+constexpr int AW = 8;     // warps per CTA
+constexpr int PST = 6;    // stages of the per-warp P ring (PST - 1 tiles in flight per warp: the kernel is bound by
+                          // the HBM latency per warp, not by issue)
+constexpr int TD = PST / 2;   // T chunks issued ahead of use: a chunk must sit in a cp.async group no younger than
+                             // the P tile of its first step
+constexpr int TST = TD + 1;  // slots of the CTA-wide T chunk ring
+constexpr int PRS = 80;   // bytes per P tile row: 16 frames fp32 + 16 pad => conflict-free fragment reads
+
+__device__ __forceinline__ float lds32f(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+template <int KS>
+__global__ void __launch_bounds__(AW * 32)
+    kf_activation_coop(const float* __restrict__ P, const __nv_bfloat16* __restrict__ Ts, float* __restrict__ V,
+                       __nv_bfloat16* __restrict__ Vs, int NS, int I, int J, int K, int nchunk_i, int nchunk_j,
+                       int flooring, float eps) {
+  constexpr int KP = 16 * KS, JKS = KP + PADH;
+  constexpr int CHB = 2 * JCV * JKS * 2;  // bytes of one 32-bin T chunk (hi + lo)
+  constexpr int PTB = 16 * PRS;           // bytes of one P tile stage
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const uint32_t ts_s = (uint32_t)__cvta_generic_to_shared(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int n = blockIdx.y, b = blockIdx.z;
+  const uint32_t pw_s = ts_s + TST * CHB + warp * (PST * PTB);
+  const int j0 = (blockIdx.x * AW + warp) * 16;
+  const bool warp_active = j0 < J;
+  const size_t bn = (size_t)b * NS + n;
+  float* Vb = V + bn * K * J;
+  const float* Pb = P + bn * I * J;
+  const int fr[2] = {min(j0 + g, J - 1), min(j0 + g + 8, J - 1)};
+  const bool fvalid[2] = {j0 + g < J, j0 + g + 8 < J};
+
+  // V^T tile (16 frames x KP) -> A fragments; fp32 copies for the final update
+  uint32_t Vhi[KS][4], Vlo[KS][4];
+  float Vold[KS][2][2][2];  // [ks][nb][rr][e]: basis ks*16+nb*8+2t+e, frame rr
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+    for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int k0 = ks * 16 + nb * 8 + 2 * t;
+        const float v0 = (k0 < K && fvalid[rr]) ? Vb[(size_t)k0 * J + fr[rr]] : 0.f;
+        const float v1 = (k0 + 1 < K && fvalid[rr]) ? Vb[(size_t)(k0 + 1) * J + fr[rr]] : 0.f;
+        Vold[ks][nb][rr][0] = v0;
+        Vold[ks][nb][rr][1] = v1;
+        const Split sp = split2(v0, v1);
+        Vhi[ks][nb * 2 + rr] = sp.hi;
+        Vlo[ks][nb * 2 + rr] = sp.lo;
+      }
+  float num[2 * KS][4], den[2 * KS][4];
+#pragma unroll
+  for (int q = 0; q < 2 * KS; ++q)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) num[q][c] = den[q][c] = 0.f;
+
+  const unsigned char* tsrc = reinterpret_cast<const unsigned char*>(Ts) + bn * (size_t)nchunk_i * CHB;
+  auto issue_t = [&](int chunk, int buf) {
+    for (int c = threadIdx.x; c < CHB / 16; c += AW * 32)
+      cp_async16(ts_s + buf * CHB + c * 16, tsrc + (size_t)chunk * CHB + c * 16);
+  };
+  // P tile of step s: 16 bins x 64 bytes, 4 lanes per row.  The P scratch is padded by 16 rows, so the (masked)
+  // rows past the last bin need no clamping.
+  const float* psrc[2];
+  uint32_t pdst[2];
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int idx = it * 32 + lane, r = idx >> 2, part = idx & 3;
+    psrc[it] = Pb + (size_t)r * J + min(j0, J - 16) + part * 4;
+    pdst[it] = pin(pw_s + r * PRS + part * 16);
+  }
+  const size_t pstep = (size_t)16 * J;
+  // tiles are requested in step order: the source pointers simply advance
+  auto issue_p = [&](uint32_t slot_bytes) {
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      cp_async16(pdst[it] + slot_bytes, psrc[it]);
+      psrc[it] += pstep;
+    }
+  };
+  const int mid = lane >> 3, mrow = lane & 7;
+  const uint32_t l1off = (mid >> 1) * (JCV * JKS * 2) + (mrow * JKS + (mid & 1) * 8) * 2;
+  const uint32_t l2off = (mid >> 1) * (JCV * JKS * 2) + (((mid & 1) * 8 + mrow) * JKS) * 2;
+  // fragment reads of P: (bin 8h + 2t + e, frame g + 8rr) = per-lane base + compile-time offset
+  const uint32_t plane = pin(pw_s + (2 * t) * PRS + g * 4);
+  const uint32_t l1base = pin(ts_s + l1off), l2base = pin(ts_s + l2off);
+  const int nsteps = (I + 15) >> 4;
+  const bool frames_full = fvalid[0] && fvalid[1];
+  // group s carries the P tile of step s (+ the T chunk needed PST - 1 steps later); PST - 1 groups are in flight
+#pragma unroll
+  for (int q = 0; q < PST - 1; ++q) {
+    if ((q & 1) == 0 && (q >> 1) < nchunk_i) issue_t(q >> 1, (q >> 1) % TST);
+    if (warp_active && q < nsteps) issue_p(q * PTB);
+    cp_async_commit();
+  }
+  uint32_t rd_slot = 0, wr_slot = (PST - 1) * PTB;  // byte offsets of the P ring slots read / refilled this step
+  uint32_t t_slot = 0;                               // byte offset of the T chunk in use
+  for (int s = 0; s < nsteps; ++s) {
+    cp_async_wait<PST - 2>();
+    if ((s & 1) == 0) {
+      __syncthreads();  // chunk s/2 has landed for every thread; chunk s/2 - 1 is no longer read
+      const int cn = (s >> 1) + TD;
+      if (cn < nchunk_i) issue_t(cn, cn % TST);
+    } else {
+      __syncwarp();
+    }
+    if (warp_active && s + PST - 1 < nsteps) issue_p(wr_slot);
+    cp_async_commit();
+    const uint32_t tb1 = l1base + t_slot + (s & 1) * (16 * JKS * 2), tb2 = l2base + t_slot + (s & 1) * (16 * JKS * 2);
+    const uint32_t pb = plane + rd_slot;
+    rd_slot = rd_slot + PTB == PST * PTB ? 0 : rd_slot + PTB;
+    wr_slot = wr_slot + PTB == PST * PTB ? 0 : wr_slot + PTB;
+    if (s & 1) t_slot = t_slot + CHB == TST * CHB ? 0 : t_slot + CHB;
+    if (!warp_active) continue;
+
+    // ---- GEMM1: R^T[16 frames x 16 bins] = V^T T^T ---------------------------------------------------
+    float R[2][4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {  // h: bins 8h .. 8h+7 of the step (n-tile)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) R[h][c] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        uint32_t bh0, bh1, bl0, bl1;
+        ldsm_x4(bh0, bh1, bl0, bl1, tb1 + (8 * h * JKS + ks * 16) * 2);
+        mma_split(R[h], Vhi[ks], Vlo[ks], bh0, bh1, bl0, bl1);
+      }
+    }
+    // ---- elementwise at (frame rr, bin 8h + 2t + e) -------------------------------------------------------
+    uint32_t Ahi[4], Alo[4], Bhi[4], Blo[4];
+    const int lim = I - s * 16;  // valid bins in this step
+    if (lim >= 16 && frames_full) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          const float iv0 = fast_rcp(R[h][rr * 2]), iv1 = fast_rcp(R[h][rr * 2 + 1]);
+          const float p0 = lds32f(pb + (8 * h) * PRS + 32 * rr), p1 = lds32f(pb + (8 * h + 1) * PRS + 32 * rr);
+          const Split sa = split2(p0 * iv0 * iv0, p1 * iv1 * iv1);
+          const Split sb = split2(iv0, iv1);
+          Ahi[h * 2 + rr] = sa.hi;
+          Alo[h * 2 + rr] = sa.lo;
+          Bhi[h * 2 + rr] = sb.hi;
+          Blo[h * 2 + rr] = sb.lo;
+        }
+    } else {
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          float a_[2], i_[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const bool ok = (8 * h + 2 * t + e < lim) && fvalid[rr];
+            const float p = lds32f(pb + (8 * h + e) * PRS + 32 * rr);
+            const float iv = ok ? fast_rcp(R[h][rr * 2 + e]) : 0.f;
+            i_[e] = iv;
+            a_[e] = ok ? p * iv * iv : 0.f;
+          }
+          const Split sa = split2(a_[0], a_[1]);
+          const Split sb = split2(i_[0], i_[1]);
+          Ahi[h * 2 + rr] = sa.hi;
+          Alo[h * 2 + rr] = sa.lo;
+          Bhi[h * 2 + rr] = sb.hi;
+          Blo[h * 2 + rr] = sb.lo;
+        }
+    }
+    // ---- GEMM2: num^T += A^T T, den^T += B^T T  (contraction over the 16 bins) ---------------------------
+#pragma unroll
+    for (int q = 0; q < 2 * KS; ++q) {
+      uint32_t th0, th1, tl0, tl1;
+      ldsm_x4_t(th0, th1, tl0, tl1, tb2 + q * 16);
+      mma_split(num[q], Ahi, Alo, th0, th1, tl0, tl1);
+      mma_split(den[q], Bhi, Blo, th0, th1, tl0, tl1);
+    }
+  }
+  if (!warp_active) return;
+  // ---- V <- floor(V * sqrt(num / den))      (ilrma.py:1201-1202, p = 2), plus the pre-split copy --------------
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+    for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        if (!fvalid[rr]) continue;
+        const int q = ks * 2 + nb;
+        const int k0 = ks * 16 + nb * 8 + 2 * t;
+        float vn[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          vn[e] = 0.f;
+          if (k0 + e < K) {
+            const float ratio = num[q][rr * 2 + e] / den[q][rr * 2 + e];
+            vn[e] = ssb_floor(sqrtf(ratio) * Vold[ks][nb][rr][e], flooring, eps);
+            Vb[(size_t)(k0 + e) * J + fr[rr]] = vn[e];
+          }
+        }
+        const Split sp = split2(vn[0], vn[1]);
+        __nv_bfloat16* vh = Vs + (bn * nchunk_j + (fr[rr] >> 5)) * (size_t)(2 * JCV * JKS) + (fr[rr] & 31) * JKS + k0;
+        *reinterpret_cast<uint32_t*>(vh) = sp.hi;
+        *reinterpret_cast<uint32_t*>(vh + JCV * JKS) = sp.lo;
       }
 }
 
 template <int N, int KS>
-int launch_coop(const ssb_config* c, const cf* X, const cf* W, float* T, const float* V, float* P,
-                __nv_bfloat16* Vs, cudaStream_t st) {
+int launch_coop(const ssb_config* c, const cf* X, const cf* W, float* T, float* V, float* P, __nv_bfloat16* Vs,
+                __nv_bfloat16* Ts, int vs_valid, cudaStream_t st) {
   const int B = c->n_batch, I = c->n_bins, J = c->n_frames, K = c->n_basis;
   constexpr int BT = CoopShape<N>::BT, NW = CoopShape<N>::NW;
   constexpr int KP = 16 * KS, JKS = KP + PADH;
-  const int nchunk = (J + JCV - 1) / JCV;
-  dim3 gv(nchunk, B * N);
-  kf_vsplit<KS><<<gv, 128, 0, st>>>(V, Vs, J, K, nchunk);
-  if (ssb_check_launch("coop_vsplit", st)) return 1;
-  const size_t sm = (size_t)XST * BT * N * 2048 + (size_t)NW * 2 * (2 * JCV * JKS * 2);
+  constexpr int CHB = 2 * JCV * JKS * 2;
+  const int nchunk = (J + JCV - 1) / JCV, nchunk_i = (I + JCV - 1) / JCV;
+  if (!vs_valid) {
+    dim3 gv(nchunk, B * N);
+    kf_vsplit<KS><<<gv, 128, 0, st>>>(V, Vs, J, K, nchunk);
+    if (ssb_check_launch("coop_vsplit", st)) return 1;
+  }
+  const size_t sm = (size_t)XST * BT * N * 2048 + (size_t)NW * 2 * CHB;
+  const size_t sm_act = (size_t)TST * CHB + (size_t)AW * PST * 16 * PRS;
   static bool attr_set = false;
   if (!attr_set) {
     SSB_CUDA(cudaFuncSetAttribute(kf_basis_coop<N, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    SSB_CUDA(cudaFuncSetAttribute(kf_activation_coop<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_act));
     attr_set = true;
   }
   dim3 grid((I + 16 * BT - 1) / (16 * BT), B);
-  kf_basis_coop<N, KS><<<grid, NW * 32, sm, st>>>(X, W, T, Vs, P, I, J, K, nchunk, c->flooring, c->eps);
-  return ssb_check_launch("coop_basis", st);
+  kf_basis_coop<N, KS><<<grid, NW * 32, sm, st>>>(X, W, T, Vs, P, Ts, I, J, K, nchunk, nchunk_i, c->flooring, c->eps);
+  if (ssb_check_launch("coop_basis", st)) return 1;
+  dim3 ga((J + AW * 16 - 1) / (AW * 16), N, B);
+  kf_activation_coop<KS><<<ga, AW * 32, sm_act, st>>>(P, Ts, V, Vs, N, I, J, K, nchunk_i, nchunk, c->flooring, c->eps);
+  return ssb_check_launch("coop_activation", st);
 }
 
 }  // namespace
 
-size_t ssb_coop_ws_bytes(const ssb_config* c) {
+static size_t coop_chunk_bytes(const ssb_config* c) {
   const size_t KP = c->n_basis <= 16 ? 16 : 32;
+  return 2 * JCV * (KP + PADH) * sizeof(__nv_bfloat16);
+}
+static size_t coop_vs_bytes(const ssb_config* c) {
   const size_t nchunk = ((size_t)c->n_frames + JCV - 1) / JCV;
-  return (size_t)c->n_batch * c->n_sources * nchunk * (2 * JCV * (KP + PADH)) * sizeof(__nv_bfloat16);
+  return (((size_t)c->n_batch * c->n_sources * nchunk * coop_chunk_bytes(c)) + 255) & ~(size_t)255;
+}
+static size_t coop_ts_bytes(const ssb_config* c) {
+  const size_t nchunk = ((size_t)c->n_bins + JCV - 1) / JCV;
+  return (((size_t)c->n_batch * c->n_sources * nchunk * coop_chunk_bytes(c)) + 255) & ~(size_t)255;
 }
 
-// basis update for every source of every mixture; Vs is scratch of ssb_coop_ws_bytes() bytes
-int ssb_coop_basis(const ssb_config* c, const cf* X, const cf* W, float* T, const float* V, float* P, void* Vs,
-                   cudaStream_t st) {
-  SSB_REQUIRE((c->n_frames % 16) == 0 && c->n_basis <= 32 && W != nullptr && Vs != nullptr,
-              "coop_basis: unsupported configuration");
+// scratch: pre-split activation Vs followed by pre-split basis Ts (must be zero-initialised once)
+size_t ssb_coop_ws_bytes(const ssb_config* c) { return coop_vs_bytes(c) + coop_ts_bytes(c); }
+
+// MM source model for every source of every mixture: [V -> Vs unless vs_valid] basis (T, Ts, P), activation (V, Vs)
+int ssb_coop_source(const ssb_config* c, const cf* X, const cf* W, float* T, float* V, float* P, void* ws,
+                    int vs_valid, cudaStream_t st) {
+  SSB_REQUIRE((c->n_frames % 16) == 0 && c->n_basis <= 32 && W != nullptr && ws != nullptr,
+              "coop_source: unsupported configuration");
+  __nv_bfloat16* Vs = (__nv_bfloat16*)ws;
+  __nv_bfloat16* Ts = (__nv_bfloat16*)((char*)ws + coop_vs_bytes(c));
   if (c->n_basis <= 16) {
-    SSB_DISPATCH_N(c->n_sources, return (launch_coop<NN, 1>(c, X, W, T, V, P, (__nv_bfloat16*)Vs, st)));
+    SSB_DISPATCH_N(c->n_sources, return (launch_coop<NN, 1>(c, X, W, T, V, P, Vs, Ts, vs_valid, st)));
   } else {
-    SSB_DISPATCH_N(c->n_sources, return (launch_coop<NN, 2>(c, X, W, T, V, P, (__nv_bfloat16*)Vs, st)));
+    SSB_DISPATCH_N(c->n_sources, return (launch_coop<NN, 2>(c, X, W, T, V, P, Vs, Ts, vs_valid, st)));
   }
   return 0;
 }

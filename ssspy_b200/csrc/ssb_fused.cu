@@ -1111,7 +1111,7 @@ __global__ void __launch_bounds__(256) kf_normalize(const double* __restrict__ q
 }
 
 template <int N, int KS>
-int launch_all(const ssb_config* c, const cf* X, cf* W, float* T, float* V, float* P, cf* U, void* vs,
+int launch_all(const ssb_config* c, const cf* X, cf* W, float* T, float* V, float* P, cf* U, ssb_fused_ws* vs,
                cudaStream_t st) {
   const int B = c->n_batch, I = c->n_bins, J = c->n_frames, K = c->n_basis;
   constexpr int KP = 16 * KS;
@@ -1139,15 +1139,16 @@ int launch_all(const ssb_config* c, const cf* X, cf* W, float* T, float* V, floa
     attr_set = true;
   }
   if (coop && vs != nullptr && W != nullptr) {
-    if (ssb_coop_basis(c, X, W, T, V, P, vs, st)) return 1;
+    if (ssb_coop_source(c, X, W, T, V, P, vs->base, vs->vs_valid ? 1 : 0, st)) return 1;
+    vs->vs_valid = true;  // ssb_update_once clears it again unless it runs inside ssb_run
   } else {
     dim3 gb((I + FW * 16 - 1) / (FW * 16), N, B);
     kf_basis<N, KS, STG, 0><<<gb, FW * 32, sm_basis, st>>>(X, W, T, V, P, I, J, K, c->flooring, c->eps);
     if (ssb_check_launch("fused_basis", st)) return 1;
+    dim3 ga((J + FW * 16 - 1) / (FW * 16), N, B);
+    kf_activation<KS><<<ga, FW * 32, sm_act, st>>>(P, T, V, N, I, J, K, c->flooring, c->eps);
+    if (ssb_check_launch("fused_activation", st)) return 1;
   }
-  dim3 ga((J + FW * 16 - 1) / (FW * 16), N, B);
-  kf_activation<KS><<<ga, FW * 32, sm_act, st>>>(P, T, V, N, I, J, K, c->flooring, c->eps);
-  if (ssb_check_launch("fused_activation", st)) return 1;
   dim3 gc((N + G - 1) / G, (I + FW * 16 - 1) / (FW * 16), B);
   kf_phi_cov<N, KS><<<gc, FW * 32, sm_cov, st>>>(X, T, V, U, I, J, K);
   return ssb_check_launch("fused_phi_cov", st);
@@ -1159,6 +1160,8 @@ int launch_all(const ssb_config* c, const cf* X, cf* W, float* T, float* V, floa
 size_t ssb_fused_carve(ssb_fused_ws* ws, const ssb_config* c, char* base) {
   ws->base = base;
   ws->bytes = ssb_fused_supported(c) ? ((ssb_coop_ws_bytes(c) + 255) & ~(size_t)255) : 0;
+  ws->zeroed = false;
+  ws->vs_valid = false;
   return ws->bytes;
 }
 
@@ -1171,10 +1174,15 @@ int ssb_fused_supported(const ssb_config* c) {
 int ssb_fused_prepare(ssb_fused_ws*, const ssb_config*, const cf*, cudaStream_t) { return 0; }
 
 // source model (T then V) + weighted covariance U with the tensor-core kernels
-int ssb_fused_source_and_cov(const ssb_config* c, const ssb_fused_ws* ws, const cf* X, cf* W, float* T, float* V,
+int ssb_fused_source_and_cov(const ssb_config* c, ssb_fused_ws* ws, const cf* X, cf* W, float* T, float* V,
                              float* P, cf* U, cudaStream_t st) {
   const int KS = c->n_basis <= 16 ? 1 : 2;
-  void* vs = (ws && ws->bytes) ? ws->base : nullptr;
+  ssb_fused_ws* vs = (ws && ws->bytes) ? ws : nullptr;
+  if (vs && !vs->zeroed) {
+    SSB_CUDA(cudaMemsetAsync(vs->base, 0, vs->bytes, st));
+    vs->zeroed = true;
+    vs->vs_valid = false;
+  }
   if (KS == 1) {
     SSB_DISPATCH_N(c->n_sources, return (launch_all<NN, 1>(c, X, W, T, V, P, U, vs, st)));
   } else {

@@ -5,6 +5,9 @@
 struct ssb_fused_ws {
   char* base = nullptr;
   size_t bytes = 0;
+  bool zeroed = false;    // the pre-split operand buffers rely on zero padding rows / columns
+  bool vs_valid = false;  // Vs holds the split of the current V (set by the activation kernel, kept across the
+                          // iterations of ssb_run only)
 };
 
 // bytes of extra scratch (base may be NULL to only measure)
@@ -14,13 +17,14 @@ int ssb_fused_supported(const ssb_config* cfg);
 int ssb_fused_prepare(ssb_fused_ws* ws, const ssb_config* cfg, const cf* X, cudaStream_t st);
 // MM source model (T then V, p = 2) followed by phi = 1/(T V) and the weighted covariances U
 // P[B,N,I,J] f32 is scratch (power spectrogram handed from the basis to the activation update)
-int ssb_fused_source_and_cov(const ssb_config* cfg, const ssb_fused_ws* ws, const cf* X, cf* W, float* T, float* V,
+int ssb_fused_source_and_cov(const ssb_config* cfg, ssb_fused_ws* ws, const cf* X, cf* W, float* T, float* V,
                              float* P, cf* U, cudaStream_t st);
-// cooperative basis update (ssb_coop.cu): one CTA = 16-bin tiles x all sources sharing the X slab in shared memory;
-// Vs is scratch of ssb_coop_ws_bytes() bytes (pre-split bf16 copy of V)
+// cooperative MM source model (ssb_coop.cu): basis kernel with one CTA = 16-bin tiles x all sources sharing the X
+// slab in shared memory, then the activation kernel; ws is zero-initialised scratch of ssb_coop_ws_bytes() bytes
+// (pre-split bf16 copies of V and T)
 size_t ssb_coop_ws_bytes(const ssb_config* cfg);
-int ssb_coop_basis(const ssb_config* cfg, const cf* X, const cf* W, float* T, const float* V, float* P, void* Vs,
-                   cudaStream_t st);
+int ssb_coop_source(const ssb_config* cfg, const cf* X, const cf* W, float* T, float* V, float* P, void* ws,
+                    int vs_valid, cudaStream_t st);
 // closed-form IP1 for two sources; with C != NULL also q[mat,n] = Re(w_n C w_n^H) for the normalisation
 int ssb_fused_ip1_n2(cf* W, const cf* U, const cf* C, double* q, int n_mat, int flooring, float eps,
                      cudaStream_t st);

@@ -35,11 +35,13 @@ int ssbk_separate(const cf* X, const cf* W, cf* Y, float* P, int B, int N, int I
 int ssbk_abs2(const cf* Y, float* P, size_t n, cudaStream_t st);
 int ssbk_wcov(const cf* X, const float* phi, long long sb, long long sn, long long si, const int* src, int n_src,
               cf* U, int B, int N, int I, int J, cudaStream_t st);
-int ssbk_ip1(cf* W, const cf* U, int n_mat, int N, int flooring, float eps, cudaStream_t st);
+// C, q (optional): also emit q[mat, n] = Re(w_n C_mat w_n^H), the per-bin term of the power normalisation
+int ssbk_ip1(cf* W, const cf* U, int n_mat, int N, int flooring, float eps, cudaStream_t st, const cf* C = nullptr,
+             double* q = nullptr);
 // uidx (host, 2*n_pairs, may be NULL => U slice index = source index): which of the n_u slices of U
 // each pair member uses
 int ssbk_ip2(cf* W, const cf* U, int n_mat, int N, const int* pairs, int n_pairs, int n_u, const int* uidx,
-             int flooring, float eps, cudaStream_t st);
+             int flooring, float eps, cudaStream_t st, const cf* C = nullptr, double* q = nullptr);
 int ssbk_iss1(cf* Y, const float* phi, long long sb, long long sn, long long si, int B, int N, int I, int J,
               int flooring, float eps, cudaStream_t st);
 // pairs (host, 2*n_pairs, already wrapped into [0, N)); _update_spatial_model.py:197-314

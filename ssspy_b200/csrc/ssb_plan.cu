@@ -578,9 +578,8 @@ extern "C" int ssb_normalize(ssb_plan* p, void* stream) {
   return ilrma_normalize(p, (cudaStream_t)stream);
 }
 
-extern "C" int ssb_update_once(ssb_plan* p, void* stream) {
-  TRY(require_bound(p));
-  cudaStream_t st = (cudaStream_t)stream;
+namespace {
+int update_once_impl(ssb_plan* p, cudaStream_t st) {
   if (p->mnmf()) {  // mnmf.py:1278-1303
     TRY(mnmf_source(p, st));
     TRY(mnmf_spatial(p, st));
@@ -607,21 +606,23 @@ extern "C" int ssb_update_once(ssb_plan* p, void* stream) {
     if (p->cfg.fast_path && ssb_fused_supported(&p->cfg)) {
       const ssb_config& c = p->cfg;
       TRY(ssb_fused_source_and_cov(&c, &p->fused, p->X, p->W, p->T, p->V, p->big, p->U, st));
+      // power normalisation without a pass over X: the IP kernels emit q[b,i,n] = Re(w_n C_i w_n^H) and one small
+      // kernel reduces it over the bins and rescales T and W
+      const bool pw = c.normalization == SSB_NORM_POWER;
+      SSB_REQUIRE(!pw || p->prepared, "plan not prepared (call ssb_plan_prepare after bind)");
+      const cf* Cq = pw ? p->C : nullptr;
       if (c.spatial == SSB_SPATIAL_IP1) {
-        if (c.n_sources == 2) {
-          const bool pw = c.normalization == SSB_NORM_POWER;
-          SSB_REQUIRE(!pw || p->prepared, "plan not prepared (call ssb_plan_prepare after bind)");
-          TRY(ssb_fused_ip1_n2(p->W, p->U, pw ? p->C : nullptr, p->rowloss, c.n_batch * c.n_bins, c.flooring, c.eps, st));
-          if (pw)
-            return ssb_fused_normalize(p->rowloss, p->T, p->W, c.n_batch, 2, c.n_bins, c.n_basis, c.domain, c.flooring,
-                                       c.eps, st);
-        } else {
-          TRY(ssbk_ip1(p->W, p->U, c.n_batch * c.n_bins, c.n_sources, c.flooring, c.eps, st));
-        }
+        if (c.n_sources == 2)
+          TRY(ssb_fused_ip1_n2(p->W, p->U, Cq, p->rowloss, c.n_batch * c.n_bins, c.flooring, c.eps, st));
+        else
+          TRY(ssbk_ip1(p->W, p->U, c.n_batch * c.n_bins, c.n_sources, c.flooring, c.eps, st, Cq, p->rowloss));
       } else {
         TRY(ssbk_ip2(p->W, p->U, c.n_batch * c.n_bins, c.n_sources, c.pairs, c.n_pairs, c.n_sources, nullptr,
-                     c.flooring, c.eps, st));
+                     c.flooring, c.eps, st, Cq, p->rowloss));
       }
+      if (pw)
+        return ssb_fused_normalize(p->rowloss, p->T, p->W, c.n_batch, c.n_sources, c.n_bins, c.n_basis, c.domain,
+                                   c.flooring, c.eps, st);
       if (c.normalization != SSB_NORM_NONE) TRY(ilrma_normalize(p, st));
       return 0;
     }
@@ -633,6 +634,14 @@ extern "C" int ssb_update_once(ssb_plan* p, void* stream) {
   TRY(iva_source(p, st));
   return iva_spatial(p, st);
 }
+}  // namespace
+
+extern "C" int ssb_update_once(ssb_plan* p, void* stream) {
+  TRY(require_bound(p));
+  // the caller may have rewritten V since the last call: the pre-split copy is only trusted inside ssb_run
+  p->fused.vs_valid = false;
+  return update_once_impl(p, (cudaStream_t)stream);
+}
 
 extern "C" int ssb_compute_loss(ssb_plan* p, double* loss, void* stream) {
   TRY(require_bound(p));
@@ -643,10 +652,12 @@ extern "C" int ssb_compute_loss(ssb_plan* p, double* loss, void* stream) {
 
 extern "C" int ssb_run(ssb_plan* p, int n_iter, double* loss, void* stream) {
   TRY(require_bound(p));
+  p->fused.vs_valid = false;
   for (int it = 0; it < n_iter; ++it) {
-    TRY(ssb_update_once(p, stream));
+    TRY(update_once_impl(p, (cudaStream_t)stream));
     if (loss) TRY(ssb_compute_loss(p, loss + (size_t)it * p->cfg.n_batch, stream));
   }
+  p->fused.vs_valid = false;
   return 0;
 }
 

@@ -323,9 +323,34 @@ __device__ __forceinline__ void group_row_times(const cd (&wrow)[N], const cf* s
   }
 }
 
+
+// q[mat, r] = Re(w_r C w_r^H) for the row held by lane r (the per-bin term of the power normalisation
+// psi_n^2 = mean_i q); C_i staged in `su`.  The stored complex64 filter is what counts.
+template <int N>
+__device__ __forceinline__ void group_emit_q(const cd (&wrow)[N], cf* su, const cf* __restrict__ Cg, int r, bool valid,
+                                             double* __restrict__ q) {
+  __syncwarp();
+  group_load_u<N>(su, Cg, r);
+  __syncwarp();
+  if (!valid || r >= N) return;
+  cd wf[N];
+#pragma unroll
+  for (int c = 0; c < N; ++c) wf[c] = cf2cd(cd2cf(wrow[c]));
+  double acc = 0.0;
+#pragma unroll
+  for (int c = 0; c < N; ++c) {
+    cd s = cd_make(0, 0);
+#pragma unroll
+    for (int a = 0; a < N; ++a) s = cd_fma(wf[a], cf2cd(su[a * N + c]), s);
+    acc += cd_mulc(s, wf[c]).x;
+  }
+  *q = acc;
+}
+
 template <int N>
 __global__ void __launch_bounds__(QW * 32) kq_ip1(cf* __restrict__ W, const cf* __restrict__ U, int n_mat,
-                                                  int flooring, double eps) {
+                                                  int flooring, double eps, const cf* __restrict__ Cn,
+                                                  double* __restrict__ qn) {
   constexpr int GS = GroupShape<N>::GS, GW = GroupShape<N>::GW;
   __shared__ cf s_u[QW][GW][N * N];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -367,6 +392,7 @@ __global__ void __launch_bounds__(QW * 32) kq_ip1(cf* __restrict__ W, const cf* 
 #pragma unroll
     for (int c = 0; c < N; ++c) W[((size_t)mat * N + r) * N + c] = cd2cf(wrow[c]);
   }
+  if (Cn != nullptr) group_emit_q<N>(wrow, su, Cn + (size_t)mat * N * N, r, valid, qn + (size_t)mat * N + r);
 }
 
 // G[x][y] = sum_{a,c} conj(P[a][x]) U[a][c] P[c][y] with P row-distributed (lane a holds P[a][0..1])
@@ -393,7 +419,8 @@ __device__ __forceinline__ void group_quad2(const cd (&P)[2], const cf* su, int 
 
 template <int N>
 __global__ void __launch_bounds__(QW * 32) kq_ip2(cf* __restrict__ W, const cf* __restrict__ U, int n_mat,
-                                                  PairList pl, int flooring, double eps) {
+                                                  PairList pl, int flooring, double eps, const cf* __restrict__ Cn,
+                                                  double* __restrict__ qn) {
   constexpr int GS = GroupShape<N>::GS, GW = GroupShape<N>::GW;
   __shared__ cf s_um[QW][GW][N * N];
   __shared__ cf s_un[QW][GW][N * N];
@@ -468,6 +495,7 @@ __global__ void __launch_bounds__(QW * 32) kq_ip2(cf* __restrict__ W, const cf* 
 #pragma unroll
     for (int c = 0; c < N; ++c) W[((size_t)mat * N + r) * N + c] = cd2cf(wrow[c]);
   }
+  if (Cn != nullptr) group_emit_q<N>(wrow, sum_, Cn + (size_t)mat * N * N, r, valid, qn + (size_t)mat * N + r);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1017,14 +1045,14 @@ int ssbk_wcov(const cf* X, const float* phi, long long sb, long long sn, long lo
   return ssb_check_launch("weighted_covariance", st);
 }
 
-int ssbk_ip1(cf* W, const cf* U, int n_mat, int N, int flooring, float eps, cudaStream_t st) {
+int ssbk_ip1(cf* W, const cf* U, int n_mat, int N, int flooring, float eps, cudaStream_t st, const cf* C, double* q) {
   SSB_DISPATCH_N(N, kq_ip1<NN><<<blocks_for(n_mat, QW * GroupShape<NN>::GW), QW * 32, 0, st>>>(W, U, n_mat, flooring,
-                                                                                                 (double)eps));
+                                                                                                 (double)eps, C, q));
   return ssb_check_launch("update_by_ip1", st);
 }
 
 int ssbk_ip2(cf* W, const cf* U, int n_mat, int N, const int* pairs, int n_pairs, int n_u, const int* uidx,
-             int flooring, float eps, cudaStream_t st) {
+             int flooring, float eps, cudaStream_t st, const cf* C, double* q) {
   SSB_REQUIRE(n_pairs >= 0 && n_pairs <= SSB_MAX_PAIRS, "update_by_ip2: n_pairs=%d exceeds %d", n_pairs,
               SSB_MAX_PAIRS);
   PairList pl;
@@ -1040,7 +1068,7 @@ int ssbk_ip2(cf* W, const cf* U, int n_mat, int N, const int* pairs, int n_pairs
   }
   if (n_pairs == 0) return 0;
   SSB_DISPATCH_N(N, kq_ip2<NN><<<blocks_for(n_mat, QW * GroupShape<NN>::GW), QW * 32, 0, st>>>(W, U, n_mat, pl, flooring,
-                                                                                                 (double)eps));
+                                                                                                 (double)eps, C, q));
   return ssb_check_launch("update_by_ip2", st);
 }
 

@@ -3,11 +3,11 @@ cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -q -x 2>&1 | tail -15 > gpurun_out/r1s2_gputests.log
 cat gpurun_out/r1s2_gputests.log
-for coop in 1 0; do
-SSB_COOP=$coop timeout 900 python tools/bench_configs.py --steps 10 --only "GaussILRMA-IP" > gpurun_out/r1s2_configs_coop$coop.jsonl 2> gpurun_out/r1s2_configs.err
+timeout 900 python tools/bench_configs.py --steps 10 --only "GaussILRMA-IP" > gpurun_out/r1s2_configs_g.jsonl 2> gpurun_out/r1s2_configs.err
 python - <<PY
 import json
-for l in open('gpurun_out/r1s2_configs_coop$coop.jsonl'):
-    d=json.loads(l); print('coop=$coop', d['config'][:60], d['ms_per_step'], d['hbm_frac'], d['kernels_ms_per_step'])
+for l in open('gpurun_out/r1s2_configs_g.jsonl'):
+    d=json.loads(l); print(d['config'][:60], d['ms_per_step'], d['hbm_frac'], d['kernels_ms_per_step'])
 PY
-done
+timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/r1s2_bench2.json 2> gpurun_out/r1s2_bench2.err
+cut -c1-400 gpurun_out/r1s2_bench2.json; tail -3 gpurun_out/r1s2_bench2.err
