@@ -254,15 +254,17 @@ def main():
     # dominant kernel on its own: its compulsory bytes (what it must read/write even in a perfectly fused
     # iteration: X once + the small T/V/W state) over its average launch duration, and the DRAM traffic
     # ncu measured for one launch of it (profiles/r1_ncu_traffic.json, same workload)
-    dom_alg = {"fused_basis": 8 * N * I * J + 4 * (2 * N * I * K + N * K * J),
-               "fused_phi_cov": 8 * N * I * J + 4 * (N * I * K + N * K * J) + 8 * N * N * N * I,
-               "fused_activation": 4 * N * I * J + 4 * (N * I * K + 2 * N * K * J)}.get(dom[0])
+    alg_basis = 8 * N * I * J + 4 * (2 * N * I * K + N * K * J)
+    alg_cov = 8 * N * I * J + 4 * (N * I * K + N * K * J) + 8 * N * N * N * I
+    alg_act = 4 * N * I * J + 4 * (N * I * K + 2 * N * K * J)
+    dom_alg = {"fused_basis": alg_basis, "coop_basis": alg_basis, "fused_phi_cov": alg_cov, "coop_phi_cov": alg_cov,
+               "fused_activation": alg_act, "coop_activation": alg_act}.get(dom[0])
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")) as f:
             tj = json.load(f)
         if (N, I, J, K, B) == (2, 1025, 512, 16, 64):
-            traffic = tj["dram_bytes_per_launch"].get({"fused_basis": "kf_basis", "fused_activation": "kf_activation",
+            traffic = tj["dram_bytes_per_launch"].get({"coop_basis": "kf_basis_coop", "coop_activation": "kf_activation_coop",
                                                        "fused_phi_cov": "kf_phi_cov"}.get(dom[0], ""))
     except Exception:
         traffic = None

@@ -10,6 +10,7 @@
 // [frame][basis] layout (kf_vsplit); both MMA operand orientations come out of that one layout with
 // ldmatrix / ldmatrix.trans, so the hot loop has 4 LDSM instead of 16 LDS and no split arithmetic for V.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "ssb_fused.h"
 #include "ssb_kernels.h"
@@ -632,4 +633,278 @@ int ssb_coop_source(const ssb_config* c, const cf* X, const cf* W, float* T, flo
     SSB_DISPATCH_N(c->n_sources, return (launch_coop<NN, 2>(c, X, W, T, V, P, Vs, Ts, vs_valid, st)));
   }
   return 0;
+}
+
+// ================================================================================================
+// Cooperative weighted covariance for N = 4 and N = 8 (GaussILRMA, p = 2):
+//   phi = 1 / (T V)                                   (ssspy/bss/ilrma.py:1494-1498)
+//   U[b,i,n,a,c] = (1/J) sum_j phi[n,i,j] x_a conj(x_c) (ilrma.py:1500-1505)
+// kf_phi_cov (ssb_fused.cu) keeps every Hermitian entry of G sources in each thread: 2 N^2 registers per source, so
+// at N = 8 only two sources share the products of a frame and the kernel runs 8 warps per SM at 255 registers.
+// Here a CTA owns BT tiles of 16 bins; the X slab of a tile goes once through a shared cp.async ring and the work on
+// it is split over WPT = (N / G) * N/2 warps: warp (sg, q) accumulates, for the G sources of group sg, the q-th
+// Hamiltonian path of the complete graph on the N channels (Walecki's zigzag decomposition: K_N = N/2 paths of
+// N - 1 edges, q, q+1, q-1, q+2, ... mod N) plus the two diagonal entries at the path's end points (q and q + N/2).
+// Every warp therefore runs the SAME code on a per-warp permutation of the channels (only shared-memory offsets
+// differ): N - 1 complex products shared by G sources, N accumulator registers per source instead of N^2, and phi
+// from the pre-split V chunks (ldmatrix) like in kf_basis_coop.  One row group (8 bins) of the tile per pass over
+// the frames, as in kf_phi_cov.
+namespace {
+
+template <int N>
+struct CovCoop {
+  static constexpr int G = 4;                  // sources per warp
+  static constexpr int EQ = N / 2;             // Hamiltonian paths = warps per source group
+  static constexpr int WPT = (N / G) * EQ;     // warps per tile
+  static constexpr int BT = 8 / WPT;           // tiles per CTA
+  static_assert(N == 4 || N == 8, "N = 4, 8 only");
+};
+
+template <int N, int KS>
+__global__ void __launch_bounds__(256) kf_cov_coop(const cf* __restrict__ X, const float* __restrict__ T,
+                                                   const __nv_bfloat16* __restrict__ Vs, cf* __restrict__ U, int I,
+                                                   int J, int K, int nchunk) {
+  using S = CovCoop<N>;
+  constexpr int G = S::G, BT = S::BT, EQ = S::EQ;
+  constexpr int KP = 16 * KS, JKS = KP + PADH;
+  constexpr int CHB = 2 * JCV * JKS * 2;   // bytes of one source's V chunk
+  constexpr int XTB = N * 2048;            // bytes of one tile's X stage
+  constexpr int XSB = BT * XTB;            // bytes of one X stage
+  constexpr int NT = 256;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const uint32_t xs_s = (uint32_t)__cvta_generic_to_shared(smem_raw);
+  const uint32_t vs_s = xs_s + XST * XSB;  // V ring: [2][N][CHB]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int bt = warp / S::WPT, p = warp - bt * S::WPT;
+  const int sg = p / EQ, q = p - sg * EQ;
+  const int b = blockIdx.y;
+  const int i0 = (blockIdx.x * BT + bt) * 16;
+  const bool tile_active = i0 < I;
+  const float invJ = 1.0f / (float)J;
+
+  // channel order of this warp's Hamiltonian path: q, q+1, q-1, q+2, q-2, ... (mod N)
+  int perm[N];
+  uint32_t choff[N];
+#pragma unroll
+  for (int m = 0; m < N; ++m) {
+    const int d = (m + 1) >> 1;
+    perm[m] = (q + ((m & 1) ? d : N - d)) & (N - 1);
+    choff[m] = pin((uint32_t)perm[m] * 2048u);
+  }
+
+  // cooperative loaders: X stage = BT*N*16 rows x 8 pieces of 16 bytes; V chunk = N*CHB bytes
+  constexpr int XP = BT * N * 128 / NT;
+  const cf* xsrc[XP];
+  uint32_t xdst[XP];
+#pragma unroll
+  for (int it = 0; it < XP; ++it) {
+    const int e = it * NT + tid, ch8 = e & 7, r = (e >> 3) & 15, m = (e >> 7) % N, tl = e / (128 * N);
+    const int ib = min((blockIdx.x * BT + tl) * 16 + r, I - 1);
+    xsrc[it] = X + (((size_t)b * N + m) * I + ib) * (size_t)J + 2 * ch8;
+    xdst[it] = pin(xs_s + tl * XTB + (m * 16 + r) * 128 + ((ch8 ^ ((r & 1) << 2)) << 4));
+  }
+  auto issue_x = [&](uint32_t slot_bytes) {
+#pragma unroll
+    for (int it = 0; it < XP; ++it) {
+      cp_async16(xdst[it] + slot_bytes, xsrc[it]);
+      xsrc[it] += 16;
+    }
+  };
+  constexpr int VP = N * CHB / 16 / NT;
+  static_assert((N * CHB / 16) % NT == 0, "V chunk pieces must divide over the CTA");
+  // piece e of a chunk: source e / (CHB/16), byte (e % (CHB/16)) * 16; source s of chunk c sits at ((b*N+s)*nchunk+c)*CHB
+  const unsigned char* vp[VP];
+  uint32_t vd[VP];
+#pragma unroll
+  for (int it = 0; it < VP; ++it) {
+    const int e = it * NT + tid, s = e / (CHB / 16), off = (e % (CHB / 16)) * 16;
+    vp[it] = reinterpret_cast<const unsigned char*>(Vs) + ((size_t)b * N + s) * nchunk * CHB + off;
+    vd[it] = pin(vs_s + s * CHB + off);
+  }
+  auto issue_v = [&](int buf) {
+#pragma unroll
+    for (int it = 0; it < VP; ++it) {
+      cp_async16(vd[it] + buf * (N * CHB), vp[it]);
+      vp[it] += CHB;
+    }
+  };
+  const int mid = lane >> 3, mrow = lane & 7;
+  const uint32_t l1base = pin(vs_s + sg * G * CHB + (mid >> 1) * (JCV * JKS * 2) + (mrow * JKS + (mid & 1) * 8) * 2);
+  const int nsteps = J >> 4;
+
+#pragma unroll 1
+  for (int rs = 0; rs < 2; ++rs) {
+    const int row = i0 + g + 8 * rs;
+    // T fragments of the G sources (both row groups feed the MMA; only row group rs is used afterwards)
+    uint32_t Thi[G][KS][4], Tlo[G][KS][4];
+#pragma unroll
+    for (int gs = 0; gs < G; ++gs)
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          const float* tr = T + (((size_t)b * N + sg * G + gs) * I + min(i0 + g + 8 * rr, I - 1)) * K;
+#pragma unroll
+          for (int nb = 0; nb < 2; ++nb) {
+            const int k0 = ks * 16 + nb * 8 + 2 * t;
+            const Split sp = split2((k0 < K) ? tr[k0] : 0.f, (k0 + 1 < K) ? tr[k0 + 1] : 0.f);
+            Thi[gs][ks][nb * 2 + rr] = sp.hi;
+            Tlo[gs][ks][nb * 2 + rr] = sp.lo;
+          }
+        }
+    float2 ao[G][N - 1], ad[G];  // path edges (x'_e conj x'_{e+1}); end-point powers (|x'_0|^2, |x'_{N-1}|^2)
+#pragma unroll
+    for (int gs = 0; gs < G; ++gs) {
+#pragma unroll
+      for (int e = 0; e < N - 1; ++e) ao[gs][e] = make_float2(0.f, 0.f);
+      ad[gs] = make_float2(0.f, 0.f);
+    }
+    // one frame: the products of this warp's path, shared by its G sources
+    auto accum = [&](const float (&xr)[N], const float (&xi)[N], const float (&phf)[G]) {
+      float2 pp[G];
+#pragma unroll
+      for (int gs = 0; gs < G; ++gs) pp[gs] = make_float2(phf[gs], phf[gs]);
+#pragma unroll
+      for (int e = 0; e < N - 1; ++e) {
+        const float2 pr = make_float2(fmaf(xr[e], xr[e + 1], xi[e] * xi[e + 1]), fmaf(xi[e], xr[e + 1], -(xr[e] * xi[e + 1])));
+#pragma unroll
+        for (int gs = 0; gs < G; ++gs) ao[gs][e] = __ffma2_rn(pp[gs], pr, ao[gs][e]);
+      }
+      const float2 pd = make_float2(fmaf(xr[0], xr[0], xi[0] * xi[0]), fmaf(xr[N - 1], xr[N - 1], xi[N - 1] * xi[N - 1]));
+#pragma unroll
+      for (int gs = 0; gs < G; ++gs) ad[gs] = __ffma2_rn(pp[gs], pd, ad[gs]);
+    };
+    const uint32_t xlane[2] = {pin(xs_s + bt * XTB + (g + 8 * rs) * 128 + ((t ^ ((g & 1) << 2)) << 4)),
+                               pin(xs_s + bt * XTB + (g + 8 * rs) * 128 + (((4 + t) ^ ((g & 1) << 2)) << 4))};
+    // restart the streams
+    if (rs) {
+#pragma unroll
+      for (int it = 0; it < XP; ++it) xsrc[it] -= nsteps * 16;
+#pragma unroll
+      for (int it = 0; it < VP; ++it) vp[it] -= (size_t)nchunk * CHB;
+    }
+    __syncthreads();  // the previous pass no longer reads the rings
+    issue_v(0);
+    issue_x(0);
+    cp_async_commit();
+    if (nsteps > 1) issue_x(XSB);
+    cp_async_commit();
+    uint32_t rd_slot = 0, wr_slot = 2 * XSB;
+#pragma unroll 1
+    for (int s = 0; s < nsteps; ++s) {
+      cp_async_wait<XST - 2>();
+      __syncthreads();
+      if (s + 2 < nsteps) issue_x(wr_slot);
+      if ((s & 1) == 0 && (s >> 1) + 1 < nchunk) issue_v(((s >> 1) + 1) & 1);
+      cp_async_commit();
+      const uint32_t vb1 = l1base + ((s >> 1) & 1) * (N * CHB) + (s & 1) * (16 * JKS * 2);
+      const uint32_t xb[2] = {xlane[0] + rd_slot, xlane[1] + rd_slot};
+      rd_slot = rd_slot + XSB == XST * XSB ? 0 : rd_slot + XSB;
+      wr_slot = wr_slot + XSB == XST * XSB ? 0 : wr_slot + XSB;
+      if (!tile_active) continue;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float ph[2][G];
+#pragma unroll
+        for (int gs = 0; gs < G; ++gs) {
+          float R[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks) {
+            uint32_t bh0, bh1, bl0, bl1;
+            ldsm_x4(bh0, bh1, bl0, bl1, vb1 + gs * CHB + (8 * h * JKS + ks * 16) * 2);
+            mma_split(R, Thi[gs][ks], Tlo[gs][ks], bh0, bh1, bl0, bl1);
+          }
+          ph[0][gs] = fast_rcp(rs ? R[2] : R[0]);
+          ph[1][gs] = fast_rcp(rs ? R[3] : R[1]);
+        }
+        float4 x[N];
+#pragma unroll
+        for (int m = 0; m < N; ++m) x[m] = lds128(xb[h] + choff[m]);
+        float xr[N], xi[N];
+#pragma unroll
+        for (int m = 0; m < N; ++m) {
+          xr[m] = x[m].x;
+          xi[m] = x[m].y;
+        }
+        accum(xr, xi, ph[0]);
+#pragma unroll
+        for (int m = 0; m < N; ++m) {
+          xr[m] = x[m].z;
+          xi[m] = x[m].w;
+        }
+        accum(xr, xi, ph[1]);
+      }
+    }
+    if (tile_active) {
+      const bool wr = (t == 0) && (row < I);
+#pragma unroll
+      for (int gs = 0; gs < G; ++gs) {
+        cf* u = U + (((size_t)b * I + min(row, I - 1)) * N + sg * G + gs) * N * N;
+#pragma unroll
+        for (int e = 0; e < N - 1; ++e) {
+          float2 v = ao[gs][e];
+          v.x += __shfl_xor_sync(SSB_FULL, v.x, 1);
+          v.y += __shfl_xor_sync(SSB_FULL, v.y, 1);
+          v.x += __shfl_xor_sync(SSB_FULL, v.x, 2);
+          v.y += __shfl_xor_sync(SSB_FULL, v.y, 2);
+          const int a = perm[e], c = perm[e + 1];
+          if (wr) {
+            u[a * N + c] = make_float2(v.x * invJ, v.y * invJ);
+            u[c * N + a] = make_float2(v.x * invJ, -v.y * invJ);
+          }
+        }
+        float2 v = ad[gs];
+        v.x += __shfl_xor_sync(SSB_FULL, v.x, 1);
+        v.y += __shfl_xor_sync(SSB_FULL, v.y, 1);
+        v.x += __shfl_xor_sync(SSB_FULL, v.x, 2);
+        v.y += __shfl_xor_sync(SSB_FULL, v.y, 2);
+        if (wr) {
+          u[perm[0] * N + perm[0]] = make_float2(v.x * invJ, 0.f);
+          u[perm[N - 1] * N + perm[N - 1]] = make_float2(v.y * invJ, 0.f);
+        }
+      }
+    }
+  }
+}
+
+template <int N, int KS>
+int launch_cov_coop(const ssb_config* c, const cf* X, const float* T, const __nv_bfloat16* Vs, cf* U, cudaStream_t st) {
+  using S = CovCoop<N>;
+  const int B = c->n_batch, I = c->n_bins, J = c->n_frames, K = c->n_basis;
+  constexpr int KP = 16 * KS, JKS = KP + PADH, CHB = 2 * JCV * JKS * 2;
+  const int nchunk = (J + JCV - 1) / JCV;
+  const size_t sm = (size_t)XST * S::BT * N * 2048 + (size_t)2 * N * CHB;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SSB_CUDA(cudaFuncSetAttribute(kf_cov_coop<N, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    attr_set = true;
+  }
+  dim3 grid((I + 16 * S::BT - 1) / (16 * S::BT), B);
+  kf_cov_coop<N, KS><<<grid, 256, sm, st>>>(X, T, Vs, U, I, J, K, nchunk);
+  return ssb_check_launch("coop_phi_cov", st);
+}
+
+}  // namespace
+
+// N = 8 only by default: at N = 4 kf_phi_cov already shares the products among all four sources and reads X once,
+// and the cooperative kernel's second pass over the row groups misses L2 (measured 0.47 ms vs 0.41 ms,
+// profiles/r1_ncu_coop_summary.md); SSB_COOP_COV=2 forces it for N = 4 as well.
+int ssb_coop_cov_supported(const ssb_config* c) {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("SSB_COOP_COV");
+    mode = e ? atoi(e) : 1;
+  }
+  const bool n_ok = c->n_sources == 8 || (mode == 2 && c->n_sources == 4);
+  return n_ok && (c->n_frames % 16) == 0 && c->n_basis <= 32;
+}
+
+// weighted covariance of every source from the pre-split activation Vs held in ws (valid after ssb_coop_source)
+int ssb_coop_cov(const ssb_config* c, const cf* X, const float* T, const void* ws, cf* U, cudaStream_t st) {
+  SSB_REQUIRE(ssb_coop_cov_supported(c) && ws != nullptr, "coop_cov: unsupported configuration");
+  const __nv_bfloat16* Vs = (const __nv_bfloat16*)ws;
+  const bool k16 = c->n_basis <= 16;
+  if (c->n_sources == 4) return k16 ? launch_cov_coop<4, 1>(c, X, T, Vs, U, st) : launch_cov_coop<4, 2>(c, X, T, Vs, U, st);
+  return k16 ? launch_cov_coop<8, 1>(c, X, T, Vs, U, st) : launch_cov_coop<8, 2>(c, X, T, Vs, U, st);
 }

@@ -1149,6 +1149,14 @@ int launch_all(const ssb_config* c, const cf* X, cf* W, float* T, float* V, floa
     kf_activation<KS><<<ga, FW * 32, sm_act, st>>>(P, T, V, N, I, J, K, c->flooring, c->eps);
     if (ssb_check_launch("fused_activation", st)) return 1;
   }
+  // SSB_COOP_COV: 1 (default) cooperative covariance kernel for N = 4, 8 (needs the Vs left by ssb_coop_source)
+  static int coop_cov = -1;
+  if (coop_cov < 0) {
+    const char* e = getenv("SSB_COOP_COV");
+    coop_cov = e ? atoi(e) : 1;
+  }
+  if (coop && coop_cov && vs != nullptr && W != nullptr && ssb_coop_cov_supported(c))
+    return ssb_coop_cov(c, X, T, vs->base, U, st);
   dim3 gc((N + G - 1) / G, (I + FW * 16 - 1) / (FW * 16), B);
   kf_phi_cov<N, KS><<<gc, FW * 32, sm_cov, st>>>(X, T, V, U, I, J, K);
   return ssb_check_launch("fused_phi_cov", st);

@@ -23,6 +23,9 @@ int ssb_fused_source_and_cov(const ssb_config* cfg, ssb_fused_ws* ws, const cf* 
 // slab in shared memory, then the activation kernel; ws is zero-initialised scratch of ssb_coop_ws_bytes() bytes
 // (pre-split bf16 copies of V and T)
 size_t ssb_coop_ws_bytes(const ssb_config* cfg);
+// cooperative weighted covariance (N = 4, 8): reads the pre-split Vs left in ws by ssb_coop_source
+int ssb_coop_cov_supported(const ssb_config* cfg);
+int ssb_coop_cov(const ssb_config* cfg, const cf* X, const float* T, const void* ws, cf* U, cudaStream_t st);
 int ssb_coop_source(const ssb_config* cfg, const cf* X, const cf* W, float* T, float* V, float* P, void* ws,
                     int vs_valid, cudaStream_t st);
 // closed-form IP1 for two sources; with C != NULL also q[mat,n] = Re(w_n C w_n^H) for the normalisation
