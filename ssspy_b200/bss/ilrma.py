@@ -5,10 +5,10 @@ GaussILRMA :582-1989, TILRMA :1992-3334, GGDILRMA :3337-4410).  Same constructor
 (``basis``, ``activation``, ``latent``, ``demix_filter``, ``output``, ``loss``); all arithmetic runs in
 libssb.so's CUDA kernels.
 
-Covered: spatial_algorithm IP / IP1 / IP2 / ISS / ISS1 / ISS2, source_algorithm MM / ME, any ``domain`` in (0, 2],
-``partitioning`` False / True (latent variable Z), normalization True / "power" / "projection_back" / False,
-projection-back and minimal-distortion-principle scale restoration, ISS2 included.  IPA raises NotImplementedError
-(no CPU fallback).
+Covered: spatial_algorithm IP / IP1 / IP2 / ISS / ISS1 / ISS2 / IPA (IPA for GaussILRMA only, as in the reference),
+source_algorithm MM / ME, any ``domain`` in (0, 2], ``partitioning`` False / True (latent variable Z),
+normalization True / "power" / "projection_back" / False, projection-back and minimal-distortion-principle scale
+restoration.  There is no CPU fallback.
 """
 import ctypes
 import functools

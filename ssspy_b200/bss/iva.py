@@ -1,7 +1,7 @@
 """Auxiliary-function IVA on the device (host mirror of ssspy/bss/iva.py: IVABase :48-281,
 AuxIVABase :553-641, AuxIVA :1403-2214, AuxLaplaceIVA :2976-3128, AuxGaussIVA :3131-3473).
 
-Covered: spatial_algorithm IP / IP1 / IP2 / ISS / ISS1 / ISS2 with the Laplace and Gauss contrasts.  The
+Covered: spatial_algorithm IP / IP1 / IP2 / ISS / ISS1 / ISS2 / IPA with the Laplace and Gauss contrasts.  The
 contrast functions are arbitrary Python callables in the reference; on the device they are an
 enum, so the generic ``AuxIVA`` accepts only the two known contrasts (no CPU fallback).
 """
