@@ -3,6 +3,8 @@
 // One warp owns one (mixture, bin); the N x N complex linear algebra is done in fp64 in shared
 // memory by the warp (ssb_common.cuh), the frame reductions in fp32 with a warp tree reduce.
 #include "ssb_group.cuh"
+#include <stdlib.h>
+
 #include "ssb_kernels.h"
 
 namespace {
@@ -705,6 +707,185 @@ __global__ void __launch_bounds__(ISS_NW * 32) k_iss1_cta(cf* __restrict__ Y, co
 }
 
 // ------------------------------------------------------------------------------------------------
+// ISS1 in the covariance domain (N <= 4), one WARP per (b,i).  The N sequential steps of
+// ssspy/bss/_update_spatial_model.py:181-192 only need second-order statistics of the slab: with y = A y_old,
+//   num_m = mean_j phi_m y_m conj(y_n) = a_m U_m a_n^H,   den_m = mean_j phi_m |y_n|^2 = a_n U_m a_n^H,
+//   U_m = mean_j phi_m y_old y_old^H,   a_m = row m of A,
+// and the update y_m -= v_m y_n is A[m,:] -= v_m A[n,:].  So: one sweep over the slab for the N weighted
+// covariances (Hermitian products of a frame shared by the N sources, one reduce-scatter over the lanes instead of
+// N x 3N warp reductions), the N rank-one updates of A in fp64 with A distributed over the lanes (lane (m, r) owns
+// A[m][r] and row r of U_m), and one sweep applying A (the slab is re-read from L2: the footprint of all resident
+// warps is a few tens of MB).  No shared-memory slab, no CTA barrier, any n_frames.
+constexpr int ISSC_W = 4;  // warps (= bins) per block
+template <int N>
+__global__ void __launch_bounds__(ISSC_W * 32) k_iss1_cov(cf* __restrict__ Y, const float* __restrict__ phi,
+                                                          long long sb, long long sn, long long si, int n_bins_total,
+                                                          int I, int J, int flooring, float eps) {
+  constexpr int NO = N * (N - 1) / 2;      // off-diagonal pairs (a < c)
+  constexpr int NV = N * N;                // reals per source: NO (re, im) pairs + N diagonals
+  constexpr int NVAL = N * NV;             // statistics per bin
+  constexpr int NVP = (NVAL + 31) / 32 * 32;
+  constexpr int PER = NVP / 32;
+  __shared__ float s_red[ISSC_W][NVP];
+  __shared__ cf s_A[ISSC_W][N * N];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bi = blockIdx.x * ISSC_W + w;
+  if (bi >= n_bins_total) return;
+  const int b = bi / I, i = bi - b * I;
+  const size_t base = ((size_t)b * N * I + i) * J;
+  const size_t cs = (size_t)I * J;
+  const float* ph0 = phi + (size_t)b * sb + (size_t)i * si;
+  // ---- sweep 1: weighted covariances ---------------------------------------------------------------------------
+  float acc[NVP];  // per source m: [m*NV + 2e], [m*NV + 2e + 1] = Re, Im of pair e; [m*NV + 2*NO + a] = diagonal a
+#pragma unroll
+  for (int e = 0; e < NVP; ++e) acc[e] = 0.f;
+#pragma unroll 2
+  for (int j = lane; j < J; j += 32) {
+    cf y[N];
+    float ph[N];
+#pragma unroll
+    for (int m = 0; m < N; ++m) {
+      y[m] = Y[base + m * cs + j];
+      ph[m] = ph0[(size_t)m * sn + j];
+    }
+    int e = 0;
+#pragma unroll
+    for (int a = 0; a < N; ++a)
+#pragma unroll
+      for (int c = a + 1; c < N; ++c, ++e) {
+        const float pr = fmaf(y[a].x, y[c].x, y[a].y * y[c].y), pi = fmaf(y[a].y, y[c].x, -(y[a].x * y[c].y));
+#pragma unroll
+        for (int m = 0; m < N; ++m) {
+          acc[m * NV + 2 * e] = fmaf(ph[m], pr, acc[m * NV + 2 * e]);
+          acc[m * NV + 2 * e + 1] = fmaf(ph[m], pi, acc[m * NV + 2 * e + 1]);
+        }
+      }
+#pragma unroll
+    for (int a = 0; a < N; ++a) {
+      const float pd = fmaf(y[a].x, y[a].x, y[a].y * y[a].y);
+#pragma unroll
+      for (int m = 0; m < N; ++m) acc[m * NV + 2 * NO + a] = fmaf(ph[m], pd, acc[m * NV + 2 * NO + a]);
+    }
+  }
+  // reduce-scatter over the lanes: after the step with offset o a lane keeps the half of its values selected by
+  // bit o of its id; lane l ends with PER consecutive values of the warp sum
+  {
+    int cnt = NVP;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      cnt >>= 1;
+      const bool up = (lane & o) != 0;
+#pragma unroll
+      for (int e = 0; e < NVP / 2; ++e) {
+        if (e < cnt) {
+          const float send = up ? acc[e] : acc[e + cnt];
+          const float keep = up ? acc[e + cnt] : acc[e];
+          acc[e] = keep + __shfl_xor_sync(SSB_FULL, send, o);
+        }
+      }
+    }
+    int off = 0, span = NVP;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      span >>= 1;
+      if (lane & o) off += span;
+    }
+#pragma unroll
+    for (int q = 0; q < PER; ++q) s_red[w][off + q] = acc[q];
+  }
+  __syncwarp();
+  // ---- N rank-one updates of A: lane (m, r) owns A[m][r] and row r of U_m (fp64) ----------------------------------
+  {
+    const int m = lane / N, r = lane - m * N;
+    const bool act = lane < N * N;
+    const double invJ = 1.0 / (double)J;
+    cd Um[N];  // U_m[r][s], s = 0..N-1
+#pragma unroll
+    for (int s_ = 0; s_ < N; ++s_) {
+      double re = 0.0, im = 0.0;
+      if (act) {
+        if (s_ == r) {
+          re = (double)s_red[w][m * NV + 2 * NO + r];
+        } else {
+          const int a = r < s_ ? r : s_, c = r < s_ ? s_ : r;
+          const int e = a * N - a * (a + 1) / 2 + (c - a - 1);
+          re = (double)s_red[w][m * NV + 2 * e];
+          im = (double)s_red[w][m * NV + 2 * e + 1];
+          if (r > s_) im = -im;  // U[c][a] = conj(U[a][c])
+        }
+      }
+      Um[s_] = cd_make(re * invJ, im * invJ);
+    }
+    cd amr = cd_make((act && m == r) ? 1.0 : 0.0, 0.0);  // A[m][r]
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      // row n of A, gathered from lanes (n, s)
+      cd an[N];
+#pragma unroll
+      for (int s_ = 0; s_ < N; ++s_) an[s_] = shfl_cd(amr, n * N + s_);
+      // t_r = sum_s U_m[r][s] conj(A[n][s]);  num_m = sum_r A[m][r] t_r;  den_m = sum_r A[n][r] t_r
+      cd tr = cd_make(0, 0);
+#pragma unroll
+      for (int s_ = 0; s_ < N; ++s_) tr = cd_fma(Um[s_], cd_conj(an[s_]), tr);
+      cd anr = an[0];
+#pragma unroll
+      for (int s_ = 1; s_ < N; ++s_)
+        if (r == s_) anr = an[s_];
+      cd pn = act ? cd_mul(amr, tr) : cd_make(0, 0);
+      double pden = act ? cd_mul(anr, tr).x : 0.0;
+      if (N == 3) {  // the three lanes of a source are not an xor group
+        cd sacc = cd_make(0, 0);
+        double dacc = 0.0;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          const int src = (m * 3 + q) & 31;
+          sacc.x += __shfl_sync(SSB_FULL, pn.x, src);
+          sacc.y += __shfl_sync(SSB_FULL, pn.y, src);
+          dacc += __shfl_sync(SSB_FULL, pden, src);
+        }
+        pn = sacc;
+        pden = dacc;
+      } else {
+#pragma unroll
+        for (int o = 1; o < N; o <<= 1) {
+          pn.x += __shfl_xor_sync(SSB_FULL, pn.x, o);
+          pn.y += __shfl_xor_sync(SSB_FULL, pn.y, o);
+          pden += __shfl_xor_sync(SSB_FULL, pden, o);
+        }
+      }
+      // same rounding points as the step-by-step kernel: fp32 statistics, floor, fp32 quotient
+      const float d_ = ssb_floor((float)pden, flooring, eps);
+      cd v;
+      if (m == n) v = cd_make((double)(1.0f - 1.0f / sqrtf(d_)), 0.0);
+      else v = cd_make((double)((float)pn.x / d_), (double)((float)pn.y / d_));
+      amr = cd_sub(amr, cd_mul(v, anr));  // A[m][r] -= v_m A[n][r]
+    }
+    if (act) s_A[w][lane] = cd2cf(amr);
+  }
+  __syncwarp();
+  // ---- sweep 2: y <- A y (slab re-read through L2) -----------------------------------------------------------------
+  cf a_[N * N];
+#pragma unroll
+  for (int e = 0; e < N * N; ++e) a_[e] = s_A[w][e];
+#pragma unroll 2
+  for (int j = lane; j < J; j += 32) {
+    cf y[N];
+#pragma unroll
+    for (int m = 0; m < N; ++m) y[m] = Y[base + m * cs + j];
+#pragma unroll
+    for (int p = 0; p < N; ++p) {
+      float orr = 0.f, oi = 0.f;
+#pragma unroll
+      for (int q = 0; q < N; ++q) {
+        orr = fmaf(a_[p * N + q].x, y[q].x, fmaf(-a_[p * N + q].y, y[q].y, orr));
+        oi = fmaf(a_[p * N + q].x, y[q].y, fmaf(a_[p * N + q].y, y[q].x, oi));
+      }
+      Y[base + p * cs + j] = make_float2(orr, oi);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // ISS2 (ssspy/bss/_update_spatial_model.py:197-314): pairwise iterative source steering, one CTA per (b,i).
 // For every pair (m, n), u = (y_m, y_n):
 //   all sources s:   G_s = mean_j phi_s u u^H                                   (2x2 Hermitian)
@@ -1074,8 +1255,21 @@ int ssbk_ip2(cf* W, const cf* U, int n_mat, int N, const int* pairs, int n_pairs
 
 int ssbk_iss1(cf* Y, const float* phi, long long sb, long long sn, long long si, int B, int N, int I, int J,
               int flooring, float eps, cudaStream_t st) {
-  // CTA-per-bin shared-memory variant when the (source x frame) slab of Y + weights fits one CTA
+  // CTA-per-bin shared-memory variants when the (source x frame) slab of Y + weights fits one CTA
   const size_t slab = (size_t)N * J * (sizeof(cf) + sizeof(float));
+  static int cov_mode = -1;  // SSB_ISS_COV: 1 (default) covariance-domain kernel for N <= 4, 0 step-by-step kernels
+  if (cov_mode < 0) {
+    const char* e = getenv("SSB_ISS_COV");
+    cov_mode = e ? atoi(e) : 1;
+  }
+  if (N <= 4 && cov_mode) {
+    const int nb = B * I;
+    const int blocks = (nb + ISSC_W - 1) / ISSC_W;
+    if (N == 2) k_iss1_cov<2><<<blocks, ISSC_W * 32, 0, st>>>(Y, phi, sb, sn, si, nb, I, J, flooring, eps);
+    else if (N == 3) k_iss1_cov<3><<<blocks, ISSC_W * 32, 0, st>>>(Y, phi, sb, sn, si, nb, I, J, flooring, eps);
+    else k_iss1_cov<4><<<blocks, ISSC_W * 32, 0, st>>>(Y, phi, sb, sn, si, nb, I, J, flooring, eps);
+    return ssb_check_launch("update_by_iss1", st);
+  }
   if (slab <= 200 * 1024) {
     SSB_DISPATCH_N(N, {
       static bool attr_set = false;
