@@ -636,6 +636,213 @@ int ssb_coop_source(const ssb_config* c, const cf* X, const cf* W, float* T, flo
 }
 
 // ================================================================================================
+// Multiplicative updates with the two elementwise factors given as arrays (FastGaussMNMF,
+// ssspy/bss/mnmf.py:1351-1358, :1408-1415):
+//   OUTER_ROWS = true  (basis):       T[i,k] <- floor(T sqrt(sum_j A[i,j] V[k,j] / sum_j Bm[i,j] V[k,j]))
+//   OUTER_ROWS = false (activation):  V[k,j] <- floor(V sqrt(sum_i T[i,k] A[i,j] / sum_i T[i,k] Bm[i,j]))
+// i.e. the second GEMM of kf_basis_coop / kf_activation_coop with its A operand streamed from memory instead of
+// computed: warp = 16 "outer" indices (bins resp. frames) of one (mixture, source), all warps of the CTA walk the
+// "inner" (reduction) index together; the pre-split operand chunks (Vs resp. Ts, 32 inner indices) go through a
+// CTA-wide ring, every warp streams its own 16 x 16 tiles of A and Bm through a private cp.async ring, splits them
+// to bf16 (hi, lo) and feeds mma.sync.  The result is also written pre-split (Ts resp. Vs) for the next kernel.
+constexpr int ABST = 4;          // stages of the per-warp tile ring
+constexpr int ABTD = ABST / 2;   // operand chunks issued ahead (see TD)
+constexpr int ABTS = ABTD + 1;   // slots of the operand chunk ring
+
+__device__ __forceinline__ float2 lds64f(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
+  return v;
+}
+
+template <int KS, bool OUTER_ROWS>
+__global__ void __launch_bounds__(AW * 32)
+    kf_update_ab(const float* __restrict__ A, const float* __restrict__ Bm, float* __restrict__ Out,
+                 const __nv_bfloat16* __restrict__ Opd, __nv_bfloat16* __restrict__ OutSplit, int I, int J, int K,
+                 int nchunk_in, int nchunk_out, int flooring, float eps) {
+  constexpr int KP = 16 * KS, JKS = KP + PADH;
+  constexpr int CHB = 2 * JCV * JKS * 2;          // bytes of one 32-index operand chunk (hi + lo)
+  constexpr int PITCH = OUTER_ROWS ? 96 : 80;     // tile row pitch: conflict-free LDS.64 resp. LDS.32 fragment reads
+  constexpr int PTB = 16 * PITCH;                 // bytes of one tile
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const uint32_t op_s = (uint32_t)__cvta_generic_to_shared(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const size_t bn = blockIdx.y;
+  const int n_outer = OUTER_ROWS ? I : J, n_inner = OUTER_ROWS ? J : I;
+  const uint32_t pw_s = op_s + ABTS * CHB + warp * (ABST * 2 * PTB);  // [stage][A | Bm][16 rows][PITCH]
+  const int o0 = (blockIdx.x * AW + warp) * 16;
+  const bool warp_active = o0 < n_outer;
+  const int oc[2] = {min(o0 + g, n_outer - 1), min(o0 + g + 8, n_outer - 1)};
+  const bool ovalid[2] = {o0 + g < n_outer, o0 + g + 8 < n_outer};
+  const float* Ab = A + bn * (size_t)I * J;
+  const float* Bb = Bm + bn * (size_t)I * J;
+  float* Ob = Out + bn * (size_t)K * (OUTER_ROWS ? I : J);
+
+  // current values of the entries this thread updates: [ks][nb][rr][e] = (outer rr, basis ks*16 + nb*8 + 2t + e)
+  float old[KS][2][2][2];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+    for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int k = ks * 16 + nb * 8 + 2 * t + e;
+          old[ks][nb][rr][e] = (k < K) ? (OUTER_ROWS ? Ob[(size_t)oc[rr] * K + k] : Ob[(size_t)k * J + oc[rr]]) : 0.f;
+        }
+  float num[2 * KS][4], den[2 * KS][4];
+#pragma unroll
+  for (int q = 0; q < 2 * KS; ++q)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) num[q][c] = den[q][c] = 0.f;
+
+  const unsigned char* osrc = reinterpret_cast<const unsigned char*>(Opd) + bn * (size_t)nchunk_in * CHB;
+  auto issue_op = [&](int chunk, int buf) {
+    for (int c = threadIdx.x; c < CHB / 16; c += AW * 32)
+      cp_async16(op_s + buf * CHB + c * 16, osrc + (size_t)chunk * CHB + c * 16);
+  };
+  // tile of step s: 16 rows x 64 bytes of A and of Bm, 4 lanes per row, 2 + 2 pieces per lane.
+  //   OUTER_ROWS: rows = this warp's outer indices (clamped), columns = inner indices 16 s ..
+  //   else      : rows = inner indices 16 s .. (clamped to the array), columns = this warp's outer indices
+  const float* tsrc[2][2];
+  uint32_t tdst[2];
+  int trow[2];
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int idx = it * 32 + lane, r = idx >> 2, part = idx & 3;
+    trow[it] = r;
+    tdst[it] = pin(pw_s + r * PITCH + part * 16);
+    if (OUTER_ROWS) {
+      const size_t off = (size_t)min(o0 + r, I - 1) * J + part * 4;
+      tsrc[it][0] = Ab + off;
+      tsrc[it][1] = Bb + off;
+    } else {
+      const size_t off = (size_t)min(o0, J - 16) + part * 4;
+      tsrc[it][0] = Ab + off;
+      tsrc[it][1] = Bb + off;
+    }
+  }
+  auto issue_tile = [&](int step, uint32_t slot_bytes) {
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const size_t adv = OUTER_ROWS ? (size_t)step * 16 : (size_t)min(step * 16 + trow[it], I - 1) * J;
+      cp_async16(tdst[it] + slot_bytes, tsrc[it][0] + adv);
+      cp_async16(tdst[it] + slot_bytes + PTB, tsrc[it][1] + adv);
+    }
+  };
+  const int mid = lane >> 3, mrow = lane & 7;
+  const uint32_t l2base = pin(op_s + (mid >> 1) * (JCV * JKS * 2) + (((mid & 1) * 8 + mrow) * JKS) * 2);
+  const uint32_t flane = OUTER_ROWS ? pin(pw_s + g * PITCH + (2 * t) * 4) : pin(pw_s + (2 * t) * PITCH + g * 4);
+  const int nsteps = (n_inner + 15) >> 4;
+#pragma unroll
+  for (int q = 0; q < ABST - 1; ++q) {
+    if ((q & 1) == 0 && (q >> 1) < nchunk_in) issue_op(q >> 1, (q >> 1) % ABTS);
+    if (warp_active && q < nsteps) issue_tile(q, q * (2 * PTB));
+    cp_async_commit();
+  }
+  uint32_t rd_slot = 0, wr_slot = (ABST - 1) * (2 * PTB), o_slot = 0;
+  for (int s = 0; s < nsteps; ++s) {
+    cp_async_wait<ABST - 2>();
+    if ((s & 1) == 0) {
+      __syncthreads();
+      const int cn = (s >> 1) + ABTD;
+      if (cn < nchunk_in) issue_op(cn, cn % ABTS);
+    } else {
+      __syncwarp();
+    }
+    if (warp_active && s + ABST - 1 < nsteps) issue_tile(s + ABST - 1, wr_slot);
+    cp_async_commit();
+    const uint32_t ob = l2base + o_slot + (s & 1) * (16 * JKS * 2);
+    const uint32_t fb = flane + rd_slot;
+    rd_slot = rd_slot + 2 * PTB == ABST * 2 * PTB ? 0 : rd_slot + 2 * PTB;
+    wr_slot = wr_slot + 2 * PTB == ABST * 2 * PTB ? 0 : wr_slot + 2 * PTB;
+    if (s & 1) o_slot = o_slot + CHB == ABTS * CHB ? 0 : o_slot + CHB;
+    if (!warp_active) continue;
+    // A fragments: a0 = (outer g, inner 2t..), a1 = (outer g+8, inner 2t..), a2 = (outer g, inner 2t+8..), a3
+    uint32_t Ahi[4], Alo[4], Bhi[4], Blo[4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        float2 av, bv;
+        if (OUTER_ROWS) {
+          av = lds64f(fb + (8 * rr) * PITCH + (8 * h) * 4);
+          bv = lds64f(fb + PTB + (8 * rr) * PITCH + (8 * h) * 4);
+        } else {
+          av = make_float2(lds32f(fb + (8 * h) * PITCH + 32 * rr), lds32f(fb + (8 * h + 1) * PITCH + 32 * rr));
+          bv = make_float2(lds32f(fb + PTB + (8 * h) * PITCH + 32 * rr), lds32f(fb + PTB + (8 * h + 1) * PITCH + 32 * rr));
+        }
+        const Split sa = split2(av.x, av.y);
+        const Split sb = split2(bv.x, bv.y);
+        Ahi[h * 2 + rr] = sa.hi;
+        Alo[h * 2 + rr] = sa.lo;
+        Bhi[h * 2 + rr] = sb.hi;
+        Blo[h * 2 + rr] = sb.lo;
+      }
+#pragma unroll
+    for (int q = 0; q < 2 * KS; ++q) {
+      uint32_t th0, th1, tl0, tl1;
+      ldsm_x4_t(th0, th1, tl0, tl1, ob + q * 16);
+      mma_split(num[q], Ahi, Alo, th0, th1, tl0, tl1);
+      mma_split(den[q], Bhi, Blo, th0, th1, tl0, tl1);
+    }
+  }
+  if (!warp_active) return;
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+    for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        if (!ovalid[rr]) continue;
+        const int q = ks * 2 + nb;
+        const int k0 = ks * 16 + nb * 8 + 2 * t;
+        float vn[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          vn[e] = 0.f;
+          if (k0 + e < K) {
+            vn[e] = ssb_floor(old[ks][nb][rr][e] * sqrtf(num[q][rr * 2 + e] / den[q][rr * 2 + e]), flooring, eps);
+            if (OUTER_ROWS) Ob[(size_t)oc[rr] * K + k0 + e] = vn[e];
+            else Ob[(size_t)(k0 + e) * J + oc[rr]] = vn[e];
+          }
+        }
+        const Split sp = split2(vn[0], vn[1]);
+        __nv_bfloat16* oh = OutSplit + (bn * nchunk_out + (oc[rr] >> 5)) * (size_t)(2 * JCV * JKS) + (oc[rr] & 31) * JKS + k0;
+        *reinterpret_cast<uint32_t*>(oh) = sp.hi;
+        *reinterpret_cast<uint32_t*>(oh + JCV * JKS) = sp.lo;
+      }
+}
+
+template <int KS>
+int launch_update_ab(int which, const float* A, const float* Bm, float* T, float* V, __nv_bfloat16* Vs,
+                     __nv_bfloat16* Ts, int BN, int I, int J, int K, int flooring, float eps, cudaStream_t st) {
+  constexpr int KP = 16 * KS, JKS = KP + PADH, CHB = 2 * JCV * JKS * 2;
+  const int nchunk_j = (J + JCV - 1) / JCV, nchunk_i = (I + JCV - 1) / JCV;
+  const size_t sm_b = (size_t)ABTS * CHB + (size_t)AW * ABST * 2 * 16 * 96;
+  const size_t sm_a = (size_t)ABTS * CHB + (size_t)AW * ABST * 2 * 16 * 80;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SSB_CUDA(cudaFuncSetAttribute(kf_update_ab<KS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_b));
+    SSB_CUDA(cudaFuncSetAttribute(kf_update_ab<KS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_a));
+    attr_set = true;
+  }
+  if (which == 0) {
+    dim3 gv(nchunk_j, BN);
+    kf_vsplit<KS><<<gv, 128, 0, st>>>(V, Vs, J, K, nchunk_j);
+    if (ssb_check_launch("coop_vsplit", st)) return 1;
+    dim3 grid((I + AW * 16 - 1) / (AW * 16), BN);
+    kf_update_ab<KS, true><<<grid, AW * 32, sm_b, st>>>(A, Bm, T, Vs, Ts, I, J, K, nchunk_j, nchunk_i, flooring, eps);
+    return ssb_check_launch("coop_basis_ab", st);
+  }
+  dim3 grid((J + AW * 16 - 1) / (AW * 16), BN);
+  kf_update_ab<KS, false><<<grid, AW * 32, sm_a, st>>>(A, Bm, V, Ts, Vs, I, J, K, nchunk_i, nchunk_j, flooring, eps);
+  return ssb_check_launch("coop_activation_ab", st);
+}
+
+// ================================================================================================
 // Cooperative weighted covariance for N = 4 and N = 8 (GaussILRMA, p = 2):
 //   phi = 1 / (T V)                                   (ssspy/bss/ilrma.py:1494-1498)
 //   U[b,i,n,a,c] = (1/J) sum_j phi[n,i,j] x_a conj(x_c) (ilrma.py:1500-1505)
@@ -907,4 +1114,17 @@ int ssb_coop_cov(const ssb_config* c, const cf* X, const float* T, const void* w
   const bool k16 = c->n_basis <= 16;
   if (c->n_sources == 4) return k16 ? launch_cov_coop<4, 1>(c, X, T, Vs, U, st) : launch_cov_coop<4, 2>(c, X, T, Vs, U, st);
   return k16 ? launch_cov_coop<8, 1>(c, X, T, Vs, U, st) : launch_cov_coop<8, 2>(c, X, T, Vs, U, st);
+}
+
+// FastGaussMNMF source model on the tensor pipe: which = 0 basis (reads V, writes T and the pre-split Ts),
+// which = 1 activation (reads the Ts left by the basis call, writes V).  ws as for ssb_coop_source.
+int ssb_coop_update_ab(const ssb_config* c, int which, const float* A, const float* Bm, float* T, float* V, void* ws,
+                       cudaStream_t st) {
+  SSB_REQUIRE((c->n_frames % 16) == 0 && c->n_basis <= 32 && ws != nullptr, "coop_update_ab: unsupported configuration");
+  __nv_bfloat16* Vs = (__nv_bfloat16*)ws;
+  __nv_bfloat16* Ts = (__nv_bfloat16*)((char*)ws + coop_vs_bytes(c));
+  const int BN = c->n_batch * c->n_sources;
+  if (c->n_basis <= 16)
+    return launch_update_ab<1>(which, A, Bm, T, V, Vs, Ts, BN, c->n_bins, c->n_frames, c->n_basis, c->flooring, c->eps, st);
+  return launch_update_ab<2>(which, A, Bm, T, V, Vs, Ts, BN, c->n_bins, c->n_frames, c->n_basis, c->flooring, c->eps, st);
 }

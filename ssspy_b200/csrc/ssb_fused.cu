@@ -1167,7 +1167,8 @@ int launch_all(const ssb_config* c, const cf* X, cf* W, float* T, float* V, floa
 // ---- host side ------------------------------------------------------------------------------------
 size_t ssb_fused_carve(ssb_fused_ws* ws, const ssb_config* c, char* base) {
   ws->base = base;
-  ws->bytes = ssb_fused_supported(c) ? ((ssb_coop_ws_bytes(c) + 255) & ~(size_t)255) : 0;
+  const bool mnmf_ab = c->model == SSB_MODEL_FASTMNMF_GAUSS && c->n_basis <= 32 && (c->n_frames % 16) == 0;
+  ws->bytes = (ssb_fused_supported(c) || mnmf_ab) ? ((ssb_coop_ws_bytes(c) + 255) & ~(size_t)255) : 0;
   ws->zeroed = false;
   ws->vs_valid = false;
   return ws->bytes;

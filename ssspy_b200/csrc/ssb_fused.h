@@ -26,6 +26,9 @@ size_t ssb_coop_ws_bytes(const ssb_config* cfg);
 // cooperative weighted covariance (N = 4, 8): reads the pre-split Vs left in ws by ssb_coop_source
 int ssb_coop_cov_supported(const ssb_config* cfg);
 int ssb_coop_cov(const ssb_config* cfg, const cf* X, const float* T, const void* ws, cf* U, cudaStream_t st);
+// FastGaussMNMF: tensor-core multiplicative updates with elementwise factors given as arrays (which: 0 basis, 1 activation)
+int ssb_coop_update_ab(const ssb_config* cfg, int which, const float* A, const float* Bm, float* T, float* V, void* ws,
+                       cudaStream_t st);
 int ssb_coop_source(const ssb_config* cfg, const cf* X, const cf* W, float* T, float* V, float* P, void* ws,
                     int vs_valid, cudaStream_t st);
 // closed-form IP1 for two sources; with C != NULL also q[mat,n] = Re(w_n C w_n^H) for the normalisation

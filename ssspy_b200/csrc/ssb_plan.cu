@@ -444,10 +444,18 @@ int mnmf_source(ssb_plan* p, cudaStream_t st) {
   const int B = c.n_batch, N = c.n_sources, I = c.n_bins, J = c.n_frames, K = c.n_basis;
   const float* lam;
   TRY(mnmf_lambda(p, &lam, st));
+  // tensor-core updates (ssb_coop.cu) when the shape allows, else the CUDA-core contractions
+  const bool tc = c.fast_path && c.n_basis <= 32 && (J % 16) == 0 && p->fused.bytes > 0;
+  if (tc && !p->fused.zeroed) {
+    SSB_CUDA(cudaMemsetAsync(p->fused.base, 0, p->fused.bytes, st));
+    p->fused.zeroed = true;
+  }
   TRY(ssbk_mnmf_gh(p->X, p->T, p->V, lam, p->W, p->variance, p->big, p->big2, B, N, I, J, K, st));
-  TRY(ssbk_nmf_basis_ab(p->big, p->big2, p->T, p->V, B * N, I, J, K, c.flooring, c.eps, st));
+  if (tc) TRY(ssb_coop_update_ab(&c, 0, p->big, p->big2, p->T, p->V, p->fused.base, st));
+  else TRY(ssbk_nmf_basis_ab(p->big, p->big2, p->T, p->V, B * N, I, J, K, c.flooring, c.eps, st));
   TRY(mnmf_lambda(p, &lam, st));
   TRY(ssbk_mnmf_gh(p->X, p->T, p->V, lam, p->W, p->variance, p->big, p->big2, B, N, I, J, K, st));
+  if (tc) return ssb_coop_update_ab(&c, 1, p->big, p->big2, p->T, p->V, p->fused.base, st);
   return ssbk_nmf_activation_ab(p->big, p->big2, p->T, p->V, B * N, I, J, K, c.flooring, c.eps, st);
 }
 
