@@ -134,14 +134,16 @@ __global__ void __launch_bounds__(MW * 32) km_phi(const cf* __restrict__ X, cons
   }
 }
 
-// spatial update (mnmf.py:1660-1675) and the per-bin sums zsum[b,i,m] = sum_j Z2_m for the normalisation;
-// one source per pass over the frames keeps the accumulators in registers.  update_d = 0: zsum only.
+// spatial update (mnmf.py:1660-1675) and the per-bin sums zsum[b,i,m] = sum_j Z2_m for the normalisation.
+// Every source uses the D of the previous iteration (L is formed from the context loaded up front), so GS sources
+// share one pass over the frames: GS = N for N <= 4 (one pass), 1 otherwise (registers).  update_d = 0: zsum only.
 template <int N>
 __global__ void __launch_bounds__(MW * 32) km_spatial(const cf* __restrict__ X, const float* __restrict__ T,
                                                       const float* __restrict__ V, const float* __restrict__ Lam,
                                                  const cf* __restrict__ Q,
                                                       float* __restrict__ D, double* __restrict__ zsum, int B, int I,
                                                       int J, int K, int update_d) {
+  constexpr int GS = N <= 4 ? N : 1;
   __shared__ BinCtx<N> ctx[MW];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bin = blockIdx.x * MW + wib;
@@ -149,34 +151,46 @@ __global__ void __launch_bounds__(MW * 32) km_spatial(const cf* __restrict__ X, 
   const int b = bin / I, i = bin - b * I;
   BinCtx<N>& c = ctx[wib];
   load_ctx<N>(c, T, Q, D, b, i, I, K, lane);
-  float newD[N];  // lane n < N... each lane keeps the row it will write: computed per source below
-  for (int n = 0; n < (update_d ? N : 1); ++n) {
-    float num[N], den[N], zs[N];
+  for (int n0 = 0; n0 < (update_d ? N : 1); n0 += GS) {
+    float num[GS][N], den[GS][N], zs[N];
 #pragma unroll
-    for (int m = 0; m < N; ++m) num[m] = den[m] = zs[m] = 0.f;
+    for (int m = 0; m < N; ++m) {
+      zs[m] = 0.f;
+#pragma unroll
+      for (int gs = 0; gs < GS; ++gs) num[gs][m] = den[gs][m] = 0.f;
+    }
     for (int j = lane; j < J; j += 32) {
       float lam[N], L[N], Z2[N];
       frame_stats<N>(c, X, V, Lam, b, i, j, I, J, K, lam, L, Z2);
-      float ln = lam[0];
+      float ln[GS];
 #pragma unroll
-      for (int q = 1; q < N; ++q) ln = (q == n) ? lam[q] : ln;
+      for (int gs = 0; gs < GS; ++gs) {
+        ln[gs] = lam[0];
+#pragma unroll
+        for (int q = 1; q < N; ++q) ln[gs] = (q == n0 + gs) ? lam[q] : ln[gs];
+      }
 #pragma unroll
       for (int m = 0; m < N; ++m) {
         const float r = 1.0f / L[m];
-        num[m] = fmaf(ln * r * r, Z2[m], num[m]);
-        den[m] = fmaf(ln, r, den[m]);
+        const float a = r * r * Z2[m];
         zs[m] += Z2[m];
+#pragma unroll
+        for (int gs = 0; gs < GS; ++gs) {
+          num[gs][m] = fmaf(ln[gs], a, num[gs][m]);
+          den[gs][m] = fmaf(ln[gs], r, den[gs][m]);
+        }
       }
     }
 #pragma unroll
     for (int m = 0; m < N; ++m) {
-      const float nu = warp_sum(num[m]), de = warp_sum(den[m]), z = warp_sum(zs[m]);
-      if (update_d) newD[m] = sqrtf(nu / de) * c.D[n][m];
-      if (n == 0 && lane == 0) zsum[((size_t)b * I + i) * N + m] = (double)z;
-    }
-    if (update_d && lane == 0) {
+      const float z = warp_sum(zs[m]);
+      if (n0 == 0 && lane == 0) zsum[((size_t)b * I + i) * N + m] = (double)z;
 #pragma unroll
-      for (int m = 0; m < N; ++m) D[(((size_t)b * I + i) * N + n) * N + m] = newD[m];
+      for (int gs = 0; gs < GS; ++gs) {
+        const float nu = warp_sum(num[gs][m]), de = warp_sum(den[gs][m]);
+        if (update_d && lane == 0 && n0 + gs < N)
+          D[(((size_t)b * I + i) * N + n0 + gs) * N + m] = sqrtf(nu / de) * c.D[n0 + gs][m];
+      }
     }
   }
 }
