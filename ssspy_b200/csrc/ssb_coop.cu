@@ -858,26 +858,27 @@ int launch_update_ab(int which, const float* A, const float* Bm, float* T, float
 // the frames, as in kf_phi_cov.
 namespace {
 
-template <int N>
+template <int N, int G_>
 struct CovCoop {
-  static constexpr int G = 4;                  // sources per warp
+  static constexpr int G = G_;                 // sources per warp
   static constexpr int EQ = N / 2;             // Hamiltonian paths = warps per source group
   static constexpr int WPT = (N / G) * EQ;     // warps per tile
-  static constexpr int BT = 8 / WPT;           // tiles per CTA
+  static constexpr int BT = (8 / WPT) > 0 ? 8 / WPT : 1;  // tiles per CTA
+  static constexpr int NT = WPT * BT * 32;     // threads per CTA
   static_assert(N == 4 || N == 8, "N = 4, 8 only");
 };
 
-template <int N, int KS>
-__global__ void __launch_bounds__(256) kf_cov_coop(const cf* __restrict__ X, const float* __restrict__ T,
+template <int N, int KS, int G_>
+__global__ void __launch_bounds__(CovCoop<N, G_>::NT) kf_cov_coop(const cf* __restrict__ X, const float* __restrict__ T,
                                                    const __nv_bfloat16* __restrict__ Vs, cf* __restrict__ U, int I,
                                                    int J, int K, int nchunk) {
-  using S = CovCoop<N>;
+  using S = CovCoop<N, G_>;
   constexpr int G = S::G, BT = S::BT, EQ = S::EQ;
   constexpr int KP = 16 * KS, JKS = KP + PADH;
   constexpr int CHB = 2 * JCV * JKS * 2;   // bytes of one source's V chunk
   constexpr int XTB = N * 2048;            // bytes of one tile's X stage
   constexpr int XSB = BT * XTB;            // bytes of one X stage
-  constexpr int NT = 256;
+  constexpr int NT = S::NT;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const uint32_t xs_s = (uint32_t)__cvta_generic_to_shared(smem_raw);
   const uint32_t vs_s = xs_s + XST * XSB;  // V ring: [2][N][CHB]
@@ -1075,20 +1076,20 @@ __global__ void __launch_bounds__(256) kf_cov_coop(const cf* __restrict__ X, con
   }
 }
 
-template <int N, int KS>
+template <int N, int KS, int G_>
 int launch_cov_coop(const ssb_config* c, const cf* X, const float* T, const __nv_bfloat16* Vs, cf* U, cudaStream_t st) {
-  using S = CovCoop<N>;
+  using S = CovCoop<N, G_>;
   const int B = c->n_batch, I = c->n_bins, J = c->n_frames, K = c->n_basis;
   constexpr int KP = 16 * KS, JKS = KP + PADH, CHB = 2 * JCV * JKS * 2;
   const int nchunk = (J + JCV - 1) / JCV;
   const size_t sm = (size_t)XST * S::BT * N * 2048 + (size_t)2 * N * CHB;
   static bool attr_set = false;
   if (!attr_set) {
-    SSB_CUDA(cudaFuncSetAttribute(kf_cov_coop<N, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    SSB_CUDA(cudaFuncSetAttribute(kf_cov_coop<N, KS, G_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     attr_set = true;
   }
   dim3 grid((I + 16 * S::BT - 1) / (16 * S::BT), B);
-  kf_cov_coop<N, KS><<<grid, 256, sm, st>>>(X, T, Vs, U, I, J, K, nchunk);
+  kf_cov_coop<N, KS, G_><<<grid, S::NT, sm, st>>>(X, T, Vs, U, I, J, K, nchunk);
   return ssb_check_launch("coop_phi_cov", st);
 }
 
@@ -1112,8 +1113,14 @@ int ssb_coop_cov(const ssb_config* c, const cf* X, const float* T, const void* w
   SSB_REQUIRE(ssb_coop_cov_supported(c) && ws != nullptr, "coop_cov: unsupported configuration");
   const __nv_bfloat16* Vs = (const __nv_bfloat16*)ws;
   const bool k16 = c->n_basis <= 16;
-  if (c->n_sources == 4) return k16 ? launch_cov_coop<4, 1>(c, X, T, Vs, U, st) : launch_cov_coop<4, 2>(c, X, T, Vs, U, st);
-  return k16 ? launch_cov_coop<8, 1>(c, X, T, Vs, U, st) : launch_cov_coop<8, 2>(c, X, T, Vs, U, st);
+  static int g2 = -1;  // SSB_COV_G: sources per warp at N = 8 (4: fewer product instructions, 2: twice the warps)
+  if (g2 < 0) {
+    const char* e = getenv("SSB_COV_G");
+    g2 = (e && atoi(e) == 2) ? 1 : 0;
+  }
+  if (c->n_sources == 4) return k16 ? launch_cov_coop<4, 1, 4>(c, X, T, Vs, U, st) : launch_cov_coop<4, 2, 4>(c, X, T, Vs, U, st);
+  if (g2) return k16 ? launch_cov_coop<8, 1, 2>(c, X, T, Vs, U, st) : launch_cov_coop<8, 2, 2>(c, X, T, Vs, U, st);
+  return k16 ? launch_cov_coop<8, 1, 4>(c, X, T, Vs, U, st) : launch_cov_coop<8, 2, 4>(c, X, T, Vs, U, st);
 }
 
 // FastGaussMNMF source model on the tensor pipe: which = 0 basis (reads V, writes T and the pre-split Ts),
