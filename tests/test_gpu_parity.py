@@ -391,11 +391,14 @@ def test_full_size_properties_and_one_mixture_oracle(N, spatial):
 @pytest.mark.parametrize("N,I,J,K,spatial", [(2, 37, 48, 5, "IP"), (3, 130, 272, 16, "IP"), (4, 20, 32, 20, "IP2"),
                                              (2, 257, 512, 16, "IP"), (8, 17, 64, 3, "IP"), (5, 33, 80, 32, "IP"),
                                              (3, 40, 64, 6, "ISS"), (4, 33, 272, 20, "ISS"), (6, 18, 48, 4, "IP2"),
-                                             (7, 10, 32, 16, "IP")])
+                                             (7, 10, 32, 16, "IP"), (8, 21, 96, 24, "IP"), (8, 9, 48, 32, "IP2"),
+                                             (2, 70, 528, 16, "IP"), (2, 33, 64, 6, "ISS"), (4, 130, 96, 9, "IP")])
 def test_fused_tensor_core_path_matches_oracle_and_modular(N, I, J, K, spatial):
     """The fused mma.sync kernels (bf16 hi/lo split, n_frames % 16 == 0, K <= 32) against the fp64 oracle
     and against the modular CUDA-core kernels (fast_path=False); covers ragged bin tiles (I % 16 != 0),
-    K padding (K < 16, 16 < K < 32) and two staging rounds over frames (J > 256)."""
+    K padding (K < 16, 16 < K < 32), odd numbers of 16-frame steps / half-filled 32-frame operand chunks, partially
+    filled cooperative CTAs, the N = 8 cooperative covariance kernel at K <= 16 and K > 16, and the covariance-domain
+    ISS1 kernel (N <= 4)."""
     from oracle import ilrma as oilrma
     from ssspy_b200.bss import GaussILRMA
     from ssspy_b200.utils.synth import make_batch, make_nmf_init
@@ -465,12 +468,15 @@ def test_fast_gauss_mnmf_matches_reference(name):
     assert relerr(phase_align_rows(Q, g["Q"]) if alg == "IP2" else Q, g["Q"]) < 3 * TOL_Y
 
 
+@pytest.mark.parametrize("J,K", [(40, 4), (48, 4), (64, 20)])
 @pytest.mark.parametrize("alg", ["IP", "IP2"])
-def test_fast_gauss_mnmf_batched_vs_oracle_and_rng(alg):
+def test_fast_gauss_mnmf_batched_vs_oracle_and_rng(alg, J, K):
+    """J % 16 == 0 takes the tensor-core multiplicative updates (kf_update_ab; K <= 16 and K > 16), J = 40 the
+    CUDA-core contractions."""
     from oracle import mnmf as omnmf
     from ssspy_b200.bss import FastGaussMNMF
     from ssspy_b200.utils.synth import make_batch
-    B, N, I, J, K, n_iter = 2, 3, 14, 40, 4, 4
+    B, N, I, n_iter = 2, 3, 14, 4
     X = make_batch(B, N, I, J, config_id=5, mode="mix")
     m = FastGaussMNMF(n_basis=K, diagonalizer_algorithm=alg, rng=np.random.default_rng(77))
     Y = m(X, n_iter=n_iter)
