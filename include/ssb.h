@@ -48,6 +48,9 @@ enum {
                              (MM and ME source updates, IP1 / IP2 / ISS1) */
   SSB_MODEL_ILRMA_GGD = 5 /* ssspy/bss/ilrma.py:3337 GGDILRMA: generalised Gaussian, model_param = beta in (0, 2)
                              (MM only, IP1 / IP2 / ISS1) */
+  ,
+  SSB_MODEL_FDICA_LAPLACE = 6 /* ssspy/bss/fdica.py:1527 AuxLaplaceFDICA: per-bin weights 2 / floor(2 |y|), IP1 / IP2
+                                 (fdica.py:1065-1245); ssb_plan_permutation_* is its permutation alignment */
 };
 /* spatial_algorithm (ssspy/bss/ilrma.py:27, ssspy/bss/iva.py:44) */
 enum { SSB_SPATIAL_IP1 = 0, SSB_SPATIAL_IP2 = 1, SSB_SPATIAL_ISS1 = 2,
@@ -180,6 +183,18 @@ int ssb_update_by_iss2(void* Y, const float* phi, long long phi_sb, long long ph
  * reference's `normalization` and `max_iter` arguments */
 int ssb_update_by_ipa(void* Y, const float* phi, long long phi_sb, long long phi_sn, long long phi_si, int B, int N,
                       int I, int J, int normalization, int max_iter, int flooring, float eps, void* stream);
+/* correlation-based permutation solver (ssspy/algorithm/permutation_alignment.py:12-121), two phases around the
+ * host-side argsort of the per-bin correlations (numpy.argsort on float64, as the reference):
+ *   ssb_permutation_correlation: corr[B,I] f64 = sum_j (sum_n P_n)^2, P = |Y| / floor(norm over the sources)
+ *   ssb_permutation_align: visits the bins of mixture b in order[b, 0..I-1] (int32, device), permutes Y[B,N,I,J] (and
+ *   the rows of W[B,I,N,N] when W != NULL) in place and writes the chosen permutations perms[B,I,N] (int32).
+ * The plan forms operate on the bound Y = W X (FDICA: recomputed first) and W. */
+int ssb_permutation_correlation(const void* Y, double* corr, int B, int N, int I, int J, int flooring, float eps,
+                                void* stream);
+int ssb_permutation_align(void* Y, void* W, const int32_t* order, int32_t* perms, int B, int N, int I, int J,
+                          int flooring, float eps, void* stream);
+int ssb_plan_permutation_correlation(ssb_plan* plan, double* corr, void* stream);
+int ssb_plan_permutation_align(ssb_plan* plan, const int32_t* order, int32_t* perms, void* stream);
 /* projection_back, filter form (ssspy/algorithm/projection_back.py:87-99):
  * Wout[m,n,:] = W[m,n,:] * (W[m]^-1)[ref, n]; Wout may alias W. */
 int ssb_projection_back_w(const void* W, void* Wout, int n_mat, int N, int reference_id, void* stream);

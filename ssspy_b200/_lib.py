@@ -14,7 +14,7 @@ SSB_MAX_BASIS = 64
 SSB_MAX_PAIRS = 64
 
 MODEL_ILRMA_GAUSS, MODEL_IVA_LAPLACE, MODEL_IVA_GAUSS, MODEL_FASTMNMF_GAUSS = 0, 1, 2, 3
-MODEL_ILRMA_T, MODEL_ILRMA_GGD = 4, 5
+MODEL_ILRMA_T, MODEL_ILRMA_GGD, MODEL_FDICA_LAPLACE = 4, 5, 6
 SPATIAL_IP1, SPATIAL_IP2, SPATIAL_ISS1, SPATIAL_ISS2, SPATIAL_IPA = 0, 1, 2, 3, 4
 SOURCE_MM, SOURCE_ME = 0, 1
 FLOOR_MAX, FLOOR_ADD, FLOOR_NONE = 0, 1, 2
@@ -68,6 +68,10 @@ SIGNATURES = {
     "ssb_update_by_iss1": [_vp, _vp, _ll, _ll, _ll, _i, _i, _i, _i, _i, _f, _vp],
     "ssb_update_by_iss2": [_vp, _vp, _ll, _ll, _ll, _i, _i, _i, _i, _i32p, _i, _i, _f, _vp],
     "ssb_update_by_ipa": [_vp, _vp, _ll, _ll, _ll, _i, _i, _i, _i, _i, _i, _i, _f, _vp],
+    "ssb_permutation_correlation": [_vp, _vp, _i, _i, _i, _i, _i, _f, _vp],
+    "ssb_permutation_align": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp],
+    "ssb_plan_permutation_correlation": [_vp, _vp, _vp],
+    "ssb_plan_permutation_align": [_vp, _vp, _vp, _vp],
     "ssb_projection_back_w": [_vp, _vp, _i, _i, _i, _vp],
     "ssb_projection_back_y": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "ssb_inv": [_vp, _vp, _i, _i, _vp],

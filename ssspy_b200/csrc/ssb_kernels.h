@@ -47,6 +47,14 @@ int ssbk_iss1(cf* Y, const float* phi, long long sb, long long sn, long long si,
 // pairs (host, 2*n_pairs, already wrapped into [0, N)); _update_spatial_model.py:197-314
 int ssbk_iss2(cf* Y, const float* phi, long long sb, long long sn, long long si, int B, int N, int I, int J,
               const int* pairs, int n_pairs, int flooring, float eps, cudaStream_t st);
+// AuxLaplaceFDICA (ssb_fdica.cu): per-(source, bin, frame) weights for the sources in `src` (NULL = all, in order)
+// written as phi[B, n_src, I, J]; per-bin loss term; correlation-based permutation solver
+int ssbk_fdica_phi(const cf* X, const cf* W, float* phi, const int* src, int n_src, int B, int N, int I, int J,
+                   int flooring, float eps, cudaStream_t st);
+int ssbk_fdica_rowloss(const cf* X, const cf* W, double* rowloss, int B, int N, int I, int J, cudaStream_t st);
+int ssbk_perm_corr(const cf* Y, double* corr, int B, int N, int I, int J, int flooring, float eps, cudaStream_t st);
+int ssbk_perm_align(cf* Y, cf* W, const int* order, int* perms, int B, int N, int I, int J, int flooring, float eps,
+                    cudaStream_t st);
 int ssbk_ipa(cf* Y, const float* phi, long long sb, long long sn, long long si, int B, int N, int I, int J,
              int normalization, int max_iter, int flooring, float eps, cudaStream_t st);
 int ssbk_pb_w(const cf* W, cf* Wout, cf* scale_out, int n_mat, int N, int ref, cudaStream_t st);

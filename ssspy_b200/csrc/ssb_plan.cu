@@ -145,6 +145,7 @@ struct ssb_plan {
     return (cfg.spatial == SSB_SPATIAL_ISS1 || cfg.spatial == SSB_SPATIAL_ISS2 || cfg.spatial == SSB_SPATIAL_IPA) &&
            !mnmf();
   }
+  bool fdica() const { return cfg.model == SSB_MODEL_FDICA_LAPLACE; }
   bool ilrma() const {
     return cfg.model == SSB_MODEL_ILRMA_GAUSS || cfg.model == SSB_MODEL_ILRMA_T || cfg.model == SSB_MODEL_ILRMA_GGD;
   }
@@ -170,7 +171,7 @@ size_t carve(ssb_plan* p, char* base) {
   const size_t B = c.n_batch, N = c.n_sources, I = c.n_bins, J = c.n_frames;
   Carver cv{base};
   // + 16 rows of slack: the fused activation kernel prefetches whole 16-bin tiles of P without clamping
-  p->big = (p->ilrma() || p->mnmf()) ? cv.take<float>(B * N * I * J + 16 * J) : nullptr;
+  p->big = (p->ilrma() || p->mnmf() || p->fdica()) ? cv.take<float>(B * N * I * J + 16 * J) : nullptr;
   p->big2 = p->mnmf() ? cv.take<float>(B * N * I * J) : nullptr;
   p->qinv = p->mnmf() ? cv.take<cd>(B * I * N * N) : nullptr;
   p->big3 = p->mnmf() ? cv.take<float>(B * N * I * J) : nullptr;
@@ -197,7 +198,10 @@ size_t carve(ssb_plan* p, char* base) {
 
 int validate(const ssb_config* c) {
   SSB_REQUIRE(c != nullptr, "config is NULL");
-  SSB_REQUIRE(c->model >= 0 && c->model <= 5, "unknown model %d", c->model);
+  SSB_REQUIRE(c->model >= 0 && c->model <= 6, "unknown model %d", c->model);
+  if (c->model == SSB_MODEL_FDICA_LAPLACE)
+    SSB_REQUIRE(c->spatial == SSB_SPATIAL_IP1 || c->spatial == SSB_SPATIAL_IP2, "Not support spatial algorithm id %d.",
+                c->spatial);
   SSB_REQUIRE(c->spatial >= 0 && c->spatial <= 4, "Not support spatial algorithm id %d.", c->spatial);
   if (c->spatial == SSB_SPATIAL_IPA) {
     SSB_REQUIRE(c->model != SSB_MODEL_ILRMA_T, "IPA is not supported for t-ILRMA.");
@@ -426,6 +430,35 @@ int iva_loss(ssb_plan* p, double* loss, cudaStream_t st) {
   return ssbk_iva_loss(p->r2, p->variance, p->logdet, loss, c.model, c.n_batch, c.n_sources, c.n_bins, c.n_frames, st);
 }
 
+// ---- AuxLaplaceFDICA (fdica.py:1065-1245): per-bin weights, the IP kernels of the IVA path ------------------------
+int fdica_spatial(ssb_plan* p, cudaStream_t st) {
+  const ssb_config& c = p->cfg;
+  const int B = c.n_batch, N = c.n_sources, I = c.n_bins, J = c.n_frames;
+  const bool fast = c.fast_path && (J % 16) == 0;
+  if (c.spatial == SSB_SPATIAL_IP2) {  // weights recomputed for every pair with the current W (fdica.py:1218-1243)
+    for (int q = 0; q < c.n_pairs; ++q) {
+      const int pr[2] = {c.pairs[2 * q], c.pairs[2 * q + 1]};
+      const int uidx[2] = {0, 1};
+      TRY(ssbk_fdica_phi(p->X, p->W, p->big, pr, 2, B, N, I, J, c.flooring, c.eps, st));
+      if (fast) TRY(ssb_fused_cov_w(p->X, p->big, 2LL * I * J, (long long)I * J, J, 2, p->U, B, N, I, J, st));
+      else TRY(ssbk_wcov(p->X, p->big, 2LL * I * J, (long long)I * J, J, nullptr, 2, p->U, B, N, I, J, st));
+      TRY(ssbk_ip2(p->W, p->U, B * I, N, pr, 1, 2, uidx, c.flooring, c.eps, st));
+    }
+    return 0;
+  }
+  TRY(ssbk_fdica_phi(p->X, p->W, p->big, nullptr, N, B, N, I, J, c.flooring, c.eps, st));
+  if (fast) TRY(ssb_fused_cov_w(p->X, p->big, (long long)N * I * J, (long long)I * J, J, N, p->U, B, N, I, J, st));
+  else TRY(ssbk_wcov(p->X, p->big, (long long)N * I * J, (long long)I * J, J, nullptr, N, p->U, B, N, I, J, st));
+  return ssbk_ip1(p->W, p->U, B * I, N, c.flooring, c.eps, st);
+}
+
+int fdica_loss(ssb_plan* p, double* loss, cudaStream_t st) {
+  const ssb_config& c = p->cfg;
+  TRY(ssbk_fdica_rowloss(p->X, p->W, p->rowloss, c.n_batch, c.n_sources, c.n_bins, c.n_frames, st));
+  TRY(ssbk_logdet(p->W, p->logdet, c.n_batch * c.n_bins, c.n_sources, st));
+  return ssbk_ilrma_loss_reduce(p->rowloss, p->logdet, loss, c.n_batch, 1, c.n_bins, st);
+}
+
 // ---- FastGaussMNMF: W slot = diagonaliser Q[B,I,N,N] c64, variance slot = spatial D[B,I,N,N] f32 ----------
 // Lambda = T V on the tensor pipe when the fused kernel covers the shape, else NULL (the consumers then
 // contract over K themselves)
@@ -570,12 +603,14 @@ extern "C" int ssb_plan_prepare(ssb_plan* p, void* stream) {
 extern "C" int ssb_update_source_model(ssb_plan* p, void* stream) {
   TRY(require_bound(p));
   if (p->mnmf()) return mnmf_source(p, (cudaStream_t)stream);
+  if (p->fdica()) return 0;  // no source parameters
   return p->ilrma() ? ilrma_source(p, (cudaStream_t)stream) : iva_source(p, (cudaStream_t)stream);
 }
 
 extern "C" int ssb_update_spatial_model(ssb_plan* p, void* stream) {
   TRY(require_bound(p));
   if (p->mnmf()) return mnmf_spatial(p, (cudaStream_t)stream);
+  if (p->fdica()) return fdica_spatial(p, (cudaStream_t)stream);
   return p->ilrma() ? ilrma_spatial(p, (cudaStream_t)stream) : iva_spatial(p, (cudaStream_t)stream);
 }
 
@@ -639,6 +674,7 @@ int update_once_impl(ssb_plan* p, cudaStream_t st) {
     if (p->cfg.normalization != SSB_NORM_NONE) TRY(ilrma_normalize(p, st));
     return 0;
   }
+  if (p->fdica()) return fdica_spatial(p, st);
   TRY(iva_source(p, st));
   return iva_spatial(p, st);
 }
@@ -655,6 +691,7 @@ extern "C" int ssb_compute_loss(ssb_plan* p, double* loss, void* stream) {
   TRY(require_bound(p));
   SSB_REQUIRE(loss != nullptr, "loss output is NULL");
   if (p->mnmf()) return mnmf_loss(p, loss, (cudaStream_t)stream);
+  if (p->fdica()) return fdica_loss(p, loss, (cudaStream_t)stream);
   return p->ilrma() ? ilrma_loss(p, loss, (cudaStream_t)stream) : iva_loss(p, loss, (cudaStream_t)stream);
 }
 
@@ -776,6 +813,38 @@ extern "C" int ssb_update_by_ipa(void* Y, const float* phi, long long phi_sb, lo
   if (B <= 0 || I <= 0 || J <= 0) return 0;
   return ssbk_ipa((cf*)Y, phi, phi_sb, phi_sn, phi_si, B, N, I, J, normalization, max_iter, flooring, eps,
                   (cudaStream_t)stream);
+}
+
+extern "C" int ssb_permutation_correlation(const void* Y, double* corr, int B, int N, int I, int J, int flooring,
+                                           float eps, void* stream) {
+  SSB_REQUIRE(Y && corr, "NULL argument");
+  if (B <= 0 || I <= 0 || J <= 0) return 0;
+  return ssbk_perm_corr((const cf*)Y, corr, B, N, I, J, flooring, eps, (cudaStream_t)stream);
+}
+
+extern "C" int ssb_permutation_align(void* Y, void* W, const int32_t* order, int32_t* perms, int B, int N, int I, int J,
+                                     int flooring, float eps, void* stream) {
+  SSB_REQUIRE(Y && order && perms, "NULL argument");
+  if (B <= 0 || I <= 0 || J <= 0) return 0;
+  return ssbk_perm_align((cf*)Y, (cf*)W, order, perms, B, N, I, J, flooring, eps, (cudaStream_t)stream);
+}
+
+// solve_permutation_by_correlation (fdica.py:257-281): Y = W X first, then the two phases on the bound buffers
+extern "C" int ssb_plan_permutation_correlation(ssb_plan* p, double* corr, void* stream) {
+  TRY(require_bound(p));
+  const ssb_config& c = p->cfg;
+  SSB_REQUIRE(p->W != nullptr && corr != nullptr, "permutation alignment needs demixing filters");
+  cudaStream_t st = (cudaStream_t)stream;
+  TRY(ssbk_separate(p->X, p->W, p->Y, nullptr, c.n_batch, c.n_sources, c.n_bins, c.n_frames, st));
+  return ssbk_perm_corr(p->Y, corr, c.n_batch, c.n_sources, c.n_bins, c.n_frames, c.flooring, c.eps, st);
+}
+
+extern "C" int ssb_plan_permutation_align(ssb_plan* p, const int32_t* order, int32_t* perms, void* stream) {
+  TRY(require_bound(p));
+  const ssb_config& c = p->cfg;
+  SSB_REQUIRE(p->W != nullptr && order != nullptr && perms != nullptr, "NULL argument");
+  return ssbk_perm_align(p->Y, p->W, order, perms, c.n_batch, c.n_sources, c.n_bins, c.n_frames, c.flooring, c.eps,
+                         (cudaStream_t)stream);
 }
 
 extern "C" int ssb_projection_back_w(const void* W, void* Wout, int n_mat, int N, int reference_id, void* stream) {

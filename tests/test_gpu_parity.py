@@ -620,3 +620,85 @@ def test_iss2_seeded_batched_vs_oracle(cls_name, N, J):
     for b in range(B):
         assert relerr(Y[b], ref[b]["Y"]) < tol_seeded("IP2")
         np.testing.assert_allclose(np.asarray(m.loss)[:, b], ref[b]["loss"], rtol=1e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize("name", golden_cases("fdica_"))
+def test_aux_laplace_fdica_matches_reference(name):
+    """AuxLaplaceFDICA (ssspy/bss/fdica.py:1527-1667): iterations, permutation alignment, scale restoration against
+    fixtures of the unmodified reference; the permutation of every bin must equal the oracle's exactly."""
+    from oracle import fdica as ofdica
+    from ssspy_b200.bss import AuxLaplaceFDICA
+    g = load(name)
+    spatial = str(g["spatial"])
+    kwargs = {"demix_filter": g["W0"]} if "W0" in g else {}
+    m = AuxLaplaceFDICA(spatial_algorithm=spatial, flooring_fn=_floor_fn(str(g["flooring"])),
+                        pair_selector=_pair_selector(g["pairs"]) if spatial == "IP2" else None,
+                        permutation_alignment=bool(g["permutation_alignment"]),
+                        scale_restoration=sr_arg(g["scale_restoration"]), record_loss=True,
+                        reference_id=int(g["reference_id"]))
+    Y = m(g["X"], n_iter=int(g["n_iter"]), **kwargs)
+    assert Y.shape == g["Y"].shape and Y.dtype == np.complex128
+    assert type(m.loss[-1]) is float and len(m.loss) == int(g["n_iter"]) + 1
+    assert_loss_close(m.loss, g["loss"])
+    if bool(g["permutation_alignment"]):
+        st = ofdica.run(g["X"], int(g["n_iter"]), W=g.get("W0"), floor=FLOORS[str(g["flooring"])],
+                        spatial_algorithm=spatial, pairs=[tuple(p) for p in g["pairs"]] if spatial == "IP2" else None,
+                        reference_id=int(g["reference_id"]), scale_restoration=sr_arg(g["scale_restoration"]))
+        np.testing.assert_array_equal(m.permutation, st["perms"])
+    if sr_arg(g["scale_restoration"]) or spatial != "IP2":
+        assert relerr(Y, g["Y"]) < TOL_Y
+        W = m.demix_filter
+        assert relerr(phase_align_rows(W, g["W"]) if spatial == "IP2" else W, g["W"]) < 3 * TOL_Y
+    else:
+        assert relerr(np.abs(Y), np.abs(g["Y"])) < TOL_Y
+
+
+@pytest.mark.parametrize("N", [2, 3, 4])
+def test_permutation_solver_matches_reference(N):
+    """correlation_based_permutation_solver (ssspy/algorithm/permutation_alignment.py:12-121): the outputs are
+    rearrangements of the inputs, so they must be bit-identical to the reference's."""
+    import torch
+    from ssspy_b200.algorithm import correlation_based_permutation_solver
+    g = load("permutation_solver")
+    Y, W = g[f"N{N}_Y"], g[f"N{N}_W"]
+    Yo, Wo = correlation_based_permutation_solver(Y, W, overwrite=False)
+    np.testing.assert_array_equal(Yo, g[f"N{N}_Yout"])
+    np.testing.assert_array_equal(Wo, g[f"N{N}_Wout"])
+    assert Yo is not Y and not np.array_equal(Yo, Y)
+    Ya = correlation_based_permutation_solver(Y, flooring_fn=_floor_fn("add"), overwrite=False)
+    np.testing.assert_array_equal(Ya, g[f"N{N}_Yout_add"])
+    # overwrite=True mutates the arguments, as the reference does
+    Y2, W2 = Y.copy(), W.copy()
+    r = correlation_based_permutation_solver(Y2, W2)
+    assert r[0] is Y2 and r[1] is W2
+    np.testing.assert_array_equal(Y2, g[f"N{N}_Yout"])
+    # CUDA tensors in -> CUDA tensors out; batched = per-mixture results
+    Yt = torch.from_numpy(np.stack([Y, Y[::-1].copy()])).cuda()
+    Yb = correlation_based_permutation_solver(Yt, overwrite=False)
+    assert Yb.is_cuda and Yb.shape == Yt.shape
+    np.testing.assert_array_equal(Yb[0].cpu().numpy(), g[f"N{N}_Yout"])
+    with pytest.raises(ValueError, match="1th argument is invalid"):
+        correlation_based_permutation_solver(Y, W[:, :1])
+
+
+@pytest.mark.parametrize("spatial,N,I,J", [("IP", 2, 129, 128), ("IP2", 3, 40, 96), ("IP", 4, 65, 80)])
+def test_aux_laplace_fdica_batched_vs_oracle(spatial, N, I, J):
+    from oracle import fdica as ofdica
+    from ssspy_b200.bss import AuxLaplaceFDICA
+    from ssspy_b200.utils.synth import make_batch
+    B, n_iter = 2, 6
+    X = make_batch(B, N, I, J, config_id=13, mode="mix")
+    m = AuxLaplaceFDICA(spatial_algorithm=spatial)
+    Y = m(X, n_iter=n_iter)
+    assert Y.shape == X.shape and m.permutation.shape == (B, I, N)
+    for b in range(B):
+        st = ofdica.run(X[b], n_iter, spatial_algorithm=spatial)
+        np.testing.assert_array_equal(m.permutation[b], st["perms"])
+        assert relerr(Y[b], st["Y"]) < tol_seeded(spatial)
+        np.testing.assert_allclose(np.asarray(m.loss)[:, b], st["loss"], rtol=1e-3 if spatial == "IP2" else 1e-5, atol=1e-4)
+    # generic contrast callables cannot run on the device
+    from ssspy_b200.bss import AuxFDICA
+    with pytest.raises(NotImplementedError, match="no CPU fallback"):
+        AuxFDICA(contrast_fn=lambda y: 2 * np.abs(y), d_contrast_fn=lambda y: 2 * np.ones_like(y))(X[0], n_iter=1)
+    with pytest.raises(ValueError, match="Specify contrast function"):
+        AuxFDICA()

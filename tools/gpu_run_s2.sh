@@ -1,5 +1,5 @@
 set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -25 > gpurun_out/r1s2_gputests.log
+timeout 1500 python -m pytest tests -m gpu -q -x -k "fdica or permutation" 2>&1 | tail -40 > gpurun_out/r1s2_gputests.log
 cat gpurun_out/r1s2_gputests.log
