@@ -266,7 +266,12 @@ __global__ void __launch_bounds__(CoopShape<N>::NW * 32)
 
   // rows past the last bin (last tile only) work on a clamped copy of row I-1: their accumulator rows are separate
   // and never stored, so the loop needs no masking beyond the P store
-  float* pout[2] = {pin_ptr(Pout + (bn * I + rowc[0]) * (size_t)J + 2 * t), pin_ptr(Pout + (bn * I + rowc[1]) * (size_t)J + 2 * t)};
+  // P is handed to kf_activation_coop in 16 x 16 tiles ([bn][bin tile][frame tile][16 bins][16 frames], 1 KB each):
+  // a warp writes, and later reads, one contiguous kilobyte per step, and the eight warps of an activation CTA read
+  // 8 KB contiguous, instead of sixteen 64-byte pieces 4 J bytes apart (DRAM page locality).  Rows past the last
+  // bin fall into the padding of the last tile.
+  const size_t ptile0 = ((bn * (size_t)((I + 15) >> 4) + (size_t)(i0 >> 4)) * (size_t)(J >> 4)) * 256;
+  float* pout[2] = {pin_ptr(Pout + ptile0 + g * 16 + 2 * t), pin_ptr(Pout + ptile0 + (g + 8) * 16 + 2 * t)};
   uint32_t rd_slot = 0, wr_slot = 2 * (BT * XTB);  // byte offsets of the X stage read / refilled this step
   for (int s = 0; s < nsteps; ++s) {
     cp_async_wait<XST - 2>();
@@ -305,7 +310,7 @@ __global__ void __launch_bounds__(CoopShape<N>::NW * 32)
         float p0, p1;
         power2<N>(x, w[rr], p0, p1);
         // the power spectrogram is kept for the activation update (same W => same P, ilrma.py:1169-1172)
-        if (rvalid[rr]) *reinterpret_cast<float2*>(pout[rr] + 8 * h) = make_float2(p0, p1);
+        *reinterpret_cast<float2*>(pout[rr] + 8 * h) = make_float2(p0, p1);
         const float i0v = fast_rcp(R[h][rr * 2 + 0]);
         const float i1v = fast_rcp(R[h][rr * 2 + 1]);
         const Split sa = split2(p0 * i0v * i0v, p1 * i1v * i1v);
@@ -315,8 +320,8 @@ __global__ void __launch_bounds__(CoopShape<N>::NW * 32)
         Bhi[h * 2 + rr] = sb.hi;
         Blo[h * 2 + rr] = sb.lo;
       }
-    pout[0] += 16;
-    pout[1] += 16;
+    pout[0] += 256;
+    pout[1] += 256;
     // ---- GEMM2: num += A V^T, den += B V^T  (contraction over the 16 frames) ---------------------------
 #pragma unroll
     for (int q = 0; q < 2 * KS; ++q) {
@@ -379,12 +384,13 @@ __device__ __forceinline__ float lds32f(uint32_t addr) {
   return v;
 }
 
-template <int KS>
-__global__ void __launch_bounds__(AW * 32)
+template <int KS, int ACW, int ACP, int MINB>
+__global__ void __launch_bounds__(ACW * 32, MINB)
     kf_activation_coop(const float* __restrict__ P, const __nv_bfloat16* __restrict__ Ts, float* __restrict__ V,
                        __nv_bfloat16* __restrict__ Vs, int NS, int I, int J, int K, int nchunk_i, int nchunk_j,
                        int flooring, float eps) {
   constexpr int KP = 16 * KS, JKS = KP + PADH;
+  constexpr int PST = ACP, TD = ACP / 2, TST = TD + 1, AW = ACW;  // shadow the defaults of the file scope
   constexpr int CHB = 2 * JCV * JKS * 2;  // bytes of one 32-bin T chunk (hi + lo)
   constexpr int PTB = 16 * PRS;           // bytes of one P tile stage
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -397,7 +403,7 @@ __global__ void __launch_bounds__(AW * 32)
   const bool warp_active = j0 < J;
   const size_t bn = (size_t)b * NS + n;
   float* Vb = V + bn * K * J;
-  const float* Pb = P + bn * I * J;
+  const float* Pb = P + bn * (size_t)((I + 15) >> 4) * (size_t)(J >> 4) * 256;  // tiled, see kf_basis_coop
   const int fr[2] = {min(j0 + g, J - 1), min(j0 + g + 8, J - 1)};
   const bool fvalid[2] = {j0 + g < J, j0 + g + 8 < J};
 
@@ -437,10 +443,10 @@ __global__ void __launch_bounds__(AW * 32)
 #pragma unroll
   for (int it = 0; it < 2; ++it) {
     const int idx = it * 32 + lane, r = idx >> 2, part = idx & 3;
-    psrc[it] = Pb + (size_t)r * J + min(j0, J - 16) + part * 4;
+    psrc[it] = Pb + (size_t)(min(j0, J - 16) >> 4) * 256 + r * 16 + part * 4;
     pdst[it] = pin(pw_s + r * PRS + part * 16);
   }
-  const size_t pstep = (size_t)16 * J;
+  const size_t pstep = (size_t)(J >> 4) * 256;  // next bin tile of the same frame tile
   // tiles are requested in step order: the source pointers simply advance
   auto issue_p = [&](uint32_t slot_bytes) {
 #pragma unroll
@@ -587,18 +593,37 @@ int launch_coop(const ssb_config* c, const cf* X, const cf* W, float* T, float* 
     if (ssb_check_launch("coop_vsplit", st)) return 1;
   }
   const size_t sm = (size_t)XST * BT * N * 2048 + (size_t)NW * 2 * CHB;
+  // activation kernel shape: warps of 16 frames per CTA, stages of the P ring, CTAs per SM.  Default 8 / 6 / 2.
+  // SSB_ACT_SHAPE=1 selects 4 warps x 7 CTAs = 28 warps per SM at 72 registers, which makes config 2 (4096 warp
+  // tasks on 148 SMs) a single full wave instead of 1.73 waves of 16 warps: measured 0.106 vs 0.102 ms, i.e. the
+  // kernel is bound by issued instructions, not by the wave shape.
+  static int act_shape = -1;
+  if (act_shape < 0) {
+    const char* e = getenv("SSB_ACT_SHAPE");
+    act_shape = e ? atoi(e) : 0;
+  }
+  constexpr int AW1 = 4, AP1 = 3, AB1 = 7;
   const size_t sm_act = (size_t)TST * CHB + (size_t)AW * PST * 16 * PRS;
+  const size_t sm_act1 = (size_t)(AP1 / 2 + 1) * CHB + (size_t)AW1 * AP1 * 16 * PRS;
   static bool attr_set = false;
   if (!attr_set) {
     SSB_CUDA(cudaFuncSetAttribute(kf_basis_coop<N, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    SSB_CUDA(cudaFuncSetAttribute(kf_activation_coop<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_act));
+    SSB_CUDA(cudaFuncSetAttribute(kf_activation_coop<KS, AW, PST, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_act));
+    SSB_CUDA(cudaFuncSetAttribute(kf_activation_coop<KS, AW1, AP1, AB1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_act1));
     attr_set = true;
   }
   dim3 grid((I + 16 * BT - 1) / (16 * BT), B);
   kf_basis_coop<N, KS><<<grid, NW * 32, sm, st>>>(X, W, T, Vs, P, Ts, I, J, K, nchunk, nchunk_i, c->flooring, c->eps);
   if (ssb_check_launch("coop_basis", st)) return 1;
-  dim3 ga((J + AW * 16 - 1) / (AW * 16), N, B);
-  kf_activation_coop<KS><<<ga, AW * 32, sm_act, st>>>(P, Ts, V, Vs, N, I, J, K, nchunk_i, nchunk, c->flooring, c->eps);
+  if (act_shape == 1 && KS == 1) {  // K > 16 spills at 72 registers
+    dim3 ga((J + AW1 * 16 - 1) / (AW1 * 16), N, B);
+    kf_activation_coop<KS, AW1, AP1, AB1><<<ga, AW1 * 32, sm_act1, st>>>(P, Ts, V, Vs, N, I, J, K, nchunk_i, nchunk,
+                                                                         c->flooring, c->eps);
+  } else {
+    dim3 ga((J + AW * 16 - 1) / (AW * 16), N, B);
+    kf_activation_coop<KS, AW, PST, 2><<<ga, AW * 32, sm_act, st>>>(P, Ts, V, Vs, N, I, J, K, nchunk_i, nchunk,
+                                                                    c->flooring, c->eps);
+  }
   return ssb_check_launch("coop_activation", st);
 }
 

@@ -170,8 +170,9 @@ size_t carve(ssb_plan* p, char* base) {
   const ssb_config& c = p->cfg;
   const size_t B = c.n_batch, N = c.n_sources, I = c.n_bins, J = c.n_frames;
   Carver cv{base};
-  // + 16 rows of slack: the fused activation kernel prefetches whole 16-bin tiles of P without clamping
-  p->big = (p->ilrma() || p->mnmf() || p->fdica()) ? cv.take<float>(B * N * I * J + 16 * J) : nullptr;
+  // bins rounded up to 16 (the cooperative kernels keep P in 16 x 16 tiles) + 16 rows of slack: the per-source
+  // activation kernel prefetches whole 16-bin tiles of P without clamping
+  p->big = (p->ilrma() || p->mnmf() || p->fdica()) ? cv.take<float>(B * N * ((I + 15) / 16 * 16) * J + 16 * J) : nullptr;
   p->big2 = p->mnmf() ? cv.take<float>(B * N * I * J) : nullptr;
   p->qinv = p->mnmf() ? cv.take<cd>(B * I * N * N) : nullptr;
   p->big3 = p->mnmf() ? cv.take<float>(B * N * I * J) : nullptr;
