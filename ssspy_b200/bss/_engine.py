@@ -176,7 +176,7 @@ class DeviceSeparatorMixin:
     # ``chunk_size`` (mixtures per chunk; None = one plan over the whole batch) and ``n_streams`` are
     # plain attributes; ``SSB_CHUNK`` / ``SSB_STREAMS`` override them.
     chunk_size = None
-    n_streams = 3
+    n_streams = 4
 
     def _dims(self):
         B, N, I, J = self._dX.shape
@@ -187,10 +187,14 @@ class DeviceSeparatorMixin:
         cs = os.environ.get("SSB_CHUNK")
         cs = int(cs) if cs else self.chunk_size
         if cs is None and self._cpu_tensor_io and B >= 8:
-            # host tensors in/out: four chunks on three streams hide most of the PCIe copies behind the
-            # iterations of the other chunks (measured +30 % end to end at config 2).  Device-resident
-            # input stays one plan: L2-sized chunks were measured slower, the extra kernel boundaries
-            # cost more than the L2 hits save.
+            # host tensors in/out: eight chunks on four streams hide most of the PCIe copies behind the iterations
+            # of the other chunks (tools/e2e_sweep.py: 22.8 ms vs 26.0 ms for one plan at config 2)
+            cs = -(-B // 8)
+        elif cs is None and B >= 32 and np.prod(self._dims()[1:]) <= (1 << 22):
+            # device-resident input: four chunks on four streams.  Every kernel of the iteration ends in a partially
+            # filled wave (1.7 - 3.7 waves per launch at config 2); the kernels of the other chunks fill those SMs
+            # (measured 0.373 -> 0.345 ms per step).  Smaller, L2-sized chunks were measured slower,
+            # and so is chunking when one mixture alone fills the GPU for many waves (config 4: +3 %).
             cs = -(-B // 4)
         if not cs or cs >= B:
             return [(0, B)]

@@ -883,21 +883,23 @@ int launch_update_ab(int which, const float* A, const float* Bm, float* T, float
 // the frames, as in kf_phi_cov.
 namespace {
 
-template <int N, int G_>
+template <int N, int G_, bool RSW_ = false>
 struct CovCoop {
   static constexpr int G = G_;                 // sources per warp
   static constexpr int EQ = N / 2;             // Hamiltonian paths = warps per source group
-  static constexpr int WPT = (N / G) * EQ;     // warps per tile
+  static constexpr bool RSW = RSW_;            // the two row groups (8 bins each) of a tile go to different warps
+                                               // (one pass over the frames) instead of two passes of the same warp
+  static constexpr int WPT = (N / G) * EQ * (RSW ? 2 : 1);  // warps per tile
   static constexpr int BT = (8 / WPT) > 0 ? 8 / WPT : 1;  // tiles per CTA
   static constexpr int NT = WPT * BT * 32;     // threads per CTA
   static_assert(N == 4 || N == 8, "N = 4, 8 only");
 };
 
-template <int N, int KS, int G_>
-__global__ void __launch_bounds__(CovCoop<N, G_>::NT) kf_cov_coop(const cf* __restrict__ X, const float* __restrict__ T,
-                                                   const __nv_bfloat16* __restrict__ Vs, cf* __restrict__ U, int I,
-                                                   int J, int K, int nchunk) {
-  using S = CovCoop<N, G_>;
+template <int N, int KS, int G_, bool RSW_>
+__global__ void __launch_bounds__(CovCoop<N, G_, RSW_>::NT, RSW_ ? 2 : 0)
+    kf_cov_coop(const cf* __restrict__ X, const float* __restrict__ T, const __nv_bfloat16* __restrict__ Vs,
+                cf* __restrict__ U, int I, int J, int K, int nchunk) {
+  using S = CovCoop<N, G_, RSW_>;
   constexpr int G = S::G, BT = S::BT, EQ = S::EQ;
   constexpr int KP = 16 * KS, JKS = KP + PADH;
   constexpr int CHB = 2 * JCV * JKS * 2;   // bytes of one source's V chunk
@@ -909,7 +911,8 @@ __global__ void __launch_bounds__(CovCoop<N, G_>::NT) kf_cov_coop(const cf* __re
   const uint32_t vs_s = xs_s + XST * XSB;  // V ring: [2][N][CHB]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int bt = warp / S::WPT, p = warp - bt * S::WPT;
+  const int bt = warp / S::WPT, p0 = warp - bt * S::WPT;
+  const int rsw = S::RSW ? (p0 & 1) : 0, p = S::RSW ? (p0 >> 1) : p0;
   const int sg = p / EQ, q = p - sg * EQ;
   const int b = blockIdx.y;
   const int i0 = (blockIdx.x * BT + bt) * 16;
@@ -967,7 +970,8 @@ __global__ void __launch_bounds__(CovCoop<N, G_>::NT) kf_cov_coop(const cf* __re
   const int nsteps = J >> 4;
 
 #pragma unroll 1
-  for (int rs = 0; rs < 2; ++rs) {
+  for (int pass = 0; pass < (S::RSW ? 1 : 2); ++pass) {
+    const int rs = S::RSW ? rsw : pass;
     const int row = i0 + g + 8 * rs;
     // T fragments of the G sources (both row groups feed the MMA; only row group rs is used afterwards)
     uint32_t Thi[G][KS][4], Tlo[G][KS][4];
@@ -1011,7 +1015,7 @@ __global__ void __launch_bounds__(CovCoop<N, G_>::NT) kf_cov_coop(const cf* __re
     const uint32_t xlane[2] = {pin(xs_s + bt * XTB + (g + 8 * rs) * 128 + ((t ^ ((g & 1) << 2)) << 4)),
                                pin(xs_s + bt * XTB + (g + 8 * rs) * 128 + (((4 + t) ^ ((g & 1) << 2)) << 4))};
     // restart the streams
-    if (rs) {
+    if (pass) {
 #pragma unroll
       for (int it = 0; it < XP; ++it) xsrc[it] -= nsteps * 16;
 #pragma unroll
@@ -1101,35 +1105,36 @@ __global__ void __launch_bounds__(CovCoop<N, G_>::NT) kf_cov_coop(const cf* __re
   }
 }
 
-template <int N, int KS, int G_>
+template <int N, int KS, int G_, bool RSW_ = false>
 int launch_cov_coop(const ssb_config* c, const cf* X, const float* T, const __nv_bfloat16* Vs, cf* U, cudaStream_t st) {
-  using S = CovCoop<N, G_>;
+  using S = CovCoop<N, G_, RSW_>;
   const int B = c->n_batch, I = c->n_bins, J = c->n_frames, K = c->n_basis;
   constexpr int KP = 16 * KS, JKS = KP + PADH, CHB = 2 * JCV * JKS * 2;
   const int nchunk = (J + JCV - 1) / JCV;
   const size_t sm = (size_t)XST * S::BT * N * 2048 + (size_t)2 * N * CHB;
   static bool attr_set = false;
   if (!attr_set) {
-    SSB_CUDA(cudaFuncSetAttribute(kf_cov_coop<N, KS, G_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    SSB_CUDA(cudaFuncSetAttribute(kf_cov_coop<N, KS, G_, RSW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     attr_set = true;
   }
   dim3 grid((I + 16 * S::BT - 1) / (16 * S::BT), B);
-  kf_cov_coop<N, KS, G_><<<grid, S::NT, sm, st>>>(X, T, Vs, U, I, J, K, nchunk);
+  kf_cov_coop<N, KS, G_, RSW_><<<grid, S::NT, sm, st>>>(X, T, Vs, U, I, J, K, nchunk);
   return ssb_check_launch("coop_phi_cov", st);
 }
 
 }  // namespace
 
-// N = 8 only by default: at N = 4 kf_phi_cov already shares the products among all four sources and reads X once,
-// and the cooperative kernel's second pass over the row groups misses L2 (measured 0.47 ms vs 0.41 ms,
-// profiles/r1_ncu_coop_summary.md); SSB_COOP_COV=2 forces it for N = 4 as well.
+// N = 8: two passes of each warp over the row groups (registers); N = 4: the row groups go to different warps (four
+// warps per tile, one pass over X, two CTAs per SM): 0.41 -> 0.35 ms against kf_phi_cov.  The two-pass variant was
+// slower than kf_phi_cov at N = 4 (0.47 ms: its second pass misses L2, profiles/r1_ncu_coop_summary.md).
+// SSB_COOP_COV=0 falls back to kf_phi_cov.
 int ssb_coop_cov_supported(const ssb_config* c) {
   static int mode = -1;
   if (mode < 0) {
     const char* e = getenv("SSB_COOP_COV");
     mode = e ? atoi(e) : 1;
   }
-  const bool n_ok = c->n_sources == 8 || (mode == 2 && c->n_sources == 4);
+  const bool n_ok = mode != 0 && (c->n_sources == 8 || c->n_sources == 4);
   return n_ok && (c->n_frames % 16) == 0 && c->n_basis <= 32;
 }
 
@@ -1143,7 +1148,9 @@ int ssb_coop_cov(const ssb_config* c, const cf* X, const float* T, const void* w
     const char* e = getenv("SSB_COV_G");
     g2 = (e && atoi(e) == 2) ? 1 : 0;
   }
-  if (c->n_sources == 4) return k16 ? launch_cov_coop<4, 1, 4>(c, X, T, Vs, U, st) : launch_cov_coop<4, 2, 4>(c, X, T, Vs, U, st);
+  // N = 4: row groups over warps (4 warps per tile, one pass over X, 2 CTAs per SM)
+  if (c->n_sources == 4)
+    return k16 ? launch_cov_coop<4, 1, 4, true>(c, X, T, Vs, U, st) : launch_cov_coop<4, 2, 4, true>(c, X, T, Vs, U, st);
   if (g2) return k16 ? launch_cov_coop<8, 1, 2>(c, X, T, Vs, U, st) : launch_cov_coop<8, 2, 2>(c, X, T, Vs, U, st);
   return k16 ? launch_cov_coop<8, 1, 4>(c, X, T, Vs, U, st) : launch_cov_coop<8, 2, 4>(c, X, T, Vs, U, st);
 }
