@@ -89,6 +89,8 @@ class DeviceSeparatorMixin:
         self._plan_key = None
         self._loss_buf = None
         self._pending_h2d = None   # host tensor whose upload is enqueued per chunk by _ensure_plan
+        self._defer_ok = False     # stock __call__: upload + initial separation run at the head of each chunk's pipeline
+        self._deferred_sep = None  # (W, Y) of the deferred initial separation
         self._host_output = None   # pinned host copy of `output` filled per chunk by __call__
         self._host_out_buf = None
 
@@ -210,7 +212,13 @@ class DeviceSeparatorMixin:
         return [self._streams[ci % ns] for ci in range(len(layout))]
 
     def _initial_separate(self, W, Y):
-        """Y = W X chunk by chunk (after the chunk's pending host->device copy of X, if any)."""
+        """Y = W X chunk by chunk (after the chunk's pending host->device copy of X, if any).  In a stock ``__call__``
+        on a host tensor both are deferred to the head of each chunk's pipeline (``_chunk_init``): enqueued up
+        front, the uploads of all chunks would sit in the streams ahead of every iteration and could not overlap
+        them."""
+        if self._pending_h2d is not None and self._defer_ok:
+            self._deferred_sep = (W, Y)
+            return
         B, N, I, J = self._dims()
         layout = self._chunk_layout()
         streams = self._chunk_streams(layout)
@@ -266,14 +274,19 @@ class DeviceSeparatorMixin:
             if fork is not None:
                 st.wait_event(fork)
             with torch.cuda.stream(st):
-                if self._pending_h2d is not None:
+                deferred = self._deferred_sep is not None
+                if self._pending_h2d is not None and not deferred:
                     self._dX[b0:b1].copy_(self._pending_h2d[b0:b1], non_blocking=True)
                 ws = self._ws_slots[ch["slot"]]
                 ptrs = [0 if t is None else t[b0:b1].data_ptr() for t in tens]
                 _lib.call("ssb_plan_bind", ch["plan"], self._dX[b0:b1].data_ptr(), ptrs[0], ptrs[1], ptrs[2], ptrs[3],
                           ptrs[4], ws.data_ptr(), ws.numel())
-                _lib.call("ssb_plan_prepare", ch["plan"], st.cuda_stream)
-        self._pending_h2d = None
+                if deferred:
+                    ch["init"] = True  # upload, prepare and W X at the head of this chunk's first piece of work
+                else:
+                    _lib.call("ssb_plan_prepare", ch["plan"], st.cuda_stream)
+        if self._deferred_sep is None:
+            self._pending_h2d = None
         self._plan_key = key
 
     def _destroy_plan(self):
@@ -302,6 +315,7 @@ class DeviceSeparatorMixin:
         work when ``fork``)."""
         self._ensure_plan()
         if len(self._chunks) == 1:
+            self._chunk_init(self._chunks[0], torch.cuda.current_stream())
             fn(self._chunks[0], _device.stream_ptr())
             return
         if fork:
@@ -311,7 +325,24 @@ class DeviceSeparatorMixin:
                 st.wait_event(ev)
         for ch in self._chunks:
             with torch.cuda.stream(ch["stream"]):
+                self._chunk_init(ch, ch["stream"])
                 fn(ch, ch["stream"].cuda_stream)
+
+    def _chunk_init(self, ch, st):
+        """Deferred head of a chunk's pipeline: host->device copy of its mixtures, one-time plan work, Y = W X."""
+        if not ch.get("init"):
+            return
+        ch["init"] = False
+        b0, b1 = ch["b0"], ch["b1"]
+        B, N, I, J = self._dims()
+        self._dX[b0:b1].copy_(self._pending_h2d[b0:b1], non_blocking=True)
+        _lib.call("ssb_plan_prepare", ch["plan"], st.cuda_stream)
+        W, Y = self._deferred_sep
+        _lib.call("ssb_separate", self._dX[b0:b1].data_ptr(), W[b0:b1].data_ptr(), Y[b0:b1].data_ptr(), b1 - b0, N, I, J,
+                  st.cuda_stream)
+        if not any(c.get("init") for c in self._chunks):
+            self._pending_h2d = None
+            self._deferred_sep = None
 
     def _plan_call(self, fn, *extra):
         self._for_chunks(lambda ch, sp: _lib.call(fn, ch["plan"], *extra, sp))

@@ -290,7 +290,11 @@ class _DeviceILRMA(ILRMABase):
     def __call__(self, input, n_iter=100, initial_call=True, **kwargs):
         """Separate ``input`` of shape (n_channels, n_bins, n_frames) [or (batch, ...)] (ilrma.py:820-855)."""
         self.input = input
-        self._reset(flooring_fn=self.flooring_fn, **kwargs)
+        self._defer_ok = self._stock_call()
+        try:
+            self._reset(flooring_fn=self.flooring_fn, **kwargs)
+        finally:
+            self._defer_ok = False
         if self._stock_call():
             # base.py:48-77 + scale restoration + output copy as one pipeline per chunk of mixtures
             self._stock_pipeline(n_iter, initial_call, pb=bool(self.scale_restoration))

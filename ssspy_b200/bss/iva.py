@@ -146,7 +146,11 @@ class AuxIVA(AuxIVABase):
         if self._model is None:
             _not_on_device("AuxIVA with user-defined contrast functions (use AuxLaplaceIVA / AuxGaussIVA)")
         self.input = input
-        self._reset(**kwargs)
+        self._defer_ok = self._stock_call()
+        try:
+            self._reset(**kwargs)
+        finally:
+            self._defer_ok = False
         if self._stock_call():
             self._stock_pipeline(n_iter, initial_call, pb=bool(self.scale_restoration))
             return self.output
