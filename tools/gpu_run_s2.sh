@@ -1,5 +1,6 @@
 cd $GRAFT_REPO_ROOT
-timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -3
-python tools/e2e_profile.py 2>&1 | tail -3
-python bench.py --steps 20 --warmup 3 --no-cpu-baseline | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['value'], d['e2e'], d['roofline']['frac'], d['gpu_launches'])"
-python tools/e2e_sweep.py 2>&1 | head -8
+mkdir -p gpurun_out
+timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/r1_bench_v3.json 2> gpurun_out/r1_bench_v3.err
+python -c "
+import json; d=json.load(open('gpurun_out/r1_bench_v3.json')); print(d['ms_per_step'], d['value'], d['roofline']['frac'], d['roofline']['dominant_kernel'], d['roofline']['dominant_kernel_frac'], d['roofline']['traffic'], d['e2e']['value'], d['gpu_launches']); print(d['roofline']['kernels_ms_per_step']); print(d['cpu_baseline'])"
+timeout 300 python bench.py --impl reference --steps 2 --warmup 1 | cut -c1-300
