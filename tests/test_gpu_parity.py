@@ -702,3 +702,35 @@ def test_aux_laplace_fdica_batched_vs_oracle(spatial, N, I, J):
         AuxFDICA(contrast_fn=lambda y: 2 * np.abs(y), d_contrast_fn=lambda y: 2 * np.ones_like(y))(X[0], n_iter=1)
     with pytest.raises(ValueError, match="Specify contrast function"):
         AuxFDICA()
+
+
+def test_chunked_streams_ragged_batch_matches_single_plan():
+    """A device-resident batch of >= 32 mixtures runs as four chunk plans on four streams (ragged chunks here:
+    9 + 9 + 9 + 8); results, loss trajectory and the host-tensor pipeline must equal the single-plan run."""
+    import torch
+    from ssspy_b200.bss import GaussILRMA
+    from ssspy_b200.utils.synth import make_batch, make_nmf_init
+    B, N, I, J, K, n_iter = 35, 2, 40, 64, 5, 4
+    X = make_batch(B, N, I, J, config_id=17, mode="mix")
+    T, V = make_nmf_init(N, I, J, K, seed=3)
+    one = GaussILRMA(n_basis=K)
+    one.chunk_size = B
+    Y1 = one(X, n_iter=n_iter, basis=T, activation=V)
+    many = GaussILRMA(n_basis=K)
+    Y4 = many(X, n_iter=n_iter, basis=T, activation=V)
+    assert len(many._chunks) == 4 and len(one._chunks) == 1
+    np.testing.assert_array_equal(Y4, Y1)  # same kernels on the same data: bit-identical
+    np.testing.assert_array_equal(np.asarray(many.loss), np.asarray(one.loss))
+    np.testing.assert_array_equal(many.basis, one.basis)
+    # pinned host tensor in -> pinned host tensor out through the 8-chunk pipeline with deferred uploads
+    Xt = torch.from_numpy(X.astype(np.complex64)).pin_memory()
+    host = GaussILRMA(n_basis=K)
+    Yt = host(Xt, n_iter=n_iter, basis=T, activation=V)
+    assert isinstance(Yt, torch.Tensor) and not Yt.is_cuda and len(host._chunks) == 7  # ceil(35 / 8) = 5 per chunk
+    assert relerr(Yt.numpy(), Y1) < 1e-5  # chunks of 5 instead of 9 mixtures and a complex64 host tensor: fp32 rounding level
+    # callbacks force the per-iteration path (update_once on every chunk, joined each step)
+    seen = []
+    cb = GaussILRMA(n_basis=K, callbacks=lambda m: seen.append(len(m.loss)))
+    Yc = cb(X, n_iter=n_iter, basis=T, activation=V)
+    assert len(seen) == n_iter + 1
+    np.testing.assert_array_equal(Yc, Y1)
