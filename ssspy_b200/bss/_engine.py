@@ -265,9 +265,13 @@ class DeviceSeparatorMixin:
             nbytes = ctypes.c_size_t(0)
             _lib.call("ssb_plan_workspace_bytes", plan, ctypes.byref(nbytes))
             ws_need = max(ws_need, nbytes.value, 256)
-            self._chunks.append({"b0": b0, "b1": b1, "plan": plan, "slot": ci % ns, "stream": streams[ci]})
-        if len(self._ws_slots) < ns or any(w.numel() < ws_need for w in self._ws_slots[:ns]):
-            self._ws_slots = [_device.empty((ws_need,), torch.uint8) for _ in range(ns)]
+            self._chunks.append({"b0": b0, "b1": b1, "plan": plan, "slot": ci, "stream": streams[ci]})
+        # One workspace per chunk (together they are as large as the workspace of a single plan over the batch).
+        # A workspace holds state that outlives a call (the unweighted covariances of the power normalisation), so
+        # chunks must not share one even when they share a stream.
+        nch = len(self._chunks)
+        if len(self._ws_slots) != nch or any(w.numel() < ws_need for w in self._ws_slots):
+            self._ws_slots = [_device.empty((ws_need,), torch.uint8) for _ in range(nch)]
         for ch in self._chunks:
             b0, b1 = ch["b0"], ch["b1"]
             st = ch["stream"] if ch["stream"] is not None else cur
