@@ -1,14 +1,20 @@
-// Cooperative basis update of the fused GaussILRMA path (source_algorithm="MM", domain=2):
-//   T <- T sqrt( sum_j V P / R^2  /  sum_j V / R ),  P = |w_n^H x|^2,  R = T V      (ssspy/bss/ilrma.py:1051-1128)
+// Cooperative tensor-core kernels of the fused GaussILRMA path (source_algorithm="MM", domain=2) and of FastGaussMNMF.
+//
+//   kf_vsplit            V -> pre-split bf16 (hi, lo) chunks (only when V did not come from kf_activation_coop)
+//   kf_basis_coop        T <- T sqrt( sum_j V P / R^2  /  sum_j V / R ),  P = |w_n^H x|^2,  R = T V
+//                        (ssspy/bss/ilrma.py:1051-1128); also writes P (16 x 16 tiles) and the pre-split T
+//   kf_activation_coop   V <- V sqrt( sum_i T P / R^2  /  sum_i T / R )   (ilrma.py:1130-1204); also the pre-split V
+//   kf_update_ab         the same two updates with the elementwise factors given as arrays (ssspy/bss/mnmf.py:1351-1415)
+//   kf_cov_coop          phi = 1 / (T V), U_n = mean_j phi x x^H for N = 4, 8 (ilrma.py:1494-1505)
 //
 // kf_basis (ssb_fused.cu) gives every (mixture, source) its own CTAs, so a bin's (channel x frame) slab is pulled
 // from L2 once per source: N x the compulsory traffic, and at N = 8 the kernel sits on the L2 -> SM bandwidth
 // (profiles/r1_bench_configs_e.jsonl: 1.96 ms against a 0.33 ms HBM floor).  Here one CTA owns BT tiles of 16 bins
 // for ALL sources: warp (bt, n) updates source n of tile bt, the N warps of a tile share its X slab through a
 // 3-stage cp.async ring in shared memory (each warp fetches "its" channel, a named barrier per tile hands the stage
-// over) and every warp streams its own activation tile.  V is pre-split once per call into bf16 (hi, lo) in the
-// [frame][basis] layout (kf_vsplit); both MMA operand orientations come out of that one layout with
-// ldmatrix / ldmatrix.trans, so the hot loop has 4 LDSM instead of 16 LDS and no split arithmetic for V.
+// over) and every warp streams its own activation tile.  The small operands are pre-split once per update into bf16
+// (hi, lo) in a [frame][basis] / [bin][basis] layout; both MMA operand orientations come out of that one layout with
+// ldmatrix / ldmatrix.trans, so the hot loops have 4 LDSM instead of 16 LDS and no split arithmetic for T / V.
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
