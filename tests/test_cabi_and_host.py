@@ -152,3 +152,39 @@ def test_t_and_ggd_plan_validation():
     cfg.model_param = 1.0
     _lib.call("ssb_plan_create", ctypes.byref(cfg), ctypes.byref(plan))
     _lib.call("ssb_plan_destroy", plan)
+
+
+def test_fdica_constructor_checks_and_plan_validation():
+    from ssspy_b200 import _lib
+    from ssspy_b200.bss import AuxFDICA, AuxLaplaceFDICA
+    with pytest.raises(ValueError, match="Specify contrast function"):
+        AuxFDICA()
+    with pytest.raises(AssertionError, match="Not support"):
+        AuxLaplaceFDICA(spatial_algorithm="ISS")
+    with pytest.raises(ValueError, match="Specify 'reference_id'"):
+        AuxLaplaceFDICA(reference_id=None)
+    m = AuxLaplaceFDICA(spatial_algorithm="IP2")
+    assert repr(m).startswith("AuxLaplaceFDICA(spatial_algorithm=IP2, permutation_alignment=True")
+    assert list(m.pair_selector(3)) == [(0, 1), (1, 2), (2, 0)]
+    cfg = _lib.SsbConfig()
+    cfg.model, cfg.spatial, cfg.n_batch, cfg.n_sources, cfg.n_bins, cfg.n_frames = _lib.MODEL_FDICA_LAPLACE, 2, 1, 2, 4, 4
+    cfg.domain = 2.0
+    plan = ctypes.c_void_p()
+    with pytest.raises(_lib.SsbError, match="Not support spatial algorithm"):
+        _lib.call("ssb_plan_create", ctypes.byref(cfg), ctypes.byref(plan))
+    cfg.spatial = 0
+    _lib.call("ssb_plan_create", ctypes.byref(cfg), ctypes.byref(plan))
+    _lib.call("ssb_plan_destroy", plan)
+
+
+def test_ipa_plan_validation():
+    from ssspy_b200 import _lib
+    cfg = _lib.SsbConfig()
+    cfg.model, cfg.spatial, cfg.n_batch, cfg.n_sources, cfg.n_bins, cfg.n_frames, cfg.n_basis = 4, 4, 1, 2, 4, 4, 2
+    cfg.domain, cfg.model_param = 2.0, 3.0
+    plan = ctypes.c_void_p()
+    with pytest.raises(_lib.SsbError, match="IPA is not supported for t-ILRMA"):
+        _lib.call("ssb_plan_create", ctypes.byref(cfg), ctypes.byref(plan))
+    cfg.model, cfg.ipa_newton_iter = 0, -1
+    with pytest.raises(_lib.SsbError, match="newton_iter"):
+        _lib.call("ssb_plan_create", ctypes.byref(cfg), ctypes.byref(plan))
