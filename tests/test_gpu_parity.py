@@ -392,11 +392,12 @@ def test_full_size_properties_and_one_mixture_oracle(N, spatial):
                                              (2, 257, 512, 16, "IP"), (8, 17, 64, 3, "IP"), (5, 33, 80, 32, "IP"),
                                              (3, 40, 64, 6, "ISS"), (4, 33, 272, 20, "ISS"), (6, 18, 48, 4, "IP2"),
                                              (7, 10, 32, 16, "IP"), (8, 21, 96, 24, "IP"), (8, 9, 48, 32, "IP2"),
-                                             (2, 70, 528, 16, "IP"), (2, 33, 64, 6, "ISS"), (4, 130, 96, 9, "IP")])
+                                             (2, 70, 528, 16, "IP"), (2, 33, 64, 6, "ISS"), (4, 130, 96, 9, "IP"),
+                                             (2, 20, 16, 4, "IP"), (3, 18, 16, 3, "IP"), (8, 16, 32, 16, "IP")])
 def test_fused_tensor_core_path_matches_oracle_and_modular(N, I, J, K, spatial):
     """The fused mma.sync kernels (bf16 hi/lo split, n_frames % 16 == 0, K <= 32) against the fp64 oracle
     and against the modular CUDA-core kernels (fast_path=False); covers ragged bin tiles (I % 16 != 0),
-    K padding (K < 16, 16 < K < 32), odd numbers of 16-frame steps / half-filled 32-frame operand chunks, partially
+    K padding (K < 16, 16 < K < 32), a single 16-frame step (J = 16), odd numbers of steps / half-filled 32-frame operand chunks, partially
     filled cooperative CTAs, the N = 8 cooperative covariance kernel at K <= 16 and K > 16, and the covariance-domain
     ISS1 kernel (N <= 4)."""
     from oracle import ilrma as oilrma
