@@ -1,0 +1,4 @@
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/r1_gputests_final.log 2>&1
+tail -4 gpurun_out/r1_gputests_final.log; grep -n "^E \|^FAILED" gpurun_out/r1_gputests_final.log | head -8
