@@ -736,36 +736,56 @@ __global__ void __launch_bounds__(ISSC_W * 32) k_iss1_cov(cf* __restrict__ Y, co
   const size_t cs = (size_t)I * J;
   const float* ph0 = phi + (size_t)b * sb + (size_t)i * si;
   // ---- sweep 1: weighted covariances ---------------------------------------------------------------------------
-  float acc[NVP];  // per source m: [m*NV + 2e], [m*NV + 2e + 1] = Re, Im of pair e; [m*NV + 2*NO + a] = diagonal a
+  // accumulators as (re, im) pairs [and pairs of diagonal entries], one packed FFMA2 per pair and source
+  constexpr int NDP = (N + 1) / 2;
+  float2 ao[N][NO], ad[N][NDP];
 #pragma unroll
-  for (int e = 0; e < NVP; ++e) acc[e] = 0.f;
+  for (int m = 0; m < N; ++m) {
+#pragma unroll
+    for (int e = 0; e < NO; ++e) ao[m][e] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < NDP; ++k) ad[m][k] = make_float2(0.f, 0.f);
+  }
 #pragma unroll 2
   for (int j = lane; j < J; j += 32) {
     cf y[N];
-    float ph[N];
+    float2 pp[N];
 #pragma unroll
     for (int m = 0; m < N; ++m) {
       y[m] = Y[base + m * cs + j];
-      ph[m] = ph0[(size_t)m * sn + j];
+      const float ph = ph0[(size_t)m * sn + j];
+      pp[m] = make_float2(ph, ph);
     }
     int e = 0;
 #pragma unroll
     for (int a = 0; a < N; ++a)
 #pragma unroll
       for (int c = a + 1; c < N; ++c, ++e) {
-        const float pr = fmaf(y[a].x, y[c].x, y[a].y * y[c].y), pi = fmaf(y[a].y, y[c].x, -(y[a].x * y[c].y));
+        const float2 pr = make_float2(fmaf(y[a].x, y[c].x, y[a].y * y[c].y), fmaf(y[a].y, y[c].x, -(y[a].x * y[c].y)));
 #pragma unroll
-        for (int m = 0; m < N; ++m) {
-          acc[m * NV + 2 * e] = fmaf(ph[m], pr, acc[m * NV + 2 * e]);
-          acc[m * NV + 2 * e + 1] = fmaf(ph[m], pi, acc[m * NV + 2 * e + 1]);
-        }
+        for (int m = 0; m < N; ++m) ao[m][e] = __ffma2_rn(pp[m], pr, ao[m][e]);
       }
 #pragma unroll
-    for (int a = 0; a < N; ++a) {
-      const float pd = fmaf(y[a].x, y[a].x, y[a].y * y[a].y);
+    for (int k = 0; k < NDP; ++k) {
+      const int a = 2 * k, c = (2 * k + 1 < N) ? 2 * k + 1 : 2 * k;
+      const float2 pd = make_float2(fmaf(y[a].x, y[a].x, y[a].y * y[a].y),
+                                    (2 * k + 1 < N) ? fmaf(y[c].x, y[c].x, y[c].y * y[c].y) : 0.f);
 #pragma unroll
-      for (int m = 0; m < N; ++m) acc[m * NV + 2 * NO + a] = fmaf(ph[m], pd, acc[m * NV + 2 * NO + a]);
+      for (int m = 0; m < N; ++m) ad[m][k] = __ffma2_rn(pp[m], pd, ad[m][k]);
     }
+  }
+  float acc[NVP];  // per source m: [m*NV + 2e], [m*NV + 2e + 1] = Re, Im of pair e; [m*NV + 2*NO + a] = diagonal a
+#pragma unroll
+  for (int e = 0; e < NVP; ++e) acc[e] = 0.f;
+#pragma unroll
+  for (int m = 0; m < N; ++m) {
+#pragma unroll
+    for (int e = 0; e < NO; ++e) {
+      acc[m * NV + 2 * e] = ao[m][e].x;
+      acc[m * NV + 2 * e + 1] = ao[m][e].y;
+    }
+#pragma unroll
+    for (int a = 0; a < N; ++a) acc[m * NV + 2 * NO + a] = (a & 1) ? ad[m][a >> 1].y : ad[m][a >> 1].x;
   }
   // reduce-scatter over the lanes: after the step with offset o a lane keeps the half of its values selected by
   // bit o of its id; lane l ends with PER consecutive values of the warp sum
@@ -864,23 +884,31 @@ __global__ void __launch_bounds__(ISSC_W * 32) k_iss1_cov(cf* __restrict__ Y, co
   }
   __syncwarp();
   // ---- sweep 2: y <- A y (slab re-read through L2) -----------------------------------------------------------------
-  cf a_[N * N];
+  // out_p = sum_q a_pq y_q as (re, im) pairs: (y.x, y.x) * (a.x, a.y) + (y.y, y.y) * (-a.y, a.x), two FFMA2 per term
+  float2 a_[N * N], as_[N * N];
 #pragma unroll
-  for (int e = 0; e < N * N; ++e) a_[e] = s_A[w][e];
+  for (int e = 0; e < N * N; ++e) {
+    a_[e] = s_A[w][e];
+    as_[e] = make_float2(-a_[e].y, a_[e].x);
+  }
 #pragma unroll 2
   for (int j = lane; j < J; j += 32) {
-    cf y[N];
+    float2 yx[N], yy[N];
 #pragma unroll
-    for (int m = 0; m < N; ++m) y[m] = Y[base + m * cs + j];
+    for (int m = 0; m < N; ++m) {
+      const cf y = Y[base + m * cs + j];
+      yx[m] = make_float2(y.x, y.x);
+      yy[m] = make_float2(y.y, y.y);
+    }
 #pragma unroll
     for (int p = 0; p < N; ++p) {
-      float orr = 0.f, oi = 0.f;
+      float2 o = make_float2(0.f, 0.f);
 #pragma unroll
       for (int q = 0; q < N; ++q) {
-        orr = fmaf(a_[p * N + q].x, y[q].x, fmaf(-a_[p * N + q].y, y[q].y, orr));
-        oi = fmaf(a_[p * N + q].x, y[q].y, fmaf(a_[p * N + q].y, y[q].x, oi));
+        o = __ffma2_rn(yx[q], a_[p * N + q], o);
+        o = __ffma2_rn(yy[q], as_[p * N + q], o);
       }
-      Y[base + p * cs + j] = make_float2(orr, oi);
+      Y[base + p * cs + j] = o;
     }
   }
 }
