@@ -5,4 +5,5 @@ provides device buffers and streams.  There is no CPU fallback.
 """
 __version__ = "0.1.0"
 
-from . import algorithm, bss, linalg, special, utils  # noqa: F401,E402
+from . import algorithm, bss, io, linalg, special, utils  # noqa: F401,E402
+from .io import wavread, wavwrite  # noqa: F401,E402
