@@ -1112,7 +1112,7 @@ __global__ void __launch_bounds__(256) kf_normalize(const double* __restrict__ q
 
 template <int N, int KS>
 int launch_all(const ssb_config* c, const cf* X, cf* W, float* T, float* V, float* P, cf* U, ssb_fused_ws* vs,
-               cudaStream_t st) {
+               int phases, cudaStream_t st) {
   const int B = c->n_batch, I = c->n_bins, J = c->n_frames, K = c->n_basis;
   constexpr int KP = 16 * KS;
   constexpr bool STG = N <= 4;  // cp.async staging of X in the source-model kernels
@@ -1126,11 +1126,7 @@ int launch_all(const ssb_config* c, const cf* X, cf* W, float* T, float* V, floa
   const size_t ring_cov = (size_t)FW * XSTAGES * 2 * NRC * N * 32 * sizeof(float4);
   const size_t sm_cov = (size_t)(2 * G * CovShape<N>::jcc(KP) * (KP + PADH)) * sizeof(__nv_bfloat16) + (CovShape<N>::STG ? ring_cov : 0);
   // SSB_COOP: 1 (default) cooperative basis kernel (ssb_coop.cu), 0 one CTA per (mixture, source)
-  static int coop = -1;
-  if (coop < 0) {
-    const char* e = getenv("SSB_COOP");
-    coop = e ? atoi(e) : 1;
-  }
+  const int coop = ssb_fused_coop_enabled();
   static bool attr_set = false;
   if (!attr_set) {
     SSB_CUDA(cudaFuncSetAttribute(kf_basis<N, KS, STG, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_basis));
@@ -1138,7 +1134,9 @@ int launch_all(const ssb_config* c, const cf* X, cf* W, float* T, float* V, floa
     SSB_CUDA(cudaFuncSetAttribute(kf_phi_cov<N, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_cov));
     attr_set = true;
   }
-  if (coop && vs != nullptr && W != nullptr) {
+  if (!(phases & 1)) {
+    // covariance only (the source model of this iteration has already run)
+  } else if (coop && vs != nullptr && W != nullptr) {
     if (ssb_coop_source(c, X, W, T, V, P, vs->base, vs->vs_valid ? 1 : 0, st)) return 1;
     vs->vs_valid = true;  // ssb_update_once clears it again unless it runs inside ssb_run
   } else {
@@ -1149,6 +1147,7 @@ int launch_all(const ssb_config* c, const cf* X, cf* W, float* T, float* V, floa
     kf_activation<KS><<<ga, FW * 32, sm_act, st>>>(P, T, V, N, I, J, K, c->flooring, c->eps);
     if (ssb_check_launch("fused_activation", st)) return 1;
   }
+  if (!(phases & 2)) return 0;
   // SSB_COOP_COV: 1 (default) cooperative covariance kernel for N = 4, 8 (needs the Vs left by ssb_coop_source)
   static int coop_cov = -1;
   if (coop_cov < 0) {
@@ -1165,6 +1164,16 @@ int launch_all(const ssb_config* c, const cf* X, cf* W, float* T, float* V, floa
 }  // namespace
 
 // ---- host side ------------------------------------------------------------------------------------
+// SSB_COOP: 1 (default) cooperative source-model kernels (ssb_coop.cu), 0 one CTA per (mixture, source)
+int ssb_fused_coop_enabled() {
+  static int coop = -1;
+  if (coop < 0) {
+    const char* e = getenv("SSB_COOP");
+    coop = e ? atoi(e) : 1;
+  }
+  return coop;
+}
+
 size_t ssb_fused_carve(ssb_fused_ws* ws, const ssb_config* c, char* base) {
   ws->base = base;
   const bool mnmf_ab = c->model == SSB_MODEL_FASTMNMF_GAUSS && c->n_basis <= 32 && (c->n_frames % 16) == 0;
@@ -1184,7 +1193,7 @@ int ssb_fused_prepare(ssb_fused_ws*, const ssb_config*, const cf*, cudaStream_t)
 
 // source model (T then V) + weighted covariance U with the tensor-core kernels
 int ssb_fused_source_and_cov(const ssb_config* c, ssb_fused_ws* ws, const cf* X, cf* W, float* T, float* V,
-                             float* P, cf* U, cudaStream_t st) {
+                             float* P, cf* U, cudaStream_t st, int phases) {
   const int KS = c->n_basis <= 16 ? 1 : 2;
   ssb_fused_ws* vs = (ws && ws->bytes) ? ws : nullptr;
   if (vs && !vs->zeroed) {
@@ -1193,11 +1202,25 @@ int ssb_fused_source_and_cov(const ssb_config* c, ssb_fused_ws* ws, const cf* X,
     vs->vs_valid = false;
   }
   if (KS == 1) {
-    SSB_DISPATCH_N(c->n_sources, return (launch_all<NN, 1>(c, X, W, T, V, P, U, vs, st)));
+    SSB_DISPATCH_N(c->n_sources, return (launch_all<NN, 1>(c, X, W, T, V, P, U, vs, phases, st)));
   } else {
-    SSB_DISPATCH_N(c->n_sources, return (launch_all<NN, 2>(c, X, W, T, V, P, U, vs, st)));
+    SSB_DISPATCH_N(c->n_sources, return (launch_all<NN, 2>(c, X, W, T, V, P, U, vs, phases, st)));
   }
   return 0;
+}
+
+// iterations fused across the update_once boundary inside ssb_run (N = 2, IP1): see kf_cov_ip1_basis
+int ssb_fused_iter_fusable(const ssb_config* c, const ssb_fused_ws* ws) {
+  return ssb_fused_supported(c) && c->n_sources == 2 && c->spatial == SSB_SPATIAL_IP1 && ws != nullptr &&
+         ws->bytes > 0 && ssb_fused_coop_enabled() &&
+         (c->normalization == SSB_NORM_POWER || c->normalization == SSB_NORM_NONE);
+}
+
+int ssb_fused_spatial_source(const ssb_config* c, ssb_fused_ws* ws, const cf* X, cf* W, float* T, float* V, float* P,
+                             double* q, cudaStream_t st) {
+  SSB_REQUIRE(ws != nullptr && ws->bytes > 0 && ws->zeroed && ws->vs_valid,
+              "fused_spatial_source: the source model of the first iteration must have run in this ssb_run");
+  return ssb_coop_spatial_source(c, X, W, T, V, P, ws->base, q, st);
 }
 
 template <int KS>

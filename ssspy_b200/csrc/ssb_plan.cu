@@ -696,9 +696,45 @@ extern "C" int ssb_compute_loss(ssb_plan* p, double* loss, void* stream) {
   return p->ilrma() ? ilrma_loss(p, loss, (cudaStream_t)stream) : iva_loss(p, loss, (cudaStream_t)stream);
 }
 
+namespace {
+// SSB_FUSE_ITER (read at every call so that tests can toggle it): 1 = inside ssb_run, GaussILRMA-IP1 with two sources
+// runs the spatial update of iteration t and the basis update of iteration t + 1 as one kernel (kf_cov_ip1_basis)
+int fuse_iter_enabled() {
+  const char* e = getenv("SSB_FUSE_ITER");
+  return e ? (atoi(e) & 1) : 0;  // bits 1, 2: kernel variants, see launch_coop
+}
+
+// n_iter x update_once (ilrma.py:900-922) regrouped as
+//   [T, V]_1, { [U, IP1]_t + [T]_(t+1), [V]_(t+1), [normalise]_t }_(t = 1 .. n-1), [U, IP1, normalise]_n
+int run_fused_iterations(ssb_plan* p, int n_iter, cudaStream_t st) {
+  const ssb_config& c = p->cfg;
+  const bool pw = c.normalization == SSB_NORM_POWER;
+  SSB_REQUIRE(!pw || p->prepared, "plan not prepared (call ssb_plan_prepare after bind)");
+  TRY(ssb_fused_source_and_cov(&c, &p->fused, p->X, p->W, p->T, p->V, p->big, p->U, st, 1));
+  for (int it = 1; it < n_iter; ++it) {
+    TRY(ssb_fused_spatial_source(&c, &p->fused, p->X, p->W, p->T, p->V, p->big, p->rowloss, st));
+    if (pw)
+      TRY(ssb_fused_normalize(p->rowloss, p->T, p->W, c.n_batch, c.n_sources, c.n_bins, c.n_basis, c.domain, c.flooring,
+                              c.eps, st));
+  }
+  TRY(ssb_fused_source_and_cov(&c, &p->fused, p->X, p->W, p->T, p->V, p->big, p->U, st, 2));
+  TRY(ssb_fused_ip1_n2(p->W, p->U, pw ? p->C : nullptr, p->rowloss, c.n_batch * c.n_bins, c.flooring, c.eps, st));
+  if (pw)
+    TRY(ssb_fused_normalize(p->rowloss, p->T, p->W, c.n_batch, c.n_sources, c.n_bins, c.n_basis, c.domain, c.flooring,
+                            c.eps, st));
+  return 0;
+}
+}  // namespace
+
 extern "C" int ssb_run(ssb_plan* p, int n_iter, double* loss, void* stream) {
   TRY(require_bound(p));
   p->fused.vs_valid = false;
+  if (loss == nullptr && n_iter >= 2 && p->ilrma() && p->cfg.fast_path && !p->iss() &&
+      ssb_fused_iter_fusable(&p->cfg, &p->fused) && fuse_iter_enabled()) {
+    const int rc = run_fused_iterations(p, n_iter, (cudaStream_t)stream);
+    p->fused.vs_valid = false;
+    return rc;
+  }
   for (int it = 0; it < n_iter; ++it) {
     TRY(update_once_impl(p, (cudaStream_t)stream));
     if (loss) TRY(ssb_compute_loss(p, loss + (size_t)it * p->cfg.n_batch, stream));

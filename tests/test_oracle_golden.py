@@ -186,3 +186,33 @@ def test_permutation_solver_oracle(N):
     assert sorted(order.tolist()) == list(range(Y.shape[0])) and perms.shape == (Y.shape[0], N)
     Ya = ofdica.correlation_based_permutation_solver(Y, floor=FLOORS["add"])[0]
     np.testing.assert_array_equal(Ya, g[f"N{N}_Yout_add"])
+
+
+@pytest.mark.parametrize("normalization", [True, False])
+def test_deferred_power_normalisation_commutes_with_the_source_model(normalization):
+    """The identity behind kf_cov_ip1_basis (SSB_FUSE_ITER): n x update_once (ilrma.py:900-922) equals
+    [T, V]_1, { [U, IP1]_t, [T, V]_(t+1) with the UNNORMALISED W_t and T_t, then T /= psi_t^2, W /= psi_t }, [U, IP1,
+    normalise]_n -- the ratio of the basis update and the whole activation update are invariant under
+    (P, T) -> (P, T) / psi^2.  Checked in fp64 with the oracle."""
+    from oracle import ilrma as o
+    from ssspy_b200.utils.synth import make_batch, make_nmf_init
+    N, I, J, K, n_iter = 2, 37, 48, 5, 5
+    X = make_batch(1, N, I, J, config_id=23, mode="mix")[0]
+    T, V = make_nmf_init(N, I, J, K, seed=11)
+    ref = o.run(X, T, V, n_iter, normalization=normalization, record_loss=False, scale_restoration=False)
+    st = o.init_state(X, T, V, None, "IP", None)
+    o.update_basis(st)
+    o.update_activation(st)
+    for _ in range(1, n_iter):
+        o.update_spatial(st)
+        psi = np.maximum(np.sqrt(np.mean(np.abs(o.separate(st["X"], st["W"])) ** 2, axis=(-2, -1))), 1e-10)
+        o.update_basis(st)
+        o.update_activation(st)
+        if normalization:
+            st["T"] = st["T"] / psi[:, None, None] ** 2
+            st["W"] = st["W"] / psi[None, :, None]
+    o.update_spatial(st)
+    if normalization:
+        o.normalize(st)
+    for k in ("T", "V", "W"):
+        assert np.abs(st[k] - ref[k]).max() <= 1e-12 * np.abs(ref[k]).max()
