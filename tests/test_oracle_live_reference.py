@@ -1,0 +1,91 @@
+"""Differential test of the oracle against the UNMODIFIED reference imported live (build container only: skipped when
+/root/reference is absent, e.g. on the GPU box; the committed fixtures of tests/golden/ cover that case).  Random
+shapes and option combinations beyond the fixed golden cases, fp64 on both sides."""
+import functools
+import os
+import sys
+
+import numpy as np
+import pytest
+
+REF = os.environ.get("SSSPY_REF", "/root/reference")
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "ssspy")), reason="reference not available")
+
+TOL = 1e-9
+
+
+def _ref():
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import ssspy.bss.ilrma as rilrma
+    import ssspy.bss.iva as riva
+    from ssspy.special.flooring import add_flooring, max_flooring
+    from ssspy.utils.select_pair import combination_pair_selector, sequential_pair_selector
+    return rilrma, riva, add_flooring, max_flooring, combination_pair_selector, sequential_pair_selector
+
+
+def _relerr(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(np.asarray(b)), 1e-300)
+
+
+def _draw(seed):
+    rng = np.random.default_rng(seed)
+    N = int(rng.integers(2, 5))
+    I, J, K = int(rng.integers(5, 20)), int(rng.integers(24, 60)), int(rng.integers(2, 7))
+    return rng, N, I, J, K
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_gauss_ilrma_random_options_oracle_equals_reference(seed):
+    from oracle import ilrma as oilrma
+    from oracle import spatial as ospatial
+    from ssspy_b200.utils.synth import make_mixture, make_nmf_init
+    rilrma, _, add_flooring, max_flooring, comb, seq = _ref()
+    rng, N, I, J, K = _draw(1000 + seed)
+    spatial = ["IP", "IP2", "ISS", "ISS2", "IPA"][seed % 5]
+    source = "ME" if seed % 4 == 3 else "MM"
+    domain = 2 if (source == "ME" or seed % 3) else 1
+    flooring = "add" if seed % 6 == 5 else "max"
+    normalization = [True, "projection_back", False][seed % 3]
+    use_comb = spatial in ("IP2", "ISS2") and seed % 2 == 0
+    X = make_mixture(N, I, J, seed=500 + seed, mode="mix")
+    T, V = make_nmf_init(N, I, J, K, seed=600 + seed)
+    n_iter = 3
+    ref_floor = functools.partial(add_flooring if flooring == "add" else max_flooring, eps=1e-10)
+    m = rilrma.GaussILRMA(n_basis=K, spatial_algorithm=spatial, source_algorithm=source, domain=domain,
+                          flooring_fn=ref_floor, pair_selector=comb if use_comb else None,
+                          normalization=normalization, scale_restoration=True, record_loss=True, reference_id=0,
+                          rng=np.random.default_rng(0))
+    Y = m(X, n_iter=n_iter, basis=T, activation=V)
+    pairs = list((comb if use_comb else seq)(N))
+    st = oilrma.run(X, T, V, n_iter, p=float(domain),
+                    floor=ospatial.add_flooring if flooring == "add" else ospatial.max_flooring,
+                    spatial_algorithm=spatial, source_algorithm=source, normalization=normalization, pairs=pairs,
+                    reference_id=0, scale_restoration=True)
+    assert _relerr(st["Y"], Y) < TOL
+    assert _relerr(st["T"], m.basis) < TOL
+    assert _relerr(st["V"], m.activation) < TOL
+    np.testing.assert_allclose(st["loss"], m.loss, rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_aux_iva_random_options_oracle_equals_reference(seed):
+    from oracle import iva as oiva
+    from oracle import spatial as ospatial
+    from ssspy_b200.utils.synth import make_mixture
+    _, riva, add_flooring, max_flooring, comb, seq = _ref()
+    rng, N, I, J, _ = _draw(2000 + seed)
+    spatial = ["IP", "IP2", "ISS", "ISS2", "IPA"][seed % 5]
+    model = "gauss" if seed % 2 else "laplace"
+    use_comb = spatial in ("IP2", "ISS2") and seed % 4 < 2
+    X = make_mixture(N, I, J, seed=700 + seed, mode="mix")
+    cls = riva.AuxGaussIVA if model == "gauss" else riva.AuxLaplaceIVA
+    m = cls(spatial_algorithm=spatial, flooring_fn=functools.partial(max_flooring, eps=1e-10),
+            pair_selector=comb if use_comb else None, scale_restoration=True, record_loss=True, reference_id=0)
+    n_iter = 3
+    Y = m(X, n_iter=n_iter)
+    pairs = list((comb if use_comb else seq)(N))
+    st = oiva.run(X, n_iter, floor=ospatial.max_flooring, spatial_algorithm=spatial, model=model, pairs=pairs,
+                  reference_id=0, scale_restoration=True)
+    assert _relerr(st["Y"], Y) < TOL
+    np.testing.assert_allclose(st["loss"], m.loss, rtol=1e-9, atol=1e-9)
