@@ -89,3 +89,85 @@ def test_aux_iva_random_options_oracle_equals_reference(seed):
                   reference_id=0, scale_restoration=True)
     assert _relerr(st["Y"], Y) < TOL
     np.testing.assert_allclose(st["loss"], m.loss, rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_t_ggd_and_partitioned_ilrma_oracle_equals_reference(seed):
+    """TILRMA / GGDILRMA (ilrma.py:1992, :3337) and the partitioning function (latent variable) on random shapes."""
+    from oracle import ilrma as oilrma
+    from oracle import spatial as ospatial
+    from ssspy_b200.utils.synth import make_mixture, make_nmf_init
+    rilrma, _, _, max_flooring, _, seq = _ref()
+    rng, N, I, J, K = _draw(3000 + seed)
+    kind = ["t", "ggd", "gauss"][seed % 3]
+    partitioning = seed % 2 == 1
+    spatial = ["IP", "ISS", "IP2", "ISS2"][seed % 4]
+    prm = float(rng.uniform(2.0, 40.0)) if kind == "t" else float(rng.uniform(0.6, 1.9))
+    X = make_mixture(N, I, J, seed=800 + seed, mode="mix")
+    T, V = make_nmf_init(N, I, J, K, seed=900 + seed)
+    kwargs = dict(basis=T, activation=V)
+    Z0 = None
+    if partitioning:
+        Z0 = rng.random((N, K)) + 0.1
+        Z0 = Z0 / Z0.sum(axis=0)
+        T, V = T[0].copy(), V[0].copy()
+        kwargs = dict(basis=T, activation=V, latent=Z0)
+    common = dict(n_basis=K, spatial_algorithm=spatial, source_algorithm="MM", domain=2,
+                  flooring_fn=functools.partial(max_flooring, eps=1e-10), partitioning=partitioning,
+                  normalization=True, scale_restoration=True, record_loss=True, reference_id=0,
+                  rng=np.random.default_rng(0))
+    if kind == "t":
+        m = rilrma.TILRMA(dof=prm, **common)
+    elif kind == "ggd":
+        m = rilrma.GGDILRMA(beta=prm, **common)
+    else:
+        m = rilrma.GaussILRMA(**common)
+    n_iter = 3
+    Y = m(X, n_iter=n_iter, **kwargs)
+    st = oilrma.run(X, T, V, n_iter, p=2.0, floor=ospatial.max_flooring, spatial_algorithm=spatial,
+                    source_algorithm="MM", normalization=True, pairs=list(seq(N)), reference_id=0,
+                    scale_restoration=True, dist=(kind, prm if kind != "gauss" else None), Z=Z0)
+    assert _relerr(st["Y"], Y) < TOL
+    assert _relerr(st["T"], m.basis) < TOL
+    assert _relerr(st["V"], m.activation) < TOL
+    if partitioning:
+        assert _relerr(st["Z"], m.latent) < TOL
+    np.testing.assert_allclose(st["loss"], m.loss, rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_fdica_and_mnmf_oracle_equals_reference(seed):
+    """AuxLaplaceFDICA with permutation alignment (fdica.py:1527) and FastGaussMNMF with injected state (mnmf.py)."""
+    from oracle import fdica as ofdica
+    from oracle import mnmf as omnmf
+    from oracle import spatial as ospatial
+    from ssspy_b200.utils.synth import make_mixture
+    _, _, _, max_flooring, comb, seq = _ref()
+    from ssspy.bss.fdica import AuxLaplaceFDICA
+    from ssspy.bss.mnmf import FastGaussMNMF
+    rng, N, I, J, K = _draw(4000 + seed)
+    J = J + 60  # few frames make the per-bin problems of FDICA ill-conditioned (see make_golden_fdica.py)
+    alg = "IP2" if seed % 2 else "IP"
+    use_comb = alg == "IP2" and seed % 4 == 1
+    floor = functools.partial(max_flooring, eps=1e-10)
+    pairs = list((comb if use_comb else seq)(N))
+    X = make_mixture(N, I, J, seed=1100 + seed, mode="mix")
+    m = AuxLaplaceFDICA(spatial_algorithm=alg, flooring_fn=floor, pair_selector=comb if use_comb else None,
+                        permutation_alignment=True, scale_restoration=True, record_loss=True, reference_id=0)
+    Y = m(X, n_iter=3)
+    st = ofdica.run(X, 3, floor=ospatial.max_flooring, spatial_algorithm=alg, pairs=pairs, reference_id=0,
+                    permutation_alignment=True, scale_restoration=True)
+    assert _relerr(st["Y"], Y) < 1e-7
+    np.testing.assert_allclose(st["loss"], m.loss, rtol=1e-8, atol=1e-8)
+
+    T, V, D = rng.random((N, I, K)), rng.random((N, K, J)), rng.random((I, N, N))
+    Q = np.eye(N)[None] + 0.3 * (rng.standard_normal((I, N, N)) + 1j * rng.standard_normal((I, N, N)))
+    mm = FastGaussMNMF(n_basis=K, n_sources=N, diagonalizer_algorithm=alg, flooring_fn=floor,
+                       pair_selector=comb if use_comb else None, normalization=True, record_loss=True,
+                       reference_id=0, rng=np.random.default_rng(0))
+    Ym = mm(X, n_iter=3, basis=T, activation=V, spatial=D, diagonalizer=Q)
+    sm = omnmf.run(X, T, V, Q, D, 3, floor=ospatial.max_flooring, algorithm=alg, pairs=pairs, normalization=True,
+                   reference_id=0)
+    assert _relerr(sm["Y"], Ym) < 1e-7
+    assert _relerr(sm["T"], mm.basis) < 1e-8
+    np.testing.assert_allclose(sm["loss"], mm.loss, rtol=1e-8, atol=1e-8)
