@@ -12,7 +12,6 @@ printed by rank 0.
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time

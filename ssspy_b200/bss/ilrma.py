@@ -10,7 +10,6 @@ source_algorithm MM / ME, any ``domain`` in (0, 2], ``partitioning`` False / Tru
 normalization True / "power" / "projection_back" / False, projection-back and minimal-distortion-principle scale
 restoration.  There is no CPU fallback.
 """
-import ctypes
 import functools
 
 import numpy as np

@@ -10,7 +10,7 @@ import functools
 import numpy as np
 import torch
 
-from .. import _device, _lib
+from .. import _lib
 from ..special.flooring import EPS, identity, max_flooring
 from ..utils.flooring import choose_flooring_fn, flooring_to_enum
 from ..utils.select_pair import sequential_pair_selector, wrap_pairs

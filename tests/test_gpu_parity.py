@@ -5,7 +5,6 @@ and SURVEY.md 8(c): Y (after projection back) rel-Frobenius <= 1e-4, T / V rel <
 trajectory rel <= 1e-5 (+ 1e-4 absolute for values near zero), pair lists / shapes exact.
 """
 import functools
-import itertools
 import os
 
 import numpy as np
