@@ -387,12 +387,13 @@ __global__ void __launch_bounds__(CoopShape<N>::NW * 32)
 // updates that follow it: with P -> P / psi^2, T -> T / psi^2 the ratio of the basis update is unchanged and the
 // activation update is invariant, so kf_normalize runs AFTER the activation kernel and rescales the new T (and W).
 // Same tiling, rings and fragment conventions as kf_basis_coop: warp (bt, n) owns source n of tile bt.
-template <int KS>
+template <int KS, bool REV>
 __global__ void __launch_bounds__(CoopShape<2>::NW * 32)
     kf_cov_ip1_basis(const cf* __restrict__ X, cf* Wrw, float* __restrict__ T, const __nv_bfloat16* __restrict__ Vs,
                      float* __restrict__ Pout, __nv_bfloat16* __restrict__ Ts, double* __restrict__ q, int I, int J,
                      int K, int nchunk, int nchunk_i, int flooring, float eps, int l2_hints) {
   constexpr int N = 2;
+  constexpr bool rev = REV;
   constexpr int BT = CoopShape<N>::BT, NW = CoopShape<N>::NW;
   constexpr int KP = 16 * KS, JKS = KP + PADH;
   constexpr int CHB = 2 * JCV * JKS * 2;
@@ -457,12 +458,15 @@ __global__ void __launch_bounds__(CoopShape<2>::NW * 32)
   // second pass: X is read for the last time (and P is only written): keep both from displacing the slabs that other
   // CTAs still have to re-read from L2
   const uint64_t pol = l2_evict_first_policy();
+  // REV: the second pass walks the frames backwards, so that the lines a CTA read last in pass 0 (the ones most
+  // likely to be still in L2) are re-read first; all sums over the frames are order-independent
+  constexpr int xstep = rev ? -16 : 16;
   auto issue_x_last = [&](uint32_t slot_bytes) {
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
       if (l2_hints) cp_async16_hint(xdst[it] + slot_bytes, xsrc[it], pol);
       else cp_async16(xdst[it] + slot_bytes, xsrc[it]);
-      xsrc[it] += 16;
+      xsrc[it] += xstep;
     }
   };
   const unsigned char* vsrc0 = reinterpret_cast<const unsigned char*>(Vs) + bn * (size_t)nchunk * CHB + lane * 16;
@@ -599,23 +603,45 @@ __global__ void __launch_bounds__(CoopShape<2>::NW * 32)
 #pragma unroll
     for (int c = 0; c < 4; ++c) num[qi][c] = den[qi][c] = 0.f;
   float qs[2] = {0.f, 0.f};
+  // V chunk c (frames 32c .. 32c + 31) always lives in buffer c & 1
+  auto issue_v_chunk = [&](int c) {
+    const unsigned char* src = vsrc0 + (size_t)c * CHB;
 #pragma unroll
-  for (int it = 0; it < 4; ++it) xsrc[it] = xsrc0[it];
+    for (int e = 0; e < CHB / 16; e += 32) cp_async16(vdst + (c & 1) * CHB + e * 16, src + e * 16);
+  };
+  const int first = rev ? nsteps - 1 : 0;  // frame step handled first
+#pragma unroll
+  for (int it = 0; it < 4; ++it) xsrc[it] = xsrc0[it] + first * 16;
   vsrc = vsrc0;
-  issue_v(0);
+  if constexpr (rev) {
+    // the last chunk may hold a single step (odd number of steps): its predecessor is then needed one step later
+    // already, so both are requested up front (both buffers are free)
+    issue_v_chunk(first >> 1);
+    if ((first >> 1) >= 1) issue_v_chunk((first >> 1) - 1);
+  } else {
+    issue_v(0);
+  }
   issue_x_last(0);
   cp_async_commit();
   if (nsteps > 1) issue_x_last(BT * XTB);
   cp_async_commit();
-  const size_t ptile0 = ((bn * (size_t)((I + 15) >> 4) + (size_t)(i0 >> 4)) * (size_t)(J >> 4)) * 256;
+  const size_t ptile0 = ((bn * (size_t)((I + 15) >> 4) + (size_t)(i0 >> 4)) * (size_t)(J >> 4) + (size_t)first) * 256;
+  constexpr int pstep = rev ? -256 : 256;
   float* pout[2] = {pin_ptr(Pout + ptile0 + g * 16 + 2 * t), pin_ptr(Pout + ptile0 + (g + 8) * 16 + 2 * t)};
   {
     uint32_t rd_slot = 0, wr_slot = 2 * (BT * XTB);
-    for (int s = 0; s < nsteps; ++s) {
+    for (int r = 0; r < nsteps; ++r) {
+      const int s = rev ? nsteps - 1 - r : r;  // frame step of this iteration
       cp_async_wait<XST - 2>();
       bar_sync_tile<N * 32>(bt);
-      if (s + 2 < nsteps) issue_x_last(wr_slot);
-      if ((s & 1) == 0 && (s >> 1) + 1 < nchunk) issue_v(((s >> 1) + 1) & 1);
+      if (r + 2 < nsteps) issue_x_last(wr_slot);
+      if constexpr (rev) {
+        // entering chunk c = s >> 1 (s odd; the chunk of r = 0 came with its predecessor in the prologue): request
+        // chunk c - 1 into the buffer of chunk c + 1, which is finished; it is first read two steps from now
+        if ((s & 1) && r > 0 && (s >> 1) >= 1) issue_v_chunk((s >> 1) - 1);
+      } else {
+        if ((s & 1) == 0 && (s >> 1) + 1 < nchunk) issue_v(((s >> 1) + 1) & 1);
+      }
       cp_async_commit();
       const uint32_t voff = ((s >> 1) & 1) * CHB + (s & 1) * (16 * JKS * 2);
       const uint32_t vb1 = l1base + voff, vb2 = l2base + voff;
@@ -656,8 +682,8 @@ __global__ void __launch_bounds__(CoopShape<2>::NW * 32)
           Bhi[h * 2 + rr] = sb.hi;
           Blo[h * 2 + rr] = sb.lo;
         }
-      pout[0] += 256;
-      pout[1] += 256;
+      pout[0] += pstep;
+      pout[1] += pstep;
 #pragma unroll
       for (int qi = 0; qi < 2 * KS; ++qi) {
         uint32_t vh0, vh1, vl0, vl1;
@@ -949,8 +975,10 @@ int launch_coop(const ssb_config* c, const cf* X, const cf* W, float* T, float* 
   static bool attr_set = false;
   if (!attr_set) {
     SSB_CUDA(cudaFuncSetAttribute(kf_basis_coop<N, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    if (N == 2)
-      SSB_CUDA(cudaFuncSetAttribute(kf_cov_ip1_basis<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+    if (N == 2) {
+      SSB_CUDA(cudaFuncSetAttribute(kf_cov_ip1_basis<KS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+      SSB_CUDA(cudaFuncSetAttribute(kf_cov_ip1_basis<KS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+    }
     SSB_CUDA(cudaFuncSetAttribute(kf_activation_coop<KS, AW, PST, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_act));
     SSB_CUDA(cudaFuncSetAttribute(kf_activation_coop<KS, AW1, AP1, AB1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_act1));
     attr_set = true;
@@ -963,12 +991,16 @@ int launch_coop(const ssb_config* c, const cf* X, const cf* W, float* T, float* 
       return 1;
     }
     // SSB_FUSE_ITER bits (ssb_plan.cu enables the path on bit 0): 2 = one CTA per SM (shared memory padded to 120 KB:
-    // half the slabs waiting in L2 for their second pass), 4 = no L2 eviction hints
+    // half the slabs waiting in L2 for their second pass), 4 = no L2 eviction hints, 8 = second pass backwards
     const char* e = getenv("SSB_FUSE_ITER");
     const int mode = e ? atoi(e) : 1;
     const size_t smf = (mode & 2) ? (sm + 1024 > (size_t)120 * 1024 ? sm + 1024 : (size_t)120 * 1024) : sm + 1024;
-    kf_cov_ip1_basis<KS><<<grid, NW * 32, smf, st>>>(X, Wrw, T, Vs, P, Ts, q, I, J, K, nchunk, nchunk_i, c->flooring,
-                                                    c->eps, (mode & 4) ? 0 : 1);
+    if (mode & 8)
+      kf_cov_ip1_basis<KS, true><<<grid, NW * 32, smf, st>>>(X, Wrw, T, Vs, P, Ts, q, I, J, K, nchunk, nchunk_i,
+                                                            c->flooring, c->eps, (mode & 4) ? 0 : 1);
+    else
+      kf_cov_ip1_basis<KS, false><<<grid, NW * 32, smf, st>>>(X, Wrw, T, Vs, P, Ts, q, I, J, K, nchunk, nchunk_i,
+                                                             c->flooring, c->eps, (mode & 4) ? 0 : 1);
     if (ssb_check_launch("coop_cov_ip1_basis", st)) return 1;
   } else {
     kf_basis_coop<N, KS><<<grid, NW * 32, sm, st>>>(X, W, T, Vs, P, Ts, I, J, K, nchunk, nchunk_i, c->flooring, c->eps);

@@ -745,11 +745,18 @@ _MORE_FUSE_ITER = pytest.mark.skipif(not os.environ.get("SSB_TEST_EXPERIMENTAL")
                                             "path that have not been through a B200 run yet")
 
 
-@pytest.mark.parametrize("I,J,K,n_iter,normalization", [
-    (37, 48, 5, 5, True), (257, 512, 16, 4, True),
-    pytest.param(70, 528, 16, 3, False, marks=_MORE_FUSE_ITER), pytest.param(20, 16, 4, 2, True, marks=_MORE_FUSE_ITER),
-    pytest.param(33, 64, 24, 5, True, marks=_MORE_FUSE_ITER), pytest.param(129, 160, 32, 6, False, marks=_MORE_FUSE_ITER)])
-def test_fused_iteration_kernel_matches_unfused_and_oracle(I, J, K, n_iter, normalization, monkeypatch):
+@pytest.mark.parametrize("I,J,K,n_iter,normalization,mode", [
+    (37, 48, 5, 5, True, "1"), (257, 512, 16, 4, True, "1"),
+    pytest.param(70, 528, 16, 3, False, "1", marks=_MORE_FUSE_ITER),
+    pytest.param(20, 16, 4, 2, True, "1", marks=_MORE_FUSE_ITER),
+    pytest.param(33, 64, 24, 5, True, "1", marks=_MORE_FUSE_ITER),
+    pytest.param(129, 160, 32, 6, False, "1", marks=_MORE_FUSE_ITER),
+    # mode 9: second pass backwards (odd and even numbers of 16-frame steps, a single step, K > 16)
+    pytest.param(37, 48, 5, 5, True, "9", marks=_MORE_FUSE_ITER),
+    pytest.param(257, 512, 16, 4, True, "9", marks=_MORE_FUSE_ITER),
+    pytest.param(20, 16, 4, 2, True, "9", marks=_MORE_FUSE_ITER),
+    pytest.param(33, 80, 24, 3, True, "9", marks=_MORE_FUSE_ITER)])
+def test_fused_iteration_kernel_matches_unfused_and_oracle(I, J, K, n_iter, normalization, mode, monkeypatch):
     """SSB_FUSE_ITER=1 (experimental, default off): inside ssb_run the covariance + IP1 of iteration t and the basis
     update of iteration t + 1 run as one kernel (kf_cov_ip1_basis, N = 2), with the power normalisation of iteration t
     applied after the activation update.  Same results as update_once x n_iter (up to fp32 rounding: the covariance
@@ -764,7 +771,7 @@ def test_fused_iteration_kernel_matches_unfused_and_oracle(I, J, K, n_iter, norm
     T, V = make_nmf_init(N, I, J, K, seed=11)
     out = {}
     for flag in ("0", "1"):
-        monkeypatch.setenv("SSB_FUSE_ITER", flag)
+        monkeypatch.setenv("SSB_FUSE_ITER", mode if flag == "1" else "0")
         m = GaussILRMA(n_basis=K, spatial_algorithm="IP", normalization=normalization, record_loss=False)
         out[flag] = (m(X, n_iter=n_iter, basis=T, activation=V), m.basis.copy(), m.activation.copy(),
                      m.demix_filter.copy())

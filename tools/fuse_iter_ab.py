@@ -16,7 +16,7 @@ def main():
     steps = int(os.environ.get("STEPS", "20"))
     X = torch.from_numpy(make_batch(B, N, I, J, config_id=2, mode="mix").astype(np.complex64)).cuda()
     T0, V0 = make_nmf_init(N, I, J, K, seed=0)
-    for mode in sys.argv[1:] or ["0", "1", "3", "5", "7", "0"]:
+    for mode in sys.argv[1:] or ["0", "1", "9", "3", "5", "0"]:
         os.environ["SSB_FUSE_ITER"] = mode
         sep = GaussILRMA(n_basis=K, spatial_algorithm="IP", record_loss=False)
         sep(X, n_iter=0, basis=T0, activation=V0)

@@ -13,3 +13,5 @@ tail -2 gpurun_out/r2_fuse_iter_ncu.log
 SSB_TEST_EXPERIMENTAL=1 timeout 600 compute-sanitizer --tool racecheck --error-exitcode 3 python -m pytest tests/test_gpu_parity.py -q -x \
   -k "fused_iteration and (37-48 or 20-16 or 33-64)" > gpurun_out/r2_fuse_iter_racecheck.log 2>&1
 tail -4 gpurun_out/r2_fuse_iter_racecheck.log
+timeout 200 python tools/fuse_iter_ab.py > gpurun_out/r2_fuse_iter_ab.jsonl 2>&1
+cat gpurun_out/r2_fuse_iter_ab.jsonl
