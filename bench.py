@@ -157,8 +157,7 @@ def main():
             return
         workers = os.cpu_count() or 1
         n_it = max(1, min(steps, 4))
-        for _ in range(max(0, min(args.warmup, 1))):
-            pass  # each worker does its own warm-up iteration
+        # (each worker does its own untimed warm-up iteration, see _cpu_worker)
         rate, cores, sample = cpu_arm(wl, n_it, workers)
         line = {"impl": "reference", "metric": "mixture_iterations_per_sec", "value": rate, "unit": "mixture-iterations/s",
                 "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * B * args.gpus / rate,
