@@ -188,3 +188,25 @@ def test_ipa_plan_validation():
     cfg.model, cfg.ipa_newton_iter = 0, -1
     with pytest.raises(_lib.SsbError, match="newton_iter"):
         _lib.call("ssb_plan_create", ctypes.byref(cfg), ctypes.byref(plan))
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (CPU arm, the oracle port on the host cores): one JSON line with the keys of the
+    bench contract; ranks other than 0 exit 0 without output."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+           "--batch", "4", "--frames", "64"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    other = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root, env=env)
+    assert other.returncode == 0 and other.stdout.strip() == ""
