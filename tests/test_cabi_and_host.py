@@ -210,3 +210,28 @@ def test_bench_reference_arm_contract():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     other = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root, env=env)
     assert other.returncode == 0 and other.stdout.strip() == ""
+
+
+def test_chunk_layout_rules(monkeypatch):
+    """Engine chunk plans (ssspy_b200/bss/_engine.py): one plan by default; four chunks for a device-resident batch of
+    >= 32 small mixtures; eight for host tensors; explicit chunk_size / SSB_CHUNK win; chunks cover the batch exactly."""
+    import types
+    from ssspy_b200.bss import _engine
+    cls = next(v for v in vars(_engine).values() if isinstance(v, type) and hasattr(v, "_chunk_layout"))
+
+    def layout(B, dims=(2, 1025, 512), cpu=False, chunk_size=None):
+        fake = types.SimpleNamespace(_dims=lambda: (B,) + dims, _cpu_tensor_io=cpu, chunk_size=chunk_size)
+        return cls._chunk_layout(fake)
+
+    monkeypatch.delenv("SSB_CHUNK", raising=False)
+    assert layout(1) == [(0, 1)] and layout(31) == [(0, 31)]
+    assert layout(64) == [(0, 16), (16, 32), (32, 48), (48, 64)]
+    assert layout(35) == [(0, 9), (9, 18), (18, 27), (27, 35)]
+    assert layout(64, dims=(8, 2049, 1024)) == [(0, 64)]            # one mixture already fills the GPU for many waves
+    assert len(layout(64, cpu=True)) == 8 and len(layout(35, cpu=True)) == 7 and layout(7, cpu=True) == [(0, 7)]
+    assert layout(10, chunk_size=4) == [(0, 4), (4, 8), (8, 10)] and layout(10, chunk_size=10) == [(0, 10)]
+    monkeypatch.setenv("SSB_CHUNK", "3")
+    got = layout(8, chunk_size=100)
+    assert got == [(0, 3), (3, 6), (6, 8)]
+    for lay in (got, layout(64), layout(35, cpu=True)):
+        assert lay[0][0] == 0 and all(a[1] == b[0] for a, b in zip(lay, lay[1:]))
