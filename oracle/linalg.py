@@ -127,7 +127,14 @@ def solve_equation(phi, v, z, floor, max_iter=10):
 def lqpqm2(H, v, z, floor, max_iter=10):
     """argmax-side stationary point of the log-quadratically penalised quadratic minimisation, type 2
     (ssspy/linalg/lqpqm.py:13-119), singular_fn = (x < floor(0)) as update_by_ipa calls it
-    (_update_spatial_model.py:484-490).  H (*, M, M) Hermitian PSD, v (*, M), z (*,)."""
+    (_update_spatial_model.py:484-490).  H (*, M, M) Hermitian PSD, v (*, M), z (*,).
+
+    Known deviation (v = 0 branch only, lqpqm.py:78-89): the reference scales ``sigma_singular[:, -1]``, which is the
+    last ROW of the eigenvector matrix -- one entry of every eigenvector, each with LAPACK's arbitrary phase -- where
+    the derivation needs the eigenvector of the largest eigenvalue (last COLUMN).  No independent eigensolver can
+    reproduce that row, so the oracle and the CUDA kernel (ssb_ipa.cu) return scale * (last column); the two agree
+    with the reference in the last component and in the norm only.  The branch needs ||v|| < 1e-10, i.e. a source
+    exactly uncorrelated with all others, and is not reached by the fixtures."""
     phi, sigma = np.linalg.eigh(H)
     sing = np.linalg.norm(v, axis=-1) < floor(0)
     y = np.zeros_like(v)

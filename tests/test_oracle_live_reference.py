@@ -171,3 +171,30 @@ def test_fdica_and_mnmf_oracle_equals_reference(seed):
     assert _relerr(sm["Y"], Ym) < 1e-7
     assert _relerr(sm["T"], mm.basis) < 1e-8
     np.testing.assert_allclose(sm["loss"], mm.loss, rtol=1e-8, atol=1e-8)
+
+
+def test_lqpqm2_singular_branch_is_documented():
+    """lqpqm2 (lqpqm.py:13-119): the regular branch equals the reference; in the v = 0 branch the reference returns
+    scale * (last ROW of the eigenvector matrix, LAPACK phases), the oracle scale * (eigenvector of the largest
+    eigenvalue).  Pin what is common to both -- the last component and the norm -- and that the oracle's result is
+    an eigenvector (known deviation)."""
+    _ref()
+    from ssspy.linalg import lqpqm2 as ref_lqpqm2
+    from oracle import spatial as ospatial
+    from oracle.linalg import lqpqm2
+    rng = np.random.default_rng(5)
+    n, M = 6, 3
+    A = rng.standard_normal((n, M, M)) + 1j * rng.standard_normal((n, M, M))
+    H = A @ A.conj().transpose(0, 2, 1)
+    v = rng.standard_normal((n, M)) + 1j * rng.standard_normal((n, M))
+    v[:3] = 0
+    z = rng.random(n) * 0.1
+    yr = ref_lqpqm2(H, v.copy(), z)
+    yo = lqpqm2(H, v.copy(), z, ospatial.max_flooring)
+    assert _relerr(yo[3:], yr[3:]) < 1e-10
+    np.testing.assert_allclose(yo[:3, -1], yr[:3, -1], rtol=1e-10)
+    np.testing.assert_allclose(np.linalg.norm(yo[:3], axis=-1), np.linalg.norm(yr[:3], axis=-1), rtol=1e-10)
+    lam = np.linalg.eigvalsh(H[:3])[:, -1]
+    Hy = np.einsum("bij,bj->bi", H[:3], yo[:3])
+    assert _relerr(Hy, lam[:, None] * yo[:3]) < 1e-10
+    assert np.abs(yo[:3] - yr[:3]).max() > 1e-3  # the deviation is real
