@@ -198,3 +198,49 @@ def test_lqpqm2_singular_branch_is_documented():
     Hy = np.einsum("bij,bj->bi", H[:3], yo[:3])
     assert _relerr(Hy, lam[:, None] * yo[:3]) < 1e-10
     assert np.abs(yo[:3] - yr[:3]).max() > 1e-3  # the deviation is real
+
+
+@pytest.mark.parametrize("case", ["zero_frames", "silent_channel", "tiny", "huge", "dup_channel", "zero_bin"])
+@pytest.mark.parametrize("spatial", ["IP", "IP2", "ISS", "ISS2", "IPA"])
+def test_degenerate_inputs_same_outcome_as_reference(case, spatial):
+    """Degenerate inputs: the oracle must end like the reference -- the same exception type (LinAlgError for an
+    exactly singular per-bin matrix), or the same finite result."""
+    import warnings
+    from oracle import ilrma as oilrma
+    from oracle import spatial as ospatial
+    from ssspy_b200.utils.synth import make_mixture, make_nmf_init
+    rilrma, _, _, max_flooring, _, seq = _ref()
+    N, I, J, K = 3, 9, 40, 4
+    X = make_mixture(N, I, J, seed=1, mode="mix")
+    T, V = make_nmf_init(N, I, J, K, seed=2)
+    if case == "zero_frames":
+        X[:, :, :5] = 0
+    elif case == "silent_channel":
+        X[1] = 0
+    elif case == "tiny":
+        X = X * 1e-7
+    elif case == "huge":
+        X = X * 1e6
+    elif case == "dup_channel":
+        X[2] = X[0]
+    elif case == "zero_bin":
+        X[:, 3, :] = 0
+
+    def outcome(fn):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            try:
+                return None, fn()
+            except Exception as e:  # noqa: BLE001 - the exception type is what is compared
+                return type(e).__name__, None
+
+    m = rilrma.GaussILRMA(n_basis=K, spatial_algorithm=spatial, flooring_fn=functools.partial(max_flooring, eps=1e-10),
+                          record_loss=True, reference_id=0, rng=np.random.default_rng(0))
+    err_r, Y = outcome(lambda: m(X, n_iter=3, basis=T, activation=V))
+    err_o, st = outcome(lambda: oilrma.run(X, T, V, 3, floor=ospatial.max_flooring, spatial_algorithm=spatial,
+                                            pairs=list(seq(N)), reference_id=0))
+    assert err_r == err_o
+    if err_r is None:
+        assert _relerr(st["Y"], Y) < 1e-9 and _relerr(st["T"], m.basis) < 1e-9
+    else:
+        assert err_r == "LinAlgError"
