@@ -9,7 +9,7 @@ import numpy as np
 
 from . import spatial
 from .ilrma import separate
-from .projection_back import projection_back
+from .projection_back import minimal_distortion_principle, projection_back
 
 
 def init_state(X, W=None, spatial_algorithm="IP", model="laplace"):
@@ -93,7 +93,18 @@ def compute_loss(st, model="laplace"):
     return float(np.sum(np.mean(G, axis=1), axis=0) - 2 * np.sum(logdet, axis=0))
 
 
-def restore_scale(st, reference_id=0):
+def restore_scale(st, reference_id=0, method=True):
+    """Projection back (ssspy/bss/iva.py:259-267, :2196-2204) or, for ``method="minimal_distortion_principle"``, the
+    minimal distortion principle (:269-281, :2206-2214)."""
+    if isinstance(method, str) and method in ("minimal_distortion_principle", "minimal-distortion-principle", "MDP"):
+        X = st["X"]
+        Y = st["Y"] if st["W"] is None else separate(X, st["W"])
+        st["Y"] = minimal_distortion_principle(Y, X, reference_id)
+        if st["W"] is not None:
+            Xi, Yi = X.transpose(1, 0, 2), st["Y"].transpose(1, 0, 2)
+            XH = np.conj(Xi.transpose(0, 2, 1))
+            st["W"] = Yi @ XH @ np.linalg.inv(Xi @ XH)
+        return
     if st["W"] is None:
         st["Y"] = projection_back(st["Y"], reference=st["X"], reference_id=reference_id)
     else:
@@ -115,7 +126,7 @@ def run(X, n_iter, W=None, floor=spatial.max_flooring, spatial_algorithm="IP", m
         if snapshots:
             snaps.append({k: (None if v is None else v.copy()) for k, v in st.items() if k != "X"})
     if scale_restoration:
-        restore_scale(st, reference_id)
+        restore_scale(st, reference_id, scale_restoration)
     elif st["W"] is not None:
         st["Y"] = separate(st["X"], st["W"])
     st["loss"] = loss

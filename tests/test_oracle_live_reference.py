@@ -80,13 +80,15 @@ def test_aux_iva_random_options_oracle_equals_reference(seed):
     use_comb = spatial in ("IP2", "ISS2") and seed % 4 < 2
     X = make_mixture(N, I, J, seed=700 + seed, mode="mix")
     cls = riva.AuxGaussIVA if model == "gauss" else riva.AuxLaplaceIVA
+    sr = [True, "minimal_distortion_principle", False][seed % 3]
+    ref_id = seed % N
     m = cls(spatial_algorithm=spatial, flooring_fn=functools.partial(max_flooring, eps=1e-10),
-            pair_selector=comb if use_comb else None, scale_restoration=True, record_loss=True, reference_id=0)
+            pair_selector=comb if use_comb else None, scale_restoration=sr, record_loss=True, reference_id=ref_id)
     n_iter = 3
     Y = m(X, n_iter=n_iter)
     pairs = list((comb if use_comb else seq)(N))
     st = oiva.run(X, n_iter, floor=ospatial.max_flooring, spatial_algorithm=spatial, model=model, pairs=pairs,
-                  reference_id=0, scale_restoration=True)
+                  reference_id=ref_id, scale_restoration=sr)
     assert _relerr(st["Y"], Y) < TOL
     np.testing.assert_allclose(st["loss"], m.loss, rtol=1e-9, atol=1e-9)
 
