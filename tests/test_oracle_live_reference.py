@@ -246,3 +246,51 @@ def test_degenerate_inputs_same_outcome_as_reference(case, spatial):
         assert _relerr(st["Y"], Y) < 1e-9 and _relerr(st["T"], m.basis) < 1e-9
     else:
         assert err_r == "LinAlgError"
+
+
+def test_constructor_validation_mirrors_reference():
+    """Every combination of constructor options (valid, invalid and misspelt) ends the same way in the host classes
+    of ssspy_b200.bss and in the reference's: no error, or the same exception type with the same message."""
+    import itertools
+    import warnings
+    _ref()
+    import ssspy.bss.fdica as rfd
+    import ssspy.bss.ilrma as rilrma
+    import ssspy.bss.iva as riva
+    import ssspy.bss.mnmf as rmn
+    from ssspy_b200.bss import fdica as mfd
+    from ssspy_b200.bss import ilrma as milrma
+    from ssspy_b200.bss import iva as miva
+    from ssspy_b200.bss import mnmf as mmn
+
+    def outcome(fn):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            try:
+                fn()
+                return None
+            except Exception as e:  # noqa: BLE001
+                return type(e).__name__ + ": " + str(e)
+
+    spatial = ["IP", "IP1", "IP2", "ISS", "ISS1", "ISS2", "IPA", "XX"]
+    restoration = [True, False, "projection_back", "minimal_distortion_principle", "MDP", "bogus"]
+    grid = dict(spatial_algorithm=spatial, source_algorithm=["MM", "ME", "ZZ"], domain=[1, 1.5, 2],
+                partitioning=[False, True], normalization=[True, False, "power", "projection_back", "bogus"],
+                scale_restoration=restoration)
+    n = 0
+    for vals in itertools.product(*grid.values()):
+        kw = dict(zip(grid, vals))
+        for name, extra in (("GaussILRMA", {}), ("TILRMA", {"dof": 5.0}), ("GGDILRMA", {"beta": 1.3})):
+            want = outcome(lambda: getattr(rilrma, name)(n_basis=3, **extra, **kw))
+            got = outcome(lambda: getattr(milrma, name)(n_basis=3, **extra, **kw))
+            assert got == want, (name, kw)
+            n += 1
+    for sa, sr in itertools.product(spatial, restoration):
+        for name in ("AuxLaplaceIVA", "AuxGaussIVA"):
+            assert outcome(lambda: getattr(miva, name)(spatial_algorithm=sa, scale_restoration=sr)) == \
+                outcome(lambda: getattr(riva, name)(spatial_algorithm=sa, scale_restoration=sr)), (name, sa, sr)
+        assert outcome(lambda: mfd.AuxLaplaceFDICA(spatial_algorithm=sa, scale_restoration=sr)) == \
+            outcome(lambda: rfd.AuxLaplaceFDICA(spatial_algorithm=sa, scale_restoration=sr)), (sa, sr)
+        assert outcome(lambda: mmn.FastGaussMNMF(n_basis=3, diagonalizer_algorithm=sa)) == \
+            outcome(lambda: rmn.FastGaussMNMF(n_basis=3, diagonalizer_algorithm=sa)), sa
+    assert n == 12960
