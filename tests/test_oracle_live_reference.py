@@ -294,3 +294,26 @@ def test_constructor_validation_mirrors_reference():
         assert outcome(lambda: mmn.FastGaussMNMF(n_basis=3, diagonalizer_algorithm=sa)) == \
             outcome(lambda: rmn.FastGaussMNMF(n_basis=3, diagonalizer_algorithm=sa)), sa
     assert n == 12960
+
+
+def test_repr_mirrors_reference():
+    _ref()
+    import ssspy.bss.fdica as rfd
+    import ssspy.bss.ilrma as rilrma
+    import ssspy.bss.iva as riva
+    import ssspy.bss.mnmf as rmn
+    from ssspy_b200.bss import fdica as mfd
+    from ssspy_b200.bss import ilrma as milrma
+    from ssspy_b200.bss import iva as miva
+    from ssspy_b200.bss import mnmf as mmn
+    cases = [("GaussILRMA", rilrma, milrma, dict(n_basis=4)),
+             ("GaussILRMA", rilrma, milrma, dict(n_basis=4, spatial_algorithm="ISS2", partitioning=True)),
+             ("GaussILRMA", rilrma, milrma, dict(n_basis=2, spatial_algorithm="IPA", normalization=False,
+                                                  scale_restoration="MDP", record_loss=False, reference_id=1)),
+             ("TILRMA", rilrma, milrma, dict(n_basis=4, dof=100)), ("GGDILRMA", rilrma, milrma, dict(n_basis=4, beta=1.5)),
+             ("AuxLaplaceIVA", riva, miva, {}), ("AuxGaussIVA", riva, miva, dict(spatial_algorithm="IPA")),
+             ("AuxIVA", riva, miva, dict(contrast_fn=None, d_contrast_fn=None)),
+             ("AuxLaplaceFDICA", rfd, mfd, {}), ("AuxLaplaceFDICA", rfd, mfd, dict(spatial_algorithm="IP2")),
+             ("FastGaussMNMF", rmn, mmn, dict(n_basis=3)), ("FastGaussMNMF", rmn, mmn, dict(n_basis=3, n_sources=2))]
+    for name, ref_mod, new_mod, kw in cases:
+        assert repr(getattr(new_mod, name)(**kw)) == repr(getattr(ref_mod, name)(**kw)), (name, kw)
