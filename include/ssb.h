@@ -59,6 +59,8 @@ enum { SSB_SPATIAL_IP1 = 0, SSB_SPATIAL_IP2 = 1, SSB_SPATIAL_ISS1 = 2,
                               ISS; uses `ipa_normalization` / `ipa_newton_iter` (GaussILRMA and AuxIVA only) */ };
 /* source_algorithm (ssspy/bss/ilrma.py:28) */
 enum { SSB_SOURCE_MM = 0, SSB_SOURCE_ME = 1 };
+/* sub-steps of the ILRMA source model for ssb_update_source_part */
+enum { SSB_PART_LATENT = 0, SSB_PART_BASIS = 1, SSB_PART_ACTIVATION = 2 };
 /* flooring_fn (ssspy/special/flooring.py:6-18): max(x,eps) | x+eps | identity */
 enum { SSB_FLOOR_MAX = 0, SSB_FLOOR_ADD = 1, SSB_FLOOR_NONE = 2 };
 /* normalization (ssspy/bss/ilrma.py:333-363) */
@@ -134,6 +136,10 @@ int ssb_update_once(ssb_plan* plan, void* stream);
 int ssb_run(ssb_plan* plan, int n_iter, double* loss, void* stream);
 /* update_source_model: ilrma.py:924-978 (MM/ME basis+activation); iva.py:3465-3473 (variance) */
 int ssb_update_source_model(ssb_plan* plan, void* stream);
+/* one sub-step of it on its own (ILRMA family): update_latent_{mm,me} ilrma.py:1007-1049, :1206-1247;
+ * update_basis_{mm,me} :1051-1128, :1249-1325; update_activation_{mm,me} :1130-1204, :1327-1401.
+ * part = SSB_PART_*; the MM / ME rule is the plan's `source` */
+int ssb_update_source_part(ssb_plan* plan, int part, void* stream);
 /* update_spatial_model: ilrma.py:1403-1438 (IP1/IP2/ISS1); AuxIVA update_once_{ip1,ip2,iss1}
  * iva.py:1736-1966 */
 int ssb_update_spatial_model(ssb_plan* plan, void* stream);
@@ -211,6 +217,13 @@ int ssb_minimal_distortion_principle(const void* Y, const void* X, void* Yout, i
                                      int reference_id, void* stream);
 
 /* ---- ssspy.linalg helpers, batched over n_mat small matrices, complex128 in/out -------------- */
+/* ILRMABase.compute_logdet (ilrma.py:524-536): out[m] = log|det W_m| (double, device) for n_mat complex64 N x N
+ * matrices */
+int ssb_logdet(const void* W, double* out, int n_mat, int N, void* stream);
+/* ILRMABase.reconstruct_nmf (ilrma.py:297-328): R[b,n,i,j] = sum_k T[b,n,i,k] V[b,n,k,j] (Z == NULL), or with the
+ * partitioning function sum_k Z[b,n,k] T[b,i,k] V[b,k,j]; all float32 on the device */
+int ssb_reconstruct_nmf(const float* T, const float* V, const float* Z, float* R, int B, int N, int I, int J, int K,
+                        void* stream);
 /* inv2 (ssspy/linalg/inv.py:4-54) generalised to N x N (np.linalg.inv call sites:
  * projection_back.py:89,110; ilrma.py:495,504,1944) */
 int ssb_inv(const void* A, void* Ainv, int n_mat, int N, void* stream);

@@ -17,6 +17,7 @@ MODEL_ILRMA_GAUSS, MODEL_IVA_LAPLACE, MODEL_IVA_GAUSS, MODEL_FASTMNMF_GAUSS = 0,
 MODEL_ILRMA_T, MODEL_ILRMA_GGD, MODEL_FDICA_LAPLACE = 4, 5, 6
 SPATIAL_IP1, SPATIAL_IP2, SPATIAL_ISS1, SPATIAL_ISS2, SPATIAL_IPA = 0, 1, 2, 3, 4
 SOURCE_MM, SOURCE_ME = 0, 1
+PART_LATENT, PART_BASIS, PART_ACTIVATION = 0, 1, 2
 FLOOR_MAX, FLOOR_ADD, FLOOR_NONE = 0, 1, 2
 NORM_NONE, NORM_POWER, NORM_PROJECTION_BACK = 0, 1, 2
 
@@ -53,6 +54,7 @@ SIGNATURES = {
     "ssb_update_once": [_vp, _vp],
     "ssb_run": [_vp, _i, _vp, _vp],
     "ssb_update_source_model": [_vp, _vp],
+    "ssb_update_source_part": [_vp, _i, _vp],
     "ssb_update_spatial_model": [_vp, _vp],
     "ssb_normalize": [_vp, _vp],
     "ssb_compute_loss": [_vp, _vp, _vp],
@@ -74,6 +76,8 @@ SIGNATURES = {
     "ssb_plan_permutation_align": [_vp, _vp, _vp, _vp],
     "ssb_projection_back_w": [_vp, _vp, _i, _i, _i, _vp],
     "ssb_projection_back_y": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "ssb_logdet": [_vp, _vp, _i, _i, _vp],
+    "ssb_reconstruct_nmf": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "ssb_inv": [_vp, _vp, _i, _i, _vp],
     "ssb_solve": [_vp, _vp, _vp, _i, _i, _i, _vp],
     "ssb_eigh": [_vp, _vp, _i, _vp, _vp, _i, _i, _vp],

@@ -62,6 +62,32 @@ def _state_property(name):
     return property(getter, setter, deleter)
 
 
+def reconstruct_nmf(self, basis, activation, latent=None):
+    """``T V`` per source, or ``sum_k z_nk t_ik v_kj`` with the partitioning function (ilrma.py:297-328).
+    Shapes (n_sources, n_bins, n_basis) x (n_sources, n_basis, n_frames) -> (n_sources, n_bins, n_frames), or
+    (n_bins, n_basis), (n_basis, n_frames), (n_sources, n_basis) with ``latent``; leading batch axes allowed."""
+    is_t = _device.is_tensor(basis)
+    T = _device.to_device(basis, torch.float32)
+    V = _device.to_device(activation, torch.float32)
+    K = T.shape[-1]
+    I, J = T.shape[-2], V.shape[-1]
+    if latent is None:
+        lead = tuple(T.shape[:-2])
+        N = lead[-1] if lead else 1
+        B = int(np.prod(lead[:-1])) if len(lead) > 1 else 1
+        Z = None
+    else:
+        Z = _device.to_device(latent, torch.float32)
+        lead = tuple(Z.shape[:-1])
+        N = lead[-1]
+        B = int(np.prod(lead[:-1])) if len(lead) > 1 else 1
+    assert V.shape[-2] == K, "basis and activation disagree on n_basis."
+    R = _device.empty(lead + (I, J), torch.float32)
+    _lib.call("ssb_reconstruct_nmf", T.data_ptr(), V.data_ptr(), _device.ptr(Z), R.data_ptr(), B, N, I, J, K,
+              _device.stream_ptr())
+    return R if is_t else R.cpu().numpy().astype(np.float64)
+
+
 class DeviceSeparatorMixin:
     """Plan + buffer management.  Subclasses provide ``_plan_config()``."""
 
@@ -426,6 +452,16 @@ class DeviceSeparatorMixin:
             self._host_output = host
         if losses is not None:
             self.loss.extend(losses[i].copy() if self._batched else float(losses[i, 0]) for i in range(losses.shape[0]))
+
+    def compute_logdet(self, demix_filter):
+        """``log|det W_i|`` per bin (ilrma.py:524-536, iva.py:224-236, fdica.py:225-237, mnmf.py:1263-1276)."""
+        is_t = _device.is_tensor(demix_filter)
+        W = _device.to_device(demix_filter, torch.complex64)
+        N = W.shape[-1]
+        assert W.shape[-2] == N, "square matrices are expected."
+        out = _device.empty(tuple(W.shape[:-2]), torch.float64)
+        _lib.call("ssb_logdet", W.data_ptr(), out.data_ptr(), out.numel(), N, _device.stream_ptr())
+        return out if is_t else out.cpu().numpy()
 
     # ---- separate --------------------------------------------------------------------------------
     def separate(self, input, demix_filter):

@@ -20,6 +20,7 @@ from ..special.flooring import EPS, identity, max_flooring
 from ..utils.flooring import choose_flooring_fn, flooring_to_enum
 from ..utils.select_pair import sequential_pair_selector, wrap_pairs
 from ._engine import DeviceSeparatorMixin
+from ._engine import reconstruct_nmf as _engine_reconstruct_nmf
 from .base import IterativeMethodBase
 
 __all__ = ["GaussILRMA", "TILRMA", "GGDILRMA"]
@@ -401,8 +402,47 @@ class _DeviceILRMA(ILRMABase):
         shape (batch,) for batched input."""
         return self._loss_from_device()
 
+    # ---- the reference's finer-grained entry points ------------------------------------------------------------
+    reconstruct_nmf = _engine_reconstruct_nmf
 
-class GaussILRMA(_DeviceILRMA):
+    def _source_part(self, part, rule, flooring_fn):
+        assert self.source_algorithm == rule, \
+            "This separator was built with source_algorithm={}.".format(self.source_algorithm)
+        if rule == "ME" and self.domain != 2:
+            raise ValueError("Domain parameter is expected 2, but given {}.".format(self.domain))
+        self._set_flooring(choose_flooring_fn(flooring_fn, method=self))
+        self._plan_call("ssb_update_source_part", part)
+
+    def update_latent_mm(self):
+        """Latent variable of the partitioning function, MM rule (ilrma.py:1007-1049)."""
+        self._source_part(_lib.PART_LATENT, "MM", "self")
+
+    def update_basis_mm(self, flooring_fn="self"):
+        """Basis only, MM rule (ilrma.py:1051-1128)."""
+        self._source_part(_lib.PART_BASIS, "MM", flooring_fn)
+
+    def update_activation_mm(self, flooring_fn="self"):
+        """Activation only, MM rule (ilrma.py:1130-1204)."""
+        self._source_part(_lib.PART_ACTIVATION, "MM", flooring_fn)
+
+
+class _MESubsteps:
+    """ME-rule sub-steps of the source model; the reference defines them for GaussILRMA and TILRMA only."""
+
+    def update_latent_me(self):
+        """ilrma.py:1206-1247."""
+        self._source_part(_lib.PART_LATENT, "ME", "self")
+
+    def update_basis_me(self, flooring_fn="self"):
+        """ilrma.py:1249-1325."""
+        self._source_part(_lib.PART_BASIS, "ME", flooring_fn)
+
+    def update_activation_me(self, flooring_fn="self"):
+        """ilrma.py:1327-1401."""
+        self._source_part(_lib.PART_ACTIVATION, "ME", flooring_fn)
+
+
+class GaussILRMA(_MESubsteps, _DeviceILRMA):
     """ssspy/bss/ilrma.py:582-1989 (signature :752-772)."""
 
     _ipa_default_kwargs = {"lqpqm_normalization": True, "newton_iter": 1}  # ilrma.py:749-750
@@ -434,7 +474,7 @@ class GaussILRMA(_DeviceILRMA):
         return self._repr_fields("GaussILRMA", "")
 
 
-class TILRMA(_DeviceILRMA):
+class TILRMA(_MESubsteps, _DeviceILRMA):
     """Student-t ILRMA, ssspy/bss/ilrma.py:1992-3334 (signature :2145-2165): ``dof`` is the degree of freedom nu;
     nu -> inf recovers GaussILRMA.  MM and ME source updates (ilrma.py:2384-2827), IP1 / IP2 / ISS1 with the weight
     1 / (nu/(nu+2) (TV)^(2/p) + 2/(nu+2) |y|^2) (ilrma.py:2863-3145), loss :3252-3312."""

@@ -19,6 +19,7 @@ from ..special.flooring import EPS, identity, max_flooring
 from ..utils.flooring import choose_flooring_fn, flooring_to_enum
 from ..utils.select_pair import sequential_pair_selector, wrap_pairs
 from ._engine import DeviceSeparatorMixin
+from ._engine import reconstruct_nmf as _engine_reconstruct_nmf
 from .base import IterativeMethodBase
 from .ilrma import _not_on_device
 
@@ -226,6 +227,19 @@ class FastGaussMNMF(MNMFBase):
 
     def update_spatial(self):
         _not_on_device("FastGaussMNMF.update_spatial on its own (use update_spatial_model)")
+
+    def update_diagonalizer_ip1(self, flooring_fn="self"):
+        _not_on_device("FastGaussMNMF.update_diagonalizer_ip1 on its own (use update_spatial_model)")
+
+    def update_diagonalizer_ip2(self, flooring_fn="self"):
+        _not_on_device("FastGaussMNMF.update_diagonalizer_ip2 on its own (use update_spatial_model)")
+
+    def normalize_by_power(self, flooring_fn="self"):
+        """mnmf.py:632-678."""
+        self._set_flooring(choose_flooring_fn(flooring_fn, method=self))
+        self._plan_call("ssb_normalize")
+
+    reconstruct_nmf = _engine_reconstruct_nmf
 
     def normalize(self, flooring_fn="self"):
         """mnmf.py:632-678 (power normalisation of Q and D)."""

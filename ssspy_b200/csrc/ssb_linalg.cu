@@ -162,3 +162,12 @@ extern "C" int ssb_eigh(const void* A, const void* B, int type, double* lamb, vo
                                                                N);
   return ssb_check_launch("eigh", (cudaStream_t)stream);
 }
+
+// ILRMABase.compute_logdet (ssspy/bss/ilrma.py:524-536)
+extern "C" int ssb_logdet(const void* W, double* out, int n_mat, int N, void* stream) {
+  SSB_REQUIRE(N >= 1 && N <= SSB_MAX_SOURCES, "logdet: N=%d unsupported (1..%d)", N, SSB_MAX_SOURCES);
+  SSB_REQUIRE(W != nullptr && out != nullptr, "logdet: NULL argument");
+  if (n_mat <= 0) return 0;
+  return ssbk_logdet((const cf*)W, out, n_mat, N, (cudaStream_t)stream);
+}
+

@@ -690,3 +690,38 @@ int ssbk_scale_basis(float* T, const cf* s, long long s_mat_stride, long long s_
   k_scale_basis<<<blocks, 256, 0, st>>>(T, s, s_mat_stride, s_src_stride, N, I, K, p, total);
   return ssb_check_launch("scale_basis", st);
 }
+
+// ------------------------------------------------------------------------------------------------
+// ILRMABase.reconstruct_nmf (ssspy/bss/ilrma.py:297-328): one thread per (mixture, source, bin, frame)
+__global__ void k_reconstruct_nmf(const float* __restrict__ T, const float* __restrict__ V, const float* __restrict__ Z,
+                                  float* __restrict__ R, int N, int I, int J, int K, size_t total) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int j = (int)(idx % J);
+  const int i = (int)((idx / J) % I);
+  const size_t bn = idx / ((size_t)I * J);
+  float acc = 0.f;
+  if (Z == nullptr) {
+    const float* t = T + (bn * I + i) * K;
+    const float* v = V + bn * (size_t)K * J + j;
+    for (int k = 0; k < K; ++k) acc = fmaf(t[k], v[(size_t)k * J], acc);
+  } else {
+    const size_t b = bn / N;
+    const float* z = Z + bn * K;
+    const float* t = T + (b * I + i) * K;
+    const float* v = V + b * (size_t)K * J + j;
+    for (int k = 0; k < K; ++k) acc = fmaf(z[k] * t[k], v[(size_t)k * J], acc);
+  }
+  R[idx] = acc;
+}
+
+extern "C" int ssb_reconstruct_nmf(const float* T, const float* V, const float* Z, float* R, int B, int N, int I, int J,
+                                   int K, void* stream) {
+  SSB_REQUIRE(T != nullptr && V != nullptr && R != nullptr, "reconstruct_nmf: NULL argument");
+  SSB_REQUIRE(B >= 0 && N >= 1 && I >= 1 && J >= 1 && K >= 1, "reconstruct_nmf: invalid shape");
+  const size_t total = (size_t)B * N * I * J;
+  if (total == 0) return 0;
+  k_reconstruct_nmf<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(T, V, Z, R, N, I, J, K, total);
+  return ssb_check_launch("reconstruct_nmf", (cudaStream_t)stream);
+}
+

@@ -321,6 +321,38 @@ int ilrma_source(ssb_plan* p, cudaStream_t st) {
   return 0;
 }
 
+// one sub-step of the source model on its own: the reference's update_latent_* / update_basis_* / update_activation_*
+// (ilrma.py:1007-1204, :1206-1401), each starting from a fresh power spectrogram exactly as the reference methods do.
+// The kernel sequences are the corresponding slices of ilrma_source / ilrma_source_part.
+int ilrma_source_substep(ssb_plan* p, int part, cudaStream_t st) {
+  const ssb_config& c = p->cfg;
+  const int B = c.n_batch, N = c.n_sources, I = c.n_bins, J = c.n_frames, K = c.n_basis;
+  SSB_REQUIRE(part >= SSB_PART_LATENT && part <= SSB_PART_ACTIVATION, "Invalid source-model part %d.", part);
+  SSB_REQUIRE(part != SSB_PART_LATENT || p->part(), "The latent variable exists only with partitioning=True.");
+  TRY(power_spectrogram(p, st));
+  if (p->part()) {
+    float* Z = p->variance;
+    TRY(ssbk_part_teff(Z, p->T, p->teff, B, N, I, K, st));
+    if (part == SSB_PART_ACTIVATION) {
+      TRY(ssbk_nmf_activation(p->big, p->teff, p->V, B * N, I, J, K, c.domain, c.source, c.model, c.model_param,
+                              c.flooring, c.eps, st, N, p->hnum, p->hden));
+      return ssbk_part_activation(p->hnum, p->hden, p->V, B, N, K, J, c.domain, c.source, c.model, c.model_param,
+                                  c.flooring, c.eps, st);
+    }
+    TRY(ssbk_nmf_basis(p->big, p->teff, p->V, B * N, I, J, K, c.domain, c.source, c.model, c.model_param, c.flooring,
+                       c.eps, st, N, p->gnum, p->gden));
+    if (part == SSB_PART_LATENT)
+      return ssbk_part_latent(p->gnum, p->gden, p->T, Z, B, N, I, K, c.domain, c.source, c.model, c.model_param, st);
+    return ssbk_part_basis(p->gnum, p->gden, Z, p->T, B, N, I, K, c.domain, c.source, c.model, c.model_param,
+                           c.flooring, c.eps, st);
+  }
+  if (part == SSB_PART_BASIS)
+    return ssbk_nmf_basis(p->big, p->T, p->V, B * N, I, J, K, c.domain, c.source, c.model, c.model_param, c.flooring,
+                          c.eps, st);
+  return ssbk_nmf_activation(p->big, p->T, p->V, B * N, I, J, K, c.domain, c.source, c.model, c.model_param,
+                             c.flooring, c.eps, st);
+}
+
 int ilrma_spatial(ssb_plan* p, cudaStream_t st) {
   const ssb_config& c = p->cfg;
   const int B = c.n_batch, N = c.n_sources, I = c.n_bins, J = c.n_frames;
@@ -606,6 +638,13 @@ extern "C" int ssb_update_source_model(ssb_plan* p, void* stream) {
   if (p->mnmf()) return mnmf_source(p, (cudaStream_t)stream);
   if (p->fdica()) return 0;  // no source parameters
   return p->ilrma() ? ilrma_source(p, (cudaStream_t)stream) : iva_source(p, (cudaStream_t)stream);
+}
+
+extern "C" int ssb_update_source_part(ssb_plan* p, int part, void* stream) {
+  TRY(require_bound(p));
+  SSB_REQUIRE(p->ilrma(), "update_source_part is defined for the ILRMA family only");
+  p->fused.vs_valid = false;
+  return ilrma_source_substep(p, part, (cudaStream_t)stream);
 }
 
 extern "C" int ssb_update_spatial_model(ssb_plan* p, void* stream) {

@@ -782,3 +782,49 @@ def test_fused_iteration_kernel_matches_unfused_and_oracle(I, J, K, n_iter, norm
         assert relerr(out["1"][0][b], st["Y"]) < TOL_Y
         assert relerr(out["1"][1][b], st["T"]) < TOL_TV
         assert relerr(out["1"][2][b], st["V"]) < TOL_TV
+
+
+@_MORE_FUSE_ITER
+@pytest.mark.parametrize("partitioning,source", [(False, "MM"), (False, "ME"), (True, "MM"), (True, "ME")])
+def test_source_model_substeps_reconstruct_and_logdet(partitioning, source):
+    """The reference's finer-grained entry points (opt-in until their first B200 run): update_latent_* /
+    update_basis_* / update_activation_* in sequence equal update_source_model and the oracle's sub-steps;
+    reconstruct_nmf and compute_logdet against NumPy."""
+    from oracle import ilrma as oilrma
+    from ssspy_b200.bss import GaussILRMA
+    from ssspy_b200.utils.synth import make_mixture, make_nmf_init
+    N, I, J, K = 3, 33, 48, 5
+    X = make_mixture(N, I, J, seed=31, mode="mix")
+    T, V = make_nmf_init(N, I, J, K, seed=32)
+    kwargs = dict(basis=T, activation=V)
+    Z0 = None
+    if partitioning:
+        rng = np.random.default_rng(33)
+        Z0 = rng.random((N, K)) + 0.1
+        Z0 = Z0 / Z0.sum(axis=0)
+        T, V = T[0].copy(), V[0].copy()
+        kwargs = dict(basis=T, activation=V, latent=Z0)
+    rule = source.lower()
+    whole = GaussILRMA(n_basis=K, source_algorithm=source, partitioning=partitioning)
+    whole(X, n_iter=0, **kwargs)
+    whole.update_source_model()
+    parts = GaussILRMA(n_basis=K, source_algorithm=source, partitioning=partitioning)
+    parts(X, n_iter=0, **kwargs)
+    st = oilrma.init_state(X, T, V, None, "IP", Z0)
+    if partitioning:
+        getattr(parts, "update_latent_" + rule)()
+        oilrma.update_latent(st, source_algorithm=source)
+        assert relerr(parts.latent, st["Z"]) < 1e-5
+    getattr(parts, "update_basis_" + rule)()
+    oilrma.update_basis(st, source_algorithm=source)
+    assert relerr(parts.basis, st["T"]) < 1e-5
+    getattr(parts, "update_activation_" + rule)()
+    oilrma.update_activation(st, source_algorithm=source)
+    assert relerr(parts.activation, st["V"]) < 1e-5
+    assert relerr(parts.basis, whole.basis) < 1e-5 and relerr(parts.activation, whole.activation) < 1e-5
+    with pytest.raises(AssertionError):
+        getattr(parts, "update_basis_" + ("me" if rule == "mm" else "mm"))()
+    R = parts.reconstruct_nmf(parts.basis, parts.activation, latent=parts.latent if partitioning else None)
+    assert R.shape == (N, I, J) and relerr(R, oilrma.reconstruct(st)) < 1e-5
+    W = parts.demix_filter
+    assert np.allclose(parts.compute_logdet(W), np.linalg.slogdet(W)[1], rtol=1e-5, atol=1e-6)

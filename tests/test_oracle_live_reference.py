@@ -317,3 +317,23 @@ def test_repr_mirrors_reference():
              ("FastGaussMNMF", rmn, mmn, dict(n_basis=3)), ("FastGaussMNMF", rmn, mmn, dict(n_basis=3, n_sources=2))]
     for name, ref_mod, new_mod, kw in cases:
         assert repr(getattr(new_mod, name)(**kw)) == repr(getattr(ref_mod, name)(**kw)), (name, kw)
+
+
+def test_public_method_surface_covers_reference():
+    """Every public attribute of the reference's separator classes exists on the host classes (drop-in surface)."""
+    _ref()
+    import ssspy.bss.fdica as rfd
+    import ssspy.bss.ilrma as rilrma
+    import ssspy.bss.iva as riva
+    import ssspy.bss.mnmf as rmn
+    from ssspy_b200.bss import fdica as mfd
+    from ssspy_b200.bss import ilrma as milrma
+    from ssspy_b200.bss import iva as miva
+    from ssspy_b200.bss import mnmf as mmn
+    for name, ref_mod, new_mod in (("GaussILRMA", rilrma, milrma), ("TILRMA", rilrma, milrma),
+                                   ("GGDILRMA", rilrma, milrma), ("AuxIVA", riva, miva),
+                                   ("AuxLaplaceIVA", riva, miva), ("AuxGaussIVA", riva, miva),
+                                   ("AuxLaplaceFDICA", rfd, mfd), ("FastGaussMNMF", rmn, mmn)):
+        want = {n for n in dir(getattr(ref_mod, name)) if not n.startswith("_")}
+        have = {n for n in dir(getattr(new_mod, name)) if not n.startswith("_")}
+        assert sorted(want - have) == [], name

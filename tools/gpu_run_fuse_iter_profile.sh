@@ -4,7 +4,7 @@
 # the opt-in parity shapes and a racecheck of the kernel.
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-SSB_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_parity.py -q -x -k fused_iteration > gpurun_out/r2_fuse_iter_tests.log 2>&1
+SSB_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_parity.py -q -k "fused_iteration or substeps" > gpurun_out/r2_fuse_iter_tests.log 2>&1
 tail -3 gpurun_out/r2_fuse_iter_tests.log
 SSB_FUSE_ITER=1 SSB_CHUNK=64 STEPS=3 timeout 600 ncu --set full --import-source on --clock-control none \
   -k regex:'kf_cov_ip1_basis|kf_activation_coop|kf_normalize' -c 4 -f -o gpurun_out/r2_fuse_iter \
