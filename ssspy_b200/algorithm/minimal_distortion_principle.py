@@ -4,6 +4,7 @@ import numpy as np
 import torch
 
 from .. import _device, _lib
+from ..utils.select_pair import wrap_reference_id
 
 
 def minimal_distortion_principle(estimated, reference=None, reference_id=0):
@@ -20,7 +21,8 @@ def minimal_distortion_principle(estimated, reference=None, reference_id=0):
     outs = []
     for ref in (range(Xb.shape[1]) if reference_id is None else [reference_id]):
         out = torch.empty_like(Yb)
-        _lib.call("ssb_minimal_distortion_principle", Yb.data_ptr(), Xb.data_ptr(), out.data_ptr(), B, N, I, J, int(ref),
+        _lib.call("ssb_minimal_distortion_principle", Yb.data_ptr(), Xb.data_ptr(), out.data_ptr(), B, N, I, J,
+                  wrap_reference_id(ref, Xb.shape[1]),
                   _device.stream_ptr())
         outs.append(out if batched else out[0])
     res = torch.stack(outs, dim=0) if reference_id is None else outs[0]

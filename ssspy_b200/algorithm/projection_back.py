@@ -3,6 +3,7 @@ import numpy as np
 import torch
 
 from .. import _device, _lib
+from ..utils.select_pair import wrap_reference_id
 
 
 def projection_back(data_or_filter, reference=None, reference_id=0):
@@ -20,7 +21,7 @@ def projection_back(data_or_filter, reference=None, reference_id=0):
         outs = []
         for ref in refs:
             out = torch.empty_like(W)
-            _lib.call("ssb_projection_back_w", W.data_ptr(), out.data_ptr(), n_mat, N, int(ref), st())
+            _lib.call("ssb_projection_back_w", W.data_ptr(), out.data_ptr(), n_mat, N, wrap_reference_id(ref, N), st())
             outs.append(out)
         res = torch.stack(outs, dim=0) if reference_id is None else outs[0]
     else:
@@ -36,7 +37,7 @@ def projection_back(data_or_filter, reference=None, reference_id=0):
         for ref in refs:
             out = torch.empty_like(Yb)
             _lib.call("ssb_projection_back_y", Yb.data_ptr(), Xb.data_ptr(), out.data_ptr(), scale.data_ptr(),
-                      B, N, I, J, int(ref), st())
+                      B, N, I, J, wrap_reference_id(ref, N), st())
             outs.append(out if batched else out[0])
         res = torch.stack(outs, dim=0) if reference_id is None else outs[0]
     if is_t:

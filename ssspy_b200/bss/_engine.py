@@ -81,7 +81,14 @@ def reconstruct_nmf(self, basis, activation, latent=None):
         lead = tuple(Z.shape[:-1])
         N = lead[-1]
         B = int(np.prod(lead[:-1])) if len(lead) > 1 else 1
-    assert V.shape[-2] == K, "basis and activation disagree on n_basis."
+    if V.shape[-2] != K:
+        raise ValueError("basis and activation disagree on n_basis ({} vs {}).".format(K, V.shape[-2]))
+    if latent is None and (T.dim() < 2 or tuple(T.shape[:-2]) != tuple(V.shape[:-2])):
+        raise ValueError("basis {} and activation {} disagree on the leading axes.".format(tuple(T.shape), tuple(V.shape)))
+    if latent is not None and (T.dim() != 2 or V.dim() != 2 or Z.shape[-1] != K):
+        raise ValueError("with latent: basis (n_bins, n_basis), activation (n_basis, n_frames), latent (..., n_sources, "
+                         "n_basis) are expected, but given {}, {}, {}.".format(tuple(T.shape), tuple(V.shape), tuple(Z.shape)))
+    T, V = T.contiguous(), V.contiguous()
     R = _device.empty(lead + (I, J), torch.float32)
     _lib.call("ssb_reconstruct_nmf", T.data_ptr(), V.data_ptr(), _device.ptr(Z), R.data_ptr(), B, N, I, J, K,
               _device.stream_ptr())
@@ -117,8 +124,7 @@ class DeviceSeparatorMixin:
         self._pending_h2d = None   # host tensor whose upload is enqueued per chunk by _ensure_plan
         self._defer_ok = False     # stock __call__: upload + initial separation run at the head of each chunk's pipeline
         self._deferred_sep = None  # (W, Y) of the deferred initial separation
-        self._host_output = None   # pinned host copy of `output` filled per chunk by __call__
-        self._host_out_buf = None
+        self._host_output = None   # pinned host copy of `output` filled per chunk by __call__ (owned by the caller)
 
     # ---- input -----------------------------------------------------------------------------------
     @property
@@ -344,6 +350,7 @@ class DeviceSeparatorMixin:
         """Enqueue ``fn(chunk, stream_ptr)`` for every chunk on its stream (after the current stream's
         work when ``fork``)."""
         self._ensure_plan()
+        self._host_output = None  # any plan call may rewrite Y on the device: the cached host copy is stale
         if len(self._chunks) == 1:
             self._chunk_init(self._chunks[0], torch.cuda.current_stream())
             fn(self._chunks[0], _device.stream_ptr())
@@ -432,9 +439,10 @@ class DeviceSeparatorMixin:
         Y = self._dev("output")
         host = None
         if self._cpu_tensor_io:
-            if self._host_out_buf is None or self._host_out_buf.shape != Y.shape:
-                self._host_out_buf = torch.empty(Y.shape, dtype=Y.dtype, pin_memory=True)
-            host = self._host_out_buf
+            # a fresh pinned tensor per call: the caller owns what __call__ returned (ys = [sep(x) for x in files]
+            # must not alias).  torch's caching host allocator hands a released block of the same size back without
+            # a new cudaHostAlloc, so a loop that drops its results does not pay for the pinning again.
+            host = torch.empty(Y.shape, dtype=Y.dtype, pin_memory=True)
         has_w = self._state.get("demix_filter") is not None
 
         def tail(ch, sp):
@@ -457,8 +465,10 @@ class DeviceSeparatorMixin:
         """``log|det W_i|`` per bin (ilrma.py:524-536, iva.py:224-236, fdica.py:225-237, mnmf.py:1263-1276)."""
         is_t = _device.is_tensor(demix_filter)
         W = _device.to_device(demix_filter, torch.complex64)
+        if W.dim() < 2 or W.shape[-2] != W.shape[-1]:
+            raise ValueError("square matrices (..., n_sources, n_sources) are expected, but given {}.".format(tuple(W.shape)))
         N = W.shape[-1]
-        assert W.shape[-2] == N, "square matrices are expected."
+        W = W.contiguous()
         out = _device.empty(tuple(W.shape[:-2]), torch.float64)
         _lib.call("ssb_logdet", W.data_ptr(), out.data_ptr(), out.numel(), N, _device.stream_ptr())
         return out if is_t else out.cpu().numpy()
@@ -475,8 +485,18 @@ class DeviceSeparatorMixin:
         W = _device.to_device(demix_filter, torch.complex64)
         batched = X.dim() == 4
         Xb = X if batched else X.unsqueeze(0)
+        if X.dim() not in (3, 4) or W.dim() not in (3, 4):
+            raise ValueError("input (..., n_channels, n_bins, n_frames) and demix_filter (..., n_bins, n_sources, "
+                             "n_channels) are expected, but given {} and {}.".format(tuple(X.shape), tuple(W.shape)))
         Wb = W if W.dim() == 4 else W.unsqueeze(0)
         B, N, I, J = Xb.shape
+        if tuple(Wb.shape[1:]) != (I, N, N) or Wb.shape[0] not in (1, B):
+            # the kernel indexes W by (b * n_bins + i): a mismatching filter would be read out of bounds
+            raise ValueError("demix_filter of shape {} does not match input of shape {} (determined case: "
+                             "(n_bins, n_channels, n_channels) per mixture).".format(tuple(W.shape), tuple(X.shape)))
+        if Wb.shape[0] != B:
+            Wb = Wb.expand(B, I, N, N)  # one filter set for every mixture of the batch (NumPy broadcasting)
+        Xb = Xb.contiguous()
         Y = torch.empty_like(Xb)
         _lib.call("ssb_separate", Xb.data_ptr(), Wb.contiguous().data_ptr(), Y.data_ptr(), B, N, I, J,
                   _device.stream_ptr())

@@ -18,7 +18,7 @@ import torch
 from .. import _device, _lib
 from ..special.flooring import EPS, identity, max_flooring
 from ..utils.flooring import choose_flooring_fn, flooring_to_enum
-from ..utils.select_pair import sequential_pair_selector, wrap_pairs
+from ..utils.select_pair import sequential_pair_selector, wrap_pairs, wrap_reference_id
 from ._engine import DeviceSeparatorMixin
 from ._engine import reconstruct_nmf as _engine_reconstruct_nmf
 from .base import IterativeMethodBase
@@ -181,7 +181,7 @@ class ILRMABase(DeviceSeparatorMixin, IterativeMethodBase):
             cfg.normalization = _lib.NORM_PROJECTION_BACK
         else:
             raise NotImplementedError("Normalization {} is not implemented.".format(norm))
-        cfg.reference_id = 0 if self.reference_id is None else int(self.reference_id)
+        cfg.reference_id = 0 if self.reference_id is None else wrap_reference_id(self.reference_id, N)
         pairs = []
         if cfg.spatial in (_lib.SPATIAL_IP2, _lib.SPATIAL_ISS2):
             pairs = wrap_pairs(self.pair_selector(N), N)

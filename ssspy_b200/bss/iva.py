@@ -13,7 +13,7 @@ import torch
 from .. import _lib
 from ..special.flooring import EPS, identity, max_flooring
 from ..utils.flooring import choose_flooring_fn, flooring_to_enum
-from ..utils.select_pair import sequential_pair_selector, wrap_pairs
+from ..utils.select_pair import sequential_pair_selector, wrap_pairs, wrap_reference_id
 from ._engine import DeviceSeparatorMixin
 from .base import IterativeMethodBase
 from .ilrma import (MINIMAL_DISTORTION_PRINCIPLE_KEYWORDS, PROJECTION_BACK_KEYWORDS, _SPATIAL_ENUM,
@@ -199,7 +199,7 @@ class AuxIVA(AuxIVABase):
         cfg.domain = 2.0
         cfg.flooring, cfg.eps = flooring_to_enum(self.flooring_fn)
         cfg.normalization = _lib.NORM_NONE
-        cfg.reference_id = 0 if self.reference_id is None else int(self.reference_id)
+        cfg.reference_id = 0 if self.reference_id is None else wrap_reference_id(self.reference_id, N)
         pairs = []
         if cfg.spatial in (_lib.SPATIAL_IP2, _lib.SPATIAL_ISS2):
             pairs = wrap_pairs(self.pair_selector(N), N)

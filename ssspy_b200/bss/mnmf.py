@@ -17,7 +17,7 @@ import torch
 from .. import _device, _lib
 from ..special.flooring import EPS, identity, max_flooring
 from ..utils.flooring import choose_flooring_fn, flooring_to_enum
-from ..utils.select_pair import sequential_pair_selector, wrap_pairs
+from ..utils.select_pair import sequential_pair_selector, wrap_pairs, wrap_reference_id
 from ._engine import DeviceSeparatorMixin
 from ._engine import reconstruct_nmf as _engine_reconstruct_nmf
 from .base import IterativeMethodBase
@@ -164,7 +164,7 @@ class FastGaussMNMF(MNMFBase):
             cfg.normalization = _lib.NORM_POWER
         else:
             raise NotImplementedError("Normalization {} is not implemented.".format(norm))
-        cfg.reference_id = int(self.reference_id)
+        cfg.reference_id = wrap_reference_id(self.reference_id, N)
         pairs = wrap_pairs(self.pair_selector(N), N) if cfg.spatial == _lib.SPATIAL_IP2 else []
         if len(pairs) > _lib.SSB_MAX_PAIRS:
             raise NotImplementedError("more than {} pairs per iteration".format(_lib.SSB_MAX_PAIRS))

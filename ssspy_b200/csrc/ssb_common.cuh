@@ -31,6 +31,15 @@ int ssb_check_launch(const char* what, cudaStream_t st);
     }                                                                                   \
   } while (0)
 
+// Function attributes (dynamic shared memory limits) are per device: launch sites keep one "configured" flag per
+// device, indexed by the calling thread's current device.
+#define SSB_MAX_DEVICES 64
+static inline int ssb_current_device() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= SSB_MAX_DEVICES) d = 0;
+  return d;
+}
+
 // ---- complex double ---------------------------------------------------------------------------
 __host__ __device__ __forceinline__ cd cd_make(double r, double i) { return make_double2(r, i); }
 __host__ __device__ __forceinline__ cd cd_add(cd a, cd b) { return make_double2(a.x + b.x, a.y + b.y); }

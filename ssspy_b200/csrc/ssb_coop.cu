@@ -972,7 +972,8 @@ int launch_coop(const ssb_config* c, const cf* X, const cf* W, float* T, float* 
   constexpr int AW1 = 4, AP1 = 3, AB1 = 7;
   const size_t sm_act = (size_t)TST * CHB + (size_t)AW * PST * 16 * PRS;
   const size_t sm_act1 = (size_t)(AP1 / 2 + 1) * CHB + (size_t)AW1 * AP1 * 16 * PRS;
-  static bool attr_set = false;
+  static bool attr_dev[SSB_MAX_DEVICES] = {};  // function attributes are per device
+  bool& attr_set = attr_dev[ssb_current_device()];
   if (!attr_set) {
     SSB_CUDA(cudaFuncSetAttribute(kf_basis_coop<N, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     if (N == 2) {
@@ -1253,7 +1254,8 @@ int launch_update_ab(int which, const float* A, const float* Bm, float* T, float
   const int nchunk_j = (J + JCV - 1) / JCV, nchunk_i = (I + JCV - 1) / JCV;
   const size_t sm_b = (size_t)ABTS * CHB + (size_t)AW * ABST * 2 * 16 * 96;
   const size_t sm_a = (size_t)ABTS * CHB + (size_t)AW * ABST * 2 * 16 * 80;
-  static bool attr_set = false;
+  static bool attr_dev[SSB_MAX_DEVICES] = {};  // function attributes are per device
+  bool& attr_set = attr_dev[ssb_current_device()];
   if (!attr_set) {
     SSB_CUDA(cudaFuncSetAttribute(kf_update_ab<KS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_b));
     SSB_CUDA(cudaFuncSetAttribute(kf_update_ab<KS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_a));
@@ -1517,7 +1519,8 @@ int launch_cov_coop(const ssb_config* c, const cf* X, const float* T, const __nv
   constexpr int KP = 16 * KS, JKS = KP + PADH, CHB = 2 * JCV * JKS * 2;
   const int nchunk = (J + JCV - 1) / JCV;
   const size_t sm = (size_t)XST * S::BT * N * 2048 + (size_t)2 * N * CHB;
-  static bool attr_set = false;
+  static bool attr_dev[SSB_MAX_DEVICES] = {};  // function attributes are per device
+  bool& attr_set = attr_dev[ssb_current_device()];
   if (!attr_set) {
     SSB_CUDA(cudaFuncSetAttribute(kf_cov_coop<N, KS, G_, RSW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     attr_set = true;

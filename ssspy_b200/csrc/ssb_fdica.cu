@@ -337,7 +337,8 @@ int ssbk_perm_align(cf* Y, cf* W, const int* order, int* perms, int B, int N, in
   const size_t sm = (size_t)N * J * (2 * sizeof(float) + sizeof(cf));
   SSB_REQUIRE(sm <= 200 * 1024, "permutation solver: n_sources * n_frames = %d exceeds the shared-memory slab", N * J);
   SSB_DISPATCH_N(N, {
-    static bool attr_set = false;
+    static bool attr_dev[SSB_MAX_DEVICES] = {};  // function attributes are per device
+  bool& attr_set = attr_dev[ssb_current_device()];
     if (!attr_set) {
       SSB_CUDA(cudaFuncSetAttribute(k_perm_align<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       attr_set = true;

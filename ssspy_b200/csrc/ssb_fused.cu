@@ -1005,7 +1005,8 @@ int launch_cov_w(const cf* X, const float* phi, long long sb, long long sn, long
   constexpr int NRC = CovShape<N>::RS ? 1 : 2;
   constexpr int G = CovShape<N>::G;
   const size_t sm = CovShape<N>::STG_W ? (size_t)FW * XSTAGES * 2 * NRC * N * 32 * sizeof(float4) : 0;
-  static bool attr_set = false;
+  static bool attr_dev[SSB_MAX_DEVICES] = {};  // function attributes are per device
+  bool& attr_set = attr_dev[ssb_current_device()];
   if (!attr_set) {
     SSB_CUDA(cudaFuncSetAttribute(kf_cov_w<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     attr_set = true;
@@ -1127,7 +1128,8 @@ int launch_all(const ssb_config* c, const cf* X, cf* W, float* T, float* V, floa
   const size_t sm_cov = (size_t)(2 * G * CovShape<N>::jcc(KP) * (KP + PADH)) * sizeof(__nv_bfloat16) + (CovShape<N>::STG ? ring_cov : 0);
   // SSB_COOP: 1 (default) cooperative basis kernel (ssb_coop.cu), 0 one CTA per (mixture, source)
   const int coop = ssb_fused_coop_enabled();
-  static bool attr_set = false;
+  static bool attr_dev[SSB_MAX_DEVICES] = {};  // function attributes are per device
+  bool& attr_set = attr_dev[ssb_current_device()];
   if (!attr_set) {
     SSB_CUDA(cudaFuncSetAttribute(kf_basis<N, KS, STG, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_basis));
     SSB_CUDA(cudaFuncSetAttribute(kf_activation<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_act));
@@ -1231,7 +1233,8 @@ int launch_source_iss(const ssb_config* c, const cf* Y, float* T, float* V, floa
   const size_t sm_basis = (size_t)(2 * JC * (KP + PADH) + 2 * KP * (JC + PADH)) * sizeof(__nv_bfloat16) + ring16;
   const size_t sm_act = (size_t)(2 * BCH * (KP + PADH) + 2 * KP * (BCH + PADH)) * sizeof(__nv_bfloat16) +
                         (size_t)FW * XSTAGES * 8 * 32 * sizeof(float);
-  static bool attr_set = false;
+  static bool attr_dev[SSB_MAX_DEVICES] = {};  // function attributes are per device
+  bool& attr_set = attr_dev[ssb_current_device()];
   if (!attr_set) {
     SSB_CUDA(cudaFuncSetAttribute(kf_basis<1, KS, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_basis));
     SSB_CUDA(cudaFuncSetAttribute(kf_activation<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_act));

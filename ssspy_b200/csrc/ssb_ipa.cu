@@ -348,7 +348,8 @@ int ssbk_ipa(cf* Y, const float* phi, long long sb, long long sn, long long si, 
   const size_t slab = (size_t)N * J * (sizeof(cf) + sizeof(float));
   const int use_smem = slab <= 180 * 1024;
   SSB_DISPATCH_N(N, {
-    static bool attr_set = false;
+    static bool attr_dev[SSB_MAX_DEVICES] = {};  // function attributes are per device
+  bool& attr_set = attr_dev[ssb_current_device()];
     if (!attr_set) {
       SSB_CUDA(cudaFuncSetAttribute(k_ipa_cta<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
       attr_set = true;

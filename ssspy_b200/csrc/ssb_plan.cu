@@ -24,11 +24,14 @@ void ssb_set_error(const char* fmt, ...) {
 // Every kernel launch of the library goes through ssb_check_launch.  With profiling enabled an
 // event is recorded after each launch; kernels of one stream run back to back, so the gap between
 // consecutive events is that launch's device time (the first gap starts at ssb_profile_begin).
+#include <atomic>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
-static unsigned long long g_launches = 0;
-static bool g_prof_on = false;
+static std::atomic<unsigned long long> g_launches{0};
+static std::atomic<bool> g_prof_on{false};
+static std::mutex g_prof_mu;  // guards g_prof_events / g_prof_start (launches may come from several host threads)
 static std::vector<std::pair<const char*, cudaEvent_t>> g_prof_events;
 static cudaEvent_t g_prof_start = nullptr;
 
@@ -38,11 +41,12 @@ int ssb_check_launch(const char* what, cudaStream_t st) {
     ssb_set_error("CUDA launch of '%s' failed: %s", what, cudaGetErrorString(e));
     return 1;
   }
-  ++g_launches;
-  if (g_prof_on) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (g_prof_on.load(std::memory_order_relaxed)) {
     cudaEvent_t ev;
     if (cudaEventCreate(&ev) == cudaSuccess) {
       cudaEventRecord(ev, st);
+      std::lock_guard<std::mutex> lk(g_prof_mu);
       g_prof_events.push_back({what, ev});
     }
   }
@@ -50,11 +54,12 @@ int ssb_check_launch(const char* what, cudaStream_t st) {
 }
 
 extern "C" int ssb_launch_count(unsigned long long* count) {
-  *count = g_launches;
+  *count = g_launches.load();
   return 0;
 }
 
 extern "C" int ssb_profile_begin(void* stream) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
   for (auto& pe : g_prof_events) cudaEventDestroy(pe.second);
   g_prof_events.clear();
   if (!g_prof_start) SSB_CUDA(cudaEventCreate(&g_prof_start));
@@ -66,6 +71,7 @@ extern "C" int ssb_profile_begin(void* stream) {
 // Stops profiling, synchronises, and writes "name count total_ms\n" lines (sorted by total time).
 extern "C" int ssb_profile_end(char* buf, size_t buf_bytes) {
   g_prof_on = false;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
   std::map<std::string, std::pair<int, double>> agg;
   cudaEvent_t prev = g_prof_start;
   for (auto& pe : g_prof_events) {

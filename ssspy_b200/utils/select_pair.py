@@ -33,3 +33,12 @@ def wrap_pairs(pairs, n_sources):
             raise IndexError("pair ({}, {}) is out of bounds for {} sources".format(m, n, n_sources))
         out.append((m % n_sources, n % n_sources))
     return out
+
+
+def wrap_reference_id(reference_id, n_channels):
+    """``reference_id`` as an index into ``[0, n_channels)``: negative values wrap as NumPy indexing does in the
+    reference (``projection_back.py:94``, ``x[reference_id]``); out-of-range values raise ``IndexError`` like it."""
+    ref = int(reference_id)
+    if not -n_channels <= ref < n_channels:
+        raise IndexError("index {} is out of bounds for axis 0 with size {}".format(ref, n_channels))
+    return ref % n_channels

@@ -235,3 +235,13 @@ def test_chunk_layout_rules(monkeypatch):
     assert got == [(0, 3), (3, 6), (6, 8)]
     for lay in (got, layout(64), layout(35, cpu=True)):
         assert lay[0][0] == 0 and all(a[1] == b[0] for a, b in zip(lay, lay[1:]))
+
+
+def test_reference_id_wraps_like_numpy_indexing():
+    from ssspy_b200.utils.select_pair import wrap_reference_id
+    assert [wrap_reference_id(r, 4) for r in (0, 3, -1, -4)] == [0, 3, 3, 0]
+    for bad in (4, -5):
+        with pytest.raises(IndexError):
+            wrap_reference_id(bad, 4)
+        with pytest.raises(IndexError):
+            np.zeros(4)[bad]

@@ -740,22 +740,17 @@ def test_chunked_streams_ragged_batch_matches_single_plan():
     np.testing.assert_array_equal(Yc, Y1)
 
 
-_MORE_FUSE_ITER = pytest.mark.skipif(not os.environ.get("SSB_TEST_EXPERIMENTAL"),
-                                     reason="opt-in (SSB_TEST_EXPERIMENTAL=1): shapes of the default-off SSB_FUSE_ITER "
-                                            "path that have not been through a B200 run yet")
-
-
 @pytest.mark.parametrize("I,J,K,n_iter,normalization,mode", [
     (37, 48, 5, 5, True, "1"), (257, 512, 16, 4, True, "1"),
-    pytest.param(70, 528, 16, 3, False, "1", marks=_MORE_FUSE_ITER),
-    pytest.param(20, 16, 4, 2, True, "1", marks=_MORE_FUSE_ITER),
-    pytest.param(33, 64, 24, 5, True, "1", marks=_MORE_FUSE_ITER),
-    pytest.param(129, 160, 32, 6, False, "1", marks=_MORE_FUSE_ITER),
+    (70, 528, 16, 3, False, "1"),
+    (20, 16, 4, 2, True, "1"),
+    (33, 64, 24, 5, True, "1"),
+    (129, 160, 32, 6, False, "1"),
     # mode 9: second pass backwards (odd and even numbers of 16-frame steps, a single step, K > 16)
-    pytest.param(37, 48, 5, 5, True, "9", marks=_MORE_FUSE_ITER),
-    pytest.param(257, 512, 16, 4, True, "9", marks=_MORE_FUSE_ITER),
-    pytest.param(20, 16, 4, 2, True, "9", marks=_MORE_FUSE_ITER),
-    pytest.param(33, 80, 24, 3, True, "9", marks=_MORE_FUSE_ITER)])
+    (37, 48, 5, 5, True, "9"),
+    (257, 512, 16, 4, True, "9"),
+    (20, 16, 4, 2, True, "9"),
+    (33, 80, 24, 3, True, "9")])
 def test_fused_iteration_kernel_matches_unfused_and_oracle(I, J, K, n_iter, normalization, mode, monkeypatch):
     """SSB_FUSE_ITER=1 (experimental, default off): inside ssb_run the covariance + IP1 of iteration t and the basis
     update of iteration t + 1 run as one kernel (kf_cov_ip1_basis, N = 2), with the power normalisation of iteration t
@@ -784,7 +779,6 @@ def test_fused_iteration_kernel_matches_unfused_and_oracle(I, J, K, n_iter, norm
         assert relerr(out["1"][2][b], st["V"]) < TOL_TV
 
 
-@_MORE_FUSE_ITER
 @pytest.mark.parametrize("partitioning,source", [(False, "MM"), (False, "ME"), (True, "MM"), (True, "ME")])
 def test_source_model_substeps_reconstruct_and_logdet(partitioning, source):
     """The reference's finer-grained entry points (opt-in until their first B200 run): update_latent_* /
@@ -828,3 +822,68 @@ def test_source_model_substeps_reconstruct_and_logdet(partitioning, source):
     assert R.shape == (N, I, J) and relerr(R, oilrma.reconstruct(st)) < 1e-5
     W = parts.demix_filter
     assert np.allclose(parts.compute_logdet(W), np.linalg.slogdet(W)[1], rtol=1e-5, atol=1e-6)
+
+
+def test_host_tensor_results_do_not_alias_and_output_is_never_stale():
+    """ys = [sep(x) for x in files] on pinned host tensors: every call returns its own buffer; `output` read after a
+    later device-side update (update_once / restore_scale) reflects that update, not the copy made by __call__."""
+    import torch
+    from ssspy_b200.bss import GaussILRMA
+    from ssspy_b200.utils.synth import make_batch, make_nmf_init
+    B, N, I, J, K = 3, 2, 33, 48, 4
+    T, V = make_nmf_init(N, I, J, K, seed=3)
+    X1 = torch.from_numpy(make_batch(B, N, I, J, config_id=61).astype(np.complex64)).pin_memory()
+    X2 = torch.from_numpy(make_batch(B, N, I, J, config_id=62).astype(np.complex64)).pin_memory()
+    sep = GaussILRMA(n_basis=K, record_loss=False)
+    ys = []
+    for x in (X1, X2):
+        s = GaussILRMA(n_basis=K, record_loss=False)
+        ys.append(s(x, n_iter=3, basis=T, activation=V))
+    y1 = sep(X1, n_iter=3, basis=T, activation=V)
+    keep = y1.clone()
+    sep2 = GaussILRMA(n_basis=K, record_loss=False)
+    y2 = sep2(X2, n_iter=3, basis=T, activation=V)
+    assert y1.data_ptr() != y2.data_ptr() and torch.equal(y1, keep)
+    assert torch.equal(ys[0], y1) and torch.equal(ys[1], y2) and not torch.equal(y1, y2)
+    # same object, second call with the same shape: the first result must survive
+    again = GaussILRMA(n_basis=K, record_loss=False)
+    a1 = again(X1, n_iter=2, basis=T, activation=V)
+    a1_copy = a1.clone()
+    a2 = again(X2, n_iter=2)
+    assert a1.data_ptr() != a2.data_ptr() and torch.equal(a1, a1_copy)
+    # stale cache: a device-side update after __call__ must be visible through `output`
+    before = sep.output.clone()
+    sep.update_once()
+    sep._plan_call("ssb_plan_separate")
+    after = sep.output
+    assert not torch.equal(before, after)
+
+
+def test_separate_validates_shapes_and_reference_id_wraps():
+    from ssspy_b200.algorithm import projection_back
+    from ssspy_b200.bss import GaussILRMA
+    from ssspy_b200.utils.synth import make_batch, make_nmf_init
+    B, N, I, J, K = 2, 3, 17, 32, 4
+    X = make_batch(B, N, I, J, config_id=63)
+    T, V = make_nmf_init(N, I, J, K, seed=3)
+    m = GaussILRMA(n_basis=K)
+    W = np.tile(np.eye(N, dtype=np.complex128), (I, 1, 1))
+    Y = m.separate(X, W)  # one filter set broadcast over the batch (NumPy semantics of W @ X)
+    assert relerr(Y, X) < 1e-6
+    with pytest.raises(ValueError):
+        m.separate(X, W[:-1])
+    with pytest.raises(ValueError):
+        m.separate(X, np.tile(np.eye(N + 1, dtype=np.complex128), (I, 1, 1)))
+    with pytest.raises(ValueError):
+        m.reconstruct_nmf(T, V[:, :-1])
+    with pytest.raises(ValueError):
+        m.compute_logdet(np.zeros((I, N, N + 1), dtype=np.complex128))
+    neg = GaussILRMA(n_basis=K, reference_id=-1)
+    pos = GaussILRMA(n_basis=K, reference_id=N - 1)
+    Yn = neg(X[0], n_iter=2, basis=T, activation=V)
+    Yp = pos(X[0], n_iter=2, basis=T, activation=V)
+    np.testing.assert_array_equal(Yn, Yp)
+    Wm = pos.demix_filter
+    np.testing.assert_array_equal(projection_back(Wm, reference_id=-1), projection_back(Wm, reference_id=N - 1))
+    with pytest.raises(IndexError):
+        GaussILRMA(n_basis=K, reference_id=N)(X[0], n_iter=1, basis=T, activation=V)

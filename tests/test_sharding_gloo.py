@@ -29,7 +29,6 @@ def _worker(rank, world, port, B, q):
         full = torch.from_numpy((rng.standard_normal((B, 2, 5, 7)) + 1j * rng.standard_normal((B, 2, 5, 7))).astype(np.complex64))
     shard = scatter_batch(full, src=0)
     lo, hi = shard_range(B, rank, world)
-    ref = (rng.standard_normal((B, 2, 5, 7)) + 1j * 0) if False else None
     assert shard.shape[0] == hi - lo
     # per-mixture independent "work": scale each mixture by its global index + 1
     idx = torch.arange(lo, hi, dtype=torch.float32).view(-1, 1, 1, 1) + 1
