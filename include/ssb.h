@@ -97,6 +97,11 @@ typedef struct ssb_config {
                            latent variable Z[B,N,K] f32 (ilrma.py:219-226); power normalisation only */
   int32_t ipa_normalization; /* IPA: lqpqm_normalization (ilrma.py:749, iva.py:1579; default 1) */
   int32_t ipa_newton_iter;   /* IPA: newton_iter, Newton-Raphson updates of the LQPQM root (default 1) */
+  int32_t no_whitening;      /* 0 (default): the demixing-filter modes (IP1 / IP2; FastGaussMNMF diagonaliser) iterate in
+                                the whitened domain z = L^-1 x, C = mean_j x x^H = L L^H (fp64), W~ = W L: the updates
+                                of _update_spatial_model.py:63-76, :317-395 are equivariant under this change of basis
+                                and y = W x = W~ z, but complex64 rounding is no longer amplified by cond(C).  W stays
+                                the reference's demix_filter at the boundary.  1: iterate on X, W directly (A/B, tests) */
 } ssb_config;
 
 typedef struct ssb_plan ssb_plan;

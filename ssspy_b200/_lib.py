@@ -32,6 +32,7 @@ class SsbConfig(ctypes.Structure):
         ("pairs", ctypes.c_int32 * (2 * SSB_MAX_PAIRS)), ("fast_path", ctypes.c_int32),
         ("model_param", ctypes.c_float), ("partitioning", ctypes.c_int32),
         ("ipa_normalization", ctypes.c_int32), ("ipa_newton_iter", ctypes.c_int32),
+        ("no_whitening", ctypes.c_int32),
     ]
 
 

@@ -32,6 +32,15 @@ _STATE_RANKS = {"demix_filter": 4, "output": 4, "basis": 4, "activation": 4, "va
                 "diagonalizer": 4, "spatial": 4}
 
 
+def no_whitening(sep):
+    """``ssb_config.no_whitening``: the demixing-filter modes iterate in the whitened domain (``whitening`` attribute,
+    default True; ``SSB_WHITEN=0`` switches it off process-wide for A/B runs)."""
+    env = os.environ.get("SSB_WHITEN")
+    if env is not None:
+        return 0 if int(env) else 1
+    return 0 if getattr(sep, "whitening", True) else 1
+
+
 def _state_property(name):
     def getter(self):
         if name not in self._state:

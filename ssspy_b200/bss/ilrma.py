@@ -18,6 +18,7 @@ import torch
 from .. import _device, _lib
 from ..special.flooring import EPS, identity, max_flooring
 from ..utils.flooring import choose_flooring_fn, flooring_to_enum
+from ._engine import no_whitening as _no_whitening
 from ..utils.select_pair import sequential_pair_selector, wrap_pairs, wrap_reference_id
 from ._engine import DeviceSeparatorMixin
 from ._engine import reconstruct_nmf as _engine_reconstruct_nmf
@@ -191,6 +192,7 @@ class ILRMABase(DeviceSeparatorMixin, IterativeMethodBase):
         for q, (m, n) in enumerate(pairs):
             cfg.pairs[2 * q], cfg.pairs[2 * q + 1] = m, n
         cfg.fast_path = 1 if getattr(self, "fast_path", True) else 0
+        cfg.no_whitening = _no_whitening(self)
         cfg.partitioning = 1 if self.partitioning else 0
         cfg.ipa_normalization = 1 if getattr(self, "lqpqm_normalization", True) else 0
         cfg.ipa_newton_iter = int(getattr(self, "newton_iter", 1))

@@ -13,6 +13,7 @@ import torch
 from .. import _lib
 from ..special.flooring import EPS, identity, max_flooring
 from ..utils.flooring import choose_flooring_fn, flooring_to_enum
+from ._engine import no_whitening as _no_whitening
 from ..utils.select_pair import sequential_pair_selector, wrap_pairs, wrap_reference_id
 from ._engine import DeviceSeparatorMixin
 from .base import IterativeMethodBase
@@ -209,6 +210,7 @@ class AuxIVA(AuxIVABase):
         for q, (m, n) in enumerate(pairs):
             cfg.pairs[2 * q], cfg.pairs[2 * q + 1] = m, n
         cfg.fast_path = 1 if getattr(self, "fast_path", True) else 0
+        cfg.no_whitening = _no_whitening(self)
         cfg.ipa_normalization = 1 if getattr(self, "lqpqm_normalization", True) else 0
         cfg.ipa_newton_iter = int(getattr(self, "newton_iter", 1))
         return cfg

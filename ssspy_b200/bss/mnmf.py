@@ -17,6 +17,7 @@ import torch
 from .. import _device, _lib
 from ..special.flooring import EPS, identity, max_flooring
 from ..utils.flooring import choose_flooring_fn, flooring_to_enum
+from ._engine import no_whitening as _no_whitening
 from ..utils.select_pair import sequential_pair_selector, wrap_pairs, wrap_reference_id
 from ._engine import DeviceSeparatorMixin
 from ._engine import reconstruct_nmf as _engine_reconstruct_nmf
@@ -172,6 +173,7 @@ class FastGaussMNMF(MNMFBase):
         for q, (m, n) in enumerate(pairs):
             cfg.pairs[2 * q], cfg.pairs[2 * q + 1] = m, n
         cfg.fast_path = 1
+        cfg.no_whitening = _no_whitening(self)
         return cfg
 
     # ---- the reference's methods ----------------------------------------------------------------------

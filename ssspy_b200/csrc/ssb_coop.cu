@@ -977,8 +977,8 @@ int launch_coop(const ssb_config* c, const cf* X, const cf* W, float* T, float* 
   if (!attr_set) {
     SSB_CUDA(cudaFuncSetAttribute(kf_basis_coop<N, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     if (N == 2) {
-      SSB_CUDA(cudaFuncSetAttribute(kf_cov_ip1_basis<KS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
-      SSB_CUDA(cudaFuncSetAttribute(kf_cov_ip1_basis<KS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+      SSB_CUDA(cudaFuncSetAttribute(kf_cov_ip1_basis<KS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      SSB_CUDA(cudaFuncSetAttribute(kf_cov_ip1_basis<KS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     }
     SSB_CUDA(cudaFuncSetAttribute(kf_activation_coop<KS, AW, PST, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_act));
     SSB_CUDA(cudaFuncSetAttribute(kf_activation_coop<KS, AW1, AP1, AB1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_act1));

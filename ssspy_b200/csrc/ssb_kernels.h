@@ -134,5 +134,19 @@ int ssbk_mnmf_normalize(const double* zsum, cf* Q, float* D, int B, int N, int I
                         cudaStream_t st);
 int ssbk_mnmf_rowloss(const cf* X, const float* T, const float* V, const float* Lam, const cf* Q, const float* D, double* rowloss, int B,
                       int N, int I, int J, int K, cudaStream_t st);
+// Lleft (optional, [B,I,N,N] c128): Qinv <- Lleft Qinv before the filter (Q given in the whitened domain)
 int ssbk_mnmf_separate(const cf* X, const float* T, const float* V, const cf* Q, const float* D, cd* Qinv, cf* Y, int B,
-                       int N, int I, int J, int K, int ref, int flooring, float eps, cudaStream_t st);
+                       int N, int I, int J, int K, int ref, int flooring, float eps, cudaStream_t st,
+                       const cd* Lleft = nullptr);
+
+// ---- ssb_whiten.cu: whitened-domain iteration ---------------------------------------------------------------
+// C64 = mean_j x x^H (fp64), C64 = L L^H, M = L^-1, Minv = L, ldM = log|det M|, Z = M X (complex64), wsync = 0
+int ssbk_whiten_prepare(const cf* X, cd* C64, cd* M, cd* Minv, double* ldM, cf* Z, int* wsync, int B, int N, int I, int J,
+                        cudaStream_t st);
+// Ww = W Minv for the matrices whose W differs from Wexp (or that were never imported); Wexp <- W
+int ssbk_w_import(const cf* W, cf* Wexp, cf* Ww, const cd* Minv, int* wsync, int n_mat, int N, cudaStream_t st);
+// W = Ww M; Wexp <- W
+int ssbk_w_export(const cf* Ww, const cd* M, cf* W, cf* Wexp, int* wsync, int n_mat, int N, cudaStream_t st);
+// projection back on the whitened filter: s_n = (Minv Ww^-1)[ref, n], Ww[n,:] *= s_n, scale_out[mat,n] = s_n
+int ssbk_pb_whitened(cf* Ww, const cd* Minv, cf* scale_out, int n_mat, int N, int ref, cudaStream_t st);
+int ssbk_add_logdet(double* logdet, const double* ldM, int n, cudaStream_t st);

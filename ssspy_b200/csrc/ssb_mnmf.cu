@@ -273,6 +273,29 @@ __global__ void __launch_bounds__(MW * 32) km_qinv(const cf* __restrict__ Q, cd*
   }
 }
 
+// Qinv[b,i] <- Lm[b,i] Qinv[b,i]: the inverse of a diagonaliser kept in the whitened domain (Q = Q~ M, Q^-1 = M^-1 Q~^-1)
+template <int N>
+__global__ void km_leftmul(const cd* __restrict__ Lm, cd* __restrict__ Qinv, int n_mat) {
+  const int mat = blockIdx.x * blockDim.x + threadIdx.x;
+  if (mat >= n_mat) return;
+  const cd* L = Lm + (size_t)mat * N * N;
+  cd* Q = Qinv + (size_t)mat * N * N;
+  cd q[N * N], o[N * N];
+#pragma unroll
+  for (int e = 0; e < N * N; ++e) q[e] = Q[e];
+#pragma unroll
+  for (int r = 0; r < N; ++r)
+#pragma unroll
+    for (int c = 0; c < N; ++c) {
+      cd s = cd_make(0, 0);
+#pragma unroll
+      for (int k = 0; k < N; ++k) s = cd_fma(L[r * N + k], q[k * N + c], s);
+      o[r * N + c] = s;
+    }
+#pragma unroll
+  for (int e = 0; e < N * N; ++e) Q[e] = o[e];
+}
+
 // Multichannel Wiener filter (mnmf.py:1186-1217), one thread per (bin, frame), one block per bin:
 //   R = Qinv diag(L) Qinv^H -> to_psd (Hermitian eigendecomposition, eigenvalues floored, rebuilt)
 //   u_n = R^-1 R_n[:, ref],  R_n[:, ref] = Qinv diag(Lambda_n D[n,:]) conj(Qinv[ref, :])
@@ -382,10 +405,14 @@ int ssbk_mnmf_rowloss(const cf* X, const float* T, const float* V, const float* 
   return ssb_check_launch("mnmf_rowloss", st);
 }
 int ssbk_mnmf_separate(const cf* X, const float* T, const float* V, const cf* Q, const float* D, cd* Qinv, cf* Y, int B,
-                       int N, int I, int J, int K, int ref, int flooring, float eps, cudaStream_t st) {
+                       int N, int I, int J, int K, int ref, int flooring, float eps, cudaStream_t st, const cd* Lleft) {
   SSB_REQUIRE(ref >= 0 && ref < N, "reference_id=%d out of range for N=%d", ref, N);
   SSB_DISPATCH_N(N, km_qinv<NN><<<blocks_for((long long)B * I, MW * GroupShape<NN>::GW), MW * 32, 0, st>>>(Q, Qinv, B * I));
   if (ssb_check_launch("mnmf_qinv", st)) return 1;
+  if (Lleft != nullptr) {
+    SSB_DISPATCH_N(N, km_leftmul<NN><<<blocks_for((long long)B * I, 64), 64, 0, st>>>(Lleft, Qinv, B * I));
+    if (ssb_check_launch("mnmf_qinv_unwhiten", st)) return 1;
+  }
   SSB_DISPATCH_N(N, km_separate<NN><<<B * I, 128, 0, st>>>(X, T, V, D, Qinv, Y, I, J, K, ref, flooring, (double)eps));
   return ssb_check_launch("mnmf_separate", st);
 }

@@ -144,6 +144,19 @@ struct ssb_plan {
   float* teff = nullptr;
   float *gnum = nullptr, *gden = nullptr;  // [B,N,I,K]
   float *hnum = nullptr, *hden = nullptr;  // [B,N,K,J]
+  // whitened-domain iteration (ssb_whiten.cu): the kernels of the demixing-filter modes read Xk = M X and update
+  // Wk = W M^-1; X / W stay the caller's (reference-domain) buffers, synchronised at the C-ABI boundary
+  const cf* Xk = nullptr;
+  cf* Wk = nullptr;
+  bool whiten = false;
+  cf* Xw = nullptr;       // [B,N,I,J]
+  cf* Ww = nullptr;       // [B,I,N,N]
+  cf* Wexp = nullptr;     // [B,I,N,N] the W last exported / imported, bit for bit
+  cd* C64 = nullptr;      // [B,I,N,N] fp64 covariance of the mixture
+  cd* Mw = nullptr;       // [B,I,N,N] whitening matrix M = L^-1 (C = L L^H)
+  cd* Mwinv = nullptr;    // [B,I,N,N] M^-1 = L
+  double* ldM = nullptr;  // [B,I] log|det M|
+  int* wsync = nullptr;   // [B,I] 1: Wk holds the whitened image of Wexp
   bool part() const { return cfg.partitioning != 0; }
   bool mnmf() const { return cfg.model == SSB_MODEL_FASTMNMF_GAUSS; }
   // modes whose state lives in Y (no demixing filter): ISS1 / ISS2 / IPA
@@ -191,6 +204,17 @@ size_t carve(ssb_plan* p, char* base) {
   p->psi2 = cv.take<double>(B * N);
   p->rowloss = cv.take<double>(B * N * I);
   p->logdet = cv.take<double>(B * I);
+  p->whiten = !p->iss() && !c.no_whitening;
+  if (p->whiten) {
+    p->Xw = cv.take<cf>(B * N * I * J);
+    p->Ww = cv.take<cf>(B * I * N * N);
+    p->Wexp = cv.take<cf>(B * I * N * N);
+    p->C64 = cv.take<cd>(B * I * N * N);
+    p->Mw = cv.take<cd>(B * I * N * N);
+    p->Mwinv = cv.take<cd>(B * I * N * N);
+    p->ldM = cv.take<double>(B * I);
+    p->wsync = cv.take<int>(B * I);
+  }
   if (p->part()) {
     const size_t K = c.n_basis;
     p->teff = cv.take<float>(B * N * I * K);
@@ -274,22 +298,37 @@ int require_bound(const ssb_plan* p) {
   return 0;
 }
 
+// Whitened-domain boundary (ssb_whiten.cu): before a plan call reads the filters, bins whose caller-visible W changed
+// since the last export are re-imported (W~ = W M^-1); after a call that updated them, W = W~ M is written back.
+int w_enter(ssb_plan* p, cudaStream_t st) {
+  if (!p->whiten) return 0;
+  SSB_REQUIRE(p->prepared, "plan not prepared (call ssb_plan_prepare after bind)");
+  return ssbk_w_import(p->W, p->Wexp, p->Ww, p->Mwinv, p->wsync, p->cfg.n_batch * p->cfg.n_bins, p->cfg.n_sources, st);
+}
+int w_exit(ssb_plan* p, cudaStream_t st) {
+  if (!p->whiten) return 0;
+  return ssbk_w_export(p->Ww, p->Mw, p->W, p->Wexp, p->wsync, p->cfg.n_batch * p->cfg.n_bins, p->cfg.n_sources, st);
+}
+
 // P <- |Y|^2 with Y = W X (W modes) or the stored Y (ISS modes)
 int power_spectrogram(ssb_plan* p, cudaStream_t st) {
   const ssb_config& c = p->cfg;
   if (p->iss()) return ssbk_abs2(p->Y, p->big, (size_t)c.n_batch * c.n_sources * c.n_bins * c.n_frames, st);
-  return ssbk_separate(p->X, p->W, nullptr, p->big, c.n_batch, c.n_sources, c.n_bins, c.n_frames, st);
+  return ssbk_separate(p->Xk, p->Wk, nullptr, p->big, c.n_batch, c.n_sources, c.n_bins, c.n_frames, st);
 }
 
 // log|det W_i| for every (b,i); ISS modes first recover W = Y X^H (X X^H)^-1
 int logdets(ssb_plan* p, cudaStream_t st) {
   const ssb_config& c = p->cfg;
-  const cf* W = p->W;
+  const cf* W = p->Wk;
   if (p->iss()) {
-    TRY(ssbk_cross_solve(p->Y, p->X, p->S, c.n_batch, c.n_sources, c.n_bins, c.n_frames, st));
+    TRY(ssbk_cross_solve(p->Y, p->Xk, p->S, c.n_batch, c.n_sources, c.n_bins, c.n_frames, st));
     W = p->S;
   }
-  return ssbk_logdet(W, p->logdet, c.n_batch * c.n_bins, c.n_sources, st);
+  TRY(ssbk_logdet(W, p->logdet, c.n_batch * c.n_bins, c.n_sources, st));
+  // whitened filters: log|det W| = log|det W~| + log|det M|
+  if (p->whiten) TRY(ssbk_add_logdet(p->logdet, p->ldM, c.n_batch * c.n_bins, st));
+  return 0;
 }
 
 // partitioning function: latent, basis, activation in this order, each from a fresh sweep over P with the
@@ -373,9 +412,9 @@ int ilrma_spatial(ssb_plan* p, cudaStream_t st) {
     return ssbk_iss2(p->Y, p->big, sb, sn, si, B, N, I, J, c.pairs, c.n_pairs, c.flooring, c.eps, st);
   if (c.spatial == SSB_SPATIAL_IPA)  // ilrma.py:1813-1908
     return ssbk_ipa(p->Y, p->big, sb, sn, si, B, N, I, J, c.ipa_normalization, c.ipa_newton_iter, c.flooring, c.eps, st);
-  TRY(ssbk_wcov(p->X, p->big, sb, sn, si, nullptr, N, p->U, B, N, I, J, st));
-  if (c.spatial == SSB_SPATIAL_IP1) return ssbk_ip1(p->W, p->U, B * I, N, c.flooring, c.eps, st);
-  return ssbk_ip2(p->W, p->U, B * I, N, c.pairs, c.n_pairs, N, nullptr, c.flooring, c.eps, st);
+  TRY(ssbk_wcov(p->Xk, p->big, sb, sn, si, nullptr, N, p->U, B, N, I, J, st));
+  if (c.spatial == SSB_SPATIAL_IP1) return ssbk_ip1(p->Wk, p->U, B * I, N, c.flooring, c.eps, st);
+  return ssbk_ip2(p->Wk, p->U, B * I, N, c.pairs, c.n_pairs, N, nullptr, c.flooring, c.eps, st);
 }
 
 int ilrma_normalize(ssb_plan* p, cudaStream_t st) {
@@ -389,19 +428,20 @@ int ilrma_normalize(ssb_plan* p, cudaStream_t st) {
       TRY(ssbk_apply_psi(p->psi2, Tn, nullptr, p->Y, B, N, I, J, K, c.domain, c.flooring, c.eps, st));
     } else {
       SSB_REQUIRE(p->prepared, "plan not prepared (call ssb_plan_prepare after bind)");
-      TRY(ssbk_psi_from_cov(p->W, p->C, p->psi2, B, N, I, st));
-      TRY(ssbk_apply_psi(p->psi2, Tn, p->W, nullptr, B, N, I, J, K, c.domain, c.flooring, c.eps, st));
+      TRY(ssbk_psi_from_cov(p->Wk, p->C, p->psi2, B, N, I, st));
+      TRY(ssbk_apply_psi(p->psi2, Tn, p->Wk, nullptr, B, N, I, J, K, c.domain, c.flooring, c.eps, st));
     }
     if (p->part()) return ssbk_part_normalize(p->psi2, p->variance, p->T, B, N, I, K, c.domain, c.flooring, c.eps, st);
     return 0;
   }
   if (c.normalization == SSB_NORM_PROJECTION_BACK) {
     if (p->iss()) {
-      TRY(ssbk_cross_solve(p->X, p->Y, p->S, B, N, I, J, st));
+      TRY(ssbk_cross_solve(p->Xk, p->Y, p->S, B, N, I, J, st));
       TRY(ssbk_scale_rows(p->Y, p->S, p->Y, B, N, I, J, c.reference_id, st));
       return ssbk_scale_basis(p->T, p->S + (size_t)c.reference_id * N, (long long)N * N, 1, B, N, I, K, c.domain, st);
     }
-    TRY(ssbk_pb_w(p->W, p->W, p->scale, B * I, N, c.reference_id, st));
+    if (p->whiten) TRY(ssbk_pb_whitened(p->Wk, p->Mwinv, p->scale, B * I, N, c.reference_id, st));
+    else TRY(ssbk_pb_w(p->Wk, p->Wk, p->scale, B * I, N, c.reference_id, st));
     return ssbk_scale_basis(p->T, p->scale, N, 1, B, N, I, K, c.domain, st);
   }
   return 0;
@@ -421,7 +461,7 @@ int ilrma_loss(ssb_plan* p, double* loss, cudaStream_t st) {
 // r2 over all sources from the current state
 int iva_norm_all(ssb_plan* p, cudaStream_t st) {
   const ssb_config& c = p->cfg;
-  return ssbk_iva_norm2(p->X, p->iss() ? nullptr : p->W, p->Y, nullptr, c.n_sources, p->r2, c.n_batch, c.n_sources,
+  return ssbk_iva_norm2(p->Xk, p->iss() ? nullptr : p->Wk, p->Y, nullptr, c.n_sources, p->r2, c.n_batch, c.n_sources,
                         c.n_bins, c.n_frames, st);
 }
 
@@ -440,11 +480,11 @@ int iva_spatial(ssb_plan* p, cudaStream_t st) {
     for (int q = 0; q < c.n_pairs; ++q) {
       const int pr[2] = {c.pairs[2 * q], c.pairs[2 * q + 1]};
       const int uidx[2] = {0, 1};
-      TRY(ssbk_iva_norm2(p->X, p->W, nullptr, pr, 2, p->r2, B, N, I, J, st));
+      TRY(ssbk_iva_norm2(p->Xk, p->Wk, nullptr, pr, 2, p->r2, B, N, I, J, st));
       TRY(ssbk_iva_phi(p->r2, p->variance, 0, pr, 2, p->phi_iva, c.model, B, N, I, J, c.flooring, c.eps, st));
-      if (c.fast_path && (J % 16) == 0) TRY(ssb_fused_cov_w(p->X, p->phi_iva, 2LL * J, J, 0, 2, p->U, B, N, I, J, st));
-      else TRY(ssbk_wcov(p->X, p->phi_iva, 2LL * J, J, 0, nullptr, 2, p->U, B, N, I, J, st));
-      TRY(ssbk_ip2(p->W, p->U, B * I, N, pr, 1, 2, uidx, c.flooring, c.eps, st));
+      if (c.fast_path && (J % 16) == 0) TRY(ssb_fused_cov_w(p->Xk, p->phi_iva, 2LL * J, J, 0, 2, p->U, B, N, I, J, st));
+      else TRY(ssbk_wcov(p->Xk, p->phi_iva, 2LL * J, J, 0, nullptr, 2, p->U, B, N, I, J, st));
+      TRY(ssbk_ip2(p->Wk, p->U, B * I, N, pr, 1, 2, uidx, c.flooring, c.eps, st));
     }
     return 0;
   }
@@ -457,9 +497,9 @@ int iva_spatial(ssb_plan* p, cudaStream_t st) {
   if (c.spatial == SSB_SPATIAL_IPA)  // iva.py:2068-2176
     return ssbk_ipa(p->Y, p->phi_iva, (long long)N * J, J, 0, B, N, I, J, c.ipa_normalization, c.ipa_newton_iter,
                     c.flooring, c.eps, st);
-  if (c.fast_path && (J % 16) == 0) TRY(ssb_fused_cov_w(p->X, p->phi_iva, (long long)N * J, J, 0, N, p->U, B, N, I, J, st));
-  else TRY(ssbk_wcov(p->X, p->phi_iva, (long long)N * J, J, 0, nullptr, N, p->U, B, N, I, J, st));
-  return ssbk_ip1(p->W, p->U, B * I, N, c.flooring, c.eps, st);
+  if (c.fast_path && (J % 16) == 0) TRY(ssb_fused_cov_w(p->Xk, p->phi_iva, (long long)N * J, J, 0, N, p->U, B, N, I, J, st));
+  else TRY(ssbk_wcov(p->Xk, p->phi_iva, (long long)N * J, J, 0, nullptr, N, p->U, B, N, I, J, st));
+  return ssbk_ip1(p->Wk, p->U, B * I, N, c.flooring, c.eps, st);
 }
 
 int iva_loss(ssb_plan* p, double* loss, cudaStream_t st) {
@@ -478,23 +518,24 @@ int fdica_spatial(ssb_plan* p, cudaStream_t st) {
     for (int q = 0; q < c.n_pairs; ++q) {
       const int pr[2] = {c.pairs[2 * q], c.pairs[2 * q + 1]};
       const int uidx[2] = {0, 1};
-      TRY(ssbk_fdica_phi(p->X, p->W, p->big, pr, 2, B, N, I, J, c.flooring, c.eps, st));
-      if (fast) TRY(ssb_fused_cov_w(p->X, p->big, 2LL * I * J, (long long)I * J, J, 2, p->U, B, N, I, J, st));
-      else TRY(ssbk_wcov(p->X, p->big, 2LL * I * J, (long long)I * J, J, nullptr, 2, p->U, B, N, I, J, st));
-      TRY(ssbk_ip2(p->W, p->U, B * I, N, pr, 1, 2, uidx, c.flooring, c.eps, st));
+      TRY(ssbk_fdica_phi(p->Xk, p->Wk, p->big, pr, 2, B, N, I, J, c.flooring, c.eps, st));
+      if (fast) TRY(ssb_fused_cov_w(p->Xk, p->big, 2LL * I * J, (long long)I * J, J, 2, p->U, B, N, I, J, st));
+      else TRY(ssbk_wcov(p->Xk, p->big, 2LL * I * J, (long long)I * J, J, nullptr, 2, p->U, B, N, I, J, st));
+      TRY(ssbk_ip2(p->Wk, p->U, B * I, N, pr, 1, 2, uidx, c.flooring, c.eps, st));
     }
     return 0;
   }
-  TRY(ssbk_fdica_phi(p->X, p->W, p->big, nullptr, N, B, N, I, J, c.flooring, c.eps, st));
-  if (fast) TRY(ssb_fused_cov_w(p->X, p->big, (long long)N * I * J, (long long)I * J, J, N, p->U, B, N, I, J, st));
-  else TRY(ssbk_wcov(p->X, p->big, (long long)N * I * J, (long long)I * J, J, nullptr, N, p->U, B, N, I, J, st));
-  return ssbk_ip1(p->W, p->U, B * I, N, c.flooring, c.eps, st);
+  TRY(ssbk_fdica_phi(p->Xk, p->Wk, p->big, nullptr, N, B, N, I, J, c.flooring, c.eps, st));
+  if (fast) TRY(ssb_fused_cov_w(p->Xk, p->big, (long long)N * I * J, (long long)I * J, J, N, p->U, B, N, I, J, st));
+  else TRY(ssbk_wcov(p->Xk, p->big, (long long)N * I * J, (long long)I * J, J, nullptr, N, p->U, B, N, I, J, st));
+  return ssbk_ip1(p->Wk, p->U, B * I, N, c.flooring, c.eps, st);
 }
 
 int fdica_loss(ssb_plan* p, double* loss, cudaStream_t st) {
   const ssb_config& c = p->cfg;
-  TRY(ssbk_fdica_rowloss(p->X, p->W, p->rowloss, c.n_batch, c.n_sources, c.n_bins, c.n_frames, st));
-  TRY(ssbk_logdet(p->W, p->logdet, c.n_batch * c.n_bins, c.n_sources, st));
+  TRY(ssbk_fdica_rowloss(p->Xk, p->Wk, p->rowloss, c.n_batch, c.n_sources, c.n_bins, c.n_frames, st));
+  TRY(ssbk_logdet(p->Wk, p->logdet, c.n_batch * c.n_bins, c.n_sources, st));
+  if (p->whiten) TRY(ssbk_add_logdet(p->logdet, p->ldM, c.n_batch * c.n_bins, st));
   return ssbk_ilrma_loss_reduce(p->rowloss, p->logdet, loss, c.n_batch, 1, c.n_bins, st);
 }
 
@@ -522,11 +563,11 @@ int mnmf_source(ssb_plan* p, cudaStream_t st) {
     SSB_CUDA(cudaMemsetAsync(p->fused.base, 0, p->fused.bytes, st));
     p->fused.zeroed = true;
   }
-  TRY(ssbk_mnmf_gh(p->X, p->T, p->V, lam, p->W, p->variance, p->big, p->big2, B, N, I, J, K, st));
+  TRY(ssbk_mnmf_gh(p->Xk, p->T, p->V, lam, p->Wk, p->variance, p->big, p->big2, B, N, I, J, K, st));
   if (tc) TRY(ssb_coop_update_ab(&c, 0, p->big, p->big2, p->T, p->V, p->fused.base, st));
   else TRY(ssbk_nmf_basis_ab(p->big, p->big2, p->T, p->V, B * N, I, J, K, c.flooring, c.eps, st));
   TRY(mnmf_lambda(p, &lam, st));
-  TRY(ssbk_mnmf_gh(p->X, p->T, p->V, lam, p->W, p->variance, p->big, p->big2, B, N, I, J, K, st));
+  TRY(ssbk_mnmf_gh(p->Xk, p->T, p->V, lam, p->Wk, p->variance, p->big, p->big2, B, N, I, J, K, st));
   if (tc) return ssb_coop_update_ab(&c, 1, p->big, p->big2, p->T, p->V, p->fused.base, st);
   return ssbk_nmf_activation_ab(p->big, p->big2, p->T, p->V, B * N, I, J, K, c.flooring, c.eps, st);
 }
@@ -536,21 +577,21 @@ int mnmf_spatial(ssb_plan* p, cudaStream_t st) {
   const int B = c.n_batch, N = c.n_sources, I = c.n_bins, J = c.n_frames, K = c.n_basis;
   const float* lam;
   TRY(mnmf_lambda(p, &lam, st));
-  TRY(ssbk_mnmf_phi(p->X, p->T, p->V, lam, p->W, p->variance, p->big, B, N, I, J, K, st));
+  TRY(ssbk_mnmf_phi(p->Xk, p->T, p->V, lam, p->Wk, p->variance, p->big, B, N, I, J, K, st));
   if (c.fast_path && (J % 16) == 0)
-    TRY(ssb_fused_cov_w(p->X, p->big, (long long)N * I * J, (long long)I * J, J, N, p->U, B, N, I, J, st));
+    TRY(ssb_fused_cov_w(p->Xk, p->big, (long long)N * I * J, (long long)I * J, J, N, p->U, B, N, I, J, st));
   else
-    TRY(ssbk_wcov(p->X, p->big, (long long)N * I * J, (long long)I * J, J, nullptr, N, p->U, B, N, I, J, st));
-  if (c.spatial == SSB_SPATIAL_IP1) TRY(ssbk_ip1(p->W, p->U, B * I, N, c.flooring, c.eps, st));
-  else TRY(ssbk_ip2(p->W, p->U, B * I, N, c.pairs, c.n_pairs, N, nullptr, c.flooring, c.eps, st));
-  return ssbk_mnmf_spatial(p->X, p->T, p->V, lam, p->W, p->variance, p->rowloss, B, N, I, J, K, 1, st);
+    TRY(ssbk_wcov(p->Xk, p->big, (long long)N * I * J, (long long)I * J, J, nullptr, N, p->U, B, N, I, J, st));
+  if (c.spatial == SSB_SPATIAL_IP1) TRY(ssbk_ip1(p->Wk, p->U, B * I, N, c.flooring, c.eps, st));
+  else TRY(ssbk_ip2(p->Wk, p->U, B * I, N, c.pairs, c.n_pairs, N, nullptr, c.flooring, c.eps, st));
+  return ssbk_mnmf_spatial(p->Xk, p->T, p->V, lam, p->Wk, p->variance, p->rowloss, B, N, I, J, K, 1, st);
 }
 
 int mnmf_normalize(ssb_plan* p, bool have_zsum, cudaStream_t st) {
   const ssb_config& c = p->cfg;
   const int B = c.n_batch, N = c.n_sources, I = c.n_bins, J = c.n_frames, K = c.n_basis;
-  if (!have_zsum) TRY(ssbk_mnmf_spatial(p->X, p->T, p->V, nullptr, p->W, p->variance, p->rowloss, B, N, I, J, K, 0, st));
-  return ssbk_mnmf_normalize(p->rowloss, p->W, p->variance, B, N, I, J, c.flooring, c.eps, st);
+  if (!have_zsum) TRY(ssbk_mnmf_spatial(p->Xk, p->T, p->V, nullptr, p->Wk, p->variance, p->rowloss, B, N, I, J, K, 0, st));
+  return ssbk_mnmf_normalize(p->rowloss, p->Wk, p->variance, B, N, I, J, c.flooring, c.eps, st);
 }
 
 int mnmf_loss(ssb_plan* p, double* loss, cudaStream_t st) {
@@ -558,8 +599,9 @@ int mnmf_loss(ssb_plan* p, double* loss, cudaStream_t st) {
   const int B = c.n_batch, N = c.n_sources, I = c.n_bins, J = c.n_frames, K = c.n_basis;
   const float* lam;
   TRY(mnmf_lambda(p, &lam, st));
-  TRY(ssbk_mnmf_rowloss(p->X, p->T, p->V, lam, p->W, p->variance, p->rowloss, B, N, I, J, K, st));
-  TRY(ssbk_logdet(p->W, p->logdet, B * I, N, st));
+  TRY(ssbk_mnmf_rowloss(p->Xk, p->T, p->V, lam, p->Wk, p->variance, p->rowloss, B, N, I, J, K, st));
+  TRY(ssbk_logdet(p->Wk, p->logdet, B * I, N, st));
+  if (p->whiten) TRY(ssbk_add_logdet(p->logdet, p->ldM, B * I, st));
   return ssbk_ilrma_loss_reduce(p->rowloss, p->logdet, loss, B, 1, I, st);
 }
 
@@ -609,6 +651,8 @@ extern "C" int ssb_plan_bind(ssb_plan* p, const void* X, void* W, void* Y, void*
   p->ws = (char*)workspace;
   p->ws_bytes = workspace_bytes;
   carve(p, p->ws);
+  p->Xk = p->whiten ? p->Xw : p->X;
+  p->Wk = p->whiten ? p->Ww : p->W;
   p->bound = true;
   p->prepared = false;
   return 0;
@@ -626,21 +670,27 @@ extern "C" int ssb_plan_prepare(ssb_plan* p, void* stream) {
   TRY(require_bound(p));
   const ssb_config& c = p->cfg;
   cudaStream_t st = (cudaStream_t)stream;
+  if (p->whiten) {
+    // C = L L^H in fp64, Z = L^-1 X: the slab every kernel of the iteration reads from now on (ssb_whiten.cu)
+    TRY(ssbk_whiten_prepare(p->X, p->C64, p->Mw, p->Mwinv, p->ldM, p->Xw, p->wsync, c.n_batch, c.n_sources, c.n_bins,
+                            c.n_frames, st));
+  }
   if (p->mnmf()) {
     p->prepared = true;
     return 0;
   }
   if (p->ilrma() && !p->iss()) {
     // C_i = mean_j x x^H, constant over the iterations
-    TRY(ssbk_wcov(p->X, nullptr, 0, 0, 0, nullptr, 1, p->C, c.n_batch, c.n_sources, c.n_bins, c.n_frames, st));
+    TRY(ssbk_wcov(p->Xk, nullptr, 0, 0, 0, nullptr, 1, p->C, c.n_batch, c.n_sources, c.n_bins, c.n_frames, st));
   }
-  TRY(ssb_fused_prepare(&p->fused, &c, p->X, st));
+  TRY(ssb_fused_prepare(&p->fused, &c, p->Xk, st));
   p->prepared = true;
   return 0;
 }
 
 extern "C" int ssb_update_source_model(ssb_plan* p, void* stream) {
   TRY(require_bound(p));
+  TRY(w_enter(p, (cudaStream_t)stream));
   if (p->mnmf()) return mnmf_source(p, (cudaStream_t)stream);
   if (p->fdica()) return 0;  // no source parameters
   return p->ilrma() ? ilrma_source(p, (cudaStream_t)stream) : iva_source(p, (cudaStream_t)stream);
@@ -650,24 +700,40 @@ extern "C" int ssb_update_source_part(ssb_plan* p, int part, void* stream) {
   TRY(require_bound(p));
   SSB_REQUIRE(p->ilrma(), "update_source_part is defined for the ILRMA family only");
   p->fused.vs_valid = false;
+  TRY(w_enter(p, (cudaStream_t)stream));
   return ilrma_source_substep(p, part, (cudaStream_t)stream);
 }
 
 extern "C" int ssb_update_spatial_model(ssb_plan* p, void* stream) {
   TRY(require_bound(p));
-  if (p->mnmf()) return mnmf_spatial(p, (cudaStream_t)stream);
-  if (p->fdica()) return fdica_spatial(p, (cudaStream_t)stream);
-  return p->ilrma() ? ilrma_spatial(p, (cudaStream_t)stream) : iva_spatial(p, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  TRY(w_enter(p, st));
+  if (p->mnmf()) TRY(mnmf_spatial(p, st));
+  else if (p->fdica()) TRY(fdica_spatial(p, st));
+  else TRY(p->ilrma() ? ilrma_spatial(p, st) : iva_spatial(p, st));
+  return w_exit(p, st);
 }
 
 extern "C" int ssb_normalize(ssb_plan* p, void* stream) {
   TRY(require_bound(p));
-  if (p->mnmf()) return mnmf_normalize(p, false, (cudaStream_t)stream);
-  SSB_REQUIRE(p->ilrma(), "normalize is defined for ILRMA only");
-  return ilrma_normalize(p, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  TRY(w_enter(p, st));
+  if (p->mnmf()) {
+    TRY(mnmf_normalize(p, false, st));
+  } else {
+    SSB_REQUIRE(p->ilrma(), "normalize is defined for ILRMA only");
+    TRY(ilrma_normalize(p, st));
+  }
+  return w_exit(p, st);
 }
 
 namespace {
+int loss_impl(ssb_plan* p, double* loss, cudaStream_t st) {
+  if (p->mnmf()) return mnmf_loss(p, loss, st);
+  if (p->fdica()) return fdica_loss(p, loss, st);
+  return p->ilrma() ? ilrma_loss(p, loss, st) : iva_loss(p, loss, st);
+}
+
 int update_once_impl(ssb_plan* p, cudaStream_t st) {
   if (p->mnmf()) {  // mnmf.py:1278-1303
     TRY(mnmf_source(p, st));
@@ -694,7 +760,7 @@ int update_once_impl(ssb_plan* p, cudaStream_t st) {
     }
     if (p->cfg.fast_path && ssb_fused_supported(&p->cfg)) {
       const ssb_config& c = p->cfg;
-      TRY(ssb_fused_source_and_cov(&c, &p->fused, p->X, p->W, p->T, p->V, p->big, p->U, st));
+      TRY(ssb_fused_source_and_cov(&c, &p->fused, p->Xk, p->Wk, p->T, p->V, p->big, p->U, st));
       // power normalisation without a pass over X: the IP kernels emit q[b,i,n] = Re(w_n C_i w_n^H) and one small
       // kernel reduces it over the bins and rescales T and W
       const bool pw = c.normalization == SSB_NORM_POWER;
@@ -702,15 +768,15 @@ int update_once_impl(ssb_plan* p, cudaStream_t st) {
       const cf* Cq = pw ? p->C : nullptr;
       if (c.spatial == SSB_SPATIAL_IP1) {
         if (c.n_sources == 2)
-          TRY(ssb_fused_ip1_n2(p->W, p->U, Cq, p->rowloss, c.n_batch * c.n_bins, c.flooring, c.eps, st));
+          TRY(ssb_fused_ip1_n2(p->Wk, p->U, Cq, p->rowloss, c.n_batch * c.n_bins, c.flooring, c.eps, st));
         else
-          TRY(ssbk_ip1(p->W, p->U, c.n_batch * c.n_bins, c.n_sources, c.flooring, c.eps, st, Cq, p->rowloss));
+          TRY(ssbk_ip1(p->Wk, p->U, c.n_batch * c.n_bins, c.n_sources, c.flooring, c.eps, st, Cq, p->rowloss));
       } else {
-        TRY(ssbk_ip2(p->W, p->U, c.n_batch * c.n_bins, c.n_sources, c.pairs, c.n_pairs, c.n_sources, nullptr,
+        TRY(ssbk_ip2(p->Wk, p->U, c.n_batch * c.n_bins, c.n_sources, c.pairs, c.n_pairs, c.n_sources, nullptr,
                      c.flooring, c.eps, st, Cq, p->rowloss));
       }
       if (pw)
-        return ssb_fused_normalize(p->rowloss, p->T, p->W, c.n_batch, c.n_sources, c.n_bins, c.n_basis, c.domain,
+        return ssb_fused_normalize(p->rowloss, p->T, p->Wk, c.n_batch, c.n_sources, c.n_bins, c.n_basis, c.domain,
                                    c.flooring, c.eps, st);
       if (c.normalization != SSB_NORM_NONE) TRY(ilrma_normalize(p, st));
       return 0;
@@ -730,15 +796,16 @@ extern "C" int ssb_update_once(ssb_plan* p, void* stream) {
   TRY(require_bound(p));
   // the caller may have rewritten V since the last call: the pre-split copy is only trusted inside ssb_run
   p->fused.vs_valid = false;
-  return update_once_impl(p, (cudaStream_t)stream);
+  TRY(w_enter(p, (cudaStream_t)stream));
+  TRY(update_once_impl(p, (cudaStream_t)stream));
+  return w_exit(p, (cudaStream_t)stream);
 }
 
 extern "C" int ssb_compute_loss(ssb_plan* p, double* loss, void* stream) {
   TRY(require_bound(p));
   SSB_REQUIRE(loss != nullptr, "loss output is NULL");
-  if (p->mnmf()) return mnmf_loss(p, loss, (cudaStream_t)stream);
-  if (p->fdica()) return fdica_loss(p, loss, (cudaStream_t)stream);
-  return p->ilrma() ? ilrma_loss(p, loss, (cudaStream_t)stream) : iva_loss(p, loss, (cudaStream_t)stream);
+  TRY(w_enter(p, (cudaStream_t)stream));
+  return loss_impl(p, loss, (cudaStream_t)stream);
 }
 
 namespace {
@@ -755,17 +822,17 @@ int run_fused_iterations(ssb_plan* p, int n_iter, cudaStream_t st) {
   const ssb_config& c = p->cfg;
   const bool pw = c.normalization == SSB_NORM_POWER;
   SSB_REQUIRE(!pw || p->prepared, "plan not prepared (call ssb_plan_prepare after bind)");
-  TRY(ssb_fused_source_and_cov(&c, &p->fused, p->X, p->W, p->T, p->V, p->big, p->U, st, 1));
+  TRY(ssb_fused_source_and_cov(&c, &p->fused, p->Xk, p->Wk, p->T, p->V, p->big, p->U, st, 1));
   for (int it = 1; it < n_iter; ++it) {
-    TRY(ssb_fused_spatial_source(&c, &p->fused, p->X, p->W, p->T, p->V, p->big, p->rowloss, st));
+    TRY(ssb_fused_spatial_source(&c, &p->fused, p->Xk, p->Wk, p->T, p->V, p->big, p->rowloss, st));
     if (pw)
-      TRY(ssb_fused_normalize(p->rowloss, p->T, p->W, c.n_batch, c.n_sources, c.n_bins, c.n_basis, c.domain, c.flooring,
+      TRY(ssb_fused_normalize(p->rowloss, p->T, p->Wk, c.n_batch, c.n_sources, c.n_bins, c.n_basis, c.domain, c.flooring,
                               c.eps, st));
   }
-  TRY(ssb_fused_source_and_cov(&c, &p->fused, p->X, p->W, p->T, p->V, p->big, p->U, st, 2));
-  TRY(ssb_fused_ip1_n2(p->W, p->U, pw ? p->C : nullptr, p->rowloss, c.n_batch * c.n_bins, c.flooring, c.eps, st));
+  TRY(ssb_fused_source_and_cov(&c, &p->fused, p->Xk, p->Wk, p->T, p->V, p->big, p->U, st, 2));
+  TRY(ssb_fused_ip1_n2(p->Wk, p->U, pw ? p->C : nullptr, p->rowloss, c.n_batch * c.n_bins, c.flooring, c.eps, st));
   if (pw)
-    TRY(ssb_fused_normalize(p->rowloss, p->T, p->W, c.n_batch, c.n_sources, c.n_bins, c.n_basis, c.domain, c.flooring,
+    TRY(ssb_fused_normalize(p->rowloss, p->T, p->Wk, c.n_batch, c.n_sources, c.n_bins, c.n_basis, c.domain, c.flooring,
                             c.eps, st));
   return 0;
 }
@@ -774,30 +841,37 @@ int run_fused_iterations(ssb_plan* p, int n_iter, cudaStream_t st) {
 extern "C" int ssb_run(ssb_plan* p, int n_iter, double* loss, void* stream) {
   TRY(require_bound(p));
   p->fused.vs_valid = false;
+  if (n_iter <= 0) return 0;
+  // the whole loop stays in the whitened domain: one import before, one export after
+  TRY(w_enter(p, (cudaStream_t)stream));
   if (loss == nullptr && n_iter >= 2 && p->ilrma() && p->cfg.fast_path && !p->iss() &&
       ssb_fused_iter_fusable(&p->cfg, &p->fused) && fuse_iter_enabled()) {
     const int rc = run_fused_iterations(p, n_iter, (cudaStream_t)stream);
     p->fused.vs_valid = false;
-    return rc;
+    if (rc) return rc;
+    return w_exit(p, (cudaStream_t)stream);
   }
   for (int it = 0; it < n_iter; ++it) {
     TRY(update_once_impl(p, (cudaStream_t)stream));
-    if (loss) TRY(ssb_compute_loss(p, loss + (size_t)it * p->cfg.n_batch, stream));
+    if (loss) TRY(loss_impl(p, loss + (size_t)it * p->cfg.n_batch, (cudaStream_t)stream));
   }
   p->fused.vs_valid = false;
-  return 0;
+  return w_exit(p, (cudaStream_t)stream);
 }
 
 extern "C" int ssb_plan_separate(ssb_plan* p, void* stream) {
   TRY(require_bound(p));
+  TRY(w_enter(p, (cudaStream_t)stream));
   if (p->mnmf()) {  // multichannel Wiener filter, mnmf.py:1174-1217
     const ssb_config& c = p->cfg;
-    return ssbk_mnmf_separate(p->X, p->T, p->V, p->W, p->variance, p->qinv, p->Y, c.n_batch, c.n_sources, c.n_bins,
-                              c.n_frames, c.n_basis, c.reference_id, c.flooring, c.eps, (cudaStream_t)stream);
+    // the filter acts on the mixture itself: Q^-1 = M^-1 Q~^-1 in fp64, X in the caller's domain
+    return ssbk_mnmf_separate(p->X, p->T, p->V, p->Wk, p->variance, p->qinv, p->Y, c.n_batch, c.n_sources, c.n_bins,
+                              c.n_frames, c.n_basis, c.reference_id, c.flooring, c.eps, (cudaStream_t)stream,
+                              p->whiten ? p->Mwinv : nullptr);
   }
   if (p->iss()) return 0;
   const ssb_config& c = p->cfg;
-  return ssbk_separate(p->X, p->W, p->Y, nullptr, c.n_batch, c.n_sources, c.n_bins, c.n_frames, (cudaStream_t)stream);
+  return ssbk_separate(p->Xk, p->Wk, p->Y, nullptr, c.n_batch, c.n_sources, c.n_bins, c.n_frames, (cudaStream_t)stream);
 }
 
 extern "C" int ssb_restore_scale(ssb_plan* p, void* stream) {
@@ -807,11 +881,14 @@ extern "C" int ssb_restore_scale(ssb_plan* p, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const int B = c.n_batch, N = c.n_sources, I = c.n_bins, J = c.n_frames;
   if (p->iss()) {
-    TRY(ssbk_cross_solve(p->X, p->Y, p->S, B, N, I, J, st));
+    TRY(ssbk_cross_solve(p->Xk, p->Y, p->S, B, N, I, J, st));
     return ssbk_scale_rows(p->Y, p->S, p->Y, B, N, I, J, c.reference_id, st);
   }
-  TRY(ssbk_pb_w(p->W, p->W, nullptr, B * I, N, c.reference_id, st));
-  return ssbk_separate(p->X, p->W, p->Y, nullptr, B, N, I, J, st);
+  TRY(w_enter(p, st));
+  if (p->whiten) TRY(ssbk_pb_whitened(p->Wk, p->Mwinv, nullptr, B * I, N, c.reference_id, st));
+  else TRY(ssbk_pb_w(p->Wk, p->Wk, nullptr, B * I, N, c.reference_id, st));
+  TRY(w_exit(p, st));
+  return ssbk_separate(p->Xk, p->Wk, p->Y, nullptr, B, N, I, J, st);
 }
 
 // restore_scale with the minimal distortion principle (ilrma.py:567-579, :1981-1989; iva.py:269-281,
@@ -822,7 +899,12 @@ extern "C" int ssb_restore_scale_mdp(ssb_plan* p, void* stream) {
   const ssb_config& c = p->cfg;
   cudaStream_t st = (cudaStream_t)stream;
   const int B = c.n_batch, N = c.n_sources, I = c.n_bins, J = c.n_frames;
-  if (!p->iss()) TRY(ssbk_separate(p->X, p->W, p->Y, nullptr, B, N, I, J, st));
+  if (!p->iss()) {
+    TRY(w_enter(p, st));
+    TRY(ssbk_separate(p->Xk, p->Wk, p->Y, nullptr, B, N, I, J, st));
+  }
+  // the reference channel and the refit are in the caller's domain: X and W, not their whitened images (the next
+  // entry point re-imports W because it no longer matches the last export)
   TRY(ssbk_mdp(p->Y, p->X, p->Y, B, N, I, J, c.reference_id, st));
   if (!p->iss()) TRY(ssbk_cross_solve(p->Y, p->X, p->W, B, N, I, J, st));
   return 0;
@@ -915,18 +997,22 @@ extern "C" int ssb_permutation_align(void* Y, void* W, const int32_t* order, int
 extern "C" int ssb_plan_permutation_correlation(ssb_plan* p, double* corr, void* stream) {
   TRY(require_bound(p));
   const ssb_config& c = p->cfg;
-  SSB_REQUIRE(p->W != nullptr && corr != nullptr, "permutation alignment needs demixing filters");
+  SSB_REQUIRE(p->Wk != nullptr && corr != nullptr, "permutation alignment needs demixing filters");
   cudaStream_t st = (cudaStream_t)stream;
-  TRY(ssbk_separate(p->X, p->W, p->Y, nullptr, c.n_batch, c.n_sources, c.n_bins, c.n_frames, st));
+  TRY(w_enter(p, st));
+  TRY(ssbk_separate(p->Xk, p->Wk, p->Y, nullptr, c.n_batch, c.n_sources, c.n_bins, c.n_frames, st));
   return ssbk_perm_corr(p->Y, corr, c.n_batch, c.n_sources, c.n_bins, c.n_frames, c.flooring, c.eps, st);
 }
 
 extern "C" int ssb_plan_permutation_align(ssb_plan* p, const int32_t* order, int32_t* perms, void* stream) {
   TRY(require_bound(p));
   const ssb_config& c = p->cfg;
-  SSB_REQUIRE(p->W != nullptr && order != nullptr && perms != nullptr, "NULL argument");
-  return ssbk_perm_align(p->Y, p->W, order, perms, c.n_batch, c.n_sources, c.n_bins, c.n_frames, c.flooring, c.eps,
-                         (cudaStream_t)stream);
+  SSB_REQUIRE(p->Wk != nullptr && order != nullptr && perms != nullptr, "NULL argument");
+  TRY(w_enter(p, (cudaStream_t)stream));
+  // a row permutation of W is the same row permutation of W~ = W M^-1
+  TRY(ssbk_perm_align(p->Y, p->Wk, order, perms, c.n_batch, c.n_sources, c.n_bins, c.n_frames, c.flooring, c.eps,
+                      (cudaStream_t)stream));
+  return w_exit(p, (cudaStream_t)stream);
 }
 
 extern "C" int ssb_projection_back_w(const void* W, void* Wout, int n_mat, int N, int reference_id, void* stream) {

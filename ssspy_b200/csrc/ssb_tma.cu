@@ -1,0 +1,749 @@
+// TMA-fed tile kernels of the GaussILRMA iteration (source_algorithm="MM", domain=2; N = 2, 4, 8).
+//
+//   kt_tile<N, KS, MODE, TB>   CTA = TB tiles of 16 bins x ALL sources x FS = 8 / N frame ranges: consumer warp
+//                              (tile, frame range fq, source n) + one producer warp
+//     MODE_BASIS  T <- T sqrt(sum_j V P / R^2 / sum_j V / R), P = |w_n^H x|^2, R = T V   (ssspy/bss/ilrma.py:1051-1128)
+//     MODE_COV    phi = 1 / (T V), U_n = mean_j phi x x^H                                  (ilrma.py:1494-1505), N = 2
+//     MODE_FUSED  MODE_COV of iteration t, IP1 in fp64 (_update_spatial_model.py:63-76), then MODE_BASIS of iteration
+//                 t + 1 with the new filter on the SAME tile (N = 2, inside ssb_run only)
+//
+// Data movement is Blackwell-native: the (channel x frame) slab of a tile is pulled by the producer warp with
+// cp.async.bulk.tensor (TMA, one tensor map over X[B*N planes][I rows][2 J floats], box = 8 frames x 16 bins x N
+// channels) into a 3-stage shared-memory ring guarded by mbarriers (full: complete_tx, empty: one arrive per source
+// warp); the pre-split activation chunks travel as 1-D bulk copies into per-warp double buffers.  Consumer warps issue
+// no global loads at all in their frame loops: ldmatrix + LDS.128 + mma.sync + the elementwise stage.  A box lands as
+// [channel][16 rows][64 bytes]; a quarter warp's LDS.128 (2 rows x 4 frame pairs) covers 128 contiguous bytes, so the
+// layout is bank-conflict free without a swizzle, and rows past the last bin are zero-filled by the TMA unit.
+//
+// Why the frames of a tile are split over warps (FS ranges): in MODE_FUSED the tile's slab is read twice, once for the
+// covariance and once, after IP1, for the basis update.  With one warp per (tile, source) sweeping all frames, the
+// slabs waiting between their two passes (148 SMs x 16 warps x 64 KB = 155 MB at N = 2, J = 512) exceed the 126 MB L2
+// and the second pass goes back to HBM (round 1: 0.335 vs 0.345 ms, profiles/r1_fuse_iter_ab.jsonl).  With the frames
+// split four ways a CTA finishes a tile's first pass after a quarter of the bytes per warp: 39 MB in flight, and the
+// second pass is served by L2.  The per-range partial sums (U, then num / den) are combined through shared memory in a
+// fixed order, so results do not depend on scheduling.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <stdlib.h>
+
+#include <mutex>
+
+#include "ssb_fused.h"
+#include "ssb_kernels.h"
+
+namespace {
+
+constexpr int PADH = 8;   // bf16 padding of a [frame][basis] row (see ssb_coop.cu)
+constexpr int JCV = 32;   // frames per pre-split V chunk
+constexpr int XS = 3;     // stages of an X ring (16 frames each)
+constexpr int MODE_BASIS = 0, MODE_COV = 1, MODE_FUSED = 2;
+
+struct Split {
+  uint32_t hi, lo;
+};
+__device__ __forceinline__ Split split2(float a, float b) {
+  const uint32_t ua = __float_as_uint(a), ub = __float_as_uint(b);
+  Split s;
+  s.hi = __byte_perm(ua, ub, 0x7632);
+  const float ra = a - __uint_as_float(ua & 0xffff0000u);
+  const float rb = b - __uint_as_float(ub & 0xffff0000u);
+  __nv_bfloat162 l = __floats2bfloat162_rn(ra, rb);
+  s.lo = *reinterpret_cast<uint32_t*>(&l);
+  return s;
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma_split(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                          uint32_t bh0, uint32_t bh1, uint32_t bl0, uint32_t bl1) {
+  mma16816(c, ah, bh0, bh1);
+  mma16816(c, ah, bl0, bl1);
+  mma16816(c, al, bh0, bh1);
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr)
+               : "memory");
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr)
+               : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t pin(uint32_t v) {
+  asm volatile("" : "+r"(v));
+  return v;
+}
+template <typename T>
+__device__ __forceinline__ T* pin_ptr(T* p) {
+  asm volatile("" : "+l"(p));
+  return p;
+}
+
+// ---- mbarrier + TMA (PTX ISA 8.x, sm_90+) ------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// one box of the X tensor map: coordinates (float index in the row, bin, plane)
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_hint(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar,
+                                                 uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, "
+      "%3, %4}], [%5], %6;"
+      ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar), "l"(policy)
+      : "memory");
+}
+// contiguous bytes (multiple of 16, 16-byte aligned on both sides)
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+template <int NT>
+__device__ __forceinline__ void bar_sync_id(int id) {  // named barrier 1 + id over NT threads
+  asm volatile("bar.sync %0, %1;" ::"r"(id + 1), "n"(NT) : "memory");
+}
+
+// |sum_m w[m] x[m]|^2 for two consecutive frames held in a float4 per channel
+template <int N>
+__device__ __forceinline__ void power2(const float4 (&x)[N], const cf (&w)[N], float& p0, float& p1) {
+  float r0 = 0.f, i0 = 0.f, r1 = 0.f, i1 = 0.f;
+#pragma unroll
+  for (int m = 0; m < N; ++m) {
+    r0 = fmaf(w[m].x, x[m].x, fmaf(-w[m].y, x[m].y, r0));
+    i0 = fmaf(w[m].x, x[m].y, fmaf(w[m].y, x[m].x, i0));
+    r1 = fmaf(w[m].x, x[m].z, fmaf(-w[m].y, x[m].w, r1));
+    i1 = fmaf(w[m].x, x[m].w, fmaf(w[m].y, x[m].z, i1));
+  }
+  p0 = fmaf(r0, r0, i0 * i0);
+  p1 = fmaf(r1, r1, i1 * i1);
+}
+
+template <int N, int KS, int TB>
+struct TileShape {
+  static constexpr int FS = 8 / N;               // frame ranges per tile
+  static constexpr int NCW = 8 * TB;             // consumer warps
+  static constexpr int NT = (NCW + 1) * 32;      // + the producer warp
+  static constexpr int KP = 16 * KS, JKS = KP + PADH;
+  static constexpr int CHB = 2 * JCV * JKS * 2;  // bytes of one V chunk (hi + lo)
+  static constexpr int XSB = N * 2048;           // bytes of one X stage: 16 frames x 16 bins x N channels
+  static constexpr int X_BYTES = TB * FS * XS * XSB;
+  static constexpr int V_BYTES = NCW * 2 * CHB;
+  static constexpr int NBAR = TB * FS * XS * 2 + NCW * 2 * 2;
+  static constexpr int U_BYTES = TB * 2 * 4 * 16 * 4 * 4;  // MODE_COV / FUSED (N = 2): [tile][source][fq][row][4] floats
+  static constexpr int SMEM = X_BYTES + V_BYTES + U_BYTES + NBAR * 8 + 128;
+  static_assert(N == 2 || N == 4 || N == 8, "N = 2, 4, 8");
+};
+
+// Fragment conventions as in ssb_coop.cu (PTX m16n8k16): g = lane / 4, t = lane % 4; C: (row g, cols 2t, 2t+1),
+// (row g + 8, same); A: a0 (row g, k 2t..), a1 (row g+8, k 2t..), a2 (row g, k 2t+8..), a3; B: b0 (k 2t.., n g), b1.
+template <int N, int KS, int MODE, int TB>
+__global__ void __launch_bounds__(TileShape<N, KS, TB>::NT, TB == 1 ? 2 : 1)
+    kt_tile(const __grid_constant__ CUtensorMap tmX, cf* Wrw, float* __restrict__ T,
+            const __nv_bfloat16* __restrict__ Vs, float* __restrict__ Pout, __nv_bfloat16* __restrict__ Ts,
+            cf* __restrict__ U, double* __restrict__ q, int I, int J, int K, int nchunk, int nchunk_i, int flooring,
+            float eps) {
+  using S = TileShape<N, KS, TB>;
+  constexpr int FS = S::FS, NCW = S::NCW, JKS = S::JKS, CHB = S::CHB, XSB = S::XSB;
+  static_assert(MODE == MODE_BASIS || N == 2, "the covariance modes are written for two sources");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const uint32_t smem_s = (uint32_t)__cvta_generic_to_shared(smem_raw);
+  const uint32_t xring_s = smem_s;                          // [tile][fq][stage][XSB]
+  const uint32_t vring_s = smem_s + S::X_BYTES;             // [warp][2][CHB]; later the combine scratch
+  float* ucomb = reinterpret_cast<float*>(smem_raw + S::X_BYTES + S::V_BYTES);
+  const uint32_t bars_s = smem_s + S::X_BYTES + S::V_BYTES + S::U_BYTES;
+  // barrier index helpers (8 bytes each)
+  auto xfull = [&](int tb, int fq, int st) { return bars_s + (uint32_t)((((tb * FS + fq) * XS + st) * 2 + 0) * 8); };
+  auto xempty = [&](int tb, int fq, int st) { return bars_s + (uint32_t)((((tb * FS + fq) * XS + st) * 2 + 1) * 8); };
+  auto vfull = [&](int w, int st) { return bars_s + (uint32_t)((TB * FS * XS * 2 + (w * 2 + st) * 2 + 0) * 8); };
+  auto vempty = [&](int w, int st) { return bars_s + (uint32_t)((TB * FS * XS * 2 + (w * 2 + st) * 2 + 1) * 8); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int nsteps = J >> 4;
+  const int cq = (nchunk + FS - 1) / FS;  // chunks (32 frames) per frame range
+  constexpr int NPASS = MODE == MODE_FUSED ? 2 : 1;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int tb = 0; tb < TB; ++tb)
+#pragma unroll
+      for (int fq = 0; fq < FS; ++fq)
+#pragma unroll
+        for (int st = 0; st < XS; ++st) {
+          mbar_init(xfull(tb, fq, st), 1);
+          mbar_init(xempty(tb, fq, st), N);
+        }
+    for (int w = 0; w < NCW; ++w)
+      for (int st = 0; st < 2; ++st) {
+        mbar_init(vfull(w, st), 1);
+        mbar_init(vempty(w, st), 1);
+      }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // =================================== producer warp ===================================
+  if (warp == NCW) {
+    if (lane != 0) return;
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+    const uint64_t pol = l2_evict_first_policy();
+    int xcnt[TB][FS], vcnt[TB][FS];  // fills issued so far per X ring / per V ring of a frame range (same for its N warps)
+#pragma unroll
+    for (int tb = 0; tb < TB; ++tb)
+#pragma unroll
+      for (int fq = 0; fq < FS; ++fq) xcnt[tb][fq] = vcnt[tb][fq] = 0;
+    const unsigned char* vsrc = reinterpret_cast<const unsigned char*>(Vs);
+#pragma unroll 1
+    for (int pass = 0; pass < NPASS; ++pass) {
+      const bool last_use = pass == NPASS - 1;  // X is read for the last time: do not let it displace waiting slabs
+#pragma unroll 1
+      for (int ci = 0; ci < cq; ++ci) {
+#pragma unroll
+        for (int tb = 0; tb < TB; ++tb) {
+          const int i0 = (blockIdx.x * TB + tb) * 16;
+          if (i0 >= I) continue;
+#pragma unroll
+          for (int fq = 0; fq < FS; ++fq) {
+            const int c = fq * cq + ci;
+            if (c >= min((fq + 1) * cq, nchunk)) continue;
+            {  // the chunk of every source warp of this frame range
+              const int k = vcnt[tb][fq]++;
+              const int st = k & 1;
+#pragma unroll
+              for (int n = 0; n < N; ++n) {
+                const int w = (tb * FS + fq) * N + n;
+                if (k >= 2) mbar_wait(vempty(w, st), ((k >> 1) - 1) & 1);
+                mbar_expect_tx(vfull(w, st), CHB);
+                bulk_load(vring_s + (uint32_t)((w * 2 + st) * CHB), vsrc + (((size_t)b * N + n) * nchunk + c) * (size_t)CHB,
+                          CHB, vfull(w, st));
+              }
+            }
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              const int s = 2 * c + half;
+              if (s >= nsteps) break;
+              const int k = xcnt[tb][fq]++;
+              const int st = k % XS;
+              if (k >= XS) mbar_wait(xempty(tb, fq, st), ((k / XS) - 1) & 1);
+              const uint32_t dst = xring_s + (uint32_t)(((tb * FS + fq) * XS + st) * XSB);
+              mbar_expect_tx(xfull(tb, fq, st), XSB);
+              if (last_use) {
+                tma_load_3d_hint(dst, &tmX, 32 * s, i0, b * N, xfull(tb, fq, st), pol);
+                tma_load_3d_hint(dst + N * 1024, &tmX, 32 * s + 16, i0, b * N, xfull(tb, fq, st), pol);
+              } else {
+                tma_load_3d(dst, &tmX, 32 * s, i0, b * N, xfull(tb, fq, st));
+                tma_load_3d(dst + N * 1024, &tmX, 32 * s + 16, i0, b * N, xfull(tb, fq, st));
+              }
+            }
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // =================================== consumer warps ===================================
+  const int g = lane >> 2, t = lane & 3;
+  const int tb = warp >> 3, wl = warp & 7;
+  const int fq = wl / N, n = wl - fq * N;
+  const int i0 = (blockIdx.x * TB + tb) * 16;
+  const bool tile_active = i0 < I;  // (TB == 2, last CTA) an inactive tile still takes part in nothing: its warps leave
+  if (!tile_active) return;
+  const int row[2] = {i0 + g, i0 + g + 8};
+  const bool rvalid[2] = {row[0] < I, row[1] < I};
+  const int rowc[2] = {min(row[0], I - 1), min(row[1], I - 1)};
+  const size_t bn = (size_t)b * N + n;
+  const int c_lo = fq * cq, c_hi = min((fq + 1) * cq, nchunk);
+
+  uint32_t Thi[KS][4], Tlo[KS][4];
+  float Told[KS][2][2][2];  // [ks][nb][rr][e]: basis ks*16 + nb*8 + 2t + e, row rr
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const float* tr = T + (bn * I + rowc[rr]) * K;
+#pragma unroll
+      for (int nb = 0; nb < 2; ++nb) {
+        const int k0 = ks * 16 + nb * 8 + 2 * t;
+        const float v0 = (k0 < K) ? tr[k0] : 0.f;
+        const float v1 = (k0 + 1 < K) ? tr[k0 + 1] : 0.f;
+        Told[ks][nb][rr][0] = v0;
+        Told[ks][nb][rr][1] = v1;
+        const Split s = split2(v0, v1);
+        Thi[ks][nb * 2 + rr] = s.hi;
+        Tlo[ks][nb * 2 + rr] = s.lo;
+      }
+    }
+
+  // per-lane shared-memory offsets: X fragment (row g + 8 rr, frames 8 h + 2 t ..) of channel m sits at
+  //   stage + h * (N * 1024) + m * 1024 + (g + 8 rr) * 64 + t * 16
+  const uint32_t xlane = pin(xring_s + (uint32_t)((tb * FS + fq) * XS * XSB) + g * 64 + t * 16);
+  const uint32_t vs_s = vring_s + (uint32_t)(warp * 2 * CHB);
+  const int mid = lane >> 3, mrow = lane & 7;
+  // GEMM1 (non-trans): matrices (hi k0-7, hi k8-15, lo k0-7, lo k8-15) of frames [.., +8)
+  const uint32_t l1base = pin(vs_s + (mid >> 1) * (JCV * JKS * 2) + (mrow * JKS + (mid & 1) * 8) * 2);
+  // GEMM2 (trans): matrices (hi frames 0-7, hi frames 8-15, lo 0-7, lo 8-15) of basis [.., +8)
+  const uint32_t l2base = pin(vs_s + (mid >> 1) * (JCV * JKS * 2) + (((mid & 1) * 8 + mrow) * JKS) * 2);
+
+  int xk = 0, vk = 0;  // stages / chunks consumed so far by this warp (ring positions and phases)
+  cf w[2][N];          // rows g, g + 8 of W: the filter of source n
+
+  // ======================= pass 0: weighted covariance of source n (N = 2) =======================
+  if constexpr (MODE != MODE_BASIS) {
+    float ua[2][4];  // [rr]: U00, U11, Re U01, Im U01   (U_ac = sum phi x_a conj(x_c))
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) ua[rr][c] = 0.f;
+#pragma unroll 1
+    for (int c = c_lo; c < c_hi; ++c) {
+      const int vst = vk & 1;
+      mbar_wait(vfull(warp, vst), (vk >> 1) & 1);
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        const int s = 2 * c + half;
+        if (s >= nsteps) break;
+        const int xst = xk % XS;
+        mbar_wait(xfull(tb, fq, xst), (xk / XS) & 1);
+        const uint32_t vb1 = l1base + vst * CHB + half * (16 * JKS * 2);
+        const uint32_t xb = xlane + xst * XSB;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float R[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks) {
+            uint32_t bh0, bh1, bl0, bl1;
+            ldsm_x4(bh0, bh1, bl0, bl1, vb1 + (8 * h * JKS + ks * 16) * 2);
+            mma_split(R, Thi[ks], Tlo[ks], bh0, bh1, bl0, bl1);
+          }
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr) {
+            const float4 x0 = lds128(xb + h * (N * 1024) + rr * 512);
+            const float4 x1 = lds128(xb + h * (N * 1024) + 1024 + rr * 512);
+            const float f0 = fast_rcp(R[rr * 2 + 0]), f1 = fast_rcp(R[rr * 2 + 1]);  // no floor on R (ilrma.py:1494-1498)
+            ua[rr][0] = fmaf(f0, fmaf(x0.x, x0.x, x0.y * x0.y), fmaf(f1, fmaf(x0.z, x0.z, x0.w * x0.w), ua[rr][0]));
+            ua[rr][1] = fmaf(f0, fmaf(x1.x, x1.x, x1.y * x1.y), fmaf(f1, fmaf(x1.z, x1.z, x1.w * x1.w), ua[rr][1]));
+            ua[rr][2] = fmaf(f0, fmaf(x0.x, x1.x, x0.y * x1.y), fmaf(f1, fmaf(x0.z, x1.z, x0.w * x1.w), ua[rr][2]));
+            ua[rr][3] = fmaf(f0, fmaf(x0.y, x1.x, -x0.x * x1.y), fmaf(f1, fmaf(x0.w, x1.z, -x0.z * x1.w), ua[rr][3]));
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(xempty(tb, fq, xst));
+        ++xk;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(vempty(warp, vst));
+      ++vk;
+    }
+    // partial sums of this frame range -> shared memory ([tile][source][fq][row][4]); combined in fixed order
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float v = ua[rr][c];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        ua[rr][c] = v;
+      }
+    float* uc = ucomb + (size_t)tb * (2 * FS * 16 * 4);
+    if (t == 0) {
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr)
+        *reinterpret_cast<float4*>(uc + ((n * FS + fq) * 16 + g + 8 * rr) * 4) =
+            make_float4(ua[rr][0], ua[rr][1], ua[rr][2], ua[rr][3]);
+    }
+    bar_sync_id<256>(tb);
+    // the lane works on the bin rs of its pair (rows g, g + 8): both covariances, summed over the frame ranges in fp64
+    const int rs = t & 1;
+    const int r16 = g + 8 * rs;
+    const double invJ = 1.0 / (double)J;
+    cd u[2][4];  // [source][u00, u01, u10, u11]
+#pragma unroll
+    for (int sn = 0; sn < 2; ++sn) {
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+      for (int f = 0; f < FS; ++f) {
+        const float4 v = *reinterpret_cast<const float4*>(uc + ((sn * FS + f) * 16 + r16) * 4);
+        a0 += (double)v.x;
+        a1 += (double)v.y;
+        a2 += (double)v.z;
+        a3 += (double)v.w;
+      }
+      u[sn][0] = cd_make(a0 * invJ, 0.0);
+      u[sn][3] = cd_make(a1 * invJ, 0.0);
+      u[sn][1] = cd_make(a2 * invJ, a3 * invJ);
+      u[sn][2] = cd_make(a2 * invJ, -a3 * invJ);
+    }
+    const bool my_valid = rs ? rvalid[1] : rvalid[0];
+    if constexpr (MODE == MODE_COV) {
+      // U[b, i, n, :, :] complex64 (the consumer is kf_ip1_n2 / kq_ip2)
+      if (fq == 0 && t < 2 && my_valid) {
+        cf* uo = U + (((size_t)b * I + (rs ? row[1] : row[0])) * N + n) * 4;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) uo[e] = cd2cf(u[n][e]);
+      }
+      return;
+    } else {
+      // IP1, n = 0 then n = 1 with the updated row 0, all in fp64 (kf_ip1_n2); every lane of every frame range computes
+      // the same values.  W is written back UNNORMALISED (kf_normalize runs after the activation update, see
+      // ssb_coop.cu kf_cov_ip1_basis for why that order is exact); P below uses the stored complex64 filter.
+      cf* wmat = Wrw + ((size_t)b * I + (rs ? rowc[1] : rowc[0])) * 4;
+      cd wm[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) wm[e] = cf2cd(wmat[e]);
+      if (!my_valid) {  // rows past the last bin see a zero slab: keep their algebra finite (nothing is stored)
+#pragma unroll
+        for (int sn = 0; sn < 2; ++sn) {
+          u[sn][0] = u[sn][3] = cd_make(1.0, 0.0);
+          u[sn][1] = u[sn][2] = cd_make(0.0, 0.0);
+        }
+      }
+#pragma unroll
+      for (int sn = 0; sn < 2; ++sn) {
+        const cd a00 = cd_add(cd_mul(wm[0], u[sn][0]), cd_mul(wm[1], u[sn][2]));
+        const cd a01 = cd_add(cd_mul(wm[0], u[sn][1]), cd_mul(wm[1], u[sn][3]));
+        const cd a10 = cd_add(cd_mul(wm[2], u[sn][0]), cd_mul(wm[3], u[sn][2]));
+        const cd a11 = cd_add(cd_mul(wm[2], u[sn][1]), cd_mul(wm[3], u[sn][3]));
+        const cd idet = cd_inv(cd_sub(cd_mul(a00, a11), cd_mul(a01, a10)));
+        const cd x0 = sn == 0 ? cd_mul(a11, idet) : cd_mul(cd_make(-a01.x, -a01.y), idet);
+        const cd x1 = sn == 0 ? cd_mul(cd_make(-a10.x, -a10.y), idet) : cd_mul(a00, idet);
+        const cd t0 = cd_add(cd_mul(u[sn][0], x0), cd_mul(u[sn][1], x1));
+        const cd t1 = cd_add(cd_mul(u[sn][2], x0), cd_mul(u[sn][3], x1));
+        const double qq = cd_mulc(t0, x0).x + cd_mulc(t1, x1).x;
+        const double d = ssb_floor(sqrt(fmax(qq, 0.0)), flooring, (double)eps);
+        wm[sn * 2 + 0] = cd_scale(cd_conj(x0), 1.0 / d);
+        wm[sn * 2 + 1] = cd_scale(cd_conj(x1), 1.0 / d);
+      }
+      const cf wn0 = cd2cf(wm[n * 2 + 0]), wn1 = cd2cf(wm[n * 2 + 1]);
+      if (fq == 0 && t < 2 && my_valid) {
+        wmat[n * 2 + 0] = wn0;
+        wmat[n * 2 + 1] = wn1;
+      }
+      // w[rr][m]: own bin from this lane, the other bin of the pair from the neighbour lane (t ^ 1)
+      const float o0x = __shfl_xor_sync(0xffffffffu, wn0.x, 1), o0y = __shfl_xor_sync(0xffffffffu, wn0.y, 1);
+      const float o1x = __shfl_xor_sync(0xffffffffu, wn1.x, 1), o1y = __shfl_xor_sync(0xffffffffu, wn1.y, 1);
+      w[0][0] = rs ? make_float2(o0x, o0y) : wn0;
+      w[0][1] = rs ? make_float2(o1x, o1y) : wn1;
+      w[1][0] = rs ? wn0 : make_float2(o0x, o0y);
+      w[1][1] = rs ? wn1 : make_float2(o1x, o1y);
+    }
+  } else {
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+      for (int m = 0; m < N; ++m) w[rr][m] = Wrw[(((size_t)b * I + rowc[rr]) * N + n) * N + m];
+  }
+
+  // ======================= pass 1: basis update of source n with the filter w =======================
+  if constexpr (MODE != MODE_COV) {
+    float num[2 * KS][4], den[2 * KS][4];
+#pragma unroll
+    for (int qi = 0; qi < 2 * KS; ++qi)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) num[qi][c] = den[qi][c] = 0.f;
+    float qs[2] = {0.f, 0.f};
+    // P is handed to kf_activation_coop in 16 x 16 tiles ([bn][bin tile][frame tile][16 bins][16 frames], see ssb_coop.cu)
+    const size_t ptile0 = ((bn * (size_t)((I + 15) >> 4) + (size_t)(i0 >> 4)) * (size_t)(J >> 4)) * 256;
+    float* const pout0 = pin_ptr(Pout + ptile0 + g * 16 + 2 * t);
+    float* const pout1 = pin_ptr(Pout + ptile0 + (g + 8) * 16 + 2 * t);
+#pragma unroll 1
+    for (int c = c_lo; c < c_hi; ++c) {
+      const int vst = vk & 1;
+      mbar_wait(vfull(warp, vst), (vk >> 1) & 1);
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        const int s = 2 * c + half;
+        if (s >= nsteps) break;
+        const int xst = xk % XS;
+        mbar_wait(xfull(tb, fq, xst), (xk / XS) & 1);
+        const uint32_t voff = vst * CHB + half * (16 * JKS * 2);
+        const uint32_t vb1 = l1base + voff, vb2 = l2base + voff;
+        const uint32_t xb = xlane + xst * XSB;
+        // ---- GEMM1: R[16 bins x 16 frames] = T V ----
+        float R[2][4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) R[h][cc] = 0.f;
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks) {
+            uint32_t bh0, bh1, bl0, bl1;
+            ldsm_x4(bh0, bh1, bl0, bl1, vb1 + (8 * h * JKS + ks * 16) * 2);
+            mma_split(R[h], Thi[ks], Tlo[ks], bh0, bh1, bl0, bl1);
+          }
+        }
+        // ---- elementwise: P = |w^H x|^2, A = P / R^2, B = 1 / R ----
+        uint32_t Ahi[4], Alo[4], Bhi[4], Blo[4];
+        float* const po[2] = {pout0 + (size_t)s * 256, pout1 + (size_t)s * 256};
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr) {
+            float4 x[N];
+#pragma unroll
+            for (int m = 0; m < N; ++m) x[m] = lds128(xb + h * (N * 1024) + m * 1024 + rr * 512);
+            float p0, p1;
+            power2<N>(x, w[rr], p0, p1);
+            // the power spectrogram is kept for the activation update (same W => same P, ilrma.py:1169-1172)
+            *reinterpret_cast<float2*>(po[rr] + 8 * h) = make_float2(p0, p1);
+            if constexpr (MODE == MODE_FUSED) qs[rr] += p0 + p1;
+            const float i0v = fast_rcp(R[h][rr * 2 + 0]);
+            const float i1v = fast_rcp(R[h][rr * 2 + 1]);
+            const Split sa = split2(p0 * i0v * i0v, p1 * i1v * i1v);
+            const Split sb = split2(i0v, i1v);
+            Ahi[h * 2 + rr] = sa.hi;
+            Alo[h * 2 + rr] = sa.lo;
+            Bhi[h * 2 + rr] = sb.hi;
+            Blo[h * 2 + rr] = sb.lo;
+          }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(xempty(tb, fq, xst));
+        ++xk;
+        // ---- GEMM2: num += A V^T, den += B V^T (contraction over the 16 frames) ----
+#pragma unroll
+        for (int qi = 0; qi < 2 * KS; ++qi) {
+          uint32_t vh0, vh1, vl0, vl1;
+          ldsm_x4_t(vh0, vh1, vl0, vl1, vb2 + qi * 16);
+          mma_split(num[qi], Ahi, Alo, vh0, vh1, vl0, vl1);
+          mma_split(den[qi], Bhi, Blo, vh0, vh1, vl0, vl1);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(vempty(warp, vst));
+      ++vk;
+    }
+    // ---- combine the frame ranges (fixed order), then T <- floor(T sqrt(num / den))   (ilrma.py:1125-1126, p = 2) ----
+    if constexpr (FS > 1) {
+      // the V rings are dead once every warp of the tile has left its loop: they become the combine scratch
+      // [source][fq - 1][value][lane]
+      bar_sync_id<256>(tb);
+      constexpr int NV = 2 * (2 * KS) * 4 + 2;  // num, den, qs
+      float* sc = reinterpret_cast<float*>(smem_raw + S::X_BYTES) + (size_t)tb * (N * (FS - 1) * NV * 32);
+      if (fq > 0) {
+        float* dst = sc + ((size_t)(n * (FS - 1) + fq - 1) * NV) * 32 + lane;
+#pragma unroll
+        for (int qi = 0; qi < 2 * KS; ++qi)
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            dst[(qi * 4 + cc) * 32] = num[qi][cc];
+            dst[((2 * KS + qi) * 4 + cc) * 32] = den[qi][cc];
+          }
+        dst[(NV - 2) * 32] = qs[0];
+        dst[(NV - 1) * 32] = qs[1];
+      }
+      bar_sync_id<256>(tb);
+      if (fq > 0) return;
+#pragma unroll
+      for (int f = 1; f < FS; ++f) {
+        const float* src = sc + ((size_t)(n * (FS - 1) + f - 1) * NV) * 32 + lane;
+#pragma unroll
+        for (int qi = 0; qi < 2 * KS; ++qi)
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            num[qi][cc] += src[(qi * 4 + cc) * 32];
+            den[qi][cc] += src[((2 * KS + qi) * 4 + cc) * 32];
+          }
+        qs[0] += src[(NV - 2) * 32];
+        qs[1] += src[(NV - 1) * 32];
+      }
+    }
+    if constexpr (MODE == MODE_FUSED) {
+      // q[b, i, n] = mean_j |y|^2 with the unnormalised filter (the term kf_ip1_n2 gets from the unweighted covariance)
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        float v = qs[rr];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        if (t == 0 && rvalid[rr]) q[((size_t)b * I + row[rr]) * N + n] = (double)v / (double)J;
+      }
+    }
+    // the new basis is also written pre-split (bf16 hi, lo; [bin][basis] chunks of 32 bins) for kf_activation_coop
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+      for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          if (!rvalid[rr]) continue;
+          const int qi = ks * 2 + nb;
+          const int k0 = ks * 16 + nb * 8 + 2 * t;
+          float tn[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            tn[e] = 0.f;
+            if (k0 + e < K) {
+              const float ratio = num[qi][rr * 2 + e] / den[qi][rr * 2 + e];
+              tn[e] = ssb_floor(sqrtf(ratio) * Told[ks][nb][rr][e], flooring, eps);
+              T[(bn * I + row[rr]) * K + k0 + e] = tn[e];
+            }
+          }
+          const Split sp = split2(tn[0], tn[1]);
+          __nv_bfloat16* th = Ts + (bn * nchunk_i + (row[rr] >> 5)) * (size_t)(2 * JCV * JKS) + (row[rr] & 31) * JKS + k0;
+          *reinterpret_cast<uint32_t*>(th) = sp.hi;
+          *reinterpret_cast<uint32_t*>(th + JCV * JKS) = sp.lo;
+        }
+  }
+}
+
+// ---- tensor maps -----------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+// X[B*N planes][I bins][2 J floats]; box = 16 floats (8 frames) x 16 bins x N planes, no swizzle, zero fill
+int make_x_map(CUtensorMap* tm, const cf* X, int B, int N, int I, int J) {
+  EncodeTiledFn enc = encode_fn();
+  SSB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+  SSB_REQUIRE((reinterpret_cast<uintptr_t>(X) & 15) == 0 && (J % 2) == 0, "TMA needs a 16-byte aligned X and even n_frames");
+  const cuuint64_t dims[3] = {(cuuint64_t)2 * J, (cuuint64_t)I, (cuuint64_t)B * N};
+  const cuuint64_t strides[2] = {(cuuint64_t)J * 8, (cuuint64_t)I * J * 8};  // bytes, dims 1 and 2
+  const cuuint32_t box[3] = {16, 16, (cuuint32_t)N};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<cf*>(X), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SSB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for X[%d,%d,%d,%d]", (int)r, B, N, I, J);
+  return 0;
+}
+
+template <int N, int KS, int MODE, int TB>
+int launch_tile(const ssb_config* c, const cf* X, cf* W, float* T, const __nv_bfloat16* Vs, float* P, __nv_bfloat16* Ts,
+                cf* U, double* q, const char* name, cudaStream_t st) {
+  using S = TileShape<N, KS, TB>;
+  const int B = c->n_batch, I = c->n_bins, J = c->n_frames, K = c->n_basis;
+  const int nchunk = (J + JCV - 1) / JCV, nchunk_i = (I + JCV - 1) / JCV;
+  CUtensorMap tm;
+  if (make_x_map(&tm, X, B, N, I, J)) return 1;
+  // the combine scratch of the basis pass aliases the V rings: make sure it fits
+  static_assert(S::FS == 1 || N * (S::FS - 1) * (2 * (2 * KS) * 4 + 2) * 32 * 4 <= 8 * 2 * S::CHB, "combine scratch");
+  static bool attr_dev[SSB_MAX_DEVICES] = {};
+  bool& attr_set = attr_dev[ssb_current_device()];
+  if (!attr_set) {
+    SSB_CUDA(cudaFuncSetAttribute(kt_tile<N, KS, MODE, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM));
+    attr_set = true;
+  }
+  dim3 grid((I + 16 * TB - 1) / (16 * TB), B);
+  kt_tile<N, KS, MODE, TB><<<grid, S::NT, S::SMEM, st>>>(tm, W, T, Vs, P, Ts, U, q, I, J, K, nchunk, nchunk_i,
+                                                        c->flooring, c->eps);
+  return ssb_check_launch(name, st);
+}
+
+}  // namespace
+
+// SSB_TMA (read once): 1 (default) = the TMA tile kernels where they apply, 0 = the cp.async kernels of ssb_coop.cu /
+// ssb_fused.cu everywhere (A/B)
+int ssb_tma_enabled() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("SSB_TMA");
+    mode = e ? atoi(e) : 1;
+  }
+  return mode;
+}
+
+int ssb_tma_supported(const ssb_config* c) {
+  const int N = c->n_sources;
+  return ssb_tma_enabled() && (N == 2 || N == 4 || N == 8) && (c->n_frames % 16) == 0 && c->n_basis <= 32;
+}
+
+#define SSB_TILE_DISPATCH(MODE_, ...)                                                      \
+  do {                                                                                     \
+    const bool k16 = c->n_basis <= 16;                                                     \
+    switch (c->n_sources) {                                                                \
+      case 2: return k16 ? launch_tile<2, 1, MODE_, 1>(__VA_ARGS__) : launch_tile<2, 2, MODE_, 1>(__VA_ARGS__); \
+      case 4: return k16 ? launch_tile<4, 1, MODE_, 1>(__VA_ARGS__) : launch_tile<4, 2, MODE_, 1>(__VA_ARGS__); \
+      case 8: return k16 ? launch_tile<8, 1, MODE_, 1>(__VA_ARGS__) : launch_tile<8, 2, MODE_, 1>(__VA_ARGS__); \
+      default: break;                                                                      \
+    }                                                                                      \
+  } while (0)
+
+// basis update of every source (reads the pre-split activation Vs, writes T, the pre-split basis Ts and P)
+int ssb_tma_basis(const ssb_config* c, const cf* X, const cf* W, float* T, const void* Vs, float* P, void* Ts,
+                  cudaStream_t st) {
+  SSB_REQUIRE(ssb_tma_supported(c), "tma_basis: unsupported configuration");
+  SSB_TILE_DISPATCH(MODE_BASIS, c, X, const_cast<cf*>(W), T, (const __nv_bfloat16*)Vs, P, (__nv_bfloat16*)Ts, nullptr,
+                    nullptr, "tma_basis", st);
+  return 1;
+}
+
+// N = 2: weighted covariances U[B,I,2,2,2] from the pre-split activation Vs
+int ssb_tma_cov_n2(const ssb_config* c, const cf* X, float* T, const void* Vs, cf* U, cudaStream_t st) {
+  SSB_REQUIRE(ssb_tma_supported(c) && c->n_sources == 2, "tma_cov: unsupported configuration");
+  if (c->n_basis <= 16)
+    return launch_tile<2, 1, MODE_COV, 1>(c, X, nullptr, T, (const __nv_bfloat16*)Vs, nullptr, nullptr, U, nullptr,
+                                          "tma_phi_cov", st);
+  return launch_tile<2, 2, MODE_COV, 1>(c, X, nullptr, T, (const __nv_bfloat16*)Vs, nullptr, nullptr, U, nullptr,
+                                        "tma_phi_cov", st);
+}
+
+// N = 2 inside ssb_run: covariance + IP1 of iteration t (W rewritten unnormalised, q emitted) and the basis update of
+// iteration t + 1 on the same tile
+int ssb_tma_spatial_basis_n2(const ssb_config* c, const cf* X, cf* W, float* T, const void* Vs, float* P, void* Ts,
+                             double* q, cudaStream_t st) {
+  SSB_REQUIRE(ssb_tma_supported(c) && c->n_sources == 2 && q != nullptr, "tma_spatial_basis: unsupported configuration");
+  if (c->n_basis <= 16)
+    return launch_tile<2, 1, MODE_FUSED, 1>(c, X, W, T, (const __nv_bfloat16*)Vs, P, (__nv_bfloat16*)Ts, nullptr, q,
+                                            "tma_cov_ip1_basis", st);
+  return launch_tile<2, 2, MODE_FUSED, 1>(c, X, W, T, (const __nv_bfloat16*)Vs, P, (__nv_bfloat16*)Ts, nullptr, q,
+                                          "tma_cov_ip1_basis", st);
+}

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 def test_config_struct_layout_matches_header():
     from ssspy_b200 import _lib
     # 14 int32/float scalars + 128 pair slots + fast_path + model_param + partitioning + 2 IPA fields
-    assert ctypes.sizeof(_lib.SsbConfig) == 4 * (14 + 2 * _lib.SSB_MAX_PAIRS + 5)
+    assert ctypes.sizeof(_lib.SsbConfig) == 4 * (14 + 2 * _lib.SSB_MAX_PAIRS + 6)
 
 
 def test_plan_validation_runs_without_gpu():
