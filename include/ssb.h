@@ -111,6 +111,13 @@ int ssb_version(void);
 /* number of visible CUDA devices (0 => every compute call fails loudly) */
 int ssb_device_count(int* count);
 
+/* Device status flags raised by kernels since the last fetch on the current device; reads and clears them after the
+ * work enqueued on `stream` (this call synchronises the stream).  SSB_STATUS_SINGULAR: a pivoting solve / inverse met an
+ * exactly zero pivot, the case in which the reference raises numpy.linalg.LinAlgError("Singular matrix")
+ * (ssspy/linalg/_solve.py:15, ssspy/algorithm/projection_back.py:89, :110); the host classes re-raise it. */
+#define SSB_STATUS_SINGULAR 1
+int ssb_status_fetch(int* flags /* host */, void* stream);
+
 /* launch accounting: total kernel launches issued by this library in the process */
 int ssb_launch_count(unsigned long long* count);
 /* per-kernel device timing: events are recorded after every launch between begin and end;

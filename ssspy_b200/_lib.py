@@ -79,6 +79,7 @@ SIGNATURES = {
     "ssb_projection_back_y": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "ssb_logdet": [_vp, _vp, _i, _i, _vp],
     "ssb_reconstruct_nmf": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "ssb_status_fetch": [ctypes.POINTER(ctypes.c_int), _vp],
     "ssb_inv": [_vp, _vp, _i, _i, _vp],
     "ssb_solve": [_vp, _vp, _vp, _i, _i, _i, _vp],
     "ssb_eigh": [_vp, _vp, _i, _vp, _vp, _i, _i, _vp],
@@ -115,6 +116,23 @@ def call(name, *args):
     rc = getattr(lib, name)(*args)
     if rc != 0:
         raise SsbError(lib.ssb_last_error().decode("utf-8", "replace"))
+
+
+STATUS_SINGULAR = 1
+
+
+def check_status(stream_ptr=None):
+    """Synchronise ``stream_ptr`` (the current torch stream by default) and raise what the reference would have raised
+    for the work done since the last check: ``numpy.linalg.LinAlgError("Singular matrix")`` when a pivoting solve or
+    inverse met an exactly zero pivot (ssspy/linalg/_solve.py:15, ssspy/algorithm/projection_back.py:89, :110)."""
+    import numpy as np
+    if stream_ptr is None:
+        from . import _device
+        stream_ptr = _device.stream_ptr()
+    flags = ctypes.c_int(0)
+    call("ssb_status_fetch", ctypes.byref(flags), stream_ptr)
+    if flags.value & STATUS_SINGULAR:
+        raise np.linalg.LinAlgError("Singular matrix")
 
 
 def device_count():

@@ -40,6 +40,7 @@ def projection_back(data_or_filter, reference=None, reference_id=0):
                       B, N, I, J, wrap_reference_id(ref, N), st())
             outs.append(out if batched else out[0])
         res = torch.stack(outs, dim=0) if reference_id is None else outs[0]
+    _lib.check_status()  # LinAlgError("Singular matrix") like np.linalg.inv in the reference (projection_back.py:89, :110)
     if is_t:
         return res
     return res.cpu().numpy().astype(np.complex128)

@@ -134,6 +134,8 @@ class DeviceSeparatorMixin:
         self._defer_ok = False     # stock __call__: upload + initial separation run at the head of each chunk's pipeline
         self._deferred_sep = None  # (W, Y) of the deferred initial separation
         self._host_output = None   # pinned host copy of `output` filled per chunk by __call__ (owned by the caller)
+        self._h2d_stream = None    # copy streams of the host-tensor pipeline: uploads run back to back from t = 0 and
+        self._d2h_stream = None    # downloads trail the chunks, both decoupled from the compute streams
 
     # ---- input -----------------------------------------------------------------------------------
     @property
@@ -327,9 +329,24 @@ class DeviceSeparatorMixin:
                 _lib.call("ssb_plan_bind", ch["plan"], self._dX[b0:b1].data_ptr(), ptrs[0], ptrs[1], ptrs[2], ptrs[3],
                           ptrs[4], ws.data_ptr(), ws.numel())
                 if deferred:
-                    ch["init"] = True  # upload, prepare and W X at the head of this chunk's first piece of work
+                    ch["init"] = True  # wait for the upload, prepare and W X at the head of this chunk's first piece of work
                 else:
                     _lib.call("ssb_plan_prepare", ch["plan"], st.cuda_stream)
+        if self._deferred_sep is not None:
+            # every chunk's upload goes onto ONE copy stream, in chunk order, right now: the H2D engine streams the whole
+            # batch at PCIe rate from the start, and a chunk's compute stream only waits for its own piece
+            if self._h2d_stream is None:
+                self._h2d_stream = torch.cuda.Stream()
+                self._d2h_stream = torch.cuda.Stream()
+            ev0 = torch.cuda.Event()
+            ev0.record(cur)
+            self._h2d_stream.wait_event(ev0)
+            with torch.cuda.stream(self._h2d_stream):
+                for ch in self._chunks:
+                    b0, b1 = ch["b0"], ch["b1"]
+                    self._dX[b0:b1].copy_(self._pending_h2d[b0:b1], non_blocking=True)
+                    ch["h2d_event"] = torch.cuda.Event()
+                    ch["h2d_event"].record(self._h2d_stream)
         if self._deferred_sep is None:
             self._pending_h2d = None
         self._plan_key = key
@@ -381,7 +398,7 @@ class DeviceSeparatorMixin:
         ch["init"] = False
         b0, b1 = ch["b0"], ch["b1"]
         B, N, I, J = self._dims()
-        self._dX[b0:b1].copy_(self._pending_h2d[b0:b1], non_blocking=True)
+        st.wait_event(ch.pop("h2d_event"))  # this chunk's mixtures have arrived (copy stream, see _ensure_plan)
         _lib.call("ssb_plan_prepare", ch["plan"], st.cuda_stream)
         W, Y = self._deferred_sep
         _lib.call("ssb_separate", self._dX[b0:b1].data_ptr(), W[b0:b1].data_ptr(), Y[b0:b1].data_ptr(), b1 - b0, N, I, J,
@@ -407,6 +424,7 @@ class DeviceSeparatorMixin:
         buf = self._loss_buf
         self._for_chunks(lambda ch, sp: _lib.call("ssb_compute_loss", ch["plan"], buf[ch["b0"]:].data_ptr(), sp))
         self._join()
+        _lib.check_status()
         vals = buf[:B].cpu().numpy()
         return vals.copy() if self._batched else float(vals[0])
 
@@ -460,12 +478,22 @@ class DeviceSeparatorMixin:
             elif has_w:
                 _lib.call("ssb_plan_separate", ch["plan"], sp)
             if host is not None:
-                host[ch["b0"]:ch["b1"]].copy_(Y[ch["b0"]:ch["b1"]], non_blocking=True)
+                # download on the copy stream: the chunk's compute stream is free for its next chunk at once
+                done = torch.cuda.Event()
+                done.record(torch.cuda.current_stream())
+                d2h = self._d2h_stream if self._d2h_stream is not None else torch.cuda.current_stream()
+                d2h.wait_event(done)
+                with torch.cuda.stream(d2h):
+                    host[ch["b0"]:ch["b1"]].copy_(Y[ch["b0"]:ch["b1"]], non_blocking=True)
 
         rec = bool(self.record_loss)
         losses = self._run_iterations(n_iter, rec, initial_loss=bool(initial_call and rec), tail=tail)
+        if host is not None and self._d2h_stream is not None:
+            ev = torch.cuda.Event()
+            ev.record(self._d2h_stream)
+            torch.cuda.current_stream().wait_event(ev)
+        _lib.check_status()  # synchronises; LinAlgError where the reference's np.linalg.solve / inv would have raised
         if host is not None:
-            torch.cuda.current_stream().synchronize()  # the joins above made it wait for every chunk
             self._host_output = host
         if losses is not None:
             self.loss.extend(losses[i].copy() if self._batched else float(losses[i, 0]) for i in range(losses.shape[0]))

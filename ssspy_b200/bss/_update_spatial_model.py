@@ -20,6 +20,7 @@ _DEFAULT_FLOOR = functools.partial(max_flooring, eps=EPS)
 
 
 def _finish(res, orig, overwrite):
+    _lib.check_status()  # LinAlgError("Singular matrix") where the reference's np.linalg.solve raises (_solve.py:15)
     if _device.is_tensor(orig):
         if overwrite:
             orig.copy_(res.to(orig.dtype))

@@ -112,6 +112,7 @@ class AuxFDICA(FDICABase):
             self.restore_scale()
         if self._state.get("demix_filter") is not None:
             self._plan_call("ssb_plan_separate")
+        _lib.check_status()  # LinAlgError where the reference's np.linalg.solve / inv would have raised
         return self.output
 
     def __repr__(self):

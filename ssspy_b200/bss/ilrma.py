@@ -306,6 +306,7 @@ class _DeviceILRMA(ILRMABase):
             self.restore_scale()
         elif self._state.get("demix_filter") is not None:
             self._plan_call("ssb_plan_separate")
+        _lib.check_status()  # LinAlgError where the reference's np.linalg.solve / inv would have raised
         return self.output
 
     def run_iterations(self, n_iter):

@@ -64,6 +64,7 @@ class MNMFBase(DeviceSeparatorMixin, IterativeMethodBase):
         else:
             IterativeMethodBase.__call__(self, n_iter=n_iter, initial_call=initial_call)
             self._plan_call("ssb_plan_separate")
+        _lib.check_status()  # LinAlgError where the reference's np.linalg.solve / inv would have raised
         return self.output
 
 

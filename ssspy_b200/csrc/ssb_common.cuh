@@ -40,6 +40,11 @@ static inline int ssb_current_device() {
   return d;
 }
 
+// Device-side status word of the library (one per device, lazily allocated): bit 0 = a pivoting solver met an exactly
+// zero pivot, i.e. the matrix numpy.linalg.solve / inv would reject with LinAlgError("Singular matrix")
+// (ssspy/linalg/_solve.py:15, ssspy/algorithm/projection_back.py:89).  ssb_status_fetch reads and clears it.
+int* ssb_status_word();
+
 // ---- complex double ---------------------------------------------------------------------------
 __host__ __device__ __forceinline__ cd cd_make(double r, double i) { return make_double2(r, i); }
 __host__ __device__ __forceinline__ cd cd_add(cd a, cd b) { return make_double2(a.x + b.x, a.y + b.y); }
@@ -92,9 +97,10 @@ __device__ __forceinline__ double warp_sum(double v) {
 // cabs1 is not replicated -- results agree to rounding).  Returns log|det M| through *logabsdet
 // when non-null (used by the loss).
 __device__ __forceinline__ void warp_gauss_jordan(cd* A, int n, int nrhs, int ld, int lane,
-                                                  double* logabsdet = nullptr) {
+                                                  double* logabsdet = nullptr, bool* singular = nullptr) {
   const int ncol = n + nrhs;
   double lad = 0.0;
+  bool sing = false;
   for (int p = 0; p < n; ++p) {
     // pivot search (redundant on all lanes)
     int piv = p;
@@ -116,6 +122,7 @@ __device__ __forceinline__ void warp_gauss_jordan(cd* A, int n, int nrhs, int ld
     }
     __syncwarp();
     cd pv = A[p * ld + p];
+    sing = sing || (cd_abs2(pv) == 0.0);
     lad += 0.5 * log(cd_abs2(pv));
     cd ipv = cd_inv(pv);
     __syncwarp();
@@ -136,12 +143,14 @@ __device__ __forceinline__ void warp_gauss_jordan(cd* A, int n, int nrhs, int ld
     __syncwarp();
   }
   if (logabsdet) *logabsdet = lad;
+  if (singular) *singular = sing;
 }
 
 // Single-thread variant on a thread-private (local memory) matrix; used by the standalone linalg
 // helpers where one thread owns one matrix.
-__device__ __forceinline__ void thread_gauss_jordan(cd* A, int n, int nrhs, int ld) {
+__device__ __forceinline__ void thread_gauss_jordan(cd* A, int n, int nrhs, int ld, bool* singular = nullptr) {
   const int ncol = n + nrhs;
+  bool sing = false;
   for (int p = 0; p < n; ++p) {
     int piv = p;
     double best = cd_abs2(A[p * ld + p]);
@@ -158,6 +167,7 @@ __device__ __forceinline__ void thread_gauss_jordan(cd* A, int n, int nrhs, int 
         A[p * ld + c] = A[piv * ld + c];
         A[piv * ld + c] = t;
       }
+    sing = sing || (cd_abs2(A[p * ld + p]) == 0.0);
     cd ipv = cd_inv(A[p * ld + p]);
     for (int c = p + 1; c < ncol; ++c) A[p * ld + c] = cd_mul(A[p * ld + c], ipv);
     for (int r = 0; r < n; ++r) {
@@ -166,6 +176,7 @@ __device__ __forceinline__ void thread_gauss_jordan(cd* A, int n, int nrhs, int 
       for (int c = p + 1; c < ncol; ++c) A[r * ld + c] = cd_sub(A[r * ld + c], cd_mul(f, A[p * ld + c]));
     }
   }
+  if (singular) *singular = sing;
 }
 
 // Closed-form generalised 2x2 Hermitian eigenproblem A h = l B h (type 1), following

@@ -948,13 +948,14 @@ __global__ void __launch_bounds__(ACW * 32, MINB)
 
 template <int N, int KS>
 int launch_coop(const ssb_config* c, const cf* X, const cf* W, float* T, float* V, float* P, __nv_bfloat16* Vs,
-                __nv_bfloat16* Ts, int vs_valid, cudaStream_t st, cf* Wrw = nullptr, double* q = nullptr) {
+                __nv_bfloat16* Ts, int vs_valid, cudaStream_t st, cf* Wrw = nullptr, double* q = nullptr,
+                int parts = 7) {  // parts: 1 = pre-split of V, 2 = basis kernel, 4 = activation kernel
   const int B = c->n_batch, I = c->n_bins, J = c->n_frames, K = c->n_basis;
   constexpr int BT = CoopShape<N>::BT, NW = CoopShape<N>::NW;
   constexpr int KP = 16 * KS, JKS = KP + PADH;
   constexpr int CHB = 2 * JCV * JKS * 2;
   const int nchunk = (J + JCV - 1) / JCV, nchunk_i = (I + JCV - 1) / JCV;
-  if (!vs_valid) {
+  if (!vs_valid && (parts & 1)) {
     dim3 gv(nchunk, B * N);
     kf_vsplit<KS><<<gv, 128, 0, st>>>(V, Vs, J, K, nchunk);
     if (ssb_check_launch("coop_vsplit", st)) return 1;
@@ -985,7 +986,9 @@ int launch_coop(const ssb_config* c, const cf* X, const cf* W, float* T, float* 
     attr_set = true;
   }
   dim3 grid((I + 16 * BT - 1) / (16 * BT), B);
-  if (q != nullptr) {
+  if (!(parts & 2)) {
+    // the basis update is done by another kernel (ssb_tma.cu)
+  } else if (q != nullptr) {
     // spatial update of the previous iteration fused in front of the basis update (N = 2, Vs must be valid)
     if (N != 2 || Wrw == nullptr || !vs_valid) {
       ssb_set_error("coop_cov_ip1_basis: needs n_sources = 2 and a valid pre-split activation");
@@ -1007,6 +1010,7 @@ int launch_coop(const ssb_config* c, const cf* X, const cf* W, float* T, float* 
     kf_basis_coop<N, KS><<<grid, NW * 32, sm, st>>>(X, W, T, Vs, P, Ts, I, J, K, nchunk, nchunk_i, c->flooring, c->eps);
     if (ssb_check_launch("coop_basis", st)) return 1;
   }
+  if (!(parts & 4)) return 0;
   if (act_shape == 1 && KS == 1) {  // K > 16 spills at 72 registers
     dim3 ga((J + AW1 * 16 - 1) / (AW1 * 16), N, B);
     kf_activation_coop<KS, AW1, AP1, AB1><<<ga, AW1 * 32, sm_act1, st>>>(P, Ts, V, Vs, N, I, J, K, nchunk_i, nchunk,
@@ -1048,6 +1052,38 @@ int ssb_coop_source(const ssb_config* c, const cf* X, const cf* W, float* T, flo
     SSB_DISPATCH_N(c->n_sources, return (launch_coop<NN, 1>(c, X, W, T, V, P, Vs, Ts, vs_valid, st)));
   } else {
     SSB_DISPATCH_N(c->n_sources, return (launch_coop<NN, 2>(c, X, W, T, V, P, Vs, Ts, vs_valid, st)));
+  }
+  return 0;
+}
+
+void* ssb_coop_vs(const ssb_config*, void* ws) { return ws; }
+void* ssb_coop_ts(const ssb_config* c, void* ws) { return (char*)ws + coop_vs_bytes(c); }
+
+int ssb_coop_vsplit(const ssb_config* c, const float* V, void* ws, int vs_valid, cudaStream_t st) {
+  SSB_REQUIRE((c->n_frames % 16) == 0 && c->n_basis <= 32 && ws != nullptr, "coop_vsplit: unsupported configuration");
+  __nv_bfloat16* Vs = (__nv_bfloat16*)ws;
+  __nv_bfloat16* Ts = (__nv_bfloat16*)((char*)ws + coop_vs_bytes(c));
+  float* Vm = const_cast<float*>(V);
+  if (c->n_basis <= 16) {
+    SSB_DISPATCH_N(c->n_sources, return (launch_coop<NN, 1>(c, nullptr, nullptr, nullptr, Vm, nullptr, Vs, Ts, vs_valid, st,
+                                                            nullptr, nullptr, 1)));
+  } else {
+    SSB_DISPATCH_N(c->n_sources, return (launch_coop<NN, 2>(c, nullptr, nullptr, nullptr, Vm, nullptr, Vs, Ts, vs_valid, st,
+                                                            nullptr, nullptr, 1)));
+  }
+  return 0;
+}
+
+int ssb_coop_activation(const ssb_config* c, float* V, float* P, void* ws, cudaStream_t st) {
+  SSB_REQUIRE((c->n_frames % 16) == 0 && c->n_basis <= 32 && ws != nullptr, "coop_activation: unsupported configuration");
+  __nv_bfloat16* Vs = (__nv_bfloat16*)ws;
+  __nv_bfloat16* Ts = (__nv_bfloat16*)((char*)ws + coop_vs_bytes(c));
+  if (c->n_basis <= 16) {
+    SSB_DISPATCH_N(c->n_sources, return (launch_coop<NN, 1>(c, nullptr, nullptr, nullptr, V, P, Vs, Ts, 1, st, nullptr,
+                                                            nullptr, 4)));
+  } else {
+    SSB_DISPATCH_N(c->n_sources, return (launch_coop<NN, 2>(c, nullptr, nullptr, nullptr, V, P, Vs, Ts, 1, st, nullptr,
+                                                            nullptr, 4)));
   }
   return 0;
 }

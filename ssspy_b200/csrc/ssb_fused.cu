@@ -1023,7 +1023,7 @@ int launch_cov_w(const cf* X, const float* phi, long long sb, long long sn, long
 // psi_n^2 = mean_{i,j} |y|^2 = mean_i q, so normalisation needs no pass over X.
 __global__ void __launch_bounds__(128) kf_ip1_n2(cf* __restrict__ W, const cf* __restrict__ U,
                                                  const cf* __restrict__ C, double* __restrict__ q, int n_mat,
-                                                 int flooring, double eps) {
+                                                 int flooring, double eps, int* __restrict__ status) {
   const int mat = blockIdx.x * blockDim.x + threadIdx.x;
   if (mat >= n_mat) return;
   cd w[4];
@@ -1041,6 +1041,7 @@ __global__ void __launch_bounds__(128) kf_ip1_n2(cf* __restrict__ W, const cf* _
     cd a11 = cd_add(cd_mul(w[2], u[1]), cd_mul(w[3], u[3]));
     // x = A^-1 e_n  (adjugate / det)
     cd det = cd_sub(cd_mul(a00, a11), cd_mul(a01, a10));
+    if (det.x == 0.0 && det.y == 0.0) atomicOr(status, SSB_STATUS_SINGULAR);  // np.linalg.solve raises (_solve.py:15)
     cd idet = cd_inv(det);
     cd x0, x1;
     if (n == 0) {
@@ -1139,7 +1140,14 @@ int launch_all(const ssb_config* c, const cf* X, cf* W, float* T, float* V, floa
   if (!(phases & 1)) {
     // covariance only (the source model of this iteration has already run)
   } else if (coop && vs != nullptr && W != nullptr) {
-    if (ssb_coop_source(c, X, W, T, V, P, vs->base, vs->vs_valid ? 1 : 0, st)) return 1;
+    if (ssb_tma_supported(c) && (ssb_tma_mask(c) & 1)) {
+      // TMA-fed basis kernel (ssb_tma.cu) between the pre-split of V and the activation kernel of ssb_coop.cu
+      if (ssb_coop_vsplit(c, V, vs->base, vs->vs_valid ? 1 : 0, st)) return 1;
+      if (ssb_tma_basis(c, X, W, T, ssb_coop_vs(c, vs->base), P, ssb_coop_ts(c, vs->base), st)) return 1;
+      if (ssb_coop_activation(c, V, P, vs->base, st)) return 1;
+    } else if (ssb_coop_source(c, X, W, T, V, P, vs->base, vs->vs_valid ? 1 : 0, st)) {
+      return 1;
+    }
     vs->vs_valid = true;  // ssb_update_once clears it again unless it runs inside ssb_run
   } else {
     dim3 gb((I + FW * 16 - 1) / (FW * 16), N, B);
@@ -1156,6 +1164,9 @@ int launch_all(const ssb_config* c, const cf* X, cf* W, float* T, float* V, floa
     const char* e = getenv("SSB_COOP_COV");
     coop_cov = e ? atoi(e) : 1;
   }
+  // N = 2: TMA-fed covariance from the pre-split V left by the activation kernel (ssb_tma.cu)
+  if (N == 2 && coop && vs != nullptr && vs->vs_valid && ssb_tma_supported(c) && (ssb_tma_mask(c) & 2))
+    return ssb_tma_cov_n2(c, X, T, ssb_coop_vs(c, vs->base), U, st);
   if (coop && coop_cov && vs != nullptr && W != nullptr && ssb_coop_cov_supported(c))
     return ssb_coop_cov(c, X, T, vs->base, U, st);
   dim3 gc((N + G - 1) / G, (I + FW * 16 - 1) / (FW * 16), B);
@@ -1222,6 +1233,12 @@ int ssb_fused_spatial_source(const ssb_config* c, ssb_fused_ws* ws, const cf* X,
                              double* q, cudaStream_t st) {
   SSB_REQUIRE(ws != nullptr && ws->bytes > 0 && ws->zeroed && ws->vs_valid,
               "fused_spatial_source: the source model of the first iteration must have run in this ssb_run");
+  if (ssb_tma_supported(c) && (ssb_tma_mask(c) & 4)) {
+    // covariance + IP1 + next basis update on TMA-fed tiles whose frames are split over warps (the second pass over a
+    // tile is served by L2), then the activation update
+    if (ssb_tma_spatial_basis_n2(c, X, W, T, ssb_coop_vs(c, ws->base), P, ssb_coop_ts(c, ws->base), q, st)) return 1;
+    return ssb_coop_activation(c, V, P, ws->base, st);
+  }
   return ssb_coop_spatial_source(c, X, W, T, V, P, ws->base, q, st);
 }
 
@@ -1281,7 +1298,7 @@ int ssb_fused_cov_w(const cf* X, const float* phi, long long sb, long long sn, l
 
 int ssb_fused_ip1_n2(cf* W, const cf* U, const cf* C, double* q, int n_mat, int flooring, float eps,
                      cudaStream_t st) {
-  kf_ip1_n2<<<blocks_for(n_mat, 128), 128, 0, st>>>(W, U, C, q, n_mat, flooring, (double)eps);
+  kf_ip1_n2<<<blocks_for(n_mat, 128), 128, 0, st>>>(W, U, C, q, n_mat, flooring, (double)eps, ssb_status_word());
   return ssb_check_launch("fused_ip1_n2", st);
 }
 

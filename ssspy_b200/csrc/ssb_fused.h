@@ -41,6 +41,21 @@ int ssb_coop_update_ab(const ssb_config* cfg, int which, const float* A, const f
                        cudaStream_t st);
 int ssb_coop_source(const ssb_config* cfg, const cf* X, const cf* W, float* T, float* V, float* P, void* ws,
                     int vs_valid, cudaStream_t st);
+// the pieces of ssb_coop_source on their own (the TMA basis kernel of ssb_tma.cu sits between them): pre-split of V
+// into ws unless vs_valid, and the activation update from P and the pre-split basis in ws
+int ssb_coop_vsplit(const ssb_config* cfg, const float* V, void* ws, int vs_valid, cudaStream_t st);
+int ssb_coop_activation(const ssb_config* cfg, float* V, float* P, void* ws, cudaStream_t st);
+// pre-split activation Vs / basis Ts inside the cooperative scratch ws
+void* ssb_coop_vs(const ssb_config* cfg, void* ws);
+void* ssb_coop_ts(const ssb_config* cfg, void* ws);
+// TMA-fed tile kernels (ssb_tma.cu): cp.async.bulk.tensor + mbarrier rings; N = 2, 4, 8, n_frames % 16 == 0, K <= 32
+int ssb_tma_mask(const ssb_config* cfg);
+int ssb_tma_supported(const ssb_config* cfg);
+int ssb_tma_basis(const ssb_config* cfg, const cf* X, const cf* W, float* T, const void* Vs, float* P, void* Ts,
+                  cudaStream_t st);
+int ssb_tma_cov_n2(const ssb_config* cfg, const cf* X, float* T, const void* Vs, cf* U, cudaStream_t st);
+int ssb_tma_spatial_basis_n2(const ssb_config* cfg, const cf* X, cf* W, float* T, const void* Vs, float* P, void* Ts,
+                             double* q, cudaStream_t st);
 // closed-form IP1 for two sources; with C != NULL also q[mat,n] = Re(w_n C w_n^H) for the normalisation
 int ssb_fused_ip1_n2(cf* W, const cf* U, const cf* C, double* q, int n_mat, int flooring, float eps,
                      cudaStream_t st);

@@ -32,8 +32,10 @@ __device__ __forceinline__ double group_sum(double v) {
 // (x = A^-1 RHS).  gbase = first lane of the group inside the warp, r = lane - gbase.
 // logabs (optional) accumulates log|det A|.
 template <int N, int R, int GS>
-__device__ __forceinline__ void group_solve(cd (&a)[N], cd (&rhs)[R], int r, int gbase, double* logabs = nullptr) {
+__device__ __forceinline__ void group_solve(cd (&a)[N], cd (&rhs)[R], int r, int gbase, double* logabs = nullptr,
+                                            bool* singular = nullptr) {
   bool used = false;
+  bool sing = false;
   int mysrc = r;  // which lane ends up holding solution component r
   double lad = 0.0;
 #pragma unroll
@@ -51,6 +53,7 @@ __device__ __forceinline__ void group_solve(cd (&a)[N], cd (&rhs)[R], int r, int
       }
     }
     const int L = gbase + l;
+    sing = sing || (v == 0.0);  // the largest remaining pivot candidate is exactly zero (uniform over the group)
     const cd pv = shfl_cd(a[p], L);
     lad += 0.5 * log(cd_abs2(pv));
     const cd ipv = cd_inv(pv);
@@ -73,4 +76,5 @@ __device__ __forceinline__ void group_solve(cd (&a)[N], cd (&rhs)[R], int r, int
 #pragma unroll
   for (int q = 0; q < R; ++q) rhs[q] = shfl_cd(rhs[q], gbase + mysrc);
   if (logabs) *logabs = lad;
+  if (singular) *singular = sing;
 }

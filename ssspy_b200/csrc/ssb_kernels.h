@@ -42,8 +42,12 @@ int ssbk_ip1(cf* W, const cf* U, int n_mat, int N, int flooring, float eps, cuda
 // each pair member uses
 int ssbk_ip2(cf* W, const cf* U, int n_mat, int N, const int* pairs, int n_pairs, int n_u, const int* uidx,
              int flooring, float eps, cudaStream_t st, const cf* C = nullptr, double* q = nullptr);
+// r2part / r2 (optional, AuxIVA): the apply sweep of the covariance-domain kernel also emits r2[b,n,j] = sum_i |y_new|^2
+// through the partials r2part[B, ssbk_iss1_r2_groups(I), N, J] (only when ssbk_iss1_emits_r2(N, J))
 int ssbk_iss1(cf* Y, const float* phi, long long sb, long long sn, long long si, int B, int N, int I, int J,
-              int flooring, float eps, cudaStream_t st);
+              int flooring, float eps, cudaStream_t st, float* r2part = nullptr, float* r2 = nullptr);
+int ssbk_iss1_r2_groups(int I);
+int ssbk_iss1_emits_r2(int N, int J);
 // pairs (host, 2*n_pairs, already wrapped into [0, N)); _update_spatial_model.py:197-314
 int ssbk_iss2(cf* Y, const float* phi, long long sb, long long sn, long long si, int B, int N, int I, int J,
               const int* pairs, int n_pairs, int flooring, float eps, cudaStream_t st);

@@ -11,7 +11,7 @@ namespace {
 
 constexpr int MAXN = SSB_MAX_SOURCES;
 
-__global__ void k_inv(const cd* __restrict__ A, cd* __restrict__ Ainv, int n_mat, int N) {
+__global__ void k_inv(const cd* __restrict__ A, cd* __restrict__ Ainv, int n_mat, int N, int* __restrict__ status) {
   const int mat = blockIdx.x * blockDim.x + threadIdx.x;
   if (mat >= n_mat) return;
   cd M[MAXN * 2 * MAXN];
@@ -21,13 +21,15 @@ __global__ void k_inv(const cd* __restrict__ A, cd* __restrict__ Ainv, int n_mat
       M[r * ld + c] = A[(size_t)mat * N * N + r * N + c];
       M[r * ld + N + c] = cd_make(r == c ? 1.0 : 0.0, 0.0);
     }
-  thread_gauss_jordan(M, N, N, ld);
+  bool sing;
+  thread_gauss_jordan(M, N, N, ld, &sing);
+  if (sing) atomicOr(status, SSB_STATUS_SINGULAR);
   for (int r = 0; r < N; ++r)
     for (int c = 0; c < N; ++c) Ainv[(size_t)mat * N * N + r * N + c] = M[r * ld + N + c];
 }
 
 __global__ void k_solve(const cd* __restrict__ A, const cd* __restrict__ Bm, cd* __restrict__ X, int n_mat, int N,
-                        int R) {
+                        int R, int* __restrict__ status) {
   const int mat = blockIdx.x * blockDim.x + threadIdx.x;
   if (mat >= n_mat) return;
   cd M[MAXN * 2 * MAXN];
@@ -36,7 +38,9 @@ __global__ void k_solve(const cd* __restrict__ A, const cd* __restrict__ Bm, cd*
     for (int c = 0; c < N; ++c) M[r * ld + c] = A[(size_t)mat * N * N + r * N + c];
     for (int c = 0; c < R; ++c) M[r * ld + N + c] = Bm[(size_t)mat * N * R + r * R + c];
   }
-  thread_gauss_jordan(M, N, R, ld);
+  bool sing;
+  thread_gauss_jordan(M, N, R, ld, &sing);
+  if (sing) atomicOr(status, SSB_STATUS_SINGULAR);
   for (int r = 0; r < N; ++r)
     for (int c = 0; c < R; ++c) X[(size_t)mat * N * R + r * R + c] = M[r * ld + N + c];
 }
@@ -142,14 +146,15 @@ __global__ void k_eigh(const cd* __restrict__ Ain, const cd* __restrict__ Bin, i
 extern "C" int ssb_inv(const void* A, void* Ainv, int n_mat, int N, void* stream) {
   SSB_REQUIRE(N >= 1 && N <= MAXN, "inv: N=%d unsupported (1..%d)", N, MAXN);
   if (n_mat <= 0) return 0;
-  k_inv<<<blocks_for(n_mat, 64), 64, 0, (cudaStream_t)stream>>>((const cd*)A, (cd*)Ainv, n_mat, N);
+  k_inv<<<blocks_for(n_mat, 64), 64, 0, (cudaStream_t)stream>>>((const cd*)A, (cd*)Ainv, n_mat, N, ssb_status_word());
   return ssb_check_launch("inv", (cudaStream_t)stream);
 }
 
 extern "C" int ssb_solve(const void* A, const void* B, void* X, int n_mat, int N, int R, void* stream) {
   SSB_REQUIRE(N >= 1 && N <= MAXN && R >= 1 && R <= MAXN, "solve: N=%d R=%d unsupported (1..%d)", N, R, MAXN);
   if (n_mat <= 0) return 0;
-  k_solve<<<blocks_for(n_mat, 64), 64, 0, (cudaStream_t)stream>>>((const cd*)A, (const cd*)B, (cd*)X, n_mat, N, R);
+  k_solve<<<blocks_for(n_mat, 64), 64, 0, (cudaStream_t)stream>>>((const cd*)A, (const cd*)B, (cd*)X, n_mat, N, R,
+                                                               ssb_status_word());
   return ssb_check_launch("solve", (cudaStream_t)stream);
 }
 

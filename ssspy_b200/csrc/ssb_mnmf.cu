@@ -253,7 +253,8 @@ __global__ void __launch_bounds__(MW * 32) km_rowloss(const cf* __restrict__ X, 
 
 // Qinv[b,i] = Q[b,i]^-1 (complex128), one lane group per bin
 template <int N>
-__global__ void __launch_bounds__(MW * 32) km_qinv(const cf* __restrict__ Q, cd* __restrict__ Qinv, int n_mat) {
+__global__ void __launch_bounds__(MW * 32) km_qinv(const cf* __restrict__ Q, cd* __restrict__ Qinv, int n_mat,
+                                                   int* __restrict__ status) {
   constexpr int GS = GroupShape<N>::GS, GW = GroupShape<N>::GW;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int grp = lane / GS, r = lane - grp * GS, gbase = grp * GS;
@@ -266,7 +267,9 @@ __global__ void __launch_bounds__(MW * 32) km_qinv(const cf* __restrict__ Q, cd*
     a[c] = (r < N) ? cf2cd(Q[((size_t)mat * N + r) * N + c]) : cd_make(0, 0);
     rhs[c] = cd_make(r == c ? 1.0 : 0.0, 0);
   }
-  group_solve<N, N, GS>(a, rhs, r, gbase);
+  bool sing;
+  group_solve<N, N, GS>(a, rhs, r, gbase, nullptr, &sing);
+  if (sing && valid && r == 0) atomicOr(status, SSB_STATUS_SINGULAR);  // np.linalg.inv(Q) raises (mnmf.py:1198)
   if (valid && r < N) {
 #pragma unroll
     for (int c = 0; c < N; ++c) Qinv[((size_t)mat * N + r) * N + c] = rhs[c];
@@ -407,7 +410,7 @@ int ssbk_mnmf_rowloss(const cf* X, const float* T, const float* V, const float* 
 int ssbk_mnmf_separate(const cf* X, const float* T, const float* V, const cf* Q, const float* D, cd* Qinv, cf* Y, int B,
                        int N, int I, int J, int K, int ref, int flooring, float eps, cudaStream_t st, const cd* Lleft) {
   SSB_REQUIRE(ref >= 0 && ref < N, "reference_id=%d out of range for N=%d", ref, N);
-  SSB_DISPATCH_N(N, km_qinv<NN><<<blocks_for((long long)B * I, MW * GroupShape<NN>::GW), MW * 32, 0, st>>>(Q, Qinv, B * I));
+  SSB_DISPATCH_N(N, km_qinv<NN><<<blocks_for((long long)B * I, MW * GroupShape<NN>::GW), MW * 32, 0, st>>>(Q, Qinv, B * I, ssb_status_word()));
   if (ssb_check_launch("mnmf_qinv", st)) return 1;
   if (Lleft != nullptr) {
     SSB_DISPATCH_N(N, km_leftmul<NN><<<blocks_for((long long)B * I, 64), 64, 0, st>>>(Lleft, Qinv, B * I));

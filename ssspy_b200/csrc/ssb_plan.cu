@@ -100,6 +100,33 @@ extern "C" int ssb_profile_end(char* buf, size_t buf_bytes) {
   return 0;
 }
 
+// ---- device status word -----------------------------------------------------------------------------------------
+static int* g_status_dev[SSB_MAX_DEVICES] = {};
+static std::mutex g_status_mu;
+
+int* ssb_status_word() {
+  const int dev = ssb_current_device();
+  std::lock_guard<std::mutex> lk(g_status_mu);
+  if (g_status_dev[dev] == nullptr) {
+    int* p = nullptr;
+    if (cudaMalloc(&p, sizeof(int)) == cudaSuccess && cudaMemset(p, 0, sizeof(int)) == cudaSuccess) g_status_dev[dev] = p;
+    else cudaGetLastError();
+  }
+  return g_status_dev[dev];  // NULL only when the device cannot allocate 4 bytes: the next launch fails loudly
+}
+
+// Reads and clears the status word of the current device after everything enqueued on `stream` (synchronises it).
+extern "C" int ssb_status_fetch(int* flags, void* stream) {
+  SSB_REQUIRE(flags != nullptr, "flags output is NULL");
+  int* w = ssb_status_word();
+  SSB_REQUIRE(w != nullptr, "no device status word (is a CUDA device available?)");
+  cudaStream_t st = (cudaStream_t)stream;
+  SSB_CUDA(cudaMemcpyAsync(flags, w, sizeof(int), cudaMemcpyDeviceToHost, st));
+  SSB_CUDA(cudaMemsetAsync(w, 0, sizeof(int), st));
+  SSB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
 extern "C" const char* ssb_last_error(void) { return g_err; }
 extern "C" int ssb_version(void) { return SSB_VERSION; }
 extern "C" int ssb_device_count(int* count) {
@@ -157,6 +184,10 @@ struct ssb_plan {
   cd* Mwinv = nullptr;    // [B,I,N,N] M^-1 = L
   double* ldM = nullptr;  // [B,I] log|det M|
   int* wsync = nullptr;   // [B,I] 1: Wk holds the whitened image of Wexp
+  // AuxIVA-ISS1: r2[b,n,j] = sum_i |y|^2 comes out of the apply sweep of the previous iteration (ssb_spatial.cu
+  // k_iss1_cov); trusted only inside ssb_run, where nothing else touches Y between two iterations
+  float* r2part = nullptr;  // [B, groups, N, J]
+  bool r2_valid = false;
   bool part() const { return cfg.partitioning != 0; }
   bool mnmf() const { return cfg.model == SSB_MODEL_FASTMNMF_GAUSS; }
   // modes whose state lives in Y (no demixing filter): ISS1 / ISS2 / IPA
@@ -197,6 +228,10 @@ size_t carve(ssb_plan* p, char* base) {
   p->big3 = p->mnmf() ? cv.take<float>(B * N * I * J) : nullptr;
   p->phi_iva = cv.take<float>(B * N * J);
   p->r2 = cv.take<float>(B * N * J);
+  const bool iva = c.model == SSB_MODEL_IVA_LAPLACE || c.model == SSB_MODEL_IVA_GAUSS;
+  p->r2part = (iva && c.spatial == SSB_SPATIAL_ISS1 && ssbk_iss1_emits_r2(c.n_sources, c.n_frames))
+                  ? cv.take<float>(B * (size_t)ssbk_iss1_r2_groups(c.n_bins) * N * J)
+                  : nullptr;
   p->U = cv.take<cf>(B * I * N * N * N);
   p->C = cv.take<cf>(B * I * N * N);
   p->S = cv.take<cf>(B * I * N * N);
@@ -461,6 +496,7 @@ int ilrma_loss(ssb_plan* p, double* loss, cudaStream_t st) {
 // r2 over all sources from the current state
 int iva_norm_all(ssb_plan* p, cudaStream_t st) {
   const ssb_config& c = p->cfg;
+  if (p->r2_valid) return 0;  // r2 of the current Y was emitted by the last ISS1 apply sweep
   return ssbk_iva_norm2(p->Xk, p->iss() ? nullptr : p->Wk, p->Y, nullptr, c.n_sources, p->r2, c.n_batch, c.n_sources,
                         c.n_bins, c.n_frames, st);
 }
@@ -490,8 +526,11 @@ int iva_spatial(ssb_plan* p, cudaStream_t st) {
   }
   TRY(iva_norm_all(p, st));
   TRY(ssbk_iva_phi(p->r2, p->variance, 0, nullptr, N, p->phi_iva, c.model, B, N, I, J, c.flooring, c.eps, st));
-  if (c.spatial == SSB_SPATIAL_ISS1)
-    return ssbk_iss1(p->Y, p->phi_iva, (long long)N * J, J, 0, B, N, I, J, c.flooring, c.eps, st);
+  if (c.spatial == SSB_SPATIAL_ISS1) {
+    TRY(ssbk_iss1(p->Y, p->phi_iva, (long long)N * J, J, 0, B, N, I, J, c.flooring, c.eps, st, p->r2part, p->r2));
+    p->r2_valid = p->r2part != nullptr;
+    return 0;
+  }
   if (c.spatial == SSB_SPATIAL_ISS2)  // iva.py:1968-2066: weights once, then every pair
     return ssbk_iss2(p->Y, p->phi_iva, (long long)N * J, J, 0, B, N, I, J, c.pairs, c.n_pairs, c.flooring, c.eps, st);
   if (c.spatial == SSB_SPATIAL_IPA)  // iva.py:2068-2176
@@ -690,6 +729,7 @@ extern "C" int ssb_plan_prepare(ssb_plan* p, void* stream) {
 
 extern "C" int ssb_update_source_model(ssb_plan* p, void* stream) {
   TRY(require_bound(p));
+  p->r2_valid = false;
   TRY(w_enter(p, (cudaStream_t)stream));
   if (p->mnmf()) return mnmf_source(p, (cudaStream_t)stream);
   if (p->fdica()) return 0;  // no source parameters
@@ -706,6 +746,7 @@ extern "C" int ssb_update_source_part(ssb_plan* p, int part, void* stream) {
 
 extern "C" int ssb_update_spatial_model(ssb_plan* p, void* stream) {
   TRY(require_bound(p));
+  p->r2_valid = false;
   cudaStream_t st = (cudaStream_t)stream;
   TRY(w_enter(p, st));
   if (p->mnmf()) TRY(mnmf_spatial(p, st));
@@ -796,14 +837,17 @@ extern "C" int ssb_update_once(ssb_plan* p, void* stream) {
   TRY(require_bound(p));
   // the caller may have rewritten V since the last call: the pre-split copy is only trusted inside ssb_run
   p->fused.vs_valid = false;
+  p->r2_valid = false;
   TRY(w_enter(p, (cudaStream_t)stream));
   TRY(update_once_impl(p, (cudaStream_t)stream));
+  p->r2_valid = false;
   return w_exit(p, (cudaStream_t)stream);
 }
 
 extern "C" int ssb_compute_loss(ssb_plan* p, double* loss, void* stream) {
   TRY(require_bound(p));
   SSB_REQUIRE(loss != nullptr, "loss output is NULL");
+  p->r2_valid = false;
   TRY(w_enter(p, (cudaStream_t)stream));
   return loss_impl(p, loss, (cudaStream_t)stream);
 }
@@ -811,9 +855,11 @@ extern "C" int ssb_compute_loss(ssb_plan* p, double* loss, void* stream) {
 namespace {
 // SSB_FUSE_ITER (read at every call so that tests can toggle it): 1 = inside ssb_run, GaussILRMA-IP1 with two sources
 // runs the spatial update of iteration t and the basis update of iteration t + 1 as one kernel (kf_cov_ip1_basis)
-int fuse_iter_enabled() {
+int fuse_iter_enabled(const ssb_config* c) {
   const char* e = getenv("SSB_FUSE_ITER");
-  return e ? (atoi(e) & 1) : 0;  // bits 1, 2: kernel variants, see launch_coop
+  // default: on with the TMA tile kernels (ssb_tma.cu: second pass served by L2), off with the cp.async kernel of
+  // round 1 (its second pass misses L2).  bits 1, 2, 3 select variants of the latter, see launch_coop
+  return e ? (atoi(e) & 1) : ((ssb_tma_mask(c) & 4) ? 1 : 0);
 }
 
 // n_iter x update_once (ilrma.py:900-922) regrouped as
@@ -841,11 +887,12 @@ int run_fused_iterations(ssb_plan* p, int n_iter, cudaStream_t st) {
 extern "C" int ssb_run(ssb_plan* p, int n_iter, double* loss, void* stream) {
   TRY(require_bound(p));
   p->fused.vs_valid = false;
+  p->r2_valid = false;
   if (n_iter <= 0) return 0;
   // the whole loop stays in the whitened domain: one import before, one export after
   TRY(w_enter(p, (cudaStream_t)stream));
   if (loss == nullptr && n_iter >= 2 && p->ilrma() && p->cfg.fast_path && !p->iss() &&
-      ssb_fused_iter_fusable(&p->cfg, &p->fused) && fuse_iter_enabled()) {
+      ssb_fused_iter_fusable(&p->cfg, &p->fused) && fuse_iter_enabled(&p->cfg)) {
     const int rc = run_fused_iterations(p, n_iter, (cudaStream_t)stream);
     p->fused.vs_valid = false;
     if (rc) return rc;
@@ -856,6 +903,7 @@ extern "C" int ssb_run(ssb_plan* p, int n_iter, double* loss, void* stream) {
     if (loss) TRY(loss_impl(p, loss + (size_t)it * p->cfg.n_batch, (cudaStream_t)stream));
   }
   p->fused.vs_valid = false;
+  p->r2_valid = false;
   return w_exit(p, (cudaStream_t)stream);
 }
 

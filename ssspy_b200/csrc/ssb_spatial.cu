@@ -352,9 +352,10 @@ __device__ __forceinline__ void group_emit_q(const cd (&wrow)[N], cf* su, const 
 template <int N>
 __global__ void __launch_bounds__(QW * 32) kq_ip1(cf* __restrict__ W, const cf* __restrict__ U, int n_mat,
                                                   int flooring, double eps, const cf* __restrict__ Cn,
-                                                  double* __restrict__ qn) {
+                                                  double* __restrict__ qn, int* __restrict__ status) {
   constexpr int GS = GroupShape<N>::GS, GW = GroupShape<N>::GW;
   __shared__ cf s_u[QW][GW][N * N];
+  bool any_sing = false;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int grp = lane / GS, r = lane - grp * GS, gbase = grp * GS;
   const int mat_raw = (blockIdx.x * QW + warp) * GW + grp;
@@ -372,7 +373,9 @@ __global__ void __launch_bounds__(QW * 32) kq_ip1(cf* __restrict__ W, const cf* 
     cd a[N], rhs[1];
     group_row_times<N>(wrow, su, a);
     rhs[0] = cd_make(r == n ? 1.0 : 0.0, 0);
-    group_solve<N, 1, GS>(a, rhs, r, gbase);
+    bool sing;
+    group_solve<N, 1, GS>(a, rhs, r, gbase, nullptr, &sing);
+    any_sing = any_sing || sing;
     // w = rhs (component r on lane r);  wUw = Re(w^H U_n w)
     cd t = cd_make(0, 0);
 #pragma unroll
@@ -394,6 +397,7 @@ __global__ void __launch_bounds__(QW * 32) kq_ip1(cf* __restrict__ W, const cf* 
 #pragma unroll
     for (int c = 0; c < N; ++c) W[((size_t)mat * N + r) * N + c] = cd2cf(wrow[c]);
   }
+  if (any_sing && valid && r == 0) atomicOr(status, SSB_STATUS_SINGULAR);
   if (Cn != nullptr) group_emit_q<N>(wrow, su, Cn + (size_t)mat * N * N, r, valid, qn + (size_t)mat * N + r);
 }
 
@@ -422,8 +426,9 @@ __device__ __forceinline__ void group_quad2(const cd (&P)[2], const cf* su, int 
 template <int N>
 __global__ void __launch_bounds__(QW * 32) kq_ip2(cf* __restrict__ W, const cf* __restrict__ U, int n_mat,
                                                   PairList pl, int flooring, double eps, const cf* __restrict__ Cn,
-                                                  double* __restrict__ qn) {
+                                                  double* __restrict__ qn, int* __restrict__ status) {
   constexpr int GS = GroupShape<N>::GS, GW = GroupShape<N>::GW;
+  bool any_sing = false;
   __shared__ cf s_um[QW][GW][N * N];
   __shared__ cf s_un[QW][GW][N * N];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -447,11 +452,13 @@ __global__ void __launch_bounds__(QW * 32) kq_ip2(cf* __restrict__ W, const cf* 
     group_row_times<N>(wrow, sum_, a);
     Pm[0] = cd_make(r == m ? 1.0 : 0.0, 0);
     Pm[1] = cd_make(r == n ? 1.0 : 0.0, 0);
-    group_solve<N, 2, GS>(a, Pm, r, gbase);
+    bool sing_m, sing_n;
+    group_solve<N, 2, GS>(a, Pm, r, gbase, nullptr, &sing_m);
     group_row_times<N>(wrow, sun_, a);
     Pn[0] = cd_make(r == m ? 1.0 : 0.0, 0);
     Pn[1] = cd_make(r == n ? 1.0 : 0.0, 0);
-    group_solve<N, 2, GS>(a, Pn, r, gbase);
+    group_solve<N, 2, GS>(a, Pn, r, gbase, nullptr, &sing_n);
+    any_sing = any_sing || sing_m || sing_n;
     cd Gm[4], Gn[4];
     group_quad2<N, GS>(Pm, sum_, r, gbase, Gm);
     group_quad2<N, GS>(Pn, sun_, r, gbase, Gn);
@@ -497,6 +504,7 @@ __global__ void __launch_bounds__(QW * 32) kq_ip2(cf* __restrict__ W, const cf* 
 #pragma unroll
     for (int c = 0; c < N; ++c) W[((size_t)mat * N + r) * N + c] = cd2cf(wrow[c]);
   }
+  if (any_sing && valid && r == 0) atomicOr(status, SSB_STATUS_SINGULAR);
   if (Cn != nullptr) group_emit_q<N>(wrow, sum_, Cn + (size_t)mat * N * N, r, valid, qn + (size_t)mat * N + r);
 }
 
@@ -717,10 +725,15 @@ __global__ void __launch_bounds__(ISS_NW * 32) k_iss1_cta(cf* __restrict__ Y, co
 // A[m][r] and row r of U_m), and one sweep applying A (the slab is re-read from L2: the footprint of all resident
 // warps is a few tens of MB).  No shared-memory slab, no CTA barrier, any n_frames.
 constexpr int ISSC_W = 4;  // warps (= bins) per block
+//
+// r2part != NULL (AuxIVA inside ssb_run): the apply sweep also accumulates |y_new|^2 per (source, frame) over the bins a
+// warp walks (grid = (groups, mixtures); warp w of group gx takes bins gx * W + w, + groups * W, ...), in shared memory
+// owned by the warp (lane j-strided: no atomics), and the block writes one partial r2part[b, gx, n, j]: the next
+// iteration's r[n, j] = ||y_n[:, j]|| (ssspy/bss/iva.py:1961-1964) then needs no pass over Y at all.
 template <int N>
 __global__ void __launch_bounds__(ISSC_W * 32) k_iss1_cov(cf* __restrict__ Y, const float* __restrict__ phi,
-                                                          long long sb, long long sn, long long si, int n_bins_total,
-                                                          int I, int J, int flooring, float eps) {
+                                                          long long sb, long long sn, long long si, int I, int J,
+                                                          int flooring, float eps, float* __restrict__ r2part) {
   constexpr int NO = N * (N - 1) / 2;      // off-diagonal pairs (a < c)
   constexpr int NV = N * N;                // reals per source: NO (re, im) pairs + N diagonals
   constexpr int NVAL = N * NV;             // statistics per bin
@@ -728,12 +741,17 @@ __global__ void __launch_bounds__(ISSC_W * 32) k_iss1_cov(cf* __restrict__ Y, co
   constexpr int PER = NVP / 32;
   __shared__ float s_red[ISSC_W][NVP];
   __shared__ cf s_A[ISSC_W][N * N];
+  extern __shared__ float s_r2[];  // [ISSC_W][N][J] when r2part != NULL
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int bi = blockIdx.x * ISSC_W + w;
-  if (bi >= n_bins_total) return;
-  const int b = bi / I, i = bi - b * I;
-  const size_t base = ((size_t)b * N * I + i) * J;
+  const int b = blockIdx.y;
   const size_t cs = (size_t)I * J;
+  float* my_r2 = s_r2 + (size_t)w * N * J;
+  if (r2part != nullptr) {
+    for (int e = lane; e < N * J; e += 32) my_r2[e] = 0.f;
+    __syncwarp();
+  }
+  for (int i = blockIdx.x * ISSC_W + w; i < I; i += gridDim.x * ISSC_W) {
+  const size_t base = ((size_t)b * N * I + i) * J;
   const float* ph0 = phi + (size_t)b * sb + (size_t)i * si;
   // ---- sweep 1: weighted covariances ---------------------------------------------------------------------------
   // accumulators as (re, im) pairs [and pairs of diagonal entries], one packed FFMA2 per pair and source
@@ -909,8 +927,30 @@ __global__ void __launch_bounds__(ISSC_W * 32) k_iss1_cov(cf* __restrict__ Y, co
         o = __ffma2_rn(yy[q], as_[p * N + q], o);
       }
       Y[base + p * cs + j] = o;
+      if (r2part != nullptr) my_r2[p * J + j] += fmaf(o.x, o.x, o.y * o.y);
     }
   }
+  __syncwarp();  // s_red / s_A are reused by this warp's next bin
+  }
+  if (r2part != nullptr) {
+    __syncthreads();
+    float* out = r2part + ((size_t)b * gridDim.x + blockIdx.x) * N * J;
+    for (int e = threadIdx.x; e < N * J; e += ISSC_W * 32) {
+      float v = 0.f;
+#pragma unroll
+      for (int ww = 0; ww < ISSC_W; ++ww) v += s_r2[(size_t)ww * N * J + e];
+      out[e] = v;
+    }
+  }
+}
+
+// r2[b, n, j] = sum_g r2part[b, g, n, j] (fixed order)
+__global__ void k_r2_sum(const float* __restrict__ part, float* __restrict__ r2, int G, int NJ, int B) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (e >= NJ) return;
+  float v = 0.f;
+  for (int g = 0; g < G; ++g) v += part[((size_t)b * G + g) * NJ + e];
+  r2[(size_t)b * NJ + e] = v;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1063,7 +1103,8 @@ __global__ void __launch_bounds__(ISS_NW * 32) k_iss2_cta(cf* __restrict__ Y, co
 // scale_out[mat*N + n] (optional) receives (W^-1)[ref, n] for the projection-back normalisation.
 template <int N>
 __global__ void __launch_bounds__(WPB * 32) k_pb_w(const cf* __restrict__ W, cf* __restrict__ Wout,
-                                                   cf* __restrict__ scale_out, int n_mat, int ref) {
+                                                   cf* __restrict__ scale_out, int n_mat, int ref,
+                                                   int* __restrict__ status) {
   __shared__ cd sA[WPB][N * 2 * N];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mat = blockIdx.x * WPB + wib;
@@ -1074,7 +1115,9 @@ __global__ void __launch_bounds__(WPB * 32) k_pb_w(const cf* __restrict__ W, cf*
     A[e] = c < N ? cf2cd(W[(size_t)mat * N * N + r * N + c]) : cd_make(c - N == r ? 1.0 : 0.0, 0);
   }
   __syncwarp();
-  warp_gauss_jordan(A, N, N, 2 * N, lane);
+  bool sing;
+  warp_gauss_jordan(A, N, N, 2 * N, lane, nullptr, &sing);
+  if (sing && lane == 0) atomicOr(status, SSB_STATUS_SINGULAR);  // np.linalg.inv raises here (projection_back.py:89)
   // scale[n] = Winv[ref][n] = A[ref][N + n]
   for (int e = lane; e < N * N; e += 32) {
     int n = e / N;
@@ -1092,7 +1135,8 @@ __global__ void __launch_bounds__(WPB * 32) k_pb_w(const cf* __restrict__ W, cf*
 // One warp per (b,i); N+1 passes over the slab (Gram matrix, then one row of A Bm^H per pass).
 template <int N>
 __global__ void __launch_bounds__(WPB * 32) k_cross_solve(const cf* __restrict__ Am, const cf* __restrict__ Bm,
-                                                          cf* __restrict__ S, int B, int I, int J) {
+                                                          cf* __restrict__ S, int B, int I, int J,
+                                                          int* __restrict__ status) {
   __shared__ cd sG[WPB][N * 2 * N];  // [Gram | I] -> Gram^-1
   __shared__ cd sC[WPB][N * N];      // A Bm^H
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1158,7 +1202,9 @@ __global__ void __launch_bounds__(WPB * 32) k_cross_solve(const cf* __restrict__
     }
   }
   __syncwarp();
-  warp_gauss_jordan(G, N, N, 2 * N, lane);
+  bool sing;
+  warp_gauss_jordan(G, N, N, 2 * N, lane, nullptr, &sing);
+  if (sing && lane == 0) atomicOr(status, SSB_STATUS_SINGULAR);  // np.linalg.inv of the Gram matrix (projection_back.py:110)
   for (int e = lane; e < N * N; e += 32) {
     int r = e / N, c = e - r * N;
     cd s = cd_make(0, 0);
@@ -1256,7 +1302,8 @@ int ssbk_wcov(const cf* X, const float* phi, long long sb, long long sn, long lo
 
 int ssbk_ip1(cf* W, const cf* U, int n_mat, int N, int flooring, float eps, cudaStream_t st, const cf* C, double* q) {
   SSB_DISPATCH_N(N, kq_ip1<NN><<<blocks_for(n_mat, QW * GroupShape<NN>::GW), QW * 32, 0, st>>>(W, U, n_mat, flooring,
-                                                                                                 (double)eps, C, q));
+                                                                                                 (double)eps, C, q,
+                                                                                                 ssb_status_word()));
   return ssb_check_launch("update_by_ip1", st);
 }
 
@@ -1277,12 +1324,20 @@ int ssbk_ip2(cf* W, const cf* U, int n_mat, int N, const int* pairs, int n_pairs
   }
   if (n_pairs == 0) return 0;
   SSB_DISPATCH_N(N, kq_ip2<NN><<<blocks_for(n_mat, QW * GroupShape<NN>::GW), QW * 32, 0, st>>>(W, U, n_mat, pl, flooring,
-                                                                                                 (double)eps, C, q));
+                                                                                                 (double)eps, C, q,
+                                                                                                 ssb_status_word()));
   return ssb_check_launch("update_by_ip2", st);
 }
 
+int ssbk_iss1_r2_groups(int I) { return (I + ISSC_W * 16 - 1) / (ISSC_W * 16) < 1 ? 1 : (I + ISSC_W * 16 - 1) / (ISSC_W * 16); }
+
+int ssbk_iss1_emits_r2(int N, int J) {
+  const char* e = getenv("SSB_ISS_COV");
+  return N <= 4 && (e == nullptr || atoi(e) != 0) && (size_t)ISSC_W * N * J * sizeof(float) <= 160 * 1024;
+}
+
 int ssbk_iss1(cf* Y, const float* phi, long long sb, long long sn, long long si, int B, int N, int I, int J,
-              int flooring, float eps, cudaStream_t st) {
+              int flooring, float eps, cudaStream_t st, float* r2part, float* r2) {
   // CTA-per-bin shared-memory variants when the (source x frame) slab of Y + weights fits one CTA
   const size_t slab = (size_t)N * J * (sizeof(cf) + sizeof(float));
   static int cov_mode = -1;  // SSB_ISS_COV: 1 (default) covariance-domain kernel for N <= 4, 0 step-by-step kernels
@@ -1291,12 +1346,30 @@ int ssbk_iss1(cf* Y, const float* phi, long long sb, long long sn, long long si,
     cov_mode = e ? atoi(e) : 1;
   }
   if (N <= 4 && cov_mode) {
-    const int nb = B * I;
-    const int blocks = (nb + ISSC_W - 1) / ISSC_W;
-    if (N == 2) k_iss1_cov<2><<<blocks, ISSC_W * 32, 0, st>>>(Y, phi, sb, sn, si, nb, I, J, flooring, eps);
-    else if (N == 3) k_iss1_cov<3><<<blocks, ISSC_W * 32, 0, st>>>(Y, phi, sb, sn, si, nb, I, J, flooring, eps);
-    else k_iss1_cov<4><<<blocks, ISSC_W * 32, 0, st>>>(Y, phi, sb, sn, si, nb, I, J, flooring, eps);
-    return ssb_check_launch("update_by_iss1", st);
+    const bool emit = r2part != nullptr && r2 != nullptr && ssbk_iss1_emits_r2(N, J);
+    // emitting: ~16 bins per warp (one partial per block and mixture); else one bin per warp as before
+    const int groups = emit ? ssbk_iss1_r2_groups(I) : (I + ISSC_W - 1) / ISSC_W;
+    const size_t sm = emit ? (size_t)ISSC_W * N * J * sizeof(float) : 0;
+    float* part = emit ? r2part : nullptr;
+    dim3 grid(groups, B);
+    static bool attr_dev[SSB_MAX_DEVICES] = {};
+    bool& attr_set = attr_dev[ssb_current_device()];
+    if (!attr_set) {
+      SSB_CUDA(cudaFuncSetAttribute(k_iss1_cov<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      SSB_CUDA(cudaFuncSetAttribute(k_iss1_cov<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      SSB_CUDA(cudaFuncSetAttribute(k_iss1_cov<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      attr_set = true;
+    }
+    if (N == 2) k_iss1_cov<2><<<grid, ISSC_W * 32, sm, st>>>(Y, phi, sb, sn, si, I, J, flooring, eps, part);
+    else if (N == 3) k_iss1_cov<3><<<grid, ISSC_W * 32, sm, st>>>(Y, phi, sb, sn, si, I, J, flooring, eps, part);
+    else k_iss1_cov<4><<<grid, ISSC_W * 32, sm, st>>>(Y, phi, sb, sn, si, I, J, flooring, eps, part);
+    if (ssb_check_launch("update_by_iss1", st)) return 1;
+    if (emit) {
+      dim3 g2(blocks_for((long long)N * J, 256), B);
+      k_r2_sum<<<g2, 256, 0, st>>>(r2part, r2, groups, N * J, B);
+      return ssb_check_launch("iva_r2_from_iss1", st);
+    }
+    return 0;
   }
   if (slab <= 200 * 1024) {
     SSB_DISPATCH_N(N, {
@@ -1343,12 +1416,14 @@ int ssbk_iss2(cf* Y, const float* phi, long long sb, long long sn, long long si,
 
 int ssbk_pb_w(const cf* W, cf* Wout, cf* scale_out, int n_mat, int N, int ref, cudaStream_t st) {
   SSB_REQUIRE(ref >= 0 && ref < N, "projection_back: reference_id=%d out of range for N=%d", ref, N);
-  SSB_DISPATCH_N(N, k_pb_w<NN><<<blocks_for(n_mat, WPB), WPB * 32, 0, st>>>(W, Wout, scale_out, n_mat, ref));
+  SSB_DISPATCH_N(N, k_pb_w<NN><<<blocks_for(n_mat, WPB), WPB * 32, 0, st>>>(W, Wout, scale_out, n_mat, ref,
+                                                                            ssb_status_word()));
   return ssb_check_launch("projection_back_w", st);
 }
 
 int ssbk_cross_solve(const cf* A, const cf* Bm, cf* S, int B, int N, int I, int J, cudaStream_t st) {
-  SSB_DISPATCH_N(N, k_cross_solve<NN><<<blocks_for((long long)B * I, WPB), WPB * 32, 0, st>>>(A, Bm, S, B, I, J));
+  SSB_DISPATCH_N(N, k_cross_solve<NN><<<blocks_for((long long)B * I, WPB), WPB * 32, 0, st>>>(A, Bm, S, B, I, J,
+                                                                                              ssb_status_word()));
   return ssb_check_launch("cross_solve", st);
 }
 

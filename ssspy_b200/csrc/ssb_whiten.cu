@@ -221,7 +221,7 @@ __global__ void k_w_export(const cf* __restrict__ Ww, const cd* __restrict__ M, 
 // One thread per bin, fp64 Gauss-Jordan with partial pivoting on [W~ | I].  scale_out[mat, n] (optional) = s_n.
 template <int N>
 __global__ void k_pb_whitened(cf* __restrict__ Ww, const cd* __restrict__ Minv, cf* __restrict__ scale_out, int n_mat,
-                              int ref) {
+                              int ref, int* __restrict__ status) {
   const int mat = blockIdx.x * blockDim.x + threadIdx.x;
   if (mat >= n_mat) return;
   cd A[N][2 * N];
@@ -249,6 +249,7 @@ __global__ void k_pb_whitened(cf* __restrict__ Ww, const cd* __restrict__ Minv, 
         A[p][c] = A[piv][c];
         A[piv][c] = t;
       }
+    if (cd_abs2(A[p][p]) == 0.0) atomicOr(status, SSB_STATUS_SINGULAR);  // np.linalg.inv raises (projection_back.py:89)
     const cd ipv = cd_inv(A[p][p]);
     for (int c = 0; c < 2 * N; ++c) A[p][c] = cd_mul(A[p][c], ipv);
     for (int r = 0; r < N; ++r) {
@@ -306,7 +307,8 @@ int ssbk_w_export(const cf* Ww, const cd* M, cf* W, cf* Wexp, int* wsync, int n_
 }
 
 int ssbk_pb_whitened(cf* Ww, const cd* Minv, cf* scale_out, int n_mat, int N, int ref, cudaStream_t st) {
-  SSB_DISPATCH_N(N, k_pb_whitened<NN><<<blocks_for(n_mat, 64), 64, 0, st>>>(Ww, Minv, scale_out, n_mat, ref));
+  SSB_DISPATCH_N(N, k_pb_whitened<NN><<<blocks_for(n_mat, 64), 64, 0, st>>>(Ww, Minv, scale_out, n_mat, ref,
+                                                                            ssb_status_word()));
   return ssb_check_launch("whiten_projection_back", st);
 }
 

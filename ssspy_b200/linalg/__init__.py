@@ -32,6 +32,7 @@ def inv(a):
     out = torch.empty_like(A)
     n_mat = A.numel() // (N * N) if N else 0
     _lib.call("ssb_inv", A.data_ptr(), out.data_ptr(), n_mat, N, _device.stream_ptr())
+    _lib.check_status()  # numpy.linalg.LinAlgError("Singular matrix") like np.linalg.inv
     return _finish(out, is_t, real)
 
 
@@ -57,6 +58,7 @@ def solve(a, b):
     X = torch.empty_like(Bm)
     n_mat = A.numel() // (N * N)
     _lib.call("ssb_solve", A.data_ptr(), Bm.data_ptr(), X.data_ptr(), n_mat, N, R, _device.stream_ptr())
+    _lib.check_status()  # numpy.linalg.LinAlgError("Singular matrix") like np.linalg.solve (_solve.py:15)
     if vec:
         X = X[..., 0]
     return _finish(X, is_t, real_a and real_b)

@@ -191,8 +191,9 @@ def test_ipa_plan_validation():
 
 
 def test_bench_reference_arm_contract():
-    """`bench.py --impl reference` (CPU arm, the oracle port on the host cores): one JSON line with the keys of the
-    bench contract; ranks other than 0 exit 0 without output."""
+    """`bench.py --impl reference` (CPU arm: the unmodified reference's update_once from baseline/_ref, $SSSPY_REF or
+    /root/reference when importable, else the oracle port, on the host cores): one JSON line with the keys of the bench
+    contract; ranks other than 0 exit 0 without output."""
     import json
     import subprocess
     import sys
@@ -205,7 +206,13 @@ def test_bench_reference_arm_contract():
     for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
                 "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert key in line, key
-    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] in ("reference", "port")
+    if os.path.isdir(os.path.join(root, "baseline", "_ref", "ssspy")) or os.path.isdir("/root/reference/ssspy"):
+        assert line["cpu_baseline"]["kind"] == "reference"
+    # the port is still there for a box without the reference
+    port = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root,
+                          env=dict(os.environ, SSSPY_REF="/nonexistent", SSB_BENCH_FORCE_PORT="1"))
+    assert port.returncode == 0 and json.loads(port.stdout.strip().splitlines()[-1])["cpu_baseline"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     other = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root, env=env)

@@ -889,3 +889,75 @@ def test_separate_validates_shapes_and_reference_id_wraps():
     np.testing.assert_array_equal(projection_back(Wm, reference_id=-1), projection_back(Wm, reference_id=N - 1))
     with pytest.raises(IndexError):
         GaussILRMA(n_basis=K, reference_id=N)(X[0], n_iter=1, basis=T, activation=V)
+
+
+def test_singular_inputs_raise_linalg_error_like_the_reference():
+    """Exactly singular per-bin matrices: the reference raises numpy.linalg.LinAlgError("Singular matrix") from
+    np.linalg.solve / inv (ssspy/linalg/_solve.py:15, ssspy/algorithm/projection_back.py:89); the CUDA solvers set a
+    device flag on an exactly zero pivot and the host classes re-raise it at their next synchronisation point."""
+    from ssspy_b200 import linalg
+    from ssspy_b200.algorithm import projection_back
+    from ssspy_b200.bss import AuxLaplaceIVA, GaussILRMA
+    from ssspy_b200.bss._update_spatial_model import update_by_ip1
+    A = np.zeros((3, 2, 2), dtype=np.complex128)
+    A[0] = np.eye(2)
+    A[1] = [[1, 2], [2, 4]]  # rank one: second pivot is exactly zero
+    A[2] = np.eye(2)
+    with pytest.raises(np.linalg.LinAlgError, match="Singular matrix"):
+        linalg.inv(A)
+    with pytest.raises(np.linalg.LinAlgError):
+        linalg.solve(A, np.ones((3, 2), dtype=np.complex128))
+    with pytest.raises(np.linalg.LinAlgError):
+        np.linalg.inv(A)  # the reference's call
+    ok = linalg.inv(np.tile(np.eye(2, dtype=np.complex128) * 2, (3, 1, 1)))  # the flag does not stick
+    np.testing.assert_allclose(ok, np.tile(np.eye(2) * 0.5, (3, 1, 1)))
+    with pytest.raises(np.linalg.LinAlgError):
+        projection_back(A.astype(np.complex64), reference_id=0)
+    # a silent channel: every weighted covariance is singular, W U is singular, np.linalg.solve raises in update_by_ip1
+    rng = np.random.default_rng(5)
+    N, I, J = 2, 5, 16
+    U = np.zeros((I, N, N, N), dtype=np.complex128)
+    U[..., 0, 0] = 1.0
+    W = np.tile(np.eye(N, dtype=np.complex128), (I, 1, 1))
+    with pytest.raises(np.linalg.LinAlgError):
+        update_by_ip1(W.copy(), U)
+    X = rng.standard_normal((N, I, J)) + 1j * rng.standard_normal((N, I, J))
+    X[1] = 0.0
+    for sep in (GaussILRMA(n_basis=2, rng=np.random.default_rng(0)), AuxLaplaceIVA()):
+        with pytest.raises(np.linalg.LinAlgError):
+            sep(X, n_iter=2)
+    # and a regular mixture right after runs clean
+    Xg = rng.standard_normal((N, I, J)) + 1j * rng.standard_normal((N, I, J))
+    Y = GaussILRMA(n_basis=2, rng=np.random.default_rng(0))(Xg, n_iter=2)
+    assert np.all(np.isfinite(Y))
+
+
+@pytest.mark.parametrize("N,I,J,K,n_iter", [(2, 37, 48, 5, 4), (2, 257, 512, 16, 4), (2, 70, 528, 24, 3), (2, 20, 16, 4, 2),
+                                            (4, 130, 96, 9, 3), (4, 33, 272, 20, 3), (8, 21, 96, 24, 3), (8, 17, 64, 3, 3),
+                                            (2, 1025, 512, 16, 3)])
+def test_tma_tile_kernels_match_cp_async_kernels_and_oracle(N, I, J, K, n_iter, monkeypatch):
+    """The TMA-fed tile kernels (ssb_tma.cu: cp.async.bulk.tensor + mbarrier rings; SSB_TMA=7 forces every one of them:
+    basis N = 2 / 4 / 8, covariance N = 2, and inside ssb_run the fused covariance + IP1 + basis kernel N = 2) against
+    the cp.async kernels (SSB_TMA=0) and the fp64 oracle: ragged bin tiles, K <= 16 and K > 16, a single 16-frame step,
+    odd step counts, several tiles per persistent CTA (the last shape with batch 6: 390 tiles on 296 resident CTAs)."""
+    from oracle import ilrma as oilrma
+    from ssspy_b200.bss import GaussILRMA
+    from ssspy_b200.utils.synth import make_batch, make_nmf_init
+    B = 6 if I > 1000 else 3
+    X = make_batch(B, N, I, J, config_id=29, mode="mix")
+    T, V = make_nmf_init(N, I, J, K, seed=13)
+    out = {}
+    for tma in ("0", "7"):
+        monkeypatch.setenv("SSB_TMA", tma)
+        for rec in (True, False):  # with the loss: update_once path; without: ssb_run (fused iterations at N = 2)
+            m = GaussILRMA(n_basis=K, spatial_algorithm="IP", record_loss=rec)
+            m.chunk_size = B
+            out[tma, rec] = (m(X, n_iter=n_iter, basis=T, activation=V), m.basis.copy(), m.activation.copy())
+    for rec in (True, False):
+        for a, b in zip(out["7", rec], out["0", rec]):
+            assert relerr(a, b) < 2e-5
+    for b in range(B if I < 1000 else 1):
+        st = oilrma.run(X[b], T, V, n_iter, spatial_algorithm="IP", record_loss=False)
+        for rec in (True, False):
+            assert relerr(out["7", rec][0][b], st["Y"]) < TOL_Y
+            assert relerr(out["7", rec][1][b], st["T"]) < TOL_TV

@@ -1,0 +1,28 @@
+set -x
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+timeout 2400 python -m pytest tests -m gpu -q -rfEs -x > gpurun_out/r2g_gputests.log 2>&1
+tail -6 gpurun_out/r2g_gputests.log
+for cfg in "default:" "fuse0:SSB_FUSE_ITER=0" "tma0:SSB_TMA=0"; do
+  name=${cfg%%:*}; envs=${cfg#*:}
+  env $envs timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r2g_bench_$name.json 2> gpurun_out/r2g_bench_$name.err
+  python - <<PY
+import json
+d=json.load(open("gpurun_out/r2g_bench_$name.json"))
+print("$name", "ms/step %.4f"%d["ms_per_step"], "frac %.3f"%d["roofline"]["frac"], d["roofline"]["kernels_ms_per_step"])
+PY
+done
+for n in 4 8; do
+  timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-e2e --sources $n > gpurun_out/r2g_bench_n$n.json 2> gpurun_out/r2g_bench_n$n.err
+  python - <<PY
+import json
+for f in ("gpurun_out/r2g_bench_n$n.json",):
+    d=json.load(open(f)); print(f, "ms/step %.4f"%d["ms_per_step"], "frac %.3f"%d["roofline"]["frac"], d["roofline"]["kernels_ms_per_step"])
+PY
+done
+timeout 600 python bench.py --config 3 --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r2g_bench_c3.json 2> gpurun_out/r2g_bench_c3.err
+python - <<PY
+import json
+d=json.load(open("gpurun_out/r2g_bench_c3.json")); print("c3", "ms/step %.4f"%d["ms_per_step"], "frac %.3f"%d["roofline"]["frac"], d["roofline"]["kernels_ms_per_step"])
+PY
+tail -3 gpurun_out/r2g_bench_c3.err
