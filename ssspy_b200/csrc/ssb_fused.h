@@ -50,6 +50,9 @@ void* ssb_coop_vs(const ssb_config* cfg, void* ws);
 void* ssb_coop_ts(const ssb_config* cfg, void* ws);
 // TMA-fed tile kernels (ssb_tma.cu): cp.async.bulk.tensor + mbarrier rings; N = 2, 4, 8, n_frames % 16 == 0, K <= 32
 int ssb_tma_mask(const ssb_config* cfg);
+// tensor-core weighted covariance for N = 8 (ssb_covmma.cu): U = sum_j phi G as split-bf16 mma, X by TMA
+int ssb_cov_mma_supported(const ssb_config* cfg, const cf* X);
+int ssb_cov_mma(const ssb_config* cfg, const cf* X, const float* T, const void* Vs, cf* U, cudaStream_t st);
 int ssb_tma_supported(const ssb_config* cfg);
 int ssb_tma_basis(const ssb_config* cfg, const cf* X, const cf* W, float* T, const void* Vs, float* P, void* Ts,
                   cudaStream_t st);

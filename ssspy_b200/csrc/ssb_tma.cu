@@ -111,11 +111,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(done)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(1000000)  // suspend-time hint (ns): sleep in hardware rather than spin in the loop
         : "memory");
   } while (!done);
 }
@@ -271,18 +271,17 @@ __global__ void __launch_bounds__(TileShape<N, KS, FS_>::NT, KS == 1 ? 2 : 1)
   float* const ucomb = ucomb0 + tb * S::U_FLOATS;  // this tile's combine scratch
   float* const sc = sc0 + tb * S::C_FLOATS;
   const int rs = t & 1;  // the lane's bin of its pair (rows g, g + 8) in the per-bin algebra between the passes
-  int xk = 0, vk = 0;    // stages / chunks consumed so far by this warp (ring positions and phases)
+  int xslot = 0, xphase = 0;  // X stage consumed next by this warp: slot in the ring and phase parity of its barrier
+  int vk = 0;                 // V chunks consumed so far by this warp
 
   // ---- requests: X stages of this frame range (issued by lane 0 of its source-0 warp) and V chunks of this warp ----
   const bool range_active = c_lo < c_hi;
   const bool x_issuer = n == 0 && lane == 0;
   const uint64_t pol = l2_evict_first_policy();
   StepIter xit{first_group, 0, c_lo, 0};  // next X stage to request; every lane tracks it, one lane issues
-  int xreq = 0;
-  auto x_request = [&]() {
+  auto x_request = [&](int st) {  // into slot st (== requests so far % XS)
     if (xit.tile >= ntiles) return;
     if (x_issuer) {
-      const int st = xreq % XS;
       const int xb_ = tile_b(xit.tile), ti0 = tile_i0(xit.tile), s = 2 * xit.c + xit.half;
       const uint32_t dst = xring_s + (uint32_t)((rg * XS + st) * XSB), bar = xfull(rg, st);
       mbar_expect_tx(bar, XSB);
@@ -295,7 +294,6 @@ __global__ void __launch_bounds__(TileShape<N, KS, FS_>::NT, KS == 1 ? 2 : 1)
         tma_load_3d(dst + N * 1024, &tmX, 32 * s + 16, ti0, xb_ * N, bar);
       }
     }
-    ++xreq;
     ++xit.half;
     if (xit.half == 2 || 2 * xit.c + xit.half >= nsteps) {
       xit.half = 0;
@@ -317,23 +315,9 @@ __global__ void __launch_bounds__(TileShape<N, KS, FS_>::NT, KS == 1 ? 2 : 1)
     if (n != 0) {
       __syncwarp();
       bar_arrive_id<N * 32>(S::RING_BAR0 + rg * XS + xst);
-      if (xit.tile < ntiles) {  // keep the iterator in step with the issuer (cheap, uniform)
-        ++xreq;
-        ++xit.half;
-        if (xit.half == 2 || 2 * xit.c + xit.half >= nsteps) {
-          xit.half = 0;
-          if (++xit.c >= c_hi) {
-            xit.c = c_lo;
-            if (++xit.pass == NPASS) {
-              xit.pass = 0;
-              xit.tile = next_group(xit.tile);
-            }
-          }
-        }
-      }
     } else {
       bar_sync_id<N * 32>(S::RING_BAR0 + rg * XS + xst);
-      x_request();
+      x_request(xst);
     }
   };
   const unsigned char* vsrc = reinterpret_cast<const unsigned char*>(Vs);
@@ -361,7 +345,7 @@ __global__ void __launch_bounds__(TileShape<N, KS, FS_>::NT, KS == 1 ? 2 : 1)
     v_request();
     v_request();
 #pragma unroll
-    for (int e = 0; e < XS; ++e) x_request();
+    for (int e = 0; e < XS; ++e) x_request(e);
   }
 
 #pragma unroll 1
@@ -421,7 +405,7 @@ __global__ void __launch_bounds__(TileShape<N, KS, FS_>::NT, KS == 1 ? 2 : 1)
         for (int half = 0; half < 2; ++half) {
           const int s = 2 * c + half;
           if (s >= nsteps) break;
-          const int xst = xk % XS;
+          const int xst = xslot;
           const uint32_t vb1 = l1base + vst * CHB + half * (16 * JKS * 2);
           const uint32_t xb = xlane + xst * XSB;
           float Rc[2][4];
@@ -436,7 +420,7 @@ __global__ void __launch_bounds__(TileShape<N, KS, FS_>::NT, KS == 1 ? 2 : 1)
               mma_split(Rc[h], Thi[ks], Tlo[ks], bh0, bh1, bl0, bl1);
             }
           }
-          mbar_wait(xfull(rg, xst), (xk / XS) & 1);  // behind the first GEMM, which only needs V
+          mbar_wait(xfull(rg, xst), xphase);  // behind the first GEMM, which only needs V
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const float (&R)[4] = Rc[h];
@@ -452,7 +436,10 @@ __global__ void __launch_bounds__(TileShape<N, KS, FS_>::NT, KS == 1 ? 2 : 1)
             }
           }
           x_release_and_request(xst);
-          ++xk;
+          if (++xslot == XS) {
+            xslot = 0;
+            xphase ^= 1;
+          }
         }
         __syncwarp();
         v_request();  // this warp is done with the chunk: its buffer takes the chunk two ahead
@@ -600,7 +587,7 @@ __global__ void __launch_bounds__(TileShape<N, KS, FS_>::NT, KS == 1 ? 2 : 1)
         for (int half = 0; half < 2; ++half) {
           const int s = 2 * c + half;
           if (s >= nsteps) break;
-          const int xst = xk % XS;
+          const int xst = xslot;
           const uint32_t voff = vst * CHB + half * (16 * JKS * 2);
           const uint32_t vb1 = l1base + voff, vb2 = l2base + voff;
           const uint32_t xb = xlane + xst * XSB;
@@ -618,7 +605,7 @@ __global__ void __launch_bounds__(TileShape<N, KS, FS_>::NT, KS == 1 ? 2 : 1)
             }
           }
           // ---- elementwise: P = |w^H x|^2, A = P / R^2, B = 1 / R ----
-          mbar_wait(xfull(rg, xst), (xk / XS) & 1);  // behind the first GEMM, which only needs V
+          mbar_wait(xfull(rg, xst), xphase);  // behind the first GEMM, which only needs V
           uint32_t Ahi[4], Alo[4], Bhi[4], Blo[4];
           float* const po[2] = {pout0 + (size_t)s * 256, pout1 + (size_t)s * 256};
 #pragma unroll
@@ -643,7 +630,10 @@ __global__ void __launch_bounds__(TileShape<N, KS, FS_>::NT, KS == 1 ? 2 : 1)
               Blo[h * 2 + rr] = sb.lo;
             }
           x_release_and_request(xst);
-          ++xk;
+          if (++xslot == XS) {
+            xslot = 0;
+            xphase ^= 1;
+          }
           // ---- GEMM2: num += A V^T, den += B V^T (contraction over the 16 frames) ----
 #pragma unroll
           for (int qi = 0; qi < 2 * KS; ++qi) {

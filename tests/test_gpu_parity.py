@@ -19,13 +19,11 @@ TOL_TV = 1e-4
 
 
 def tol_seeded(spatial, base=TOL_Y):
-    """IP2 on the seeded (non-golden) inputs: with uniform random NMF initialisation the two weighted
-    covariances of a pair are nearly proportional in the first iterations, which makes the 2x2
-    generalised eigenvectors ill-conditioned.  Measured with the fp64 oracle: merely rounding U to
-    complex64 moves the final Y by 1.3e-4 (N=2, I=1025, J=512, 2 iterations) versus 5e-7 for IP1
-    ("IP2 sensitivity").  fp32 state cannot track the fp64 trajectory to 1e-4 there, so
-    those cases are checked at 5e-3 (the golden IP2 fixtures stay at 1e-4)."""
-    return 5e-3 if spatial == "IP2" else base
+    """Seeded (non-golden) inputs are held to the same bounds as the golden fixtures for every spatial algorithm.  Round 1
+    needed 5e-3 for IP2: with complex64 state the rounding of the weighted covariances was amplified by the condition
+    number of the mixture covariance (3.8e-2 on Y at BASELINE config 4).  The demixing-filter modes now iterate in the
+    whitened domain (ssb_whiten.cu), which removes that factor: measured 2e-6 .. 8e-5 on a B200."""
+    return base
 
 
 def _floor_fn(name):
@@ -243,10 +241,7 @@ def test_batched_input_equals_per_mixture_oracle(spatial):
     for b in range(B):
         st = oilrma.run(X[b], T[b], V[b], n_iter, spatial_algorithm=spatial)
         assert relerr(Y[b], st["Y"]) < tol_seeded(spatial)
-        if spatial == "IP2":
-            np.testing.assert_allclose(np.asarray(m.loss)[:, b], st["loss"], rtol=1e-3)
-        else:
-            assert_loss_close(np.asarray(m.loss)[:, b], st["loss"])
+        assert_loss_close(np.asarray(m.loss)[:, b], st["loss"])
         assert relerr(m.basis[b], st["T"]) < tol_seeded(spatial, TOL_TV)
 
 
@@ -382,10 +377,7 @@ def test_full_size_properties_and_one_mixture_oracle(N, spatial):
     Y1 = m1(X[0], n_iter=2, basis=T, activation=V)
     st = oilrma.run(X[0], T, V, 2, spatial_algorithm=spatial)
     assert relerr(Y1, st["Y"]) < tol_seeded(spatial)
-    if spatial == "IP2":
-        np.testing.assert_allclose(m1.loss, st["loss"], rtol=1e-3)
-    else:
-        assert_loss_close(m1.loss, st["loss"])
+    assert_loss_close(m1.loss, st["loss"])
 
 
 @pytest.mark.parametrize("N,I,J,K,spatial", [(2, 37, 48, 5, "IP"), (3, 130, 272, 16, "IP"), (4, 20, 32, 20, "IP2"),
@@ -419,10 +411,7 @@ def test_fused_tensor_core_path_matches_oracle_and_modular(N, I, J, K, spatial):
         assert relerr(Yf[b], st["Y"]) < tol_seeded(spatial)
         assert relerr(fused.basis[b], st["T"]) < tol_seeded(spatial, TOL_TV)
         assert relerr(fused.activation[b], st["V"]) < tol_seeded(spatial, TOL_TV)
-        if spatial == "IP2":
-            np.testing.assert_allclose(np.asarray(fused.loss)[:, b], st["loss"], rtol=1e-3)
-        else:
-            assert_loss_close(np.asarray(fused.loss)[:, b], st["loss"])
+        assert_loss_close(np.asarray(fused.loss)[:, b], st["loss"])
 
 
 @pytest.mark.parametrize("model", ["laplace", "gauss"])
@@ -442,10 +431,7 @@ def test_aux_iva_fused_covariance_and_group_solvers(model, N, I, J, spatial):
     for b in range(B):
         st = oiva.run(X[b], n_iter, spatial_algorithm=spatial, model=model)
         assert relerr(Y[b], st["Y"]) < tol_seeded(spatial)
-        if spatial == "IP2":
-            np.testing.assert_allclose(np.asarray(m.loss)[:, b], st["loss"], rtol=1e-3, atol=1e-3)
-        else:
-            assert_loss_close(np.asarray(m.loss)[:, b], st["loss"])
+        assert_loss_close(np.asarray(m.loss)[:, b], st["loss"])
 
 
 @pytest.mark.parametrize("name", golden_cases("mnmf_"))
@@ -489,7 +475,7 @@ def test_fast_gauss_mnmf_batched_vs_oracle_and_rng(alg, J, K):
         Q = np.tile(np.eye(N, dtype=np.complex128), (I, 1, 1))
         st = omnmf.run(X[b], T, V, Q, D, n_iter, algorithm=alg)
         assert relerr(Y[b], st["Y"]) < tol_seeded(alg)
-        np.testing.assert_allclose(np.asarray(m.loss)[:, b], st["loss"], rtol=1e-3 if alg == "IP2" else 1e-5, atol=1e-4)
+        np.testing.assert_allclose(np.asarray(m.loss)[:, b], st["loss"], rtol=1e-5, atol=1e-4)
     # update_once through the split phase calls gives the same state as the fused call
     a = FastGaussMNMF(n_basis=K, diagonalizer_algorithm=alg, rng=np.random.default_rng(5))
     a(X[0], n_iter=2)
@@ -696,7 +682,7 @@ def test_aux_laplace_fdica_batched_vs_oracle(spatial, N, I, J):
         st = ofdica.run(X[b], n_iter, spatial_algorithm=spatial)
         np.testing.assert_array_equal(m.permutation[b], st["perms"])
         assert relerr(Y[b], st["Y"]) < tol_seeded(spatial)
-        np.testing.assert_allclose(np.asarray(m.loss)[:, b], st["loss"], rtol=1e-3 if spatial == "IP2" else 1e-5, atol=1e-4)
+        np.testing.assert_allclose(np.asarray(m.loss)[:, b], st["loss"], rtol=1e-5, atol=1e-4)
     # generic contrast callables cannot run on the device
     from ssspy_b200.bss import AuxFDICA
     with pytest.raises(NotImplementedError, match="no CPU fallback"):
