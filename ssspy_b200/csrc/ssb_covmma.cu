@@ -7,10 +7,10 @@
 // reduction is a GEMM once the Hermitian products are formed first (they do not depend on the source):
 //   G[j, col]   = the 64 real numbers Re / Im x_a conj(x_c) (a < c) and |x_a|^2 of frame j      (CUDA cores, once)
 //   U[n, col]   = sum_j phi[n, j] G[j, col]                                                    (tensor pipe)
-// per bin an (8 sources) x (64 columns) x (J frames) product.  Both operands are split into bf16 (hi, lo); the sixteen
-// rows of the m16n8k16 A operand hold phi_hi of the eight sources on rows 0-7 and phi_lo on rows 8-15, so ONE mma per
-// (column tile, G part) yields phi_hi G and phi_lo G together and their sum at the end keeps all four partial products:
-// 16 mma per (bin, 16 frames) instead of 1152 FFMA per lane-frame group.
+// per bin an (8 sources) x (64 columns) x (J frames) product.  G is split into bf16 (hi, lo), phi into (hi, mid, lo); the
+// sixteen rows of the m16n8k16 A operand hold phi_hi of the eight sources on rows 0-7 and phi_mid on rows 8-15, so ONE
+// mma per (column tile, G part) yields phi_hi G and phi_mid G together; a second A operand carries phi_lo on rows 0-7
+// and multiplies G_hi only: 24 mma per (bin, 16 frames) instead of 1152 FFMA per lane-frame group.
 //
 // CTA = one tile of 16 bins, 16 warps, one barrier per 16-frame step:
 //   phase A  warp (source n, frame half h): R[16 bins x 8 frames] = T_n V_n on the tensor pipe (3 mma per 16 basis
@@ -18,7 +18,7 @@
 //            ([bin][16 rows][16 frames] bf16, 48-byte rows and 784-byte bins: conflict-free stores and ldmatrix)
 //   barrier  (the previous step's X stage and V chunk are free behind it: lane 0 of warp 0 / of warps 0-7 re-arm them)
 //   phase B  warp = bin: A from ldmatrix, G from the bin's X slab (5 channels per lane: lane group g pairs channel g
-//            with g+1, g+2, g+3, g+4; groups 4-7 use their last slot for two diagonal entries), 16 mma, fp32 accumulators
+//            with g+1, g+2, g+3, g+4; groups 4-7 use their last slot for two diagonal entries), 24 mma, fp32 accumulators
 // X arrives by TMA (cp.async.bulk.tensor, tensor map with the plane axis INSIDE the bin axis so that a box lands as
 // [bin][channel][64 bytes]: lanes of one quarter warp that read different channels hit different banks), V chunks by
 // bulk copies, all on mbarriers; there is no empty-barrier: the per-step CTA barrier is the release.
@@ -34,31 +34,39 @@
 namespace {
 
 constexpr int PADH = 8, JCV = 32, XS = 3, N = 8;
-constexpr int PHI_ROW = 48, PHI_BIN = 16 * PHI_ROW + 16;  // bytes: 784 per bin
+constexpr int PHI_ROW = 48, PHI_BIN = 24 * PHI_ROW + 16;  // bytes: 1168 per bin (24 rows: hi, mid, lo of 8 sources)
 
 struct Split {
   uint32_t hi, lo;
 };
 __device__ __forceinline__ Split split2(float a, float b) {
-  const uint32_t ua = __float_as_uint(a), ub = __float_as_uint(b);
-  Split s;
-  s.hi = __byte_perm(ua, ub, 0x7632);
-  const float ra = a - __uint_as_float(ua & 0xffff0000u);
-  const float rb = b - __uint_as_float(ub & 0xffff0000u);
-  __nv_bfloat162 l = __floats2bfloat162_rn(ra, rb);
-  s.lo = *reinterpret_cast<uint32_t*>(&l);
-  return s;
-}
-// Round-to-nearest split: hi = bf16_rn(x), lo = bf16_rn(x - hi): |x - hi - lo| <= 2^-18 |x|, one bit better than the
-// truncating split used for the NMF operands; the covariance feeds the per-bin eigenproblems of IP2, where the operand
-// rounding is what limits the agreement with the fp64 reference.
-__device__ __forceinline__ Split split2_rn(float a, float b) {
   Split s;
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   s.hi = *reinterpret_cast<uint32_t*>(&h);
   const float ra = a - __uint_as_float(s.hi << 16);
   const float rb = b - __uint_as_float(s.hi & 0xffff0000u);
   __nv_bfloat162 l = __floats2bfloat162_rn(ra, rb);
+  s.lo = *reinterpret_cast<uint32_t*>(&l);
+  return s;
+}
+// Three-way split for the weights: hi + mid + lo with |x - hi - mid - lo| <= 2^-27 |x|.  The rounding of phi[n, j] is shared
+// by every entry of U_n, so a two-way split (2^-18) perturbs the covariance coherently: in the fp64 oracle, rounding phi
+// to hi + lo alone moves the final Y of an IP2 run by 2e-5 (N = 8, J = 1024, whitened, 5 iterations), the same split of
+// the products G by 3e-6, and hi + mid + lo is indistinguishable from fp32 (2.4e-7).
+struct Split3 {
+  uint32_t hi, mid, lo;
+};
+__device__ __forceinline__ Split3 split3(float a, float b) {
+  Split3 s;
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  s.hi = *reinterpret_cast<uint32_t*>(&h);
+  const float ra = a - __uint_as_float(s.hi << 16);
+  const float rb = b - __uint_as_float(s.hi & 0xffff0000u);
+  __nv_bfloat162 m = __floats2bfloat162_rn(ra, rb);
+  s.mid = *reinterpret_cast<uint32_t*>(&m);
+  const float qa = ra - __uint_as_float(s.mid << 16);
+  const float qb = rb - __uint_as_float(s.mid & 0xffff0000u);
+  __nv_bfloat162 l = __floats2bfloat162_rn(qa, qb);
   s.lo = *reinterpret_cast<uint32_t*>(&l);
   return s;
 }
@@ -78,6 +86,9 @@ __device__ __forceinline__ void ldsm_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2
                : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
                : "r"(addr)
                : "memory");
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t& r0, uint32_t& r1, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr) : "memory");
 }
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
@@ -132,7 +143,9 @@ struct CovShape8 {
   static constexpr int SMEM = X_BYTES + V_BYTES + PHI_BYTES + NBAR * 8 + 128;
 };
 
-template <int KS>
+// PHI3: three-way weights (IP2, whose pairwise eigenproblems amplify the coherent rounding of phi); IP1 keeps the
+// two-way split (its result is 1.4e-6 from the oracle at N = 8) and 16 mma per step: rows 8-15 then carry phi_lo.
+template <int KS, bool PHI3>
 __global__ void __launch_bounds__(512, 1)
     kc_cov_mma8(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ T, const __nv_bfloat16* __restrict__ Vs,
                 cf* __restrict__ U, int I, int J, int K, int nchunk) {
@@ -198,7 +211,7 @@ __global__ void __launch_bounds__(512, 1)
   // V fragments of frames [8 hA, 8 hA + 8) of a step: matrices (hi k0-7, hi k8-15, lo k0-7, lo k8-15)
   const uint32_t vlane = vring_s + (uint32_t)(nA * 2 * CHB) + (mid >> 1) * (JCV * JKS * 2) +
                          ((8 * hA + mrow) * JKS + (mid & 1) * 8) * 2;
-  // phi store: bins g, g + 8; rows nA (hi), 8 + nA (lo); frames 8 hA + 2 t, + 1
+  // phi store: bins g, g + 8; rows nA (hi), 8 + nA (mid), 16 + nA (lo); frames 8 hA + 2 t, + 1
   const uint32_t plane_st = phi_s + (uint32_t)(g * PHI_BIN + nA * PHI_ROW + (8 * hA + 2 * t) * 2);
 
   // ---- phase B role: bin bb = warp ----
@@ -206,16 +219,25 @@ __global__ void __launch_bounds__(512, 1)
   const bool bin_valid = i0 + bb < I;
   // A operand (16 x 16 bf16): matrices (rows 0-7, k 0-7), (rows 8-15, k 0-7), (rows 0-7, k 8-15), (rows 8-15, k 8-15)
   const uint32_t plane_ld = phi_s + (uint32_t)(bb * PHI_BIN + (((mid & 1) * 8 + mrow) * PHI_ROW) + (mid >> 1) * 16);
+  // second A operand: rows 0-7 = phi_lo (rows 16-23 of the bin), rows 8-15 = 0; matrices (k 0-7), (k 8-15)
+  const uint32_t plane_ld2 = phi_s + (uint32_t)(bb * PHI_BIN + ((16 + mrow) * PHI_ROW) + (mid & 1) * 16);
   // X of this bin: channel c_k = (g + k) & 7, frames 8 h + 2 t, + 1 at  stage + h * XHB + bb * 512 + c_k * 64 + t * 16
   uint32_t xoff[5];
 #pragma unroll
   for (int k = 0; k < 5; ++k) xoff[k] = xring_s + (uint32_t)(bb * 512 + ((g + k) & 7) * 64 + t * 16);
   const bool diag_slot = g >= 4;  // the (g, g + 4) slot of lane groups 4-7 carries |x_g|^2 and |x_{g+4}|^2 instead
-  float D[8][4];
+  // D: the accumulator fragments of the running mma chain; every FLUSH steps they are added into Ssum with ordinary
+  // round-to-nearest FADDs and cleared.  The tensor pipe adds into its fp32 accumulator with truncation, so a chain over
+  // all J / 16 steps would bias the (positive) diagonal sums by about (J / 16) * 2^-24; chains of FLUSH = 2 keep the
+  // accumulation error at the level of the lane-partial sums of the FP32-pipe kernel (kf_cov_coop).
+  constexpr int FLUSH = 2;
+  float D[8][4], Ssum[8][2];
 #pragma unroll
-  for (int q = 0; q < 8; ++q)
+  for (int q = 0; q < 8; ++q) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) D[q][c] = 0.f;
+    Ssum[q][0] = Ssum[q][1] = 0.f;
+  }
 
 #pragma unroll 1
   for (int s = 0; s < nsteps; ++s) {
@@ -235,13 +257,20 @@ __global__ void __launch_bounds__(512, 1)
         mma16816(R, Tlo[ks], bl0, bl1);  // all four partial products: phase A is a small part of the step
       }
       // no floor on R (ilrma.py:1494-1498)
-      const Split p0 = split2_rn(fast_rcp(R[0]), fast_rcp(R[1]));  // bin g
-      const Split p1 = split2_rn(fast_rcp(R[2]), fast_rcp(R[3]));  // bin g + 8
+      const Split3 p0 = split3(fast_rcp(R[0]), fast_rcp(R[1]));  // bin g
+      const Split3 p1 = split3(fast_rcp(R[2]), fast_rcp(R[3]));  // bin g + 8
       const uint32_t pd = plane_st + (s & 1) * (16 * PHI_BIN);
       sts32(pd, p0.hi);
-      sts32(pd + 8 * PHI_ROW, p0.lo);
       sts32(pd + 8 * PHI_BIN, p1.hi);
-      sts32(pd + 8 * PHI_BIN + 8 * PHI_ROW, p1.lo);
+      if (PHI3) {
+        sts32(pd + 8 * PHI_ROW, p0.mid);
+        sts32(pd + 16 * PHI_ROW, p0.lo);
+        sts32(pd + 8 * PHI_BIN + 8 * PHI_ROW, p1.mid);
+        sts32(pd + 8 * PHI_BIN + 16 * PHI_ROW, p1.lo);
+      } else {  // hi + mid is the two-way split
+        sts32(pd + 8 * PHI_ROW, p0.mid);
+        sts32(pd + 8 * PHI_BIN + 8 * PHI_ROW, p1.mid);
+      }
     }
     __syncthreads();
     // behind the barrier every warp has left step s - 1: its X stage and (after an odd step) its V chunk are free
@@ -256,6 +285,8 @@ __global__ void __launch_bounds__(512, 1)
     mbar_wait(xfull(s % XS), (s / XS) & 1);
     uint32_t A[4];
     ldsm_x4(A[0], A[1], A[2], A[3], plane_ld + (s & 1) * (16 * PHI_BIN));
+    uint32_t A2[4] = {0u, 0u, 0u, 0u};
+    if (PHI3) ldsm_x2(A2[0], A2[2], plane_ld2 + (s & 1) * (16 * PHI_BIN));
     const uint32_t xst = (uint32_t)((s % XS) * XSB);
     float4 x0[2];  // channel c_0 = g: (re, im) of frames 8 h + 2 t, + 1
 #pragma unroll
@@ -284,15 +315,26 @@ __global__ void __launch_bounds__(512, 1)
           im[h][1] = fmaf(v11, xb.z, v21 * xb.w);
         }
       }
-      const Split r0 = split2_rn(re[0][0], re[0][1]), r1 = split2_rn(re[1][0], re[1][1]);
+      const Split r0 = split2(re[0][0], re[0][1]), r1 = split2(re[1][0], re[1][1]);
       mma16816(D[2 * qp], A, r0.hi, r1.hi);
       mma16816(D[2 * qp], A, r0.lo, r1.lo);
-      const Split m0 = split2_rn(im[0][0], im[0][1]), m1 = split2_rn(im[1][0], im[1][1]);
+      if (PHI3) mma16816(D[2 * qp], A2, r0.hi, r1.hi);  // phi_lo G_hi (phi_lo G_lo is below 2^-27)
+      const Split m0 = split2(im[0][0], im[0][1]), m1 = split2(im[1][0], im[1][1]);
       mma16816(D[2 * qp + 1], A, m0.hi, m1.hi);
       mma16816(D[2 * qp + 1], A, m0.lo, m1.lo);
+      if (PHI3) mma16816(D[2 * qp + 1], A2, m0.hi, m1.hi);
+    }
+    if ((s % FLUSH) == FLUSH - 1 || s == nsteps - 1) {  // rows g (phi_hi, phi_lo parts) + g + 8 (phi_mid part) of source g
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          Ssum[q][e] += D[q][e] + D[q][2 + e];
+          D[q][e] = D[q][2 + e] = 0.f;
+        }
     }
   }
-  // ---- U[b, i0 + bb, n = g, :, :]: rows g (phi_hi part) + g + 8 (phi_lo part); columns 2t, 2t + 1 of every tile ----
+  // ---- U[b, i0 + bb, n = g, :, :]: source g; columns 2t, 2t + 1 of every tile ----
   if (!bin_valid) return;
   const float invJ = 1.0f / (float)J;
   cf* u = U + (((size_t)b * I + i0 + bb) * N + g) * N * N;
@@ -301,8 +343,8 @@ __global__ void __launch_bounds__(512, 1)
     const int jc = 2 * t + e;  // column inside the tiles = lane group that produced it
 #pragma unroll
     for (int qp = 0; qp < 4; ++qp) {
-      const float re = (D[2 * qp][e] + D[2 * qp][2 + e]) * invJ;
-      const float im = (D[2 * qp + 1][e] + D[2 * qp + 1][2 + e]) * invJ;
+      const float re = Ssum[2 * qp][e] * invJ;
+      const float im = Ssum[2 * qp + 1][e] * invJ;
       if (qp < 3 || jc < 4) {
         const int a = jc, c = (jc + qp + 1) & 7;
         u[a * N + c] = make_float2(re, im);
@@ -349,7 +391,7 @@ int make_x_map_bin_major(CUtensorMap* tm, const cf* X, int B, int I, int J) {
              : 1;
 }
 
-template <int KS>
+template <int KS, bool PHI3>
 int launch_cov_mma8(const ssb_config* c, const cf* X, const float* T, const __nv_bfloat16* Vs, cf* U, cudaStream_t st) {
   using S = CovShape8<KS>;
   const int B = c->n_batch, I = c->n_bins, J = c->n_frames, K = c->n_basis;
@@ -358,23 +400,24 @@ int launch_cov_mma8(const ssb_config* c, const cf* X, const float* T, const __nv
   static bool attr_dev[SSB_MAX_DEVICES] = {};
   bool& attr_set = attr_dev[ssb_current_device()];
   if (!attr_set) {
-    SSB_CUDA(cudaFuncSetAttribute(kc_cov_mma8<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM));
+    SSB_CUDA(cudaFuncSetAttribute(kc_cov_mma8<KS, PHI3>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM));
     attr_set = true;
   }
   dim3 grid((I + 15) / 16, B);
-  kc_cov_mma8<KS><<<grid, 512, S::SMEM, st>>>(tm, T, Vs, U, I, J, K, (J + JCV - 1) / JCV);
+  kc_cov_mma8<KS, PHI3><<<grid, 512, S::SMEM, st>>>(tm, T, Vs, U, I, J, K, (J + JCV - 1) / JCV);
   return ssb_check_launch("mma_phi_cov", st);
 }
 
 }  // namespace
 
-// SSB_COV_MMA (read at every call): unset / 1 = tensor-core covariance at N = 8 for IP1, 2 = also for IP2, 0 = never
-// (kf_cov_coop on the FP32 pipe).  IP2 stays on the FP32-pipe kernel by default: its pairwise generalised eigenproblems
-// amplify the operand rounding of the split-bf16 products (2^-18 per operand) more than IP1 does; at BASELINE config 4
-// the final Y is 1.1e-4 from the fp64 oracle with this kernel against 7.3e-5 with kf_cov_coop, and the bound is 1e-4.
+// SSB_COV_MMA (read at every call): unset / 2 = tensor-core covariance at N = 8 for IP1 and IP2, 1 = IP1 only,
+// 0 = never (kf_cov_coop on the FP32 pipe).  IP2's pairwise generalised eigenproblems amplify the rounding of the
+// weights: with two-way operands BASELINE config 4 ended 1.1e-4 from the fp64 oracle (bound 1e-4; 7.3e-5 with
+// kf_cov_coop); with the three-way weights, flushed accumulators and round-to-nearest splits everywhere it is 3.9e-5
+// (profiles/r2_baseline_shapes_rn_split.txt), so IP2 runs here by default as well.
 int ssb_cov_mma_supported(const ssb_config* c, const cf* X) {
   const char* e = getenv("SSB_COV_MMA");
-  const int mode = e != nullptr ? atoi(e) : 1;
+  const int mode = e != nullptr ? atoi(e) : 2;
   if (mode == 0) return 0;
   if (c->spatial != SSB_SPATIAL_IP1 && mode < 2) return 0;
   if (c->n_sources != 8 || (c->n_frames % 16) != 0 || c->n_basis > 32) return 0;
@@ -387,6 +430,10 @@ int ssb_cov_mma_supported(const ssb_config* c, const cf* X) {
 }
 
 int ssb_cov_mma(const ssb_config* c, const cf* X, const float* T, const void* Vs, cf* U, cudaStream_t st) {
-  if (c->n_basis <= 16) return launch_cov_mma8<1>(c, X, T, (const __nv_bfloat16*)Vs, U, st);
-  return launch_cov_mma8<2>(c, X, T, (const __nv_bfloat16*)Vs, U, st);
+  const bool phi3 = c->spatial != SSB_SPATIAL_IP1;
+  if (c->n_basis <= 16)
+    return phi3 ? launch_cov_mma8<1, true>(c, X, T, (const __nv_bfloat16*)Vs, U, st)
+                : launch_cov_mma8<1, false>(c, X, T, (const __nv_bfloat16*)Vs, U, st);
+  return phi3 ? launch_cov_mma8<2, true>(c, X, T, (const __nv_bfloat16*)Vs, U, st)
+              : launch_cov_mma8<2, false>(c, X, T, (const __nv_bfloat16*)Vs, U, st);
 }

@@ -33,23 +33,53 @@ struct Split {
   uint32_t hi, lo;
 };
 
-// (a -> low half, b -> high half): hi = truncated bf16 pair, lo = bf16(rn) of the exact residuals
+// (a -> low half, b -> high half): hi = bf16(rn) pair, lo = bf16(rn) of the exact residuals: |x - hi - lo| <= 2^-18 |x| with
+// a random sign.  (A truncated hi leaves every lo >= 0, so the dropped lo * lo product biases each contraction by up to
+// 2^-16: measured as a 1e-5 relative error of T against the fp64 oracle, 6e-7 with this split; same instruction count.)
 __device__ __forceinline__ Split split2(float a, float b) {
-  const uint32_t ua = __float_as_uint(a), ub = __float_as_uint(b);
   Split s;
-  s.hi = __byte_perm(ua, ub, 0x7632);
-  const float ra = a - __uint_as_float(ua & 0xffff0000u);
-  const float rb = b - __uint_as_float(ub & 0xffff0000u);
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  s.hi = *reinterpret_cast<uint32_t*>(&h);
+  const float ra = a - __uint_as_float(s.hi << 16);
+  const float rb = b - __uint_as_float(s.hi & 0xffff0000u);
   __nv_bfloat162 l = __floats2bfloat162_rn(ra, rb);
   s.lo = *reinterpret_cast<uint32_t*>(&l);
   return s;
 }
 
 __device__ __forceinline__ void split1(float a, __nv_bfloat16* hi, __nv_bfloat16* lo) {
-  const uint32_t ua = __float_as_uint(a);
-  const unsigned short h = (unsigned short)(ua >> 16);
-  *reinterpret_cast<unsigned short*>(hi) = h;
-  *lo = __float2bfloat16_rn(a - __uint_as_float(ua & 0xffff0000u));
+  const __nv_bfloat16 h = __float2bfloat16_rn(a);
+  *hi = h;
+  *lo = __float2bfloat16_rn(a - __bfloat162float(h));
+}
+
+// Three-way splits (hi + mid + lo, residual 2^-27): kf_phi writes the weights the ISS kernels consume as an array, and
+// the ISS updates of an ill-conditioned bin amplify their relative error by 1e3 (measured: one bin of 1025 at 2.9e-3
+// with two-way operands, which alone put the whole Y at 1.2e-4 from the oracle; tools/diag_iss.py).
+struct Split3 {
+  uint32_t hi, mid, lo;
+};
+__device__ __forceinline__ Split3 split3(float a, float b) {
+  Split3 s;
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  s.hi = *reinterpret_cast<uint32_t*>(&h);
+  const float ra = a - __uint_as_float(s.hi << 16);
+  const float rb = b - __uint_as_float(s.hi & 0xffff0000u);
+  __nv_bfloat162 m = __floats2bfloat162_rn(ra, rb);
+  s.mid = *reinterpret_cast<uint32_t*>(&m);
+  const float qa = ra - __uint_as_float(s.mid << 16);
+  const float qb = rb - __uint_as_float(s.mid & 0xffff0000u);
+  __nv_bfloat162 l = __floats2bfloat162_rn(qa, qb);
+  s.lo = *reinterpret_cast<uint32_t*>(&l);
+  return s;
+}
+__device__ __forceinline__ void split1_3(float a, __nv_bfloat16* hi, __nv_bfloat16* mid, __nv_bfloat16* lo) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(a);
+  const float r = a - __bfloat162float(h);
+  const __nv_bfloat16 m = __float2bfloat16_rn(r);
+  *hi = h;
+  *mid = m;
+  *lo = __float2bfloat16_rn(r - __bfloat162float(m));
 }
 
 // D += A(16x16, row) * B(16x8, col), bf16 inputs, fp32 accumulate
@@ -415,7 +445,8 @@ __global__ void __launch_bounds__(FW * 32) kf_phi(const float* __restrict__ T, c
   constexpr int JKS = KP + PADH;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __nv_bfloat16* vjk_hi = reinterpret_cast<__nv_bfloat16*>(smem_raw);
-  __nv_bfloat16* vjk_lo = vjk_hi + JC * JKS;
+  __nv_bfloat16* vjk_mid = vjk_hi + JC * JKS;
+  __nv_bfloat16* vjk_lo = vjk_mid + JC * JKS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const size_t bn = blockIdx.y;
@@ -424,7 +455,7 @@ __global__ void __launch_bounds__(FW * 32) kf_phi(const float* __restrict__ T, c
   const int row[2] = {i0 + g, i0 + g + 8};
   const bool rvalid[2] = {row[0] < I, row[1] < I};
   const int rowc[2] = {min(row[0], I - 1), min(row[1], I - 1)};
-  uint32_t Thi[KS][4], Tlo[KS][4];
+  uint32_t Thi[KS][4], Tmid[KS][4], Tlo[KS][4];
 #pragma unroll
   for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
@@ -433,8 +464,9 @@ __global__ void __launch_bounds__(FW * 32) kf_phi(const float* __restrict__ T, c
 #pragma unroll
       for (int nb = 0; nb < 2; ++nb) {
         const int k0 = ks * 16 + nb * 8 + 2 * t;
-        const Split s = split2((k0 < K) ? tr[k0] : 0.f, (k0 + 1 < K) ? tr[k0 + 1] : 0.f);
+        const Split3 s = split3((k0 < K) ? tr[k0] : 0.f, (k0 + 1 < K) ? tr[k0 + 1] : 0.f);
         Thi[ks][nb * 2 + rr] = s.hi;
+        Tmid[ks][nb * 2 + rr] = s.mid;
         Tlo[ks][nb * 2 + rr] = s.lo;
       }
     }
@@ -454,9 +486,10 @@ __global__ void __launch_bounds__(FW * 32) kf_phi(const float* __restrict__ T, c
       for (int it = 0; it < NIT; ++it) {
         const int e = threadIdx.x + it * FW * 32;
         const int k = e / JC, jj = e - k * JC;
-        __nv_bfloat16 h, l;
-        split1(vals[it], &h, &l);
+        __nv_bfloat16 h, m, l;
+        split1_3(vals[it], &h, &m, &l);
         vjk_hi[jj * JKS + k] = h;
+        vjk_mid[jj * JKS + k] = m;
         vjk_lo[jj * JKS + k] = l;
       }
     }
@@ -464,13 +497,27 @@ __global__ void __launch_bounds__(FW * 32) kf_phi(const float* __restrict__ T, c
     if (!warp_active) continue;
     const int jend = min(JC, J - jc0);
     for (int jj = 0; jj < jend; jj += 8) {
+      // small terms first; every product down to 2^-18 of the result is kept (hi lo, lo hi, mid mid)
       float R[4] = {0.f, 0.f, 0.f, 0.f};
       const int fr = jj + g;
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
         const __nv_bfloat16* ph = vjk_hi + fr * JKS + ks * 16 + 2 * t;
+        const __nv_bfloat16* pm = vjk_mid + fr * JKS + ks * 16 + 2 * t;
         const __nv_bfloat16* pl = vjk_lo + fr * JKS + ks * 16 + 2 * t;
-        mma_split(R, Thi[ks], Tlo[ks], lds32(ph), lds32(ph + 8), lds32(pl), lds32(pl + 8));
+        const uint32_t h0 = lds32(ph), h1 = lds32(ph + 8), m0 = lds32(pm), m1 = lds32(pm + 8);
+        mma16816(R, Tlo[ks], h0, h1);
+        mma16816(R, Thi[ks], lds32(pl), lds32(pl + 8));
+        mma16816(R, Tmid[ks], m0, m1);
+      }
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const __nv_bfloat16* ph = vjk_hi + fr * JKS + ks * 16 + 2 * t;
+        const __nv_bfloat16* pm = vjk_mid + fr * JKS + ks * 16 + 2 * t;
+        const uint32_t h0 = lds32(ph), h1 = lds32(ph + 8);
+        mma16816(R, Tmid[ks], h0, h1);
+        mma16816(R, Thi[ks], lds32(pm), lds32(pm + 8));
+        mma16816(R, Thi[ks], h0, h1);
       }
 #pragma unroll
       for (int rr = 0; rr < 2; ++rr)
@@ -1280,11 +1327,18 @@ int ssb_fused_phi(const ssb_config* c, const float* T, const float* V, float* ph
   const int BN = c->n_batch * c->n_sources, I = c->n_bins, J = c->n_frames, K = c->n_basis;
   dim3 grid((I + FW * 16 - 1) / (FW * 16), BN);
   if (K <= 16) {
-    const size_t sm = (size_t)(2 * JC * (16 + PADH)) * sizeof(__nv_bfloat16);
+    const size_t sm = (size_t)(3 * JC * (16 + PADH)) * sizeof(__nv_bfloat16);
     if (inverse) kf_phi<1, true><<<grid, FW * 32, sm, st>>>(T, V, phi, I, J, K);
     else kf_phi<1, false><<<grid, FW * 32, sm, st>>>(T, V, phi, I, J, K);
   } else {
-    const size_t sm = (size_t)(2 * JC * (32 + PADH)) * sizeof(__nv_bfloat16);
+    const size_t sm = (size_t)(3 * JC * (32 + PADH)) * sizeof(__nv_bfloat16);  // 60 KB: above the 48 KB default
+    static bool attr_dev[SSB_MAX_DEVICES] = {};  // function attributes are per device
+    bool& attr_set = attr_dev[ssb_current_device()];
+    if (!attr_set) {
+      SSB_CUDA(cudaFuncSetAttribute(kf_phi<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      SSB_CUDA(cudaFuncSetAttribute(kf_phi<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      attr_set = true;
+    }
     if (inverse) kf_phi<2, true><<<grid, FW * 32, sm, st>>>(T, V, phi, I, J, K);
     else kf_phi<2, false><<<grid, FW * 32, sm, st>>>(T, V, phi, I, J, K);
   }

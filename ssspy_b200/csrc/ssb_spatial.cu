@@ -423,8 +423,8 @@ __device__ __forceinline__ void group_quad2(const cd (&P)[2], const cf* su, int 
     }
 }
 
-template <int N>
-__global__ void __launch_bounds__(QW * 32) kq_ip2(cf* __restrict__ W, const cf* __restrict__ U, int n_mat,
+template <int N, int MINB = (N <= 4 ? 4 : 3)>
+__global__ void __launch_bounds__(QW * 32, MINB) kq_ip2(cf* __restrict__ W, const cf* __restrict__ U, int n_mat,
                                                   PairList pl, int flooring, double eps, const cf* __restrict__ Cn,
                                                   double* __restrict__ qn, int* __restrict__ status) {
   constexpr int GS = GroupShape<N>::GS, GW = GroupShape<N>::GW;
@@ -1323,6 +1323,13 @@ int ssbk_ip2(cf* W, const cf* U, int n_mat, int N, const int* pairs, int n_pairs
     pl.un[q] = (short)(uidx ? uidx[2 * q + 1] : n);
   }
   if (n_pairs == 0) return 0;
+  // SSB_IP2_OCC=1 (experiment): the N = 8 kernel capped at 128 registers (4 blocks per SM instead of 3)
+  static const int occ = getenv("SSB_IP2_OCC") != nullptr ? atoi(getenv("SSB_IP2_OCC")) : 0;
+  if (N == 8 && occ == 1) {
+    kq_ip2<8, 4><<<blocks_for(n_mat, QW * GroupShape<8>::GW), QW * 32, 0, st>>>(W, U, n_mat, pl, flooring, (double)eps, C,
+                                                                              q, ssb_status_word());
+    return ssb_check_launch("update_by_ip2", st);
+  }
   SSB_DISPATCH_N(N, kq_ip2<NN><<<blocks_for(n_mat, QW * GroupShape<NN>::GW), QW * 32, 0, st>>>(W, U, n_mat, pl, flooring,
                                                                                                  (double)eps, C, q,
                                                                                                  ssb_status_word()));

@@ -42,11 +42,11 @@ struct Split {
   uint32_t hi, lo;
 };
 __device__ __forceinline__ Split split2(float a, float b) {
-  const uint32_t ua = __float_as_uint(a), ub = __float_as_uint(b);
   Split s;
-  s.hi = __byte_perm(ua, ub, 0x7632);
-  const float ra = a - __uint_as_float(ua & 0xffff0000u);
-  const float rb = b - __uint_as_float(ub & 0xffff0000u);
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  s.hi = *reinterpret_cast<uint32_t*>(&h);
+  const float ra = a - __uint_as_float(s.hi << 16);
+  const float rb = b - __uint_as_float(s.hi & 0xffff0000u);
   __nv_bfloat162 l = __floats2bfloat162_rn(ra, rb);
   s.lo = *reinterpret_cast<uint32_t*>(&l);
   return s;
