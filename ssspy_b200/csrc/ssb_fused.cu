@@ -1214,8 +1214,8 @@ int launch_all(const ssb_config* c, const cf* X, cf* W, float* T, float* V, floa
   // N = 2: TMA-fed covariance from the pre-split V left by the activation kernel (ssb_tma.cu)
   if (N == 2 && coop && vs != nullptr && vs->vs_valid && ssb_tma_supported(c) && (ssb_tma_mask(c) & 2))
     return ssb_tma_cov_n2(c, X, T, ssb_coop_vs(c, vs->base), U, st);
-  // N = 8: the frame reduction as a GEMM on the tensor pipe (ssb_covmma.cu), from the same pre-split V
-  if (N == 8 && coop && vs != nullptr && vs->vs_valid && ssb_cov_mma_supported(c, X))
+  // N = 4, 8: the frame reduction as a GEMM on the tensor pipe (ssb_covmma.cu), from the same pre-split V
+  if ((N == 8 || N == 4) && coop && vs != nullptr && vs->vs_valid && ssb_cov_mma_supported(c, X))
     return ssb_cov_mma(c, X, T, ssb_coop_vs(c, vs->base), U, st);
   if (coop && coop_cov && vs != nullptr && W != nullptr && ssb_coop_cov_supported(c))
     return ssb_coop_cov(c, X, T, vs->base, U, st);

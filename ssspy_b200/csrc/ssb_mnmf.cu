@@ -39,9 +39,34 @@ __device__ __forceinline__ void load_ctx(BinCtx<N>& c, const float* __restrict__
   __syncwarp();
 }
 
+// Q and D of the bin in registers: they are loop invariants of the frame sweeps (48 registers at N = 4); reading them
+// from shared memory in every frame cost one LDS per FMA operand (km_spatial ran at 20 % issue utilisation)
+template <int N>
+struct RegCtx {
+  static constexpr bool REG = N <= 4;  // larger N: the copy would spill, keep reading shared memory
+  static constexpr int NR = REG ? N : 1;
+  cf Qr[NR][NR];
+  float Dr[NR][NR];
+  const BinCtx<N>& s;
+  const float (*T)[SSB_MAX_BASIS];
+  __device__ __forceinline__ explicit RegCtx(const BinCtx<N>& c) : s(c), T(c.T) {
+    if (REG) {
+#pragma unroll
+      for (int a = 0; a < NR; ++a)
+#pragma unroll
+        for (int b = 0; b < NR; ++b) {
+          Qr[a][b] = c.Q[a][b];
+          Dr[a][b] = c.D[a][b];
+        }
+    }
+  }
+  __device__ __forceinline__ cf q(int a, int b) const { return REG ? Qr[REG ? a : 0][REG ? b : 0] : s.Q[a][b]; }
+  __device__ __forceinline__ float d(int a, int b) const { return REG ? Dr[REG ? a : 0][REG ? b : 0] : s.D[a][b]; }
+};
+
 // Lambda_n, L_m and Z2_m of one (bin, frame)
 template <int N>
-__device__ __forceinline__ void frame_stats(const BinCtx<N>& c, const cf* __restrict__ X, const float* __restrict__ V,
+__device__ __forceinline__ void frame_stats(const RegCtx<N>& c, const cf* __restrict__ X, const float* __restrict__ V,
                                             const float* __restrict__ Lam, int b, int i, int j, int I, int J, int K,
                                             float (&lam)[N], float (&L)[N], float (&Z2)[N]) {
   cf x[N];
@@ -62,10 +87,10 @@ __device__ __forceinline__ void frame_stats(const BinCtx<N>& c, const cf* __rest
   for (int m = 0; m < N; ++m) {
     float l = 0.f, zr = 0.f, zi = 0.f;
 #pragma unroll
-    for (int n = 0; n < N; ++n) l = fmaf(lam[n], c.D[n][m], l);
+    for (int n = 0; n < N; ++n) l = fmaf(lam[n], c.d(n, m), l);
 #pragma unroll
     for (int cc = 0; cc < N; ++cc) {
-      const cf q = c.Q[m][cc];
+      const cf q = c.q(m, cc);
       zr = fmaf(q.x, x[cc].x, fmaf(-q.y, x[cc].y, zr));
       zi = fmaf(q.x, x[cc].y, fmaf(q.y, x[cc].x, zi));
     }
@@ -86,8 +111,10 @@ __global__ void __launch_bounds__(MW * 32) km_gh(const cf* __restrict__ X, const
   const int bin = blockIdx.x * MW + wib;
   if (bin >= B * I) return;
   const int b = bin / I, i = bin - b * I;
-  BinCtx<N>& c = ctx[wib];
-  load_ctx<N>(c, T, Q, D, b, i, I, K, lane);
+  BinCtx<N>& cs = ctx[wib];
+  load_ctx<N>(cs, T, Q, D, b, i, I, K, lane);
+  const RegCtx<N> c(cs);
+#pragma unroll 2
   for (int j = lane; j < J; j += 32) {
     float lam[N], L[N], Z2[N];
     frame_stats<N>(c, X, V, Lam, b, i, j, I, J, K, lam, L, Z2);
@@ -102,8 +129,8 @@ __global__ void __launch_bounds__(MW * 32) km_gh(const cf* __restrict__ X, const
       float g = 0.f, h = 0.f;
 #pragma unroll
       for (int m = 0; m < N; ++m) {
-        g = fmaf(c.D[n][m], r2[m], g);
-        h = fmaf(c.D[n][m], r[m], h);
+        g = fmaf(c.d(n, m), r2[m], g);
+        h = fmaf(c.d(n, m), r[m], h);
       }
       const size_t o = (((size_t)b * N + n) * I + i) * J + j;
       G[o] = g;
@@ -124,8 +151,10 @@ __global__ void __launch_bounds__(MW * 32) km_phi(const cf* __restrict__ X, cons
   const int bin = blockIdx.x * MW + wib;
   if (bin >= B * I) return;
   const int b = bin / I, i = bin - b * I;
-  BinCtx<N>& c = ctx[wib];
-  load_ctx<N>(c, T, Q, D, b, i, I, K, lane);
+  BinCtx<N>& cs = ctx[wib];
+  load_ctx<N>(cs, T, Q, D, b, i, I, K, lane);
+  const RegCtx<N> c(cs);
+#pragma unroll 2
   for (int j = lane; j < J; j += 32) {
     float lam[N], L[N], Z2[N];
     frame_stats<N>(c, X, V, Lam, b, i, j, I, J, K, lam, L, Z2);
@@ -149,8 +178,9 @@ __global__ void __launch_bounds__(MW * 32) km_spatial(const cf* __restrict__ X, 
   const int bin = blockIdx.x * MW + wib;
   if (bin >= B * I) return;
   const int b = bin / I, i = bin - b * I;
-  BinCtx<N>& c = ctx[wib];
-  load_ctx<N>(c, T, Q, D, b, i, I, K, lane);
+  BinCtx<N>& cs = ctx[wib];
+  load_ctx<N>(cs, T, Q, D, b, i, I, K, lane);
+  const RegCtx<N> c(cs);
   for (int n0 = 0; n0 < (update_d ? N : 1); n0 += GS) {
     float num[GS][N], den[GS][N], zs[N];
 #pragma unroll
@@ -159,6 +189,7 @@ __global__ void __launch_bounds__(MW * 32) km_spatial(const cf* __restrict__ X, 
 #pragma unroll
       for (int gs = 0; gs < GS; ++gs) num[gs][m] = den[gs][m] = 0.f;
     }
+#pragma unroll 2
     for (int j = lane; j < J; j += 32) {
       float lam[N], L[N], Z2[N];
       frame_stats<N>(c, X, V, Lam, b, i, j, I, J, K, lam, L, Z2);
@@ -189,7 +220,7 @@ __global__ void __launch_bounds__(MW * 32) km_spatial(const cf* __restrict__ X, 
       for (int gs = 0; gs < GS; ++gs) {
         const float nu = warp_sum(num[gs][m]), de = warp_sum(den[gs][m]);
         if (update_d && lane == 0 && n0 + gs < N)
-          D[(((size_t)b * I + i) * N + n0 + gs) * N + m] = sqrtf(nu / de) * c.D[n0 + gs][m];
+          D[(((size_t)b * I + i) * N + n0 + gs) * N + m] = sqrtf(nu / de) * c.d(n0 + gs, m);
       }
     }
   }
@@ -236,9 +267,11 @@ __global__ void __launch_bounds__(MW * 32) km_rowloss(const cf* __restrict__ X, 
   const int bin = blockIdx.x * MW + wib;
   if (bin >= B * I) return;
   const int b = bin / I, i = bin - b * I;
-  BinCtx<N>& c = ctx[wib];
-  load_ctx<N>(c, T, Q, D, b, i, I, K, lane);
+  BinCtx<N>& cs = ctx[wib];
+  load_ctx<N>(cs, T, Q, D, b, i, I, K, lane);
+  const RegCtx<N> c(cs);
   double acc = 0.0;
+#pragma unroll 2
   for (int j = lane; j < J; j += 32) {
     float lam[N], L[N], Z2[N];
     frame_stats<N>(c, X, V, Lam, b, i, j, I, J, K, lam, L, Z2);

@@ -1323,8 +1323,9 @@ int ssbk_ip2(cf* W, const cf* U, int n_mat, int N, const int* pairs, int n_pairs
     pl.un[q] = (short)(uidx ? uidx[2 * q + 1] : n);
   }
   if (n_pairs == 0) return 0;
-  // SSB_IP2_OCC=1 (experiment): the N = 8 kernel capped at 128 registers (4 blocks per SM instead of 3)
-  static const int occ = getenv("SSB_IP2_OCC") != nullptr ? atoi(getenv("SSB_IP2_OCC")) : 0;
+  // N = 8: the kernel capped at 128 registers (4 blocks per SM instead of 3; 28 bytes of spills): 2.62 -> 2.45 ms at
+  // BASELINE config 4 (gpurun_out/r2p_c4_occ.json); SSB_IP2_OCC=0 restores the 168-register build
+  static const int occ = getenv("SSB_IP2_OCC") != nullptr ? atoi(getenv("SSB_IP2_OCC")) : 1;
   if (N == 8 && occ == 1) {
     kq_ip2<8, 4><<<blocks_for(n_mat, QW * GroupShape<8>::GW), QW * 32, 0, st>>>(W, U, n_mat, pl, flooring, (double)eps, C,
                                                                               q, ssb_status_word());
@@ -1369,7 +1370,8 @@ int ssbk_iss1(cf* Y, const float* phi, long long sb, long long sn, long long si,
     }
     if (N == 2) k_iss1_cov<2><<<grid, ISSC_W * 32, sm, st>>>(Y, phi, sb, sn, si, I, J, flooring, eps, part);
     else if (N == 3) k_iss1_cov<3><<<grid, ISSC_W * 32, sm, st>>>(Y, phi, sb, sn, si, I, J, flooring, eps, part);
-    else k_iss1_cov<4><<<grid, ISSC_W * 32, sm, st>>>(Y, phi, sb, sn, si, I, J, flooring, eps, part);
+    else k_iss1_cov<4><<<grid, ISSC_W * 32, sm, st>>>(Y, phi, sb, sn, si, I, J, flooring, eps, part);  // (capping it at 128
+    // registers for four blocks per SM changes nothing: 2.83 vs 2.72 ms at config 3, gpurun_out/r2q_c3_*.json)
     if (ssb_check_launch("update_by_iss1", st)) return 1;
     if (emit) {
       dim3 g2(blocks_for((long long)N * J, 256), B);
