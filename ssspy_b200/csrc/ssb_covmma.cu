@@ -651,7 +651,8 @@ int launch_cov_mma4(const ssb_config* c, const cf* X, const float* T, const __nv
 
 }  // namespace
 
-// SSB_COV_MMA (read at every call): unset / 2 = tensor-core covariance at N = 8 for IP1 and IP2, 1 = IP1 only,
+// SSB_COV_MMA (read at every call): unset / 2 = tensor-core covariance at N = 8 (and N = 4 with SSB_COV_MMA4=1) for IP1 and
+// IP2, 1 = IP1 only,
 // 0 = never (kf_cov_coop on the FP32 pipe).  IP2's pairwise generalised eigenproblems amplify the rounding of the
 // weights: with two-way operands BASELINE config 4 ended 1.1e-4 from the fp64 oracle (bound 1e-4; 7.3e-5 with
 // kf_cov_coop); with the three-way weights, flushed accumulators and round-to-nearest splits everywhere it is 3.9e-5
@@ -662,7 +663,11 @@ int ssb_cov_mma_supported(const ssb_config* c, const cf* X) {
   if (mode == 0) return 0;
   if (c->spatial != SSB_SPATIAL_IP1 && mode < 2) return 0;
   if ((c->n_sources != 8 && c->n_sources != 4) || (c->n_frames % 16) != 0 || c->n_basis > 32) return 0;
-  if (c->n_sources == 4 && mode >= 0 && getenv("SSB_COV_MMA4") != nullptr && atoi(getenv("SSB_COV_MMA4")) == 0) return 0;
+  // N = 4 is opt-in (SSB_COV_MMA4=1): parity-green, but 0.45 ms against 0.35 ms for kf_cov_coop at I = 1025, J = 512,
+  // B = 64 (gpurun_out/r2r_n4_*.json).  With 16 columns per frame the products, their bf16 splits and the diagonal-lane
+  // selects cost as many issue slots (~210 per warp and 16-frame step) as the 64 FFMA per frame they replace; deeper
+  // rings (5 X stages, 3 V slots) changed nothing, i.e. the kernel is issue-bound, not latency-bound.
+  if (c->n_sources == 4 && !(getenv("SSB_COV_MMA4") != nullptr && atoi(getenv("SSB_COV_MMA4")) == 1)) return 0;
   static int map_ok = -1;  // whether the driver accepts a tensor map whose strides are not increasing
   if (map_ok < 0) {
     CUtensorMap tm;

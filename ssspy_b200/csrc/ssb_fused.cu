@@ -939,10 +939,10 @@ struct CovSrc {
   int n;
 };
 
-template <int N>
+template <int N, bool MN>
 __global__ void __launch_bounds__(FW * 32) kf_cov_w(const cf* __restrict__ X, const float* __restrict__ phi,
                                                     long long sb, long long sn, long long si, int n_src,
-                                                    cf* __restrict__ U, int I, int J) {
+                                                    cf* __restrict__ U, int I, int J, const float* __restrict__ Dm) {
   constexpr int G = CovShape<N>::G;
   constexpr bool RS = CovShape<N>::RS;
   constexpr bool STG = CovShape<N>::STG_W;
@@ -982,6 +982,19 @@ __global__ void __launch_bounds__(FW * 32) kf_cov_w(const cf* __restrict__ X, co
       HermAcc<N, G> acc[NR];
 #pragma unroll
       for (int r = 0; r < NR; ++r) acc[r].zero();
+      // MN (FastGaussMNMF, ssspy/bss/mnmf.py:1504-1514): `phi` holds Lambda[b, n, i, j] = (T V) and the weight of
+      // "source" m is 1 / sum_n Lambda_n D[i, n, m], formed here instead of by a separate pass that wrote it out
+      float dreg[MN ? NR : 1][MN ? N : 1][MN ? G : 1];
+      if (MN) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r)
+#pragma unroll
+          for (int n = 0; n < N; ++n)
+#pragma unroll
+            for (int gs = 0; gs < G; ++gs)
+              dreg[MN ? r : 0][MN ? n : 0][MN ? gs : 0] =
+                  Dm[(((size_t)b * I + rowc[RS ? rs : r]) * N + n) * N + min(s0 + gs, n_src - 1)];
+      }
       int step = 0;
       if (STG) {
         issue(0, 0, rs);
@@ -1007,13 +1020,32 @@ __global__ void __launch_bounds__(FW * 32) kf_cov_w(const cf* __restrict__ X, co
 #pragma unroll
           for (int r = 0; r < NR; ++r) {
             float ph0[G], ph1[G];
+            if (MN) {
+              float2 lam[N];
 #pragma unroll
-            for (int gs = 0; gs < G; ++gs) {
-              const int s = min(s0 + gs, n_src - 1);
-              const float2 ph = *reinterpret_cast<const float2*>(phi + (size_t)b * sb + (size_t)s * sn +
-                                                                 (size_t)rowc[RS ? rs : r] * si + jj + 8 * h + 2 * t);
-              ph0[gs] = ph.x;
-              ph1[gs] = ph.y;
+              for (int n = 0; n < N; ++n)
+                lam[n] = *reinterpret_cast<const float2*>(phi + (size_t)b * sb + (size_t)n * sn +
+                                                          (size_t)rowc[RS ? rs : r] * si + jj + 8 * h + 2 * t);
+#pragma unroll
+              for (int gs = 0; gs < G; ++gs) {
+                float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+                for (int n = 0; n < N; ++n) {
+                  l0 = fmaf(lam[n].x, dreg[MN ? r : 0][MN ? n : 0][MN ? gs : 0], l0);
+                  l1 = fmaf(lam[n].y, dreg[MN ? r : 0][MN ? n : 0][MN ? gs : 0], l1);
+                }
+                ph0[gs] = fast_rcp(l0);
+                ph1[gs] = fast_rcp(l1);
+              }
+            } else {
+#pragma unroll
+              for (int gs = 0; gs < G; ++gs) {
+                const int s = min(s0 + gs, n_src - 1);
+                const float2 ph = *reinterpret_cast<const float2*>(phi + (size_t)b * sb + (size_t)s * sn +
+                                                                   (size_t)rowc[RS ? rs : r] * si + jj + 8 * h + 2 * t);
+                ph0[gs] = ph.x;
+                ph1[gs] = ph.y;
+              }
             }
             float xr[N], xi[N];
 #pragma unroll
@@ -1048,18 +1080,23 @@ __global__ void __launch_bounds__(FW * 32) kf_cov_w(const cf* __restrict__ X, co
 
 template <int N>
 int launch_cov_w(const cf* X, const float* phi, long long sb, long long sn, long long si, int n_src, cf* U, int B,
-                 int I, int J, cudaStream_t st) {
+                 int I, int J, cudaStream_t st, const float* Dm = nullptr) {
   constexpr int NRC = CovShape<N>::RS ? 1 : 2;
   constexpr int G = CovShape<N>::G;
   const size_t sm = CovShape<N>::STG_W ? (size_t)FW * XSTAGES * 2 * NRC * N * 32 * sizeof(float4) : 0;
   static bool attr_dev[SSB_MAX_DEVICES] = {};  // function attributes are per device
   bool& attr_set = attr_dev[ssb_current_device()];
   if (!attr_set) {
-    SSB_CUDA(cudaFuncSetAttribute(kf_cov_w<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    SSB_CUDA(cudaFuncSetAttribute(kf_cov_w<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    SSB_CUDA(cudaFuncSetAttribute(kf_cov_w<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     attr_set = true;
   }
   dim3 grid((n_src + G - 1) / G, (I + FW * 16 - 1) / (FW * 16), B);
-  kf_cov_w<N><<<grid, FW * 32, sm, st>>>(X, phi, sb, sn, si, n_src, U, I, J);
+  if (Dm != nullptr) {
+    kf_cov_w<N, true><<<grid, FW * 32, sm, st>>>(X, phi, sb, sn, si, n_src, U, I, J, Dm);
+    return ssb_check_launch("fused_cov_lambda", st);
+  }
+  kf_cov_w<N, false><<<grid, FW * 32, sm, st>>>(X, phi, sb, sn, si, n_src, U, I, J, nullptr);
   return ssb_check_launch("fused_cov_w", st);
 }
 
@@ -1350,6 +1387,14 @@ int ssb_fused_cov_w(const cf* X, const float* phi, long long sb, long long sn, l
                     int N, int I, int J, cudaStream_t st) {
   SSB_REQUIRE((J % 16) == 0, "fused_cov_w needs n_frames %% 16 == 0");
   SSB_DISPATCH_N(N, return (launch_cov_w<NN>(X, phi, sb, sn, si, n_src, U, B, I, J, st)));
+  return 0;
+}
+
+// FastGaussMNMF: U[b, i, m] = mean_j x x^H / (sum_n Lambda[b, n, i, j] D[b, i, n, m])   (mnmf.py:1504-1514)
+int ssb_fused_cov_lambda(const cf* X, const float* Lam, const float* Dm, cf* U, int B, int N, int I, int J,
+                         cudaStream_t st) {
+  SSB_REQUIRE((J % 16) == 0, "fused_cov_lambda needs n_frames %% 16 == 0");
+  SSB_DISPATCH_N(N, return (launch_cov_w<NN>(X, Lam, (long long)N * I * J, (long long)I * J, J, N, U, B, I, J, st, Dm)));
   return 0;
 }
 

@@ -70,6 +70,9 @@ int ssb_fused_normalize(const double* q, float* T, cf* W, int B, int N, int I, i
 // requires n_frames % 16 == 0
 int ssb_fused_cov_w(const cf* X, const float* phi, long long sb, long long sn, long long si, int n_src, cf* U, int B,
                     int N, int I, int J, cudaStream_t st);
+// FastGaussMNMF diagonaliser covariance with the weights 1 / (sum_n Lambda_n D[i, n, m]) formed in the kernel
+int ssb_fused_cov_lambda(const cf* X, const float* Lam, const float* Dm, cf* U, int B, int N, int I, int J,
+                         cudaStream_t st);
 // ISS modes: MM source model (T then V, p = 2) with P = |Y|^2, and phi = 1/(T V) as an array
 int ssb_fused_source_iss(const ssb_config* cfg, const cf* Y, float* T, float* V, float* P, cudaStream_t st);
 // inverse = 1: phi = 1/(T V); inverse = 0: Lambda = T V

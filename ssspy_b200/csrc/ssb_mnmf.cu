@@ -64,22 +64,51 @@ struct RegCtx {
   __device__ __forceinline__ float d(int a, int b) const { return REG ? Dr[REG ? a : 0][REG ? b : 0] : s.D[a][b]; }
 };
 
+// Row pointers of one (mixture, bin): computed once per warp, so that the frame loops index with `plane * cs + j` only
+// (the index arithmetic of the round-1 kernels, recomputed from (b, n, i, j) for every load, was most of their
+// instructions: 767 IMAD + 737 IADD3 + 455 LEA against 677 FFMA in km_spatial<4>)
+struct RowBase {
+  const cf* x;        // X[b, 0, i, 0]
+  const float* lam;   // Lam[b, 0, i, 0] or NULL
+  const float* v;     // V[b, 0, 0, 0]
+  size_t cs;          // I * J: stride between the channel / source planes of X and Lam
+  size_t vs;          // K * J: stride between the sources of V
+  int J, K;
+};
+__device__ __forceinline__ RowBase row_base(const cf* X, const float* V, const float* Lam, int b, int i, int N, int I,
+                                            int J, int K) {
+  RowBase r;
+  const size_t o = ((size_t)b * N * I + i) * J;
+  r.x = X + o;
+  r.lam = Lam != nullptr ? Lam + o : nullptr;
+  r.v = V + (size_t)b * N * K * J;
+  r.cs = (size_t)I * J;
+  r.vs = (size_t)K * J;
+  r.J = J;
+  r.K = K;
+  return r;
+}
+__device__ __forceinline__ float mn_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 // Lambda_n, L_m and Z2_m of one (bin, frame)
-template <int N>
-__device__ __forceinline__ void frame_stats(const RegCtx<N>& c, const cf* __restrict__ X, const float* __restrict__ V,
-                                            const float* __restrict__ Lam, int b, int i, int j, int I, int J, int K,
-                                            float (&lam)[N], float (&L)[N], float (&Z2)[N]) {
+template <int N, bool LAM>
+__device__ __forceinline__ void frame_stats(const RegCtx<N>& c, const RowBase& rb, int j, float (&lam)[N],
+                                            float (&L)[N], float (&Z2)[N]) {
   cf x[N];
 #pragma unroll
-  for (int m = 0; m < N; ++m) x[m] = X[(((size_t)b * N + m) * I + i) * J + j];
+  for (int m = 0; m < N; ++m) x[m] = rb.x[m * rb.cs + j];
 #pragma unroll
   for (int n = 0; n < N; ++n) {
-    if (Lam != nullptr) {  // Lambda = T V precomputed on the tensor pipe
-      lam[n] = Lam[(((size_t)b * N + n) * I + i) * J + j];
+    if (LAM) {  // Lambda = T V precomputed on the tensor pipe (compile-time: keeps the K loop out of the hot version)
+      lam[n] = rb.lam[n * rb.cs + j];
     } else {
-      const float* v = V + ((size_t)b * N + n) * K * J + j;
+      const float* v = rb.v + n * rb.vs + j;
       float s = 0.f;
-      for (int k = 0; k < K; ++k) s = fmaf(c.T[n][k], v[(size_t)k * J], s);
+      for (int k = 0; k < rb.K; ++k) s = fmaf(c.T[n][k], v[(size_t)k * rb.J], s);
       lam[n] = s;
     }
   }
@@ -100,7 +129,7 @@ __device__ __forceinline__ void frame_stats(const RegCtx<N>& c, const cf* __rest
 }
 
 // G[b,n,i,j] = sum_m D[n,m] Z2_m / L_m^2,  H[b,n,i,j] = sum_m D[n,m] / L_m     (mnmf.py:1348-1350)
-template <int N>
+template <int N, bool LAM>
 __global__ void __launch_bounds__(MW * 32) km_gh(const cf* __restrict__ X, const float* __restrict__ T,
                                                  const float* __restrict__ V, const float* __restrict__ Lam,
                                                  const cf* __restrict__ Q,
@@ -114,14 +143,16 @@ __global__ void __launch_bounds__(MW * 32) km_gh(const cf* __restrict__ X, const
   BinCtx<N>& cs = ctx[wib];
   load_ctx<N>(cs, T, Q, D, b, i, I, K, lane);
   const RegCtx<N> c(cs);
+  const RowBase rb = row_base(X, V, Lam, b, i, N, I, J, K);
+  const size_t gh0 = ((size_t)b * N * I + i) * J;
 #pragma unroll 2
   for (int j = lane; j < J; j += 32) {
     float lam[N], L[N], Z2[N];
-    frame_stats<N>(c, X, V, Lam, b, i, j, I, J, K, lam, L, Z2);
+    frame_stats<N, LAM>(c, rb, j, lam, L, Z2);
     float r[N], r2[N];
 #pragma unroll
     for (int m = 0; m < N; ++m) {
-      r[m] = 1.0f / L[m];
+      r[m] = mn_rcp(L[m]);
       r2[m] = Z2[m] * r[m] * r[m];
     }
 #pragma unroll
@@ -132,7 +163,7 @@ __global__ void __launch_bounds__(MW * 32) km_gh(const cf* __restrict__ X, const
         g = fmaf(c.d(n, m), r2[m], g);
         h = fmaf(c.d(n, m), r[m], h);
       }
-      const size_t o = (((size_t)b * N + n) * I + i) * J + j;
+      const size_t o = gh0 + n * rb.cs + j;
       G[o] = g;
       H[o] = h;
     }
@@ -140,7 +171,7 @@ __global__ void __launch_bounds__(MW * 32) km_gh(const cf* __restrict__ X, const
 }
 
 // phi[b,m,i,j] = 1 / L[i,j,m]      (mnmf.py:1504-1510)
-template <int N>
+template <int N, bool LAM>
 __global__ void __launch_bounds__(MW * 32) km_phi(const cf* __restrict__ X, const float* __restrict__ T,
                                                   const float* __restrict__ V, const float* __restrict__ Lam,
                                                  const cf* __restrict__ Q,
@@ -154,20 +185,21 @@ __global__ void __launch_bounds__(MW * 32) km_phi(const cf* __restrict__ X, cons
   BinCtx<N>& cs = ctx[wib];
   load_ctx<N>(cs, T, Q, D, b, i, I, K, lane);
   const RegCtx<N> c(cs);
+  const RowBase rb = row_base(X, V, Lam, b, i, N, I, J, K);
 #pragma unroll 2
   for (int j = lane; j < J; j += 32) {
     float lam[N], L[N], Z2[N];
-    frame_stats<N>(c, X, V, Lam, b, i, j, I, J, K, lam, L, Z2);
+    frame_stats<N, LAM>(c, rb, j, lam, L, Z2);
 #pragma unroll
-    for (int m = 0; m < N; ++m) phi[(((size_t)b * N + m) * I + i) * J + j] = 1.0f / L[m];
+    for (int m = 0; m < N; ++m) phi[((size_t)b * N * I + i) * J + m * rb.cs + j] = mn_rcp(L[m]);
   }
 }
 
 // spatial update (mnmf.py:1660-1675) and the per-bin sums zsum[b,i,m] = sum_j Z2_m for the normalisation.
 // Every source uses the D of the previous iteration (L is formed from the context loaded up front), so GS sources
 // share one pass over the frames: GS = N for N <= 4 (one pass), 1 otherwise (registers).  update_d = 0: zsum only.
-template <int N>
-__global__ void __launch_bounds__(MW * 32) km_spatial(const cf* __restrict__ X, const float* __restrict__ T,
+template <int N, bool LAM>
+__global__ void __launch_bounds__(MW * 32, (N <= 4 ? 4 : 1)) km_spatial(const cf* __restrict__ X, const float* __restrict__ T,
                                                       const float* __restrict__ V, const float* __restrict__ Lam,
                                                  const cf* __restrict__ Q,
                                                       float* __restrict__ D, double* __restrict__ zsum, int B, int I,
@@ -181,6 +213,7 @@ __global__ void __launch_bounds__(MW * 32) km_spatial(const cf* __restrict__ X, 
   BinCtx<N>& cs = ctx[wib];
   load_ctx<N>(cs, T, Q, D, b, i, I, K, lane);
   const RegCtx<N> c(cs);
+  const RowBase rb = row_base(X, V, Lam, b, i, N, I, J, K);
   for (int n0 = 0; n0 < (update_d ? N : 1); n0 += GS) {
     float num[GS][N], den[GS][N], zs[N];
 #pragma unroll
@@ -192,7 +225,7 @@ __global__ void __launch_bounds__(MW * 32) km_spatial(const cf* __restrict__ X, 
 #pragma unroll 2
     for (int j = lane; j < J; j += 32) {
       float lam[N], L[N], Z2[N];
-      frame_stats<N>(c, X, V, Lam, b, i, j, I, J, K, lam, L, Z2);
+      frame_stats<N, LAM>(c, rb, j, lam, L, Z2);
       float ln[GS];
 #pragma unroll
       for (int gs = 0; gs < GS; ++gs) {
@@ -202,7 +235,7 @@ __global__ void __launch_bounds__(MW * 32) km_spatial(const cf* __restrict__ X, 
       }
 #pragma unroll
       for (int m = 0; m < N; ++m) {
-        const float r = 1.0f / L[m];
+        const float r = mn_rcp(L[m]);
         const float a = r * r * Z2[m];
         zs[m] += Z2[m];
 #pragma unroll
@@ -256,7 +289,7 @@ __global__ void km_normalize(const double* __restrict__ zsum, cf* __restrict__ Q
 }
 
 // rowloss[b,i] = mean_j sum_m (Z2/L + log L)     (mnmf.py:1255-1258)
-template <int N>
+template <int N, bool LAM>
 __global__ void __launch_bounds__(MW * 32) km_rowloss(const cf* __restrict__ X, const float* __restrict__ T,
                                                       const float* __restrict__ V, const float* __restrict__ Lam,
                                                  const cf* __restrict__ Q,
@@ -270,11 +303,12 @@ __global__ void __launch_bounds__(MW * 32) km_rowloss(const cf* __restrict__ X, 
   BinCtx<N>& cs = ctx[wib];
   load_ctx<N>(cs, T, Q, D, b, i, I, K, lane);
   const RegCtx<N> c(cs);
+  const RowBase rb = row_base(X, V, Lam, b, i, N, I, J, K);
   double acc = 0.0;
 #pragma unroll 2
   for (int j = lane; j < J; j += 32) {
     float lam[N], L[N], Z2[N];
-    frame_stats<N>(c, X, V, Lam, b, i, j, I, J, K, lam, L, Z2);
+    frame_stats<N, LAM>(c, rb, j, lam, L, Z2);
     float s = 0.f;
 #pragma unroll
     for (int m = 0; m < N; ++m) s += Z2[m] / L[m] + logf(L[m]);
@@ -415,18 +449,25 @@ __global__ void __launch_bounds__(128) km_separate(const cf* __restrict__ X, con
 
 int ssbk_mnmf_gh(const cf* X, const float* T, const float* V, const float* Lam, const cf* Q, const float* D, float* G, float* H, int B,
                  int N, int I, int J, int K, cudaStream_t st) {
-  SSB_DISPATCH_N(N, km_gh<NN><<<blocks_for((long long)B * I, MW), MW * 32, 0, st>>>(X, T, V, Lam, Q, D, G, H, B, I, J, K));
+  if (Lam != nullptr) { SSB_DISPATCH_N(N, (km_gh<NN, true><<<blocks_for((long long)B * I, MW), MW * 32, 0, st>>>(X, T, V, Lam, Q, D, G, H, B, I, J, K))); }
+  else { SSB_DISPATCH_N(N, (km_gh<NN, false><<<blocks_for((long long)B * I, MW), MW * 32, 0, st>>>(X, T, V, Lam, Q, D, G, H, B, I, J, K))); }
   return ssb_check_launch("mnmf_gh", st);
 }
 int ssbk_mnmf_phi(const cf* X, const float* T, const float* V, const float* Lam, const cf* Q, const float* D, float* phi, int B, int N,
                   int I, int J, int K, cudaStream_t st) {
-  SSB_DISPATCH_N(N, km_phi<NN><<<blocks_for((long long)B * I, MW), MW * 32, 0, st>>>(X, T, V, Lam, Q, D, phi, B, I, J, K));
+  if (Lam != nullptr) { SSB_DISPATCH_N(N, (km_phi<NN, true><<<blocks_for((long long)B * I, MW), MW * 32, 0, st>>>(X, T, V, Lam, Q, D, phi, B, I, J, K))); }
+  else { SSB_DISPATCH_N(N, (km_phi<NN, false><<<blocks_for((long long)B * I, MW), MW * 32, 0, st>>>(X, T, V, Lam, Q, D, phi, B, I, J, K))); }
   return ssb_check_launch("mnmf_phi", st);
 }
 int ssbk_mnmf_spatial(const cf* X, const float* T, const float* V, const float* Lam, const cf* Q, float* D, double* zsum, int B, int N,
                       int I, int J, int K, int update_d, cudaStream_t st) {
-  SSB_DISPATCH_N(N, km_spatial<NN><<<blocks_for((long long)B * I, MW), MW * 32, 0, st>>>(X, T, V, Lam, Q, D, zsum, B, I,
-                                                                                          J, K, update_d));
+  if (Lam != nullptr) {
+    SSB_DISPATCH_N(N, (km_spatial<NN, true><<<blocks_for((long long)B * I, MW), MW * 32, 0, st>>>(X, T, V, Lam, Q, D, zsum,
+                                                                                                   B, I, J, K, update_d)));
+  } else {
+    SSB_DISPATCH_N(N, (km_spatial<NN, false><<<blocks_for((long long)B * I, MW), MW * 32, 0, st>>>(X, T, V, Lam, Q, D, zsum,
+                                                                                                    B, I, J, K, update_d)));
+  }
   return ssb_check_launch("mnmf_spatial", st);
 }
 int ssbk_mnmf_normalize(const double* zsum, cf* Q, float* D, int B, int N, int I, int J, int flooring, float eps,
@@ -436,8 +477,13 @@ int ssbk_mnmf_normalize(const double* zsum, cf* Q, float* D, int B, int N, int I
 }
 int ssbk_mnmf_rowloss(const cf* X, const float* T, const float* V, const float* Lam, const cf* Q, const float* D, double* rowloss, int B,
                       int N, int I, int J, int K, cudaStream_t st) {
-  SSB_DISPATCH_N(N, km_rowloss<NN><<<blocks_for((long long)B * I, MW), MW * 32, 0, st>>>(X, T, V, Lam, Q, D, rowloss, B,
-                                                                                          I, J, K));
+  if (Lam != nullptr) {
+    SSB_DISPATCH_N(N, (km_rowloss<NN, true><<<blocks_for((long long)B * I, MW), MW * 32, 0, st>>>(X, T, V, Lam, Q, D, rowloss,
+                                                                                                   B, I, J, K)));
+  } else {
+    SSB_DISPATCH_N(N, (km_rowloss<NN, false><<<blocks_for((long long)B * I, MW), MW * 32, 0, st>>>(X, T, V, Lam, Q, D, rowloss,
+                                                                                                    B, I, J, K)));
+  }
   return ssb_check_launch("mnmf_rowloss", st);
 }
 int ssbk_mnmf_separate(const cf* X, const float* T, const float* V, const cf* Q, const float* D, cd* Qinv, cf* Y, int B,

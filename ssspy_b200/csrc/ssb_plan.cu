@@ -616,11 +616,16 @@ int mnmf_spatial(ssb_plan* p, cudaStream_t st) {
   const int B = c.n_batch, N = c.n_sources, I = c.n_bins, J = c.n_frames, K = c.n_basis;
   const float* lam;
   TRY(mnmf_lambda(p, &lam, st));
-  TRY(ssbk_mnmf_phi(p->Xk, p->T, p->V, lam, p->Wk, p->variance, p->big, B, N, I, J, K, st));
-  if (c.fast_path && (J % 16) == 0)
-    TRY(ssb_fused_cov_w(p->Xk, p->big, (long long)N * I * J, (long long)I * J, J, N, p->U, B, N, I, J, st));
-  else
-    TRY(ssbk_wcov(p->Xk, p->big, (long long)N * I * J, (long long)I * J, J, nullptr, N, p->U, B, N, I, J, st));
+  if (lam != nullptr && c.fast_path && (J % 16) == 0) {
+    // the weights 1 / L_m are formed inside the covariance kernel from Lambda and D (no phi array, no km_phi pass)
+    TRY(ssb_fused_cov_lambda(p->Xk, lam, p->variance, p->U, B, N, I, J, st));
+  } else {
+    TRY(ssbk_mnmf_phi(p->Xk, p->T, p->V, lam, p->Wk, p->variance, p->big, B, N, I, J, K, st));
+    if (c.fast_path && (J % 16) == 0)
+      TRY(ssb_fused_cov_w(p->Xk, p->big, (long long)N * I * J, (long long)I * J, J, N, p->U, B, N, I, J, st));
+    else
+      TRY(ssbk_wcov(p->Xk, p->big, (long long)N * I * J, (long long)I * J, J, nullptr, N, p->U, B, N, I, J, st));
+  }
   if (c.spatial == SSB_SPATIAL_IP1) TRY(ssbk_ip1(p->Wk, p->U, B * I, N, c.flooring, c.eps, st));
   else TRY(ssbk_ip2(p->Wk, p->U, B * I, N, c.pairs, c.n_pairs, N, nullptr, c.flooring, c.eps, st));
   return ssbk_mnmf_spatial(p->Xk, p->T, p->V, lam, p->Wk, p->variance, p->rowloss, B, N, I, J, K, 1, st);

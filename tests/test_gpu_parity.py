@@ -414,6 +414,33 @@ def test_fused_tensor_core_path_matches_oracle_and_modular(N, I, J, K, spatial):
         assert_loss_close(np.asarray(fused.loss)[:, b], st["loss"])
 
 
+@pytest.mark.parametrize("I,J,K,spatial", [(40, 96, 9, "IP"), (33, 48, 20, "IP2"), (130, 272, 16, "IP2"), (17, 16, 4, "IP")])
+def test_tensor_core_covariance_n4_opt_in(monkeypatch, I, J, K, spatial):
+    """kc_cov_mma4 (ssb_covmma.cu): the weighted covariance of four sources as a split-bf16 GEMM, TMA-fed.  It is
+    parity-green but slower than the FP32-pipe kernel at N = 4 and therefore opt-in (SSB_COV_MMA4=1, read at every call);
+    ragged bin tiles, K <= 16 and K > 16, an odd number of 32-frame chunks and a single 16-frame step."""
+    from oracle import ilrma as oilrma
+    from ssspy_b200 import _lib
+    from ssspy_b200.bss import GaussILRMA
+    from ssspy_b200.utils.synth import make_batch, make_nmf_init
+    monkeypatch.setenv("SSB_COV_MMA4", "1")
+    N, B, n_iter = 4, 2, 4
+    X = make_batch(B, N, I, J, config_id=14, mode="mix")
+    T, V = make_nmf_init(N, I, J, K, seed=11)
+    m = GaussILRMA(n_basis=K, spatial_algorithm=spatial)
+    import torch
+    m.chunk_size = B  # one plan on the current stream: the kernel-name profile below then sees every launch
+    _lib.call("ssb_profile_begin", torch.cuda.current_stream().cuda_stream)
+    Y = m(X, n_iter=n_iter, basis=T, activation=V)
+    names = {k[0] for k in _lib.profile_end()}
+    assert "mma_phi_cov" in names, names  # the opt-in kernel is the one that ran
+    for b in range(B):
+        st = oilrma.run(X[b], T, V, n_iter, spatial_algorithm=spatial)
+        assert relerr(Y[b], st["Y"]) < tol_seeded(spatial)
+        assert relerr(m.basis[b], st["T"]) < tol_seeded(spatial, TOL_TV)
+        assert_loss_close(np.asarray(m.loss)[:, b], st["loss"])
+
+
 @pytest.mark.parametrize("model", ["laplace", "gauss"])
 @pytest.mark.parametrize("N,I,J,spatial", [(2, 37, 64, "IP"), (3, 21, 48, "IP2"), (4, 33, 80, "IP"), (5, 9, 96, "IP"),
                                            (8, 12, 160, "IP2"), (4, 19, 64, "ISS")])
