@@ -246,6 +246,30 @@ int ssb_solve(const void* A, const void* B, void* X, int n_mat, int N, int R, vo
  * eigenvectors in the columns of Z[n_mat,N,N] c128 */
 int ssb_eigh(const void* A, const void* B, int type, double* lamb, void* Z, int n_mat, int N,
              void* stream);
+/* cbrt (ssspy/linalg/cubic.py:4-22) of n complex128 values: cbrt(|x|) exp(i arg(x) / 3) */
+int ssb_cbrt(const void* x, void* y, long long n, void* stream);
+/* solve_cubic (ssspy/linalg/polynomial.py:9-104): the three roots of x^3 + A x^2 + B x + C for n coefficient triples
+ * (complex128), roots[3][n] in the reference's order (Cardano; P == 0 handled as in :82-92) */
+int ssb_solve_cubic(const void* A, const void* B, const void* C, void* roots, long long n, void* stream);
+/* lqpqm2 (ssspy/linalg/lqpqm.py:13-119): H[n_bins,M,M] c128 (positive semidefinite), v[n_bins,M] c128, z[n_bins] f64
+ * -> y[n_bins,M] c128; flooring / eps as in ssb_config; singular_mode 0: ||v|| < flooring(0) (the reference's
+ * default "flooring"), 1: ||v|| == 0 (singular_fn=None); max_iter Newton-Raphson steps (:122-219) */
+int ssb_lqpqm2(const void* H, const void* v, const double* z, void* y, int n_bins, int M, int flooring, double eps,
+               int singular_mode, int max_iter, void* stream);
+
+/* ---- STFT front / back end (not part of ssspy: its notebooks call scipy.signal.stft / istft with window="hann",
+ * nperseg=n_fft, noverlap=n_fft-hop, e.g. notebooks/BSS/ILRMA/GaussILRMA-IP1-MM.ipynb; same conventions here:
+ * boundary="zeros", padded=True, one-sided, scaling="spectrum") ---- */
+/* number of frames scipy.signal.stft produces for n_samples samples */
+int ssb_stft_frames(long long n_samples, int nperseg, int hop, int* n_frames);
+/* x[n_rows, n_samples] f64, window[nperseg] f64 (device), window_sum = sum(window) -> Z[n_rows, nperseg/2+1, n_frames]
+ * c128; nperseg a power of two in [16, 8192] */
+int ssb_stft(const double* x, const double* window, double window_sum, void* Z, int n_rows, long long n_samples,
+             int nperseg, int hop, void* stream);
+/* Z[n_rows, nperseg/2+1, n_frames] c128 -> y[n_rows, nperseg + (n_frames-1) hop - 2 (nperseg/2)] f64 by weighted
+ * overlap-add; seg[n_rows, n_frames, nperseg] f64 is scratch */
+int ssb_istft(const void* Z, const double* window, double window_sum, double* y, double* seg, int n_rows, int n_frames,
+              int nperseg, int hop, void* stream);
 
 #ifdef __cplusplus
 }

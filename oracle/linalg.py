@@ -150,3 +150,34 @@ def lqpqm2(H, v, z, floor, max_iter=10):
         lam = solve_equation(pn, vt, zn, floor, max_iter)
         y[ns] = np.sum(sn * (pn * vt / (lam[:, None] - pn))[:, None, :], axis=-1)
     return y
+
+
+def cbrt(x):
+    """Cube root with complex support: cbrt(|x|) exp(i arg(x) / 3) (ssspy/linalg/cubic.py:4-22)."""
+    x = np.asarray(x)
+    if np.iscomplexobj(x):
+        return np.cbrt(np.abs(x)) * np.exp(1j * np.angle(x) / 3)
+    return np.cbrt(x)
+
+
+def solve_cubic(A, B, C, D=None, all=True):
+    """All three roots of A x^3 + B x^2 + C x + D (D given) or x^3 + A x^2 + B x + C, shape (3, *), Cardano in the
+    reference's branch choices (ssspy/linalg/polynomial.py:9-104): principal sqrt of the discriminant, the complex cube
+    root above, U := 1 and X1 := cbrt(-Q) where P == 0."""
+    A, B, C = (np.asarray(t) for t in (A, B, C))
+    if D is not None:
+        if np.any(A == 0):
+            raise np.linalg.LinAlgError("Coefficients include zero.")
+        return solve_cubic(B / A, C / A, np.asarray(D) / A, all=all)
+    P = (-(A ** 2) / 3 + B).astype(np.complex128)
+    Q = ((2 * A ** 3) / 27 - (A * B) / 3 + C).astype(np.complex128)
+    om, omc = (-1 + 1j * np.sqrt(3)) / 2, (-1 - 1j * np.sqrt(3)) / 2
+    U = cbrt(-Q / 2 + np.sqrt((Q / 2) ** 2 + (P / 3) ** 3))
+    sing = P == 0
+    U = np.where(sing, 1, U)
+    V = -P / (3 * U)
+    X1 = np.where(sing, cbrt(-Q), U + V)
+    X2 = np.where(sing, X1 * om, U * om + V * omc)
+    X3 = np.where(sing, X1 * omc, U * omc + V * om)
+    x = np.stack([X1, X2, X3], axis=0) - A / 3
+    return x if all else x[0]

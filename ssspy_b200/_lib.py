@@ -83,6 +83,12 @@ SIGNATURES = {
     "ssb_inv": [_vp, _vp, _i, _i, _vp],
     "ssb_solve": [_vp, _vp, _vp, _i, _i, _i, _vp],
     "ssb_eigh": [_vp, _vp, _i, _vp, _vp, _i, _i, _vp],
+    "ssb_stft_frames": [ctypes.c_longlong, _i, _i, _vp],
+    "ssb_stft": [_vp, _vp, ctypes.c_double, _vp, _i, ctypes.c_longlong, _i, _i, _vp],
+    "ssb_istft": [_vp, _vp, ctypes.c_double, _vp, _vp, _i, _i, _i, _i, _vp],
+    "ssb_cbrt": [_vp, _vp, ctypes.c_longlong, _vp],
+    "ssb_solve_cubic": [_vp, _vp, _vp, _vp, ctypes.c_longlong, _vp],
+    "ssb_lqpqm2": [_vp, _vp, _vp, _vp, _i, _i, _i, ctypes.c_double, _i, _i, _vp],
 }
 
 _lib = None

@@ -80,7 +80,8 @@ __device__ double largest_cubic_root(double A, double B, double C) {
 
 // lqpqm2 (lqpqm.py:13-119) with singular_fn = (x < floor(0)) as update_by_ipa calls it (:484-490)
 template <int M>
-__device__ void lqpqm2(const cd* H, const cd* v, double z, int flooring, double eps, int max_iter, cd* y) {
+__device__ void lqpqm2(const cd* H, const cd* v, double z, int flooring, double eps, int max_iter, cd* y,
+                       int sing_mode = 0) {
   cd A[M * M], S[M * M];
   for (int e = 0; e < M * M; ++e) A[e] = H[e];
   jacobi_herm(A, S, M);
@@ -90,7 +91,7 @@ __device__ void lqpqm2(const cd* H, const cd* v, double z, int flooring, double 
   double nv = 0.0;
   for (int r = 0; r < M; ++r) nv += cd_abs2(v[r]);
   nv = sqrt(nv);
-  if (nv < f0) {  // v = 0 (lqpqm.py:78-89)
+  if (sing_mode == 0 ? nv < f0 : nv == 0.0) {  // v = 0 (lqpqm.py:78-89)
     int kmax = 0;
     for (int k = 1; k < M; ++k)
       if (phi[k] > phi[kmax]) kmax = k;
@@ -339,6 +340,65 @@ __global__ void __launch_bounds__(IPA_NW * 32) k_ipa_cta(cf* __restrict__ Y, con
   }
 }
 
+
+// ---- standalone operators of ssspy.linalg used by the IPA path (complex128 / float64 on the wire) -------------
+// cbrt of a complex number as the reference defines it: cbrt(|x|) exp(i arg(x) / 3)   (ssspy/linalg/cubic.py:4-22)
+__device__ __forceinline__ cd cbrt_c(cd x) {
+  const double a = cbrt(sqrt(cd_abs2(x))), ph = atan2(x.y, x.x) / 3.0;
+  return cd_make(a * cos(ph), a * sin(ph));
+}
+// principal square root (numpy.sqrt on complex128)
+__device__ __forceinline__ cd sqrt_c(cd x) {
+  const double r = sqrt(cd_abs2(x));
+  if (r == 0.0) return cd_make(0.0, 0.0);
+  const double re = sqrt(0.5 * (r + fabs(x.x)));
+  const double im = 0.5 * fabs(x.y) / re;
+  if (x.x >= 0.0) return cd_make(re, x.y < 0.0 ? -im : im);
+  return cd_make(im, x.y < 0.0 ? -re : re);
+}
+
+__global__ void k_cbrt(const cd* __restrict__ x, cd* __restrict__ y, long long n) {
+  const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (e < n) y[e] = cbrt_c(x[e]);
+}
+
+// roots of x^3 + A x^2 + B x + C (ssspy/linalg/polynomial.py:43-104), out[3][n]
+__global__ void k_solve_cubic(const cd* __restrict__ A, const cd* __restrict__ B, const cd* __restrict__ C,
+                              cd* __restrict__ out, long long n) {
+  const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const cd a = A[e], b = B[e], c = C[e];
+  const cd a2 = cd_mul(a, a);
+  const cd P = cd_add(cd_scale(a2, -1.0 / 3.0), b);
+  const cd Q = cd_add(cd_sub(cd_scale(cd_mul(a2, a), 2.0 / 27.0), cd_scale(cd_mul(a, b), 1.0 / 3.0)), c);
+  const cd hq = cd_scale(Q, 0.5), tp = cd_scale(P, 1.0 / 3.0);
+  const cd disc = cd_add(cd_mul(hq, hq), cd_mul(cd_mul(tp, tp), tp));
+  const bool sing = P.x == 0.0 && P.y == 0.0;
+  const cd U = sing ? cd_make(1.0, 0.0) : cbrt_c(cd_add(cd_make(-hq.x, -hq.y), sqrt_c(disc)));
+  const cd V = cd_mul(cd_scale(P, -1.0 / 3.0), cd_inv(U));
+  const cd om = cd_make(-0.5, 0.8660254037844386), omc = cd_make(-0.5, -0.8660254037844386);
+  const cd X1 = sing ? cbrt_c(cd_make(-Q.x, -Q.y)) : cd_add(U, V);
+  const cd X2 = sing ? cd_mul(X1, om) : cd_add(cd_mul(U, om), cd_mul(V, omc));
+  const cd X3 = sing ? cd_mul(X1, omc) : cd_add(cd_mul(U, omc), cd_mul(V, om));
+  const cd sh = cd_scale(a, 1.0 / 3.0);
+  out[e] = cd_sub(X1, sh);
+  out[n + e] = cd_sub(X2, sh);
+  out[2 * n + e] = cd_sub(X3, sh);
+}
+
+// lqpqm2 per bin (ssspy/linalg/lqpqm.py:13-119); sing_mode 0: ||v|| < floor(0) ("flooring"), 1: ||v|| == 0 (None)
+template <int M>
+__global__ void k_lqpqm2(const cd* __restrict__ H, const cd* __restrict__ v, const double* __restrict__ z,
+                         cd* __restrict__ y, int n_bins, int flooring, double eps, int sing_mode, int max_iter) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_bins) return;
+  cd h[M * M], vv[M], yy[M];
+  for (int e = 0; e < M * M; ++e) h[e] = H[(size_t)i * M * M + e];
+  for (int r = 0; r < M; ++r) vv[r] = v[(size_t)i * M + r];
+  lqpqm2<M>(h, vv, z[i], flooring, eps, max_iter, yy, sing_mode);
+  for (int r = 0; r < M; ++r) y[(size_t)i * M + r] = yy[r];
+}
+
 }  // namespace
 
 int ssbk_ipa(cf* Y, const float* phi, long long sb, long long sn, long long si, int B, int N, int I, int J,
@@ -358,4 +418,38 @@ int ssbk_ipa(cf* Y, const float* phi, long long sb, long long sn, long long si, 
                                                                     normalization, max_iter, use_smem);
   });
   return ssb_check_launch("update_by_ipa", st);
+}
+
+// ---- C-ABI: standalone cbrt / solve_cubic / lqpqm2 (include/ssb.h) -------------------------------------------
+extern "C" int ssb_cbrt(const void* x, void* y, long long n, void* stream) {
+  if (n <= 0) return 0;
+  SSB_REQUIRE(x != nullptr && y != nullptr, "cbrt: NULL buffer");
+  k_cbrt<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const cd*)x, (cd*)y, n);
+  return ssb_check_launch("cbrt", (cudaStream_t)stream);
+}
+
+extern "C" int ssb_solve_cubic(const void* A, const void* B, const void* C, void* roots, long long n, void* stream) {
+  if (n <= 0) return 0;
+  SSB_REQUIRE(A != nullptr && B != nullptr && C != nullptr && roots != nullptr, "solve_cubic: NULL buffer");
+  k_solve_cubic<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>((const cd*)A, (const cd*)B, (const cd*)C,
+                                                                               (cd*)roots, n);
+  return ssb_check_launch("solve_cubic", (cudaStream_t)stream);
+}
+
+extern "C" int ssb_lqpqm2(const void* H, const void* v, const double* z, void* y, int n_bins, int M, int flooring,
+                          double eps, int singular_mode, int max_iter, void* stream) {
+  if (n_bins <= 0) return 0;
+  SSB_REQUIRE(M >= 1 && M <= SSB_MAX_SOURCES - 1, "lqpqm2: matrices of size %d (1..%d supported)", M, SSB_MAX_SOURCES - 1);
+  SSB_REQUIRE(max_iter >= 0, "lqpqm2: max_iter=%d must be non-negative", max_iter);
+  SSB_REQUIRE(H != nullptr && v != nullptr && z != nullptr && y != nullptr, "lqpqm2: NULL buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = (unsigned)((n_bins + 63) / 64);
+#define SSB_LQ(MM) \
+  case MM: k_lqpqm2<MM><<<grid, 64, 0, st>>>((const cd*)H, (const cd*)v, z, (cd*)y, n_bins, flooring, eps, singular_mode, max_iter); break;
+  switch (M) {
+    SSB_LQ(1) SSB_LQ(2) SSB_LQ(3) SSB_LQ(4) SSB_LQ(5) SSB_LQ(6) SSB_LQ(7)
+    default: break;
+  }
+#undef SSB_LQ
+  return ssb_check_launch("lqpqm2", st);
 }

@@ -168,6 +168,80 @@ def test_spatial_operators_match_reference(N):
     assert ret is W2 and relerr(W2, g[f"N{N}_ip1_max"]) < 1e-5
 
 
+def test_stft_istft_match_scipy_conventions():
+    """ssspy_b200.transform.stft / istft (ssb_stft.cu) against scipy.signal.stft / istft outputs for the call the
+    reference's notebooks make (window="hann", nperseg=n_fft, noverlap=n_fft-hop): same tuples, shapes and values;
+    round trip; CUDA tensors stay on the device and feed a separator directly."""
+    import torch
+    from ssspy_b200.bss import AuxLaplaceIVA
+    from ssspy_b200.transform import istft, stft
+    g = load("stft")
+    for c in "abcd":
+        n, h = int(g[c + "_n_fft"]), int(g[c + "_hop"])
+        x = g[c + "_x"]
+        f, t, Z = stft(x, window="hann", nperseg=n, noverlap=n - h)
+        assert Z.shape == g[c + "_Z"].shape and Z.dtype == np.complex128
+        np.testing.assert_allclose(f, g[c + "_f"], atol=1e-15)
+        np.testing.assert_allclose(t, g[c + "_t"], atol=1e-12)
+        np.testing.assert_allclose(Z, g[c + "_Z"], atol=1e-12)
+        ty, y = istft(g[c + "_Z"], window="hann", nperseg=n, noverlap=n - h)
+        assert y.shape == g[c + "_y"].shape
+        np.testing.assert_allclose(ty, np.arange(y.shape[-1]), atol=0)  # (scipy's own t is arange(x.shape[0]): the batch axis)
+        np.testing.assert_allclose(y, g[c + "_y"], atol=1e-11)
+        np.testing.assert_allclose(istft(g[c + "_Zr"], nperseg=n, noverlap=n - h)[1], g[c + "_yr"], atol=1e-11)
+        np.testing.assert_allclose(istft(Z, nperseg=n, noverlap=n - h)[1][..., :x.shape[-1]], x, atol=1e-11)  # round trip
+    _, _, Zw = stft(g["w_x"], window=g["w_win"], nperseg=128, noverlap=96)
+    np.testing.assert_allclose(Zw, g["w_Z"], atol=1e-12)
+    np.testing.assert_allclose(istft(g["w_Z"], window=g["w_win"], nperseg=128, noverlap=96)[1], g["w_y"], atol=1e-11)
+    # device-resident pipeline: waveform -> STFT -> separator -> inverse STFT without a host copy
+    xd = torch.as_tensor(g["d_x"], device="cuda")
+    _, _, Zd = stft(xd, nperseg=1024, noverlap=768)
+    assert Zd.is_cuda and relerr(Zd.cpu().numpy(), g["d_Z"]) < 1e-12
+    Yd = AuxLaplaceIVA(spatial_algorithm="IP")(Zd.to(torch.complex64), n_iter=3)
+    _, yd = istft(Yd if torch.is_tensor(Yd) else torch.as_tensor(Yd, device="cuda"), nperseg=1024, noverlap=768)
+    assert yd.is_cuda and yd.shape == (2, 5120) and bool(torch.isfinite(yd).all())
+    with pytest.raises(NotImplementedError):
+        stft(g["a_x"], window="hamming", nperseg=64)
+    with pytest.raises(ValueError, match="noverlap must be less than nperseg"):
+        stft(g["a_x"], nperseg=64, noverlap=64)
+    with pytest.raises(ValueError, match="greater than input length"):
+        stft(g["a_x"][..., :32], nperseg=64)
+
+
+def test_linalg_operators_of_the_ipa_path():
+    """Standalone cbrt / solve_cubic / lqpqm2 on the device (ssb_cbrt, ssb_solve_cubic, ssb_lqpqm2) against vectors
+    produced by the unmodified reference (ssspy/linalg/cubic.py:4, polynomial.py:9, lqpqm.py:13); roots additionally
+    satisfy their polynomial; error behaviour of solve_cubic as the reference's."""
+    import torch
+    from ssspy_b200.linalg import cbrt, lqpqm2, solve_cubic
+    g = load("linalg_ops")
+    out = cbrt(g["cbrt_real_in"])
+    assert not np.iscomplexobj(out)
+    np.testing.assert_allclose(out, g["cbrt_real_out"], rtol=1e-13, atol=0)
+    np.testing.assert_allclose(cbrt(g["cbrt_cplx_in"]), g["cbrt_cplx_out"], rtol=1e-12, atol=0)
+    A, B, C = g["cubic_A"], g["cubic_B"], g["cubic_C"]
+    x = solve_cubic(A, B, C)
+    assert x.shape == (3,) + A.shape and x.dtype == np.complex128
+    np.testing.assert_allclose(x, g["cubic_roots"], rtol=1e-10, atol=1e-11)
+    np.testing.assert_allclose(x ** 3 + A * x ** 2 + B * x + C, 0, atol=1e-9)
+    np.testing.assert_allclose(solve_cubic(A, B, C, all=False), g["cubic_first"], rtol=1e-10, atol=1e-11)
+    np.testing.assert_allclose(solve_cubic(g["cubic_cA"], g["cubic_cB"], g["cubic_cC"]), g["cubic_croots"], rtol=1e-10,
+                               atol=1e-11)
+    np.testing.assert_allclose(solve_cubic(g["cubic_gA"], g["cubic_gB"], g["cubic_gC"], g["cubic_gD"]),
+                               g["cubic_groots"], rtol=1e-10, atol=1e-11)
+    with pytest.raises(np.linalg.LinAlgError, match="Coefficients include zero"):
+        solve_cubic(np.array([1.0, 0.0]), np.ones(2), np.ones(2), np.ones(2))
+    xt = solve_cubic(torch.as_tensor(A, device="cuda"), torch.as_tensor(B, device="cuda"), torch.as_tensor(C, device="cuda"))
+    assert xt.is_cuda and relerr(xt.cpu().numpy(), g["cubic_roots"]) < 1e-10  # CUDA tensors in -> CUDA tensors out
+    for M in (1, 2, 3, 5):
+        H, v, z = g["lqpqm2_M%d_H" % M], g["lqpqm2_M%d_v" % M], g["lqpqm2_M%d_z" % M]
+        for it in (1, 10):
+            y = lqpqm2(H, v, z, max_iter=it)
+            assert y.shape == v.shape and relerr(y, g["lqpqm2_M%d_it%d_out" % (M, it)]) < 1e-8, (M, it)
+    with pytest.raises(NotImplementedError):
+        lqpqm2(H, v, z, singular_fn=lambda x: x < 1e-3)
+
+
 def test_linalg_known_answers_and_identities():
     """ssspy/linalg docstring known answers + the reference's property tests
     (tests/package/linalg/test_eigh.py:13-130, test_inv.py:9-18)."""

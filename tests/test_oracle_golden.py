@@ -216,3 +216,41 @@ def test_deferred_power_normalisation_commutes_with_the_source_model(normalizati
         o.normalize(st)
     for k in ("T", "V", "W"):
         assert np.abs(st[k] - ref[k]).max() <= 1e-12 * np.abs(ref[k]).max()
+
+
+def test_linalg_operators_of_the_ipa_path_match_reference():
+    """cbrt, solve_cubic and lqpqm2 (ssspy/linalg/cubic.py:4, polynomial.py:9, lqpqm.py:13) against vectors produced
+    by the unmodified reference (tests/golden/make_golden_linalg_ops.py)."""
+    g = load("linalg_ops")
+    np.testing.assert_allclose(olinalg.cbrt(g["cbrt_real_in"]), g["cbrt_real_out"], rtol=1e-13, atol=0)
+    np.testing.assert_allclose(olinalg.cbrt(g["cbrt_cplx_in"]), g["cbrt_cplx_out"], rtol=1e-13, atol=0)
+    np.testing.assert_allclose(olinalg.solve_cubic(g["cubic_A"], g["cubic_B"], g["cubic_C"]), g["cubic_roots"],
+                               rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(olinalg.solve_cubic(g["cubic_A"], g["cubic_B"], g["cubic_C"], all=False),
+                               g["cubic_first"], rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(olinalg.solve_cubic(g["cubic_cA"], g["cubic_cB"], g["cubic_cC"]), g["cubic_croots"],
+                               rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(olinalg.solve_cubic(g["cubic_gA"], g["cubic_gB"], g["cubic_gC"], g["cubic_gD"]),
+                               g["cubic_groots"], rtol=1e-12, atol=1e-13)
+    with pytest.raises(np.linalg.LinAlgError, match="Coefficients include zero"):
+        olinalg.solve_cubic(np.array([1.0, 0.0]), np.ones(2), np.ones(2), np.ones(2))
+    for M in (1, 2, 3, 5):
+        for it in (1, 10):
+            y = olinalg.lqpqm2(g["lqpqm2_M%d_H" % M], g["lqpqm2_M%d_v" % M], g["lqpqm2_M%d_z" % M], FLOORS["max"],
+                               max_iter=it)
+            assert relerr(y, g["lqpqm2_M%d_it%d_out" % (M, it)]) < 1e-9, (M, it)
+
+
+def test_stft_oracle_matches_scipy():
+    """oracle.transform against scipy.signal.stft / istft called as the reference's notebooks call them
+    (tests/golden/make_golden_stft.py); incl. an inverse of a spectrogram that is not the STFT of any signal."""
+    from oracle import transform as ot
+    g = load("stft")
+    for c in "abcd":
+        n, h = int(g[c + "_n_fft"]), int(g[c + "_hop"])
+        w = ot.hann(n)
+        np.testing.assert_allclose(ot.stft(g[c + "_x"], w, h), g[c + "_Z"], atol=1e-13)
+        np.testing.assert_allclose(ot.istft(g[c + "_Z"], w, h), g[c + "_y"], atol=1e-12)
+        np.testing.assert_allclose(ot.istft(g[c + "_Zr"], w, h), g[c + "_yr"], atol=1e-12)
+    np.testing.assert_allclose(ot.stft(g["w_x"], g["w_win"], 32), g["w_Z"], atol=1e-13)
+    np.testing.assert_allclose(ot.istft(g["w_Z"], g["w_win"], 32), g["w_y"], atol=1e-12)
