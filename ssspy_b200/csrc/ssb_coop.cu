@@ -1311,6 +1311,282 @@ int launch_update_ab(int which, const float* A, const float* Bm, float* T, float
 }
 
 // ================================================================================================
+// kf_mnmf_update<OUTER_ROWS>: the FastGaussMNMF multiplicative updates (ssspy/bss/mnmf.py:1344-1415) for four sources
+// with their elementwise factors formed IN the kernel instead of read from G / H arrays (km_gh wrote 4.3 GB and read
+// 6.6 GB per update, and Lambda = T V made another 2 GB round trip):
+//   Lambda_n = T_n V_n                                   GEMM1 on the tensor pipe (as kf_basis_coop)
+//   L_m = sum_n Lambda_n D[i,n,m], r_m = 1 / L_m, G_n = sum_m D[i,n,m] Z2_m r_m^2, H_n = sum_m D[i,n,m] r_m   per point
+//   num_n += G_n Op_n^T, den_n += H_n Op_n^T             GEMM2 (as kf_update_ab), Op = pre-split V resp. T chunks
+// Z2[b,m,i,j] = |q_m^H x|^2 is the only array streamed (written once per iteration by km_z2).  Warp = 16 outer indices
+// (bins resp. frames) of one mixture x ALL four sources: the accumulator fragments of GEMM1 sit at the same (outer,
+// inner) positions for every source, so the 4 x 4 mixing by D is thread-local.  K <= 16 (one k-step; 64 accumulator
+// registers for the four sources).  OUTER_ROWS = true: basis update (outer = bins, inner = frames, D of the thread's
+// two bins in registers); false: activation update (outer = frames, inner = bins, D of the 32 bins of a chunk staged in
+// shared memory next to the operand chunks).
+constexpr int MUW = 4;   // warps per CTA
+constexpr int MUS = 3;   // slots of the operand chunk ring
+
+template <bool OUTER_ROWS>
+__global__ void __launch_bounds__(MUW * 32)
+    kf_mnmf_update(const float* __restrict__ Z2, const float* __restrict__ Dm, float* Out,
+                   const float* OuterSrc /* == Out: read at the start, written at the end */,
+                   const __nv_bfloat16* __restrict__ Opd,
+                   __nv_bfloat16* __restrict__ OutSplit, int I, int J, int K, int nchunk_in, int nchunk_out,
+                   int flooring, float eps) {
+  constexpr int NS = 4, KP = 16, JKS = KP + PADH;
+  constexpr int CHB = 2 * JCV * JKS * 2;   // bytes of one 32-index operand chunk (hi + lo) of one source
+  constexpr int DCB = JCV * 16 * 4;        // bytes of the D block of one chunk (32 bins x 16 floats), activation only
+  constexpr int SLOT = NS * CHB + (OUTER_ROWS ? 0 : DCB);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const uint32_t op_s = (uint32_t)__cvta_generic_to_shared(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const size_t b = blockIdx.y;
+  const int n_outer = OUTER_ROWS ? I : J, n_inner = OUTER_ROWS ? J : I;
+  const int o0 = (blockIdx.x * MUW + warp) * 16;
+  const bool warp_active = o0 < n_outer;
+  const int oc[2] = {min(o0 + g, n_outer - 1), min(o0 + g + 8, n_outer - 1)};
+  const bool ovalid[2] = {o0 + g < n_outer, o0 + g + 8 < n_outer};
+  // outer-side A operand of GEMM1, per source: (outer row rr, basis nb * 8 + 2t, + 1), kept in shared memory
+  // ([source][hi | lo][4][lane]: conflict-free 32-bit accesses) to leave the registers to the accumulators
+  uint32_t* ofr = reinterpret_cast<uint32_t*>(smem_raw + MUS * SLOT) + warp * (NS * 2 * 4 * 32) + lane;
+#pragma unroll
+  for (int n = 0; n < NS; ++n)
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+      for (int nb = 0; nb < 2; ++nb) {
+        const int k0 = nb * 8 + 2 * t;
+        float v0 = 0.f, v1 = 0.f;
+        if (OUTER_ROWS) {  // T[b, n, bin, k]
+          const float* tr = OuterSrc + ((b * NS + n) * I + oc[rr]) * (size_t)K;
+          v0 = k0 < K ? tr[k0] : 0.f;
+          v1 = k0 + 1 < K ? tr[k0 + 1] : 0.f;
+        } else {           // V[b, n, k, frame]
+          const float* vc = OuterSrc + (b * NS + n) * (size_t)K * J + oc[rr];
+          v0 = k0 < K ? vc[(size_t)k0 * J] : 0.f;
+          v1 = k0 + 1 < K ? vc[(size_t)(k0 + 1) * J] : 0.f;
+        }
+        const Split sp = split2(v0, v1);
+        ofr[((n * 2 + 0) * 4 + nb * 2 + rr) * 32] = sp.hi;
+        ofr[((n * 2 + 1) * 4 + nb * 2 + rr) * 32] = sp.lo;
+      }
+  // D of the thread's two bins (basis update): dreg[rr][n * 4 + m]
+  float dreg[OUTER_ROWS ? 2 : 1][16];
+  if (OUTER_ROWS) {
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+      for (int e = 0; e < 16; e += 4) {
+        const float4 d4 = *reinterpret_cast<const float4*>(Dm + ((b * I + oc[rr]) * 16 + e));
+        dreg[rr][e] = d4.x;
+        dreg[rr][e + 1] = d4.y;
+        dreg[rr][e + 2] = d4.z;
+        dreg[rr][e + 3] = d4.w;
+      }
+  }
+  float num[NS][2][4], den[NS][2][4];
+#pragma unroll
+  for (int n = 0; n < NS; ++n)
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) num[n][q][c] = den[n][q][c] = 0.f;
+
+  // operand chunks of the four sources (+ the D block of the chunk's 32 bins) -> ring slot
+  const unsigned char* osrc = reinterpret_cast<const unsigned char*>(Opd);
+  auto issue_op = [&](int chunk, int slot) {
+    for (int c = threadIdx.x; c < NS * (CHB / 16); c += MUW * 32) {
+      const int n = c / (CHB / 16), w = c - n * (CHB / 16);
+      cp_async16(op_s + slot * SLOT + n * CHB + w * 16, osrc + ((b * NS + n) * (size_t)nchunk_in + chunk) * CHB + w * 16);
+    }
+    if (!OUTER_ROWS) {
+      for (int c = threadIdx.x; c < DCB / 16; c += MUW * 32) {
+        const int bin = min(chunk * JCV + (c >> 2), I - 1);
+        cp_async16(op_s + slot * SLOT + NS * CHB + c * 16, Dm + ((b * I + bin) * 16 + (c & 3) * 4));
+      }
+    }
+  };
+  const int mid = lane >> 3, mrow = lane & 7;
+  // GEMM1 (non-trans): matrices (hi k0-7, hi k8-15, lo k0-7, lo k8-15) of inner indices [.., +8)
+  const uint32_t l1base = pin(op_s + (mid >> 1) * (JCV * JKS * 2) + (mrow * JKS + (mid & 1) * 8) * 2);
+  // GEMM2 (trans): matrices (hi inner 0-7, hi inner 8-15, lo 0-7, lo 8-15) of basis [.., +8)
+  const uint32_t l2base = pin(op_s + (mid >> 1) * (JCV * JKS * 2) + (((mid & 1) * 8 + mrow) * JKS) * 2);
+  const size_t plane = (size_t)I * J;
+  const float* z2b = Z2 + b * NS * plane;
+  const int nsteps = (n_inner + 15) >> 4;
+  issue_op(0, 0);
+  cp_async_commit();
+  if (nchunk_in > 1) issue_op(1, 1);
+  cp_async_commit();
+  for (int s = 0; s < nsteps; ++s) {
+    const int chunk = s >> 1, slot = chunk % MUS;
+    if ((s & 1) == 0) {
+      cp_async_wait<1>();
+      __syncthreads();  // chunk `chunk` has landed for every warp; slot (chunk + 2) % MUS was last read two steps ago
+      if (chunk + 2 < nchunk_in) issue_op(chunk + 2, (chunk + 2) % MUS);
+      cp_async_commit();
+    }
+    if (!warp_active) continue;
+    const uint32_t sb = slot * SLOT + (s & 1) * (16 * JKS * 2);
+    uint32_t Ahi[NS][4], Alo[NS][4], Bhi[NS][4], Blo[NS][4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      // ---- Z2 of the half step: [m][rr] = (inner e = 0, 1) ----
+      float2 z2v[NS][2];
+      const int in0 = s * 16 + 8 * h + 2 * t;  // first inner index of this lane
+#pragma unroll
+      for (int m = 0; m < NS; ++m)
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          if (OUTER_ROWS) {
+            z2v[m][rr] = *reinterpret_cast<const float2*>(z2b + m * plane + (size_t)oc[rr] * J + in0);
+          } else {
+            const float* zp = z2b + m * plane + oc[rr];
+            z2v[m][rr] = make_float2(zp[(size_t)min(in0, I - 1) * J], zp[(size_t)min(in0 + 1, I - 1) * J]);
+          }
+        }
+      // ---- GEMM1: Lambda_n[16 outer x 8 inner] ----
+      float lam[NS][4];
+#pragma unroll
+      for (int n = 0; n < NS; ++n) {
+        uint32_t oh[4], ol[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          oh[j] = ofr[((n * 2 + 0) * 4 + j) * 32];
+          ol[j] = ofr[((n * 2 + 1) * 4 + j) * 32];
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) lam[n][c] = 0.f;
+        uint32_t bh0, bh1, bl0, bl1;
+        ldsm_x4(bh0, bh1, bl0, bl1, l1base + sb + n * CHB + (8 * h * JKS) * 2);
+        mma_split(lam[n], oh, ol, bh0, bh1, bl0, bl1);
+      }
+      // ---- per point: L, r, G, H; split into the A fragments of GEMM2 ----
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        float G[NS][2], H[NS][2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          float d[16];
+          bool valid = true;
+          if (OUTER_ROWS) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) d[q] = dreg[OUTER_ROWS ? rr : 0][q];
+          } else {
+            const int ib = (s & 1) * 16 + 8 * h + 2 * t + e;  // bin inside the chunk
+            valid = chunk * JCV + ib < I;
+#pragma unroll
+            for (int q = 0; q < 16; q += 4) {
+              const float4 d4 = lds128(op_s + slot * SLOT + NS * CHB + ib * 64 + q * 4);
+              d[q] = d4.x;
+              d[q + 1] = d4.y;
+              d[q + 2] = d4.z;
+              d[q + 3] = d4.w;
+            }
+          }
+          float r[NS], r2[NS];
+#pragma unroll
+          for (int m = 0; m < NS; ++m) {
+            float l = 0.f;
+#pragma unroll
+            for (int n = 0; n < NS; ++n) l = fmaf(lam[n][rr * 2 + e], d[n * 4 + m], l);
+            r[m] = fast_rcp(l);
+            r2[m] = (e ? z2v[m][rr].y : z2v[m][rr].x) * r[m] * r[m];
+          }
+#pragma unroll
+          for (int n = 0; n < NS; ++n) {
+            float gg = 0.f, hh = 0.f;
+#pragma unroll
+            for (int m = 0; m < NS; ++m) {
+              gg = fmaf(d[n * 4 + m], r2[m], gg);
+              hh = fmaf(d[n * 4 + m], r[m], hh);
+            }
+            // inner indices past the end: the operand rows are zero, the factor must be finite (Lambda = 0 there)
+            G[n][e] = valid ? gg : 0.f;
+            H[n][e] = valid ? hh : 0.f;
+          }
+        }
+#pragma unroll
+        for (int n = 0; n < NS; ++n) {
+          const Split sa = split2(G[n][0], G[n][1]);
+          const Split sh = split2(H[n][0], H[n][1]);
+          Ahi[n][h * 2 + rr] = sa.hi;
+          Alo[n][h * 2 + rr] = sa.lo;
+          Bhi[n][h * 2 + rr] = sh.hi;
+          Blo[n][h * 2 + rr] = sh.lo;
+        }
+      }
+    }
+    // ---- GEMM2: num_n += G_n Op_n^T, den_n += H_n Op_n^T (contraction over the 16 inner indices) ----
+#pragma unroll
+    for (int n = 0; n < NS; ++n)
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        uint32_t th0, th1, tl0, tl1;
+        ldsm_x4_t(th0, th1, tl0, tl1, l2base + sb + n * CHB + q * 16);
+        mma_split(num[n][q], Ahi[n], Alo[n], th0, th1, tl0, tl1);
+        mma_split(den[n][q], Bhi[n], Blo[n], th0, th1, tl0, tl1);
+      }
+  }
+  cp_async_wait<0>();
+  if (!warp_active) return;
+  // ---- Out <- floor(Out sqrt(num / den)), also written pre-split for the next kernel ----
+#pragma unroll
+  for (int n = 0; n < NS; ++n) {
+    const size_t bn = b * NS + n;
+    float* Ob = Out + bn * (size_t)K * (OUTER_ROWS ? I : J);
+#pragma unroll
+    for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        if (!ovalid[rr]) continue;
+        const int k0 = nb * 8 + 2 * t;
+        float vn[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          vn[e] = 0.f;
+          if (k0 + e < K) {
+            float* op = OUTER_ROWS ? Ob + (size_t)oc[rr] * K + k0 + e : Ob + (size_t)(k0 + e) * J + oc[rr];
+            vn[e] = ssb_floor(*op * sqrtf(num[n][nb][rr * 2 + e] / den[n][nb][rr * 2 + e]), flooring, eps);
+            *op = vn[e];
+          }
+        }
+        const Split sp = split2(vn[0], vn[1]);
+        __nv_bfloat16* oh = OutSplit + (bn * nchunk_out + (oc[rr] >> 5)) * (size_t)(2 * JCV * JKS) + (oc[rr] & 31) * JKS + k0;
+        *reinterpret_cast<uint32_t*>(oh) = sp.hi;
+        *reinterpret_cast<uint32_t*>(oh + JCV * JKS) = sp.lo;
+      }
+  }
+}
+
+int launch_mnmf_update(int which, const float* Z2, const float* Dm, float* T, float* V, __nv_bfloat16* Vs,
+                       __nv_bfloat16* Ts, int B, int I, int J, int K, int flooring, float eps, cudaStream_t st) {
+  constexpr int JKS = 16 + PADH, CHB = 2 * JCV * JKS * 2;
+  const int nchunk_j = (J + JCV - 1) / JCV, nchunk_i = (I + JCV - 1) / JCV;
+  const size_t ofr = (size_t)MUW * 4 * 2 * 4 * 32 * 4;
+  const size_t sm_b = (size_t)MUS * (4 * CHB) + ofr, sm_a = (size_t)MUS * (4 * CHB + JCV * 16 * 4) + ofr;
+  static bool attr_dev[SSB_MAX_DEVICES] = {};  // function attributes are per device
+  bool& attr_set = attr_dev[ssb_current_device()];
+  if (!attr_set) {
+    SSB_CUDA(cudaFuncSetAttribute(kf_mnmf_update<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_b));
+    SSB_CUDA(cudaFuncSetAttribute(kf_mnmf_update<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_a));
+    attr_set = true;
+  }
+  if (which == 0) {
+    dim3 gv(nchunk_j, B * 4);
+    kf_vsplit<1><<<gv, 128, 0, st>>>(V, Vs, J, K, nchunk_j);
+    if (ssb_check_launch("coop_vsplit", st)) return 1;
+    dim3 grid((I + MUW * 16 - 1) / (MUW * 16), B);
+    kf_mnmf_update<true><<<grid, MUW * 32, sm_b, st>>>(Z2, Dm, T, T, Vs, Ts, I, J, K, nchunk_j, nchunk_i, flooring, eps);
+    return ssb_check_launch("mnmf_basis_fused", st);
+  }
+  dim3 grid((J + MUW * 16 - 1) / (MUW * 16), B);
+  kf_mnmf_update<false><<<grid, MUW * 32, sm_a, st>>>(Z2, Dm, V, V, Ts, Vs, I, J, K, nchunk_i, nchunk_j, flooring, eps);
+  return ssb_check_launch("mnmf_activation_fused", st);
+}
+
+// ================================================================================================
 // Cooperative weighted covariance for N = 4 and N = 8 (GaussILRMA, p = 2):
 //   phi = 1 / (T V)                                   (ssspy/bss/ilrma.py:1494-1498)
 //   U[b,i,n,a,c] = (1/J) sum_j phi[n,i,j] x_a conj(x_c) (ilrma.py:1500-1505)
@@ -1597,6 +1873,17 @@ int ssb_coop_cov(const ssb_config* c, const cf* X, const float* T, const void* w
     return k16 ? launch_cov_coop<4, 1, 4, true>(c, X, T, Vs, U, st) : launch_cov_coop<4, 2, 4, true>(c, X, T, Vs, U, st);
   if (g2) return k16 ? launch_cov_coop<8, 1, 2>(c, X, T, Vs, U, st) : launch_cov_coop<8, 2, 2>(c, X, T, Vs, U, st);
   return k16 ? launch_cov_coop<8, 1, 4>(c, X, T, Vs, U, st) : launch_cov_coop<8, 2, 4>(c, X, T, Vs, U, st);
+}
+
+// FastGaussMNMF source model with the factors formed in the kernel (four sources, K <= 16): which = 0 basis, 1 activation
+int ssb_coop_mnmf_update(const ssb_config* c, int which, const float* Z2, const float* Dm, float* T, float* V, void* ws,
+                         cudaStream_t st) {
+  SSB_REQUIRE(c->n_sources == 4 && (c->n_frames % 16) == 0 && c->n_basis <= 16 && ws != nullptr,
+              "coop_mnmf_update: unsupported configuration");
+  __nv_bfloat16* Vs = (__nv_bfloat16*)ws;
+  __nv_bfloat16* Ts = (__nv_bfloat16*)((char*)ws + coop_vs_bytes(c));
+  return launch_mnmf_update(which, Z2, Dm, T, V, Vs, Ts, c->n_batch, c->n_bins, c->n_frames, c->n_basis, c->flooring,
+                            c->eps, st);
 }
 
 // FastGaussMNMF source model on the tensor pipe: which = 0 basis (reads V, writes T and the pre-split Ts),

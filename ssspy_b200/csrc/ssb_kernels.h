@@ -130,6 +130,7 @@ int ssbk_nmf_activation_ab(const float* A, const float* Bm, const float* T, floa
                            int flooring, float eps, cudaStream_t st);
 int ssbk_mnmf_gh(const cf* X, const float* T, const float* V, const float* Lam, const cf* Q, const float* D, float* G, float* H, int B,
                  int N, int I, int J, int K, cudaStream_t st);
+int ssbk_mnmf_z2(const cf* X, const cf* Q, float* Z2, int B, int N, int I, int J, cudaStream_t st);
 int ssbk_mnmf_phi(const cf* X, const float* T, const float* V, const float* Lam, const cf* Q, const float* D, float* phi, int B, int N,
                   int I, int J, int K, cudaStream_t st);
 int ssbk_mnmf_spatial(const cf* X, const float* T, const float* V, const float* Lam, const cf* Q, float* D, double* zsum, int B, int N,

