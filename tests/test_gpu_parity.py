@@ -227,7 +227,10 @@ def test_linalg_operators_of_the_ipa_path():
     well = np.ones(A.shape, dtype=bool)
     well[3:6] = False
     np.testing.assert_allclose(x[:, well], g["cubic_roots"][:, well], rtol=1e-10, atol=1e-11)
-    np.testing.assert_allclose(x ** 3 + A * x ** 2 + B * x + C, 0, atol=1e-9)
+    # (where -Q / 2 + sqrt(disc) cancels to zero the reference itself returns NaN: same pattern here)
+    assert np.array_equal(np.isnan(x[:, ~well]), np.isnan(g["cubic_roots"][:, ~well]))
+    fin = np.isfinite(x).all(axis=0)
+    np.testing.assert_allclose((x ** 3 + A * x ** 2 + B * x + C)[:, fin], 0, atol=1e-9)
     np.testing.assert_allclose(solve_cubic(A, B, C, all=False)[well], g["cubic_first"][well], rtol=1e-10, atol=1e-11)
     np.testing.assert_allclose(solve_cubic(g["cubic_cA"], g["cubic_cB"], g["cubic_cC"]), g["cubic_croots"], rtol=1e-10,
                                atol=1e-11)
