@@ -368,10 +368,12 @@ __global__ void k_solve_cubic(const cd* __restrict__ A, const cd* __restrict__ B
   const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (e >= n) return;
   const cd a = A[e], b = B[e], c = C[e];
-  const cd a2 = cd_mul(a, a);
-  const cd P = cd_add(cd_scale(a2, -1.0 / 3.0), b);
-  const cd Q = cd_add(cd_sub(cd_scale(cd_mul(a2, a), 2.0 / 27.0), cd_scale(cd_mul(a, b), 1.0 / 3.0)), c);
-  const cd hq = cd_scale(Q, 0.5), tp = cd_scale(P, 1.0 / 3.0);
+  // divisions, not multiplications by reciprocals: P == 0 decides the branch below, and coefficients constructed as
+  // B = A^2 / 3 must give P = 0 exactly as they do in the reference's -(A**2) / 3 + B
+  const cd a2 = cd_mul(a, a), a3 = cd_mul(a2, a), ab = cd_mul(a, b);
+  const cd P = cd_make(-a2.x / 3.0 + b.x, -a2.y / 3.0 + b.y);
+  const cd Q = cd_make((2.0 * a3.x) / 27.0 - ab.x / 3.0 + c.x, (2.0 * a3.y) / 27.0 - ab.y / 3.0 + c.y);
+  const cd hq = cd_scale(Q, 0.5), tp = cd_make(P.x / 3.0, P.y / 3.0);
   const cd disc = cd_add(cd_mul(hq, hq), cd_mul(cd_mul(tp, tp), tp));
   const bool sing = P.x == 0.0 && P.y == 0.0;
   const cd U = sing ? cd_make(1.0, 0.0) : cbrt_c(cd_add(cd_make(-hq.x, -hq.y), sqrt_c(disc)));

@@ -222,15 +222,14 @@ def test_linalg_operators_of_the_ipa_path():
     A, B, C = g["cubic_A"], g["cubic_B"], g["cubic_C"]
     x = solve_cubic(A, B, C)
     assert x.shape == (3,) + A.shape and x.dtype == np.complex128
-    # entries 3..5 are near-triple roots (P = B - A^2 / 3 ~ 1e-16): their roots move by cbrt(eps) ~ 1e-5 with the rounding
-    # of P (the device contracts a * a / 3 into FMAs), so they are checked through the polynomial only
+    # entries 3..5 are constructed with B = A^2 / 3 (P == 0 exactly in the reference's arithmetic, the singular branch):
+    # the kernel reproduces that branch decision; the roots of such triple-root-like cubics move by cbrt(eps) ~ 1e-5 with
+    # any rounding difference in Q, so their values are checked through the polynomial only
     well = np.ones(A.shape, dtype=bool)
     well[3:6] = False
     np.testing.assert_allclose(x[:, well], g["cubic_roots"][:, well], rtol=1e-10, atol=1e-11)
-    # (where -Q / 2 + sqrt(disc) cancels to zero the reference itself returns NaN: same pattern here)
-    assert np.array_equal(np.isnan(x[:, ~well]), np.isnan(g["cubic_roots"][:, ~well]))
-    fin = np.isfinite(x).all(axis=0)
-    np.testing.assert_allclose((x ** 3 + A * x ** 2 + B * x + C)[:, fin], 0, atol=1e-9)
+    assert np.isfinite(x).all()
+    np.testing.assert_allclose(x ** 3 + A * x ** 2 + B * x + C, 0, atol=1e-9)
     np.testing.assert_allclose(solve_cubic(A, B, C, all=False)[well], g["cubic_first"][well], rtol=1e-10, atol=1e-11)
     np.testing.assert_allclose(solve_cubic(g["cubic_cA"], g["cubic_cB"], g["cubic_cC"]), g["cubic_croots"], rtol=1e-10,
                                atol=1e-11)
