@@ -231,6 +231,21 @@ class DeviceSeparatorMixin:
         B = self._dims()[0]
         cs = os.environ.get("SSB_CHUNK")
         cs = int(cs) if cs else self.chunk_size
+        sizes = os.environ.get("SSB_HOST_LAYOUT") or getattr(self, "host_layout", None)
+        if sizes and cs is None and self._cpu_tensor_io:
+            # explicit chunk sizes for host tensors (experiments: the upload is the critical path, so the tail of the
+            # pipeline -- iterations and download of the LAST chunk -- is what an uneven layout shortens)
+            if isinstance(sizes, str):
+                sizes = [int(v) for v in sizes.split(",") if v.strip()]
+            out, b0 = [], 0
+            for n in sizes:
+                if b0 >= B:
+                    break
+                out.append((b0, min(b0 + int(n), B)))
+                b0 += int(n)
+            if b0 < B:
+                out.append((b0, B))
+            return out
         if cs is None and self._cpu_tensor_io and B >= 8:
             # host tensors in/out: eight chunks on four streams hide most of the PCIe copies behind the iterations
             # of the other chunks (tools/e2e_sweep.py: 22.8 ms vs 26.0 ms for one plan at config 2)

@@ -733,8 +733,7 @@ constexpr int ISSC_W = 4;  // warps (= bins) per block
 template <int N>
 __global__ void __launch_bounds__(ISSC_W * 32) k_iss1_cov(cf* __restrict__ Y, const float* __restrict__ phi,
                                                           long long sb, long long sn, long long si, int I, int J,
-                                                          int flooring, float eps, float* __restrict__ r2part,
-                                                          int prefetch_next) {
+                                                          int flooring, float eps, float* __restrict__ r2part) {
   constexpr int NO = N * (N - 1) / 2;      // off-diagonal pairs (a < c)
   constexpr int NV = N * N;                // reals per source: NO (re, im) pairs + N diagonals
   constexpr int NVAL = N * NV;             // statistics per bin
@@ -754,16 +753,7 @@ __global__ void __launch_bounds__(ISSC_W * 32) k_iss1_cov(cf* __restrict__ Y, co
   for (int i = blockIdx.x * ISSC_W + w; i < I; i += gridDim.x * ISSC_W) {
   const size_t base = ((size_t)b * N * I + i) * J;
   const float* ph0 = phi + (size_t)b * sb + (size_t)i * si;
-  // The warp's next bin: pull its slab into L2 now.  A warp alternates memory sweeps with a serial fp64 algebra phase
-  // and keeps only two iterations of loads in flight, so sweep 1 ran at HBM latency (3.1 TB/s for the kernel);
-  // SSB_ISS_PREFETCH=0 switches the hint off.
-  if (prefetch_next && i + (int)gridDim.x * ISSC_W < I) {
-    const cf* nb = Y + ((size_t)b * N * I + i + gridDim.x * ISSC_W) * J;
-#pragma unroll
-    for (int m = 0; m < N; ++m)
-      for (int e = lane * 16; e < J; e += 32 * 16)  // one 128-byte line per lane
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + m * cs + e));
-  }
+  // (prefetch.global.L2 of the warp's next bin at this point was measured: 2.83 vs 2.78 ms at config 3, no gain)
   // ---- sweep 1: weighted covariances ---------------------------------------------------------------------------
   // accumulators as (re, im) pairs [and pairs of diagonal entries], one packed FFMA2 per pair and source
   constexpr int NDP = (N + 1) / 2;
@@ -1379,10 +1369,9 @@ int ssbk_iss1(cf* Y, const float* phi, long long sb, long long sn, long long si,
       SSB_CUDA(cudaFuncSetAttribute(k_iss1_cov<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
       attr_set = true;
     }
-    static const int pf = getenv("SSB_ISS_PREFETCH") != nullptr ? atoi(getenv("SSB_ISS_PREFETCH")) : 1;
-    if (N == 2) k_iss1_cov<2><<<grid, ISSC_W * 32, sm, st>>>(Y, phi, sb, sn, si, I, J, flooring, eps, part, pf);
-    else if (N == 3) k_iss1_cov<3><<<grid, ISSC_W * 32, sm, st>>>(Y, phi, sb, sn, si, I, J, flooring, eps, part, pf);
-    else k_iss1_cov<4><<<grid, ISSC_W * 32, sm, st>>>(Y, phi, sb, sn, si, I, J, flooring, eps, part, pf);  // (capping it at 128
+    if (N == 2) k_iss1_cov<2><<<grid, ISSC_W * 32, sm, st>>>(Y, phi, sb, sn, si, I, J, flooring, eps, part);
+    else if (N == 3) k_iss1_cov<3><<<grid, ISSC_W * 32, sm, st>>>(Y, phi, sb, sn, si, I, J, flooring, eps, part);
+    else k_iss1_cov<4><<<grid, ISSC_W * 32, sm, st>>>(Y, phi, sb, sn, si, I, J, flooring, eps, part);  // (capping it at 128
     // registers for four blocks per SM changes nothing: 2.83 vs 2.72 ms at config 3, gpurun_out/r2q_c3_*.json)
     if (ssb_check_launch("update_by_iss1", st)) return 1;
     if (emit) {
