@@ -1337,6 +1337,9 @@ __global__ void __launch_bounds__(MUW * 32)
   constexpr int CHB = 2 * JCV * JKS * 2;   // bytes of one 32-index operand chunk (hi + lo) of one source
   constexpr int DCB = JCV * 16 * 4;        // bytes of the D block of one chunk (32 bins x 16 floats), activation only
   constexpr int SLOT = NS * CHB + (OUTER_ROWS ? 0 : DCB);
+  constexpr int PITCH = OUTER_ROWS ? 96 : 80;  // Z2 tile row pitch: conflict-free LDS.64 resp. LDS.32 fragment reads
+  constexpr int PTB = 16 * PITCH;              // bytes of one 16 x 16 tile
+  constexpr int ZST = 2;                       // stages of the per-warp Z2 tile ring (four tiles, one per m, per stage)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const uint32_t op_s = (uint32_t)__cvta_generic_to_shared(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1350,6 +1353,9 @@ __global__ void __launch_bounds__(MUW * 32)
   // outer-side A operand of GEMM1, per source: (outer row rr, basis nb * 8 + 2t, + 1), kept in shared memory
   // ([source][hi | lo][4][lane]: conflict-free 32-bit accesses) to leave the registers to the accumulators
   uint32_t* ofr = reinterpret_cast<uint32_t*>(smem_raw + MUS * SLOT) + warp * (NS * 2 * 4 * 32) + lane;
+  // per-warp ring of Z2 tiles [stage][m][16 rows][PITCH]: cp.async one step ahead, so the loads of step s + 1 are in
+  // flight while step s is computed (with direct global loads the kernel stalled on them: 40 % issue utilisation)
+  const uint32_t zr_s = op_s + MUS * SLOT + MUW * (NS * 2 * 4 * 32 * 4) + warp * (ZST * NS * PTB);
 #pragma unroll
   for (int n = 0; n < NS; ++n)
 #pragma unroll
@@ -1415,36 +1421,57 @@ __global__ void __launch_bounds__(MUW * 32)
   const size_t plane = (size_t)I * J;
   const float* z2b = Z2 + b * NS * plane;
   const int nsteps = (n_inner + 15) >> 4;
+  // tile of step s: 16 rows x 64 bytes per m, 4 lanes per row, 2 pieces per lane
+  //   OUTER_ROWS: rows = this warp's outer bins (clamped), columns = inner frames 16 s ..
+  //   else      : rows = inner bins 16 s .. (clamped), columns = this warp's outer frames
+  const float* tsrc[2];
+  uint32_t tdst[2];
+  int trow[2];
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int idx = it * 32 + lane, r = idx >> 2, part = idx & 3;
+    trow[it] = r;
+    tdst[it] = zr_s + r * PITCH + part * 16;
+    tsrc[it] = OUTER_ROWS ? z2b + (size_t)min(o0 + r, I - 1) * J + part * 4 : z2b + (size_t)min(o0, J - 16) + part * 4;
+  }
+  auto issue_tile = [&](int step) {
+    const uint32_t st = (step & 1) * (NS * PTB);
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const size_t adv = OUTER_ROWS ? (size_t)step * 16 : (size_t)min(step * 16 + trow[it], I - 1) * J;
+#pragma unroll
+      for (int m = 0; m < NS; ++m) cp_async16(tdst[it] + st + m * PTB, tsrc[it] + m * plane + adv);
+    }
+  };
+  const uint32_t zlane = OUTER_ROWS ? zr_s + g * PITCH + (2 * t) * 4 : zr_s + (2 * t) * PITCH + g * 4;
   issue_op(0, 0);
-  cp_async_commit();
-  if (nchunk_in > 1) issue_op(1, 1);
+  if (warp_active) issue_tile(0);
   cp_async_commit();
   for (int s = 0; s < nsteps; ++s) {
     const int chunk = s >> 1, slot = chunk % MUS;
-    if ((s & 1) == 0) {
-      cp_async_wait<1>();
-      __syncthreads();  // chunk `chunk` has landed for every warp; slot (chunk + 2) % MUS was last read two steps ago
-      if (chunk + 2 < nchunk_in) issue_op(chunk + 2, (chunk + 2) % MUS);
-      cp_async_commit();
-    }
+    // group s + 1: the Z2 tiles of the next step and, on even steps, the next operand chunk (its slot was last read
+    // two chunks ago, i.e. before the barrier of step s - 2)
+    if (warp_active && s + 1 < nsteps) issue_tile(s + 1);
+    if ((s & 1) == 0 && chunk + 1 < nchunk_in) issue_op(chunk + 1, (chunk + 1) % MUS);
+    cp_async_commit();
+    cp_async_wait<1>();  // everything but the group just committed: tiles of step s, operand chunk `chunk`
+    if ((s & 1) == 0) __syncthreads();  // the chunk was copied by all threads of the CTA
+    else __syncwarp();                  // the tiles by all lanes of the warp
     if (!warp_active) continue;
     const uint32_t sb = slot * SLOT + (s & 1) * (16 * JKS * 2);
     uint32_t Ahi[NS][4], Alo[NS][4], Bhi[NS][4], Blo[NS][4];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      // ---- Z2 of the half step: [m][rr] = (inner e = 0, 1) ----
+      // ---- Z2 of the half step from the ring: [m][rr] = (inner e = 0, 1) ----
       float2 z2v[NS][2];
-      const int in0 = s * 16 + 8 * h + 2 * t;  // first inner index of this lane
+      const uint32_t zb = zlane + (s & 1) * (NS * PTB);
 #pragma unroll
       for (int m = 0; m < NS; ++m)
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
-          if (OUTER_ROWS) {
-            z2v[m][rr] = *reinterpret_cast<const float2*>(z2b + m * plane + (size_t)oc[rr] * J + in0);
-          } else {
-            const float* zp = z2b + m * plane + oc[rr];
-            z2v[m][rr] = make_float2(zp[(size_t)min(in0, I - 1) * J], zp[(size_t)min(in0 + 1, I - 1) * J]);
-          }
+          if (OUTER_ROWS) z2v[m][rr] = lds64f(zb + m * PTB + (8 * rr) * PITCH + (8 * h) * 4);
+          else z2v[m][rr] = make_float2(lds32f(zb + m * PTB + (8 * h) * PITCH + 32 * rr),
+                                        lds32f(zb + m * PTB + (8 * h + 1) * PITCH + 32 * rr));
         }
       // ---- GEMM1: Lambda_n[16 outer x 8 inner] ----
       float lam[NS][4];
@@ -1565,7 +1592,8 @@ int launch_mnmf_update(int which, const float* Z2, const float* Dm, float* T, fl
   constexpr int JKS = 16 + PADH, CHB = 2 * JCV * JKS * 2;
   const int nchunk_j = (J + JCV - 1) / JCV, nchunk_i = (I + JCV - 1) / JCV;
   const size_t ofr = (size_t)MUW * 4 * 2 * 4 * 32 * 4;
-  const size_t sm_b = (size_t)MUS * (4 * CHB) + ofr, sm_a = (size_t)MUS * (4 * CHB + JCV * 16 * 4) + ofr;
+  const size_t sm_b = (size_t)MUS * (4 * CHB) + ofr + (size_t)MUW * 2 * 4 * 16 * 96;
+  const size_t sm_a = (size_t)MUS * (4 * CHB + JCV * 16 * 4) + ofr + (size_t)MUW * 2 * 4 * 16 * 80;
   static bool attr_dev[SSB_MAX_DEVICES] = {};  // function attributes are per device
   bool& attr_set = attr_dev[ssb_current_device()];
   if (!attr_set) {
