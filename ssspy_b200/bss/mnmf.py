@@ -209,6 +209,13 @@ class FastGaussMNMF(MNMFBase):
         if self.normalization:
             self.normalize(flooring_fn=flooring_fn)
 
+    def run_iterations(self, n_iter):
+        """``n_iter`` x ``update_once`` on the current state without loss recording or callbacks (the loop of
+        ssspy/bss/base.py:68-77) as one ``ssb_run`` per chunk plan: inside it the spatial sweep hands Z2 = |Q x|^2 of the
+        new diagonaliser to the source model of the next iteration."""
+        self._set_flooring(self.flooring_fn)
+        self._run_iterations(int(n_iter), False)
+
     def update_source_model(self, flooring_fn="self"):
         """``update_basis`` then ``update_activation`` (mnmf.py:1305-1417)."""
         self._set_flooring(choose_flooring_fn(flooring_fn, method=self))

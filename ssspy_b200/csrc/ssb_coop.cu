@@ -1332,7 +1332,7 @@ __global__ void __launch_bounds__(MUW * 32)
                    const float* OuterSrc /* == Out: read at the start, written at the end */,
                    const __nv_bfloat16* __restrict__ Opd,
                    __nv_bfloat16* __restrict__ OutSplit, int I, int J, int K, int nchunk_in, int nchunk_out,
-                   int flooring, float eps) {
+                   int flooring, float eps, const float* __restrict__ zscale) {
   constexpr int NS = 4, KP = 16, JKS = KP + PADH;
   constexpr int CHB = 2 * JCV * JKS * 2;   // bytes of one 32-index operand chunk (hi + lo) of one source
   constexpr int DCB = JCV * 16 * 4;        // bytes of the D block of one chunk (32 bins x 16 floats), activation only
@@ -1420,6 +1420,10 @@ __global__ void __launch_bounds__(MUW * 32)
   const uint32_t l2base = pin(op_s + (mid >> 1) * (JCV * JKS * 2) + (((mid & 1) * 8 + mrow) * JKS) * 2);
   const size_t plane = (size_t)I * J;
   const float* z2b = Z2 + b * NS * plane;
+  // Z2 written before the power normalisation of the diagonaliser (km_spatial): Z2_m / psi_m^2 is the current value
+  float zs[NS];
+#pragma unroll
+  for (int m = 0; m < NS; ++m) zs[m] = zscale != nullptr ? zscale[b * NS + m] : 1.0f;
   const int nsteps = (n_inner + 15) >> 4;
   // tile of step s: 16 rows x 64 bytes per m, 4 lanes per row, 2 pieces per lane
   //   OUTER_ROWS: rows = this warp's outer bins (clamped), columns = inner frames 16 s ..
@@ -1519,7 +1523,7 @@ __global__ void __launch_bounds__(MUW * 32)
 #pragma unroll
             for (int n = 0; n < NS; ++n) l = fmaf(lam[n][rr * 2 + e], d[n * 4 + m], l);
             r[m] = fast_rcp(l);
-            r2[m] = (e ? z2v[m][rr].y : z2v[m][rr].x) * r[m] * r[m];
+            r2[m] = (e ? z2v[m][rr].y : z2v[m][rr].x) * zs[m] * r[m] * r[m];
           }
 #pragma unroll
           for (int n = 0; n < NS; ++n) {
@@ -1587,8 +1591,9 @@ __global__ void __launch_bounds__(MUW * 32)
   }
 }
 
-int launch_mnmf_update(int which, const float* Z2, const float* Dm, float* T, float* V, __nv_bfloat16* Vs,
-                       __nv_bfloat16* Ts, int B, int I, int J, int K, int flooring, float eps, cudaStream_t st) {
+int launch_mnmf_update(int which, const float* Z2, const float* zscale, const float* Dm, float* T, float* V,
+                       __nv_bfloat16* Vs, __nv_bfloat16* Ts, int B, int I, int J, int K, int flooring, float eps,
+                       cudaStream_t st) {
   constexpr int JKS = 16 + PADH, CHB = 2 * JCV * JKS * 2;
   const int nchunk_j = (J + JCV - 1) / JCV, nchunk_i = (I + JCV - 1) / JCV;
   const size_t ofr = (size_t)MUW * 4 * 2 * 4 * 32 * 4;
@@ -1606,11 +1611,13 @@ int launch_mnmf_update(int which, const float* Z2, const float* Dm, float* T, fl
     kf_vsplit<1><<<gv, 128, 0, st>>>(V, Vs, J, K, nchunk_j);
     if (ssb_check_launch("coop_vsplit", st)) return 1;
     dim3 grid((I + MUW * 16 - 1) / (MUW * 16), B);
-    kf_mnmf_update<true><<<grid, MUW * 32, sm_b, st>>>(Z2, Dm, T, T, Vs, Ts, I, J, K, nchunk_j, nchunk_i, flooring, eps);
+    kf_mnmf_update<true><<<grid, MUW * 32, sm_b, st>>>(Z2, Dm, T, T, Vs, Ts, I, J, K, nchunk_j, nchunk_i, flooring, eps,
+                                                        zscale);
     return ssb_check_launch("mnmf_basis_fused", st);
   }
   dim3 grid((J + MUW * 16 - 1) / (MUW * 16), B);
-  kf_mnmf_update<false><<<grid, MUW * 32, sm_a, st>>>(Z2, Dm, V, V, Ts, Vs, I, J, K, nchunk_i, nchunk_j, flooring, eps);
+  kf_mnmf_update<false><<<grid, MUW * 32, sm_a, st>>>(Z2, Dm, V, V, Ts, Vs, I, J, K, nchunk_i, nchunk_j, flooring, eps,
+                                                       zscale);
   return ssb_check_launch("mnmf_activation_fused", st);
 }
 
@@ -1904,13 +1911,13 @@ int ssb_coop_cov(const ssb_config* c, const cf* X, const float* T, const void* w
 }
 
 // FastGaussMNMF source model with the factors formed in the kernel (four sources, K <= 16): which = 0 basis, 1 activation
-int ssb_coop_mnmf_update(const ssb_config* c, int which, const float* Z2, const float* Dm, float* T, float* V, void* ws,
-                         cudaStream_t st) {
+int ssb_coop_mnmf_update(const ssb_config* c, int which, const float* Z2, const float* zscale, const float* Dm, float* T,
+                         float* V, void* ws, cudaStream_t st) {
   SSB_REQUIRE(c->n_sources == 4 && (c->n_frames % 16) == 0 && c->n_basis <= 16 && ws != nullptr,
               "coop_mnmf_update: unsupported configuration");
   __nv_bfloat16* Vs = (__nv_bfloat16*)ws;
   __nv_bfloat16* Ts = (__nv_bfloat16*)((char*)ws + coop_vs_bytes(c));
-  return launch_mnmf_update(which, Z2, Dm, T, V, Vs, Ts, c->n_batch, c->n_bins, c->n_frames, c->n_basis, c->flooring,
+  return launch_mnmf_update(which, Z2, zscale, Dm, T, V, Vs, Ts, c->n_batch, c->n_bins, c->n_frames, c->n_basis, c->flooring,
                             c->eps, st);
 }
 

@@ -38,8 +38,9 @@ int ssb_coop_cov_supported(const ssb_config* cfg);
 int ssb_coop_cov(const ssb_config* cfg, const cf* X, const float* T, const void* ws, cf* U, cudaStream_t st);
 // FastGaussMNMF: tensor-core multiplicative updates with elementwise factors given as arrays (which: 0 basis, 1 activation)
 // the same updates with G / H formed in the kernel from Z2 = |Q x|^2 and D (four sources, K <= 16; ssb_coop.cu)
-int ssb_coop_mnmf_update(const ssb_config* cfg, int which, const float* Z2, const float* Dm, float* T, float* V, void* ws,
-                         cudaStream_t st);
+// (zscale[b * 4 + m], optional: Z2 is multiplied by it on load)
+int ssb_coop_mnmf_update(const ssb_config* cfg, int which, const float* Z2, const float* zscale, const float* Dm, float* T,
+                         float* V, void* ws, cudaStream_t st);
 int ssb_coop_update_ab(const ssb_config* cfg, int which, const float* A, const float* Bm, float* T, float* V, void* ws,
                        cudaStream_t st);
 int ssb_coop_source(const ssb_config* cfg, const cf* X, const cf* W, float* T, float* V, float* P, void* ws,

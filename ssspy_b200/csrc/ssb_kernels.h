@@ -134,9 +134,9 @@ int ssbk_mnmf_z2(const cf* X, const cf* Q, float* Z2, int B, int N, int I, int J
 int ssbk_mnmf_phi(const cf* X, const float* T, const float* V, const float* Lam, const cf* Q, const float* D, float* phi, int B, int N,
                   int I, int J, int K, cudaStream_t st);
 int ssbk_mnmf_spatial(const cf* X, const float* T, const float* V, const float* Lam, const cf* Q, float* D, double* zsum, int B, int N,
-                      int I, int J, int K, int update_d, cudaStream_t st);
+                      int I, int J, int K, int update_d, cudaStream_t st, float* z2out = nullptr);
 int ssbk_mnmf_normalize(const double* zsum, cf* Q, float* D, int B, int N, int I, int J, int flooring, float eps,
-                        cudaStream_t st);
+                        cudaStream_t st, float* zscale = nullptr);
 int ssbk_mnmf_rowloss(const cf* X, const float* T, const float* V, const float* Lam, const cf* Q, const float* D, double* rowloss, int B,
                       int N, int I, int J, int K, cudaStream_t st);
 // Lleft (optional, [B,I,N,N] c128): Qinv <- Lleft Qinv before the filter (Q given in the whitened domain)

@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(MW * 32, (N <= 4 ? 4 : 1)) km_spatial(const cf
                                                       const float* __restrict__ V, const float* __restrict__ Lam,
                                                  const cf* __restrict__ Q,
                                                       float* __restrict__ D, double* __restrict__ zsum, int B, int I,
-                                                      int J, int K, int update_d) {
+                                                      int J, int K, int update_d, float* __restrict__ z2out) {
   constexpr int GS = N <= 4 ? N : 1;
   __shared__ BinCtx<N> ctx[MW];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -255,10 +255,8 @@ __global__ void __launch_bounds__(MW * 32, (N <= 4 ? 4 : 1)) km_spatial(const cf
 #pragma unroll
       for (int gs = 0; gs < GS; ++gs) num[gs][m] = den[gs][m] = 0.f;
     }
-#pragma unroll 2
-    for (int j = lane; j < J; j += 32) {
-      float lam[N], L[N], Z2[N];
-      frame_stats<N, LAM>(c, rb, j, lam, L, Z2);
+    // accumulate one frame: lam[n] = Lambda_n, Z2[m], L[m]
+    auto accumulate = [&](const float (&lam)[N], const float (&L)[N], const float (&Z2)[N]) {
       float ln[GS];
 #pragma unroll
       for (int gs = 0; gs < GS; ++gs) {
@@ -275,6 +273,60 @@ __global__ void __launch_bounds__(MW * 32, (N <= 4 ? 4 : 1)) km_spatial(const cf
         for (int gs = 0; gs < GS; ++gs) {
           num[gs][m] = fmaf(ln[gs], a, num[gs][m]);
           den[gs][m] = fmaf(ln[gs], r, den[gs][m]);
+        }
+      }
+    };
+    if (LAM && N <= 4 && (J & 1) == 0) {
+      // two frames per lane: 16-byte loads of X, 8-byte loads of Lambda, and (inside ssb_run) 8-byte stores of the Z2 of
+      // the filters just updated, which the source model of the next iteration streams (kf_mnmf_update)
+      for (int j = 2 * lane; j < J; j += 64) {
+        float4 x[N];
+        float2 l2[N];
+#pragma unroll
+        for (int m = 0; m < N; ++m) {
+          x[m] = *reinterpret_cast<const float4*>(rb.x + m * rb.cs + j);
+          l2[m] = *reinterpret_cast<const float2*>(rb.lam + m * rb.cs + j);
+        }
+        float za[N], zb[N];
+#pragma unroll
+        for (int f = 0; f < 2; ++f) {
+          float lam[N], L[N], Z2[N];
+#pragma unroll
+          for (int n = 0; n < N; ++n) lam[n] = f ? l2[n].y : l2[n].x;
+#pragma unroll
+          for (int m = 0; m < N; ++m) {
+            float l = 0.f, zr = 0.f, zi = 0.f;
+#pragma unroll
+            for (int n = 0; n < N; ++n) l = fmaf(lam[n], c.d(n, m), l);
+#pragma unroll
+            for (int cc = 0; cc < N; ++cc) {
+              const cf q = c.q(m, cc);
+              const float xr = f ? x[cc].z : x[cc].x, xi = f ? x[cc].w : x[cc].y;
+              zr = fmaf(q.x, xr, fmaf(-q.y, xi, zr));
+              zi = fmaf(q.x, xi, fmaf(q.y, xr, zi));
+            }
+            L[m] = l;
+            Z2[m] = zr * zr + zi * zi;
+            if (f) zb[m] = Z2[m];
+            else za[m] = Z2[m];
+          }
+          accumulate(lam, L, Z2);
+        }
+        if (z2out != nullptr && n0 == 0) {
+#pragma unroll
+          for (int m = 0; m < N; ++m)
+            *reinterpret_cast<float2*>(z2out + ((size_t)b * N * I + i) * J + m * rb.cs + j) = make_float2(za[m], zb[m]);
+        }
+      }
+    } else {
+#pragma unroll 2
+      for (int j = lane; j < J; j += 32) {
+        float lam[N], L[N], Z2[N];
+        frame_stats<N, LAM>(c, rb, j, lam, L, Z2);
+        accumulate(lam, L, Z2);
+        if (z2out != nullptr && n0 == 0) {
+#pragma unroll
+          for (int m = 0; m < N; ++m) z2out[((size_t)b * N * I + i) * J + m * rb.cs + j] = Z2[m];
         }
       }
     }
@@ -294,7 +346,7 @@ __global__ void __launch_bounds__(MW * 32, (N <= 4 ? 4 : 1)) km_spatial(const cf
 
 // psi_m = floor(sqrt(mean_ij Z2_m)); Q[:,m,:] /= psi_m; D[:,:,m] /= psi_m^2   (mnmf.py:666-678)
 __global__ void km_normalize(const double* __restrict__ zsum, cf* __restrict__ Q, float* __restrict__ D, int N, int I,
-                             int J, int flooring, double eps) {
+                             int J, int flooring, double eps, float* __restrict__ zscale) {
   __shared__ double sh[8];
   __shared__ double s_psi[SSB_MAX_SOURCES];
   const int b = blockIdx.x;
@@ -308,6 +360,7 @@ __global__ void km_normalize(const double* __restrict__ zsum, cf* __restrict__ Q
       double t = 0.0;
       for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
       s_psi[m] = ssb_floor(sqrt(t / ((double)I * (double)J)), flooring, eps);
+      if (zscale != nullptr) zscale[b * N + m] = (float)(1.0 / (s_psi[m] * s_psi[m]));  // Z2_m scales with |q_m|^2
     }
     __syncthreads();
   }
@@ -498,19 +551,19 @@ int ssbk_mnmf_phi(const cf* X, const float* T, const float* V, const float* Lam,
   return ssb_check_launch("mnmf_phi", st);
 }
 int ssbk_mnmf_spatial(const cf* X, const float* T, const float* V, const float* Lam, const cf* Q, float* D, double* zsum, int B, int N,
-                      int I, int J, int K, int update_d, cudaStream_t st) {
+                      int I, int J, int K, int update_d, cudaStream_t st, float* z2out) {
   if (Lam != nullptr) {
     SSB_DISPATCH_N(N, (km_spatial<NN, true><<<blocks_for((long long)B * I, MW), MW * 32, 0, st>>>(X, T, V, Lam, Q, D, zsum,
-                                                                                                   B, I, J, K, update_d)));
+                                                                                                   B, I, J, K, update_d, z2out)));
   } else {
     SSB_DISPATCH_N(N, (km_spatial<NN, false><<<blocks_for((long long)B * I, MW), MW * 32, 0, st>>>(X, T, V, Lam, Q, D, zsum,
-                                                                                                    B, I, J, K, update_d)));
+                                                                                                    B, I, J, K, update_d, z2out)));
   }
   return ssb_check_launch("mnmf_spatial", st);
 }
 int ssbk_mnmf_normalize(const double* zsum, cf* Q, float* D, int B, int N, int I, int J, int flooring, float eps,
-                        cudaStream_t st) {
-  km_normalize<<<B, 256, 0, st>>>(zsum, Q, D, N, I, J, flooring, (double)eps);
+                        cudaStream_t st, float* zscale) {
+  km_normalize<<<B, 256, 0, st>>>(zsum, Q, D, N, I, J, flooring, (double)eps, zscale);
   return ssb_check_launch("mnmf_normalize", st);
 }
 int ssbk_mnmf_rowloss(const cf* X, const float* T, const float* V, const float* Lam, const cf* Q, const float* D, double* rowloss, int B,

@@ -188,6 +188,10 @@ struct ssb_plan {
   // k_iss1_cov); trusted only inside ssb_run, where nothing else touches Y between two iterations
   float* r2part = nullptr;  // [B, groups, N, J]
   bool r2_valid = false;
+  // FastGaussMNMF inside ssb_run: km_spatial leaves Z2 = |Q x|^2 of the new filters in `big` for the next iteration's
+  // source model; zscale[b, m] = 1 / psi_m^2 when the power normalisation rescaled Q after it was written
+  bool in_run = false, z2_valid = false, z2_scaled = false;
+  float* zscale = nullptr;
   bool part() const { return cfg.partitioning != 0; }
   bool mnmf() const { return cfg.model == SSB_MODEL_FASTMNMF_GAUSS; }
   // modes whose state lives in Y (no demixing filter): ISS1 / ISS2 / IPA
@@ -226,6 +230,7 @@ size_t carve(ssb_plan* p, char* base) {
   p->big2 = p->mnmf() ? cv.take<float>(B * N * I * J) : nullptr;
   p->qinv = p->mnmf() ? cv.take<cd>(B * I * N * N) : nullptr;
   p->big3 = p->mnmf() ? cv.take<float>(B * N * I * J) : nullptr;
+  p->zscale = p->mnmf() ? cv.take<float>(B * N) : nullptr;
   p->phi_iva = cv.take<float>(B * N * J);
   p->r2 = cv.take<float>(B * N * J);
   const bool iva = c.model == SSB_MODEL_IVA_LAPLACE || c.model == SSB_MODEL_IVA_GAUSS;
@@ -591,6 +596,14 @@ int mnmf_lambda(ssb_plan* p, const float** lam, cudaStream_t st) {
   return 0;
 }
 
+// four sources, K <= 16: G / H and Lambda are formed inside the update kernels from Z2 = |Q x|^2 and D; no Lambda, G, H
+// arrays at all.  SSB_MNMF_FUSED=0 (read once) keeps the array path.
+bool mnmf_fused_source(const ssb_plan* p) {
+  static const int fused_src = getenv("SSB_MNMF_FUSED") != nullptr ? atoi(getenv("SSB_MNMF_FUSED")) : 1;
+  const ssb_config& c = p->cfg;
+  return fused_src && c.fast_path && c.n_sources == 4 && c.n_basis <= 16 && (c.n_frames % 16) == 0 && p->fused.bytes > 0;
+}
+
 int mnmf_source(ssb_plan* p, cudaStream_t st) {
   const ssb_config& c = p->cfg;
   const int B = c.n_batch, N = c.n_sources, I = c.n_bins, J = c.n_frames, K = c.n_basis;
@@ -602,11 +615,15 @@ int mnmf_source(ssb_plan* p, cudaStream_t st) {
   }
   // four sources, K <= 16: G / H and Lambda are formed inside the update kernels from Z2 = |Q x|^2 (one pass over X)
   // and D; no Lambda, G, H arrays at all.  SSB_MNMF_FUSED=0 (read once) keeps the array path below.
-  static const int fused_src = getenv("SSB_MNMF_FUSED") != nullptr ? atoi(getenv("SSB_MNMF_FUSED")) : 1;
-  if (tc && fused_src && N == 4 && K <= 16) {
-    TRY(ssbk_mnmf_z2(p->Xk, p->Wk, p->big, B, N, I, J, st));
-    TRY(ssb_coop_mnmf_update(&c, 0, p->big, p->variance, p->T, p->V, p->fused.base, st));
-    return ssb_coop_mnmf_update(&c, 1, p->big, p->variance, p->T, p->V, p->fused.base, st);
+  if (tc && mnmf_fused_source(p)) {
+    if (!p->in_run) p->z2_valid = false;  // outside ssb_run anything may have changed Q between two calls
+    if (!p->z2_valid) {
+      TRY(ssbk_mnmf_z2(p->Xk, p->Wk, p->big, B, N, I, J, st));
+      p->z2_scaled = false;
+    }
+    const float* zs = p->z2_scaled ? p->zscale : nullptr;
+    TRY(ssb_coop_mnmf_update(&c, 0, p->big, zs, p->variance, p->T, p->V, p->fused.base, st));
+    return ssb_coop_mnmf_update(&c, 1, p->big, zs, p->variance, p->T, p->V, p->fused.base, st);
   }
   const float* lam;
   TRY(mnmf_lambda(p, &lam, st));
@@ -636,14 +653,25 @@ int mnmf_spatial(ssb_plan* p, cudaStream_t st) {
   }
   if (c.spatial == SSB_SPATIAL_IP1) TRY(ssbk_ip1(p->Wk, p->U, B * I, N, c.flooring, c.eps, st));
   else TRY(ssbk_ip2(p->Wk, p->U, B * I, N, c.pairs, c.n_pairs, N, nullptr, c.flooring, c.eps, st));
-  return ssbk_mnmf_spatial(p->Xk, p->T, p->V, lam, p->Wk, p->variance, p->rowloss, B, N, I, J, K, 1, st);
+  // inside ssb_run the sweep also leaves Z2 of the new filters for the next iteration's source model (SSB_MNMF_Z2EMIT=0:
+  // a separate km_z2 pass per iteration instead)
+  static const int emit_on = getenv("SSB_MNMF_Z2EMIT") != nullptr ? atoi(getenv("SSB_MNMF_Z2EMIT")) : 1;
+  const bool emit = emit_on && p->in_run && lam != nullptr && mnmf_fused_source(p);
+  TRY(ssbk_mnmf_spatial(p->Xk, p->T, p->V, lam, p->Wk, p->variance, p->rowloss, B, N, I, J, K, 1, st,
+                        emit ? p->big : nullptr));
+  p->z2_valid = emit;
+  p->z2_scaled = false;
+  return 0;
 }
 
 int mnmf_normalize(ssb_plan* p, bool have_zsum, cudaStream_t st) {
   const ssb_config& c = p->cfg;
   const int B = c.n_batch, N = c.n_sources, I = c.n_bins, J = c.n_frames, K = c.n_basis;
   if (!have_zsum) TRY(ssbk_mnmf_spatial(p->Xk, p->T, p->V, nullptr, p->Wk, p->variance, p->rowloss, B, N, I, J, K, 0, st));
-  return ssbk_mnmf_normalize(p->rowloss, p->Wk, p->variance, B, N, I, J, c.flooring, c.eps, st);
+  TRY(ssbk_mnmf_normalize(p->rowloss, p->Wk, p->variance, B, N, I, J, c.flooring, c.eps, st,
+                          p->z2_valid ? p->zscale : nullptr));
+  p->z2_scaled = p->z2_valid;
+  return 0;
 }
 
 int mnmf_loss(ssb_plan* p, double* loss, cudaStream_t st) {
@@ -911,9 +939,16 @@ extern "C" int ssb_run(ssb_plan* p, int n_iter, double* loss, void* stream) {
     if (rc) return rc;
     return w_exit(p, (cudaStream_t)stream);
   }
-  for (int it = 0; it < n_iter; ++it) {
-    TRY(update_once_impl(p, (cudaStream_t)stream));
-    if (loss) TRY(loss_impl(p, loss + (size_t)it * p->cfg.n_batch, (cudaStream_t)stream));
+  {
+    struct RunScope {  // state handed from one iteration to the next is only trusted between the iterations of this loop
+      ssb_plan* q;
+      explicit RunScope(ssb_plan* q_) : q(q_) { q->in_run = true; q->z2_valid = false; }
+      ~RunScope() { q->in_run = false; q->z2_valid = false; }
+    } scope(p);
+    for (int it = 0; it < n_iter; ++it) {
+      TRY(update_once_impl(p, (cudaStream_t)stream));
+      if (loss) TRY(loss_impl(p, loss + (size_t)it * p->cfg.n_batch, (cudaStream_t)stream));
+    }
   }
   p->fused.vs_valid = false;
   p->r2_valid = false;
