@@ -377,357 +377,6 @@ __global__ void __launch_bounds__(CoopShape<N>::NW * 32)
 }
 
 // ------------------------------------------------------------------------------------------------
-// kf_cov_ip1_basis (N = 2): the spatial update of iteration t and the basis update of iteration t + 1 in one kernel,
-// so that a bin tile's X is pulled from HBM once for both (the second pass hits L2):
-//   pass 0   R = T V,  phi = 1 / R,  U_n = mean_j phi x x^H                           (ilrma.py:1494-1505)
-//   between  IP1 in fp64, n = 0 then n = 1 with the updated row 0 (_update_spatial_model.py:63-76); W is written
-//            back UNNORMALISED and q[b,i,n] = mean_j |w_n^H x|^2 is emitted for kf_normalize
-//   pass 1   kf_basis_coop's loop with the new w_n: P = |w_n^H x|^2,  T <- T sqrt(sum_j V P / R^2 / sum_j V / R)
-// The power normalisation of iteration t (W /= psi, T /= psi^2, ilrma.py:412-444) commutes with the two source-model
-// updates that follow it: with P -> P / psi^2, T -> T / psi^2 the ratio of the basis update is unchanged and the
-// activation update is invariant, so kf_normalize runs AFTER the activation kernel and rescales the new T (and W).
-// Same tiling, rings and fragment conventions as kf_basis_coop: warp (bt, n) owns source n of tile bt.
-template <int KS, bool REV>
-__global__ void __launch_bounds__(CoopShape<2>::NW * 32)
-    kf_cov_ip1_basis(const cf* __restrict__ X, cf* Wrw, float* __restrict__ T, const __nv_bfloat16* __restrict__ Vs,
-                     float* __restrict__ Pout, __nv_bfloat16* __restrict__ Ts, double* __restrict__ q, int I, int J,
-                     int K, int nchunk, int nchunk_i, int flooring, float eps, int l2_hints) {
-  constexpr int N = 2;
-  constexpr bool rev = REV;
-  constexpr int BT = CoopShape<N>::BT, NW = CoopShape<N>::NW;
-  constexpr int KP = 16 * KS, JKS = KP + PADH;
-  constexpr int CHB = 2 * JCV * JKS * 2;
-  constexpr int XTB = N * 2048;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const uint32_t xs_s = (uint32_t)__cvta_generic_to_shared(smem_raw);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = lane >> 2, t = lane & 3;
-  const int bt = warp / N, n = warp - bt * N;
-  const int b = blockIdx.y;
-  const uint32_t vs_s = xs_s + XST * BT * XTB + warp * 2 * CHB;
-  cf* wx = reinterpret_cast<cf*>(smem_raw + XST * BT * XTB + NW * 2 * CHB) + bt * 32;  // new row 0: [16 rows][2]
-  const int i0 = (blockIdx.x * BT + bt) * 16;
-  if (i0 >= I) return;
-  const int row[2] = {i0 + g, i0 + g + 8};
-  const bool rvalid[2] = {row[0] < I, row[1] < I};
-  const int rowc[2] = {min(row[0], I - 1), min(row[1], I - 1)};
-  const size_t bn = (size_t)b * N + n;
-
-  uint32_t Thi[KS][4], Tlo[KS][4];
-  float Told[KS][2][2][2];
-#pragma unroll
-  for (int ks = 0; ks < KS; ++ks)
-#pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-      const float* tr = T + (bn * I + rowc[rr]) * K;
-#pragma unroll
-      for (int nb = 0; nb < 2; ++nb) {
-        const int k0 = ks * 16 + nb * 8 + 2 * t;
-        const float v0 = (k0 < K) ? tr[k0] : 0.f;
-        const float v1 = (k0 + 1 < K) ? tr[k0 + 1] : 0.f;
-        Told[ks][nb][rr][0] = v0;
-        Told[ks][nb][rr][1] = v1;
-        const Split s = split2(v0, v1);
-        Thi[ks][nb * 2 + rr] = s.hi;
-        Tlo[ks][nb * 2 + rr] = s.lo;
-      }
-    }
-  // the lane works on the demixing matrix of row rs of its pair (rows g, g + 8) between the passes
-  const int rs = t & 1;
-  cf* wmat = Wrw + ((size_t)b * I + (rs ? rowc[1] : rowc[0])) * 4;
-  cf wo[4];
-#pragma unroll
-  for (int e = 0; e < 4; ++e) wo[e] = wmat[e];
-
-  const cf* xsrc0[4];
-  const cf* xsrc[4];
-  uint32_t xdst[4];
-#pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int c = it * 32 + lane, r = c >> 3, ch = c & 7;
-    xsrc0[it] = X + (bn * I + min(i0 + r, I - 1)) * (size_t)J + 2 * ch;
-    xdst[it] = pin(xs_s + bt * XTB + (n * 16 + r) * 128 + ((ch ^ ((r & 1) << 2)) << 4));
-  }
-  auto issue_x = [&](uint32_t slot_bytes) {
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      cp_async16(xdst[it] + slot_bytes, xsrc[it]);
-      xsrc[it] += 16;
-    }
-  };
-  // second pass: X is read for the last time (and P is only written): keep both from displacing the slabs that other
-  // CTAs still have to re-read from L2
-  const uint64_t pol = l2_evict_first_policy();
-  // REV: the second pass walks the frames backwards, so that the lines a CTA read last in pass 0 (the ones most
-  // likely to be still in L2) are re-read first; all sums over the frames are order-independent
-  constexpr int xstep = rev ? -16 : 16;
-  auto issue_x_last = [&](uint32_t slot_bytes) {
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      if (l2_hints) cp_async16_hint(xdst[it] + slot_bytes, xsrc[it], pol);
-      else cp_async16(xdst[it] + slot_bytes, xsrc[it]);
-      xsrc[it] += xstep;
-    }
-  };
-  const unsigned char* vsrc0 = reinterpret_cast<const unsigned char*>(Vs) + bn * (size_t)nchunk * CHB + lane * 16;
-  const unsigned char* vsrc = vsrc0;
-  const uint32_t vdst = pin(vs_s + lane * 16);
-  auto issue_v = [&](int buf) {
-#pragma unroll
-    for (int c = 0; c < CHB / 16; c += 32) cp_async16(vdst + buf * CHB + c * 16, vsrc + c * 16);
-    vsrc += CHB;
-  };
-  const uint32_t xlane[2] = {pin(xs_s + bt * XTB + g * 128 + ((t ^ ((g & 1) << 2)) << 4)),
-                             pin(xs_s + bt * XTB + g * 128 + (((4 + t) ^ ((g & 1) << 2)) << 4))};
-  const int mid = lane >> 3, mrow = lane & 7;
-  const uint32_t l1base = pin(vs_s + (mid >> 1) * (JCV * JKS * 2) + (mrow * JKS + (mid & 1) * 8) * 2);
-  const uint32_t l2base = pin(vs_s + (mid >> 1) * (JCV * JKS * 2) + (((mid & 1) * 8 + mrow) * JKS) * 2);
-  const int nsteps = J >> 4;
-  static_assert(XST == 3, "see kf_basis_coop");
-
-  // ================= pass 0: weighted covariance of source n =================
-  float ua[2][4];  // [rr]: U00, U11, Re U01, Im U01   (U_ac = sum phi x_a conj(x_c))
-#pragma unroll
-  for (int rr = 0; rr < 2; ++rr)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) ua[rr][c] = 0.f;
-#pragma unroll
-  for (int it = 0; it < 4; ++it) xsrc[it] = xsrc0[it];
-  issue_v(0);
-  issue_x(0);
-  cp_async_commit();
-  if (nsteps > 1) issue_x(BT * XTB);
-  cp_async_commit();
-  {
-    uint32_t rd_slot = 0, wr_slot = 2 * (BT * XTB);
-    for (int s = 0; s < nsteps; ++s) {
-      cp_async_wait<XST - 2>();
-      bar_sync_tile<N * 32>(bt);
-      if (s + 2 < nsteps) issue_x(wr_slot);
-      if ((s & 1) == 0 && (s >> 1) + 1 < nchunk) issue_v(((s >> 1) + 1) & 1);
-      cp_async_commit();
-      const uint32_t voff = ((s >> 1) & 1) * CHB + (s & 1) * (16 * JKS * 2);
-      const uint32_t vb1 = l1base + voff;
-      const uint32_t xb0 = xlane[0] + rd_slot, xb1 = xlane[1] + rd_slot;
-      rd_slot = rd_slot + BT * XTB == XST * BT * XTB ? 0 : rd_slot + BT * XTB;
-      wr_slot = wr_slot + BT * XTB == XST * BT * XTB ? 0 : wr_slot + BT * XTB;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        float R[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-          uint32_t bh0, bh1, bl0, bl1;
-          ldsm_x4(bh0, bh1, bl0, bl1, vb1 + (8 * h * JKS + ks * 16) * 2);
-          mma_split(R, Thi[ks], Tlo[ks], bh0, bh1, bl0, bl1);
-        }
-#pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-          const float4 x0 = lds128((h ? xb1 : xb0) + rr * 1024);
-          const float4 x1 = lds128((h ? xb1 : xb0) + 2048 + rr * 1024);
-          const float f0 = fast_rcp(R[rr * 2 + 0]), f1 = fast_rcp(R[rr * 2 + 1]);  // no floor on R (ilrma.py:1494-1498)
-          ua[rr][0] = fmaf(f0, fmaf(x0.x, x0.x, x0.y * x0.y), fmaf(f1, fmaf(x0.z, x0.z, x0.w * x0.w), ua[rr][0]));
-          ua[rr][1] = fmaf(f0, fmaf(x1.x, x1.x, x1.y * x1.y), fmaf(f1, fmaf(x1.z, x1.z, x1.w * x1.w), ua[rr][1]));
-          ua[rr][2] = fmaf(f0, fmaf(x0.x, x1.x, x0.y * x1.y), fmaf(f1, fmaf(x0.z, x1.z, x0.w * x1.w), ua[rr][2]));
-          ua[rr][3] = fmaf(f0, fmaf(x0.y, x1.x, -x0.x * x1.y), fmaf(f1, fmaf(x0.w, x1.z, -x0.z * x1.w), ua[rr][3]));
-        }
-      }
-    }
-  }
-  cp_async_wait<0>();
-  const float invJ = 1.0f / (float)J;
-#pragma unroll
-  for (int rr = 0; rr < 2; ++rr)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      float v = ua[rr][c];
-      v += __shfl_xor_sync(0xffffffffu, v, 1);
-      v += __shfl_xor_sync(0xffffffffu, v, 2);
-      ua[rr][c] = v * invJ;
-    }
-
-  // ================= IP1 of row n (fp64); warp 1 waits for warp 0's row =================
-  cf wn[2];  // the new row n of this lane's matrix (row rs of the pair)
-  {
-    const cd u00 = cd_make((double)(rs ? ua[1][0] : ua[0][0]), 0.0);
-    const cd u11 = cd_make((double)(rs ? ua[1][1] : ua[0][1]), 0.0);
-    const cd u01 = cd_make((double)(rs ? ua[1][2] : ua[0][2]), (double)(rs ? ua[1][3] : ua[0][3]));
-    const cd u10 = cd_conj(u01);
-    cd w0[2] = {cf2cd(wo[0]), cf2cd(wo[1])};
-    const cd w1[2] = {cf2cd(wo[2]), cf2cd(wo[3])};
-    if (n == 1) {
-      bar_sync_tile<N * 32>(bt);
-      const int r = g + 8 * rs;
-      w0[0] = cf2cd(wx[r * 2 + 0]);
-      w0[1] = cf2cd(wx[r * 2 + 1]);
-    }
-    // A = W U_n, x = A^-1 e_n (adjugate / det), d = floor(sqrt(max(Re(x^H U_n x), 0))), w_n = conj(x) / d
-    const cd a00 = cd_add(cd_mul(w0[0], u00), cd_mul(w0[1], u10));
-    const cd a01 = cd_add(cd_mul(w0[0], u01), cd_mul(w0[1], u11));
-    const cd a10 = cd_add(cd_mul(w1[0], u00), cd_mul(w1[1], u10));
-    const cd a11 = cd_add(cd_mul(w1[0], u01), cd_mul(w1[1], u11));
-    const cd idet = cd_inv(cd_sub(cd_mul(a00, a11), cd_mul(a01, a10)));
-    const cd x0 = n == 0 ? cd_mul(a11, idet) : cd_mul(cd_make(-a01.x, -a01.y), idet);
-    const cd x1 = n == 0 ? cd_mul(cd_make(-a10.x, -a10.y), idet) : cd_mul(a00, idet);
-    const cd t0 = cd_add(cd_mul(u00, x0), cd_mul(u01, x1));
-    const cd t1 = cd_add(cd_mul(u10, x0), cd_mul(u11, x1));
-    const double qq = cd_mulc(t0, x0).x + cd_mulc(t1, x1).x;
-    const double d = ssb_floor(sqrt(fmax(qq, 0.0)), flooring, (double)eps);
-    wn[0] = cd2cf(cd_scale(cd_conj(x0), 1.0 / d));
-    wn[1] = cd2cf(cd_scale(cd_conj(x1), 1.0 / d));
-    if (t < 2 && (rs ? rvalid[1] : rvalid[0])) {
-      wmat[n * 2 + 0] = wn[0];
-      wmat[n * 2 + 1] = wn[1];
-    }
-    if (n == 0) {
-      if (t < 2) {
-        const int r = g + 8 * rs;
-        wx[r * 2 + 0] = wn[0];
-        wx[r * 2 + 1] = wn[1];
-      }
-      bar_sync_tile<N * 32>(bt);
-    }
-  }
-  // w[rr][m]: own row from this lane, the other row of the pair from the neighbour lane (t ^ 1)
-  cf w[2][N];
-#pragma unroll
-  for (int m = 0; m < N; ++m) {
-    const float ox = __shfl_xor_sync(0xffffffffu, wn[m].x, 1), oy = __shfl_xor_sync(0xffffffffu, wn[m].y, 1);
-    w[0][m] = rs ? make_float2(ox, oy) : wn[m];
-    w[1][m] = rs ? wn[m] : make_float2(ox, oy);
-  }
-
-  // ================= pass 1: basis update with the new filter (X from L2) =================
-  float num[2 * KS][4], den[2 * KS][4];
-#pragma unroll
-  for (int qi = 0; qi < 2 * KS; ++qi)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) num[qi][c] = den[qi][c] = 0.f;
-  float qs[2] = {0.f, 0.f};
-  // V chunk c (frames 32c .. 32c + 31) always lives in buffer c & 1
-  auto issue_v_chunk = [&](int c) {
-    const unsigned char* src = vsrc0 + (size_t)c * CHB;
-#pragma unroll
-    for (int e = 0; e < CHB / 16; e += 32) cp_async16(vdst + (c & 1) * CHB + e * 16, src + e * 16);
-  };
-  const int first = rev ? nsteps - 1 : 0;  // frame step handled first
-#pragma unroll
-  for (int it = 0; it < 4; ++it) xsrc[it] = xsrc0[it] + first * 16;
-  vsrc = vsrc0;
-  if constexpr (rev) {
-    // the last chunk may hold a single step (odd number of steps): its predecessor is then needed one step later
-    // already, so both are requested up front (both buffers are free)
-    issue_v_chunk(first >> 1);
-    if ((first >> 1) >= 1) issue_v_chunk((first >> 1) - 1);
-  } else {
-    issue_v(0);
-  }
-  issue_x_last(0);
-  cp_async_commit();
-  if (nsteps > 1) issue_x_last(BT * XTB);
-  cp_async_commit();
-  const size_t ptile0 = ((bn * (size_t)((I + 15) >> 4) + (size_t)(i0 >> 4)) * (size_t)(J >> 4) + (size_t)first) * 256;
-  constexpr int pstep = rev ? -256 : 256;
-  float* pout[2] = {pin_ptr(Pout + ptile0 + g * 16 + 2 * t), pin_ptr(Pout + ptile0 + (g + 8) * 16 + 2 * t)};
-  {
-    uint32_t rd_slot = 0, wr_slot = 2 * (BT * XTB);
-    for (int r = 0; r < nsteps; ++r) {
-      const int s = rev ? nsteps - 1 - r : r;  // frame step of this iteration
-      cp_async_wait<XST - 2>();
-      bar_sync_tile<N * 32>(bt);
-      if (r + 2 < nsteps) issue_x_last(wr_slot);
-      if constexpr (rev) {
-        // entering chunk c = s >> 1 (s odd; the chunk of r = 0 came with its predecessor in the prologue): request
-        // chunk c - 1 into the buffer of chunk c + 1, which is finished; it is first read two steps from now
-        if ((s & 1) && r > 0 && (s >> 1) >= 1) issue_v_chunk((s >> 1) - 1);
-      } else {
-        if ((s & 1) == 0 && (s >> 1) + 1 < nchunk) issue_v(((s >> 1) + 1) & 1);
-      }
-      cp_async_commit();
-      const uint32_t voff = ((s >> 1) & 1) * CHB + (s & 1) * (16 * JKS * 2);
-      const uint32_t vb1 = l1base + voff, vb2 = l2base + voff;
-      const uint32_t xb0 = xlane[0] + rd_slot, xb1 = xlane[1] + rd_slot;
-      rd_slot = rd_slot + BT * XTB == XST * BT * XTB ? 0 : rd_slot + BT * XTB;
-      wr_slot = wr_slot + BT * XTB == XST * BT * XTB ? 0 : wr_slot + BT * XTB;
-      float R[2][4];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) R[h][c] = 0.f;
-#pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-          uint32_t bh0, bh1, bl0, bl1;
-          ldsm_x4(bh0, bh1, bl0, bl1, vb1 + (8 * h * JKS + ks * 16) * 2);
-          mma_split(R[h], Thi[ks], Tlo[ks], bh0, bh1, bl0, bl1);
-        }
-      }
-      uint32_t Ahi[4], Alo[4], Bhi[4], Blo[4];
-#pragma unroll
-      for (int h = 0; h < 2; ++h)
-#pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-          float4 x[N];
-#pragma unroll
-          for (int m = 0; m < N; ++m) x[m] = lds128((h ? xb1 : xb0) + m * 2048 + rr * 1024);
-          float p0, p1;
-          power2<N>(x, w[rr], p0, p1);
-          if (l2_hints) __stcs(reinterpret_cast<float2*>(pout[rr] + 8 * h), make_float2(p0, p1));
-          else *reinterpret_cast<float2*>(pout[rr] + 8 * h) = make_float2(p0, p1);
-          qs[rr] += p0 + p1;
-          const float i0v = fast_rcp(R[h][rr * 2 + 0]);
-          const float i1v = fast_rcp(R[h][rr * 2 + 1]);
-          const Split sa = split2(p0 * i0v * i0v, p1 * i1v * i1v);
-          const Split sb = split2(i0v, i1v);
-          Ahi[h * 2 + rr] = sa.hi;
-          Alo[h * 2 + rr] = sa.lo;
-          Bhi[h * 2 + rr] = sb.hi;
-          Blo[h * 2 + rr] = sb.lo;
-        }
-      pout[0] += pstep;
-      pout[1] += pstep;
-#pragma unroll
-      for (int qi = 0; qi < 2 * KS; ++qi) {
-        uint32_t vh0, vh1, vl0, vl1;
-        ldsm_x4_t(vh0, vh1, vl0, vl1, vb2 + qi * 16);
-        mma_split(num[qi], Ahi, Alo, vh0, vh1, vl0, vl1);
-        mma_split(den[qi], Bhi, Blo, vh0, vh1, vl0, vl1);
-      }
-    }
-  }
-  // q[b, i, n] = mean_j |y|^2 with the unnormalised filter (the term kf_ip1_n2 gets from the unweighted covariance)
-#pragma unroll
-  for (int rr = 0; rr < 2; ++rr) {
-    float v = qs[rr];
-    v += __shfl_xor_sync(0xffffffffu, v, 1);
-    v += __shfl_xor_sync(0xffffffffu, v, 2);
-    if (t == 0 && rvalid[rr]) q[((size_t)b * I + row[rr]) * N + n] = (double)v / (double)J;
-  }
-#pragma unroll
-  for (int ks = 0; ks < KS; ++ks)
-#pragma unroll
-    for (int nb = 0; nb < 2; ++nb)
-#pragma unroll
-      for (int rr = 0; rr < 2; ++rr) {
-        if (!rvalid[rr]) continue;
-        const int qi = ks * 2 + nb;
-        const int k0 = ks * 16 + nb * 8 + 2 * t;
-        float tn[2];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          tn[e] = 0.f;
-          if (k0 + e < K) {
-            const float ratio = num[qi][rr * 2 + e] / den[qi][rr * 2 + e];
-            tn[e] = ssb_floor(sqrtf(ratio) * Told[ks][nb][rr][e], flooring, eps);
-            T[(bn * I + row[rr]) * K + k0 + e] = tn[e];
-          }
-        }
-        const Split sp = split2(tn[0], tn[1]);
-        __nv_bfloat16* th = Ts + (bn * nchunk_i + (row[rr] >> 5)) * (size_t)(2 * JCV * JKS) + (row[rr] & 31) * JKS + k0;
-        *reinterpret_cast<uint32_t*>(th) = sp.hi;
-        *reinterpret_cast<uint32_t*>(th + JCV * JKS) = sp.lo;
-      }
-}
-
-// ------------------------------------------------------------------------------------------------
 // kf_activation_coop:  V <- V sqrt( sum_i T P / R^2  /  sum_i T / R ),  R = T V with the new T
 // (ssspy/bss/ilrma.py:1130-1204).  CTA = (group of AW*16 frames, source, mixture); warp = 16 frames and owns its V
 // entries completely (no partial sums, no atomics: deterministic).  All warps walk over the bins together: the
@@ -948,7 +597,7 @@ __global__ void __launch_bounds__(ACW * 32, MINB)
 
 template <int N, int KS>
 int launch_coop(const ssb_config* c, const cf* X, const cf* W, float* T, float* V, float* P, __nv_bfloat16* Vs,
-                __nv_bfloat16* Ts, int vs_valid, cudaStream_t st, cf* Wrw = nullptr, double* q = nullptr,
+                __nv_bfloat16* Ts, int vs_valid, cudaStream_t st,
                 int parts = 7) {  // parts: 1 = pre-split of V, 2 = basis kernel, 4 = activation kernel
   const int B = c->n_batch, I = c->n_bins, J = c->n_frames, K = c->n_basis;
   constexpr int BT = CoopShape<N>::BT, NW = CoopShape<N>::NW;
@@ -977,10 +626,6 @@ int launch_coop(const ssb_config* c, const cf* X, const cf* W, float* T, float* 
   bool& attr_set = attr_dev[ssb_current_device()];
   if (!attr_set) {
     SSB_CUDA(cudaFuncSetAttribute(kf_basis_coop<N, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    if (N == 2) {
-      SSB_CUDA(cudaFuncSetAttribute(kf_cov_ip1_basis<KS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-      SSB_CUDA(cudaFuncSetAttribute(kf_cov_ip1_basis<KS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    }
     SSB_CUDA(cudaFuncSetAttribute(kf_activation_coop<KS, AW, PST, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_act));
     SSB_CUDA(cudaFuncSetAttribute(kf_activation_coop<KS, AW1, AP1, AB1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_act1));
     attr_set = true;
@@ -988,24 +633,6 @@ int launch_coop(const ssb_config* c, const cf* X, const cf* W, float* T, float* 
   dim3 grid((I + 16 * BT - 1) / (16 * BT), B);
   if (!(parts & 2)) {
     // the basis update is done by another kernel (ssb_tma.cu)
-  } else if (q != nullptr) {
-    // spatial update of the previous iteration fused in front of the basis update (N = 2, Vs must be valid)
-    if (N != 2 || Wrw == nullptr || !vs_valid) {
-      ssb_set_error("coop_cov_ip1_basis: needs n_sources = 2 and a valid pre-split activation");
-      return 1;
-    }
-    // SSB_FUSE_ITER bits (ssb_plan.cu enables the path on bit 0): 2 = one CTA per SM (shared memory padded to 120 KB:
-    // half the slabs waiting in L2 for their second pass), 4 = no L2 eviction hints, 8 = second pass backwards
-    const char* e = getenv("SSB_FUSE_ITER");
-    const int mode = e ? atoi(e) : 1;
-    const size_t smf = (mode & 2) ? (sm + 1024 > (size_t)120 * 1024 ? sm + 1024 : (size_t)120 * 1024) : sm + 1024;
-    if (mode & 8)
-      kf_cov_ip1_basis<KS, true><<<grid, NW * 32, smf, st>>>(X, Wrw, T, Vs, P, Ts, q, I, J, K, nchunk, nchunk_i,
-                                                            c->flooring, c->eps, (mode & 4) ? 0 : 1);
-    else
-      kf_cov_ip1_basis<KS, false><<<grid, NW * 32, smf, st>>>(X, Wrw, T, Vs, P, Ts, q, I, J, K, nchunk, nchunk_i,
-                                                             c->flooring, c->eps, (mode & 4) ? 0 : 1);
-    if (ssb_check_launch("coop_cov_ip1_basis", st)) return 1;
   } else {
     kf_basis_coop<N, KS><<<grid, NW * 32, sm, st>>>(X, W, T, Vs, P, Ts, I, J, K, nchunk, nchunk_i, c->flooring, c->eps);
     if (ssb_check_launch("coop_basis", st)) return 1;
@@ -1066,10 +693,10 @@ int ssb_coop_vsplit(const ssb_config* c, const float* V, void* ws, int vs_valid,
   float* Vm = const_cast<float*>(V);
   if (c->n_basis <= 16) {
     SSB_DISPATCH_N(c->n_sources, return (launch_coop<NN, 1>(c, nullptr, nullptr, nullptr, Vm, nullptr, Vs, Ts, vs_valid, st,
-                                                            nullptr, nullptr, 1)));
+                                                            1)));
   } else {
     SSB_DISPATCH_N(c->n_sources, return (launch_coop<NN, 2>(c, nullptr, nullptr, nullptr, Vm, nullptr, Vs, Ts, vs_valid, st,
-                                                            nullptr, nullptr, 1)));
+                                                            1)));
   }
   return 0;
 }
@@ -1079,27 +706,11 @@ int ssb_coop_activation(const ssb_config* c, float* V, float* P, void* ws, cudaS
   __nv_bfloat16* Vs = (__nv_bfloat16*)ws;
   __nv_bfloat16* Ts = (__nv_bfloat16*)((char*)ws + coop_vs_bytes(c));
   if (c->n_basis <= 16) {
-    SSB_DISPATCH_N(c->n_sources, return (launch_coop<NN, 1>(c, nullptr, nullptr, nullptr, V, P, Vs, Ts, 1, st, nullptr,
-                                                            nullptr, 4)));
+    SSB_DISPATCH_N(c->n_sources, return (launch_coop<NN, 1>(c, nullptr, nullptr, nullptr, V, P, Vs, Ts, 1, st, 4)));
   } else {
-    SSB_DISPATCH_N(c->n_sources, return (launch_coop<NN, 2>(c, nullptr, nullptr, nullptr, V, P, Vs, Ts, 1, st, nullptr,
-                                                            nullptr, 4)));
+    SSB_DISPATCH_N(c->n_sources, return (launch_coop<NN, 2>(c, nullptr, nullptr, nullptr, V, P, Vs, Ts, 1, st, 4)));
   }
   return 0;
-}
-
-// N = 2 inside ssb_run: IP1 of the iteration that has just had its source model updated (W is rewritten
-// unnormalised, q[b,i,n] = mean_j |y|^2 emitted), then basis and activation update of the NEXT iteration; the caller
-// runs kf_normalize afterwards (see kf_cov_ip1_basis).  Needs the Vs left by the previous activation update.
-int ssb_coop_spatial_source(const ssb_config* c, const cf* X, cf* W, float* T, float* V, float* P, void* ws, double* q,
-                            cudaStream_t st) {
-  SSB_REQUIRE((c->n_frames % 16) == 0 && c->n_basis <= 32 && c->n_sources == 2 && W != nullptr && ws != nullptr &&
-                  q != nullptr,
-              "coop_spatial_source: unsupported configuration");
-  __nv_bfloat16* Vs = (__nv_bfloat16*)ws;
-  __nv_bfloat16* Ts = (__nv_bfloat16*)((char*)ws + coop_vs_bytes(c));
-  if (c->n_basis <= 16) return launch_coop<2, 1>(c, X, W, T, V, P, Vs, Ts, 1, st, W, q);
-  return launch_coop<2, 2>(c, X, W, T, V, P, Vs, Ts, 1, st, W, q);
 }
 
 // ================================================================================================

@@ -1309,10 +1309,10 @@ int ssb_fused_source_and_cov(const ssb_config* c, ssb_fused_ws* ws, const cf* X,
   return 0;
 }
 
-// iterations fused across the update_once boundary inside ssb_run (N = 2, IP1): see kf_cov_ip1_basis
+// iterations fused across the update_once boundary inside ssb_run (N = 2, IP1): see ssb_fused_spatial_source
 int ssb_fused_iter_fusable(const ssb_config* c, const ssb_fused_ws* ws) {
   return ssb_fused_supported(c) && c->n_sources == 2 && c->spatial == SSB_SPATIAL_IP1 && ws != nullptr &&
-         ws->bytes > 0 && ssb_fused_coop_enabled() &&
+         ws->bytes > 0 && ssb_fused_coop_enabled() && ssb_tma_supported(c) && (ssb_tma_mask(c) & 4) != 0 &&
          (c->normalization == SSB_NORM_POWER || c->normalization == SSB_NORM_NONE);
 }
 
@@ -1320,13 +1320,16 @@ int ssb_fused_spatial_source(const ssb_config* c, ssb_fused_ws* ws, const cf* X,
                              double* q, cudaStream_t st) {
   SSB_REQUIRE(ws != nullptr && ws->bytes > 0 && ws->zeroed && ws->vs_valid,
               "fused_spatial_source: the source model of the first iteration must have run in this ssb_run");
-  if (ssb_tma_supported(c) && (ssb_tma_mask(c) & 4)) {
-    // covariance + IP1 + next basis update on TMA-fed tiles whose frames are split over warps (the second pass over a
-    // tile is served by L2), then the activation update
-    if (ssb_tma_spatial_basis_n2(c, X, W, T, ssb_coop_vs(c, ws->base), P, ssb_coop_ts(c, ws->base), q, st)) return 1;
-    return ssb_coop_activation(c, V, P, ws->base, st);
-  }
-  return ssb_coop_spatial_source(c, X, W, T, V, P, ws->base, q, st);
+  SSB_REQUIRE(ssb_tma_supported(c) && (ssb_tma_mask(c) & 4),
+              "fused_spatial_source: the fused covariance + IP1 + basis kernel is the TMA tile kernel (SSB_TMA bit 2)");
+  // covariance + IP1 + next basis update on TMA-fed tiles whose frames are split over warps (the second pass over a tile
+  // is served by L2), then the activation update.  The power normalisation of iteration t (W /= psi, T /= psi^2,
+  // ilrma.py:412-444) commutes with the two source-model updates that follow it: with P -> P / psi^2, T -> T / psi^2 the
+  // ratio of the basis update is unchanged and the activation update is invariant, so kf_normalize runs AFTER the
+  // activation kernel and rescales the new T (and W); W is written back unnormalised and q[b,i,n] = mean_j |w_n^H x|^2 is
+  // emitted for it (tests/test_oracle_golden.py::test_deferred_power_normalisation_commutes_with_the_source_model).
+  if (ssb_tma_spatial_basis_n2(c, X, W, T, ssb_coop_vs(c, ws->base), P, ssb_coop_ts(c, ws->base), q, st)) return 1;
+  return ssb_coop_activation(c, V, P, ws->base, st);
 }
 
 template <int KS>

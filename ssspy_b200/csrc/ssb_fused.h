@@ -23,12 +23,11 @@ int ssb_fused_source_and_cov(const ssb_config* cfg, ssb_fused_ws* ws, const cf* 
 int ssb_fused_coop_enabled();
 // N = 2, IP1, inside ssb_run only: [covariance + IP1 of iteration t, W unnormalised, q = mean_j |y|^2] fused with the
 // basis update of iteration t + 1 (one pass over X from HBM), then the activation update; the caller normalises
-// afterwards (kf_cov_ip1_basis in ssb_coop.cu explains why the order is legal)
+// afterwards (ssb_fused_spatial_source in ssb_fused.cu explains why the order is legal); the kernel is the TMA tile
+// kernel of ssb_tma.cu (SSB_TMA bit 2)
 int ssb_fused_iter_fusable(const ssb_config* cfg, const ssb_fused_ws* ws);
 int ssb_fused_spatial_source(const ssb_config* cfg, ssb_fused_ws* ws, const cf* X, cf* W, float* T, float* V, float* P,
                              double* q, cudaStream_t st);
-int ssb_coop_spatial_source(const ssb_config* cfg, const cf* X, cf* W, float* T, float* V, float* P, void* ws, double* q,
-                            cudaStream_t st);
 // cooperative MM source model (ssb_coop.cu): basis kernel with one CTA = 16-bin tiles x all sources sharing the X
 // slab in shared memory, then the activation kernel; ws is zero-initialised scratch of ssb_coop_ws_bytes() bytes
 // (pre-split bf16 copies of V and T)

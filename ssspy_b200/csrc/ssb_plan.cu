@@ -894,13 +894,12 @@ extern "C" int ssb_compute_loss(ssb_plan* p, double* loss, void* stream) {
 }
 
 namespace {
-// SSB_FUSE_ITER (read at every call so that tests can toggle it): 1 = inside ssb_run, GaussILRMA-IP1 with two sources
-// runs the spatial update of iteration t and the basis update of iteration t + 1 as one kernel (kf_cov_ip1_basis)
-int fuse_iter_enabled(const ssb_config* c) {
+// Iterations fused across the update_once boundary (GaussILRMA-IP1, two sources, inside ssb_run): the spatial update of
+// iteration t and the basis update of iteration t + 1 as one TMA tile kernel (ssb_tma.cu).  On when SSB_TMA has bit 2
+// (ssb_fused_iter_fusable checks it); SSB_FUSE_ITER=0 (read at every call so that tests can toggle it) switches it off.
+int fuse_iter_enabled(const ssb_config*) {
   const char* e = getenv("SSB_FUSE_ITER");
-  // default: on with the TMA tile kernels (ssb_tma.cu: second pass served by L2), off with the cp.async kernel of
-  // round 1 (its second pass misses L2).  bits 1, 2, 3 select variants of the latter, see launch_coop
-  return e ? (atoi(e) & 1) : ((ssb_tma_mask(c) & 4) ? 1 : 0);
+  return e ? (atoi(e) & 1) : 1;
 }
 
 // n_iter x update_once (ilrma.py:900-922) regrouped as

@@ -518,7 +518,7 @@ __global__ void __launch_bounds__(TileShape<N, KS, FS_>::NT, KS == 1 ? 2 : 1)
       } else {
         // IP1, n = 0 then n = 1 with the updated row 0, all in fp64 (kf_ip1_n2); every lane of every frame range computes
         // the same values.  W is written back UNNORMALISED (kf_normalize runs after the activation update, see
-        // ssb_coop.cu kf_cov_ip1_basis for why that order is exact); P below uses the stored complex64 filter.
+        // ssb_fused_spatial_source in ssb_fused.cu for why that order is exact); P below uses the stored complex64 filter.
         cf* wmat = Wrw + ((size_t)b * I + (rs ? rowc[1] : rowc[0])) * 4;
         if (!my_valid) {  // rows past the last bin see a zero slab: keep their algebra finite (nothing is stored)
 #pragma unroll

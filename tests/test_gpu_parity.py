@@ -833,24 +833,16 @@ def test_chunked_streams_ragged_batch_matches_single_plan():
     np.testing.assert_array_equal(Yc, Y1)
 
 
-@pytest.mark.parametrize("I,J,K,n_iter,normalization,mode", [
-    (37, 48, 5, 5, True, "1"), (257, 512, 16, 4, True, "1"),
-    (70, 528, 16, 3, False, "1"),
-    (20, 16, 4, 2, True, "1"),
-    (33, 64, 24, 5, True, "1"),
-    (129, 160, 32, 6, False, "1"),
-    # mode 9: second pass backwards (odd and even numbers of 16-frame steps, a single step, K > 16)
-    (37, 48, 5, 5, True, "9"),
-    (257, 512, 16, 4, True, "9"),
-    (20, 16, 4, 2, True, "9"),
-    (33, 80, 24, 3, True, "9")])
-def test_fused_iteration_kernel_matches_unfused_and_oracle(I, J, K, n_iter, normalization, mode, monkeypatch):
-    """SSB_FUSE_ITER=1 (experimental, default off): inside ssb_run the covariance + IP1 of iteration t and the basis
-    update of iteration t + 1 run as one kernel (kf_cov_ip1_basis, N = 2), with the power normalisation of iteration t
-    applied after the activation update.  Same results as update_once x n_iter (up to fp32 rounding: the covariance
-    is accumulated in another order and the scaling is reordered) and as the fp64 oracle.  The first two shapes
-    passed on a B200 (gpurun_out/r1s3_gputests.log); the third measured 2.5e-5 between the two device paths on T
-    without normalisation, hence the 5e-5 bound; the opt-in shapes add one 16-frame step, n_iter = 2 and K > 16."""
+@pytest.mark.parametrize("I,J,K,n_iter,normalization", [
+    (37, 48, 5, 5, True), (257, 512, 16, 4, True), (70, 528, 16, 3, False), (20, 16, 4, 2, True), (33, 64, 24, 5, True),
+    (129, 160, 32, 6, False), (33, 80, 24, 3, True)])
+def test_fused_iteration_kernel_matches_unfused_and_oracle(I, J, K, n_iter, normalization, monkeypatch):
+    """Iterations fused across the update_once boundary (opt-in: SSB_TMA bit 2; SSB_FUSE_ITER=0 switches the fusion off
+    while keeping the TMA kernels): inside ssb_run the covariance + IP1 of iteration t and the basis update of iteration
+    t + 1 run as one TMA tile kernel (N = 2), with the power normalisation of iteration t applied after the activation
+    update.  Same results as update_once x n_iter (up to fp32 rounding: the covariance is accumulated in another order
+    and the scaling is reordered) and as the fp64 oracle; odd and even numbers of 16-frame steps, a single step, K > 16,
+    n_iter = 2, with and without normalisation."""
     from oracle import ilrma as oilrma
     from ssspy_b200.bss import GaussILRMA
     from ssspy_b200.utils.synth import make_batch, make_nmf_init
@@ -858,8 +850,9 @@ def test_fused_iteration_kernel_matches_unfused_and_oracle(I, J, K, n_iter, norm
     X = make_batch(B, N, I, J, config_id=23, mode="mix")
     T, V = make_nmf_init(N, I, J, K, seed=11)
     out = {}
+    monkeypatch.setenv("SSB_TMA", "7")
     for flag in ("0", "1"):
-        monkeypatch.setenv("SSB_FUSE_ITER", mode if flag == "1" else "0")
+        monkeypatch.setenv("SSB_FUSE_ITER", flag)
         m = GaussILRMA(n_basis=K, spatial_algorithm="IP", normalization=normalization, record_loss=False)
         out[flag] = (m(X, n_iter=n_iter, basis=T, activation=V), m.basis.copy(), m.activation.copy(),
                      m.demix_filter.copy())

@@ -190,7 +190,7 @@ def test_permutation_solver_oracle(N):
 
 @pytest.mark.parametrize("normalization", [True, False])
 def test_deferred_power_normalisation_commutes_with_the_source_model(normalization):
-    """The identity behind kf_cov_ip1_basis (SSB_FUSE_ITER): n x update_once (ilrma.py:900-922) equals
+    """The identity behind the fused covariance + IP1 + basis kernel (ssb_fused_spatial_source, SSB_TMA bit 2): n x update_once (ilrma.py:900-922) equals
     [T, V]_1, { [U, IP1]_t, [T, V]_(t+1) with the UNNORMALISED W_t and T_t, then T /= psi_t^2, W /= psi_t }, [U, IP1,
     normalise]_n -- the ratio of the basis update and the whole activation update are invariant under
     (P, T) -> (P, T) / psi^2.  Checked in fp64 with the oracle."""
