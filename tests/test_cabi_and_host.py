@@ -252,3 +252,38 @@ def test_reference_id_wraps_like_numpy_indexing():
             wrap_reference_id(bad, 4)
         with pytest.raises(IndexError):
             np.zeros(4)[bad]
+
+
+def test_transform_and_linalg_operator_argument_checks_run_without_gpu():
+    """Host-side validation of ssspy_b200.transform.stft / istft (scipy.signal's messages where scipy has one) and of the
+    standalone linalg operators happens before anything touches the device; the frame count is a host computation
+    (ssb_stft_frames) that matches scipy's."""
+    from ssspy_b200 import _lib
+    from ssspy_b200.linalg import lqpqm2
+    from ssspy_b200.transform import istft, stft
+    x = np.zeros((2, 1000))
+    with pytest.raises(NotImplementedError, match="window"):
+        stft(x, window="hamming", nperseg=64)
+    with pytest.raises(ValueError, match="noverlap must be less than nperseg"):
+        stft(x, nperseg=64, noverlap=64)
+    with pytest.raises(ValueError, match="window must have length of nperseg"):
+        stft(x, window=np.ones(32), nperseg=64)
+    for kw in (dict(nfft=128), dict(boundary="even"), dict(padded=False), dict(return_onesided=False), dict(axis=0),
+               dict(scaling="psd"), dict(detrend="constant")):
+        with pytest.raises(NotImplementedError):
+            stft(x, nperseg=64, **kw)
+    with pytest.raises(NotImplementedError, match="complex"):
+        stft(x.astype(np.complex128), nperseg=64)
+    with pytest.raises(ValueError, match="at least 2d"):
+        istft(np.zeros(33, dtype=np.complex128))
+    with pytest.raises(ValueError, match="does not match"):
+        istft(np.zeros((33, 10), dtype=np.complex128), nperseg=128)
+    with pytest.raises(NotImplementedError):
+        lqpqm2(np.zeros((1, 2, 2)), np.zeros((1, 2)), np.zeros(1), singular_fn=lambda v: v < 1e-3)
+    # frames as scipy.signal.stft counts them: zero extension by nperseg // 2 on both sides, padded to whole hops
+    import scipy.signal as ss
+    for n_samples, nperseg, hop in ((1000, 64, 16), (4097, 256, 128), (700, 512, 128), (5000, 1024, 256), (513, 512, 512)):
+        n = ctypes.c_int(0)
+        _lib.call("ssb_stft_frames", n_samples, nperseg, hop, ctypes.byref(n))
+        want = ss.stft(np.zeros(n_samples), nperseg=nperseg, noverlap=nperseg - hop)[2].shape[-1]
+        assert n.value == want, (n_samples, nperseg, hop, n.value, want)

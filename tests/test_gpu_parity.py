@@ -521,6 +521,28 @@ def test_tensor_core_covariance_n4_opt_in(monkeypatch, I, J, K, spatial):
         assert_loss_close(np.asarray(m.loss)[:, b], st["loss"])
 
 
+@pytest.mark.parametrize("scale", [1e-4, 1e-2, 1e2])
+@pytest.mark.parametrize("spatial,N", [("IP", 2), ("IP2", 4), ("ISS", 3)])
+def test_input_scale_does_not_change_parity(scale, spatial, N):
+    """Device state is fp32 where the reference is fp64: STFTs of audio in [-1, 1] span 1e-4 .. 1e2, so the same mixture
+    is run at three input scales (the NMF factors P / R^2 and 1 / R then move by scale^-2) and held to the same bounds
+    against the oracle at that scale; fused and modular kernels."""
+    from oracle import ilrma as oilrma
+    from ssspy_b200.bss import GaussILRMA
+    from ssspy_b200.utils.synth import make_batch, make_nmf_init
+    B, I, J, K, n_iter = 2, 40, 64, 6, 6
+    X = make_batch(B, N, I, J, config_id=31, mode="mix") * scale
+    T, V = make_nmf_init(N, I, J, K, seed=5)
+    for fast in (True, False):
+        m = GaussILRMA(n_basis=K, spatial_algorithm=spatial)
+        m.fast_path = fast
+        Y = m(X, n_iter=n_iter, basis=T, activation=V)
+        for b in range(B):
+            st = oilrma.run(X[b], T, V, n_iter, spatial_algorithm=spatial)
+            assert relerr(Y[b], st["Y"]) < tol_seeded(spatial), (fast, b)
+            assert_loss_close(np.asarray(m.loss)[:, b], st["loss"])
+
+
 @pytest.mark.parametrize("model", ["laplace", "gauss"])
 @pytest.mark.parametrize("N,I,J,spatial", [(2, 37, 64, "IP"), (3, 21, 48, "IP2"), (4, 33, 80, "IP"), (5, 9, 96, "IP"),
                                            (8, 12, 160, "IP2"), (4, 19, 64, "ISS")])
@@ -594,6 +616,41 @@ def test_fast_gauss_mnmf_batched_vs_oracle_and_rng(alg, J, K):
         b2.normalize()
     assert relerr(b2.basis, a.basis) < 1e-5 and relerr(b2.spatial, a.spatial) < 1e-5
     assert abs(b2.compute_loss() - a.loss[-1]) <= 1e-5 * abs(a.loss[-1])
+
+
+@pytest.mark.parametrize("alg", ["IP", "IP2"])
+@pytest.mark.parametrize("I,J,K", [(14, 16, 3), (37, 48, 16), (70, 80, 9), (33, 272, 12)])
+def test_fast_gauss_mnmf_four_sources_fused_source_model(alg, I, J, K):
+    """N = 4, K <= 16, J % 16 == 0: the source model runs in kf_mnmf_update (Lambda by GEMM1, 4 x 4 mixing by D per point,
+    GEMM2; Z2 = |Q x|^2 the only streamed array) -- ragged bin tiles and chunks, K < 16, a single 16-frame step, an odd
+    number of 32-index chunks -- against the fp64 oracle; and inside ssb_run (run_iterations) the spatial sweep hands Z2
+    to the next iteration, which must give the same state as update_once called n times."""
+    from oracle import mnmf as omnmf
+    from ssspy_b200.bss import FastGaussMNMF
+    from ssspy_b200.utils.synth import make_batch
+    B, N, n_iter = 2, 4, 4
+    X = make_batch(B, N, I, J, config_id=6, mode="mix")
+    m = FastGaussMNMF(n_basis=K, diagonalizer_algorithm=alg, rng=np.random.default_rng(78))
+    Y = m(X, n_iter=n_iter)
+    rng = np.random.default_rng(78)
+    for b in range(B):
+        T = rng.random((N, I, K))
+        V = rng.random((N, K, J))
+        D = rng.random((I, N, N))
+        Q = np.tile(np.eye(N, dtype=np.complex128), (I, 1, 1))
+        st = omnmf.run(X[b], T, V, Q, D, n_iter, algorithm=alg)
+        assert relerr(Y[b], st["Y"]) < tol_seeded(alg)
+        assert relerr(m.basis[b], st["T"]) < TOL_TV and relerr(m.activation[b], st["V"]) < TOL_TV
+        np.testing.assert_allclose(np.asarray(m.loss)[:, b], st["loss"], rtol=1e-5, atol=1e-4)
+    a = FastGaussMNMF(n_basis=K, diagonalizer_algorithm=alg, rng=np.random.default_rng(5), record_loss=False)
+    a(X, n_iter=0)
+    a.run_iterations(3)
+    c = FastGaussMNMF(n_basis=K, diagonalizer_algorithm=alg, rng=np.random.default_rng(5), record_loss=False)
+    c(X, n_iter=0)
+    for _ in range(3):
+        c.update_once()
+    for name in ("basis", "activation", "spatial", "diagonalizer"):
+        assert relerr(getattr(a, name), getattr(c, name)) < 2e-5, name
 
 
 def test_minimal_distortion_principle_matches_reference():
