@@ -134,10 +134,15 @@ extern "C" int ssb_stft(const double* x, const double* window, double window_sum
   SSB_REQUIRE(window_sum != 0.0, "stft: the window sums to zero");
   const size_t sm = (size_t)nperseg * sizeof(cd);
   if (set_smem(k_stft, sm)) return 1;
-  dim3 grid(n_frames, n_rows);
-  k_stft<<<grid, 256, sm, (cudaStream_t)stream>>>(x, window, (cd*)Z, n_samples, nperseg, logn, hop, n_frames,
-                                                  1.0 / fabs(window_sum));  // scaling="spectrum"
-  return ssb_check_launch("stft", (cudaStream_t)stream);
+  const int n_bins = nperseg / 2 + 1;
+  for (int r0 = 0; r0 < n_rows; r0 += 32768) {  // grid.y is limited to 65535
+    dim3 grid(n_frames, n_rows - r0 < 32768 ? n_rows - r0 : 32768);
+    k_stft<<<grid, 256, sm, (cudaStream_t)stream>>>(x + (size_t)r0 * n_samples, window,
+                                                    (cd*)Z + (size_t)r0 * n_bins * n_frames, n_samples, nperseg, logn,
+                                                    hop, n_frames, 1.0 / fabs(window_sum));  // scaling="spectrum"
+    if (ssb_check_launch("stft", (cudaStream_t)stream)) return 1;
+  }
+  return 0;
 }
 
 extern "C" int ssb_istft(const void* Z, const double* window, double window_sum, double* y, double* seg, int n_rows,
@@ -150,12 +155,18 @@ extern "C" int ssb_istft(const void* Z, const double* window, double window_sum,
   const size_t sm = (size_t)nperseg * sizeof(cd);
   if (set_smem(k_istft, sm)) return 1;
   cudaStream_t st = (cudaStream_t)stream;
-  dim3 grid(n_frames, n_rows);
-  k_istft<<<grid, 256, sm, st>>>((const cd*)Z, window, seg, nperseg, logn, n_frames);
-  if (ssb_check_launch("istft", st)) return 1;
+  const int n_bins = nperseg / 2 + 1;
   const long long n_out = (long long)nperseg + (long long)(n_frames - 1) * hop - 2 * (long long)(nperseg / 2);
-  if (n_out <= 0) return 0;
-  dim3 g2((unsigned)((n_out + 255) / 256), n_rows);
-  k_ola<<<g2, 256, 0, st>>>(seg, window, y, n_out, nperseg, hop, n_frames, window_sum);
-  return ssb_check_launch("istft_overlap_add", st);
+  for (int r0 = 0; r0 < n_rows; r0 += 32768) {  // grid.y is limited to 65535
+    const int nr = n_rows - r0 < 32768 ? n_rows - r0 : 32768;
+    dim3 grid(n_frames, nr);
+    double* segr = seg + (size_t)r0 * n_frames * nperseg;
+    k_istft<<<grid, 256, sm, st>>>((const cd*)Z + (size_t)r0 * n_bins * n_frames, window, segr, nperseg, logn, n_frames);
+    if (ssb_check_launch("istft", st)) return 1;
+    if (n_out <= 0) continue;
+    dim3 g2((unsigned)((n_out + 255) / 256), nr);
+    k_ola<<<g2, 256, 0, st>>>(segr, window, y + (size_t)r0 * n_out, n_out, nperseg, hop, n_frames, window_sum);
+    if (ssb_check_launch("istft_overlap_add", st)) return 1;
+  }
+  return 0;
 }
