@@ -1064,14 +1064,14 @@ __global__ void __launch_bounds__(MUW * 32)
   cp_async_commit();
   for (int s = 0; s < nsteps; ++s) {
     const int chunk = s >> 1, slot = chunk % MUS;
-    // group s + 1: the Z2 tiles of the next step and, on even steps, the next operand chunk (its slot was last read
-    // two chunks ago, i.e. before the barrier of step s - 2)
+    cp_async_wait<0>();  // the group committed one step ago: tiles of step s and, on even steps, operand chunk `chunk`
+    if ((s & 1) == 0) __syncthreads();  // the chunk was copied by all threads of the CTA
+    else __syncwarp();                  // the tiles by all lanes of the warp
+    // behind the barrier every lane has finished reading the tiles of step s - 1 (the stage refilled now) and every warp
+    // the operand chunk two chunks back (the slot refilled now): group s + 1 flies while step s is computed
     if (warp_active && s + 1 < nsteps) issue_tile(s + 1);
     if ((s & 1) == 0 && chunk + 1 < nchunk_in) issue_op(chunk + 1, (chunk + 1) % MUS);
     cp_async_commit();
-    cp_async_wait<1>();  // everything but the group just committed: tiles of step s, operand chunk `chunk`
-    if ((s & 1) == 0) __syncthreads();  // the chunk was copied by all threads of the CTA
-    else __syncwarp();                  // the tiles by all lanes of the warp
     if (!warp_active) continue;
     const uint32_t sb = slot * SLOT + (s & 1) * (16 * JKS * 2);
     uint32_t Ahi[NS][4], Alo[NS][4], Bhi[NS][4], Blo[NS][4];
